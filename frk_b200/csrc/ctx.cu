@@ -1,0 +1,222 @@
+// Context, error string, memory helpers and the int32 exclusive scan used by the CSR builders.
+#include "common.cuh"
+#include <cstdarg>
+
+static thread_local char g_err[1024] = "";
+
+void frk_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *frk_last_error(void) { return g_err; }
+extern "C" int frk_abi_version(void) { return FRKB200_ABI_VERSION; }
+
+extern "C" int frk_ctx_create(int device, void *stream, frk_ctx **out) {
+    FRK_REQUIRE(out != nullptr, "frk_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        frk_set_error("frk_ctx_create: no CUDA device available (%s); libfrkb200 has no CPU fallback",
+                      cudaGetErrorString(e));
+        return 1;
+    }
+    FRK_REQUIRE(device >= 0 && device < ndev, "frk_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
+    FRK_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FRK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    FRK_REQUIRE(prop.major >= 10, "frk_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+    frk_ctx *c = new frk_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    c->sm_count = prop.multiProcessorCount;
+    FRK_CHECK_CUDA(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
+    FRK_CHECK_CUDA(cudaMalloc((void **)&c->d_small, 4096 * sizeof(double)));
+    *out = c;
+    return 0;
+}
+
+extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->d_small) cudaFree(ctx->d_small);
+    delete ctx;
+    return 0;
+}
+
+extern "C" int frk_sync(frk_ctx *ctx) {
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int frk_malloc(frk_ctx *ctx, size_t bytes, void **d_out) {
+    FRK_CHECK_CUDA(cudaSetDevice(ctx->device));
+    FRK_CHECK_CUDA(cudaMalloc(d_out, bytes ? bytes : 8));
+    return 0;
+}
+
+extern "C" int frk_free(frk_ctx *ctx, void *d_ptr) {
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    FRK_CHECK_CUDA(cudaFree(d_ptr));
+    return 0;
+}
+
+extern "C" int frk_h2d(frk_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    FRK_CHECK_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int frk_d2h(frk_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    FRK_CHECK_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int frk_memset0(frk_ctx *ctx, void *d_dst, size_t bytes) {
+    FRK_CHECK_CUDA(cudaMemsetAsync(d_dst, 0, bytes, ctx->stream));
+    return 0;
+}
+
+extern "C" int64_t frk_launch_count(frk_ctx *ctx) { return ctx->launches; }
+
+int frk_scratch(frk_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch_bytes) {
+        FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch) FRK_CHECK_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        FRK_CHECK_CUDA(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// exclusive scan: three passes (block sums -> scan of block sums -> rescan + offset).
+// 1024 threads x 4 items per block.  Block sums are int64 so that an overflowing total
+// (nnz >= 2^31, which R's dgCMatrix cannot hold either) is detected, not wrapped.
+// ---------------------------------------------------------------------------------
+constexpr int SCAN_T = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_T * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *smem_warp /*32*/, int &block_total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) smem_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = smem_warp[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        smem_warp[lane] = wi - w;            // exclusive warp offsets
+        if (lane == 31) smem_warp[32] = wi;  // block total
+    }
+    __syncthreads();
+    block_total = smem_warp[32];
+    int res = incl - v + smem_warp[wid];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_block_sums(const int *__restrict__ in, int64_t n, int64_t *__restrict__ bsum) {
+    __shared__ int sw[33];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) s += in[base + k];
+    int tot;
+    block_exclusive_scan(s, sw, tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) scan_of_block_sums(int64_t *bsum, int64_t nb, int64_t *total) {
+    // single block; sequential over chunks of 1024
+    __shared__ int64_t sh[1024];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < nb; c0 += 1024) {
+        int64_t i = c0 + threadIdx.x;
+        int64_t v = i < nb ? bsum[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        int64_t incl = sh[threadIdx.x];
+        if (i < nb) bsum[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_apply(const int *__restrict__ in, int64_t n, const int64_t *__restrict__ boff,
+                                                     const int64_t *__restrict__ total, int *__restrict__ out) {
+    __shared__ int sw[33];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int tot;
+    int ex = block_exclusive_scan(s, sw, tot);
+    int64_t off = boff[blockIdx.x] + ex;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = (int)off;
+        off += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = (int)(*total);
+}
+
+int frk_exclusive_scan_i32(frk_ctx *ctx, const int *d_in, int64_t n, int *d_out, int64_t *h_total) {
+    int64_t nb = cdiv(n > 0 ? n : 1, SCAN_TILE);
+    // scratch use is local to this call: block sums + total live in d_small if they fit, else scratch tail
+    int64_t *bsum = nullptr;
+    void *tmp = nullptr;
+    if ((nb + 1) * sizeof(int64_t) <= 4096 * sizeof(double)) {
+        bsum = (int64_t *)ctx->d_small;
+    } else {
+        FRK_CHECK_CUDA(cudaMallocAsync(&tmp, (nb + 1) * sizeof(int64_t), ctx->stream));
+        bsum = (int64_t *)tmp;
+    }
+    int64_t *total = bsum + nb;
+    FRK_LAUNCH(ctx, scan_block_sums, (unsigned)nb, SCAN_T, 0, d_in, n, bsum);
+    FRK_LAUNCH(ctx, scan_of_block_sums, 1, 1024, 0, bsum, nb, total);
+    FRK_LAUNCH(ctx, scan_apply, (unsigned)nb, SCAN_T, 0, d_in, n, bsum, total, d_out);
+    int64_t tot = 0;
+    FRK_CHECK_CUDA(cudaMemcpyAsync(&tot, total, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (tmp) FRK_CHECK_CUDA(cudaFreeAsync(tmp, ctx->stream));
+    FRK_REQUIRE(tot < (int64_t)2147483647, "scan total %lld exceeds the int32 CSR limit (2^31-1); shard the rows",
+                (long long)tot);
+    if (h_total) *h_total = tot;
+    return 0;
+}

@@ -1,0 +1,245 @@
+"""Manifolds, BAU containers and the point->BAU mapping -- the host-side mirror of the reference's
+R/geometryfns.R interface for the hot path (same names, argument meaning and error behaviour).
+
+Only r-sized or O(grid-axis) work happens here in NumPy (as it does in R in the reference); every
+N- or m-sized computation is a libfrkb200 kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+
+from ._lib import FRKError, call, c_i64, vp
+from .runtime import Device, get_device
+
+FRK_REAL_LINE, FRK_PLANE, FRK_SPHERE = 1, 2, 3
+
+
+@dataclass(frozen=True)
+class Manifold:
+    """real_line() / plane() / sphere(radius)  (R/geometryfns.R:19-189).
+
+    Only the built-in measures exist on the device; a custom ``measure@dist`` has no CUDA
+    kernel and is refused (north_star: no CPU fallback)."""
+    kind: str
+    radius: float = 6371.0
+
+    @property
+    def dim(self) -> int:
+        return 1 if self.kind == "real_line" else 2
+
+    @property
+    def code(self) -> int:
+        return {"real_line": FRK_REAL_LINE, "plane": FRK_PLANE, "sphere": FRK_SPHERE}[self.kind]
+
+
+def real_line() -> Manifold:
+    return Manifold("real_line")
+
+
+def plane() -> Manifold:
+    return Manifold("plane")
+
+
+def sphere(radius: float = 6371.0) -> Manifold:
+    """sphere(radius=6371), R/geometryfns.R:97-103."""
+    if not radius > 0:
+        raise ValueError("radius needs to be positive")
+    return Manifold("sphere", float(radius))
+
+
+def host_distance(m: Manifold, x1: np.ndarray, x2: np.ndarray) -> np.ndarray:
+    """distance(manifold, x1, x2) for r-sized inputs (basis placement, BuildD); the reference keeps
+    these on the host as well (R/basisfns.R:485-490,1131-1153).  Same operation order as
+    distR / dist_sphere (R/geometryfns.R:202-219,1717-1740)."""
+    x1 = np.asarray(x1, dtype=np.float64)
+    x2 = np.asarray(x2, dtype=np.float64)
+    if m.kind == "sphere":
+        def normals(x):
+            xr = (x * np.pi) / 180.0
+            cl = np.cos(xr[:, 1])
+            return cl * np.cos(xr[:, 0]), cl * np.sin(xr[:, 0]), np.sin(xr[:, 1])
+        a1, a2, a3 = normals(x1)
+        b1, b2, b3 = normals(x2)
+        dl = (a1[:, None] * b1[None, :] + a2[:, None] * b2[None, :]) + a3[:, None] * b3[None, :]
+        dl = np.where(np.abs(dl) > 1.0, np.sign(dl), dl)
+        return m.radius * np.arccos(dl)
+    acc = None
+    for k in range(x1.shape[1]):
+        df = x1[:, k][:, None] - x2[:, k][None, :]
+        acc = df * df if acc is None else acc + df * df
+    return np.sqrt(acc)
+
+
+# ---------------------------------------------------------------------------------------
+# data and BAU containers
+# ---------------------------------------------------------------------------------------
+
+@dataclass
+class SpatialPointsDataFrame:
+    """coords (n x d) + named numeric columns -- mirror of sp's class as FRK uses it."""
+    coords: np.ndarray
+    data: Dict[str, np.ndarray]
+
+    def __post_init__(self):
+        self.coords = np.asarray(self.coords, dtype=np.float64)
+        if self.coords.ndim == 1:
+            self.coords = self.coords[:, None]
+        n = self.coords.shape[0]
+        for k, v in self.data.items():
+            v = np.asarray(v, dtype=np.float64)
+            if v.shape[0] != n:
+                raise ValueError(f"column {k!r} has {v.shape[0]} rows, expected {n}")
+            self.data[k] = v
+
+    def __len__(self):
+        return self.coords.shape[0]
+
+
+@dataclass
+class GridBAUs:
+    """SpatialPixelsDataFrame of grid BAUs on the plane (auto_BAU, R/geometryfns.R:553-697).
+
+    BAU row i has centroid (xgrid[i % nx], ygrid[i // nx]) -- expand.grid order.  ``fields`` holds
+    BAU-level columns; ``fs`` (fine-scale variance field) must be present before SRE()."""
+    xgrid: np.ndarray
+    ygrid: np.ndarray
+    cellsize: np.ndarray
+    fields: Dict[str, np.ndarray] = field(default_factory=dict)
+
+    @property
+    def nx(self):
+        return len(self.xgrid)
+
+    @property
+    def ny(self):
+        return len(self.ygrid)
+
+    def __len__(self):
+        return self.nx * self.ny
+
+    @property
+    def offset(self):
+        return np.array([self.xgrid[0], self.ygrid[0]], dtype=np.float64)
+
+    @property
+    def dims(self):
+        return np.array([self.nx, self.ny], dtype=np.int32)
+
+    def centroids(self, lo: int = 0, hi: Optional[int] = None) -> np.ndarray:
+        hi = len(self) if hi is None else hi
+        idx = np.arange(lo, hi)
+        return np.column_stack([self.xgrid[idx % self.nx], self.ygrid[idx // self.nx]])
+
+    def cell2bau(self) -> np.ndarray:
+        """sp full-grid cell (rows counted from the top) -> BAU row."""
+        cell = np.arange(len(self), dtype=np.int64)
+        return ((self.ny - 1 - cell // self.nx) * self.nx + cell % self.nx).astype(np.int32)
+
+    def __setitem__(self, k, v):
+        v = np.broadcast_to(np.asarray(v, dtype=np.float64), (len(self),)).copy()
+        self.fields[k] = v
+
+    def __getitem__(self, k):
+        return self.fields[k]
+
+
+@dataclass
+class PointBAUs:
+    """BAUs given by their centroids only (e.g. ISEA3H hexagons on the sphere).  The point-in-
+    polygon lookup for such BAUs is on the host in the reference (sp::over) and is not part of the
+    device path yet (SURVEY.md s8 'next' #2): data must carry a precomputed ``bau`` column."""
+    coords: np.ndarray
+    fields: Dict[str, np.ndarray] = field(default_factory=dict)
+
+    def __len__(self):
+        return self.coords.shape[0]
+
+    def centroids(self, lo: int = 0, hi: Optional[int] = None) -> np.ndarray:
+        return np.asarray(self.coords[lo:hi], dtype=np.float64)
+
+    def __setitem__(self, k, v):
+        self.fields[k] = np.broadcast_to(np.asarray(v, dtype=np.float64), (len(self),)).copy()
+
+    def __getitem__(self, k):
+        return self.fields[k]
+
+
+def _seq_by(a: float, b: float, by: float) -> np.ndarray:
+    n = int(math.floor((b - a) / by + 1e-10))        # seq.default(from, to, by)
+    return a + np.arange(n + 1, dtype=np.float64) * by
+
+
+def auto_BAUs(manifold: Manifold, cellsize=None, data: Optional[SpatialPointsDataFrame] = None,
+              xlims=None, ylims=None, type: str = "grid", nonconvex_hull: bool = False) -> GridBAUs:
+    """auto_BAUs(manifold = plane(), type = "grid", ...), R/geometryfns.R:340,553-697.
+
+    The grid is the reference's (20 % buffer unless limits are given, seq(..., by = cellsize),
+    expand.grid order).  Hull pruning of the grid (fmesher / sp::over on a polygon, :665-682) is
+    BAU construction, out of the hot-path scope: the full rectangle is returned."""
+    if manifold.kind != "plane" or type != "grid":
+        raise FRKError("auto_BAUs on the device path builds grid BAUs on the plane only; "
+                       "pass PointBAUs for other BAU types")
+    if nonconvex_hull:
+        raise FRKError("nonconvex_hull=TRUE needs fmesher (host geometry, out of scope); use nonconvex_hull=False")
+    if data is None and (xlims is None or ylims is None):
+        raise ValueError("Data must be supplied when generating BAUs on a plane")
+    if data is not None:
+        coords = data.coords
+        xr = (coords[:, 0].min(), coords[:, 0].max()) if xlims is None else tuple(xlims)
+        yr = (coords[:, 1].min(), coords[:, 1].max()) if ylims is None else tuple(ylims)
+    else:
+        xr, yr = tuple(xlims), tuple(ylims)
+    if cellsize is None:
+        cellsize = max(xr[1] - xr[0], yr[1] - yr[0]) / 100.0     # .choose_cellsize default, :1963-1979
+    cellsize = np.broadcast_to(np.asarray(cellsize, dtype=np.float64), (2,)).copy()
+    dx, dy = xr[1] - xr[0], yr[1] - yr[0]
+    bx = 0.2 if xlims is None else 0.0
+    by = 0.2 if ylims is None else 0.0
+    xg = _seq_by(xr[0] - dx * bx, xr[1] + dx * bx, cellsize[0])
+    yg = _seq_by(yr[0] - dy * by, yr[1] + dy * by, cellsize[1])
+    b = GridBAUs(xg, yg, cellsize)
+    return b
+
+
+def map_data_to_BAUs(data: SpatialPointsDataFrame, BAUs, columns, dev: Optional[Device] = None,
+                     row_range=None):
+    """map_data_to_BAUs(SpatialPoints, BAUs, average_in_BAU = TRUE), R/geometryfns.R:1222-1320.
+
+    Device pipeline: integer point-in-cell lookup (sp::over on SpatialPixels) -> drop NAs ->
+    group by BAU -> mean of every requested column.  Returns device tensors
+    (obs_bau[m] ascending BAU rows, means (ncols x m, i.e. m x ncols column-major), counts[m]) and
+    the per-point BAU index.  ``row_range=(lo,hi)`` keeps only points whose BAU is owned by this
+    rank (multi-GPU row partition) and returns BAU rows relative to ``lo``."""
+    dev = dev or get_device()
+    n = len(data)
+    ncols = len(columns)
+    nbau = len(BAUs)
+    lo, hi = (0, nbau) if row_range is None else row_range
+    if isinstance(BAUs, GridBAUs):
+        d_xy = dev.upload(data.coords[:, :2])
+        d_bau = dev.empty(max(n, 1), "i4")
+        off, cs, dm = BAUs.offset, np.asarray(BAUs.cellsize, dtype=np.float64), BAUs.dims
+        # BAUs are in expand.grid order, so sp's top-down cell index maps to the BAU row by formula
+        call("frk_grid_lookup_range", dev.ctx, n, dev.ptr(d_xy), n, vp(off.ctypes.data), vp(cs.ctypes.data),
+             vp(dm.ctypes.data), vp(None), 1, int(lo), int(hi), dev.ptr(d_bau))
+    else:
+        if "bau" not in data.data:
+            raise FRKError("point-in-polygon lookup for non-grid BAUs is not on the device path; "
+                           "supply a precomputed 'bau' column (0-based BAU row, -1 = NA)")
+        b = np.asarray(data.data["bau"]).astype(np.int64)
+        b = np.where((b >= lo) & (b < hi), b - lo, -1)     # host: the lookup itself was done on the host
+        d_bau = dev.upload(b.astype(np.int32))
+    vals = np.column_stack([data.data[c] for c in columns]) if ncols else np.zeros((n, 0))
+    d_vals = dev.upload(vals)
+    d_obs = dev.empty(max(n, 1), "i4")
+    d_means = dev.empty(max(n * ncols, 1), "f8")
+    d_cnt = dev.empty(max(n, 1), "i4")
+    m = c_i64(0)
+    call("frk_bin_mean", dev.ctx, n, dev.ptr(d_bau), hi - lo, ncols, dev.ptr(d_vals), dev.ptr(d_obs),
+         dev.ptr(d_means), dev.ptr(d_cnt), C.byref(m))
+    return dict(m=int(m.value), obs_bau=d_obs, means=d_means, ld=n, counts=d_cnt, bau=d_bau)

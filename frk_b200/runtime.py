@@ -1,0 +1,118 @@
+"""Device runtime: one libfrkb200 context per process/GPU.  PyTorch supplies device memory,
+the stream and ``torch.distributed`` (NCCL) -- plumbing only; every computation on the hot
+path is a libfrkb200 kernel reached through the C ABI with raw device pointers."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from ._lib import FRKError, call, lib, vp
+
+_DEVICE = None
+
+
+class Device:
+    def __init__(self, index: Optional[int] = None):
+        import torch
+        if not torch.cuda.is_available():
+            raise FRKError("frk_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if index is None:
+            index = int(os.environ.get("LOCAL_RANK", torch.cuda.current_device()))
+        self.torch = torch
+        self.index = index
+        torch.cuda.set_device(index)
+        self.tdev = torch.device("cuda", index)
+        self.stream = torch.cuda.current_stream(index)
+        ctx = vp()
+        call("frk_ctx_create", index, vp(self.stream.cuda_stream), C.byref(ctx))
+        self.ctx = ctx
+
+    # ---- memory (torch-owned) ------------------------------------------------------
+    def empty(self, n, dtype="f8"):
+        t = self.torch
+        dt = {"f8": t.float64, "i4": t.int32, "i8": t.int64}[dtype]
+        return t.empty(int(n), dtype=dt, device=self.tdev)
+
+    def zeros(self, n, dtype="f8"):
+        x = self.empty(n, dtype)
+        call("frk_memset0", self.ctx, self.ptr(x), x.numel() * x.element_size())
+        return x
+
+    def upload(self, a: np.ndarray, dtype=None):
+        """Host array -> device (column-major flattening for 2-D inputs, as R stores matrices)."""
+        a = np.asarray(a)
+        if dtype is not None:
+            a = a.astype(dtype, copy=False)
+        flat = np.ascontiguousarray(a.T).ravel() if a.ndim == 2 else np.ascontiguousarray(a).ravel()
+        code = {"float64": "f8", "int32": "i4", "int64": "i8"}[str(flat.dtype)]
+        out = self.empty(flat.size, code)
+        if flat.size:
+            call("frk_h2d", self.ctx, self.ptr(out), vp(flat.ctypes.data), flat.nbytes)
+            call("frk_sync", self.ctx)      # flat may be a temporary
+        return out
+
+    def download(self, t, n: Optional[int] = None) -> np.ndarray:
+        n = t.numel() if n is None else int(n)
+        npdt = {8: {True: np.float64, False: np.int64}, 4: {False: np.int32}}[t.element_size()][t.is_floating_point()]
+        out = np.empty(n, dtype=npdt)
+        if n:
+            call("frk_d2h", self.ctx, vp(out.ctypes.data), self.ptr(t), out.nbytes)
+        return out
+
+    @staticmethod
+    def ptr(t, offset_elems: int = 0):
+        if t is None:
+            return vp(None)
+        return vp(t.data_ptr() + offset_elems * t.element_size())
+
+    def sync(self):
+        call("frk_sync", self.ctx)
+
+    def launches(self) -> int:
+        return int(lib.frk_launch_count(self.ctx))
+
+    # ---- distributed plumbing --------------------------------------------------------
+    @property
+    def world(self) -> int:
+        d = self.torch.distributed
+        return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+
+    @property
+    def rank(self) -> int:
+        d = self.torch.distributed
+        return d.get_rank() if d.is_available() and d.is_initialized() else 0
+
+    def allreduce_(self, t):
+        """In-place fp64 sum over ranks (NCCL over NVLink); no-op for a single rank."""
+        if self.world > 1:
+            self.torch.distributed.all_reduce(t)
+        return t
+
+    def allreduce_host(self, a: np.ndarray) -> np.ndarray:
+        """Sum a small host vector over ranks (M-step moments, O(p^2) doubles)."""
+        if self.world == 1:
+            return a
+        t = self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.tdev)
+        self.torch.distributed.all_reduce(t)
+        return t.cpu().numpy()
+
+
+def get_device(index: Optional[int] = None) -> Device:
+    """Process-wide device runtime (created on first use)."""
+    global _DEVICE
+    if _DEVICE is None:
+        _DEVICE = Device(index)
+    return _DEVICE
+
+
+def partition_rows(n: int, world: int, rank: int):
+    """Contiguous block partition of n rows over `world` ranks: [lo, hi) for `rank`
+    (BAUs block-partitioned by row range; each observation lives on the rank
+    that owns its BAU)."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi

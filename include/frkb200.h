@@ -1,0 +1,220 @@
+/*
+ * frkb200.h -- C ABI of libfrkb200.so: the B200 (sm_100a) implementation of the
+ * Gaussian fixed-rank-kriging hot path of the R package FRK (v2.3.1).
+ *
+ * This is the drop-in boundary.  The reference has no native code on this path
+ * (it is R on top of Matrix/sp/stats), so every entry point below replaces an R
+ * function; the file:line of the reference interface each one stands in for is
+ * cited with it (paths relative to the reference root).  The `.Call` shim a
+ * maintainer adds on the R side is shown in INTEGRATION.md (r/src/frkb200_R.c).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types.
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from frk_last_error() (thread-local).  No exception crosses the ABI.
+ *   - matrices are column-major fp64 (R layout); indices are 0-based int32.
+ *   - pointers named d_* are DEVICE pointers (cudaMalloc'd by the caller, by
+ *     frk_malloc(), or torch-owned memory); h_* are HOST pointers.
+ *   - all launches go to the stream given at frk_ctx_create(); calls are
+ *     asynchronous unless they return a value to the host (documented per call).
+ *   - there is no CPU fallback anywhere: without a CUDA device frk_ctx_create fails.
+ */
+#ifndef FRKB200_H
+#define FRKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRKB200_ABI_VERSION 1
+
+typedef struct frk_ctx frk_ctx;       /* device + stream + scratch workspace        */
+typedef struct frk_basis frk_basis;   /* device-resident basis + cell lists          */
+
+/* manifold(): R/geometryfns.R:19-189 */
+enum { FRK_REAL_LINE = 1, FRK_PLANE = 2, FRK_SPHERE = 3 };
+/* local_basis(type=): R/basisfns.R:99-146 */
+enum { FRK_BISQUARE = 0, FRK_GAUSSIAN = 1, FRK_EXP = 2, FRK_MATERN32 = 3 };
+
+/* ---- context / memory ------------------------------------------------- */
+int         frk_abi_version(void);
+const char *frk_last_error(void);
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL */
+int frk_ctx_create(int device, void *stream, frk_ctx **out);
+int frk_ctx_destroy(frk_ctx *ctx);
+int frk_sync(frk_ctx *ctx);
+int frk_malloc(frk_ctx *ctx, size_t bytes, void **d_out);
+int frk_free(frk_ctx *ctx, void *d_ptr);
+int frk_h2d(frk_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* async on ctx stream */
+int frk_d2h(frk_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);   /* synchronises        */
+int frk_memset0(frk_ctx *ctx, void *d_dst, size_t bytes);
+/* number of kernels this library has launched on ctx since creation (bench.py: gpu_launches) */
+int64_t frk_launch_count(frk_ctx *ctx);
+
+/* ---- basis: local_basis()/Basis object, R/basisfns.R:99-146, R/AllClass.R:78 -----
+ * h_loc: r x d column-major centroids; h_scale: r; h_res: r (1-based resolution).
+ * radius: sphere radius (R/geometryfns.R:97), ignored otherwise.
+ * Builds the per-resolution cell lists used by frk_eval_basis_*.                    */
+int frk_basis_create(frk_ctx *ctx, int manifold, double radius, int type, int d, int r,
+                     const double *h_loc, const double *h_scale, const int *h_res,
+                     frk_basis **out);
+int frk_basis_destroy(frk_basis *b);
+int frk_basis_n(const frk_basis *b);     /* number of basis functions r     */
+int frk_basis_dim(const frk_basis *b);   /* manifold dimension d (1 or 2)    */
+
+/* ---- eval_basis(Basis, matrix): R/basisfns.R:709-748 + .point_eval_fn :1157-1161 +
+ *      closures :1213-1250 + distR R/geometryfns.R:202-219 / dist_sphere :1717-1740.
+ * d_s: n x d column-major coordinates (leading dimension ld_s >= n).
+ * Two calls: _count fills d_rowptr[n+1] (exclusive scan of the per-row non-zero count,
+ * pattern = {phi != 0}) and returns nnz to the host; _fill writes ascending column indices
+ * and values.  normalise != 0 fuses SRE()'s row normalisation (R/SRE.R:416-421).          */
+int frk_eval_basis_count(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *d_s, int64_t ld_s,
+                         int *d_rowptr, int64_t *h_nnz);
+int frk_eval_basis_fill(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *d_s, int64_t ld_s,
+                        const int *d_rowptr, int *d_col, double *d_val, int normalise);
+
+/* eval_basis(TensorP_Basis, matrix): R/basisfns.R:812-824 + quickbind R/linalgfns.R:80-118.
+ * S[i, j1 + r1*j2] = S1[i,j1]*S2[i,j2] from two CSR operands with the same rows.          */
+int frk_csr_tensor_count(frk_ctx *ctx, int64_t n, const int *d_rowptr1, const int *d_rowptr2,
+                         int *d_rowptr, int64_t *h_nnz);
+int frk_csr_tensor_fill(frk_ctx *ctx, int64_t n, int r1,
+                        const int *d_rowptr1, const int *d_col1, const double *d_val1,
+                        const int *d_rowptr2, const int *d_col2, const double *d_val2,
+                        const int *d_rowptr, int *d_col, double *d_val);
+/* SRE() row normalisation on an existing CSR: R/SRE.R:416-421 */
+int frk_csr_row_normalise(frk_ctx *ctx, int64_t n, const int *d_rowptr, double *d_val);
+
+/* ---- map_data_to_BAUs(SpatialPoints, SpatialPixels): R/geometryfns.R:1222-1320 ------
+ * sp::over on a pixel grid = integer point-in-cell lookup (sp getGridIndex).
+ * d_xy: n x 2 column-major; h_offset = cellcentre.offset, h_cellsize, h_dims = cells.dim.
+ * d_cell2bau: map full-grid cell (row-wise from the TOP row) -> BAU row, or NULL for
+ * identity.  d_bau[n] receives the 0-based BAU row, -1 for NA (outside / not a BAU).      */
+int frk_grid_lookup(frk_ctx *ctx, int64_t n, const double *d_xy, int64_t ld_xy,
+                    const double *h_offset, const double *h_cellsize, const int *h_dims,
+                    const int *d_cell2bau, int *d_bau);
+/* Same lookup for a row-partitioned run: with d_cell2bau == NULL and expand_grid_order != 0 the BAU
+ * row is computed directly for BAUs stored in expand.grid order (x fastest, y ascending -- how
+ * auto_BAU lays them out, R/geometryfns.R:629-637); rows outside [bau_lo, bau_hi) become NA and
+ * the rest are returned relative to bau_lo (the rank's local BAU rows).                     */
+int frk_grid_lookup_range(frk_ctx *ctx, int64_t n, const double *d_xy, int64_t ld_xy,
+                          const double *h_offset, const double *h_cellsize, const int *h_dims,
+                          const int *d_cell2bau, int expand_grid_order, int bau_lo, int bau_hi,
+                          int *d_bau);
+/* group_by(BAU) %>% summarise_all(mean): R/geometryfns.R:1286-1302.  d_vals: n x ncols
+ * column-major (ld n).  Outputs (capacity n rows): d_obs_bau[m] ascending BAU rows,
+ * d_means m x ncols column-major with leading dimension n, d_counts[m].  Returns m.
+ * Deterministic: members of a BAU are summed in ascending original point order.           */
+int frk_bin_mean(frk_ctx *ctx, int64_t n, const int *d_bau, int64_t nbau, int ncols,
+                 const double *d_vals, int *d_obs_bau, double *d_means, int *d_counts,
+                 int64_t *h_m);
+
+/* ---- S = Cmat %*% S0 for point data (row gather): R/SRE.R:502, BuildC
+ *      R/geometryfns.R:1557-1568 -------------------------------------------------- */
+int frk_csr_gather_count(frk_ctx *ctx, int64_t m, const int *d_rows, const int *d_rowptr_src,
+                         int *d_rowptr_dst, int64_t *h_nnz);
+int frk_csr_gather_fill(frk_ctx *ctx, int64_t m, const int *d_rows,
+                        const int *d_rowptr_src, const int *d_col_src, const double *d_val_src,
+                        const int *d_rowptr_dst, int *d_col_dst, double *d_val_dst);
+
+/* ---- E-step / log-likelihood accumulators: R/SREfit.R:194 (crossprod(cholDinvT %*% S)),
+ *      :252 (Q_eta), :254 (t(S) %*% Dinv %*% (Z - X alpha)), :198,:211 (scalars).
+ * For the m local rows of S (CSR) with d_j = sigma2fs*vfs_j + ve_j, rho_j = z_j - x_j'alpha:
+ *   d_acc[0 .. r*r)        += upper triangle (row<=col, column-major) of sum_j s_j s_j'/d_j
+ *   d_acc[r*r .. r*r+r)    += sum_j s_j rho_j / d_j
+ *   d_acc[r*r+r]           += sum_j rho_j^2 / d_j
+ *   d_acc[r*r+r+1]         += sum_j log d_j
+ * d_acc is ONE contiguous buffer of r*r + r + 2 doubles so that a single fp64 all-reduce per
+ * EM iteration combines the ranks.  The caller zeroes it first.  X: m x p column-major
+ * (ld m); h_alpha: p.                                                                     */
+int frk_gram_rhs(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int *d_col,
+                 const double *d_val, const double *d_z, const double *d_X, int p,
+                 const double *h_alpha, const double *d_ve, const double *d_vfs, double sigma2fs,
+                 double *d_acc);
+
+/* ---- gather-based sparse quadratic form + SpMV: R/SREutils.R:286-300 (.batch_compute_var,
+ *      rowSums((S0 Cov) * S0)), R/SREfit.R:332-334 (Omega_diag1), S %*% mu_eta.
+ * q_i = s_i' M s_i (M symmetric r x r column-major, ld r), t_i = s_i' mu.  Either output
+ * may be NULL.                                                                            */
+int frk_quadform_spmv(frk_ctx *ctx, int64_t n, int r, const int *d_rowptr, const int *d_col,
+                      const double *d_val, const double *d_M, const double *d_mu,
+                      double *d_q, double *d_t);
+
+/* ---- M-step row sums: R/SREfit.R:335-356 (J), :391-405 (alpha), :408-417 (sigma2fs).
+ * With u_j = 1/d_j, w_j = vfs_j/d_j^2 (mode 0, heteroscedastic J at sigma2fs) or u=w=1
+ * (mode 1, homoscedastic closed form) writes to h_out (2p^2 + 2p + 2 doubles, synchronises):
+ *   [0,p^2) sum u x x'   [p^2,p^2+p) sum u x (z-t)   [..+1) sum vfs u
+ *   [..+1) sum w (Omega1 - 2 t z + z^2), Omega1 = q + t^2 (d_q = s_j' S_eta s_j)   [..+p) sum w x (t - z)   [..+p^2) sum w x x'      */
+int frk_mstep_sums(frk_ctx *ctx, int64_t m, int p, const double *d_X, const double *d_z,
+                   const double *d_t, const double *d_q, const double *d_ve,
+                   const double *d_vfs, double sigma2fs, int mode, double *h_out);
+
+/* ---- predict at BAUs: R/SREpredict.R:334-375 and the point-data closed form of :308-333.
+ * mode 0 (obs_fs=TRUE or sigma2fs==0): mu = xa + smu, var = q.
+ * mode 1 (obs_fs=FALSE, sigma2fs>0):   a = A/(A+Qf), Qf = 1/(sigma2fs*fs);
+ *        var = (1-a)^2 q + 1/(A+Qf);  mu = xa + smu + (ytil - A*smu)/(A+Qf).
+ * d_A / d_ytil may be NULL (treated as 0: unobserved BAUs).  sd = sqrt(var).               */
+int frk_predict_finalize(frk_ctx *ctx, int64_t n, int mode, double sigma2fs, const double *d_q,
+                         const double *d_smu, const double *d_xa, const double *d_A,
+                         const double *d_ytil, const double *d_fs, double *d_mu, double *d_var,
+                         double *d_sd);
+/* scatter per-observation values to their BAU: dst[idx[j]] += src[j] (C' Ve^-1 C, C' Ve^-1 rho) */
+int frk_scatter_add(frk_ctx *ctx, int64_t m, const int *d_idx, const double *d_src, double *d_dst);
+/* y = z - X alpha, optionally divided by d_div (may be NULL) */
+int frk_resid(frk_ctx *ctx, int64_t m, int p, const double *d_X, const double *h_alpha,
+              const double *d_z, const double *d_div, double *d_out);
+
+/* out = X alpha  (X %*% alpha at the BAUs, R/SREpredict.R:274,347) */
+int frk_xalpha(frk_ctx *ctx, int64_t n, int p, const double *d_X, const double *h_alpha, double *d_out);
+
+/* ---- dense fp64 (Matrix::chol / chol2inv / determinant / solve; R/linalgfns.R:21-36) ----
+ * All r x r column-major with leading dimension r.                                         */
+/* In-place lower Cholesky A = L L' (chol(), R/SREfit.R:177,195,253,273); the strict upper
+ * triangle is left untouched.  *h_logdet = 2*sum(log(diag L)) (logdet, R/linalgfns.R:32).
+ * Fails (status != 0) if A is not positive definite.                                       */
+int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet);
+/* chol2inv: given L from frk_potrf in d_L (left intact), writes the full symmetric inverse of
+ * A to d_Ainv.  d_work: r*r doubles of scratch (receives L^-T).                             */
+int frk_potri(frk_ctx *ctx, int r, const double *d_L, double *d_Ainv, double *d_work);
+/* y = A x for symmetric full-storage A */
+int frk_symv(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double *d_y);
+/* out = mirror(upper triangle of G) + B   (Q_eta = S'D^-1 S + K^-1, R/SREfit.R:252); B may be NULL */
+int frk_sym_from_upper_add(frk_ctx *ctx, int r, const double *d_Gupper, const double *d_B, double *d_out);
+/* out = A + x x'   (S_eta + tcrossprod(mu_eta), R/SREfit.R:332,689) */
+int frk_add_outer(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double *d_out);
+/* out = exp(-D / tau) * scale   (block-exponential K_i, R/SREfit.R:517,631) */
+int frk_exp_kernel(frk_ctx *ctx, int64_t n, const double *d_D, double tau, double scale, double *d_out);
+/* *h_out = sum(A * B) elementwise over n entries (sum(diag2(.,., symm=TRUE)), R/SREfit.R:478,524) */
+int frk_dot(frk_ctx *ctx, int64_t n, const double *d_A, const double *d_B, double *h_out);
+/* copy the ni x ni block A[idx, idx] (idx device int32) out of / into an r x r matrix
+ * (S_eta[idx,idx], Khat[idx,idx], bdiag + reverse_permute: R/SREfit.R:459-464,625-649)      */
+int frk_block_gather(frk_ctx *ctx, int r, const double *d_A, int ni, const int *d_idx, double *d_out);
+int frk_block_scatter(frk_ctx *ctx, int r, double *d_A, int ni, const int *d_idx, const double *d_in);
+/* out[i + ni*j] = x[idx[i]]*x[idx[j]] + A[idx[i], idx[j]]  (eta2 blocks, R/SREfit.R:459-464) */
+int frk_block_gather_outer(frk_ctx *ctx, int r, const double *d_A, const double *d_x, int ni,
+                           const int *d_idx, double *d_out);
+/* C(MxN, ldc) = beta*C + alpha * A(MxK, lda) * B(NxK, ldb)'  -- the fp64 tensor-core GEMM all
+ * blocked factorisations are built from (exported for tests and the fp64 peak probe).       */
+int frk_dgemm_nt(frk_ctx *ctx, int M, int N, int K, double alpha, const double *d_A, int lda,
+                 const double *d_B, int ldb, double beta, double *d_C, int ldc);
+
+/* ---- host-buffer entry points (what the R .Call shim binds; H2D/D2H inside) ------------ */
+/* eval_basis on host coordinates -> host CSR.  Call with h_col == NULL to get nnz only.     */
+int frk_eval_basis_host(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *h_s,
+                        int normalise, int *h_rowptr, int *h_col, double *h_val, int64_t *h_nnz);
+int frk_grid_lookup_host(frk_ctx *ctx, int64_t n, const double *h_xy, const double *h_offset,
+                         const double *h_cellsize, const int *h_dims, const int *h_cell2bau,
+                         int64_t ncell, int *h_bau);
+/* var = diag(S0 Cov S0'), smu = S0 mu for a host CSR (R/SREutils.R:245-305)                 */
+int frk_quadform_host(frk_ctx *ctx, int64_t n, int r, const int *h_rowptr, const int *h_col,
+                      const double *h_val, const double *h_M, const double *h_mu,
+                      double *h_q, double *h_t);
+/* chol2inv(chol(A)) + log-determinant for a host matrix (R/SREfit.R:178-179,253,273)        */
+int frk_chol2inv_host(frk_ctx *ctx, int r, const double *h_A, double *h_Ainv, double *h_logdet);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRKB200_H */
