@@ -45,6 +45,7 @@ SIGNATURES = {
     "frk_free": (c_int, [vp, vp]),
     "frk_h2d": (c_int, [vp, vp, vp, C.c_size_t]),
     "frk_d2h": (c_int, [vp, vp, vp, C.c_size_t]),
+    "frk_d2d": (c_int, [vp, vp, vp, C.c_size_t]),
     "frk_memset0": (c_int, [vp, vp, C.c_size_t]),
     "frk_launch_count": (c_i64, [vp]),
     "frk_basis_create": (c_int, [vp, c_int, c_dbl, c_int, c_int, c_int, vp, vp, vp, C.POINTER(vp)]),
@@ -59,19 +60,27 @@ SIGNATURES = {
     "frk_grid_lookup": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, vp]),
     "frk_grid_lookup_range": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, c_int, c_int, c_int, vp]),
     "frk_bin_mean": (c_int, [vp, c_i64, vp, c_i64, c_int, vp, vp, vp, vp, p_i64]),
+    "frk_grid_centroids": (c_int, [vp, c_i64, c_i64, c_int, vp, vp, vp]),
     "frk_csr_gather_count": (c_int, [vp, c_i64, vp, vp, vp, p_i64]),
     "frk_csr_gather_fill": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),
     "frk_gram_rhs": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, c_int, vp, vp, vp, c_dbl, vp]),
     "frk_quadform_spmv": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp]),
     "frk_mstep_sums": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, c_dbl, c_int, vp]),
+    "frk_vec_stats": (c_int, [vp, c_i64, vp, c_dbl, vp]),
+    "frk_square": (c_int, [vp, c_i64, vp, vp]),
+    "frk_recip": (c_int, [vp, c_i64, vp, vp]),
+    "frk_gather_rows": (c_int, [vp, c_i64, c_int, vp, vp, c_i64, vp, c_i64]),
     "frk_predict_finalize": (c_int, [vp, c_i64, c_int, c_dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_scatter_add": (c_int, [vp, c_i64, vp, vp, vp]),
     "frk_resid": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp]),
     "frk_xalpha": (c_int, [vp, c_i64, c_int, vp, vp, vp]),
     "frk_potrf": (c_int, [vp, c_int, vp, p_dbl]),
     "frk_potri": (c_int, [vp, c_int, vp, vp, vp]),
+    "frk_upper_tmulv": (c_int, [vp, c_int, vp, vp, vp]),
     "frk_symv": (c_int, [vp, c_int, vp, vp, vp]),
     "frk_sym_from_upper_add": (c_int, [vp, c_int, vp, vp, vp]),
+    "frk_scaled_identity": (c_int, [vp, c_int, c_dbl, vp]),
+    "frk_add_diag": (c_int, [vp, c_int, vp, vp]),
     "frk_add_outer": (c_int, [vp, c_int, vp, vp, vp]),
     "frk_exp_kernel": (c_int, [vp, c_i64, vp, c_dbl, c_dbl, vp]),
     "frk_dot": (c_int, [vp, c_i64, vp, vp, p_dbl]),

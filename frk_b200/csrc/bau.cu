@@ -164,3 +164,27 @@ extern "C" int frk_csr_gather_fill(frk_ctx *ctx, int64_t m, const int *d_rows, c
                d_rowptr_dst, d_col_dst, d_val_dst);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// BAU centroids of a pixel grid in expand.grid order (x fastest), rows [lo, hi):
+// coordinates(BAUs) as SRE() passes them to eval_basis (R/SRE.R:412, R/geometryfns.R:629-637).
+// out: (hi-lo) x 2 column-major.
+// ---------------------------------------------------------------------------------
+__global__ void grid_centroids_kernel(int64_t lo, int64_t n, int nx, const double *__restrict__ xg, const double *__restrict__ yg,
+                                      double *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = lo + i;
+        out[i] = __ldg(xg + (b % nx));
+        out[i + n] = __ldg(yg + (b / nx));
+    }
+}
+
+extern "C" int frk_grid_centroids(frk_ctx *ctx, int64_t lo, int64_t hi, int nx, const double *d_xgrid, const double *d_ygrid,
+                                  double *d_out) {
+    FRK_REQUIRE(ctx && d_xgrid && d_ygrid && d_out && nx > 0 && hi >= lo, "frk_grid_centroids: bad argument");
+    const int64_t n = hi - lo;
+    if (n == 0) return 0;
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, grid_centroids_kernel, grid, 256, 0, lo, n, nx, d_xgrid, d_ygrid, d_out);
+    return 0;
+}

@@ -78,6 +78,11 @@ extern "C" int frk_d2h(frk_ctx *ctx, void *h_dst, const void *d_src, size_t byte
     return 0;
 }
 
+extern "C" int frk_d2d(frk_ctx *ctx, void *d_dst, const void *d_src, size_t bytes) {
+    FRK_CHECK_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
 extern "C" int frk_memset0(frk_ctx *ctx, void *d_dst, size_t bytes) {
     FRK_CHECK_CUDA(cudaMemsetAsync(d_dst, 0, bytes, ctx->stream));
     return 0;

@@ -539,3 +539,48 @@ extern "C" int frk_block_scatter(frk_ctx *ctx, int r, double *d_A, int ni, const
     FRK_LAUNCH(ctx, block_scatter_kernel, ctx->sm_count * 8, 256, 0, r, d_A, ni, d_idx, d_in);
     return 0;
 }
+
+// x = Y' b for upper-triangular Y (= L^-T left in d_work by frk_potri): x = L^-1 b, i.e.
+// (rDinv %*% S) %*% solve(R) of .loglik.ind (R/SREfit.R:211).  One warp per column of Y.
+__global__ void __launch_bounds__(256) upper_tmulv_kernel(int r, const double *__restrict__ Y, const double *__restrict__ b,
+                                                          double *__restrict__ x) {
+    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (i >= r) return;
+    const double *y = Y + (size_t)i * r;
+    double s = 0.0;
+    for (int k = lane; k <= i; k += 32) s += y[k] * __ldg(b + k);
+    s = warp_sum(s);
+    if (lane == 0) x[i] = s;
+}
+
+extern "C" int frk_upper_tmulv(frk_ctx *ctx, int r, const double *d_Y, const double *d_b, double *d_x) {
+    FRK_REQUIRE(ctx && d_Y && d_b && d_x && r > 0, "frk_upper_tmulv: bad argument");
+    FRK_LAUNCH(ctx, upper_tmulv_kernel, (unsigned)cdiv((int64_t)r * 32, 256), 256, 0, r, d_Y, d_b, d_x);
+    return 0;
+}
+
+// A = value * I   (.EM_initialise: S_eta = Q_eta = I, Khat = var(Z) I, Khat_inv = I / var(Z); R/SRE.R:710-722)
+__global__ void scaled_identity_kernel(int r, double value, double *__restrict__ A) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)r * r; idx += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(idx % r), j = (int)(idx / r);
+        A[idx] = (i == j) ? value : 0.0;
+    }
+}
+
+extern "C" int frk_scaled_identity(frk_ctx *ctx, int r, double value, double *d_A) {
+    FRK_REQUIRE(ctx && d_A && r > 0, "frk_scaled_identity: bad argument");
+    FRK_LAUNCH(ctx, scaled_identity_kernel, ctx->sm_count * 8, 256, 0, r, value, d_A);
+    return 0;
+}
+
+// diag(A) += d   (ridge term of .regularise_K, R/SREfit.R:669-686)
+__global__ void add_diag_kernel(int r, const double *__restrict__ d, double *__restrict__ A) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r) A[i + (size_t)i * r] += d[i];
+}
+
+extern "C" int frk_add_diag(frk_ctx *ctx, int r, const double *d_diag, double *d_A) {
+    FRK_REQUIRE(ctx && d_A && d_diag && r > 0, "frk_add_diag: bad argument");
+    FRK_LAUNCH(ctx, add_diag_kernel, (unsigned)cdiv(r, 256), 256, 0, r, d_diag, d_A);
+    return 0;
+}

@@ -309,3 +309,99 @@ extern "C" int frk_xalpha(frk_ctx *ctx, int64_t n, int p, const double *d_X, con
     FRK_LAUNCH(ctx, xalpha_kernel, grid, 256, 0, n, p, d_X, al, d_out);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// vector statistics: sum(x - shift), sum((x - shift)^2), min, max  (var(Z) and mean(Ve) of
+// .EM_initialise R/SRE.R:704-731; the homoscedasticity test all(a == a[1]) R/SREfit.R:278-280)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vec_stats_kernel(int64_t n, const double *__restrict__ x, double shift,
+                                                        double *__restrict__ partial) {
+    double s = 0.0, s2 = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i], c = v - shift;
+        s += c; s2 += c * c;
+        mn = fmin(mn, v); mx = fmax(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ double sh[8][4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh[wid][0] = s; sh[wid][1] = s2; sh[wid][2] = mn; sh[wid][3] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { s += sh[w][0]; s2 += sh[w][1]; mn = fmin(mn, sh[w][2]); mx = fmax(mx, sh[w][3]); }
+        double *o = partial + (size_t)blockIdx.x * 4;
+        o[0] = s; o[1] = s2; o[2] = mn; o[3] = mx;
+    }
+}
+
+__global__ void vec_stats_final_kernel(int nblocks, const double *__restrict__ partial, double *__restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0, s2 = 0, mn = INFINITY, mx = -INFINITY;
+        for (int b = 0; b < nblocks; b++) {
+            s += partial[b * 4]; s2 += partial[b * 4 + 1];
+            mn = fmin(mn, partial[b * 4 + 2]); mx = fmax(mx, partial[b * 4 + 3]);
+        }
+        out[0] = s; out[1] = s2; out[2] = mn; out[3] = mx;
+    }
+}
+
+extern "C" int frk_vec_stats(frk_ctx *ctx, int64_t n, const double *d_x, double shift, double *h_out) {
+    FRK_REQUIRE(ctx && h_out && (n == 0 || d_x), "frk_vec_stats: NULL argument");
+    if (n == 0) { h_out[0] = h_out[1] = 0.0; h_out[2] = INFINITY; h_out[3] = -INFINITY; return 0; }
+    const int nblocks = (int)std::min<int64_t>(cdiv(n, 256), 512);
+    double *part = ctx->d_small, *out = ctx->d_small + 2048;
+    FRK_LAUNCH(ctx, vec_stats_kernel, nblocks, 256, 0, n, d_x, shift, part);
+    FRK_LAUNCH(ctx, vec_stats_final_kernel, 1, 32, 0, nblocks, part, out);
+    FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned, out, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; i++) h_out[i] = ctx->h_pinned[i];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// element-wise helpers for SRE(): Ve = std^2 (R/SRE.R:468), 1/Ve (R/SREpredict.R:286-293), and the
+// row gather behind Vfs = diag(fs[bau]) (R/SRE.R:498) and X = model matrix at the observed BAUs (:464-465)
+// ---------------------------------------------------------------------------------
+__global__ void vec_unary_kernel(int64_t n, int op, const double *__restrict__ a, double *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = a[i];
+        out[i] = op == 0 ? v * v : 1.0 / v;
+    }
+}
+
+extern "C" int frk_square(frk_ctx *ctx, int64_t n, const double *d_a, double *d_out) {
+    if (n == 0) return 0;
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, vec_unary_kernel, grid, 256, 0, n, 0, d_a, d_out);
+    return 0;
+}
+
+extern "C" int frk_recip(frk_ctx *ctx, int64_t n, const double *d_a, double *d_out) {
+    if (n == 0) return 0;
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, vec_unary_kernel, grid, 256, 0, n, 1, d_a, d_out);
+    return 0;
+}
+
+__global__ void gather_rows_kernel(int64_t m, int ncols, const int *__restrict__ idx, const double *__restrict__ src, int64_t ld_src,
+                                   double *__restrict__ dst, int64_t ld_dst) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = idx[j];
+        for (int c = 0; c < ncols; c++) dst[j + c * ld_dst] = src[s + c * ld_src];
+    }
+}
+
+extern "C" int frk_gather_rows(frk_ctx *ctx, int64_t m, int ncols, const int *d_idx, const double *d_src, int64_t ld_src,
+                               double *d_dst, int64_t ld_dst) {
+    FRK_REQUIRE(ctx && (m == 0 || (d_idx && d_src && d_dst)), "frk_gather_rows: NULL argument");
+    if (m == 0 || ncols == 0) return 0;
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(m, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, gather_rows_kernel, grid, 256, 0, m, ncols, d_idx, d_src, ld_src, d_dst, ld_dst);
+    return 0;
+}

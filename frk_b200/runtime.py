@@ -93,11 +93,24 @@ class Device:
 
     def allreduce_host(self, a: np.ndarray) -> np.ndarray:
         """Sum a small host vector over ranks (M-step moments, O(p^2) doubles)."""
-        if self.world == 1:
-            return a
-        t = self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.tdev)
-        self.torch.distributed.all_reduce(t)
-        return t.cpu().numpy()
+        return allreduce_host(a, "sum", self.tdev)
+
+    def allreduce_host_max(self, a: np.ndarray) -> np.ndarray:
+        return allreduce_host(a, "max", self.tdev)
+
+
+def allreduce_host(a: np.ndarray, op: str = "sum", device=None) -> np.ndarray:
+    """All-reduce a small host vector over the ranks of the default process group (NCCL on the GPU
+    box, gloo in the CPU tests); identity when torch.distributed is not initialised."""
+    import torch
+    d = torch.distributed
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if not (d.is_available() and d.is_initialized()) or d.get_world_size() == 1:
+        return a
+    on_gpu = d.get_backend() == "nccl"
+    t = torch.as_tensor(a.copy(), device=device if on_gpu else "cpu")
+    d.all_reduce(t, op=d.ReduceOp.SUM if op == "sum" else d.ReduceOp.MAX)
+    return t.cpu().numpy()
 
 
 def get_device(index: Optional[int] = None) -> Device:

@@ -50,6 +50,7 @@ int frk_malloc(frk_ctx *ctx, size_t bytes, void **d_out);
 int frk_free(frk_ctx *ctx, void *d_ptr);
 int frk_h2d(frk_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* async on ctx stream */
 int frk_d2h(frk_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);   /* synchronises        */
+int frk_d2d(frk_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);   /* async on ctx stream */
 int frk_memset0(frk_ctx *ctx, void *d_dst, size_t bytes);
 /* number of kernels this library has launched on ctx since creation (bench.py: gpu_launches) */
 int64_t frk_launch_count(frk_ctx *ctx);
@@ -111,6 +112,12 @@ int frk_bin_mean(frk_ctx *ctx, int64_t n, const int *d_bau, int64_t nbau, int nc
                  const double *d_vals, int *d_obs_bau, double *d_means, int *d_counts,
                  int64_t *h_m);
 
+/* coordinates(BAUs) of a pixel grid in expand.grid order (x fastest), BAU rows [lo, hi): what SRE()
+ * hands to eval_basis (R/SRE.R:412; grid layout R/geometryfns.R:629-637).  d_xgrid[nx], d_ygrid[ny]
+ * device axes; d_out (hi-lo) x 2 column-major.                                               */
+int frk_grid_centroids(frk_ctx *ctx, int64_t lo, int64_t hi, int nx, const double *d_xgrid,
+                       const double *d_ygrid, double *d_out);
+
 /* ---- S = Cmat %*% S0 for point data (row gather): R/SRE.R:502, BuildC
  *      R/geometryfns.R:1557-1568 -------------------------------------------------- */
 int frk_csr_gather_count(frk_ctx *ctx, int64_t m, const int *d_rows, const int *d_rowptr_src,
@@ -151,6 +158,18 @@ int frk_mstep_sums(frk_ctx *ctx, int64_t m, int p, const double *d_X, const doub
                    const double *d_t, const double *d_q, const double *d_ve,
                    const double *d_vfs, double sigma2fs, int mode, double *h_out);
 
+/* h_out[4] = sum(x - shift), sum((x - shift)^2), min(x), max(x)  (synchronises).  var(Z) and
+ * mean(diag Ve) of .EM_initialise (R/SRE.R:704-731); all(a == a[1]) test (R/SREfit.R:278-280).  */
+int frk_vec_stats(frk_ctx *ctx, int64_t n, const double *d_x, double shift, double *h_out);
+
+/* out = a*a  (Ve = std^2, R/SRE.R:468)  and  out = 1/a  (Ve^-1, R/SREpredict.R:286-293) */
+int frk_square(frk_ctx *ctx, int64_t n, const double *d_a, double *d_out);
+int frk_recip(frk_ctx *ctx, int64_t n, const double *d_a, double *d_out);
+/* dst[j, c] = src[idx[j], c] for ncols column-major columns: Vfs = fs[bau] (R/SRE.R:498) and the model
+ * matrix X at the observed BAUs (R/SRE.R:464-465)                                                */
+int frk_gather_rows(frk_ctx *ctx, int64_t m, int ncols, const int *d_idx, const double *d_src,
+                    int64_t ld_src, double *d_dst, int64_t ld_dst);
+
 /* ---- predict at BAUs: R/SREpredict.R:334-375 and the point-data closed form of :308-333.
  * mode 0 (obs_fs=TRUE or sigma2fs==0): mu = xa + smu, var = q.
  * mode 1 (obs_fs=FALSE, sigma2fs>0):   a = A/(A+Qf), Qf = 1/(sigma2fs*fs);
@@ -178,10 +197,16 @@ int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet);
 /* chol2inv: given L from frk_potrf in d_L (left intact), writes the full symmetric inverse of
  * A to d_Ainv.  d_work: r*r doubles of scratch (receives L^-T).                             */
 int frk_potri(frk_ctx *ctx, int r, const double *d_L, double *d_Ainv, double *d_work);
+/* x = Y' b for the upper-triangular Y = L^-T that frk_potri leaves in d_work, i.e. x = L^-1 b:
+ * (rDinv %*% S) %*% solve(R) in .loglik.ind (R/SREfit.R:211)                                  */
+int frk_upper_tmulv(frk_ctx *ctx, int r, const double *d_Y, const double *d_b, double *d_x);
 /* y = A x for symmetric full-storage A */
 int frk_symv(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double *d_y);
 /* out = mirror(upper triangle of G) + B   (Q_eta = S'D^-1 S + K^-1, R/SREfit.R:252); B may be NULL */
 int frk_sym_from_upper_add(frk_ctx *ctx, int r, const double *d_Gupper, const double *d_B, double *d_out);
+/* A = value * I  (.EM_initialise, R/SRE.R:710-722);  diag(A) += d  (.regularise_K, R/SREfit.R:669-686) */
+int frk_scaled_identity(frk_ctx *ctx, int r, double value, double *d_A);
+int frk_add_diag(frk_ctx *ctx, int r, const double *d_diag, double *d_A);
 /* out = A + x x'   (S_eta + tcrossprod(mu_eta), R/SREfit.R:332,689) */
 int frk_add_outer(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double *d_out);
 /* out = exp(-D / tau) * scale   (block-exponential K_i, R/SREfit.R:517,631) */

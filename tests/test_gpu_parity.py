@@ -1,0 +1,231 @@
+"""GPU parity: libfrkb200 (through the C ABI / the frk_b200 host mirror) against the CPU oracle on the same
+seeded inputs.  Oracle provenance: CPU restatement of the cited reference lines (no R in this image).
+Bars (BASELINE.json north_star): C_Z and the S sparsity pattern bit-exact; S values, mu_eta, predictive
+variances and the log-likelihood trace within rtol 1e-9."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from cases import pseudo_isea3h, readme_points, sphere_points
+from oracle import frk_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _mk_basis(F, ob):
+    man = {"plane": F.plane(), "real_line": F.real_line(), "sphere": F.sphere(ob.manifold.radius)}[ob.manifold.kind]
+    return F.Basis(man, ob.loc.copy(), ob.scale.copy(), ob.res.copy(), ob.type, ob.regular)
+
+
+def _same_pattern(A, B):
+    A = A.tocsr(); B = B.tocsr()
+    A.sort_indices(); B.sort_indices()
+    return np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+
+
+@pytest.mark.parametrize("btype", ["bisquare", "Gaussian", "exp", "Matern32"])
+def test_eval_basis_plane(dev, btype):
+    import frk_b200 as F
+    xy, _ = readme_points(3000, seed=3)
+    ob = O.auto_basis(O.plane(), xy, regular=1, nres=2 if btype != "bisquare" else 3, type=btype)
+    S_o = O.eval_basis(ob, xy)
+    S_g = F.eval_basis(_mk_basis(F, ob), xy, dev)
+    assert _same_pattern(S_o, S_g)
+    if btype == "bisquare":      # +,-,*,/,sqrt only: bit-exact
+        assert np.array_equal(S_o.tocsr().data, S_g.data)
+    else:
+        np.testing.assert_allclose(S_g.data, S_o.tocsr().data, rtol=RTOL, atol=0)
+
+
+def test_eval_basis_plane_edges(dev):
+    """points exactly on a support boundary (y == R -> explicit zero dropped), on centroids, outside everything."""
+    import frk_b200 as F
+    loc = np.array([[0.0, 0.0], [1.0, 0.0], [0.5, 0.5]])
+    ob = O.local_basis(O.plane(), loc, [0.5, 0.5, 0.25], "bisquare")
+    s = np.array([[0.5, 0.0], [0.0, 0.0], [1.0, 0.0], [0.25, 0.5], [10.0, 10.0], [0.5, 0.25], [0.3, 0.4]])
+    S_o = O.eval_basis(ob, s)
+    S_g = F.eval_basis(_mk_basis(F, ob), s, dev)
+    assert _same_pattern(S_o, S_g)
+    assert np.array_equal(S_o.tocsr().data, S_g.data)
+    assert S_g[1, 0] == 1.0 and S_g[0].nnz == 0 and S_g[4].nnz == 0
+    # empty input
+    S_e = F.eval_basis(_mk_basis(F, ob), np.zeros((0, 2)), dev)
+    assert S_e.shape == (0, 3) and S_e.nnz == 0
+
+
+def test_eval_basis_real_line(dev):
+    import frk_b200 as F
+    rng = np.random.default_rng(5)
+    t = rng.uniform(0, 30, 500)[:, None]
+    ob = O.auto_basis(O.real_line(), t, regular=6, nres=2, type="bisquare")
+    S_o = O.eval_basis(ob, t)
+    S_g = F.eval_basis(_mk_basis(F, ob), t, dev)
+    assert _same_pattern(S_o, S_g)
+    assert np.array_equal(S_o.tocsr().data, S_g.data)
+
+
+@pytest.mark.parametrize("btype", ["bisquare", "Matern32"])
+def test_eval_basis_sphere(dev, btype):
+    import frk_b200 as F
+    ll, _ = sphere_points(4000, seed=11)
+    ll = np.vstack([ll, [[0.0, 90.0], [0.0, -90.0], [180.0, 0.0], [-180.0, 0.0], [179.999, 45.0]]])
+    ob = O.auto_basis(O.sphere(), ll, nres=3 if btype == "bisquare" else 2, type=btype, isea3h=pseudo_isea3h(), isea3h_lo=1)
+    S_o = O.eval_basis(ob, ll).tocsr()
+    S_g = F.eval_basis(_mk_basis(F, ob), ll, dev)
+    # libm vs CUDA cos/sin/acos differ by <= 1-2 ulp: pattern can only differ at exact ties on the support edge
+    D = (abs(S_o - S_g)).tocoo()
+    if not _same_pattern(S_o, S_g):
+        extra = (S_o != 0).astype(int) - (S_g != 0).astype(int)
+        bad = abs(extra).tocoo()
+        vals = np.maximum(abs(S_o[bad.row, bad.col]).A1, abs(S_g[bad.row, bad.col]).A1)
+        assert vals.max() < 1e-20, "pattern differs away from the support edge"
+    np.testing.assert_allclose(S_g.toarray(), S_o.toarray(), rtol=1e-9, atol=1e-13)
+
+
+def test_tensor_basis(dev):
+    import frk_b200 as F
+    xy, _ = readme_points(800, seed=8)
+    rng = np.random.default_rng(9)
+    t = rng.uniform(0, 20, 800)
+    ob1 = O.auto_basis(O.plane(), xy, regular=1, nres=2)
+    ob2 = O.local_basis(O.real_line(), np.arange(2.0, 20.0, 4.0)[:, None], np.full(5, 3.0), "Gaussian")
+    ot = O.TensorP_Basis(ob1, ob2)
+    s = np.column_stack([xy, t])
+    S_o = O.eval_basis(ot, s)
+    gt = F.TensorP(_mk_basis(F, ob1), _mk_basis(F, ob2))
+    S_g = F.eval_basis(gt, s, dev)
+    assert _same_pattern(S_o, S_g)
+    np.testing.assert_allclose(S_g.data, S_o.tocsr().data, rtol=RTOL)
+
+
+def test_grid_lookup_and_binning(dev):
+    """C_Z: integer point-in-cell lookup and per-BAU means -- bit-exact indices."""
+    import frk_b200 as F
+    xy, z = readme_points(5000, seed=4)
+    xy[:7] = [[0.5, 0.5], [-1, 0.5], [0.5, 7], [0.005, 0.005], [0.015, 0.995], [1.0, 1.0], [np.nan, 0.2]]
+    ob = O.auto_BAUs_plane(xy[7:], cellsize=0.01, xlims=(0, 1), ylims=(0, 1))
+    bau_o = O.points_to_BAUs(xy, ob)
+    gb = F.auto_BAUs(F.plane(), cellsize=0.01, xlims=(0, 1), ylims=(0, 1))
+    assert np.array_equal(gb.xgrid, ob.xgrid) and np.array_equal(gb.ygrid, ob.ygrid)
+    std = np.full(len(z), 0.5) + 0.1 * (np.arange(len(z)) % 3)
+    data = F.SpatialPointsDataFrame(xy, {"z": z, "std": std})
+    out = F.map_data_to_BAUs(data, gb, ["z", "std"], dev)
+    bau_g = dev.download(out["bau"], len(z))
+    assert np.array_equal(bau_g, bau_o)
+    uo, mo, co = O.bin_mean(bau_o, np.column_stack([z, std]))
+    m = out["m"]
+    assert m == len(uo)
+    assert np.array_equal(dev.download(out["obs_bau"], m), uo)
+    assert np.array_equal(dev.download(out["counts"], m), co)
+    means = dev.download(out["means"]).reshape(2, -1)[:, :m].T
+    np.testing.assert_allclose(means, mo, rtol=1e-12, atol=1e-15)
+    # host-buffer C-ABI entry point, with an explicit cell2bau map
+    import ctypes as C
+    from frk_b200._lib import call, vp
+    h = np.empty(len(z), dtype=np.int32)
+    xyf = np.asfortranarray(xy)
+    off, cs, dm, c2b = gb.offset, np.asarray(gb.cellsize), gb.dims, gb.cell2bau()
+    call("frk_grid_lookup_host", dev.ctx, len(z), vp(xyf.ctypes.data), vp(off.ctypes.data), vp(cs.ctypes.data),
+         vp(dm.ctypes.data), vp(c2b.ctypes.data), len(c2b), vp(h.ctypes.data))
+    assert np.array_equal(h, bau_o)
+
+
+def _dense_case(r, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((r, r + 5))
+    return A @ A.T + r * np.eye(r)
+
+
+@pytest.mark.parametrize("r", [1, 7, 64, 65, 200, 819])
+def test_chol2inv(dev, r):
+    import ctypes as C
+    from frk_b200._lib import call, vp
+    A = _dense_case(r, r)
+    Ainv = np.empty_like(A)
+    ld = C.c_double(0)
+    Af = np.asfortranarray(A)
+    call("frk_chol2inv_host", dev.ctx, r, vp(Af.ctypes.data), vp(Ainv.ctypes.data), C.byref(ld))
+    ref = O.chol2inv(O.chol_upper(A))
+    np.testing.assert_allclose(Ainv.T, ref, rtol=1e-9, atol=1e-12 * abs(ref).max())
+    np.testing.assert_allclose(ld.value, np.linalg.slogdet(A)[1], rtol=1e-12)
+    assert np.array_equal(Ainv, Ainv.T)
+
+
+def test_potrf_not_pd(dev):
+    import ctypes as C
+    from frk_b200 import FRKError
+    from frk_b200._lib import call, vp
+    A = np.eye(70); A[66, 66] = -1.0
+    out = np.empty_like(A); ld = C.c_double(0)
+    with pytest.raises(FRKError, match="not positive definite"):
+        call("frk_chol2inv_host", dev.ctx, 70, vp(A.ctypes.data), vp(out.ctypes.data), C.byref(ld))
+
+
+def test_dgemm_nt(dev):
+    from frk_b200._lib import call
+    rng = np.random.default_rng(0)
+    for (M, N, K) in [(128, 64, 16), (130, 70, 33), (257, 129, 64), (5, 3, 2)]:
+        A = rng.standard_normal((M, K)); B = rng.standard_normal((N, K)); Cc = rng.standard_normal((M, N))
+        dA, dB, dC = dev.upload(A), dev.upload(B), dev.upload(Cc)
+        call("frk_dgemm_nt", dev.ctx, M, N, K, 0.5, dev.ptr(dA), M, dev.ptr(dB), N, -2.0, dev.ptr(dC), M)
+        out = dev.download(dC).reshape(N, M).T
+        np.testing.assert_allclose(out, 0.5 * A @ B.T - 2.0 * Cc, rtol=1e-12, atol=1e-12)
+
+
+def _setup_plane(F, m=1000, seed=1, nres=2, hetero=False, K_type="block-exponential", cellsize=0.02):
+    xy, z = readme_points(m, seed)
+    std = np.full(m, 0.5)
+    if hetero:
+        std = 0.3 + 0.4 * np.random.default_rng(seed + 100).uniform(size=m)
+    ob = O.auto_basis(O.plane(), xy, regular=1, nres=nres)
+    obaus = O.auto_BAUs_plane(xy, cellsize=cellsize)
+    bau = O.points_to_BAUs(xy, obaus)
+    uo, means, _ = O.bin_mean(bau, np.column_stack([z, std]))
+    Mo = O.SRE(ob, obaus.centroids(), np.ones(obaus.n), uo, means[:, 0], means[:, 1], K_type=K_type)
+    gb = F.auto_BAUs(F.plane(), cellsize=cellsize, data=F.SpatialPointsDataFrame(xy, {}))
+    gb["fs"] = 1.0
+    data = F.SpatialPointsDataFrame(xy, {"z": z, "std": std})
+    Mg = F.SRE("z ~ 1", data, _mk_basis(F, ob), gb, est_error=False, K_type=K_type)
+    return Mo, Mg
+
+
+@pytest.mark.parametrize("K_type,hetero", [("unstructured", False), ("block-exponential", False),
+                                           ("unstructured", True), ("block-exponential", True)])
+def test_em_fit_and_predict_readme(dev, K_type, hetero):
+    """BASELINE config 1 (README quick start): SRE -> SRE.fit(EM) -> predict against the oracle."""
+    import frk_b200 as F
+    Mo, Mg = _setup_plane(F, K_type=K_type, hetero=hetero)
+    # SRE(): S pattern bit-exact, values to 1e-9, C_Z exact
+    Sg = Mg.S.to_scipy(dev)
+    assert _same_pattern(Mo.S, Sg)
+    np.testing.assert_allclose(Sg.data, Mo.S.data, rtol=RTOL)
+    assert np.array_equal(dev.download(Mg.obs_bau, Mg.m), Mo.obs_bau)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL)
+    assert Mg.homoscedastic == (not hetero)
+    n_EM = 6
+    O.SRE_fit(Mo, n_EM=n_EM, tol=0.0)
+    F.SRE_fit(Mg, n_EM=n_EM, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-7 if hetero else RTOL)   # uniroot tol = eps^0.25
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=1e-7 if hetero else RTOL)
+    scale = abs(Mo.mu_eta).max()
+    np.testing.assert_allclose(Mg.get("mu_eta"), Mo.mu_eta, rtol=1e-7, atol=1e-9 * scale)
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pg = F.predict(Mg, obs_fs=obs_fs)
+        np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-9 * abs(po[0]).max())
+        np.testing.assert_allclose(pg["var"], po[1], rtol=1e-7)
+        np.testing.assert_allclose(pg["sd"], po[2], rtol=1e-7)
+
+
+def test_predict_closed_form_matches_general(dev):
+    """KAT-5 analogue (test_SRE.R:46-52): the device's Case-2 prediction equals the literal joint (eta, xi) solve."""
+    import frk_b200 as F
+    Mo, Mg = _setup_plane(F, m=300, nres=1, cellsize=0.1, K_type="unstructured")
+    O.SRE_fit(Mo, n_EM=3, tol=0.0)
+    F.SRE_fit(Mg, n_EM=3, tol=0.0)
+    mu, var, sd = O.predict_general(Mo)
+    pg = F.predict(Mg, obs_fs=False)
+    np.testing.assert_allclose(pg["var"], var, rtol=1e-7)
+    np.testing.assert_allclose(pg["mu"], mu, rtol=1e-7, atol=1e-9)
