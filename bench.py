@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE config 3 (SURVEY.md s8(d) "C3"):
+
+    1e6 observations uniform on the unit square, z = sin(8x) + cos(8y) + 0.5 N(0,1), std = 0.5;
+    BAUs = 3163 x 3163 pixel grid over [0,1]^2 (1.0e7 BAUs); basis auto_basis(plane(), nres = 3, regular = 2,
+    type = "bisquare") -> r = 3276; SRE(K_type = "block-exponential", the reference default) -> SRE.fit(EM) -> predict.
+
+A "step" is one EM iteration (log-likelihood + E-step + M-step, R/SREfit.R:104-115).  `value` = EM iterations / s
+with everything resident in HBM; `predict` = BAUs predicted / s; `e2e` = the same metrics through the public
+host-buffer API (SRE() from pinned host arrays -> SRE_fit -> fitted slots back on the host; predict() -> host).
+Rows (BAUs and the observations in them) are partitioned over the ranks: the problem size is fixed as N grows
+("scaling": "strong"), one fp64 all-reduce of r^2 + r + 2 doubles per EM iteration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference`: the CPU restatement of the reference (oracle/, NumPy/SciPy on all host cores; R itself is not
+installable here) on the same workload, each step one EM iteration, bounded by --cpu-budget seconds.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "EM iters/sec (N=1e6 obs, r=3276) [+ predicted BAUs/sec over 1e7 BAUs in 'predict']"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--k-type", default="block-exponential", choices=["block-exponential", "unstructured"])
+    ap.add_argument("--n-obs", type=int, default=1_000_000)
+    ap.add_argument("--grid", type=int, default=3163, help="BAU grid is grid x grid over the unit square")
+    ap.add_argument("--regular", type=int, default=2)
+    ap.add_argument("--nres", type=int, default=3)
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--predict-reps", type=int, default=5)
+    return ap.parse_args()
+
+
+def workload(args):
+    rng = np.random.default_rng(3)
+    n = args.n_obs
+    x = rng.uniform(0, 1, n)
+    y = rng.uniform(0, 1, n)
+    z = np.sin(8 * x) + np.cos(8 * y) + 0.5 * rng.standard_normal(n)
+    std = np.full(n, 0.5)
+    return np.column_stack([x, y]), z, std
+
+
+def config(args, r, n_bau, m):
+    return {"workload": f"C3: {args.n_obs} obs U(0,1)^2, bisquare auto_basis(plane, nres={args.nres}, regular={args.regular}) r={r}, "
+                        f"{args.grid}x{args.grid}={n_bau} grid BAUs, K_type={args.k_type}, {m} occupied BAUs",
+            "n_obs": args.n_obs, "r": r, "n_bau": n_bau, "m_binned": m, "K_type": args.k_type,
+            "cache": "inputs larger than L2 (S 0.37 GB, six r x r fp64 matrices 86 MB each, S0 4 GB); no L2 flush",
+            "partition": "BAU rows block-partitioned over ranks; r-sized state replicated"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm (oracle) -- also the cpu_baseline leg of the GPU arm
+# ---------------------------------------------------------------------------------------------------
+
+def cpu_em(args, budget_s, max_steps, warmup=0):
+    """EM iterations of the oracle on the full workload (S evaluated at the occupied BAUs only; BAU-level
+    prediction timed on a 1e5-BAU sample).  Returns a dict for the JSON line."""
+    from threadpoolctl import threadpool_info
+    from oracle import frk_oracle as O
+    xy, z, std = workload(args)
+    ob = O.auto_basis(O.plane(), np.array([[0.0, 0.0], [1.0, 1.0]]), regular=args.regular, nres=args.nres)
+    ba = O.auto_BAUs_plane(xy, cellsize=1.0 / (args.grid - 1), xlims=(0, 1), ylims=(0, 1))
+    bau = O.points_to_BAUs(xy, ba)
+    uo, means, _ = O.bin_mean(bau, np.column_stack([z, std]))
+    cc = np.column_stack([ba.xgrid[uo % ba.nx], ba.ygrid[uo // ba.nx]])
+    M = O.SRE(ob, cc, np.ones(len(uo)), np.arange(len(uo)), means[:, 0], means[:, 1], K_type=args.k_type, fast_eval=True)
+    times = []
+    t_all = time.time()
+    for it in range(warmup + max_steps):
+        t0 = time.time()
+        O.loglik(M); O.Estep(M); O.Mstep(M)
+        dt = time.time() - t0
+        if it >= warmup:
+            times.append(dt)
+        if time.time() - t_all > budget_s and len(times) >= 1:
+            break
+    # prediction sample: 1e5 BAUs
+    nb = min(100_000, ba.n)
+    idx = np.linspace(0, ba.n - 1, nb).astype(np.int64)
+    S0s = O.normalise_rows(O.eval_basis_fast(ob, np.column_stack([ba.xgrid[idx % ba.nx], ba.ygrid[idx // ba.nx]])))
+    t0 = time.time()
+    v = O.batch_compute_var(S0s, M.S_eta)
+    mu = S0s @ M.mu_eta
+    tp = time.time() - t0
+    blas = [f"{d.get('internal_api')}:{d.get('num_threads')}" for d in threadpool_info()]
+    return dict(iters=len(times), s_per_iter=float(np.mean(times)), iters_per_s=len(times) / float(np.sum(times)),
+                predict_baus_per_s=nb / tp, cores=os.cpu_count(), blas=blas, r=ob.n, n_bau=ba.n, m=len(uo),
+                sample=f"{len(times)} full EM iteration(s) (loglik+E+M, K_type={args.k_type}) at m={len(uo)}, r={ob.n} "
+                       f"after {warmup} warm-up; predict on a {nb}-BAU sample; NumPy/SciPy oracle, BLAS threads {blas}")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_em(args, budget_s=max(args.cpu_budget, 150.0), max_steps=args.steps, warmup=0)
+    line = {"impl": "reference", "metric": METRIC, "value": res["iters_per_s"], "unit": "EM iters/s", "n_gpus": args.gpus,
+            "steps": res["iters"], "warmup": 0, "ms_per_step": 1e3 * res["s_per_iter"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config(args, res["r"], res["n_bau"], res["m"]),
+            "predict": {"value": res["predict_baus_per_s"], "unit": "BAUs/s"},
+            "cpu_baseline": {"value": res["iters_per_s"], "unit": "EM iters/s", "cores": res["cores"], "kind": "port",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["iters_per_s"], "unit": "EM iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fp64_peak_probe(torch, dev):
+    """cuBLAS DGEMM 8192^3, best of 5: the measured fp64 denominator (MEASURED_PEAKS.json has none)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    best = 1e9
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import frk_b200 as F
+    from frk_b200._lib import call, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = F.get_device(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- host inputs in pinned memory -------------------------------------------------------
+    xy, z, std = workload(args)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    xy_p = pin(np.asfortranarray(xy).T.copy()).T          # column-major (n x 2) view over pinned memory
+    data = F.SpatialPointsDataFrame(xy_p, {"z": pin(z), "std": pin(std)})
+    basis = F.auto_basis(F.plane(), np.array([[0.0, 0.0], [1.0, 1.0]]), regular=args.regular, nres=args.nres)
+    BAUs = F.auto_BAUs(F.plane(), cellsize=1.0 / (args.grid - 1), xlims=(0, 1), ylims=(0, 1))
+    BAUs.fields["fs"] = pin(np.ones(len(BAUs)))
+    r, N = basis.n, len(BAUs)
+
+    # ---- (A) device-resident EM iterations --------------------------------------------------------
+    mdl = F.SRE("z ~ 1", data, basis, BAUs, est_error=False, K_type=args.k_type, dev=dev)
+    F.SRE_fit(mdl, n_EM=args.warmup, tol=0.0)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    l0 = dev.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    F.SRE_fit(mdl, n_EM=args.steps, tol=0.0)
+    e1.record()
+    barrier()
+    t_em = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    launches = dev.launches() - l0
+    llk_tail = [float(v) for v in mdl.info_fit["llk"][-2:]]
+
+    # ---- (B) device-resident prediction ---------------------------------------------------------------
+    for _ in range(2):
+        F.predict(mdl, obs_fs=False, to_host=False)
+    barrier()
+    lp0 = dev.launches()
+    e0.record()
+    for _ in range(args.predict_reps):
+        F.predict(mdl, obs_fs=False, to_host=False)
+    e1.record()
+    barrier()
+    t_pred = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / args.predict_reps
+    launches_pred = (dev.launches() - lp0) // args.predict_reps
+    clk = clocks.stop()
+
+    # ---- (D) per-kernel roofline pass (CUDA events around every launch, same steps) --------------------
+    kernels, roof = [], None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s")
+    if not args.no_profile:
+        fp64_peak = fp64_peak_probe(torch, dev.tdev)
+        call("frk_profile", dev.ctx, 1)
+        F.SRE_fit(mdl, n_EM=2, tol=0.0)
+        n_f_tau_launch_iters = 2
+        F.predict(mdl, obs_fs=False, to_host=False)
+        buf = C.create_string_buffer(1 << 16)
+        call("frk_profile_report", dev.ctx, buf, len(buf))
+        call("frk_profile", dev.ctx, 0)
+        rep = json.loads(buf.value.decode())
+        # algorithmic bytes of the streaming kernels (DESIGN.md "roofline accounting")
+        nloc = mdl.hi - mdl.lo
+        gram_bytes = mdl.S.nnz * 12 + mdl.m * (4 + 8 * (3 + mdl.p)) + (r * r + r) * 8
+        quad_S_bytes = mdl.S.nnz * 12 + mdl.m * (4 + 16) + r * r * 8
+        quad_S0_bytes = mdl.S0.nnz * 12 + nloc * (4 + 16) + r * r * 8
+        tot_ms = sum(k["ms"] for k in rep) or 1.0
+        for k in sorted(rep, key=lambda k: -k["ms"]):
+            ent = {"kernel": k["kernel"], "launches": k["launches"], "ms_total": round(k["ms"], 3), "share": round(k["ms"] / tot_ms, 4)}
+            if k["flops"] > 0:
+                ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
+                ent.update(bound="fp64", achieved=ach, peak=fp64_peak, unit="TFLOP/s", frac=ach / fp64_peak)
+            elif "gram_rhs_kernel" in k["kernel"]:
+                ach = gram_bytes * k["launches"] / (k["ms"] * 1e-3) / 1e9
+                ent.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak)
+            elif "quadform_spmv_kernel" in k["kernel"]:
+                # launches: 2 on S (M-step), 1 on S0 (predict)
+                by = quad_S_bytes * n_f_tau_launch_iters + quad_S0_bytes
+                ach = by / (k["ms"] * 1e-3) / 1e9
+                ent.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak)
+            kernels.append(ent)
+        top = kernels[0]
+        if "achieved" in top:
+            roof = {"bound": "tensor" if top["bound"] == "fp64" else "hbm", "kernel": top["kernel"], "achieved": top["achieved"],
+                    "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                    "peak_source": ("cuBLAS DGEMM 8192^3 probe in this run (fp64 DMMA; MEASURED_PEAKS.json has no fp64 figure)"
+                                    if top["bound"] == "fp64" else hbm_src),
+                    "share_of_step": top["share"]}
+
+    # ---- (C) end to end through the public host-buffer API -------------------------------------------
+    del mdl
+    torch.cuda.empty_cache()
+    barrier()
+    t0 = time.perf_counter()
+    m2 = F.SRE("z ~ 1", data, basis, BAUs, est_error=False, K_type=args.k_type, dev=dev)
+    F.SRE_fit(m2, n_EM=args.steps, tol=0.0)
+    slots = {k: m2.get(k) for k in ("mu_eta", "S_eta", "Khat", "Khat_inv")}
+    barrier()
+    t_fit_e2e = max_over_ranks(time.perf_counter() - t0)
+    h2d_fit, d2h_fit = m2.h2d_bytes, m2.d2h_bytes
+    t0 = time.perf_counter()
+    pr = F.predict(m2, obs_fs=False, to_host=True)
+    barrier()
+    t_pred_e2e = max_over_ranks(time.perf_counter() - t0)
+    d2h_pred = 3 * 8 * (m2.hi - m2.lo)
+    finite = bool(np.isfinite(pr["mu"]).all() and (pr["var"] > 0).all())
+    m_binned = m2.m_total
+
+    # ---- (E) CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = cpu_em(args, budget_s=args.cpu_budget, max_steps=2, warmup=0)
+        cpu = {"value": res["iters_per_s"], "unit": "EM iters/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
+               "predict_baus_per_s": res["predict_baus_per_s"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": args.steps / t_em, "unit": "EM iters/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_em / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args, r, N, m_binned),
+                "predict": {"value": N / t_pred, "unit": "BAUs/s", "ms": 1e3 * t_pred, "launches": launches_pred,
+                            "e2e": {"value": N / t_pred_e2e, "unit": "BAUs/s", "d2h_bytes": d2h_pred * world, "results_ok": finite}},
+                "e2e": {"value": args.steps / t_fit_e2e, "unit": "EM iters/s", "h2d_bytes_per_step": h2d_fit / args.steps,
+                        "d2h_bytes_per_step": d2h_fit / args.steps,
+                        "what": f"SRE() from pinned host arrays + SRE_fit({args.steps} EM iterations) + fitted r x r slots back to host, wall clock"},
+                "gpu_launches": int(launches), "clocks": clk, "llk_last": llk_tail}
+        if roof:
+            line["roofline"] = roof
+        if kernels:
+            line["kernels"] = kernels[:12]
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,9 +4,14 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/frkb200.h"
+
+// per-kernel timing (bench.py roofline): CUDA events around every launch while profiling is on
+struct frk_prof_rec { const char *name; cudaEvent_t e0, e1; double flops, bytes; };
+struct frk_prof_stat { int64_t launches = 0; double ms = 0, flops = 0, bytes = 0; };
 
 struct frk_ctx {
     int device = 0;
@@ -18,7 +23,16 @@ struct frk_ctx {
     size_t scratch_bytes = 0;
     double *h_pinned = nullptr;   // 4096 doubles
     double *d_small = nullptr;    // 4096 doubles
+    // profiling
+    bool profiling = false;
+    double next_flops = 0, next_bytes = 0;          // algorithmic work of the next launch (FRK_WORK)
+    std::vector<frk_prof_rec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    std::map<std::string, frk_prof_stat> prof_stats;
 };
+
+int frk_prof_begin(frk_ctx *ctx, const char *name, cudaEvent_t *e1);   // records e0; returns 0
+int frk_prof_harvest(frk_ctx *ctx);
 
 void frk_set_error(const char *fmt, ...);
 
@@ -42,10 +56,17 @@ void frk_set_error(const char *fmt, ...);
 // every kernel launch goes through this so that frk_launch_count() is exact
 #define FRK_LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
     do {                                                                                \
+        cudaEvent_t _e1 = nullptr;                                                      \
+        if ((ctx)->profiling) { if (frk_prof_begin((ctx), #kernel, &_e1)) return 1; }   \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
+        if (_e1) cudaEventRecord(_e1, (ctx)->stream);                                   \
         (ctx)->launches++;                                                              \
+        (ctx)->next_flops = (ctx)->next_bytes = 0;                                      \
         FRK_CHECK_CUDA(cudaGetLastError());                                             \
     } while (0)
+
+// declare the ALGORITHMIC work (flops, bytes) of the next FRK_LAUNCH ("roofline accounting")
+#define FRK_WORK(ctx, fl, by) do { (ctx)->next_flops = (double)(fl); (ctx)->next_bytes = (double)(by); } while (0)
 
 int frk_scratch(frk_ctx *ctx, size_t bytes, void **out);   // grow-only scratch buffer
 

@@ -43,6 +43,8 @@ extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    frk_prof_harvest(ctx);
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_small) cudaFree(ctx->d_small);
@@ -85,6 +87,64 @@ extern "C" int frk_d2d(frk_ctx *ctx, void *d_dst, const void *d_src, size_t byte
 
 extern "C" int frk_memset0(frk_ctx *ctx, void *d_dst, size_t bytes) {
     FRK_CHECK_CUDA(cudaMemsetAsync(d_dst, 0, bytes, ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// per-kernel profiling
+// ---------------------------------------------------------------------------------
+int frk_prof_begin(frk_ctx *ctx, const char *name, cudaEvent_t *e1) {
+    if (ctx->prof_pending.size() >= 8192) { if (int rc = frk_prof_harvest(ctx)) return rc; }
+    cudaEvent_t ev[2];
+    for (int k = 0; k < 2; k++) {
+        if (!ctx->prof_pool.empty()) { ev[k] = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+        else FRK_CHECK_CUDA(cudaEventCreate(&ev[k]));
+    }
+    FRK_CHECK_CUDA(cudaEventRecord(ev[0], ctx->stream));
+    ctx->prof_pending.push_back({name, ev[0], ev[1], ctx->next_flops, ctx->next_bytes});
+    *e1 = ev[1];
+    return 0;
+}
+
+int frk_prof_harvest(frk_ctx *ctx) {
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof_pending) {
+        float ms = 0.f;
+        FRK_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        frk_prof_stat &st = ctx->prof_stats[r.name];
+        st.launches++; st.ms += ms; st.flops += r.flops; st.bytes += r.bytes;
+        ctx->prof_pool.push_back(r.e0);
+        ctx->prof_pool.push_back(r.e1);
+    }
+    ctx->prof_pending.clear();
+    return 0;
+}
+
+extern "C" int frk_profile(frk_ctx *ctx, int enable) {
+    FRK_REQUIRE(ctx, "frk_profile: NULL ctx");
+    if (int rc = frk_prof_harvest(ctx)) return rc;
+    if (enable && !ctx->profiling) ctx->prof_stats.clear();
+    ctx->profiling = enable != 0;
+    return 0;
+}
+
+extern "C" int frk_profile_report(frk_ctx *ctx, char *buf, size_t cap) {
+    FRK_REQUIRE(ctx && buf && cap > 2, "frk_profile_report: bad argument");
+    if (int rc = frk_prof_harvest(ctx)) return rc;
+    std::string out = "[";
+    bool first = true;
+    for (auto &kv : ctx->prof_stats) {
+        char line[768];
+        std::string nm = kv.first;
+        for (auto &ch : nm) if (ch == '"' || ch == '\\') ch = ' ';
+        snprintf(line, sizeof(line), "%s{\"kernel\": \"%s\", \"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+                 first ? "" : ", ", nm.c_str(), (long long)kv.second.launches, kv.second.ms, kv.second.flops, kv.second.bytes);
+        out += line;
+        first = false;
+    }
+    out += "]";
+    FRK_REQUIRE(out.size() + 1 <= cap, "frk_profile_report: buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
 

@@ -165,9 +165,13 @@ static int launch_gemm(frk_ctx *ctx, const GemmArgs &a) {
         attr = true;
     }
     dim3 grid((unsigned)cdiv(a.M, BM), (unsigned)cdiv(a.N, BN));
+    // algorithmic flops: full product 2MNK; lower-triangle SYRK M(M+1)K; upper-triangular Y Y' (lower half) ~ M^3/3
+    double fl = 2.0 * a.M * a.N * a.K;
+    if (a.lower) fl = a.kstart_m0 ? (double)a.M * a.M * a.M / 3.0 : (double)a.M * (a.M + 1.0) * a.K;
+    FRK_WORK(ctx, fl, 0);
     bool al = ((uintptr_t)a.A % 16 == 0) && ((uintptr_t)a.B % 16 == 0) && (a.lda % 2 == 0) && (a.ldb % 2 == 0);
-    if (al) FRK_LAUNCH(ctx, dgemm_nt_kernel<true>, grid, GEMM_T, GEMM_SMEM, a);
-    else    FRK_LAUNCH(ctx, dgemm_nt_kernel<false>, grid, GEMM_T, GEMM_SMEM, a);
+    if (al) { FRK_LAUNCH(ctx, dgemm_nt_kernel<true>, grid, GEMM_T, GEMM_SMEM, a); }
+    else    { double f2 = ctx->next_flops; FRK_WORK(ctx, f2, 0); FRK_LAUNCH(ctx, dgemm_nt_kernel<false>, grid, GEMM_T, GEMM_SMEM, a); }
     return 0;
 }
 

@@ -55,6 +55,12 @@ int frk_memset0(frk_ctx *ctx, void *d_dst, size_t bytes);
 /* number of kernels this library has launched on ctx since creation (bench.py: gpu_launches) */
 int64_t frk_launch_count(frk_ctx *ctx);
 
+/* Per-kernel device timing for bench.py's roofline: while enabled every launch is bracketed by CUDA events
+ * on the ctx stream; the report is a JSON array of {kernel, launches, ms, flops, bytes} where flops/bytes
+ * are the ALGORITHMIC work declared at the launch site.  Enabling clears earlier statistics. */
+int frk_profile(frk_ctx *ctx, int enable);
+int frk_profile_report(frk_ctx *ctx, char *buf, size_t cap);
+
 /* ---- basis: local_basis()/Basis object, R/basisfns.R:99-146, R/AllClass.R:78 -----
  * h_loc: r x d column-major centroids; h_scale: r; h_res: r (1-based resolution).
  * radius: sphere radius (R/geometryfns.R:97), ignored otherwise.
