@@ -66,6 +66,9 @@ SIGNATURES = {
     "frk_csr_gather_count": (c_int, [vp, c_i64, vp, vp, vp, p_i64]),
     "frk_csr_gather_fill": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),
     "frk_gram_rhs": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, c_int, vp, vp, vp, c_dbl, vp]),
+    "frk_csr_bucket_rows": (c_int, [vp, c_i64, vp, vp, c_int, vp, vp, vp, vp, vp]),
+    "frk_gram_rhs_bucketed": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp, vp, c_dbl, vp]),
+    "frk_quadform_spmv_bucketed": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_quadform_spmv": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp]),
     "frk_mstep_sums": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, c_dbl, c_int, vp]),
     "frk_vec_stats": (c_int, [vp, c_i64, vp, c_dbl, vp]),
@@ -78,7 +81,7 @@ SIGNATURES = {
     "frk_xalpha": (c_int, [vp, c_i64, c_int, vp, vp, vp]),
     "frk_potrf": (c_int, [vp, c_int, vp, p_dbl]),
     "frk_potri": (c_int, [vp, c_int, vp, vp, vp]),
-    "frk_upper_tmulv": (c_int, [vp, c_int, vp, vp, vp]),
+    "frk_lower_mulv": (c_int, [vp, c_int, vp, vp, vp]),
     "frk_symv": (c_int, [vp, c_int, vp, vp, vp]),
     "frk_sym_from_upper_add": (c_int, [vp, c_int, vp, vp, vp]),
     "frk_scaled_identity": (c_int, [vp, c_int, c_dbl, vp]),
@@ -90,6 +93,7 @@ SIGNATURES = {
     "frk_block_scatter": (c_int, [vp, c_int, vp, c_int, vp, vp]),
     "frk_block_gather_outer": (c_int, [vp, c_int, vp, vp, c_int, vp, vp]),
     "frk_dgemm_nt": (c_int, [vp, c_int, c_int, c_int, c_dbl, vp, c_int, vp, c_int, c_dbl, vp, c_int]),
+    "frk_dgemm": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_dbl, vp, c_int, vp, c_int, c_dbl, vp, c_int]),
     "frk_eval_basis_host": (c_int, [vp, vp, c_i64, vp, c_int, vp, vp, vp, p_i64]),
     "frk_grid_lookup_host": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, c_i64, vp]),
     "frk_quadform_host": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp]),

@@ -26,6 +26,7 @@ struct frk_ctx {
     // profiling
     bool profiling = false;
     double next_flops = 0, next_bytes = 0;          // algorithmic work of the next launch (FRK_WORK)
+    const char *next_tag = nullptr;                 // profile name of the next launch (default: the kernel's name)
     std::vector<frk_prof_rec> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
     std::map<std::string, frk_prof_stat> prof_stats;
@@ -57,15 +58,16 @@ void frk_set_error(const char *fmt, ...);
 #define FRK_LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
     do {                                                                                \
         cudaEvent_t _e1 = nullptr;                                                      \
-        if ((ctx)->profiling) { if (frk_prof_begin((ctx), #kernel, &_e1)) return 1; }   \
+        if ((ctx)->profiling) { if (frk_prof_begin((ctx), (ctx)->next_tag ? (ctx)->next_tag : #kernel, &_e1)) return 1; }   \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
         if (_e1) cudaEventRecord(_e1, (ctx)->stream);                                   \
         (ctx)->launches++;                                                              \
-        (ctx)->next_flops = (ctx)->next_bytes = 0;                                      \
+        (ctx)->next_flops = (ctx)->next_bytes = 0; (ctx)->next_tag = nullptr;               \
         FRK_CHECK_CUDA(cudaGetLastError());                                             \
     } while (0)
 
 // declare the ALGORITHMIC work (flops, bytes) of the next FRK_LAUNCH ("roofline accounting")
+#define FRK_TAG(ctx, tag) do { (ctx)->next_tag = (tag); } while (0)
 #define FRK_WORK(ctx, fl, by) do { (ctx)->next_flops = (double)(fl); (ctx)->next_bytes = (double)(by); } while (0)
 
 int frk_scratch(frk_ctx *ctx, size_t bytes, void **out);   // grow-only scratch buffer

@@ -1,26 +1,32 @@
-// Dense fp64 linear algebra for the r x r systems of the EM algorithm: one tensor-core GEMM
-// (C = beta*C + alpha*A*B', DMMA m8n8k4) and the blocked Cholesky / triangular inverse / chol2inv
-// built from it, plus the small element-wise and reduction kernels the E/M-steps need.
+// Dense fp64 linear algebra for the r x r systems of the EM algorithm.
 //
 // Reference semantics: Matrix::chol / chol2inv / determinant as used in R/SREfit.R:177-198
 // (.loglik.ind), :252-254 (.SRE.Estep.ind), :273 (Khat_inv), :475-478,517-524 (block-exponential
 // f_tau); R/linalgfns.R:21-36 (tr, diag2, logdet).
 //
-// There is no fp64 kind of tcgen05.mma, so fp64 tensor-core work on sm_100a is mma.sync DMMA.
-// Every product of the blocked algorithms is arranged as "NT" (both operands have the non-reduced
-// index contiguous in column-major storage) so one kernel with natural, coalesced 16-byte cp.async
-// loads serves potrf (panel solve + trailing SYRK), the triangular inverse (computed as L^-T, i.e.
-// in the transposed world) and the final L^-T L^-1 product.
+// There is no fp64 kind of tcgen05.mma, so fp64 tensor-core work on sm_100a is mma.sync DMMA
+// (m8n8k4).  One GEMM kernel, templated on which index of each operand is contiguous in memory,
+// with triangular k-range hints and a batch dimension, carries all the flops:
+//   potrf  two-level right-looking Cholesky: 64-wide inner steps (register-resident 64x64 potf2,
+//          thread-per-row panel trsm, rank-64 update inside the 256-wide outer panel) and one
+//          rank-256 lower SYRK per outer panel;
+//   potri  L^-1 by recursive doubling over the diagonal (64 -> 128 -> ... ; two batched GEMMs per
+//          level), then A^-1 = L^-T L^-1 as one triangular-aware product, mirrored.
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
 
 // ---------------------------------------------------------------------------------
-// GEMM NT
+// GEMM: C = beta*C + alpha * op(A) op(B),  op(A) M x K, op(B) K x N, C column-major.
+//   A_KC = false: A stored M x K column-major (m contiguous);  true: stored K x M (k contiguous)
+//   B_KC = false: B stored N x K column-major (n contiguous, "NT"); true: stored K x N (k contiguous)
 // ---------------------------------------------------------------------------------
 constexpr int BM = 128, BN = 64, BK = 16, GEMM_T = 256, STAGES = 3;
-constexpr int LDSA = BM + 4, LDSB = BN + 4;                 // = 4 (mod 16): conflict-free 8-byte fragment loads
-constexpr int STAGE_DOUBLES = BK * (LDSA + LDSB);
+constexpr int LDSA = BM + 4, LDSB = BN + 4;   // [k][m] layouts: = 4 (mod 16) -> conflict-free 8-byte fragment loads
+constexpr int LDSK = BK + 4;                  // [m][k] layouts: 20 -> the 32 fragment addresses cover the 16 bank pairs twice
+constexpr int A_STAGE = (BK * LDSA > BM * LDSK) ? BK * LDSA : BM * LDSK;
+constexpr int B_STAGE = (BK * LDSB > BN * LDSK) ? BK * LDSB : BN * LDSK;
+constexpr int STAGE_DOUBLES = A_STAGE + B_STAGE;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
 
 struct GemmArgs {
@@ -29,8 +35,10 @@ struct GemmArgs {
     const double *A; int lda;
     const double *B; int ldb;
     double *C; int ldc;
-    int lower;        // only tiles touching the lower triangle; elements above the diagonal are not stored
-    int kstart_m0;    // start the k loop at the tile's first row (A, B upper triangular: L^-T L^-1)
+    int lower;                       // only tiles touching the lower triangle; elements above the diagonal are not stored
+    int k_from_m, k_from_n, k_to_m;  // triangular operands: start k at the tile's first row / column, stop at its last row
+    long long sA, sB, sC;            // batch strides (elements) for blockIdx.z
+    int nbatch, M_last, K_last;      // the last batch entry may be ragged: its M and K
 };
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes) {
@@ -51,44 +59,81 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// rows x BK tile of a column-major operand (row index contiguous) -> smem [k][row]
-template <int ROWS, int LDS, bool ALIGN16>
+// ROWS x BK tile -> shared memory.  KC = false: operand element (row, k) at g[row + k*ld], smem [k][row] (ld LDS);
+// KC = true: element at g[k + row*ld], smem [row][k] (ld LDSK).
+template <int ROWS, int LDS, bool KC, bool ALIGN16>
 __device__ __forceinline__ void load_tile(double *s, const double *__restrict__ g, int ld, int row0, int nrows, int k0, int K) {
-    if (ALIGN16) {
-        constexpr int PER_COL = ROWS / 2;
+    if (!KC) {
+        if (ALIGN16) {
+            constexpr int PER_COL = ROWS / 2;
 #pragma unroll
-        for (int it = 0; it < (PER_COL * BK) / GEMM_T; it++) {
-            int idx = threadIdx.x + it * GEMM_T;
-            int kk = idx / PER_COL, r2 = (idx % PER_COL) * 2;
-            int row = row0 + r2, k = k0 + kk;
-            int bytes = (k < K) ? max(0, min(16, (nrows - row) * 8)) : 0;
-            const double *src = bytes ? g + row + (size_t)k * ld : g;
-            cp_async16(s + kk * LDS + r2, src, bytes);
+            for (int it = 0; it < (PER_COL * BK) / GEMM_T; it++) {
+                int idx = threadIdx.x + it * GEMM_T;
+                int kk = idx / PER_COL, r2 = (idx % PER_COL) * 2;
+                int row = row0 + r2, k = k0 + kk;
+                int bytes = (k < K) ? max(0, min(16, (nrows - row) * 8)) : 0;
+                const double *src = bytes ? g + row + (size_t)k * ld : g;
+                cp_async16(s + kk * LDS + r2, src, bytes);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (ROWS * BK) / GEMM_T; it++) {
+                int idx = threadIdx.x + it * GEMM_T;
+                int kk = idx / ROWS, r1 = idx % ROWS;
+                int row = row0 + r1, k = k0 + kk;
+                int bytes = (k < K && row < nrows) ? 8 : 0;
+                const double *src = bytes ? g + row + (size_t)k * ld : g;
+                cp_async8(s + kk * LDS + r1, src, bytes);
+            }
         }
     } else {
+        if (ALIGN16) {
+            constexpr int PER_ROW = BK / 2;
 #pragma unroll
-        for (int it = 0; it < (ROWS * BK) / GEMM_T; it++) {
-            int idx = threadIdx.x + it * GEMM_T;
-            int kk = idx / ROWS, r1 = idx % ROWS;
-            int row = row0 + r1, k = k0 + kk;
-            int bytes = (k < K && row < nrows) ? 8 : 0;
-            const double *src = bytes ? g + row + (size_t)k * ld : g;
-            cp_async8(s + kk * LDS + r1, src, bytes);
+            for (int it = 0; it < (ROWS * PER_ROW) / GEMM_T; it++) {
+                int idx = threadIdx.x + it * GEMM_T;
+                int r1 = idx / PER_ROW, k2 = (idx % PER_ROW) * 2;
+                int row = row0 + r1, k = k0 + k2;
+                int bytes = (row < nrows) ? max(0, min(16, (K - k) * 8)) : 0;
+                const double *src = bytes ? g + k + (size_t)row * ld : g;
+                cp_async16(s + r1 * LDSK + k2, src, bytes);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (ROWS * BK) / GEMM_T; it++) {
+                int idx = threadIdx.x + it * GEMM_T;
+                int r1 = idx / BK, kk = idx % BK;
+                int row = row0 + r1, k = k0 + kk;
+                int bytes = (k < K && row < nrows) ? 8 : 0;
+                const double *src = bytes ? g + k + (size_t)row * ld : g;
+                cp_async8(s + r1 * LDSK + kk, src, bytes);
+            }
         }
     }
 }
 
-template <bool ALIGN16>
-__global__ void __launch_bounds__(GEMM_T, 2) dgemm_nt_kernel(GemmArgs p) {
+template <bool A_KC, bool B_KC, bool ALIGN16>
+__global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double gsm[];
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     if (p.lower && n0 >= m0 + BM) return;
+    const int z = blockIdx.z;
+    const int M = (z == p.nbatch - 1) ? p.M_last : p.M;
+    const int K = (z == p.nbatch - 1) ? p.K_last : p.K;
+    if (m0 >= M) return;
+    const double *__restrict__ A = p.A + (size_t)z * p.sA;
+    const double *__restrict__ B = p.B + (size_t)z * p.sB;
+    double *__restrict__ Cm = p.C + (size_t)z * p.sC;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int wm = wid & 3, wn = wid >> 2;
     const int g = lane >> 2, tg = lane & 3;
 
-    int kbeg = p.kstart_m0 ? (m0 / BK) * BK : 0;
-    const int nk = (p.K - kbeg + BK - 1) / BK;
+    int kbeg = 0;
+    if (p.k_from_m) kbeg = max(kbeg, m0);
+    if (p.k_from_n) kbeg = max(kbeg, n0);
+    kbeg = (kbeg / BK) * BK;
+    const int kend = p.k_to_m ? min(K, m0 + BM) : K;
+    const int nk = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
 
     double acc[4][4][2];
 #pragma unroll
@@ -97,13 +142,13 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_nt_kernel(GemmArgs p) {
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto stageA = [&](int s) { return gsm + (size_t)s * STAGE_DOUBLES; };
-    auto stageB = [&](int s) { return gsm + (size_t)s * STAGE_DOUBLES + BK * LDSA; };
+    auto stageB = [&](int s) { return gsm + (size_t)s * STAGE_DOUBLES + A_STAGE; };
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
         if (s < nk) {
-            load_tile<BM, LDSA, ALIGN16>(stageA(s), p.A, p.lda, m0, p.M, kbeg + s * BK, p.K);
-            load_tile<BN, LDSB, ALIGN16>(stageB(s), p.B, p.ldb, n0, p.N, kbeg + s * BK, p.K);
+            load_tile<BM, LDSA, A_KC, ALIGN16>(stageA(s), A, p.lda, m0, M, kbeg + s * BK, kend);
+            load_tile<BN, LDSB, B_KC, ALIGN16>(stageB(s), B, p.ldb, n0, p.N, kbeg + s * BK, kend);
         }
         cp_async_commit();
     }
@@ -113,20 +158,22 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_nt_kernel(GemmArgs p) {
         {
             int nxt = kt + STAGES - 1;
             if (nxt < nk) {
-                load_tile<BM, LDSA, ALIGN16>(stageA(nxt % STAGES), p.A, p.lda, m0, p.M, kbeg + nxt * BK, p.K);
-                load_tile<BN, LDSB, ALIGN16>(stageB(nxt % STAGES), p.B, p.ldb, n0, p.N, kbeg + nxt * BK, p.K);
+                load_tile<BM, LDSA, A_KC, ALIGN16>(stageA(nxt % STAGES), A, p.lda, m0, M, kbeg + nxt * BK, kend);
+                load_tile<BN, LDSB, B_KC, ALIGN16>(stageB(nxt % STAGES), B, p.ldb, n0, p.N, kbeg + nxt * BK, kend);
             }
             cp_async_commit();
         }
-        const double *sA = stageA(kt % STAGES) + wm * 32 + g;
-        const double *sB = stageB(kt % STAGES) + wn * 32 + g;
+        const double *sA = stageA(kt % STAGES);
+        const double *sB = stageB(kt % STAGES);
 #pragma unroll
         for (int k4 = 0; k4 < BK / 4; k4++) {
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = sA[(k4 * 4 + tg) * LDSA + i * 8];
+            for (int i = 0; i < 4; i++)
+                a[i] = A_KC ? sA[(wm * 32 + i * 8 + g) * LDSK + k4 * 4 + tg] : sA[(k4 * 4 + tg) * LDSA + wm * 32 + i * 8 + g];
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = sB[(k4 * 4 + tg) * LDSB + j * 8];
+            for (int j = 0; j < 4; j++)
+                b[j] = B_KC ? sB[(wn * 32 + j * 8 + g) * LDSK + k4 * 4 + tg] : sB[(k4 * 4 + tg) * LDSB + wn * 32 + j * 8 + g];
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -139,7 +186,7 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_nt_kernel(GemmArgs p) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int row = m0 + wm * 32 + i * 8 + g;
-        if (row >= p.M) continue;
+        if (row >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
 #pragma unroll
@@ -147,7 +194,7 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_nt_kernel(GemmArgs p) {
                 const int colc = n0 + wn * 32 + j * 8 + tg * 2 + e;
                 if (colc >= p.N) continue;
                 if (p.lower && colc > row) continue;
-                double *c = p.C + row + (size_t)colc * p.ldc;
+                double *c = Cm + row + (size_t)colc * p.ldc;
                 double v = p.alpha * acc[i][j][e];
                 if (p.beta != 0.0) v += p.beta * (*c);
                 *c = v;
@@ -156,145 +203,210 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_nt_kernel(GemmArgs p) {
     }
 }
 
-static int launch_gemm(frk_ctx *ctx, const GemmArgs &a) {
-    if (a.M <= 0 || a.N <= 0) return 0;
+template <bool A_KC, bool B_KC>
+static int launch_gemm_t(frk_ctx *ctx, const GemmArgs &a, bool al) {
     static bool attr = false;
     if (!attr) {
-        FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_kernel<A_KC, B_KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_kernel<A_KC, B_KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         attr = true;
     }
-    dim3 grid((unsigned)cdiv(a.M, BM), (unsigned)cdiv(a.N, BN));
-    // algorithmic flops: full product 2MNK; lower-triangle SYRK M(M+1)K; upper-triangular Y Y' (lower half) ~ M^3/3
-    double fl = 2.0 * a.M * a.N * a.K;
-    if (a.lower) fl = a.kstart_m0 ? (double)a.M * a.M * a.M / 3.0 : (double)a.M * (a.M + 1.0) * a.K;
-    FRK_WORK(ctx, fl, 0);
-    bool al = ((uintptr_t)a.A % 16 == 0) && ((uintptr_t)a.B % 16 == 0) && (a.lda % 2 == 0) && (a.ldb % 2 == 0);
-    if (al) { FRK_LAUNCH(ctx, dgemm_nt_kernel<true>, grid, GEMM_T, GEMM_SMEM, a); }
-    else    { double f2 = ctx->next_flops; FRK_WORK(ctx, f2, 0); FRK_LAUNCH(ctx, dgemm_nt_kernel<false>, grid, GEMM_T, GEMM_SMEM, a); }
+    dim3 grid((unsigned)cdiv(a.M, BM), (unsigned)cdiv(a.N, BN), (unsigned)a.nbatch);
+    const double fl = ctx->next_flops;
+    const char *tg = ctx->next_tag;
+    if (al) { FRK_LAUNCH(ctx, (dgemm_kernel<A_KC, B_KC, true>), grid, GEMM_T, GEMM_SMEM, a); }
+    else    { FRK_WORK(ctx, fl, 0); FRK_TAG(ctx, tg); FRK_LAUNCH(ctx, (dgemm_kernel<A_KC, B_KC, false>), grid, GEMM_T, GEMM_SMEM, a); }
     return 0;
+}
+
+// flops: the ALGORITHMIC count of the operation this launch performs (passed by the caller)
+static int launch_gemm(frk_ctx *ctx, GemmArgs a, bool a_kc, bool b_kc, double flops, const char *tag = "dgemm_kernel") {
+    if (a.M <= 0 || a.N <= 0) return 0;
+    if (a.nbatch <= 0) { a.nbatch = 1; a.M_last = a.M; a.K_last = a.K; }
+    FRK_WORK(ctx, flops, 0);
+    FRK_TAG(ctx, tag);
+    bool al = ((uintptr_t)a.A % 16 == 0) && ((uintptr_t)a.B % 16 == 0) && (a.lda % 2 == 0) && (a.ldb % 2 == 0) &&
+              (a.sA % 2 == 0) && (a.sB % 2 == 0);
+    if (!a_kc && !b_kc) return launch_gemm_t<false, false>(ctx, a, al);
+    if (!a_kc && b_kc) return launch_gemm_t<false, true>(ctx, a, al);
+    if (a_kc && !b_kc) return launch_gemm_t<true, false>(ctx, a, al);
+    return launch_gemm_t<true, true>(ctx, a, al);
+}
+
+static GemmArgs gemm_args(int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb, double beta,
+                          double *C, int ldc) {
+    GemmArgs a{};
+    a.M = M; a.N = N; a.K = K; a.alpha = alpha; a.beta = beta; a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
+    a.nbatch = 1; a.M_last = M; a.K_last = K;
+    return a;
 }
 
 extern "C" int frk_dgemm_nt(frk_ctx *ctx, int M, int N, int K, double alpha, const double *d_A, int lda, const double *d_B,
                             int ldb, double beta, double *d_C, int ldc) {
     FRK_REQUIRE(ctx && d_A && d_B && d_C, "frk_dgemm_nt: NULL argument");
     FRK_REQUIRE(lda >= M && ldb >= N && ldc >= M && K >= 0, "frk_dgemm_nt: bad leading dimension");
-    GemmArgs a{M, N, K, alpha, beta, d_A, lda, d_B, ldb, d_C, ldc, 0, 0};
-    return launch_gemm(ctx, a);
+    return launch_gemm(ctx, gemm_args(M, N, K, alpha, d_A, lda, d_B, ldb, beta, d_C, ldc), false, false, 2.0 * M * N * K);
+}
+
+// general layouts (exported for the tests): transa/transb != 0 -> the operand is stored with k contiguous
+extern "C" int frk_dgemm(frk_ctx *ctx, int transa, int transb, int M, int N, int K, double alpha, const double *d_A, int lda,
+                         const double *d_B, int ldb, double beta, double *d_C, int ldc) {
+    FRK_REQUIRE(ctx && d_A && d_B && d_C, "frk_dgemm: NULL argument");
+    FRK_REQUIRE(lda >= (transa ? K : M) && ldb >= (transb ? K : N) && ldc >= M && K >= 0, "frk_dgemm: bad leading dimension");
+    return launch_gemm(ctx, gemm_args(M, N, K, alpha, d_A, lda, d_B, ldb, beta, d_C, ldc), transa != 0, transb != 0, 2.0 * M * N * K);
 }
 
 // ---------------------------------------------------------------------------------
-// diagonal blocks: Cholesky of an NB x NB block and inverse of its factor, one CTA each
+// 64 x 64 building blocks (one thread per row, the row lives in registers)
 // ---------------------------------------------------------------------------------
-constexpr int NB = 64;
-constexpr int DLD = NB + 1;
-constexpr size_t DIAG_SMEM = 2 * NB * DLD * sizeof(double);
+constexpr int NB = 64;     // inner block
+constexpr int NBO = 256;   // outer panel of potrf
 
-static int diag_attrs() {
-    static bool done = false;
-    if (!done) {
-        extern __global__ void potf2_inv_kernel(double *, int, int, int, double *, double *);
-        extern __global__ void trinv_blocks_kernel(const double *, int, int, double *);
-        FRK_CHECK_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-        FRK_CHECK_CUDA(cudaFuncSetAttribute(trinv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-        done = true;
-    }
-    return 0;
-}
+// Each row of a 64 x 64 block is held by SPLIT = 4 adjacent lanes, lane h owning the columns k = 4*kk + h
+// (16 registers); 256 threads per block.  The interleaved ownership makes the four lanes of a row read four
+// consecutive doubles of shared memory (one wavefront, broadcast across rows) and keeps all lanes busy.
+constexpr int SPLIT = 4, NBQ = NB / SPLIT, BLK_T = NB * SPLIT;
 
-// status[0] += sum(log(diag L)); status[1] = first failing (1-based) column, 0 if ok
-__global__ void __launch_bounds__(256) potf2_inv_kernel(double *__restrict__ A, int lda, int kb, int col_offset,
-                                                        double *__restrict__ invL /*NB x NB, ld NB*/, double *__restrict__ status) {
-    extern __shared__ __align__(16) double dsm[];
-    double *a = dsm, *x = dsm + NB * DLD;
-    __shared__ int bad;
-    const int tid = threadIdx.x;
-    if (tid == 0) bad = 0;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        int i = idx % NB, j = idx / NB;
-        a[i * DLD + j] = (i < kb && j < kb && j <= i) ? A[i + (size_t)j * lda] : (i == j ? 1.0 : 0.0);
+// Cholesky of the kb x kb diagonal block at A (lower triangle, in place).
+// status[0] += sum(log(diag L)); status[1] = first failing (1-based) column, 0 if ok.
+// The elimination runs in square-root-free (LDL') form so that the per-column critical path is one reciprocal
+// (taken by the lane that owns the diagonal, before the barrier) and one multiply: a[k] -= (a_ij / d_j) col_j[k]
+// with the UNSCALED column j; the factor is scaled at the end, l_ij = a_ij / sqrt(d_j).
+__global__ void __launch_bounds__(BLK_T) potf2_kernel(double *__restrict__ A, int lda, int kb, int col_offset, double *__restrict__ status) {
+    __shared__ double colbuf[2][NB];
+    __shared__ double rdiag[2];
+    __shared__ double rsq[NB];
+    __shared__ double slog[BLK_T / 32];
+    const int i = threadIdx.x / SPLIT, h = threadIdx.x % SPLIT;
+    double a[NBQ];
+#pragma unroll
+    for (int kk = 0; kk < NBQ; kk++) {
+        const int k = kk * SPLIT + h;
+        a[kk] = (i < kb && k < kb && k <= i) ? A[i + (size_t)k * lda] : (k == i ? 1.0 : 0.0);
     }
-    __syncthreads();
-    for (int j = 0; j < kb; j++) {
-        const double djj = a[j * DLD + j];
-        if (!(djj > 0.0)) {          // not positive definite (also catches NaN)
-            if (tid == 0 && !bad) bad = col_offset + j + 1;
-            break;                    // uniform: every thread reads the same djj
+    int bad = 0;
+#pragma unroll
+    for (int jj = 0; jj < NBQ; jj++) {                 // columns j = 4*jj + hh; a[jj] is lane hh's entry of column j
+#pragma unroll 1
+        for (int hh = 0; hh < SPLIT; hh++) {
+            const int j = jj * SPLIT + hh;
+            if (h == hh) {
+                const double v = a[jj];                // unscaled column j (rows i < j hold don't-care values)
+                colbuf[j & 1][i] = v;
+                if (i == j) rdiag[j & 1] = (v > 0.0) ? __drcp_rn(v) : -1.0;     // also catches NaN
+            }
+            __syncthreads();
+            const double rd = rdiag[j & 1];
+            if (rd < 0.0) { bad = j + 1; break; }      // uniform: not positive definite
+            const double c = colbuf[j & 1][i] * rd;
+            const double *cb = &colbuf[j & 1][h];
+            if (h > hh) a[jj] -= c * cb[jj * SPLIT];
+#pragma unroll
+            for (int kk = jj + 1; kk < NBQ; kk++) a[kk] -= c * cb[kk * SPLIT];   // entries with k > i are never read
         }
-        const double d = sqrt(djj);
-        __syncthreads();
-        if (tid == 0) a[j * DLD + j] = d;
-        for (int i = j + 1 + tid; i < kb; i += 256) a[i * DLD + j] = a[i * DLD + j] / d;
-        __syncthreads();
-        // trailing update of the lower triangle: a[i][k] -= a[i][j]*a[k][j], j<k<=i
-        const int nrem = kb - j - 1;
-        for (int idx = tid; idx < nrem * nrem; idx += 256) {
-            int i = j + 1 + idx / nrem, k = j + 1 + idx % nrem;
-            if (k <= i) a[i * DLD + k] -= a[i * DLD + j] * a[k * DLD + j];
-        }
-        __syncthreads();
+        if (bad) break;
     }
-    __syncthreads();
     if (bad) {
-        if (tid == 0 && status[1] == 0.0) status[1] = (double)bad;
+        if (threadIdx.x == 0 && status[1] == 0.0) status[1] = (double)(col_offset + bad);
         return;
     }
-    // write L back (lower triangle only)
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        int i = idx % NB, j = idx / NB;
-        if (i < kb && j < kb && j <= i) A[i + (size_t)j * lda] = a[i * DLD + j];
-    }
-    // inverse: thread t < NB solves L x = e_t by forward substitution; x[k][t]
-    if (tid < NB) {
-        const int t = tid;
-        for (int i = 0; i < NB; i++) {
-            double s = (i == t) ? 1.0 : 0.0;
-            for (int k = 0; k < i; k++) s -= a[i * DLD + k] * x[k * DLD + t];
-            x[i * DLD + t] = (i < t) ? 0.0 : s / a[i * DLD + i];
+    // d_i sits on the diagonal (lane h = i % 4 of row i): scale column j by 1/sqrt(d_j)
+    double lg = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < NBQ; kk++) {
+        if (kk * SPLIT + h == i) {
+            const double sq = sqrt(a[kk]);
+            rsq[i] = 1.0 / sq;
+            a[kk] = sq;
+            lg = (i < kb) ? log(sq) : 0.0;
         }
     }
     __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        int i = idx % NB, j = idx / NB;
-        invL[i + j * NB] = (i < kb && j < kb) ? x[i * DLD + j] : 0.0;
+#pragma unroll
+    for (int kk = 0; kk < NBQ; kk++) {
+        const int k = kk * SPLIT + h;
+        if (i < kb && k < kb && k <= i) A[i + (size_t)k * lda] = (k == i) ? a[kk] : a[kk] * rsq[k];
     }
-    if (tid == 0) {
-        double s = 0.0;
-        for (int j = 0; j < kb; j++) s += log(a[j * DLD + j]);
-        status[0] += s;
+    lg = warp_sum(lg);
+    if ((threadIdx.x & 31) == 0) slog[threadIdx.x >> 5] = lg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < BLK_T / 32; w++) t += slog[w];
+        status[0] += t;
     }
 }
 
-// batched inverse of all diagonal blocks of a factor L (for frk_potri)
-__global__ void __launch_bounds__(256) trinv_blocks_kernel(const double *__restrict__ L, int ld, int r, double *__restrict__ invL_all) {
-    extern __shared__ __align__(16) double dsm[];
-    double *a = dsm, *x = dsm + NB * DLD;
-    const int tid = threadIdx.x, o = blockIdx.x * NB, kb = min(NB, r - o);
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        int i = idx % NB, j = idx / NB;
-        a[i * DLD + j] = (i < kb && j < kb && j <= i) ? L[(o + i) + (size_t)(o + j) * ld] : (i == j ? 1.0 : 0.0);
+// Panel solve X L' = P in place: P is Mp x kb (rows below the diagonal block), L the kb x kb lower factor.
+// Right-looking per row: x_c *= 1/L[c][c] (broadcast to the row's lanes by shuffle); x_k -= x_c L[k][c] for k > c.
+// IDENT = true solves against the identity instead (P = I): row t of the result is column t of L^-1, which is
+// written transposed -> out = L^-1 (batched over blockIdx.x: the diagonal blocks of a factor).
+template <bool IDENT>
+__global__ void __launch_bounds__(BLK_T) trsm_rows_kernel(const double *__restrict__ L, int ldl, double *__restrict__ P, int ldp,
+                                                          int Mp, int kb, int r) {
+    __shared__ double Lt[NB][NB + 4];     // Lt[c][k] = L[k][c]
+    __shared__ double rd[NB];
+    const int t = threadIdx.x / SPLIT, h = threadIdx.x % SPLIT;
+    if (IDENT) {   // diagonal block blockIdx.x of the factor
+        const int o = blockIdx.x * NB;
+        kb = min(NB, r - o);
+        L += o + (size_t)o * ldl;
+        P += o + (size_t)o * ldp;
     }
-    __syncthreads();
-    if (tid < NB) {
-        const int t = tid;
-        for (int i = 0; i < NB; i++) {
-            double s = (i == t) ? 1.0 : 0.0;
-            for (int k = 0; k < i; k++) s -= a[i * DLD + k] * x[k * DLD + t];
-            x[i * DLD + t] = (i < t) ? 0.0 : s / a[i * DLD + i];
+    {   // all 16 loads of L in flight before the first store
+        double v[NB * NB / BLK_T];
+#pragma unroll
+        for (int q = 0; q < NB * NB / BLK_T; q++) {
+            const int idx = threadIdx.x + q * BLK_T, k = idx % NB, c = idx / NB;
+            v[q] = (k < kb && c < kb && c <= k) ? L[k + (size_t)c * ldl] : (k == c ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int q = 0; q < NB * NB / BLK_T; q++) {
+            const int idx = threadIdx.x + q * BLK_T, k = idx % NB, c = idx / NB;
+            Lt[c][k] = v[q];
+            if (k == c) rd[c] = __drcp_rn(v[q]);
         }
     }
     __syncthreads();
-    double *out = invL_all + (size_t)blockIdx.x * NB * NB;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        int i = idx % NB, j = idx / NB;
-        out[i + j * NB] = (i < kb && j < kb) ? x[i * DLD + j] : 0.0;
+    const int row = IDENT ? t : blockIdx.x * NB + t;
+    const bool live = IDENT ? (t < kb) : (row < Mp);
+    double x[NBQ];
+#pragma unroll
+    for (int kk = 0; kk < NBQ; kk++) {
+        const int c = kk * SPLIT + h;
+        x[kk] = IDENT ? (c == t ? 1.0 : 0.0) : ((live && c < kb) ? P[row + (size_t)c * ldp] : 0.0);
     }
-}
-
-__global__ void set_identity_kernel(int r, double *__restrict__ Y) {
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)r * r; idx += (int64_t)gridDim.x * blockDim.x) {
-        int i = (int)(idx % r), j = (int)(idx / r);
-        Y[idx] = (i == j) ? 1.0 : 0.0;
+    const int lane_base = (threadIdx.x & 31) & ~(SPLIT - 1);
+#pragma unroll
+    for (int cc = 0; cc < NBQ; cc++) {                 // columns c = 4*cc + hh
+#pragma unroll 1
+        for (int hh = 0; hh < SPLIT; hh++) {
+            const int c = cc * SPLIT + hh;
+            double xc = x[cc] * rd[c];
+            if (h == hh) x[cc] = xc;
+            xc = __shfl_sync(0xffffffffu, xc, lane_base + hh);
+            const double *lt = &Lt[c][h];
+            if (h > hh) x[cc] -= xc * lt[cc * SPLIT];
+#pragma unroll
+            for (int kk = cc + 1; kk < NBQ; kk++) x[kk] -= xc * lt[kk * SPLIT];
+        }
+    }
+    if (IDENT) {
+        // x_(row t)[c] = (L^-1)[c][t]: stage through shared memory so that row t is stored with coalesced accesses
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < NBQ; kk++) Lt[t][kk * SPLIT + h] = x[kk];       // Lt[t][c] = (L^-1)[c][t]
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < NB * NB; idx += BLK_T) {
+            const int rr = idx % NB, cc = idx / NB;                             // element (rr, cc) of L^-1
+            if (rr < kb && cc < kb) P[rr + (size_t)cc * ldp] = Lt[cc][rr];
+        }
+    } else if (live) {
+#pragma unroll
+        for (int kk = 0; kk < NBQ; kk++) {
+            const int c = kk * SPLIT + h;
+            if (c < kb) P[row + (size_t)c * ldp] = x[kk];
+        }
     }
 }
 
@@ -317,27 +429,32 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(int r, double *__rest
 
 extern "C" int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet) {
     FRK_REQUIRE(ctx && d_A && r > 0, "frk_potrf: bad argument");
-    const int nb = (int)cdiv(r, NB);
-    if (int rc = diag_attrs()) return rc;
-    // scratch: W (r x NB, ld r) | invL (NB x NB) ; status lives in d_small
-    void *raw = nullptr;
-    if (int rc = frk_scratch(ctx, ((size_t)r * NB + NB * NB) * sizeof(double), &raw)) return rc;
-    double *W = (double *)raw, *invL = W + (size_t)r * NB;
     double *status = ctx->d_small + 4096 - 8;
     FRK_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(double), ctx->stream));
-    for (int k = 0; k < nb; k++) {
-        const int o = k * NB, kb = std::min(NB, r - o), Mp = r - o - kb;
-        FRK_LAUNCH(ctx, potf2_inv_kernel, 1, 256, DIAG_SMEM, d_A + o + (size_t)o * r, r, kb, o, invL, status);
-        if (Mp > 0) {
-            // W = P * invL'   (panel solve P L^-T)
-            GemmArgs g1{Mp, kb, kb, 1.0, 0.0, d_A + (o + kb) + (size_t)o * r, r, invL, NB, W, r, 0, 0};
-            if (int rc = launch_gemm(ctx, g1)) return rc;
-            FRK_CHECK_CUDA(cudaMemcpy2DAsync(d_A + (o + kb) + (size_t)o * r, (size_t)r * sizeof(double), W, (size_t)r * sizeof(double),
-                                             (size_t)Mp * sizeof(double), kb, cudaMemcpyDeviceToDevice, ctx->stream));
-            // A22 -= W W'  (lower triangle)
-            double *A22 = d_A + (o + kb) + (size_t)(o + kb) * r;
-            GemmArgs g2{Mp, Mp, kb, -1.0, 1.0, W, r, W, r, A22, r, 1, 0};
-            if (int rc = launch_gemm(ctx, g2)) return rc;
+    const size_t ld = (size_t)r;
+    for (int J = 0; J < r; J += NBO) {
+        const int Jend = std::min(r, J + NBO);
+        for (int o = J; o < Jend; o += NB) {
+            const int kb = std::min(NB, r - o), below = r - o - kb;
+            double *Ajj = d_A + o + o * ld;
+            FRK_LAUNCH(ctx, potf2_kernel, 1, BLK_T, 0, Ajj, r, kb, o, status);
+            if (below <= 0) continue;
+            double *P = d_A + (o + kb) + o * ld;                       // below x kb panel
+            FRK_WORK(ctx, (double)below * kb * kb, 0);
+            FRK_LAUNCH(ctx, trsm_rows_kernel<false>, (unsigned)cdiv(below, NB), BLK_T, 0, Ajj, r, P, r, below, kb, r);
+            const int ncols = Jend - (o + kb);                         // remaining columns of the outer panel
+            if (ncols > 0) {                                           // A[o+kb.., o+kb..Jend) -= P P[0:ncols,:]'
+                GemmArgs g = gemm_args(below, ncols, kb, -1.0, P, r, P, r, 1.0, d_A + (o + kb) + (o + kb) * ld, r);
+                g.lower = 1;
+                if (int rc = launch_gemm(ctx, g, false, false, 2.0 * below * ncols * kb - (double)ncols * ncols * kb, "dgemm_kernel[potrf inner rank-64]")) return rc;
+            }
+        }
+        const int below = r - Jend, kw = Jend - J;
+        if (below > 0) {                                               // trailing lower SYRK with the whole outer panel
+            const double *P = d_A + Jend + J * ld;
+            GemmArgs g = gemm_args(below, below, kw, -1.0, P, r, P, r, 1.0, d_A + Jend + Jend * ld, r);
+            g.lower = 1;
+            if (int rc = launch_gemm(ctx, g, false, false, (double)below * (below + 1.0) * kw, "dgemm_kernel[potrf outer SYRK]")) return rc;
         }
     }
     FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned, status, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -347,31 +464,39 @@ extern "C" int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet) {
     return 0;
 }
 
+// chol2inv.  d_work receives X = L^-1 (lower triangular, zeros above the diagonal).
 extern "C" int frk_potri(frk_ctx *ctx, int r, const double *d_L, double *d_Ainv, double *d_work) {
     FRK_REQUIRE(ctx && d_L && d_Ainv && d_work && r > 0, "frk_potri: bad argument");
-    const int nb = (int)cdiv(r, NB);
-    if (int rc = diag_attrs()) return rc;
-    void *raw = nullptr;
-    if (int rc = frk_scratch(ctx, ((size_t)r * NB + (size_t)nb * NB * NB) * sizeof(double), &raw)) return rc;
-    double *T = (double *)raw, *invL = T + (size_t)r * NB;
-    double *Y = d_work;
-    FRK_LAUNCH(ctx, trinv_blocks_kernel, nb, 256, DIAG_SMEM, d_L, r, r, invL);
-    FRK_LAUNCH(ctx, set_identity_kernel, ctx->sm_count * 8, 256, 0, r, Y);
-    // Y = L^-T by blocked forward substitution on the rows of L^-1, stored transposed (all products NT)
-    for (int j = 0; j < nb; j++) {
-        const int o = j * NB, kb = std::min(NB, r - o), Mp = o + kb, Nn = r - Mp;
-        GemmArgs g1{Mp, kb, kb, 1.0, 0.0, Y + (size_t)o * r, r, invL + (size_t)j * NB * NB, NB, T, r, 0, 0};
-        if (int rc = launch_gemm(ctx, g1)) return rc;
-        if (Nn > 0) {
-            GemmArgs g2{Mp, Nn, kb, -1.0, 1.0, T, r, d_L + Mp + (size_t)o * r, r, Y + (size_t)Mp * r, r, 0, 0};
-            if (int rc = launch_gemm(ctx, g2)) return rc;
+    FRK_REQUIRE(d_work != d_Ainv && d_work != d_L, "frk_potri: work must not alias L or the output");
+    const size_t ld = (size_t)r;
+    double *X = d_work, *T = d_Ainv;
+    FRK_CHECK_CUDA(cudaMemsetAsync(X, 0, ld * r * sizeof(double), ctx->stream));
+    const int nblk = (int)cdiv(r, NB);
+    FRK_WORK(ctx, (double)nblk * NB * NB * NB / 3.0, 0);
+    FRK_LAUNCH(ctx, trsm_rows_kernel<true>, nblk, BLK_T, 0, d_L, r, X, r, 0, 0, r);
+    // X21 = -X22 (L21 X11), doubling the block size; T (scratch) lives in the output buffer at X21's position
+    for (long long b = NB; b < r; b *= 2) {
+        const int npairs = (int)cdiv(r - b, 2 * b);                   // pairs whose second block is non-empty
+        if (npairs <= 0) break;
+        const int b2_last = (int)std::min<long long>(b, r - (2LL * (npairs - 1) + 1) * b);
+        const long long stride = 2 * b * (1 + (long long)ld);
+        const size_t off21 = (size_t)b, off22 = (size_t)b * (1 + ld);
+        const double pairs_full = npairs - 1.0;
+        {   // T = L21 X11   (X11 lower: k from the tile's first column)
+            GemmArgs g = gemm_args((int)b, (int)b, (int)b, 1.0, d_L + off21, r, X, r, 0.0, T + off21, r);
+            g.k_from_n = 1; g.sA = g.sB = g.sC = stride; g.nbatch = npairs; g.M_last = b2_last; g.K_last = (int)b;
+            if (int rc = launch_gemm(ctx, g, false, true, (pairs_full * b + b2_last) * (double)b * b, "dgemm_kernel[potri L21 X11]")) return rc;
         }
-        FRK_CHECK_CUDA(cudaMemcpy2DAsync(Y + (size_t)o * r, (size_t)r * sizeof(double), T, (size_t)r * sizeof(double),
-                                         (size_t)Mp * sizeof(double), kb, cudaMemcpyDeviceToDevice, ctx->stream));
+        {   // X21 = -X22 T  (X22 lower: k up to the tile's last row)
+            GemmArgs g = gemm_args((int)b, (int)b, (int)b, -1.0, X + off22, r, T + off21, r, 0.0, X + off21, r);
+            g.k_to_m = 1; g.sA = g.sB = g.sC = stride; g.nbatch = npairs; g.M_last = b2_last; g.K_last = b2_last;
+            if (int rc = launch_gemm(ctx, g, false, true, (pairs_full * b * b + (double)b2_last * b2_last) * (double)b, "dgemm_kernel[potri X22 T]")) return rc;
+        }
     }
-    // A^-1 = L^-T L^-1 = Y Y'   (Y upper triangular: sum over k >= max(i,j))
-    GemmArgs g3{r, r, r, 1.0, 0.0, Y, r, Y, r, d_Ainv, r, 1, 1};
-    if (int rc = launch_gemm(ctx, g3)) return rc;
+    // A^-1 = X' X (lower triangle; X lower -> k >= max(row, col)), then mirror
+    GemmArgs g3 = gemm_args(r, r, r, 1.0, X, r, X, r, 0.0, d_Ainv, r);
+    g3.lower = 1; g3.k_from_m = 1; g3.k_from_n = 1;
+    if (int rc = launch_gemm(ctx, g3, true, true, (double)r * r * r / 3.0, "dgemm_kernel[potri X'X]")) return rc;
     dim3 grid((unsigned)cdiv(r, 32), (unsigned)cdiv(r, 32));
     FRK_LAUNCH(ctx, mirror_lower_kernel, grid, 256, 0, r, d_Ainv);
     return 0;
@@ -544,22 +669,27 @@ extern "C" int frk_block_scatter(frk_ctx *ctx, int r, double *d_A, int ni, const
     return 0;
 }
 
-// x = Y' b for upper-triangular Y (= L^-T left in d_work by frk_potri): x = L^-1 b, i.e.
-// (rDinv %*% S) %*% solve(R) of .loglik.ind (R/SREfit.R:211).  One warp per column of Y.
-__global__ void __launch_bounds__(256) upper_tmulv_kernel(int r, const double *__restrict__ Y, const double *__restrict__ b,
-                                                          double *__restrict__ x) {
-    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+// x = X b for lower-triangular X (= L^-1 left in d_work by frk_potri), i.e. x = L^-1 b:
+// (rDinv %*% S) %*% solve(R) of .loglik.ind (R/SREfit.R:211).  Column-split partial sums, then a fixed-order sum.
+__global__ void __launch_bounds__(128) lower_mulv_partial_kernel(int r, const double *__restrict__ X, const double *__restrict__ b,
+                                                                 double *__restrict__ part) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int jchunk = (r + SYMV_SPLIT - 1) / SYMV_SPLIT;
+    const int j0 = blockIdx.y * jchunk, j1 = min(r, j0 + jchunk);
     if (i >= r) return;
-    const double *y = Y + (size_t)i * r;
     double s = 0.0;
-    for (int k = lane; k <= i; k += 32) s += y[k] * __ldg(b + k);
-    s = warp_sum(s);
-    if (lane == 0) x[i] = s;
+    const int jend = min(j1, i + 1);
+    for (int j = j0; j < jend; j++) s += X[i + (size_t)j * r] * __ldg(b + j);
+    part[(size_t)blockIdx.y * r + i] = s;
 }
 
-extern "C" int frk_upper_tmulv(frk_ctx *ctx, int r, const double *d_Y, const double *d_b, double *d_x) {
-    FRK_REQUIRE(ctx && d_Y && d_b && d_x && r > 0, "frk_upper_tmulv: bad argument");
-    FRK_LAUNCH(ctx, upper_tmulv_kernel, (unsigned)cdiv((int64_t)r * 32, 256), 256, 0, r, d_Y, d_b, d_x);
+extern "C" int frk_lower_mulv(frk_ctx *ctx, int r, const double *d_X, const double *d_b, double *d_x) {
+    FRK_REQUIRE(ctx && d_X && d_b && d_x && r > 0, "frk_lower_mulv: bad argument");
+    void *raw = nullptr;
+    if (int rc = frk_scratch(ctx, (size_t)SYMV_SPLIT * r * sizeof(double), &raw)) return rc;
+    dim3 grid((unsigned)cdiv(r, 128), SYMV_SPLIT);
+    FRK_LAUNCH(ctx, lower_mulv_partial_kernel, grid, 128, 0, r, d_X, d_b, (double *)raw);
+    FRK_LAUNCH(ctx, symv_final_kernel, (unsigned)cdiv(r, 128), 128, 0, r, (const double *)raw, d_x);
     return 0;
 }
 

@@ -33,7 +33,7 @@ class Device:
     # ---- memory (torch-owned) ------------------------------------------------------
     def empty(self, n, dtype="f8"):
         t = self.torch
-        dt = {"f8": t.float64, "i4": t.int32, "i8": t.int64}[dtype]
+        dt = {"f8": t.float64, "i4": t.int32, "i8": t.int64, "u1": t.uint8}[dtype]
         return t.empty(int(n), dtype=dt, device=self.tdev)
 
     def zeros(self, n, dtype="f8"):

@@ -308,8 +308,9 @@ def _gram(mdl: SREModel, alpha: np.ndarray, sigma2fs: float):
     dev, r = mdl.dev, mdl.r
     call("frk_memset0", dev.ctx, dev.ptr(mdl._acc), (r * r + r + 2) * 8)
     a, ap = _alpha_ptr(alpha)
-    call("frk_gram_rhs", dev.ctx, mdl.m, r, dev.ptr(mdl.S.rowptr), dev.ptr(mdl.S.col), dev.ptr(mdl.S.val), dev.ptr(mdl.Z),
-         dev.ptr(mdl.X), mdl.p, ap, dev.ptr(mdl.Ve), dev.ptr(mdl.Vfs), float(sigma2fs), dev.ptr(mdl._acc))
+    call("frk_gram_rhs_bucketed", dev.ctx, mdl.m, r, dev.ptr(mdl.S.rowptr), dev.ptr(mdl.S.col), dev.ptr(mdl.S.val),
+         *mdl.S.buckets(dev), dev.ptr(mdl.Z), dev.ptr(mdl.X), mdl.p, ap, dev.ptr(mdl.Ve), dev.ptr(mdl.Vfs),
+         float(sigma2fs), dev.ptr(mdl._acc))
     dev.allreduce_(mdl._acc)                                       # the ONE large exchange per EM iteration
     return mdl._acc
 
@@ -326,8 +327,8 @@ def _posterior(mdl: SREModel, alpha, sigma2fs, Q_out, Sig_out, mu_out):
     call("frk_potrf", dev.ctx, r, dev.ptr(mdl._w1), C.byref(logdetQ))
     call("frk_potri", dev.ctx, r, dev.ptr(mdl._w1), dev.ptr(Sig_out), dev.ptr(mdl._w2))
     call("frk_symv", dev.ctx, r, dev.ptr(Sig_out), dev.ptr(b), dev.ptr(mu_out))
-    # || (rDinv S) solve(R) ||^2 with solve(R) = L^-T left in _w2 by potri   (R/SREfit.R:211)
-    call("frk_upper_tmulv", dev.ctx, r, dev.ptr(mdl._w2), dev.ptr(b), dev.ptr(mdl._vec))
+    # || (rDinv S) solve(R) ||^2 with solve(R)' = L^-1 left in _w2 by potri   (R/SREfit.R:211)
+    call("frk_lower_mulv", dev.ctx, r, dev.ptr(mdl._w2), dev.ptr(b), dev.ptr(mdl._vec))
     nrm = C.c_double(0.0)
     call("frk_dot", dev.ctx, r, dev.ptr(mdl._vec), dev.ptr(mdl._vec), C.byref(nrm))
     sc = dev.download(acc[r * r + r:r * r + r + 2])
@@ -458,8 +459,8 @@ def _mstep(mdl: SREModel, lam=0.0, known_sigma2fs=None) -> None:
     est = known_sigma2fs is None
     sigma2fs_new = sigma2fs if est else float(known_sigma2fs)
     # Omega_diag1 = rowSums((S R_eta')^2) = s_j'(S_eta + mu mu')s_j = q_j + t_j^2,  t = S mu_eta     :332-334
-    call("frk_quadform_spmv", dev.ctx, mdl.m, r, dev.ptr(mdl.S.rowptr), dev.ptr(mdl.S.col), dev.ptr(mdl.S.val),
-         dev.ptr(mdl.S_eta), dev.ptr(mdl.mu_eta), dev.ptr(mdl._q), dev.ptr(mdl._t))
+    call("frk_quadform_spmv_bucketed", dev.ctx, mdl.m, r, dev.ptr(mdl.S.rowptr), dev.ptr(mdl.S.col), dev.ptr(mdl.S.val),
+         *mdl.S.buckets(dev), dev.ptr(mdl.S_eta), dev.ptr(mdl.mu_eta), dev.ptr(mdl._q), dev.ptr(mdl._t))
 
     def gls_and_J(s2, mode=0):
         s = _mstep_sums(mdl, s2, mode)
@@ -554,8 +555,8 @@ def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True):
     sd = dev.empty(max(nloc, 1))
     if obs_fs or s2 == 0:
         Sig, mue = mdl.S_eta, mdl.mu_eta
-        call("frk_quadform_spmv", dev.ctx, nloc, r, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
-             dev.ptr(Sig), dev.ptr(mue), dev.ptr(q), dev.ptr(smu))
+        call("frk_quadform_spmv_bucketed", dev.ctx, nloc, r, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
+             *mdl.S0.buckets(dev), dev.ptr(Sig), dev.ptr(mue), dev.ptr(q), dev.ptr(smu))
         call("frk_predict_finalize", dev.ctx, nloc, 0, s2, dev.ptr(q), dev.ptr(smu), dev.ptr(xa), vp(None), vp(None),
              vp(None), dev.ptr(mu), dev.ptr(var), dev.ptr(sd))
     else:
@@ -564,8 +565,8 @@ def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True):
         mue = dev.empty(r)
         _posterior(mdl, mdl.alphahat, s2, Q, Sig, mue)
         del Q
-        call("frk_quadform_spmv", dev.ctx, nloc, r, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
-             dev.ptr(Sig), dev.ptr(mue), dev.ptr(q), dev.ptr(smu))
+        call("frk_quadform_spmv_bucketed", dev.ctx, nloc, r, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
+             *mdl.S0.buckets(dev), dev.ptr(Sig), dev.ptr(mue), dev.ptr(q), dev.ptr(smu))
         # A = diag(C' Ve^-1 C), ytil = C' Ve^-1 (Z - X alpha)
         A = dev.zeros(max(nloc, 1))
         ytil = dev.zeros(max(nloc, 1))

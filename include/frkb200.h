@@ -147,6 +147,25 @@ int frk_gram_rhs(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int 
                  const double *h_alpha, const double *d_ve, const double *d_vfs, double sigma2fs,
                  double *d_acc);
 
+/* ---- row buckets: group the rows of a CSR basis matrix by their last column index (the highest finest-
+ * resolution basis function in the row's support).  Built once per matrix (SRE()); lets the Gram and
+ * quadratic-form kernels stage the few columns a bucket touches in shared memory.
+ *   d_bptr[ncols+1], d_perm[n] : rows of bucket k are d_perm[d_bptr[k] .. d_bptr[k+1])
+ *   d_nU[ncols], d_ucol[ncols*64] : the columns bucket k touches (d_nU[k] > 64: not staged, direct path)
+ *   d_lid[nnz] : for every stored entry, its position in its bucket's column list (one byte)            */
+int frk_csr_bucket_rows(frk_ctx *ctx, int64_t n, const int *d_rowptr, const int *d_col, int ncols,
+                        int *d_perm, int *d_bptr, int *d_ucol, int *d_nU, unsigned char *d_lid);
+/* frk_gram_rhs / frk_quadform_spmv with row buckets (same results up to fp64 summation order) */
+int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int *d_col,
+                          const double *d_val, const int *d_perm, const int *d_bptr, const int *d_ucol,
+                          const int *d_nU, const unsigned char *d_lid, const double *d_z,
+                          const double *d_X, int p, const double *h_alpha, const double *d_ve,
+                          const double *d_vfs, double sigma2fs, double *d_acc);
+int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const int *d_rowptr, const int *d_col,
+                               const double *d_val, const int *d_perm, const int *d_bptr,
+                               const int *d_ucol, const int *d_nU, const unsigned char *d_lid,
+                               const double *d_M, const double *d_mu, double *d_q, double *d_t);
+
 /* ---- gather-based sparse quadratic form + SpMV: R/SREutils.R:286-300 (.batch_compute_var,
  *      rowSums((S0 Cov) * S0)), R/SREfit.R:332-334 (Omega_diag1), S %*% mu_eta.
  * q_i = s_i' M s_i (M symmetric r x r column-major, ld r), t_i = s_i' mu.  Either output
@@ -201,11 +220,11 @@ int frk_xalpha(frk_ctx *ctx, int64_t n, int p, const double *d_X, const double *
  * Fails (status != 0) if A is not positive definite.                                       */
 int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet);
 /* chol2inv: given L from frk_potrf in d_L (left intact), writes the full symmetric inverse of
- * A to d_Ainv.  d_work: r*r doubles of scratch (receives L^-T).                             */
+ * A to d_Ainv.  d_work: r*r doubles of scratch (receives L^-1, lower triangular).                             */
 int frk_potri(frk_ctx *ctx, int r, const double *d_L, double *d_Ainv, double *d_work);
-/* x = Y' b for the upper-triangular Y = L^-T that frk_potri leaves in d_work, i.e. x = L^-1 b:
+/* x = X b for the lower-triangular X = L^-1 that frk_potri leaves in d_work, i.e. x = L^-1 b:
  * (rDinv %*% S) %*% solve(R) in .loglik.ind (R/SREfit.R:211)                                  */
-int frk_upper_tmulv(frk_ctx *ctx, int r, const double *d_Y, const double *d_b, double *d_x);
+int frk_lower_mulv(frk_ctx *ctx, int r, const double *d_X, const double *d_b, double *d_x);
 /* y = A x for symmetric full-storage A */
 int frk_symv(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double *d_y);
 /* out = mirror(upper triangle of G) + B   (Q_eta = S'D^-1 S + K^-1, R/SREfit.R:252); B may be NULL */
@@ -230,6 +249,10 @@ int frk_block_gather_outer(frk_ctx *ctx, int r, const double *d_A, const double 
  * blocked factorisations are built from (exported for tests and the fp64 peak probe).       */
 int frk_dgemm_nt(frk_ctx *ctx, int M, int N, int K, double alpha, const double *d_A, int lda,
                  const double *d_B, int ldb, double beta, double *d_C, int ldc);
+
+/* general operand layouts: transa / transb != 0 -> that operand is stored with k contiguous (K x M / K x N) */
+int frk_dgemm(frk_ctx *ctx, int transa, int transb, int M, int N, int K, double alpha, const double *d_A,
+              int lda, const double *d_B, int ldb, double beta, double *d_C, int ldc);
 
 /* ---- host-buffer entry points (what the R .Call shim binds; H2D/D2H inside) ------------ */
 /* eval_basis on host coordinates -> host CSR.  Call with h_col == NULL to get nnz only.     */

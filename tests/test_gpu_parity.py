@@ -137,7 +137,7 @@ def _dense_case(r, seed):
     return A @ A.T + r * np.eye(r)
 
 
-@pytest.mark.parametrize("r", [1, 7, 64, 65, 200, 819])
+@pytest.mark.parametrize("r", [1, 7, 64, 65, 200, 256, 257, 640, 819, 1000, 2048])
 def test_chol2inv(dev, r):
     import ctypes as C
     from frk_b200._lib import call, vp
@@ -171,6 +171,76 @@ def test_dgemm_nt(dev):
         call("frk_dgemm_nt", dev.ctx, M, N, K, 0.5, dev.ptr(dA), M, dev.ptr(dB), N, -2.0, dev.ptr(dC), M)
         out = dev.download(dC).reshape(N, M).T
         np.testing.assert_allclose(out, 0.5 * A @ B.T - 2.0 * Cc, rtol=1e-12, atol=1e-12)
+
+
+def test_dgemm_layouts(dev):
+    """all four operand layouts of the DMMA GEMM (used by the recursive triangular inverse)."""
+    from frk_b200._lib import call
+    rng = np.random.default_rng(1)
+    for (M, N, K) in [(128, 64, 16), (131, 67, 35), (300, 200, 130), (64, 64, 64)]:
+        A = rng.standard_normal((M, K)); B = rng.standard_normal((K, N)); Cc = rng.standard_normal((M, N))
+        for ta in (0, 1):
+            for tb in (0, 1):
+                hA = A.T if ta else A            # stored K x M (k contiguous) when ta
+                hB = B if tb else B.T            # stored K x N (k contiguous) when tb, else N x K
+                dA, dB, dC = dev.upload(hA), dev.upload(hB), dev.upload(Cc)
+                call("frk_dgemm", dev.ctx, ta, tb, M, N, K, 1.5, dev.ptr(dA), hA.shape[0], dev.ptr(dB), hB.shape[0], 0.25,
+                     dev.ptr(dC), M)
+                out = dev.download(dC).reshape(N, M).T
+                np.testing.assert_allclose(out, 1.5 * A @ B + 0.25 * Cc, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("btype,nres", [("bisquare", 3), ("Gaussian", 1)])
+def test_gram_and_quadform_kernels(dev, btype, nres):
+    """S'D^-1 S, S'D^-1 rho and diag(S M S') -- direct and bucketed kernels -- against SciPy.  The Gaussian basis gives
+    dense rows (k = r > 40, union > 64), which exercises the in-kernel direct path of the bucketed kernels."""
+    import frk_b200 as F
+    from frk_b200._lib import call, vp
+    rng = np.random.default_rng(12)
+    xy, z = readme_points(4000, seed=6)
+    ob = O.auto_basis(O.plane(), xy, regular=1, nres=nres, type=btype)
+    So = O.normalise_rows(O.eval_basis(ob, xy)).tocsr()
+    Sg = F.eval_basis_device(_mk_basis(F, ob), xy, dev, normalise=True)
+    m, r = So.shape
+    ve = rng.uniform(0.1, 0.5, m); vfs = rng.uniform(0.5, 1.5, m); s2 = 0.37
+    X = np.column_stack([np.ones(m), xy[:, 0]]); alpha = np.array([0.3, -0.2])
+    d = s2 * vfs + ve
+    rho = z - X @ alpha
+    G_ref = (So.T @ sp.diags(1 / d) @ So).toarray()
+    b_ref = So.T @ (rho / d)
+    dz, dX, dve, dvfs = dev.upload(z), dev.upload(X), dev.upload(ve), dev.upload(vfs)
+    bk = Sg.buckets(dev)
+    pm = dev.download(Sg._buckets["perm"], m); bp = dev.download(Sg._buckets["bptr"], r + 1)
+    assert sorted(pm.tolist()) == list(range(m)) and bp[0] == 0 and bp[-1] == m
+    for bucketed in (False, True):
+        acc = dev.zeros(r * r + r + 2)
+        args = [dev.ctx, m, r, dev.ptr(Sg.rowptr), dev.ptr(Sg.col), dev.ptr(Sg.val)]
+        if bucketed:
+            args += bk
+        args += [dev.ptr(dz), dev.ptr(dX), 2, vp(alpha.ctypes.data), dev.ptr(dve), dev.ptr(dvfs), s2, dev.ptr(acc)]
+        call("frk_gram_rhs_bucketed" if bucketed else "frk_gram_rhs", *args)
+        a = dev.download(acc)
+        G = a[:r * r].reshape(r, r).T
+        G = np.triu(G) + np.triu(G, 1).T
+        assert np.all(np.tril(a[:r * r].reshape(r, r).T, -1) == 0)
+        np.testing.assert_allclose(G, G_ref, rtol=1e-11, atol=1e-12 * abs(G_ref).max())
+        np.testing.assert_allclose(a[r * r:r * r + r], b_ref, rtol=1e-10, atol=1e-12 * abs(b_ref).max())
+        np.testing.assert_allclose(a[r * r + r], np.sum(rho * rho / d), rtol=1e-12)
+        np.testing.assert_allclose(a[r * r + r + 1], np.sum(np.log(d)), rtol=1e-12)
+    Mm = _dense_case(r, 3)
+    mu = rng.standard_normal(r)
+    q_ref = np.asarray(So.multiply(So @ Mm).sum(axis=1)).ravel()
+    t_ref = So @ mu
+    dM, dmu = dev.upload(Mm), dev.upload(mu)
+    for bucketed in (False, True):
+        q, t = dev.zeros(m), dev.zeros(m)
+        args = [dev.ctx, m, r, dev.ptr(Sg.rowptr), dev.ptr(Sg.col), dev.ptr(Sg.val)]
+        if bucketed:
+            args += bk
+        args += [dev.ptr(dM), dev.ptr(dmu), dev.ptr(q), dev.ptr(t)]
+        call("frk_quadform_spmv_bucketed" if bucketed else "frk_quadform_spmv", *args)
+        np.testing.assert_allclose(dev.download(q), q_ref, rtol=1e-11)
+        np.testing.assert_allclose(dev.download(t), t_ref, rtol=1e-10, atol=1e-13)
 
 
 def _setup_plane(F, m=1000, seed=1, nres=2, hetero=False, K_type="block-exponential", cellsize=0.02):
