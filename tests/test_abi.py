@@ -1,0 +1,69 @@
+"""The drop-in boundary: libfrkb200.so loads and exports exactly the symbols include/frkb200.h declares; the ctypes
+binding lists every one of them; without a GPU the library refuses to create a context (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "frkb200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(frk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from frk_b200._lib import LIB_PATH
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\sT\s+(frk_[a-z0-9_]+)", out))
+    decl = _declared()
+    assert len(decl) >= 50
+    missing = [s for s in decl if s not in exported]
+    assert not missing, f"declared in include/frkb200.h but not exported: {missing}"
+    extra = sorted(exported - set(decl))
+    assert not extra, f"exported but undeclared: {extra}"
+
+
+def test_ctypes_binding_covers_the_header():
+    from frk_b200._lib import SIGNATURES, lib
+    assert sorted(SIGNATURES) == _declared()
+    assert lib.frk_abi_version() == 1
+
+
+def test_header_is_plain_c():
+    """the boundary is a C ABI: the header must compile as C (no C++/torch types in the signatures)."""
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_every_entry_point_cites_the_reference():
+    src = open(HEADER).read()
+    assert len(re.findall(r"R/[A-Za-z]+\.R:\d+", src)) >= 40
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from frk_b200._lib import FRKError, call, last_error, vp
+    ctx = vp()
+    with pytest.raises(FRKError, match="no CUDA device|no CPU fallback"):
+        call("frk_ctx_create", 0, vp(None), C.byref(ctx))
+    import frk_b200
+    with pytest.raises(FRKError, match="no CPU fallback"):
+        frk_b200.get_device()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under frk_b200/ may import or execute it."""
+    for dp, _, fs in os.walk(os.path.join(ROOT, "frk_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("frk_oracle", "oracle") or "import" not in "".join(
+                    ln for ln in txt.splitlines() if "oracle" in ln), f"{f} references the oracle"

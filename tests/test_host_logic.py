@@ -1,0 +1,92 @@
+"""Host-side logic of the frk_b200 mirror (no GPU needed): optimisers, formula parsing, grid construction, basis placement,
+row partitioning -- checked against the oracle's independent copies and against SciPy."""
+import numpy as np
+import pytest
+import scipy.optimize as so
+
+import frk_b200 as F
+from frk_b200.optim import nmmin, zeroin
+from frk_b200.sre import _parse_formula
+from oracle import frk_oracle as O
+
+
+def test_nmmin_matches_oracle_port_and_finds_minimum():
+    f = lambda x: (x[0] - 1.3) ** 2 + 0.5 * (x[1] + 0.7) ** 4 + 0.1 * x[0] * x[1]
+    a = nmmin(f, [0.2, 0.1], maxit=500, reltol=1e-10)
+    b = O.nmmin(f, [0.2, 0.1], maxit=500, reltol=1e-10)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2]
+    ref = so.minimize(f, [0.2, 0.1], method="Nelder-Mead", options=dict(xatol=1e-10, fatol=1e-12))
+    np.testing.assert_allclose(a[0], ref.x, atol=1e-4)
+    # 1-D, the way .update_K calls it (maxit=100, reltol=1e-4)
+    g = lambda t: np.inf if t[0] <= 1e-10 else (np.log(t[0]) - 1.0) ** 2
+    x, fx, n, fail = nmmin(g, [0.3], maxit=100, reltol=1e-4)
+    assert abs(x[0] - np.e) < 0.05 and fail == 0 and n <= 100
+
+
+def test_zeroin_matches_oracle_port_and_brentq():
+    f = lambda s: 0.5 * (1.0 / (s + 0.3) - 1.7)
+    r1 = zeroin(f, 1e-3, 10.0)
+    assert r1 == O.zeroin(f, 1e-3, 10.0)
+    assert abs(r1 - so.brentq(f, 1e-3, 10.0)) < 2e-4            # uniroot's default tol = eps^0.25
+    with pytest.raises(RuntimeError, match="opposite sign"):
+        zeroin(f, 5.0, 10.0)
+
+
+def test_parse_formula():
+    assert _parse_formula("z ~ 1") == ("z", [], True)
+    assert _parse_formula("co2avgret ~ lat + 1") == ("co2avgret", ["lat"], True)
+    assert _parse_formula("z ~ -1 + x + y") == ("z", ["x", "y"], False)
+
+
+def test_partition_rows_covers_everything():
+    for n in (0, 1, 7, 10004569):
+        for w in (1, 2, 3, 8):
+            parts = [F.partition_rows(n, w, r) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_auto_BAUs_and_auto_basis_match_oracle():
+    rng = np.random.default_rng(3)
+    xy = rng.uniform(0, 1, (200, 2)) * [2.0, 1.0]
+    gb = F.auto_BAUs(F.plane(), cellsize=0.05, data=F.SpatialPointsDataFrame(xy, {}))
+    ob = O.auto_BAUs_plane(xy, cellsize=0.05)
+    assert np.array_equal(gb.xgrid, ob.xgrid) and np.array_equal(gb.ygrid, ob.ygrid)
+    assert np.array_equal(gb.cell2bau(), ob.cell2bau())
+    assert np.array_equal(gb.centroids(), ob.centroids())
+    for t in ("bisquare", "Matern32"):
+        for reg in (1, 2):
+            a = F.auto_basis(F.plane(), xy, regular=reg, nres=2, type=t)
+            b = O.auto_basis(O.plane(), xy, regular=reg, nres=2, type=t)
+            assert np.array_equal(a.loc, b.loc) and np.array_equal(a.scale, b.scale) and np.array_equal(a.res, b.res)
+    a = F.auto_basis(F.real_line(), xy[:, :1], regular=6, nres=2)
+    b = O.auto_basis(O.real_line(), xy[:, :1], regular=6, nres=2)
+    assert np.array_equal(a.loc, b.loc) and np.array_equal(a.scale, b.scale)
+    assert [D.shape for D in F.BuildD(a)] == [(6, 6), (12, 12)]
+
+
+def test_local_basis_argument_checks_mirror_the_reference():
+    """R/basisfns.R:118-145: same conditions, same messages."""
+    with pytest.raises(ValueError, match="same as the number of manifold dimensions"):
+        F.local_basis(F.plane(), np.zeros((3, 1)), np.ones(3))
+    with pytest.raises(ValueError, match="as many scale parameters as centroids"):
+        F.local_basis(F.plane(), np.zeros((3, 2)), np.ones(2))
+    with pytest.raises(ValueError, match="greater than zero"):
+        F.local_basis(F.plane(), np.zeros((3, 2)), np.array([1.0, 0.0, 1.0]))
+    with pytest.raises(ValueError, match="Only one basis can be multiresolution"):
+        b1 = F.local_basis(F.real_line(), np.zeros((2, 1)), np.ones(2), res=[1, 2])
+        F.TensorP(b1, b1)
+
+
+def test_SRE_argument_checks_run_before_any_device_work():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the GPU tests")
+    xy = np.random.default_rng(0).uniform(size=(10, 2))
+    data = F.SpatialPointsDataFrame(xy, {"z": xy[:, 0], "std": np.ones(10)})
+    gb = F.auto_BAUs(F.plane(), cellsize=0.1, data=data)
+    basis = F.auto_basis(F.plane(), xy, nres=1)
+    with pytest.raises(F.FRKError, match="no CPU fallback"):       # no device -> loud failure, never a CPU path
+        F.SRE("z ~ 1", data, basis, gb, est_error=False)

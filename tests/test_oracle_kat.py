@@ -1,0 +1,175 @@
+"""Pins the CPU oracle to every known-answer test the reference's own tests hold for the hot path
+ and to independent algebra.  Citations are tests/testthat/<file>:<line> in the reference."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from cases import readme_points
+from oracle import frk_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_kat1_gaussian_basis_at_distance_one():
+    """test_basis.R:23-24: G2(s=(0,1)) with mu=(1,1), sigma=1 is identical to dnorm(1)*sqrt(2*pi) = exp(-0.5); same on the real line."""
+    G2 = O.local_basis(O.plane(), np.array([[1.0, 1.0]]), [1.0], "Gaussian")
+    assert O.eval_basis_dense(G2, np.array([[0.0, 1.0]]))[0, 0] == math.exp(-0.5)
+    G1 = O.local_basis(O.real_line(), np.array([[1.0]]), [1.0], "Gaussian")
+    assert O.eval_basis_dense(G1, np.array([[0.0]]))[0, 0] == math.exp(-0.5)
+
+
+def test_kat2_value_one_at_centroids():
+    """test_basis.R:51-52,62-63: diag(eval_basis(G, centroids)) == 1 and the result is sparse."""
+    xy, _ = readme_points(300, 2)
+    for t in O.BASIS_TYPES:
+        G = O.auto_basis(O.plane(), xy, nres=2, type=t)
+        S = O.eval_basis(G, G.loc)
+        assert sp.issparse(S)
+        assert np.all(S.diagonal() == 1.0)
+
+
+def test_kat3_sphere_distances():
+    """test_domains.R:25-36: unit-sphere distance (-90,0)<->(90,0) identical to pi; space-time identical to sqrt(pi^2 + 2^2)."""
+    d = O.dist_sphere(np.array([[-90.0, 0.0]]), np.array([[90.0, 0.0]]), R=1.0)
+    assert d[0, 0] == math.pi
+    dt = O.gc_dist_time(np.array([[-90.0, 0.0, 0.0]]), np.array([[90.0, 0.0, 2.0]]), R=1.0)
+    assert dt[0, 0] == math.sqrt(math.pi ** 2 + 2 ** 2)
+
+
+def test_kat4_distR_vs_pairwise():
+    """test_other.R:114-120: distR(x, x) agrees with stats::dist (sum of differences < 1e-12)."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((40, 3))
+    D = O.distR(x, x)
+    ref = np.sqrt(((x[:, None, :] - x[None, :, :]) ** 2).sum(-1))
+    assert abs(D - ref).sum() < 1e-12
+
+
+def test_kat6_linalg_identities():
+    """test_linalg.R:4-25: tr, diag2(A,A) == diag(A %*% A), chol2inv / cholesky helpers == solve(A) on a 2x2."""
+    A = np.array([[2.0, 0.5], [0.5, 1.0]])
+    assert O.tr(A) == 3.0
+    assert np.allclose(O.diag2(A, A), np.diag(A @ A))
+    R = O.chol_upper(A)
+    assert np.allclose(R.T @ R, A)
+    assert np.allclose(O.chol2inv(R), np.linalg.inv(A))
+    assert np.isclose(O.logdet(R), np.log(np.linalg.det(A)))
+
+
+def test_kat7_isea3h_counts():
+    """data/isea3h.rda: centroids per resolution 0..5 are 12/32/92/272/812/2432; nres=3 from isea3h_lo=2 gives 1176 basis
+    functions (R/basisfns.R:191)."""
+    z = np.load(os.path.join(GOLD, "isea3h_centroids.npz"))
+    assert np.bincount(z["res"]).tolist() == [12, 32, 92, 272, 812, 2432]
+    isea = {r: np.column_stack([z["lon"][z["res"] == r], z["lat"][z["res"] == r]]) for r in range(6)}
+    G = O.auto_basis(O.sphere(), np.array([[0.0, 0.0], [1.0, 1.0]]), nres=3, isea3h=isea, isea3h_lo=2)
+    assert G.n == 1176 == 92 + 272 + 812
+
+
+def test_kat8_tensor_basis_count_and_order():
+    """test_basis.R:119: 10 x 3 tensor basis has 30 functions; column order is space-fastest (R/basisfns.R:821-822)."""
+    G1 = O.local_basis(O.real_line(), np.arange(10.0)[:, None], np.full(10, 2.0), "bisquare")
+    G2 = O.local_basis(O.real_line(), np.arange(3.0)[:, None], np.full(3, 2.0), "bisquare")
+    T = O.TensorP_Basis(G1, G2)
+    assert T.n == 30
+    s = np.array([[3.2, 1.1], [7.0, 0.3]])
+    S = O.eval_basis(T, s).toarray()
+    S1 = O.eval_basis_dense(G1, s[:, :1]); S2 = O.eval_basis_dense(G2, s[:, 1:])
+    for jt in range(3):
+        assert np.array_equal(S[:, jt * 10:(jt + 1) * 10], S1 * S2[:, [jt]])
+
+
+def test_structural_counts_from_reference_tests():
+    """test_other.R:11-22 analogue (seq/by grid construction): 1 x 1 BAUs over [0,10]^2 with no buffer give 11 x 11 centroids;
+    auto_basis(plane, nres=3) has 9+81+729 = 819 functions, regular=2 gives 3276 (R/basisfns.R:458-464)."""
+    b = O.auto_BAUs_plane(np.array([[0.0, 0.0], [10.0, 10.0]]), cellsize=1.0, xlims=(0, 10), ylims=(0, 10))
+    assert b.nx == 11 and b.ny == 11 and np.array_equal(b.xgrid, np.arange(11.0))
+    u = np.array([[0.0, 0.0], [1.0, 1.0]])
+    assert O.auto_basis(O.plane(), u, nres=3).n == 819
+    assert O.auto_basis(O.plane(), u, nres=3, regular=2).n == 3276
+
+
+def test_fast_eval_matches_literal_eval():
+    xy, _ = readme_points(500, 3)
+    G = O.auto_basis(O.plane(), xy, nres=3)
+    A = O.eval_basis(G, xy).tocsr(); B = O.eval_basis_fast(G, xy).tocsr()
+    A.sort_indices(); B.sort_indices()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+
+
+def _c1(K_type="unstructured", hetero=False, m=300, nres=1, cellsize=0.1):
+    xy, z = readme_points(m, 1)
+    std = np.full(m, 0.5) if not hetero else 0.3 + 0.4 * np.random.default_rng(101).uniform(size=m)
+    ob = O.auto_basis(O.plane(), xy, regular=1, nres=nres)
+    ba = O.auto_BAUs_plane(xy, cellsize=cellsize)
+    uo, means, _ = O.bin_mean(O.points_to_BAUs(xy, ba), np.column_stack([z, std]))
+    return O.SRE(ob, ba.centroids(), np.ones(ba.n), uo, means[:, 0], means[:, 1], K_type=K_type)
+
+
+def test_kat5_predict_var_equals_diag_of_joint_cov():
+    """test_SRE.R:46-52: predict var == diag(Cov) for both obs_fs modes.  Here: the closed form used for point data equals the
+    literal (r+N)-dimensional joint solve of R/SREpredict.R:308-333, and obs_fs=TRUE equals direct conditioning."""
+    M = _c1(hetero=True)
+    O.SRE_fit(M, n_EM=4, tol=0.0)
+    assert M.sigma2fshat > 0
+    mu_c, var_c, _ = O.predict(M, obs_fs=False)
+    mu_g, var_g, _ = O.predict_general(M)
+    np.testing.assert_allclose(var_c, var_g, rtol=1e-9)
+    np.testing.assert_allclose(mu_c, mu_g, rtol=1e-9, atol=1e-11)
+
+
+def test_loglik_equals_dense_gaussian_density():
+    """Independent algebra: the Woodbury log-likelihood (.loglik.ind) equals the dense N(X alpha, S K S' + D) log-density."""
+    M = _c1(hetero=True)
+    O.SRE_fit(M, n_EM=2, tol=0.0)
+    S = M.S.toarray()
+    Sig = S @ M.Khat @ S.T + np.diag(M.sigma2fshat * M.Vfs + M.Ve)
+    res = M.Z - M.X @ M.alphahat
+    _, ld = np.linalg.slogdet(Sig)
+    dense = -0.5 * len(res) * math.log(2 * math.pi) - 0.5 * ld - 0.5 * res @ np.linalg.solve(Sig, res)
+    np.testing.assert_allclose(O.loglik(M), dense, rtol=1e-10)
+
+
+def test_em_monotone_and_golden_trace():
+    """EM never decreases the log-likelihood for the unstructured K; traces match the committed oracle fixture
+    (tests/golden/c1_oracle.json, written by tools/make_golden.py -- pins the oracle against drift)."""
+    gold = json.load(open(os.path.join(GOLD, "c1_oracle.json")))
+    xy, z = readme_points(1000, 1)
+    for key, g in gold.items():
+        K, het = key.split("|")
+        het = het.endswith("True")
+        std = np.full(1000, 0.5) if not het else 0.3 + 0.4 * np.random.default_rng(101).uniform(size=1000)
+        ob = O.auto_basis(O.plane(), xy, regular=1, nres=2)
+        ba = O.auto_BAUs_plane(xy, cellsize=0.02)
+        uo, means, _ = O.bin_mean(O.points_to_BAUs(xy, ba), np.column_stack([z, std]))
+        M = O.SRE(ob, ba.centroids(), np.ones(ba.n), uo, means[:, 0], means[:, 1], K_type=K)
+        O.SRE_fit(M, n_EM=6, tol=0.0)
+        np.testing.assert_allclose(M.info_fit["llk"], g["llk"], rtol=1e-9)
+        np.testing.assert_allclose(M.sigma2fshat, g["sigma2fs"], rtol=1e-7, atol=1e-12)
+        if K == "unstructured":
+            assert np.all(np.diff(M.info_fit["llk"]) > -1e-8)
+
+
+def test_grid_index_matches_nearest_centre():
+    """sp::over on SpatialPixels: a point belongs to the cell whose centre is nearest; outside -> NA."""
+    b = O.auto_BAUs_plane(np.zeros((1, 2)), cellsize=0.25, xlims=(0, 2), ylims=(0, 1))
+    rng = np.random.default_rng(1)
+    xy = np.column_stack([rng.uniform(-0.1, 2.1, 2000), rng.uniform(-0.1, 1.1, 2000)])
+    got = O.points_to_BAUs(xy, b)
+    cen = b.centroids()
+    d = abs(xy[:, None, :] - cen[None, :, :]).max(-1)
+    inside = d.min(1) < 0.125
+    assert np.array_equal(got[inside], d.argmin(1)[inside])
+    assert np.all(got[d.min(1) > 0.125 + 1e-12] == -1)
+
+
+def test_bin_mean_groups_and_means():
+    bau = np.array([3, 1, 3, -1, 1, 7, 3], dtype=np.int32)
+    cols = np.arange(14.0).reshape(7, 2)
+    u, mth, c = O.bin_mean(bau, cols)
+    assert u.tolist() == [1, 3, 7] and c.tolist() == [2, 3, 1]
+    np.testing.assert_allclose(mth, [[(2 + 8) / 2, (3 + 9) / 2], [(0 + 4 + 12) / 3, (1 + 5 + 13) / 3], [10, 11]])
