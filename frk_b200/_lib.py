@@ -34,6 +34,9 @@ p_i64 = C.POINTER(C.c_int64)
 p_dbl = C.POINTER(C.c_double)
 p_int = C.POINTER(C.c_int)
 
+ALLREDUCE_FN = C.CFUNCTYPE(c_int, vp, vp, c_i64, c_int, c_int)
+OBJECTIVE_FN = C.CFUNCTYPE(c_dbl, vp, c_int, p_dbl)
+
 # name -> (restype, argtypes); must list every symbol include/frkb200.h declares
 SIGNATURES = {
     "frk_abi_version": (c_int, []),
@@ -94,6 +97,19 @@ SIGNATURES = {
     "frk_block_gather_outer": (c_int, [vp, c_int, vp, vp, c_int, vp, vp]),
     "frk_dgemm_nt": (c_int, [vp, c_int, c_int, c_int, c_dbl, vp, c_int, vp, c_int, c_dbl, vp, c_int]),
     "frk_dgemm": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_dbl, vp, c_int, vp, c_int, c_dbl, vp, c_int]),
+    "frk_model_create": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, ALLREDUCE_FN, vp, C.POINTER(vp)]),
+    "frk_model_create_host": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+    "frk_model_destroy": (c_int, [vp]),
+    "frk_model_set_blocks": (c_int, [vp, c_int, vp, C.POINTER(vp)]),
+    "frk_model_init": (c_int, [vp]),
+    "frk_model_em_fit": (c_int, [vp, c_int, c_dbl, c_int, c_int, vp, vp, c_int, c_dbl, vp, p_int]),
+    "frk_model_loglik": (c_int, [vp, p_dbl]),
+    "frk_model_get": (c_int, [vp, C.c_char_p, vp]),
+    "frk_model_set": (c_int, [vp, C.c_char_p, vp]),
+    "frk_model_slot_device": (c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+    "frk_model_predict": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp, vp]),
+    "frk_optim_nelder_mead": (c_int, [OBJECTIVE_FN, vp, c_int, vp, c_int, c_dbl, vp, p_dbl, p_int, p_int]),
+    "frk_optim_zeroin": (c_int, [OBJECTIVE_FN, vp, c_dbl, c_dbl, p_dbl]),
     "frk_eval_basis_host": (c_int, [vp, vp, c_i64, vp, c_int, vp, vp, vp, p_i64]),
     "frk_grid_lookup_host": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, c_i64, vp]),
     "frk_quadform_host": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp]),

@@ -1,0 +1,775 @@
+// frk_model: the device-resident SRE object and the EM / prediction control flow above the kernels.
+//
+// Reference: R/SRE.R:704-731 (.EM_initialise), R/SREfit.R:78-160 (.EM_fit), :174-220 (.loglik.ind), :232-260
+// (.SRE.Estep.ind), :263-438 (.SRE.Mstep.ind), :441-694 (.update_K / .regularise_K), R/SREpredict.R:243-375
+// (.SRE.predict_EM), R/SREutils.R:245-305 (.batch_compute_var).  stats::optim(method = "Nelder-Mead") and
+// stats::uniroot, which the reference runs on the host around the data-parallel objective functions
+// (R/SREfit.R:386-388, :618-621), are restated here from the published algorithms (R src/appl/optim.c nmmin,
+// R src/library/stats/src/zeroin.c) so that one C-ABI call -- what the R `.Call` shim binds -- runs a whole
+// SRE.fit(method = "EM") with every m-, N- or r^2-sized operation on the GPU and nothing but scalars on the host.
+//
+// Arithmetic that the reference computes twice per iteration with identical inputs is computed once:
+// .loglik.ind and .SRE.Estep.ind both form S'D^-1 S and factor K^-1 + S'D^-1 S (the reference's two K^-1 are
+// the same chol2inv(chol(Khat))), and the M-step's Khat_inv factorisation supplies the next log|K|.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <limits>
+
+namespace {
+
+constexpr int MAXP_M = 4;
+
+struct Buckets {
+    int *perm = nullptr, *bptr = nullptr, *ucol = nullptr, *nU = nullptr;
+    unsigned char *lid = nullptr;
+};
+
+struct Block {                    // one resolution of the block-exponential K
+    int ni = 0, ix0 = 0;
+    int *d_ix = nullptr;
+    double *D = nullptr, *eta2 = nullptr, *Ki = nullptr, *Kinv = nullptr, *work = nullptr;
+    double D01 = 0.0;
+};
+
+}  // namespace
+
+struct frk_model {
+    frk_ctx *ctx = nullptr;
+    int64_t m = 0;
+    int r = 0, p = 0;
+    // S (m x r CSR), data vectors: device; owned when created from host buffers
+    const int *rowptr = nullptr, *col = nullptr;
+    const double *val = nullptr, *Z = nullptr, *X = nullptr, *Ve = nullptr, *Vfs = nullptr;
+    bool owned = false;
+    Buckets bk;
+    // r-sized slots (device), replicated on every rank
+    double *mu_eta = nullptr, *S_eta = nullptr, *Q_eta = nullptr, *Khat = nullptr, *Khat_inv = nullptr;
+    // scratch
+    double *acc = nullptr, *w1 = nullptr, *w2 = nullptr, *vec = nullptr, *t = nullptr, *q = nullptr;
+    // host state
+    double alpha[MAXP_M] = {0, 0, 0, 0};
+    double sigma2fs = 0.0, logdetK = 0.0;
+    double m_total = 0.0, Ve0 = 0.0, Vfs0 = 0.0;
+    bool homoscedastic = false, all_vfs_zero = false, initialised = false;
+    // block-exponential K
+    std::vector<Block> blocks;
+    double max_l = 0.0;
+    std::vector<double> taus, omegas;
+    // multi-rank reduction hook
+    frk_allreduce_fn allreduce = nullptr;
+    void *user = nullptr;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+#define RC(expr) do { if (int _rc = (expr)) return _rc; } while (0)
+
+template <typename T>
+int dalloc(frk_model *M, T **out, size_t n) {
+    void *p = nullptr;
+    FRK_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 8)));
+    M->allocs.push_back(p);
+    *out = (T *)p;
+    return 0;
+}
+
+int reduce_dev(frk_model *M, double *d_buf, int64_t n) {
+    if (!M->allreduce) return 0;
+    FRK_REQUIRE(M->allreduce(M->user, d_buf, n, 1, 0) == 0, "all-reduce callback failed (device buffer)");
+    return 0;
+}
+
+int reduce_host(frk_model *M, double *h_buf, int64_t n, int op) {
+    if (!M->allreduce) return 0;
+    FRK_REQUIRE(M->allreduce(M->user, h_buf, n, 0, op) == 0, "all-reduce callback failed (host buffer)");
+    return 0;
+}
+
+// sum, sum of squares about `shift`, min, max over ALL ranks' rows
+int global_stats(frk_model *M, const double *d_x, double shift, double out[4]) {
+    RC(frk_vec_stats(M->ctx, M->m, d_x, shift, out));
+    if (M->allreduce) {
+        double s[2] = {out[0], out[1]}, mn[1] = {-out[2]}, mx[1] = {out[3]};
+        RC(reduce_host(M, s, 2, 0));
+        RC(reduce_host(M, mn, 1, 1));
+        RC(reduce_host(M, mx, 1, 1));
+        out[0] = s[0]; out[1] = s[1]; out[2] = -mn[0]; out[3] = mx[0];
+    }
+    return 0;
+}
+
+// p x p solve A x = b (Gaussian elimination with partial pivoting; A column-major); p <= 4
+int solve_small(int p, const double *A, const double *b, double *x) {
+    double a[MAXP_M][MAXP_M + 1];
+    for (int i = 0; i < p; i++) { for (int j = 0; j < p; j++) a[i][j] = A[i + p * j]; a[i][p] = b[i]; }
+    for (int c = 0; c < p; c++) {
+        int piv = c;
+        for (int i = c + 1; i < p; i++) if (std::fabs(a[i][c]) > std::fabs(a[piv][c])) piv = i;
+        FRK_REQUIRE(a[piv][c] != 0.0, "the fixed-effects normal equations are singular (X'X not invertible)");
+        if (piv != c) for (int j = 0; j <= p; j++) std::swap(a[c][j], a[piv][j]);
+        for (int i = c + 1; i < p; i++) {
+            const double f = a[i][c] / a[c][c];
+            for (int j = c; j <= p; j++) a[i][j] -= f * a[c][j];
+        }
+    }
+    for (int i = p - 1; i >= 0; i--) {
+        double s = a[i][p];
+        for (int j = i + 1; j < p; j++) s -= a[i][j] * x[j];
+        x[i] = s / a[i][i];
+    }
+    return 0;
+}
+
+struct MSums { double uxx[16], uxz[4], sv, w0, wx[4], wxx[16]; };
+
+// R/SREfit.R:335-356,391-405,408-417: the row sums behind J(sigma2fs), alpha and the closed-form sigma2fs
+int mstep_sums(frk_model *M, double sigma2fs, int mode, MSums &s) {
+    const int p = M->p, ns = 2 * p * p + 2 * p + 2;
+    double out[2 * 16 + 2 * 4 + 2];
+    RC(frk_mstep_sums(M->ctx, M->m, p, M->X, M->Z, M->t, M->q, M->Ve, M->Vfs, sigma2fs, mode, out));
+    RC(reduce_host(M, out, ns, 0));                                  // O(p^2) doubles
+    int o = 0;
+    for (int i = 0; i < p * p; i++) s.uxx[i] = out[o++];
+    for (int i = 0; i < p; i++) s.uxz[i] = out[o++];
+    s.sv = out[o++]; s.w0 = out[o++];
+    for (int i = 0; i < p; i++) s.wx[i] = out[o++];
+    for (int i = 0; i < p * p; i++) s.wxx[i] = out[o++];
+    return 0;
+}
+
+// alpha = (sum u x x')^-1 sum u x (z - t);  sumwOm = sum w Omega(alpha)
+int gls_and_sums(frk_model *M, double s2, int mode, double *al, MSums &s, double &sumwOm) {
+    RC(mstep_sums(M, s2, mode, s));
+    RC(solve_small(M->p, s.uxx, s.uxz, al));
+    const int p = M->p;
+    double lin = 0.0, quad = 0.0;
+    for (int i = 0; i < p; i++) {
+        lin += al[i] * s.wx[i];
+        double row = 0.0;
+        for (int j = 0; j < p; j++) row += s.wxx[i + p * j] * al[j];
+        quad += al[i] * row;
+    }
+    sumwOm = s.w0 + 2.0 * lin + quad;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// stats::optim(method = "Nelder-Mead")  (R src/appl/optim.c: nmmin)
+// ---------------------------------------------------------------------------------
+struct NMResult { std::vector<double> x; double f; int count, fail; };
+
+int nmmin(const std::function<int(const double *, double &)> &fn, std::vector<double> B, NMResult &res, int maxit = 100,
+          double reltol = 1e-4, double abstol = -std::numeric_limits<double>::infinity(), double alpha = 1.0, double bet = 0.5,
+          double gamm = 2.0) {
+    const double big = 1.0e35;
+    const int n = (int)B.size(), n1 = n + 1, C = n + 2;
+    std::vector<double> P((size_t)n1 * C, 0.0);
+    auto Pm = [&](int i, int j) -> double & { return P[(size_t)i * C + j]; };   // P[i][j], 0-based
+    double f;
+    RC(fn(B.data(), f));
+    FRK_REQUIRE(std::isfinite(f), "function cannot be evaluated at initial parameters");
+    int funcount = 1;
+    const double convtol = reltol * (std::fabs(f) + reltol);
+    Pm(n1 - 1, 0) = f;
+    for (int i = 0; i < n; i++) Pm(i, 0) = B[i];
+    int L = 1;
+    double size = 0.0, step = 0.0;
+    for (int i = 0; i < n; i++) if (0.1 * std::fabs(B[i]) > step) step = 0.1 * std::fabs(B[i]);
+    if (step == 0.0) step = 0.1;
+    for (int j = 2; j <= n1; j++) {
+        for (int i = 0; i < n; i++) Pm(i, j - 1) = B[i];
+        double trystep = step;
+        while (Pm(j - 2, j - 1) == B[j - 2]) { Pm(j - 2, j - 1) = B[j - 2] + trystep; trystep *= 10; }
+        size += trystep;
+    }
+    double oldsize = size;
+    bool calcvert = true;
+    int fail = 0, H;
+    double VL, VH, VR;
+    while (true) {
+        if (calcvert) {
+            for (int j = 0; j < n1; j++) {
+                if (j + 1 != L) {
+                    for (int i = 0; i < n; i++) B[i] = Pm(i, j);
+                    RC(fn(B.data(), f));
+                    if (!std::isfinite(f)) f = big;
+                    funcount++;
+                    Pm(n1 - 1, j) = f;
+                }
+            }
+            calcvert = false;
+        }
+        VL = Pm(n1 - 1, L - 1); VH = VL; H = L;
+        for (int j = 1; j <= n1; j++) {
+            if (j != L) {
+                f = Pm(n1 - 1, j - 1);
+                if (f < VL) { L = j; VL = f; }
+                if (f > VH) { H = j; VH = f; }
+            }
+        }
+        if (VH <= VL + convtol || VL <= abstol) break;
+        for (int i = 0; i < n; i++) {
+            double temp = -Pm(i, H - 1);
+            for (int j = 0; j < n1; j++) temp += Pm(i, j);
+            Pm(i, C - 1) = temp / n;
+        }
+        for (int i = 0; i < n; i++) B[i] = (1.0 + alpha) * Pm(i, C - 1) - alpha * Pm(i, H - 1);
+        RC(fn(B.data(), f));
+        if (!std::isfinite(f)) f = big;
+        funcount++;
+        VR = f;
+        if (VR < VL) {
+            Pm(n1 - 1, C - 1) = f;
+            for (int i = 0; i < n; i++) {
+                f = gamm * B[i] + (1 - gamm) * Pm(i, C - 1);
+                Pm(i, C - 1) = B[i];
+                B[i] = f;
+            }
+            RC(fn(B.data(), f));
+            if (!std::isfinite(f)) f = big;
+            funcount++;
+            if (f < VR) {
+                for (int i = 0; i < n; i++) Pm(i, H - 1) = B[i];
+                Pm(n1 - 1, H - 1) = f;
+            } else {
+                for (int i = 0; i < n; i++) Pm(i, H - 1) = Pm(i, C - 1);
+                Pm(n1 - 1, H - 1) = VR;
+            }
+        } else {
+            if (VR < VH) {
+                for (int i = 0; i < n; i++) Pm(i, H - 1) = B[i];
+                Pm(n1 - 1, H - 1) = VR;
+            }
+            for (int i = 0; i < n; i++) B[i] = (1 - bet) * Pm(i, H - 1) + bet * Pm(i, C - 1);
+            RC(fn(B.data(), f));
+            if (!std::isfinite(f)) f = big;
+            funcount++;
+            if (f < Pm(n1 - 1, H - 1)) {
+                for (int i = 0; i < n; i++) Pm(i, H - 1) = B[i];
+                Pm(n1 - 1, H - 1) = f;
+            } else if (VR >= VH) {
+                calcvert = true;
+                size = 0.0;
+                for (int j = 0; j < n1; j++) {
+                    if (j + 1 != L) {
+                        for (int i = 0; i < n; i++) {
+                            Pm(i, j) = bet * (Pm(i, j) - Pm(i, L - 1)) + Pm(i, L - 1);
+                            size += std::fabs(Pm(i, j) - Pm(i, L - 1));
+                        }
+                    }
+                }
+                if (size < oldsize) oldsize = size;
+                else { fail = 10; break; }
+            }
+        }
+        if (!(funcount <= maxit)) break;
+    }
+    res.f = Pm(n1 - 1, L - 1);
+    res.x.resize(n);
+    for (int i = 0; i < n; i++) res.x[i] = Pm(i, L - 1);
+    if (funcount > maxit) fail = 1;
+    res.count = funcount; res.fail = fail;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// stats::uniroot -> R_zeroin2 (Brent), default tol = .Machine$double.eps^0.25
+// ---------------------------------------------------------------------------------
+int zeroin(const std::function<int(double, double &)> &f, double lower, double upper, double &root,
+           double tol = std::pow(std::numeric_limits<double>::epsilon(), 0.25), int maxiter = 1000) {
+    const double EPS = std::numeric_limits<double>::epsilon(), xmax = std::numeric_limits<double>::max();
+    double fa, fb;
+    RC(f(lower, fa));
+    RC(f(upper, fb));
+    fa = std::min(std::max(fa, -xmax), xmax);
+    fb = std::min(std::max(fb, -xmax), xmax);
+    FRK_REQUIRE(!(fa * fb > 0), "f() values at end points not of opposite sign");
+    double a = lower, b = upper, c = a, fc = fa;
+    if (fa == 0.0) { root = a; return 0; }
+    if (fb == 0.0) { root = b; return 0; }
+    int maxit = maxiter + 1;
+    while (maxit-- > 0) {
+        const double prev_step = b - a;
+        if (std::fabs(fc) < std::fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+        const double tol_act = 2 * EPS * std::fabs(b) + tol / 2;
+        double new_step = (c - b) / 2;
+        if (std::fabs(new_step) <= tol_act || fb == 0.0) { root = b; return 0; }
+        if (std::fabs(prev_step) >= tol_act && std::fabs(fa) > std::fabs(fb)) {
+            double t1, t2, pp, qq;
+            const double cb = c - b;
+            if (a == c) { t1 = fb / fa; pp = cb * t1; qq = 1.0 - t1; }
+            else {
+                qq = fa / fc; t1 = fb / fc; t2 = fb / fa;
+                pp = t2 * (cb * qq * (qq - t1) - (b - a) * (t1 - 1.0));
+                qq = (qq - 1.0) * (t1 - 1.0) * (t2 - 1.0);
+            }
+            if (pp > 0) qq = -qq; else pp = -pp;
+            if (pp < (0.75 * cb * qq - std::fabs(tol_act * qq) / 2) && pp < std::fabs(prev_step * qq / 2)) new_step = pp / qq;
+        }
+        if (std::fabs(new_step) < tol_act) new_step = new_step > 0 ? tol_act : -tol_act;
+        a = b; fa = fb;
+        b += new_step;
+        RC(f(b, fb));
+        if ((fb > 0 && fc > 0) || (fb < 0 && fc < 0)) { c = a; fc = fa; }
+    }
+    root = b;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// E-step + log-likelihood
+// ---------------------------------------------------------------------------------
+// acc = [upper(S'D^-1 S) | S'D^-1 rho | rho'D^-1 rho | sum log d], summed over ranks
+int gram(frk_model *M, const double *alpha, double sigma2fs) {
+    const size_t n = (size_t)M->r * M->r + M->r + 2;
+    FRK_CHECK_CUDA(cudaMemsetAsync(M->acc, 0, n * sizeof(double), M->ctx->stream));
+    RC(frk_gram_rhs_bucketed(M->ctx, M->m, M->r, M->rowptr, M->col, M->val, M->bk.perm, M->bk.bptr, M->bk.ucol, M->bk.nU, M->bk.lid,
+                             M->Z, M->X, M->p, alpha, M->Ve, M->Vfs, sigma2fs, M->acc));
+    return reduce_dev(M, M->acc, (int64_t)n);                         // the ONE large exchange per EM iteration
+}
+
+// Q = S'D^-1 S + Khat_inv; Sigma = chol2inv(chol(Q)); mu = Sigma S'D^-1 rho   (R/SREfit.R:252-254)
+// out = {logdet(R) = 2 sum log diag chol Q, rho'D^-1 rho, sum log d, ||L^-1 S'D^-1 rho||^2}
+int posterior(frk_model *M, const double *alpha, double sigma2fs, double *Q_out, double *Sig_out, double *mu_out, double out[4]) {
+    frk_ctx *ctx = M->ctx;
+    const int r = M->r;
+    const size_t rr = (size_t)r * r;
+    RC(gram(M, alpha, sigma2fs));
+    const double *b = M->acc + rr;
+    RC(frk_sym_from_upper_add(ctx, r, M->acc, M->Khat_inv, Q_out));
+    FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, Q_out, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    RC(frk_potrf(ctx, r, M->w1, &out[0]));
+    RC(frk_potri(ctx, r, M->w1, Sig_out, M->w2));
+    RC(frk_symv(ctx, r, Sig_out, b, mu_out));
+    // || (rDinv S) solve(R) ||^2 with solve(R)' = L^-1 left in w2 by potri   (R/SREfit.R:211)
+    RC(frk_lower_mulv(ctx, r, M->w2, b, M->vec));
+    RC(frk_dot(ctx, r, M->vec, M->vec, &out[3]));
+    double sc[2];
+    RC(frk_d2h(ctx, sc, M->acc + rr + r, 2 * sizeof(double)));
+    out[1] = sc[0]; out[2] = sc[1];
+    return 0;
+}
+
+double llk_from(const frk_model *M, const double o[4]) {
+    const double log_det_SigmaZ = o[0] + M->logdetK + o[2];          // logdet(R) + log|K| + logdet(cholD)
+    const double quad = o[1] - o[3];
+    return -0.5 * M->m_total * std::log(2.0 * M_PI) - 0.5 * log_det_SigmaZ - 0.5 * quad;
+}
+
+int chol2inv_logdet(frk_ctx *ctx, int n, double *A, double *Ainv, double *work, double *logdet) {
+    RC(frk_potrf(ctx, n, A, logdet));
+    return frk_potri(ctx, n, A, Ainv, work);
+}
+
+// ---------------------------------------------------------------------------------
+// M-step
+// ---------------------------------------------------------------------------------
+int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const int *h_res) {
+    frk_ctx *ctx = M->ctx;
+    const int r = M->r;
+    const size_t rr = (size_t)r * r;
+    if (K_type == FRK_K_UNSTRUCTURED) {
+        RC(frk_add_outer(ctx, r, M->S_eta, M->mu_eta, M->Khat));     // K = S_eta + mu mu', R/SREfit.R:689
+        bool any = false;
+        for (int i = 0; i < nlambda; i++) any = any || lambda[i] > 0;
+        if (any) {                                                   // K = ((K)^-1 + Lambda)^-1, :669-686
+            std::vector<double> reg(r);
+            for (int j = 0; j < r; j++) reg[j] = nlambda == 1 ? lambda[0] : lambda[(h_res ? h_res[j] : 1) - 1];
+            RC(frk_h2d(ctx, M->vec, reg.data(), r * sizeof(double)));
+            double ld;
+            RC(chol2inv_logdet(ctx, r, M->Khat, M->w1, M->w2, &ld));
+            RC(frk_add_diag(ctx, r, M->vec, M->w1));
+            RC(chol2inv_logdet(ctx, r, M->w1, M->Khat, M->w2, &ld));
+        }
+        return 0;
+    }
+    FRK_REQUIRE(!M->blocks.empty(), "K_type = \"block-exponential\" needs the per-resolution distance matrices (frk_model_set_blocks)");
+    // Knew is assembled in w1 (free here); Khat (old) is read for the start values
+    M->taus.clear(); M->omegas.clear();
+    double *Knew = M->w1;
+    FRK_CHECK_CUDA(cudaMemsetAsync(Knew, 0, rr * sizeof(double), ctx->stream));
+    for (Block &B : M->blocks) {
+        const int ni = B.ni;
+        const size_t nn = (size_t)ni * ni;
+        // eta2_i = (S_eta + mu mu')[idx, idx]                                                      :459-464
+        RC(frk_block_gather_outer(ctx, r, M->S_eta, M->mu_eta, ni, B.d_ix, B.eta2));
+        // omega_i = n_i / tr(C_i^-1 eta2_i),  C_i = Khat[idx,idx] / Khat[idx1,idx1]                 :466-482
+        RC(frk_block_gather(ctx, r, M->Khat, ni, B.d_ix, B.Ki));
+        double k2[2] = {0, 0};
+        RC(frk_d2h(ctx, k2, B.Ki, sizeof(double) * std::min<size_t>(2, nn)));
+        const double k00 = k2[0], k01 = ni > 1 ? k2[1] : 0.0;
+        double ld, trc;
+        RC(chol2inv_logdet(ctx, ni, B.Ki, B.Kinv, B.work, &ld));
+        RC(frk_dot(ctx, (int64_t)nn, B.Kinv, B.eta2, &trc));
+        const double omega = ni / (k00 * trc);                       // (K/k00)^-1 = k00 K^-1
+        M->omegas.push_back(omega);
+        auto f_tau = [&](const double *tau, double &fval) -> int {  // :485-529
+            if (tau[0] <= 1e-10) { fval = std::numeric_limits<double>::infinity(); return 0; }
+            RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau[0], 1.0, B.Ki));
+            double logdetKi, t;
+            RC(chol2inv_logdet(ctx, ni, B.Ki, B.Kinv, B.work, &logdetKi));
+            RC(frk_dot(ctx, (int64_t)nn, B.Kinv, B.eta2, &t));
+            fval = -(0.5 * (-logdetKi) - omega / 2.0 * t);
+            return 0;
+        };
+        double par0 = 1e-9;                                          // :608-614
+        if (ni > 1) {
+            const double v = -B.D01 / std::log(k01 / k00);
+            par0 = (v > 1e-9) ? v : 1e-9;                            // max(v, 1e-9); NaN -> 1e-9
+        }
+        if (!std::isfinite(par0) || par0 == 1e-9) par0 = M->max_l / 10.0;
+        NMResult nm;
+        RC(nmmin(f_tau, std::vector<double>{par0}, nm, 100, 1e-4));   // optim(): Nelder-Mead, :618-621
+        M->taus.push_back(nm.x[0]);
+        RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, nm.x[0], 1.0 / omega, B.Ki));   // K_i = exp(-D_i/tau_i)/omega_i, :625-637
+        RC(frk_block_scatter(ctx, r, Knew, ni, B.d_ix, B.Ki));
+    }
+    FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat, Knew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int *h_res, int known, double known_sigma2fs) {
+    frk_ctx *ctx = M->ctx;
+    const int r = M->r, p = M->p;
+    const size_t rr = (size_t)r * r;
+    const double sigma2fs = M->sigma2fs;
+    RC(update_K(M, K_type, nlambda, lambda, h_res));                 // :270-272
+    FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, M->Khat, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    RC(chol2inv_logdet(ctx, r, M->w1, M->Khat_inv, M->w2, &M->logdetK));   // Khat_inv = chol2inv(chol(K)), :273
+    const bool est = !known;
+    double s2new = est ? sigma2fs : known_sigma2fs;
+    // Omega_diag1 = rowSums((S R_eta')^2) = s_j'(S_eta + mu mu')s_j = q_j + t_j^2,  t = S mu_eta     :332-334
+    RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk.perm, M->bk.bptr, M->bk.ucol, M->bk.nU, M->bk.lid,
+                                  M->S_eta, M->mu_eta, M->q, M->t));
+    double al[MAXP_M];
+    MSums s;
+    double swo;
+    auto J = [&](double s2, double &val) -> int {                    // :335-356
+        if (s2 < 0) { val = std::numeric_limits<double>::infinity(); return 0; }
+        double a2[MAXP_M]; MSums ss; double sw;
+        RC(gls_and_sums(M, s2, 0, a2, ss, sw));
+        val = -(-0.5 * ss.sv + 0.5 * sw);
+        return 0;
+    };
+    auto sgn = [](double v) { return (v > 0) - (v < 0); };
+    if (!M->all_vfs_zero) {
+        if (!M->homoscedastic) {
+            if (est) {
+                double amp = 10.0;
+                bool ok = false;
+                while (!ok) {                                        // :368-380
+                    amp *= 10;
+                    double j1, j2;
+                    RC(J(sigma2fs / amp, j1));
+                    RC(J(sigma2fs * amp, j2));
+                    if (sgn(j1) != sgn(j2) || std::isnan(j1) || std::isnan(j2)) ok = true;
+                    if (amp > 1e9) ok = true;
+                }
+                if (amp > 1e9) s2new = 0.0;
+                else RC(zeroin(J, sigma2fs / amp, sigma2fs * amp, s2new));   // uniroot, :386-388
+            }
+            RC(gls_and_sums(M, s2new, 0, al, s, swo));               // :391-400
+        } else {
+            RC(gls_and_sums(M, 0.0, 1, al, s, swo));                 // :404-405
+            if (est) {
+                s2new = 1.0 / M->Vfs0 * (swo / M->m_total - M->Ve0); // :408-417
+                if (s2new < 0) s2new = 0.0;
+            }
+        }
+    } else {                                                         // :424-428
+        RC(gls_and_sums(M, 0.0, 0, al, s, swo));
+        if (est) s2new = 0.0;
+    }
+    for (int i = 0; i < p; i++) M->alpha[i] = al[i];
+    M->sigma2fs = s2new;
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------
+static int model_common_init(frk_model *M) {
+    const int r = M->r;
+    const size_t rr = (size_t)r * r;
+    RC(dalloc(M, &M->mu_eta, r)); RC(dalloc(M, &M->S_eta, rr)); RC(dalloc(M, &M->Q_eta, rr));
+    RC(dalloc(M, &M->Khat, rr)); RC(dalloc(M, &M->Khat_inv, rr));
+    RC(dalloc(M, &M->acc, rr + r + 2)); RC(dalloc(M, &M->w1, rr)); RC(dalloc(M, &M->w2, rr)); RC(dalloc(M, &M->vec, r));
+    RC(dalloc(M, &M->t, (size_t)std::max<int64_t>(M->m, 1))); RC(dalloc(M, &M->q, (size_t)std::max<int64_t>(M->m, 1)));
+    FRK_CHECK_CUDA(cudaMemsetAsync(M->q, 0, std::max<int64_t>(M->m, 1) * sizeof(double), M->ctx->stream));
+    FRK_CHECK_CUDA(cudaMemsetAsync(M->t, 0, std::max<int64_t>(M->m, 1) * sizeof(double), M->ctx->stream));
+    // row buckets of S
+    int nnz = 0;
+    RC(frk_d2h(M->ctx, &nnz, M->rowptr + M->m, sizeof(int)));
+    RC(dalloc(M, &M->bk.perm, (size_t)std::max<int64_t>(M->m, 1))); RC(dalloc(M, &M->bk.bptr, (size_t)r + 1));
+    RC(dalloc(M, &M->bk.ucol, (size_t)r * 64)); RC(dalloc(M, &M->bk.nU, (size_t)r)); RC(dalloc(M, &M->bk.lid, (size_t)std::max(nnz, 1)));
+    RC(frk_csr_bucket_rows(M->ctx, M->m, M->rowptr, M->col, r, M->bk.perm, M->bk.bptr, M->bk.ucol, M->bk.nU, M->bk.lid));
+    // totals and the homoscedasticity test all(a == a[1]) & all(b == b[1])   (R/SREfit.R:278-280)
+    double mt[1] = {(double)M->m};
+    RC(reduce_host(M, mt, 1, 0));
+    M->m_total = mt[0];
+    FRK_REQUIRE(M->m_total > 0, "no observation falls inside a BAU");
+    double ves[4], vfs[4];
+    RC(global_stats(M, M->Ve, 0.0, ves));
+    RC(global_stats(M, M->Vfs, 0.0, vfs));
+    M->homoscedastic = (ves[2] == ves[3]) && (vfs[2] == vfs[3]);
+    M->Ve0 = ves[2]; M->Vfs0 = vfs[2];
+    M->all_vfs_zero = (vfs[2] == 0.0 && vfs[3] == 0.0);
+    return 0;
+}
+
+extern "C" int frk_model_create(frk_ctx *ctx, int64_t m, int r, int p, const int *d_rowptr, const int *d_col, const double *d_val,
+                                const double *d_Z, const double *d_X, const double *d_Ve, const double *d_Vfs,
+                                frk_allreduce_fn allreduce, void *user, frk_model **out) {
+    FRK_REQUIRE(ctx && out && d_rowptr && d_Z && d_X && d_Ve && d_Vfs && r > 0 && m >= 0, "frk_model_create: bad argument");
+    FRK_REQUIRE(p >= 1 && p <= MAXP_M, "frk_model_create: %d fixed effects; the device path handles 1..%d", p, MAXP_M);
+    frk_model *M = new frk_model();
+    M->ctx = ctx; M->m = m; M->r = r; M->p = p;
+    M->rowptr = d_rowptr; M->col = d_col; M->val = d_val; M->Z = d_Z; M->X = d_X; M->Ve = d_Ve; M->Vfs = d_Vfs;
+    M->allreduce = allreduce; M->user = user;
+    if (int rc = model_common_init(M)) { frk_model_destroy(M); return rc; }
+    *out = M;
+    return 0;
+}
+
+extern "C" int frk_model_create_host(frk_ctx *ctx, int64_t m, int r, int p, const int *h_rowptr, const int *h_col,
+                                     const double *h_val, const double *h_Z, const double *h_X, const double *h_Ve,
+                                     const double *h_Vfs, frk_model **out) {
+    FRK_REQUIRE(ctx && out && h_rowptr && h_Z && h_X && h_Ve && h_Vfs && r > 0 && m >= 0, "frk_model_create_host: bad argument");
+    FRK_REQUIRE(p >= 1 && p <= MAXP_M, "frk_model_create_host: %d fixed effects; the device path handles 1..%d", p, MAXP_M);
+    frk_model *M = new frk_model();
+    M->ctx = ctx; M->m = m; M->r = r; M->p = p; M->owned = true;
+    const int64_t nnz = h_rowptr[m];
+    int *rp, *cl; double *vl, *z, *x, *ve, *vfs;
+    int rc = 0;
+    rc = rc || dalloc(M, &rp, (size_t)m + 1) || dalloc(M, &cl, (size_t)std::max<int64_t>(nnz, 1)) || dalloc(M, &vl, (size_t)std::max<int64_t>(nnz, 1)) ||
+         dalloc(M, &z, (size_t)std::max<int64_t>(m, 1)) || dalloc(M, &x, (size_t)std::max<int64_t>(m * p, 1)) ||
+         dalloc(M, &ve, (size_t)std::max<int64_t>(m, 1)) || dalloc(M, &vfs, (size_t)std::max<int64_t>(m, 1));
+    if (rc) { frk_model_destroy(M); return 1; }
+    cudaStream_t st = ctx->stream;
+    cudaMemcpyAsync(rp, h_rowptr, (m + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(cl, h_col, nnz * sizeof(int), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(vl, h_val, nnz * sizeof(double), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(z, h_Z, m * sizeof(double), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(x, h_X, m * p * sizeof(double), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(ve, h_Ve, m * sizeof(double), cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(vfs, h_Vfs, m * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { frk_set_error("frk_model_create_host: upload failed: %s", cudaGetErrorString(e)); frk_model_destroy(M); return 1; }
+    M->rowptr = rp; M->col = cl; M->val = vl; M->Z = z; M->X = x; M->Ve = ve; M->Vfs = vfs;
+    if (int rc2 = model_common_init(M)) { frk_model_destroy(M); return rc2; }
+    *out = M;
+    return 0;
+}
+
+extern "C" int frk_model_destroy(frk_model *M) {
+    if (!M) return 0;
+    cudaSetDevice(M->ctx->device);
+    cudaStreamSynchronize(M->ctx->stream);
+    for (void *p : M->allocs) cudaFree(p);
+    delete M;
+    return 0;
+}
+
+// per-resolution index sets and centroid distance matrices (BuildD, R/basisfns.R:1131-1153) for K_type = "block-exponential"
+extern "C" int frk_model_set_blocks(frk_model *M, int nres, const int *h_res, const double *const *h_D) {
+    FRK_REQUIRE(M && nres > 0 && h_res && h_D, "frk_model_set_blocks: bad argument");
+    FRK_REQUIRE(M->blocks.empty(), "frk_model_set_blocks: already set");
+    const int r = M->r;
+    for (int i = 1; i <= nres; i++) {
+        std::vector<int> ix;
+        for (int j = 0; j < r; j++) if (h_res[j] == i) ix.push_back(j);
+        FRK_REQUIRE(!ix.empty(), "frk_model_set_blocks: resolution %d has no basis function", i);
+        Block B;
+        B.ni = (int)ix.size(); B.ix0 = ix[0];
+        const size_t nn = (size_t)B.ni * B.ni;
+        RC(dalloc(M, &B.d_ix, ix.size())); RC(dalloc(M, &B.D, nn)); RC(dalloc(M, &B.eta2, nn)); RC(dalloc(M, &B.Ki, nn));
+        RC(dalloc(M, &B.Kinv, nn)); RC(dalloc(M, &B.work, nn));
+        FRK_CHECK_CUDA(cudaMemcpy(B.d_ix, ix.data(), ix.size() * sizeof(int), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(B.D, h_D[i - 1], nn * sizeof(double), cudaMemcpyHostToDevice));
+        B.D01 = B.ni > 1 ? h_D[i - 1][B.ni] : 0.0;                   // D[1,2] (column-major, symmetric)
+        if (i == 1) { double mx = 0; for (size_t k = 0; k < nn; k++) mx = std::max(mx, h_D[0][k]); M->max_l = mx; }
+        M->blocks.push_back(B);
+    }
+    return 0;
+}
+
+// .EM_initialise, R/SRE.R:704-731
+extern "C" int frk_model_init(frk_model *M) {
+    FRK_REQUIRE(M, "frk_model_init: NULL model");
+    frk_ctx *ctx = M->ctx;
+    const int r = M->r;
+    double zs[4], zs2[4], ves[4];
+    RC(global_stats(M, M->Z, 0.0, zs));
+    const double zbar = zs[0] / M->m_total;
+    RC(global_stats(M, M->Z, zbar, zs2));
+    const double varZ = M->m_total > 1 ? zs2[1] / (M->m_total - 1) : std::numeric_limits<double>::quiet_NaN();
+    RC(global_stats(M, M->Ve, 0.0, ves));
+    M->sigma2fs = (ves[0] / M->m_total) / 4.0;
+    RC(frk_scaled_identity(ctx, r, 1.0, M->S_eta));
+    RC(frk_scaled_identity(ctx, r, 1.0, M->Q_eta));
+    RC(frk_scaled_identity(ctx, r, 1.0 / (1.0 / varZ), M->Khat));
+    RC(frk_scaled_identity(ctx, r, 1.0 / (1.0 / (1.0 / varZ)), M->Khat_inv));
+    FRK_CHECK_CUDA(cudaMemsetAsync(M->mu_eta, 0, r * sizeof(double), ctx->stream));
+    M->logdetK = r * std::log(varZ);
+    // alpha = (X'X)^-1 X'Z: the mode-1 moments with t = 0
+    FRK_CHECK_CUDA(cudaMemsetAsync(M->t, 0, std::max<int64_t>(M->m, 1) * sizeof(double), ctx->stream));
+    MSums s;
+    RC(mstep_sums(M, 0.0, 1, s));
+    RC(solve_small(M->p, s.uxx, s.uxz, M->alpha));
+    M->initialised = true;
+    return 0;
+}
+
+extern "C" int frk_model_em_fit(frk_model *M, int n_EM, double tol, int K_type, int nlambda, const double *h_lambda,
+                                const int *h_res, int known_sigma2fs_given, double known_sigma2fs, double *h_llk, int *h_niter) {
+    FRK_REQUIRE(M && h_llk && h_niter && n_EM >= 0, "frk_model_em_fit: bad argument");
+    FRK_REQUIRE(M->initialised, "frk_model_em_fit: call frk_model_init (or frk_model_set for every slot) first");
+    FRK_REQUIRE(K_type == FRK_K_UNSTRUCTURED || K_type == FRK_K_BLOCK_EXPONENTIAL,
+                "K_type needs to be \"block-exponential\" or \"unstructured\" for method = \"EM\"");
+    if (known_sigma2fs_given) M->sigma2fs = known_sigma2fs;          // R/SREfit.R:19
+    int i = 0;
+    for (i = 0; i < n_EM; i++) {
+        double o[4];
+        RC(posterior(M, M->alpha, M->sigma2fs, M->Q_eta, M->S_eta, M->mu_eta, o));   // logLik + E-step, :105-106
+        h_llk[i] = llk_from(M, o);
+        RC(mstep(M, K_type, nlambda, h_lambda, h_res, known_sigma2fs_given, known_sigma2fs));   // :107
+        if (i > 0 && std::fabs(h_llk[i] - h_llk[i - 1]) < tol) { i++; break; }    // :110-114
+    }
+    *h_niter = std::min(i, n_EM);
+    FRK_CHECK_CUDA(cudaStreamSynchronize(M->ctx->stream));
+    return 0;
+}
+
+// logLik(SRE) at the current parameters (R/SREutils.R:22-32 -> .loglik.ind); the slots are left untouched
+extern "C" int frk_model_loglik(frk_model *M, double *h_out) {
+    FRK_REQUIRE(M && h_out && M->initialised, "frk_model_loglik: bad argument");
+    double *Q, *Sg, *mu;
+    const size_t rr = (size_t)M->r * M->r;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&Q, (2 * rr + M->r) * sizeof(double), M->ctx->stream));
+    Sg = Q + rr; mu = Sg + rr;
+    double o[4];
+    int rc = posterior(M, M->alpha, M->sigma2fs, Q, Sg, mu, o);
+    cudaFreeAsync(Q, M->ctx->stream);
+    if (rc) return rc;
+    *h_out = llk_from(M, o);
+    return 0;
+}
+
+static double *slot_ptr(frk_model *M, const char *name, size_t *n) {
+    const size_t rr = (size_t)M->r * M->r;
+    if (!strcmp(name, "mu_eta")) { *n = M->r; return M->mu_eta; }
+    if (!strcmp(name, "S_eta")) { *n = rr; return M->S_eta; }
+    if (!strcmp(name, "Q_eta")) { *n = rr; return M->Q_eta; }
+    if (!strcmp(name, "Khat")) { *n = rr; return M->Khat; }
+    if (!strcmp(name, "Khat_inv")) { *n = rr; return M->Khat_inv; }
+    return nullptr;
+}
+
+extern "C" int frk_model_get(frk_model *M, const char *slot, double *h_out) {
+    FRK_REQUIRE(M && slot && h_out, "frk_model_get: bad argument");
+    if (!strcmp(slot, "alphahat")) { for (int i = 0; i < M->p; i++) h_out[i] = M->alpha[i]; return 0; }
+    if (!strcmp(slot, "sigma2fshat")) { h_out[0] = M->sigma2fs; return 0; }
+    if (!strcmp(slot, "m_total")) { h_out[0] = M->m_total; return 0; }
+    if (!strcmp(slot, "homoscedastic")) { h_out[0] = M->homoscedastic ? 1.0 : 0.0; return 0; }
+    if (!strcmp(slot, "tau")) { for (size_t i = 0; i < M->taus.size(); i++) h_out[i] = M->taus[i]; return 0; }
+    if (!strcmp(slot, "omega")) { for (size_t i = 0; i < M->omegas.size(); i++) h_out[i] = M->omegas[i]; return 0; }
+    size_t n = 0;
+    double *p = slot_ptr(M, slot, &n);
+    FRK_REQUIRE(p, "frk_model_get: unknown slot '%s'", slot);
+    return frk_d2h(M->ctx, h_out, p, n * sizeof(double));
+}
+
+extern "C" int frk_model_set(frk_model *M, const char *slot, const double *h_in) {
+    FRK_REQUIRE(M && slot && h_in, "frk_model_set: bad argument");
+    if (!strcmp(slot, "alphahat")) { for (int i = 0; i < M->p; i++) M->alpha[i] = h_in[i]; return 0; }
+    if (!strcmp(slot, "sigma2fshat")) { M->sigma2fs = h_in[0]; return 0; }
+    size_t n = 0;
+    double *p = slot_ptr(M, slot, &n);
+    FRK_REQUIRE(p, "frk_model_set: unknown slot '%s'", slot);
+    RC(frk_h2d(M->ctx, p, h_in, n * sizeof(double)));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(M->ctx->stream));
+    if (!strcmp(slot, "Khat")) {                                     // keep log|K| consistent with the slot (.loglik.ind :177,197)
+        const size_t rr = (size_t)M->r * M->r;
+        FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, M->Khat, rr * sizeof(double), cudaMemcpyDeviceToDevice, M->ctx->stream));
+        RC(frk_potrf(M->ctx, M->r, M->w1, &M->logdetK));
+        M->initialised = true;
+    }
+    return 0;
+}
+
+extern "C" int frk_model_slot_device(frk_model *M, const char *slot, double **d_out) {
+    FRK_REQUIRE(M && slot && d_out, "frk_model_slot_device: bad argument");
+    size_t n = 0;
+    *d_out = slot_ptr(M, slot, &n);
+    FRK_REQUIRE(*d_out, "frk_model_slot_device: unknown slot '%s'", slot);
+    return 0;
+}
+
+// predict at n BAUs (this rank's rows): .SRE.predict_EM with predict_BAUs = TRUE, covariances = FALSE.
+// S0: n x r device CSR with its row buckets; d_XBAU n x p column-major; d_fs n; d_obs_bau m (BAU row of every observation).
+extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
+                                 const int *d_perm0, const int *d_bptr0, const int *d_ucol0, const int *d_nU0,
+                                 const unsigned char *d_lid0, const double *d_XBAU, const double *d_fs, const int *d_obs_bau,
+                                 int obs_fs, double *d_mu, double *d_var, double *d_sd) {
+    FRK_REQUIRE(M && d_rowptr0 && d_XBAU && d_mu && d_var && d_sd && n >= 0, "frk_model_predict: bad argument");
+    frk_ctx *ctx = M->ctx;
+    const int r = M->r;
+    const size_t rr = (size_t)r * r;
+    const int64_t n1 = std::max<int64_t>(n, 1), m1 = std::max<int64_t>(M->m, 1);
+    double *buf = nullptr;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&buf, (size_t)(5 * n1 + 2 * m1) * sizeof(double), ctx->stream));
+    double *xa = buf, *q = xa + n1, *smu = q + n1, *A = smu + n1, *ytil = A + n1, *tmp = ytil + n1, *inv_ve = tmp + m1;
+    int rc = 0;
+    auto run = [&]() -> int {
+        RC(frk_xalpha(ctx, n, M->p, d_XBAU, M->alpha, xa));
+        if (obs_fs || M->sigma2fs == 0.0) {                           // the stored posterior (R/SREpredict.R:334-361)
+            RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, d_perm0, d_bptr0, d_ucol0, d_nU0, d_lid0, M->S_eta,
+                                          M->mu_eta, q, smu));
+            return frk_predict_finalize(ctx, n, 0, M->sigma2fs, q, smu, xa, nullptr, nullptr, nullptr, d_mu, d_var, d_sd);
+        }
+        // joint (eta, xi) solve at the final parameters (:308-333); for point data: one more E-step + the same quadratic form
+        FRK_REQUIRE(d_fs && d_obs_bau, "frk_model_predict: obs_fs = FALSE needs the BAU fs field and the observation -> BAU map");
+        double *Q, o[4];
+        FRK_CHECK_CUDA(cudaMallocAsync((void **)&Q, (2 * rr + r) * sizeof(double), ctx->stream));
+        double *Sig = Q + rr, *mue = Sig + rr;
+        int rc2 = posterior(M, M->alpha, M->sigma2fs, Q, Sig, mue, o);
+        if (!rc2) rc2 = frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, d_perm0, d_bptr0, d_ucol0, d_nU0, d_lid0, Sig,
+                                                   mue, q, smu);
+        cudaFreeAsync(Q, ctx->stream);
+        if (rc2) return rc2;
+        // A = diag(C' Ve^-1 C), ytil = C' Ve^-1 (Z - X alpha)
+        FRK_CHECK_CUDA(cudaMemsetAsync(A, 0, 2 * n1 * sizeof(double), ctx->stream));
+        RC(frk_resid(ctx, M->m, M->p, M->X, M->alpha, M->Z, M->Ve, tmp));
+        RC(frk_scatter_add(ctx, M->m, d_obs_bau, tmp, ytil));
+        RC(frk_recip(ctx, M->m, M->Ve, inv_ve));
+        RC(frk_scatter_add(ctx, M->m, d_obs_bau, inv_ve, A));
+        return frk_predict_finalize(ctx, n, 1, M->sigma2fs, q, smu, xa, A, ytil, d_fs, d_mu, d_var, d_sd);
+    };
+    rc = run();
+    cudaFreeAsync(buf, ctx->stream);
+    return rc;
+}
+
+// ---- the host optimisers, exported so that the CPU test-suite can pin them without a GPU --------------------
+extern "C" int frk_optim_nelder_mead(frk_objective_fn fn, void *user, int n, const double *par, int maxit, double reltol,
+                                     double *x_out, double *f_out, int *count_out, int *fail_out) {
+    FRK_REQUIRE(fn && par && x_out && n > 0, "frk_optim_nelder_mead: bad argument");
+    NMResult res;
+    auto f = [&](const double *x, double &v) -> int { v = fn(user, n, x); return 0; };
+    RC(nmmin(f, std::vector<double>(par, par + n), res, maxit, reltol));
+    for (int i = 0; i < n; i++) x_out[i] = res.x[i];
+    if (f_out) *f_out = res.f;
+    if (count_out) *count_out = res.count;
+    if (fail_out) *fail_out = res.fail;
+    return 0;
+}
+
+extern "C" int frk_optim_zeroin(frk_objective_fn fn, void *user, double lower, double upper, double *root_out) {
+    FRK_REQUIRE(fn && root_out, "frk_optim_zeroin: bad argument");
+    auto f = [&](double x, double &v) -> int { v = fn(user, 1, &x); return 0; };
+    return zeroin(f, lower, upper, *root_out);
+}

@@ -91,6 +91,34 @@ class Device:
             self.torch.distributed.all_reduce(t)
         return t
 
+    def allreduce_hook(self):
+        """ctypes callback handed to frk_model_create: libfrkb200 calls it for every cross-rank reduction.  Device
+        buffers are wrapped zero-copy (``__cuda_array_interface__``) and reduced by NCCL on the ctx stream."""
+        from ._lib import ALLREDUCE_FN
+        torch, tdev = self.torch, self.tdev
+
+        class _View:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+        def hook(user, buf, n, on_device, op):
+            try:
+                d = torch.distributed
+                rop = d.ReduceOp.SUM if op == 0 else d.ReduceOp.MAX
+                if on_device:
+                    t = torch.as_tensor(_View(buf, n), device=tdev)
+                    d.all_reduce(t, op=rop)
+                else:
+                    h = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(int(n),))
+                    t = torch.as_tensor(h.copy(), device=tdev)
+                    d.all_reduce(t, op=rop)
+                    h[:] = t.cpu().numpy()
+                return 0
+            except Exception as e:      # never let an exception cross the C ABI
+                print(f"frk_b200 all-reduce hook failed: {e!r}", flush=True)
+                return 1
+        return ALLREDUCE_FN(hook)
+
     def allreduce_host(self, a: np.ndarray) -> np.ndarray:
         """Sum a small host vector over ranks (M-step moments, O(p^2) doubles)."""
         return allreduce_host(a, "sum", self.tdev)

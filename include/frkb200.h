@@ -33,6 +33,17 @@ extern "C" {
 
 typedef struct frk_ctx frk_ctx;       /* device + stream + scratch workspace        */
 typedef struct frk_basis frk_basis;   /* device-resident basis + cell lists          */
+typedef struct frk_model frk_model;   /* device-resident SRE object (S, Z, X, Ve, Vfs + the r-sized slots) */
+
+/* SRE(K_type=): R/SRE.R:322; only these two are legal for method = "EM" (R/check_args.R:184-187) */
+enum { FRK_K_UNSTRUCTURED = 0, FRK_K_BLOCK_EXPONENTIAL = 1 };
+
+/* Reduction hook for row-partitioned (multi-GPU) runs: combine buf[n] over the ranks IN PLACE and return 0.
+ * on_device != 0: buf is a device pointer and the reduction must be enqueued on the ctx stream;
+ * op: 0 = sum, 1 = max.  NULL = single rank.  (The plumbing -- torch.distributed / NCCL -- stays with the caller.) */
+typedef int (*frk_allreduce_fn)(void *user, double *buf, int64_t n, int on_device, int op);
+/* objective for the exported host optimisers: returns f(x[0..n)) */
+typedef double (*frk_objective_fn)(void *user, int n, const double *x);
 
 /* manifold(): R/geometryfns.R:19-189 */
 enum { FRK_REAL_LINE = 1, FRK_PLANE = 2, FRK_SPHERE = 3 };
@@ -253,6 +264,50 @@ int frk_dgemm_nt(frk_ctx *ctx, int M, int N, int K, double alpha, const double *
 /* general operand layouts: transa / transb != 0 -> that operand is stored with k contiguous (K x M / K x N) */
 int frk_dgemm(frk_ctx *ctx, int transa, int transb, int M, int N, int K, double alpha, const double *d_A,
               int lda, const double *d_B, int ldb, double beta, double *d_C, int ldc);
+
+/* ---- the SRE object and SRE.fit(method = "EM") / predict() as single calls ------------------------------
+ * frk_model holds this rank's rows of S (m x r CSR), Z, X (m x p column-major), Ve = diag, Vfs = diag and the
+ * slots mu_eta, S_eta, Q_eta, Khat, Khat_inv (device), alphahat, sigma2fshat (host): R/AllClass.R:133-175.
+ * _create borrows device arrays (they must outlive the model); _create_host copies host arrays (what the R shim
+ * passes: S as a dgRMatrix' p/j/x, R/SRE.R:502).                                                              */
+int frk_model_create(frk_ctx *ctx, int64_t m, int r, int p, const int *d_rowptr, const int *d_col,
+                     const double *d_val, const double *d_Z, const double *d_X, const double *d_Ve,
+                     const double *d_Vfs, frk_allreduce_fn allreduce, void *user, frk_model **out);
+int frk_model_create_host(frk_ctx *ctx, int64_t m, int r, int p, const int *h_rowptr, const int *h_col,
+                          const double *h_val, const double *h_Z, const double *h_X, const double *h_Ve,
+                          const double *h_Vfs, frk_model **out);
+int frk_model_destroy(frk_model *mdl);
+/* BuildD() (R/basisfns.R:1131-1153) for K_type = "block-exponential": h_res[r] 1-based resolution of every basis
+ * function, h_D[i] the r_i x r_i centroid distance matrix of resolution i+1 (column-major, host).              */
+int frk_model_set_blocks(frk_model *mdl, int nres, const int *h_res, const double *const *h_D);
+/* .EM_initialise (R/SRE.R:704-731) */
+int frk_model_init(frk_model *mdl);
+/* .EM_fit (R/SREfit.R:78-160): up to n_EM iterations of logLik + E-step + M-step; stops when the log-likelihood
+ * changes by less than tol.  h_lambda[nlambda] ridge parameter(s) (unstructured K; R/SREfit.R:664-694), h_res as
+ * above (may be NULL when nlambda <= 1).  h_llk[n_EM] receives info_fit$plot_lik$llk, *h_niter the iterations run. */
+int frk_model_em_fit(frk_model *mdl, int n_EM, double tol, int K_type, int nlambda, const double *h_lambda,
+                     const int *h_res, int known_sigma2fs_given, double known_sigma2fs, double *h_llk,
+                     int *h_niter);
+/* logLik(SRE) at the current slots (R/SREutils.R:22-32 -> .loglik.ind R/SREfit.R:174-220) */
+int frk_model_loglik(frk_model *mdl, double *h_out);
+/* slot access: "mu_eta" (r), "S_eta", "Q_eta", "Khat", "Khat_inv" (r x r column-major), "alphahat" (p),
+ * "sigma2fshat" (1); read-only: "m_total", "homoscedastic", "tau", "omega" (per resolution, last M-step)       */
+int frk_model_get(frk_model *mdl, const char *slot, double *h_out);
+int frk_model_set(frk_model *mdl, const char *slot, const double *h_in);
+int frk_model_slot_device(frk_model *mdl, const char *slot, double **d_out);
+/* .SRE.predict_EM at n BAUs (R/SREpredict.R:243-375; predict_BAUs = TRUE, covariances = FALSE) with
+ * .batch_compute_var (R/SREutils.R:245-305).  S0 (n x r device CSR) comes with its row buckets
+ * (frk_csr_bucket_rows); d_XBAU n x p column-major; d_fs[n]; d_obs_bau[m] = BAU row of every observation.
+ * obs_fs != 0 or sigma2fs == 0: stored posterior; else the joint (eta, xi) solve at the final parameters.      */
+int frk_model_predict(frk_model *mdl, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
+                      const int *d_perm0, const int *d_bptr0, const int *d_ucol0, const int *d_nU0,
+                      const unsigned char *d_lid0, const double *d_XBAU, const double *d_fs,
+                      const int *d_obs_bau, int obs_fs, double *d_mu, double *d_var, double *d_sd);
+/* stats::optim(method = "Nelder-Mead", control = list(maxit, reltol)) and stats::uniroot (default tol) as used by
+ * the M-step (R/SREfit.R:618-621, :386-388); exported so that the iterate path can be tested on its own.       */
+int frk_optim_nelder_mead(frk_objective_fn fn, void *user, int n, const double *par, int maxit,
+                          double reltol, double *x_out, double *f_out, int *count_out, int *fail_out);
+int frk_optim_zeroin(frk_objective_fn fn, void *user, double lower, double upper, double *root_out);
 
 /* ---- host-buffer entry points (what the R .Call shim binds; H2D/D2H inside) ------------ */
 /* eval_basis on host coordinates -> host CSR.  Call with h_col == NULL to get nnz only.     */

@@ -28,7 +28,7 @@ def test_zeroin_matches_oracle_port_and_brentq():
     r1 = zeroin(f, 1e-3, 10.0)
     assert r1 == O.zeroin(f, 1e-3, 10.0)
     assert abs(r1 - so.brentq(f, 1e-3, 10.0)) < 2e-4            # uniroot's default tol = eps^0.25
-    with pytest.raises(RuntimeError, match="opposite sign"):
+    with pytest.raises(F.FRKError, match="opposite sign"):
         zeroin(f, 5.0, 10.0)
 
 
@@ -88,5 +88,10 @@ def test_SRE_argument_checks_run_before_any_device_work():
     data = F.SpatialPointsDataFrame(xy, {"z": xy[:, 0], "std": np.ones(10)})
     gb = F.auto_BAUs(F.plane(), cellsize=0.1, data=data)
     basis = F.auto_basis(F.plane(), xy, nres=1)
+    with pytest.raises(ValueError, match="BAUs should contain a field 'fs'"):       # reference message (R/check_args.R)
+        F.SRE("z ~ 1", data, basis, gb, est_error=False)
+    gb["fs"] = 1.0
+    with pytest.raises(ValueError, match="block-exponential"):
+        F.SRE("z ~ 1", data, basis, gb, est_error=False, K_type="precision")
     with pytest.raises(F.FRKError, match="no CPU fallback"):       # no device -> loud failure, never a CPU path
         F.SRE("z ~ 1", data, basis, gb, est_error=False)
