@@ -1,0 +1,176 @@
+/*
+ * frkb200_R.c -- the `.Call` shim between the R package FRK and libfrkb200.so.
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no R (no R.h / Rinternals.h / libR).  It is the
+ * binding a maintainer adds to FRK's src/ (next to src/FRK-init.h, whose registration pattern it follows:
+ * R_CallMethodDef + R_registerRoutines + R_useDynamicSymbols(FALSE), src/FRK-init.h:38-55).  It only unpacks
+ * SEXP arguments, calls the C ABI declared in include/frkb200.h, and packs the results; every call that the
+ * Python ctypes harness (frk_b200/_lib.py) makes in the test-suite maps 1:1 onto a call below.
+ *
+ * Build (on a machine with R and CUDA):
+ *   R CMD SHLIB frkb200_R.c -I../../include -L../../frk_b200 -lfrkb200 -Wl,-rpath,<dir of libfrkb200.so>
+ *
+ * Conventions: R matrices are column-major doubles (as the C ABI expects); R indices are 1-based and are
+ * converted here; inputs are never modified (copy-on-modify); outputs are fresh allocVector()s; errors are raised
+ * with Rf_error() only after every temporary has been released; the device-resident SRE object is handed to R as
+ * an external pointer with a finalizer.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <stdlib.h>
+#include <string.h>
+#include "frkb200.h"
+
+static frk_ctx *g_ctx = NULL;
+
+static frk_ctx *ctx_or_error(void) {
+    if (!g_ctx && frk_ctx_create(0, NULL, &g_ctx)) Rf_error("frkb200: %s", frk_last_error());
+    return g_ctx;
+}
+
+#define FRK_TRY(expr, cleanup)                                                      \
+    do { if ((expr) != 0) { cleanup; Rf_error("frkb200: %s", frk_last_error()); } } while (0)
+
+/* ---- basis handle: local_basis()/auto_basis() result -> device cell lists ------------------------------------ */
+static void basis_finalizer(SEXP p) { frk_basis_destroy((frk_basis *)R_ExternalPtrAddr(p)); R_ClearExternalPtr(p); }
+
+/* .Call(frkb200_basis_create, manifold_code, radius, type_code, loc (r x d), scale (r), res (r)) */
+SEXP frkb200_basis_create(SEXP manifold, SEXP radius, SEXP type, SEXP loc, SEXP scale, SEXP res) {
+    frk_basis *b = NULL;
+    int r = Rf_nrows(loc), d = Rf_ncols(loc);
+    FRK_TRY(frk_basis_create(ctx_or_error(), Rf_asInteger(manifold), Rf_asReal(radius), Rf_asInteger(type), d, r, REAL(loc),
+                             REAL(scale), INTEGER(res), &b), (void)0);
+    SEXP p = PROTECT(R_MakeExternalPtr(b, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(p, basis_finalizer, TRUE);
+    UNPROTECT(1);
+    return p;
+}
+
+/* eval_basis(Basis, matrix): returns list(p = rowptr (n+1), j = col (nnz), x = val (nnz)) -- the slots of a dgRMatrix
+ * (R/basisfns.R:709-748).  The overlay wraps it with new("dgRMatrix", ...) and as(., "CsparseMatrix"). */
+SEXP frkb200_eval_basis(SEXP basis, SEXP s, SEXP normalise) {
+    frk_basis *b = (frk_basis *)R_ExternalPtrAddr(basis);
+    int64_t n = Rf_nrows(s), nnz = 0;
+    SEXP rp = PROTECT(Rf_allocVector(INTSXP, n + 1));
+    FRK_TRY(frk_eval_basis_host(ctx_or_error(), b, n, REAL(s), Rf_asInteger(normalise), INTEGER(rp), NULL, NULL, &nnz), UNPROTECT(1));
+    SEXP cj = PROTECT(Rf_allocVector(INTSXP, nnz)), x = PROTECT(Rf_allocVector(REALSXP, nnz));
+    FRK_TRY(frk_eval_basis_host(g_ctx, b, n, REAL(s), Rf_asInteger(normalise), INTEGER(rp), INTEGER(cj), REAL(x), &nnz), UNPROTECT(3));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, rp); SET_VECTOR_ELT(out, 1, cj); SET_VECTOR_ELT(out, 2, x);
+    UNPROTECT(4);
+    return out;
+}
+
+/* sp::over(SpatialPoints, SpatialPixels) inside map_data_to_BAUs (R/geometryfns.R:1266): 1-based BAU row, NA outside */
+SEXP frkb200_grid_lookup(SEXP xy, SEXP offset, SEXP cellsize, SEXP dims, SEXP cell2bau) {
+    int64_t n = Rf_nrows(xy);
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, n));
+    int ncell = Rf_length(cell2bau), *map = (int *)malloc(sizeof(int) * (ncell ? ncell : 1));
+    for (int i = 0; i < ncell; i++) map[i] = INTEGER(cell2bau)[i] == NA_INTEGER ? -1 : INTEGER(cell2bau)[i] - 1;
+    FRK_TRY(frk_grid_lookup_host(ctx_or_error(), n, REAL(xy), REAL(offset), REAL(cellsize), INTEGER(dims), ncell ? map : NULL, ncell,
+                                 INTEGER(out)), (free(map), UNPROTECT(1)));
+    free(map);
+    for (int64_t i = 0; i < n; i++) INTEGER(out)[i] = INTEGER(out)[i] < 0 ? NA_INTEGER : INTEGER(out)[i] + 1;
+    UNPROTECT(1);
+    return out;
+}
+
+/* ---- the SRE object on the device ------------------------------------------------------------------------------ */
+static void model_finalizer(SEXP p) { frk_model_destroy((frk_model *)R_ExternalPtrAddr(p)); R_ClearExternalPtr(p); }
+
+/* .Call(frkb200_model_create, Sp, Sj, Sx (dgRMatrix slots of object@S, 0-based), r, Z, X, diag(Ve), diag(Vfs)) */
+SEXP frkb200_model_create(SEXP Sp, SEXP Sj, SEXP Sx, SEXP r, SEXP Z, SEXP X, SEXP Ve, SEXP Vfs) {
+    frk_model *m = NULL;
+    FRK_TRY(frk_model_create_host(ctx_or_error(), Rf_length(Z), Rf_asInteger(r), Rf_ncols(X), INTEGER(Sp), INTEGER(Sj), REAL(Sx),
+                                  REAL(Z), REAL(X), REAL(Ve), REAL(Vfs), &m), (void)0);
+    SEXP p = PROTECT(R_MakeExternalPtr(m, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(p, model_finalizer, TRUE);
+    UNPROTECT(1);
+    return p;
+}
+
+/* D_basis (list of per-resolution distance matrices, BuildD R/basisfns.R:1131-1153) + basis@df$res */
+SEXP frkb200_model_set_blocks(SEXP mdl, SEXP res, SEXP Dlist) {
+    int nres = Rf_length(Dlist);
+    const double **D = (const double **)malloc(sizeof(double *) * nres);
+    for (int i = 0; i < nres; i++) D[i] = REAL(VECTOR_ELT(Dlist, i));
+    FRK_TRY(frk_model_set_blocks((frk_model *)R_ExternalPtrAddr(mdl), nres, INTEGER(res), D), free(D));
+    free(D);
+    return R_NilValue;
+}
+
+/* push the slots of the S4 object (so that saveRDS()/readRDS() between SRE.fit calls resumes EM) */
+SEXP frkb200_model_set(SEXP mdl, SEXP name, SEXP value) {
+    FRK_TRY(frk_model_set((frk_model *)R_ExternalPtrAddr(mdl), CHAR(STRING_ELT(name, 0)), REAL(value)), (void)0);
+    return R_NilValue;
+}
+
+SEXP frkb200_model_get(SEXP mdl, SEXP name, SEXP len) {
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)Rf_asReal(len)));
+    FRK_TRY(frk_model_get((frk_model *)R_ExternalPtrAddr(mdl), CHAR(STRING_ELT(name, 0)), REAL(out)), UNPROTECT(1));
+    UNPROTECT(1);
+    return out;
+}
+
+/* .EM_fit (R/SREfit.R:78-160) in one call: returns list(llk = numeric(niter), niter) */
+SEXP frkb200_em_fit(SEXP mdl, SEXP n_EM, SEXP tol, SEXP K_type, SEXP lambda, SEXP res, SEXP known_sigma2fs) {
+    int n = Rf_asInteger(n_EM), niter = 0, known = !Rf_isNull(known_sigma2fs);
+    double *llk = (double *)calloc(n > 0 ? n : 1, sizeof(double));
+    FRK_TRY(frk_model_em_fit((frk_model *)R_ExternalPtrAddr(mdl), n, Rf_asReal(tol), Rf_asInteger(K_type), Rf_length(lambda), REAL(lambda),
+                             INTEGER(res), known, known ? Rf_asReal(known_sigma2fs) : 0.0, llk, &niter), free(llk));
+    R_CheckUserInterrupt();
+    SEXP v = PROTECT(Rf_allocVector(REALSXP, niter));
+    memcpy(REAL(v), llk, sizeof(double) * niter);
+    free(llk);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, v); SET_VECTOR_ELT(out, 1, Rf_ScalarInteger(niter));
+    UNPROTECT(2);
+    return out;
+}
+
+/* .batch_compute_var(S0, Cov) (R/SREutils.R:245-305) and S0 %*% mu for a host dgRMatrix: list(var, smu) */
+SEXP frkb200_quadform(SEXP Sp, SEXP Sj, SEXP Sx, SEXP Cov, SEXP mu) {
+    int64_t n = Rf_length(Sp) - 1;
+    int r = Rf_nrows(Cov);
+    SEXP q = PROTECT(Rf_allocVector(REALSXP, n)), t = PROTECT(Rf_allocVector(REALSXP, n));
+    FRK_TRY(frk_quadform_host(ctx_or_error(), n, r, INTEGER(Sp), INTEGER(Sj), REAL(Sx), REAL(Cov), REAL(mu), REAL(q), REAL(t)), UNPROTECT(2));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, q); SET_VECTOR_ELT(out, 1, t);
+    UNPROTECT(3);
+    return out;
+}
+
+/* chol2inv(chol(A)) with attr "logdet" = determinant(A, logarithm = TRUE)$modulus (R/SREfit.R:178-179,253,273) */
+SEXP frkb200_chol2inv(SEXP A) {
+    int r = Rf_nrows(A);
+    double ld = 0.0;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, r, r));
+    FRK_TRY(frk_chol2inv_host(ctx_or_error(), r, REAL(A), REAL(out), &ld), UNPROTECT(1));
+    Rf_setAttrib(out, Rf_install("logdet"), Rf_ScalarReal(ld));
+    UNPROTECT(1);
+    return out;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"frkb200_basis_create", (DL_FUNC)&frkb200_basis_create, 6},
+    {"frkb200_eval_basis", (DL_FUNC)&frkb200_eval_basis, 3},
+    {"frkb200_grid_lookup", (DL_FUNC)&frkb200_grid_lookup, 5},
+    {"frkb200_model_create", (DL_FUNC)&frkb200_model_create, 8},
+    {"frkb200_model_set_blocks", (DL_FUNC)&frkb200_model_set_blocks, 3},
+    {"frkb200_model_set", (DL_FUNC)&frkb200_model_set, 3},
+    {"frkb200_model_get", (DL_FUNC)&frkb200_model_get, 3},
+    {"frkb200_em_fit", (DL_FUNC)&frkb200_em_fit, 7},
+    {"frkb200_quadform", (DL_FUNC)&frkb200_quadform, 5},
+    {"frkb200_chol2inv", (DL_FUNC)&frkb200_chol2inv, 1},
+    {NULL, NULL, 0}};
+
+void R_init_frkb200(DllInfo *dll) {
+    R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}
+
+void R_unload_frkb200(DllInfo *dll) {
+    (void)dll;
+    if (g_ctx) { frk_ctx_destroy(g_ctx); g_ctx = NULL; }
+}

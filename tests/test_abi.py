@@ -67,3 +67,12 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("frk_oracle", "oracle") or "import" not in "".join(
                     ln for ln in txt.splitlines() if "oracle" in ln), f"{f} references the oracle"
+
+
+def test_r_call_shim_type_checks_against_the_header():
+    """r/src/frkb200_R.c (the .Call shim of INTEGRATION.md) cannot be built here (no R), but it must at least type-check
+    against include/frkb200.h: compile it with -fsyntax-only against declaration-only stand-ins for R's headers."""
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "r_stub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "src", "frkb200_R.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
