@@ -270,19 +270,20 @@ def run_b200(args):
         rep = json.loads(buf.value.decode())
         # algorithmic bytes of the streaming kernels (DESIGN.md "roofline accounting")
         nloc = mdl.hi - mdl.lo
-        gram_bytes = mdl.S.nnz * 12 + mdl.m * (4 + 8 * (3 + mdl.p)) + (r * r + r) * 8
-        quad_S_bytes = mdl.S.nnz * 12 + mdl.m * (4 + 16) + r * r * 8
-        quad_S0_bytes = mdl.S0.nnz * 12 + nloc * (4 + 16) + r * r * 8
+        # (val 8 B + local column id 1 B per non-zero; the 4-byte global column index is not read by the bucketed kernels)
+        gram_bytes = mdl.S.nnz * 9 + mdl.m * (4 + 8 * (3 + mdl.p)) + (r * r + r) * 8
+        quad_S_bytes = mdl.S.nnz * 9 + mdl.m * (4 + 16) + r * r * 8
+        quad_S0_bytes = mdl.S0.nnz * 9 + nloc * (4 + 16) + r * r * 8
         tot_ms = sum(k["ms"] for k in rep) or 1.0
         for k in sorted(rep, key=lambda k: -k["ms"]):
             ent = {"kernel": k["kernel"], "launches": k["launches"], "ms_total": round(k["ms"], 3), "share": round(k["ms"] / tot_ms, 4)}
             if k["flops"] > 0:
                 ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
                 ent.update(bound="fp64", achieved=ach, peak=fp64_peak, unit="TFLOP/s", frac=ach / fp64_peak)
-            elif "gram_rhs_kernel" in k["kernel"]:
+            elif "gram_bucket_kernel" in k["kernel"]:
                 ach = gram_bytes * k["launches"] / (k["ms"] * 1e-3) / 1e9
                 ent.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak)
-            elif "quadform_spmv_kernel" in k["kernel"]:
+            elif "quadform_bucket_kernel" in k["kernel"]:
                 # launches: 2 on S (M-step), 1 on S0 (predict)
                 by = quad_S_bytes * n_f_tau_launch_iters + quad_S0_bytes
                 ach = by / (k["ms"] * 1e-3) / 1e9

@@ -29,7 +29,7 @@ struct Buckets {
 struct Block {                    // one resolution of the block-exponential K
     int ni = 0, ix0 = 0;
     int *d_ix = nullptr;
-    double *D = nullptr, *eta2 = nullptr, *Ki = nullptr, *Kinv = nullptr, *work = nullptr;
+    double *D = nullptr, *eta2 = nullptr, *Ki = nullptr, *Kinv = nullptr, *work = nullptr, *KinvBest = nullptr;
     double D01 = 0.0;
 };
 
@@ -53,6 +53,7 @@ struct frk_model {
     double sigma2fs = 0.0, logdetK = 0.0;
     double m_total = 0.0, Ve0 = 0.0, Vfs0 = 0.0;
     bool homoscedastic = false, all_vfs_zero = false, initialised = false;
+    bool khat_block_diag = false;   // Khat is block diagonal by resolution AND Khat_inv = chol2inv(chol(Khat)) (init / block-exponential update)
     // block-exponential K
     std::vector<Block> blocks;
     double max_l = 0.0;
@@ -367,7 +368,8 @@ int chol2inv_logdet(frk_ctx *ctx, int n, double *A, double *Ainv, double *work, 
 // ---------------------------------------------------------------------------------
 // M-step
 // ---------------------------------------------------------------------------------
-int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const int *h_res) {
+int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const int *h_res, bool &have_inverse) {
+    have_inverse = false;
     frk_ctx *ctx = M->ctx;
     const int r = M->r;
     const size_t rr = (size_t)r * r;
@@ -387,10 +389,12 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         return 0;
     }
     FRK_REQUIRE(!M->blocks.empty(), "K_type = \"block-exponential\" needs the per-resolution distance matrices (frk_model_set_blocks)");
-    // Knew is assembled in w1 (free here); Khat (old) is read for the start values
+    // K_new is assembled in w1 and K_new^-1 in w2 (both free here); the old Khat / Khat_inv are read for omega and the start values
     M->taus.clear(); M->omegas.clear();
-    double *Knew = M->w1;
+    double *Knew = M->w1, *Kinvnew = M->w2;
     FRK_CHECK_CUDA(cudaMemsetAsync(Knew, 0, rr * sizeof(double), ctx->stream));
+    FRK_CHECK_CUDA(cudaMemsetAsync(Kinvnew, 0, rr * sizeof(double), ctx->stream));
+    double logdetK = 0.0;
     for (Block &B : M->blocks) {
         const int ni = B.ni;
         const size_t nn = (size_t)ni * ni;
@@ -402,17 +406,29 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         RC(frk_d2h(ctx, k2, B.Ki, sizeof(double) * std::min<size_t>(2, nn)));
         const double k00 = k2[0], k01 = ni > 1 ? k2[1] : 0.0;
         double ld, trc;
-        RC(chol2inv_logdet(ctx, ni, B.Ki, B.Kinv, B.work, &ld));
+        if (M->khat_block_diag) {
+            // Khat is block diagonal, so (Khat[idx,idx])^-1 is the idx-block of Khat_inv = chol2inv(chol(Khat)) already held
+            RC(frk_block_gather(ctx, r, M->Khat_inv, ni, B.d_ix, B.Kinv));
+        } else {
+            RC(chol2inv_logdet(ctx, ni, B.Ki, B.Kinv, B.work, &ld));
+        }
         RC(frk_dot(ctx, (int64_t)nn, B.Kinv, B.eta2, &trc));
         const double omega = ni / (k00 * trc);                       // (K/k00)^-1 = k00 K^-1
         M->omegas.push_back(omega);
-        auto f_tau = [&](const double *tau, double &fval) -> int {  // :485-529
+        // f_tau, :485-529.  The inverse and log-determinant at the best tau seen are kept: Nelder-Mead returns its lowest
+        // vertex, i.e. an evaluated point, so K_i(tau*)^-1 and log|K_i(tau*)| need no further factorisation.
+        double bestF = std::numeric_limits<double>::infinity(), bestTau = -1.0, bestLogdet = 0.0;
+        auto f_tau = [&](const double *tau, double &fval) -> int {
             if (tau[0] <= 1e-10) { fval = std::numeric_limits<double>::infinity(); return 0; }
             RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau[0], 1.0, B.Ki));
             double logdetKi, t;
             RC(chol2inv_logdet(ctx, ni, B.Ki, B.Kinv, B.work, &logdetKi));
             RC(frk_dot(ctx, (int64_t)nn, B.Kinv, B.eta2, &t));
             fval = -(0.5 * (-logdetKi) - omega / 2.0 * t);
+            if (fval < bestF) {
+                bestF = fval; bestTau = tau[0]; bestLogdet = logdetKi;
+                FRK_CHECK_CUDA(cudaMemcpyAsync(B.KinvBest, B.Kinv, nn * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
             return 0;
         };
         double par0 = 1e-9;                                          // :608-614
@@ -423,11 +439,25 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         if (!std::isfinite(par0) || par0 == 1e-9) par0 = M->max_l / 10.0;
         NMResult nm;
         RC(nmmin(f_tau, std::vector<double>{par0}, nm, 100, 1e-4));   // optim(): Nelder-Mead, :618-621
-        M->taus.push_back(nm.x[0]);
-        RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, nm.x[0], 1.0 / omega, B.Ki));   // K_i = exp(-D_i/tau_i)/omega_i, :625-637
+        const double tau = nm.x[0];
+        M->taus.push_back(tau);
+        if (bestTau != tau) {                                        // (does not happen with nmmin's acceptance rules; kept for safety)
+            bestF = std::numeric_limits<double>::infinity();
+            double f;
+            RC(f_tau(&tau, f));
+            FRK_REQUIRE(bestTau == tau, "block-exponential update: tau = %g cannot be evaluated", tau);
+        }
+        RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau, 1.0 / omega, B.Ki));       // K_i = exp(-D_i/tau_i)/omega_i, :625-637
         RC(frk_block_scatter(ctx, r, Knew, ni, B.d_ix, B.Ki));
+        RC(frk_scale(ctx, (int64_t)nn, omega, B.KinvBest));                       // K_i^-1 = omega_i exp(-D_i/tau_i)^-1
+        RC(frk_block_scatter(ctx, r, Kinvnew, ni, B.d_ix, B.KinvBest));
+        logdetK += bestLogdet - ni * std::log(omega);
     }
     FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat, Knew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat_inv, Kinvnew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    M->logdetK = logdetK;
+    M->khat_block_diag = true;
+    have_inverse = true;                                             // Khat_inv = chol2inv(chol(K)) (:273) block by block
     return 0;
 }
 
@@ -436,9 +466,13 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
     const int r = M->r, p = M->p;
     const size_t rr = (size_t)r * r;
     const double sigma2fs = M->sigma2fs;
-    RC(update_K(M, K_type, nlambda, lambda, h_res));                 // :270-272
-    FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, M->Khat, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    RC(chol2inv_logdet(ctx, r, M->w1, M->Khat_inv, M->w2, &M->logdetK));   // Khat_inv = chol2inv(chol(K)), :273
+    bool have_inverse = false;
+    RC(update_K(M, K_type, nlambda, lambda, h_res, have_inverse));   // :270-272
+    if (!have_inverse) {
+        FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, M->Khat, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        RC(chol2inv_logdet(ctx, r, M->w1, M->Khat_inv, M->w2, &M->logdetK));   // Khat_inv = chol2inv(chol(K)), :273
+        M->khat_block_diag = false;
+    }
     const bool est = !known;
     double s2new = est ? sigma2fs : known_sigma2fs;
     // Omega_diag1 = rowSums((S R_eta')^2) = s_j'(S_eta + mu mu')s_j = q_j + t_j^2,  t = S mu_eta     :332-334
@@ -587,7 +621,7 @@ extern "C" int frk_model_set_blocks(frk_model *M, int nres, const int *h_res, co
         B.ni = (int)ix.size(); B.ix0 = ix[0];
         const size_t nn = (size_t)B.ni * B.ni;
         RC(dalloc(M, &B.d_ix, ix.size())); RC(dalloc(M, &B.D, nn)); RC(dalloc(M, &B.eta2, nn)); RC(dalloc(M, &B.Ki, nn));
-        RC(dalloc(M, &B.Kinv, nn)); RC(dalloc(M, &B.work, nn));
+        RC(dalloc(M, &B.Kinv, nn)); RC(dalloc(M, &B.work, nn)); RC(dalloc(M, &B.KinvBest, nn));
         FRK_CHECK_CUDA(cudaMemcpy(B.d_ix, ix.data(), ix.size() * sizeof(int), cudaMemcpyHostToDevice));
         FRK_CHECK_CUDA(cudaMemcpy(B.D, h_D[i - 1], nn * sizeof(double), cudaMemcpyHostToDevice));
         B.D01 = B.ni > 1 ? h_D[i - 1][B.ni] : 0.0;                   // D[1,2] (column-major, symmetric)
@@ -615,6 +649,7 @@ extern "C" int frk_model_init(frk_model *M) {
     RC(frk_scaled_identity(ctx, r, 1.0 / (1.0 / (1.0 / varZ)), M->Khat_inv));
     FRK_CHECK_CUDA(cudaMemsetAsync(M->mu_eta, 0, r * sizeof(double), ctx->stream));
     M->logdetK = r * std::log(varZ);
+    M->khat_block_diag = true;                                       // diagonal K, Khat_inv its inverse
     // alpha = (X'X)^-1 X'Z: the mode-1 moments with t = 0
     FRK_CHECK_CUDA(cudaMemsetAsync(M->t, 0, std::max<int64_t>(M->m, 1) * sizeof(double), ctx->stream));
     MSums s;
@@ -692,6 +727,7 @@ extern "C" int frk_model_set(frk_model *M, const char *slot, const double *h_in)
     FRK_REQUIRE(p, "frk_model_set: unknown slot '%s'", slot);
     RC(frk_h2d(M->ctx, p, h_in, n * sizeof(double)));
     FRK_CHECK_CUDA(cudaStreamSynchronize(M->ctx->stream));
+    if (!strcmp(slot, "Khat") || !strcmp(slot, "Khat_inv")) M->khat_block_diag = false;   // caller-supplied: assume nothing
     if (!strcmp(slot, "Khat")) {                                     // keep log|K| consistent with the slot (.loglik.ind :177,197)
         const size_t rr = (size_t)M->r * M->r;
         FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, M->Khat, rr * sizeof(double), cudaMemcpyDeviceToDevice, M->ctx->stream));

@@ -405,3 +405,16 @@ extern "C" int frk_gather_rows(frk_ctx *ctx, int64_t m, int ncols, const int *d_
     FRK_LAUNCH(ctx, gather_rows_kernel, grid, 256, 0, m, ncols, d_idx, d_src, ld_src, d_dst, ld_dst);
     return 0;
 }
+
+// x *= alpha   (K_i^-1 = omega_i exp(-D_i/tau_i)^-1 in the block-exponential update, R/SREfit.R:625-637)
+__global__ void scale_kernel(int64_t n, double alpha, double *__restrict__ x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= alpha;
+}
+
+extern "C" int frk_scale(frk_ctx *ctx, int64_t n, double alpha, double *d_x) {
+    FRK_REQUIRE(ctx && (n == 0 || d_x), "frk_scale: NULL argument");
+    if (n == 0) return 0;
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, scale_kernel, grid, 256, 0, n, alpha, d_x);
+    return 0;
+}
