@@ -70,8 +70,10 @@ SIGNATURES = {
     "frk_csr_gather_fill": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),
     "frk_gram_rhs": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, c_int, vp, vp, vp, c_dbl, vp]),
     "frk_csr_bucket_rows": (c_int, [vp, c_i64, vp, vp, c_int, vp, vp, vp, vp, vp]),
-    "frk_gram_rhs_bucketed": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp, vp, c_dbl, vp]),
-    "frk_quadform_spmv_bucketed": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "frk_rowbuckets_create": (c_int, [vp, c_i64, c_int, vp, vp, vp, C.POINTER(vp)]),
+    "frk_rowbuckets_destroy": (c_int, [vp]),
+    "frk_gram_rhs_bucketed": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, c_int, vp, vp, vp, c_dbl, vp]),
+    "frk_quadform_spmv_bucketed": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_quadform_spmv": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp]),
     "frk_mstep_sums": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, c_dbl, c_int, vp]),
     "frk_vec_stats": (c_int, [vp, c_i64, vp, c_dbl, vp]),
@@ -108,7 +110,7 @@ SIGNATURES = {
     "frk_model_get": (c_int, [vp, C.c_char_p, vp]),
     "frk_model_set": (c_int, [vp, C.c_char_p, vp]),
     "frk_model_slot_device": (c_int, [vp, C.c_char_p, C.POINTER(vp)]),
-    "frk_model_predict": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp, vp]),
+    "frk_model_predict": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp, vp]),
     "frk_optim_nelder_mead": (c_int, [OBJECTIVE_FN, vp, c_int, vp, c_int, c_dbl, vp, p_dbl, p_int, p_int]),
     "frk_optim_zeroin": (c_int, [OBJECTIVE_FN, vp, c_dbl, c_dbl, p_dbl]),
     "frk_eval_basis_host": (c_int, [vp, vp, c_i64, vp, c_int, vp, vp, vp, p_i64]),

@@ -194,18 +194,23 @@ class DeviceCSR:
     def __init__(self, n, ncol, rowptr, col, val, nnz):
         self.n, self.ncol, self.rowptr, self.col, self.val, self.nnz = int(n), int(ncol), rowptr, col, val, int(nnz)
 
-    _buckets = None      # row buckets (frk_csr_bucket_rows), built on first use
+    _buckets = None      # frk_rowbuckets handle (row buckets + ELL tiles), built on first use
 
     def buckets(self, dev: Device):
-        """(perm, bptr, ucol, nU, lid) device arrays as ctypes pointers, in the C-ABI argument order."""
         if self._buckets is None:
-            b = dict(perm=dev.empty(max(self.n, 1), "i4"), bptr=dev.empty(self.ncol + 1, "i4"),
-                     ucol=dev.empty(self.ncol * 64, "i4"), nU=dev.empty(self.ncol, "i4"), lid=dev.empty(max(self.nnz, 1), "u1"))
-            call("frk_csr_bucket_rows", dev.ctx, self.n, dev.ptr(self.rowptr), dev.ptr(self.col), self.ncol,
-                 dev.ptr(b["perm"]), dev.ptr(b["bptr"]), dev.ptr(b["ucol"]), dev.ptr(b["nU"]), dev.ptr(b["lid"]))
-            self._buckets = b
-        b = self._buckets
-        return [dev.ptr(b[k]) for k in ("perm", "bptr", "ucol", "nU", "lid")]
+            h = vp()
+            call("frk_rowbuckets_create", dev.ctx, self.n, self.ncol, dev.ptr(self.rowptr), dev.ptr(self.col), dev.ptr(self.val),
+                 C.byref(h))
+            self._buckets = h
+        return self._buckets
+
+    def __del__(self):
+        try:
+            if self._buckets is not None:
+                lib.frk_rowbuckets_destroy(self._buckets)
+                self._buckets = None
+        except Exception:
+            pass
 
     def to_scipy(self, dev: Device) -> sp.csr_matrix:
         rp = dev.download(self.rowptr, self.n + 1)

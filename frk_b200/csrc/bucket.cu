@@ -182,6 +182,133 @@ extern "C" int frk_csr_bucket_rows(frk_ctx *ctx, int64_t n, const int *d_rowptr,
 }
 
 // ---------------------------------------------------------------------------------
+// frk_rowbuckets: the bucket arrays plus a bucket-ordered, transposed copy of the matrix ("ELL tiles").
+// A tile is 32 consecutive rows of a bucket (in perm order) stored entry-major: val[e][lane], lid[e][lane] for
+// e < K_tile = the longest row of the tile (shorter rows padded with val = 0, lid = 0).  A warp reads a tile with
+// fully coalesced 16-byte cp.async copies -- no per-row pointer chasing in the per-iteration kernels.
+// ---------------------------------------------------------------------------------
+struct frk_rowbuckets {
+    frk_ctx *ctx = nullptr;
+    int64_t n = 0;
+    int ncols = 0;
+    int *perm = nullptr, *bptr = nullptr, *ucol = nullptr, *nU = nullptr;
+    unsigned char *lid = nullptr;
+    // ELL tiles
+    int T = 0;
+    int *btile = nullptr;          // [ncols+1] first tile of every bucket
+    int *tile_K = nullptr;         // [T] entries per row in the tile; -1: a row is longer than KMAX (direct path)
+    int *tile_off = nullptr;       // [T+1] offset of the tile in ell_val / ell_lid (entries)
+    double *ell_val = nullptr;
+    unsigned char *ell_lid = nullptr;
+    std::vector<void *> allocs;
+};
+
+__global__ void ell_tiles_per_bucket_kernel(int ncols, const int *__restrict__ bptr, const int *__restrict__ nU, int *__restrict__ cnt) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < ncols) cnt[b] = nU[b] > UMAX ? 0 : (bptr[b + 1] - bptr[b] + 31) / 32;
+}
+
+// one warp per bucket-tile: K = longest row
+__global__ void __launch_bounds__(256) ell_tile_K_kernel(int ncols, const int *__restrict__ bptr, const int *__restrict__ btile,
+                                                         const int *__restrict__ perm, const int *__restrict__ rowptr,
+                                                         int *__restrict__ tile_K, int *__restrict__ tile_len) {
+    const int lane = threadIdx.x & 31;
+    for (int b = blockIdx.x; b < ncols; b += gridDim.x) {
+        const int t0 = btile[b], t1 = btile[b + 1], r0 = bptr[b], r1 = bptr[b + 1];
+        for (int t = t0 + (threadIdx.x >> 5); t < t1; t += blockDim.x >> 5) {
+            const int p = r0 + (t - t0) * 32 + lane;
+            int k = 0;
+            if (p < r1) { const int row = perm[p]; k = rowptr[row + 1] - rowptr[row]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, o));
+            if (lane == 0) { tile_K[t] = k > KMAX ? -1 : k; tile_len[t] = k > KMAX ? 0 : k * 32; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ell_fill_kernel(int ncols, const int *__restrict__ bptr, const int *__restrict__ btile,
+                                                       const int *__restrict__ perm, const int *__restrict__ rowptr,
+                                                       const double *__restrict__ val, const unsigned char *__restrict__ lid,
+                                                       const int *__restrict__ tile_K, const int *__restrict__ tile_off,
+                                                       double *__restrict__ ell_val, unsigned char *__restrict__ ell_lid) {
+    const int lane = threadIdx.x & 31;
+    for (int b = blockIdx.x; b < ncols; b += gridDim.x) {
+        const int t0 = btile[b], t1 = btile[b + 1], r0 = bptr[b], r1 = bptr[b + 1];
+        for (int t = t0 + (threadIdx.x >> 5); t < t1; t += blockDim.x >> 5) {
+            const int K = tile_K[t];
+            if (K <= 0) continue;
+            const int p = r0 + (t - t0) * 32 + lane;
+            int beg = 0, k = 0;
+            if (p < r1) { const int row = perm[p]; beg = rowptr[row]; k = rowptr[row + 1] - beg; }
+            const size_t off = (size_t)tile_off[t];
+            for (int e = 0; e < K; e++) {
+                ell_val[off + (size_t)e * 32 + lane] = e < k ? val[beg + e] : 0.0;
+                ell_lid[off + (size_t)e * 32 + lane] = e < k ? lid[beg + e] : (unsigned char)0;
+            }
+        }
+    }
+}
+
+template <typename T>
+static int rb_alloc(frk_rowbuckets *B, T **out, size_t n) {
+    void *p = nullptr;
+    FRK_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
+    B->allocs.push_back(p);
+    *out = (T *)p;
+    return 0;
+}
+
+extern "C" int frk_rowbuckets_destroy(frk_rowbuckets *B) {
+    if (!B) return 0;
+    cudaSetDevice(B->ctx->device);
+    cudaStreamSynchronize(B->ctx->stream);
+    for (void *p : B->allocs) cudaFree(p);
+    delete B;
+    return 0;
+}
+
+extern "C" int frk_rowbuckets_create(frk_ctx *ctx, int64_t n, int ncols, const int *d_rowptr, const int *d_col, const double *d_val,
+                                     frk_rowbuckets **out) {
+    FRK_REQUIRE(ctx && out && d_rowptr && ncols > 0 && n >= 0, "frk_rowbuckets_create: bad argument");
+    frk_rowbuckets *B = new frk_rowbuckets();
+    B->ctx = ctx; B->n = n; B->ncols = ncols;
+    auto fail = [&](int rc) { frk_rowbuckets_destroy(B); return rc; };
+    int nnz = 0;
+    if (int rc = frk_d2h(ctx, &nnz, d_rowptr + n, sizeof(int))) return fail(rc);
+    if (rb_alloc(B, &B->perm, (size_t)std::max<int64_t>(n, 1)) || rb_alloc(B, &B->bptr, (size_t)ncols + 1) ||
+        rb_alloc(B, &B->ucol, (size_t)ncols * UMAX) || rb_alloc(B, &B->nU, (size_t)ncols) || rb_alloc(B, &B->lid, (size_t)std::max(nnz, 1)) ||
+        rb_alloc(B, &B->btile, (size_t)ncols + 1))
+        return fail(1);
+    if (int rc = frk_csr_bucket_rows(ctx, n, d_rowptr, d_col, ncols, B->perm, B->bptr, B->ucol, B->nU, B->lid)) return fail(rc);
+    if (n == 0) { cudaMemsetAsync(B->btile, 0, (size_t)(ncols + 1) * sizeof(int), ctx->stream); *out = B; return 0; }
+    // tiles per bucket -> btile
+    int *cnt = nullptr;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&cnt, (size_t)ncols * sizeof(int), ctx->stream));
+    FRK_LAUNCH(ctx, ell_tiles_per_bucket_kernel, (unsigned)cdiv(ncols, 256), 256, 0, ncols, B->bptr, B->nU, cnt);
+    int64_t T = 0;
+    int rc = frk_exclusive_scan_i32(ctx, cnt, ncols, B->btile, &T);
+    cudaFreeAsync(cnt, ctx->stream);
+    if (rc) return fail(rc);
+    B->T = (int)T;
+    if (T == 0) { *out = B; return 0; }
+    int *tile_len = nullptr;
+    if (rb_alloc(B, &B->tile_K, (size_t)T) || rb_alloc(B, &B->tile_off, (size_t)T + 1)) return fail(1);
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&tile_len, (size_t)T * sizeof(int), ctx->stream));
+    const unsigned grid = (unsigned)std::min<int64_t>(ncols, (int64_t)ctx->sm_count * 8);
+    FRK_LAUNCH(ctx, ell_tile_K_kernel, grid, 256, 0, ncols, B->bptr, B->btile, B->perm, d_rowptr, B->tile_K, tile_len);
+    int64_t total = 0;
+    rc = frk_exclusive_scan_i32(ctx, tile_len, T, B->tile_off, &total);
+    cudaFreeAsync(tile_len, ctx->stream);
+    if (rc) return fail(rc);
+    if (rb_alloc(B, &B->ell_val, (size_t)std::max<int64_t>(total, 1)) || rb_alloc(B, &B->ell_lid, (size_t)std::max<int64_t>(total, 1) + 16))
+        return fail(1);
+    FRK_LAUNCH(ctx, ell_fill_kernel, grid, 256, 0, ncols, B->bptr, B->btile, B->perm, d_rowptr, d_val, B->lid, B->tile_K, B->tile_off,
+               B->ell_val, B->ell_lid);
+    *out = B;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // Gram + rhs
 // ---------------------------------------------------------------------------------
 constexpr int GR_T = 256;         // 16 x 16 threads, 4 x 4 register tile each -> 64 x 64
@@ -322,10 +449,12 @@ __global__ void __launch_bounds__(GR_T) gram_bucket_kernel(int nbuckets, const i
 }
 
 extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int *d_col, const double *d_val,
-                                     const int *d_perm, const int *d_bptr, const int *d_ucol, const int *d_nU,
-                                     const unsigned char *d_lid, const double *d_z, const double *d_X, int p, const double *h_alpha,
+                                     const frk_rowbuckets *bk, const double *d_z, const double *d_X, int p, const double *h_alpha,
                                      const double *d_ve, const double *d_vfs, double sigma2fs, double *d_acc) {
-    FRK_REQUIRE(ctx && d_rowptr && d_acc && d_perm && d_bptr && d_ucol && d_nU && d_lid, "frk_gram_rhs_bucketed: NULL argument");
+    FRK_REQUIRE(ctx && d_rowptr && d_acc && bk, "frk_gram_rhs_bucketed: NULL argument");
+    FRK_REQUIRE(bk->n == m && bk->ncols == r, "frk_gram_rhs_bucketed: the row buckets belong to a %lld x %d matrix", (long long)bk->n, bk->ncols);
+    const int *d_perm = bk->perm, *d_bptr = bk->bptr, *d_ucol = bk->ucol, *d_nU = bk->nU;
+    const unsigned char *d_lid = bk->lid;
     FRK_REQUIRE(p >= 0 && p <= MAXP_B, "frk_gram_rhs_bucketed: %d fixed effects; the device path handles at most %d", p, MAXP_B);
     if (m == 0) return 0;
     AlphaB al{};
@@ -339,17 +468,21 @@ extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *
 // ---------------------------------------------------------------------------------
 // quadratic form + SpMV
 // ---------------------------------------------------------------------------------
-constexpr int QF_T = 128;
+constexpr int QE_WARPS = 4, QE_T = QE_WARPS * 32;
 constexpr int QF_LD = UMAX + 1;
 
 struct QuadSmem {
-    ChunkMeta<QF_T> C;
-    int ucol[UMAX];
+    double sval[QE_WARPS][KMAX][32];          // per-warp staged tile, entry-major (a verbatim copy of the ELL tile)
     double MU[UMAX][QF_LD];
     double muU[UMAX];
-    double sval[KMAX][QF_T];
-    unsigned char slid[KMAX][QF_T];
+    unsigned char slid[QE_WARPS][KMAX][32];
+    int ucol[UMAX];
 };
+
+__device__ __forceinline__ void cpa16(void *dst, const void *src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
 
 // direct evaluation for one row by one warp (rows/buckets that do not fit the shared-memory path)
 __device__ __forceinline__ void quad_row_direct(int row, int r, const int *__restrict__ rowptr, const int *__restrict__ col,
@@ -374,104 +507,99 @@ __device__ __forceinline__ void quad_row_direct(int row, int r, const int *__res
     }
 }
 
-__global__ void __launch_bounds__(QF_T) quadform_bucket_kernel(int nbuckets, const int *__restrict__ bptr, const int *__restrict__ perm,
-                                                               const int *__restrict__ ucol_all, const int *__restrict__ nU_all,
-                                                               const unsigned char *__restrict__ lid, int r,
-                                                               const int *__restrict__ rowptr, const int *__restrict__ col,
-                                                               const double *__restrict__ val, const double *__restrict__ M,
-                                                               const double *__restrict__ mu, double *__restrict__ q,
-                                                               double *__restrict__ t) {
+// One CTA per bucket (grid-stride), M[U,U] staged once per bucket; each warp owns ELL tiles of 32 rows: the tile is copied
+// verbatim into the warp's shared-memory slot with 16-byte cp.async, then lane = row evaluates
+// q = 2 sum_a v_a (M_aa v_a / 2 + sum_{b>a} M_ab v_b) from shared memory.  No block-wide barrier inside the tile loop.
+__global__ void __launch_bounds__(QE_T) quadform_ell_kernel(int nbuckets, const int *__restrict__ bptr, const int *__restrict__ perm,
+                                                            const int *__restrict__ ucol_all, const int *__restrict__ nU_all,
+                                                            const int *__restrict__ btile, const int *__restrict__ tile_K,
+                                                            const int *__restrict__ tile_off, const double *__restrict__ ell_val,
+                                                            const unsigned char *__restrict__ ell_lid, int r,
+                                                            const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                            const double *__restrict__ val, const double *__restrict__ M,
+                                                            const double *__restrict__ mu, double *__restrict__ q,
+                                                            double *__restrict__ t) {
     extern __shared__ __align__(16) unsigned char qsm_raw[];
     QuadSmem &S = *reinterpret_cast<QuadSmem *>(qsm_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int b = blockIdx.x; b < nbuckets; b += gridDim.x) {
-        const int b0 = bptr[b], b1 = bptr[b + 1];
-        if (b1 <= b0) continue;
+        const int r0 = bptr[b], r1 = bptr[b + 1];
+        if (r1 <= r0) continue;
         const int nU = nU_all[b];
         if (nU > UMAX) {
-            for (int pr = b0 + wid; pr < b1; pr += QF_T / 32) quad_row_direct(perm[pr], r, rowptr, col, val, M, mu, q, t, lane);
+            for (int pr = r0 + wid; pr < r1; pr += QE_WARPS) quad_row_direct(perm[pr], r, rowptr, col, val, M, mu, q, t, lane);
             continue;
         }
         __syncthreads();
         if (threadIdx.x < nU) S.ucol[threadIdx.x] = ucol_all[(size_t)b * UMAX + threadIdx.x];
         __syncthreads();
-        // stage M[U,U] and mu[U]
         if (M) {
-            for (int idx = threadIdx.x; idx < nU * nU; idx += QF_T) {
+            for (int idx = threadIdx.x; idx < nU * nU; idx += QE_T) {
                 const int la = idx % nU, lb = idx / nU;
                 S.MU[lb][la] = __ldg(M + S.ucol[la] + (size_t)r * S.ucol[lb]);
             }
         }
         if (threadIdx.x < nU) S.muU[threadIdx.x] = mu ? __ldg(mu + S.ucol[threadIdx.x]) : 0.0;
-        for (int c0 = b0; c0 < b1; c0 += QF_T) {
-            const int nr = min(QF_T, b1 - c0);
-            __syncthreads();
-            chunk_load<QF_T>(S.C, perm, c0, nr, rowptr);
-            const int total = S.C.off[QF_T];
-            for (int g0 = threadIdx.x; g0 < total; g0 += 4 * QF_T) {   // stage: flat walk, row-major -> [entry][row]
-                int rl[4], e0[4];                                    // four independent loads in flight per thread
-                double v[4];
-                unsigned char l[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int g = g0 + u * QF_T;
-                    rl[u] = -1;
-                    if (g < total) {
-                        rl[u] = chunk_row_of<QF_T>(S.C, g);
-                        e0[u] = g - S.C.off[rl[u]];
-                        if (S.C.off[rl[u] + 1] - S.C.off[rl[u]] > KMAX) rl[u] = -1;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (rl[u] >= 0) { const int e = S.C.beg[rl[u]] + e0[u]; v[u] = val[e]; l[u] = lid[e]; }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (rl[u] >= 0) { S.sval[e0[u]][rl[u]] = v[u]; S.slid[e0[u]][rl[u]] = l[u]; }
+        __syncthreads();
+        const int t0 = btile[b], t1 = btile[b + 1];
+        for (int tl = t0 + wid; tl < t1; tl += QE_WARPS) {
+            const int K = tile_K[tl];
+            const int p0 = r0 + (tl - t0) * 32, nrows = min(32, r1 - p0);
+            const int row = lane < nrows ? perm[p0 + lane] : -1;
+            if (K < 0) {                                           // a row longer than KMAX: direct, one row at a time
+                for (int rl = 0; rl < nrows; rl++) quad_row_direct(__shfl_sync(0xffffffffu, row, rl), r, rowptr, col, val, M, mu, q, t, lane);
+                continue;
             }
-            __syncthreads();
-            if (threadIdx.x < nr) {
-                const int tI = threadIdx.x, k = S.C.off[tI + 1] - S.C.off[tI];
-                if (k <= KMAX) {
-                    double qq = 0.0, tt = 0.0;
-                    for (int a = 0; a < k; a++) {
-                        const int la = S.slid[a][tI];
-                        const double va = S.sval[a][tI];
-                        const double *Mr = S.MU[la];
-                        double p0 = 0.5 * Mr[la] * va, p1 = 0.0;
-                        int bb = a + 1;
-                        for (; bb + 1 < k; bb += 2) {
-                            p0 += Mr[S.slid[bb][tI]] * S.sval[bb][tI];
-                            p1 += Mr[S.slid[bb + 1][tI]] * S.sval[bb + 1][tI];
-                        }
-                        if (bb < k) p0 += Mr[S.slid[bb][tI]] * S.sval[bb][tI];
-                        qq += va * (p0 + p1);
-                        tt += va * S.muU[la];
-                    }
-                    const int row = S.C.row[tI];
-                    if (q && M) q[row] = 2.0 * qq;
-                    if (t && mu) t[row] = tt;
-                }
+            const size_t off = (size_t)tile_off[tl];
+            {
+                const double *sv = ell_val + off;
+                double *dv = &S.sval[wid][0][0];
+                for (int c = lane; c < K * 16; c += 32) cpa16(dv + c * 2, sv + c * 2);
+                const unsigned char *sl = ell_lid + off;
+                unsigned char *dl = &S.slid[wid][0][0];
+                for (int c = lane; c < K * 2; c += 32) cpa16(dl + c * 16, sl + c * 16);
+                asm volatile("cp.async.commit_group;\n" ::);
             }
-            // rows longer than KMAX: direct, one warp each
-            for (int rl = wid; rl < nr; rl += QF_T / 32)
-                if (S.C.off[rl + 1] - S.C.off[rl] > KMAX) quad_row_direct(S.C.row[rl], r, rowptr, col, val, M, mu, q, t, lane);
+            int k = 0;
+            if (row >= 0) k = rowptr[row + 1] - rowptr[row];
+            asm volatile("cp.async.wait_group 0;\n" ::);
+            __syncwarp();
+            if (row >= 0) {
+                double qq = 0.0, tt = 0.0;
+                for (int a = 0; a < k; a++) {
+                    const int la = S.slid[wid][a][lane];
+                    const double va = S.sval[wid][a][lane];
+                    const double *Mr = S.MU[la];
+                    double p0a = 0.5 * Mr[la] * va, p1a = 0.0;
+                    int bb = a + 1;
+                    for (; bb + 1 < k; bb += 2) {
+                        p0a += Mr[S.slid[wid][bb][lane]] * S.sval[wid][bb][lane];
+                        p1a += Mr[S.slid[wid][bb + 1][lane]] * S.sval[wid][bb + 1][lane];
+                    }
+                    if (bb < k) p0a += Mr[S.slid[wid][bb][lane]] * S.sval[wid][bb][lane];
+                    qq += va * (p0a + p1a);
+                    tt += va * S.muU[la];
+                }
+                if (q && M) q[row] = 2.0 * qq;
+                if (t && mu) t[row] = tt;
+            }
+            __syncwarp();
         }
     }
 }
 
 extern "C" int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const int *d_rowptr, const int *d_col, const double *d_val,
-                                          const int *d_perm, const int *d_bptr, const int *d_ucol, const int *d_nU,
-                                          const unsigned char *d_lid, const double *d_M, const double *d_mu, double *d_q, double *d_t) {
-    FRK_REQUIRE(ctx && d_rowptr && d_perm && d_bptr && d_ucol && d_nU && d_lid, "frk_quadform_spmv_bucketed: NULL argument");
+                                          const frk_rowbuckets *bk, const double *d_M, const double *d_mu, double *d_q, double *d_t) {
+    FRK_REQUIRE(ctx && d_rowptr && bk, "frk_quadform_spmv_bucketed: NULL argument");
+    FRK_REQUIRE(bk->n == n && bk->ncols == r, "frk_quadform_spmv_bucketed: the row buckets belong to a %lld x %d matrix", (long long)bk->n, bk->ncols);
     if (n == 0) return 0;
     static bool attr = false;
     if (!attr) {
-        FRK_CHECK_CUDA(cudaFuncSetAttribute(quadform_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QuadSmem)));
+        FRK_CHECK_CUDA(cudaFuncSetAttribute(quadform_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QuadSmem)));
         attr = true;
     }
     unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 16);
-    FRK_LAUNCH(ctx, quadform_bucket_kernel, grid, QF_T, sizeof(QuadSmem), r, d_bptr, d_perm, d_ucol, d_nU, d_lid, r, d_rowptr, d_col,
-               d_val, d_M, d_mu, d_q, d_t);
+    FRK_LAUNCH(ctx, quadform_ell_kernel, grid, QE_T, sizeof(QuadSmem), r, bk->bptr, bk->perm, bk->ucol, bk->nU, bk->btile, bk->tile_K,
+               bk->tile_off, bk->ell_val, bk->ell_lid, r, d_rowptr, d_col, d_val, d_M, d_mu, d_q, d_t);
     return 0;
 }

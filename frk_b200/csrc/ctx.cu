@@ -33,6 +33,13 @@ extern "C" int frk_ctx_create(int device, void *stream, frk_ctx **out) {
     c->device = device;
     c->stream = (cudaStream_t)stream;
     c->sm_count = prop.multiProcessorCount;
+    {   // keep stream-ordered allocations cached in the pool across synchronisations (default: trimmed at every sync)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     FRK_CHECK_CUDA(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
     FRK_CHECK_CUDA(cudaMalloc((void **)&c->d_small, 4096 * sizeof(double)));
     *out = c;

@@ -267,74 +267,131 @@ constexpr int NBO = 256;   // outer panel of potrf
 // consecutive doubles of shared memory (one wavefront, broadcast across rows) and keeps all lanes busy.
 constexpr int SPLIT = 4, NBQ = NB / SPLIT, BLK_T = NB * SPLIT;
 
-// Cholesky of the kb x kb diagonal block at A (lower triangle, in place).
+// Cholesky of the kb x kb diagonal block at A (lower triangle, in place), kb <= 64.
 // status[0] += sum(log(diag L)); status[1] = first failing (1-based) column, 0 if ok.
-// The elimination runs in square-root-free (LDL') form so that the per-column critical path is one reciprocal
-// (taken by the lane that owns the diagonal, before the barrier) and one multiply: a[k] -= (a_ij / d_j) col_j[k]
-// with the UNSCALED column j; the factor is scaled at the end, l_ij = a_ij / sqrt(d_j).
+// The block lives in shared memory and is factored in four 16-column steps.  Only the 16 x 16 diagonal sub-block is
+// column-sequential: one warp holds it in registers (lane = row) and exchanges columns by shuffles -- no barrier and no
+// shared-memory round trip on the per-column critical path (pivot -> rsqrt -> scale -> update).  The rows below it are
+// solved one thread per row, and the rest of the block is updated by all 256 threads.
+constexpr int PB = 16;
 __global__ void __launch_bounds__(BLK_T) potf2_kernel(double *__restrict__ A, int lda, int kb, int col_offset, double *__restrict__ status) {
-    __shared__ double colbuf[2][NB];
-    __shared__ double rdiag[2];
-    __shared__ double rsq[NB];
-    __shared__ double slog[BLK_T / 32];
-    const int i = threadIdx.x / SPLIT, h = threadIdx.x % SPLIT;
-    double a[NBQ];
+    __shared__ double a[NB][NB + 1];
+    __shared__ double ld[PB][PB + 1];      // factor of the current 16 x 16 diagonal sub-block
+    __shared__ double rdg[PB];             // reciprocals of its diagonal
+    __shared__ int sbad;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    {   // load (lower triangle; identity padding beyond kb); all loads in flight before the stores
+        double v[NB * NB / BLK_T];
 #pragma unroll
-    for (int kk = 0; kk < NBQ; kk++) {
-        const int k = kk * SPLIT + h;
-        a[kk] = (i < kb && k < kb && k <= i) ? A[i + (size_t)k * lda] : (k == i ? 1.0 : 0.0);
-    }
-    int bad = 0;
-#pragma unroll
-    for (int jj = 0; jj < NBQ; jj++) {                 // columns j = 4*jj + hh; a[jj] is lane hh's entry of column j
-#pragma unroll 1
-        for (int hh = 0; hh < SPLIT; hh++) {
-            const int j = jj * SPLIT + hh;
-            if (h == hh) {
-                const double v = a[jj];                // unscaled column j (rows i < j hold don't-care values)
-                colbuf[j & 1][i] = v;
-                if (i == j) rdiag[j & 1] = (v > 0.0) ? __drcp_rn(v) : -1.0;     // also catches NaN
-            }
-            __syncthreads();
-            const double rd = rdiag[j & 1];
-            if (rd < 0.0) { bad = j + 1; break; }      // uniform: not positive definite
-            const double c = colbuf[j & 1][i] * rd;
-            const double *cb = &colbuf[j & 1][h];
-            if (h > hh) a[jj] -= c * cb[jj * SPLIT];
-#pragma unroll
-            for (int kk = jj + 1; kk < NBQ; kk++) a[kk] -= c * cb[kk * SPLIT];   // entries with k > i are never read
+        for (int q = 0; q < NB * NB / BLK_T; q++) {
+            const int idx = tid + q * BLK_T, i = idx % NB, k = idx / NB;
+            v[q] = (i < kb && k < kb && k <= i) ? A[i + (size_t)k * lda] : (i == k ? 1.0 : 0.0);
         }
-        if (bad) break;
+#pragma unroll
+        for (int q = 0; q < NB * NB / BLK_T; q++) {
+            const int idx = tid + q * BLK_T, i = idx % NB, k = idx / NB;
+            a[i][k] = v[q];
+        }
     }
-    if (bad) {
-        if (threadIdx.x == 0 && status[1] == 0.0) status[1] = (double)(col_offset + bad);
+    if (tid == 0) sbad = 0;
+    __syncthreads();
+    double lg = 0.0;
+    for (int J = 0; J < NB; J += PB) {
+        // (a) 16 x 16 diagonal sub-block: warp 0, lane = row, registers + shuffles
+        if (wid == 0) {
+            const int i = lane & (PB - 1);
+            double d[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) d[k] = a[J + i][J + k];
+            int bad = 0;
+#pragma unroll
+            for (int j = 0; j < PB; j++) {
+                const double piv = __shfl_sync(0xffffffffu, d[j], j);
+                if (!(piv > 0.0)) { if (!bad) bad = J + j + 1; }       // uniform; also catches NaN
+                const double rs = rsqrt(piv);
+                const double lij = (i == j) ? piv * rs : d[j] * rs;
+                d[j] = lij;
+#pragma unroll
+                for (int k = j + 1; k < PB; k++) d[k] -= lij * __shfl_sync(0xffffffffu, lij, k);   // entries with k > i are never used
+            }
+            if (lane < PB) {
+#pragma unroll
+                for (int k = 0; k < PB; k++) { ld[i][k] = (k <= i) ? d[k] : 0.0; a[J + i][J + k] = (k <= i) ? d[k] : 0.0; }
+                double dii = 1.0;
+#pragma unroll
+                for (int k = 0; k < PB; k++) dii = (k == i) ? d[k] : dii;      // select first: ONE reciprocal, not 16 predicated ones
+                rdg[i] = 1.0 / dii;
+            }
+            if (lane == 0 && bad) sbad = bad;
+        }
+        __syncthreads();
+        if (sbad) break;
+        const int nbelow = NB - J - PB;
+        if (nbelow <= 0) break;
+        // (b) rows below the sub-block: x L_D' = p, one thread per row, right-looking
+        if (tid < nbelow) {
+            const int row = J + PB + tid;
+            double x[PB];
+#pragma unroll
+            for (int c = 0; c < PB; c++) x[c] = a[row][J + c];
+#pragma unroll
+            for (int c = 0; c < PB; c++) {
+                const double xc = x[c] * rdg[c];
+                x[c] = xc;
+#pragma unroll
+                for (int k = c + 1; k < PB; k++) x[k] -= xc * ld[k][c];
+            }
+#pragma unroll
+            for (int c = 0; c < PB; c++) a[row][J + c] = x[c];
+        }
+        __syncthreads();
+        // (c) trailing update of the block: a[i][k] -= sum_c x[i][c] x[k][c], J+16 <= k <= i < 64; 16 x 16 threads x (<=3 x 3)
+        {
+            const int ty = tid >> 4, tx = tid & 15, base = J + PB, nt = nbelow / PB;   // nt = 3, 2, 1
+            double acc[3][3];
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) acc[ii][kk] = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < PB; c++) {
+                double xi[3], xk[3];
+#pragma unroll
+                for (int ii = 0; ii < 3; ii++) xi[ii] = ii < nt ? a[base + ty + PB * ii][J + c] : 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) xk[kk] = kk < nt ? a[base + tx + PB * kk][J + c] : 0.0;
+#pragma unroll
+                for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                    for (int kk = 0; kk < 3; kk++) acc[ii][kk] += xi[ii] * xk[kk];
+            }
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) {
+                    const int i = base + ty + PB * ii, k = base + tx + PB * kk;
+                    if (ii < nt && kk < nt && k <= i) a[i][k] -= acc[ii][kk];
+                }
+        }
+        __syncthreads();
+    }
+    if (sbad) {
+        if (tid == 0 && status[1] == 0.0) status[1] = (double)(col_offset + sbad);
         return;
     }
-    // d_i sits on the diagonal (lane h = i % 4 of row i): scale column j by 1/sqrt(d_j)
-    double lg = 0.0;
-#pragma unroll
-    for (int kk = 0; kk < NBQ; kk++) {
-        if (kk * SPLIT + h == i) {
-            const double sq = sqrt(a[kk]);
-            rsq[i] = 1.0 / sq;
-            a[kk] = sq;
-            lg = (i < kb) ? log(sq) : 0.0;
-        }
+    for (int idx = tid; idx < NB * NB; idx += BLK_T) {
+        const int i = idx % NB, k = idx / NB;
+        if (i < kb && k < kb && k <= i) A[i + (size_t)k * lda] = a[i][k];
+    }
+    // log-determinant: the 64 diagonal entries in parallel, off the factorisation's critical path
+    __shared__ double slog[2];
+    if (tid < NB) {
+        lg = tid < kb ? log(a[tid][tid]) : 0.0;
+        lg = warp_sum(lg);
+        if (lane == 0) slog[wid] = lg;
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < NBQ; kk++) {
-        const int k = kk * SPLIT + h;
-        if (i < kb && k < kb && k <= i) A[i + (size_t)k * lda] = (k == i) ? a[kk] : a[kk] * rsq[k];
-    }
-    lg = warp_sum(lg);
-    if ((threadIdx.x & 31) == 0) slog[threadIdx.x >> 5] = lg;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < BLK_T / 32; w++) t += slog[w];
-        status[0] += t;
-    }
+    if (tid == 0) status[0] += slog[0] + slog[1];
 }
 
 // Panel solve X L' = P in place: P is Mp x kb (rows below the diagonal block), L the kb x kb lower factor.

@@ -21,11 +21,6 @@ namespace {
 
 constexpr int MAXP_M = 4;
 
-struct Buckets {
-    int *perm = nullptr, *bptr = nullptr, *ucol = nullptr, *nU = nullptr;
-    unsigned char *lid = nullptr;
-};
-
 struct Block {                    // one resolution of the block-exponential K
     int ni = 0, ix0 = 0;
     int *d_ix = nullptr;
@@ -43,7 +38,7 @@ struct frk_model {
     const int *rowptr = nullptr, *col = nullptr;
     const double *val = nullptr, *Z = nullptr, *X = nullptr, *Ve = nullptr, *Vfs = nullptr;
     bool owned = false;
-    Buckets bk;
+    frk_rowbuckets *bk = nullptr;
     // r-sized slots (device), replicated on every rank
     double *mu_eta = nullptr, *S_eta = nullptr, *Q_eta = nullptr, *Khat = nullptr, *Khat_inv = nullptr;
     // scratch
@@ -327,7 +322,7 @@ int zeroin(const std::function<int(double, double &)> &f, double lower, double u
 int gram(frk_model *M, const double *alpha, double sigma2fs) {
     const size_t n = (size_t)M->r * M->r + M->r + 2;
     FRK_CHECK_CUDA(cudaMemsetAsync(M->acc, 0, n * sizeof(double), M->ctx->stream));
-    RC(frk_gram_rhs_bucketed(M->ctx, M->m, M->r, M->rowptr, M->col, M->val, M->bk.perm, M->bk.bptr, M->bk.ucol, M->bk.nU, M->bk.lid,
+    RC(frk_gram_rhs_bucketed(M->ctx, M->m, M->r, M->rowptr, M->col, M->val, M->bk,
                              M->Z, M->X, M->p, alpha, M->Ve, M->Vfs, sigma2fs, M->acc));
     return reduce_dev(M, M->acc, (int64_t)n);                         // the ONE large exchange per EM iteration
 }
@@ -476,7 +471,7 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
     const bool est = !known;
     double s2new = est ? sigma2fs : known_sigma2fs;
     // Omega_diag1 = rowSums((S R_eta')^2) = s_j'(S_eta + mu mu')s_j = q_j + t_j^2,  t = S mu_eta     :332-334
-    RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk.perm, M->bk.bptr, M->bk.ucol, M->bk.nU, M->bk.lid,
+    RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk,
                                   M->S_eta, M->mu_eta, M->q, M->t));
     double al[MAXP_M];
     MSums s;
@@ -537,11 +532,7 @@ static int model_common_init(frk_model *M) {
     FRK_CHECK_CUDA(cudaMemsetAsync(M->q, 0, std::max<int64_t>(M->m, 1) * sizeof(double), M->ctx->stream));
     FRK_CHECK_CUDA(cudaMemsetAsync(M->t, 0, std::max<int64_t>(M->m, 1) * sizeof(double), M->ctx->stream));
     // row buckets of S
-    int nnz = 0;
-    RC(frk_d2h(M->ctx, &nnz, M->rowptr + M->m, sizeof(int)));
-    RC(dalloc(M, &M->bk.perm, (size_t)std::max<int64_t>(M->m, 1))); RC(dalloc(M, &M->bk.bptr, (size_t)r + 1));
-    RC(dalloc(M, &M->bk.ucol, (size_t)r * 64)); RC(dalloc(M, &M->bk.nU, (size_t)r)); RC(dalloc(M, &M->bk.lid, (size_t)std::max(nnz, 1)));
-    RC(frk_csr_bucket_rows(M->ctx, M->m, M->rowptr, M->col, r, M->bk.perm, M->bk.bptr, M->bk.ucol, M->bk.nU, M->bk.lid));
+    RC(frk_rowbuckets_create(M->ctx, M->m, r, M->rowptr, M->col, M->val, &M->bk));
     // totals and the homoscedasticity test all(a == a[1]) & all(b == b[1])   (R/SREfit.R:278-280)
     double mt[1] = {(double)M->m};
     RC(reduce_host(M, mt, 1, 0));
@@ -604,6 +595,7 @@ extern "C" int frk_model_destroy(frk_model *M) {
     cudaSetDevice(M->ctx->device);
     cudaStreamSynchronize(M->ctx->stream);
     for (void *p : M->allocs) cudaFree(p);
+    frk_rowbuckets_destroy(M->bk);
     delete M;
     return 0;
 }
@@ -748,10 +740,9 @@ extern "C" int frk_model_slot_device(frk_model *M, const char *slot, double **d_
 // predict at n BAUs (this rank's rows): .SRE.predict_EM with predict_BAUs = TRUE, covariances = FALSE.
 // S0: n x r device CSR with its row buckets; d_XBAU n x p column-major; d_fs n; d_obs_bau m (BAU row of every observation).
 extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
-                                 const int *d_perm0, const int *d_bptr0, const int *d_ucol0, const int *d_nU0,
-                                 const unsigned char *d_lid0, const double *d_XBAU, const double *d_fs, const int *d_obs_bau,
+                                 const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs, const int *d_obs_bau,
                                  int obs_fs, double *d_mu, double *d_var, double *d_sd) {
-    FRK_REQUIRE(M && d_rowptr0 && d_XBAU && d_mu && d_var && d_sd && n >= 0, "frk_model_predict: bad argument");
+    FRK_REQUIRE(M && d_rowptr0 && bk0 && d_XBAU && d_mu && d_var && d_sd && n >= 0, "frk_model_predict: bad argument");
     frk_ctx *ctx = M->ctx;
     const int r = M->r;
     const size_t rr = (size_t)r * r;
@@ -763,8 +754,7 @@ extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, 
     auto run = [&]() -> int {
         RC(frk_xalpha(ctx, n, M->p, d_XBAU, M->alpha, xa));
         if (obs_fs || M->sigma2fs == 0.0) {                           // the stored posterior (R/SREpredict.R:334-361)
-            RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, d_perm0, d_bptr0, d_ucol0, d_nU0, d_lid0, M->S_eta,
-                                          M->mu_eta, q, smu));
+            RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, M->S_eta, M->mu_eta, q, smu));
             return frk_predict_finalize(ctx, n, 0, M->sigma2fs, q, smu, xa, nullptr, nullptr, nullptr, d_mu, d_var, d_sd);
         }
         // joint (eta, xi) solve at the final parameters (:308-333); for point data: one more E-step + the same quadratic form
@@ -773,8 +763,7 @@ extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, 
         FRK_CHECK_CUDA(cudaMallocAsync((void **)&Q, (2 * rr + r) * sizeof(double), ctx->stream));
         double *Sig = Q + rr, *mue = Sig + rr;
         int rc2 = posterior(M, M->alpha, M->sigma2fs, Q, Sig, mue, o);
-        if (!rc2) rc2 = frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, d_perm0, d_bptr0, d_ucol0, d_nU0, d_lid0, Sig,
-                                                   mue, q, smu);
+        if (!rc2) rc2 = frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, Sig, mue, q, smu);
         cudaFreeAsync(Q, ctx->stream);
         if (rc2) return rc2;
         // A = diag(C' Ve^-1 C), ytil = C' Ve^-1 (Z - X alpha)

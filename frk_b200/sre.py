@@ -288,7 +288,7 @@ def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True):
     nloc = mdl.hi - mdl.lo
     mu, var, sd = (dev.empty(max(nloc, 1)) for _ in range(3))
     call("frk_model_predict", mdl.handle, nloc, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
-         *mdl.S0.buckets(dev), dev.ptr(mdl.X_BAU), dev.ptr(mdl.fs_BAU), dev.ptr(mdl.obs_bau), 1 if obs_fs else 0,
+         mdl.S0.buckets(dev), dev.ptr(mdl.X_BAU), dev.ptr(mdl.fs_BAU), dev.ptr(mdl.obs_bau), 1 if obs_fs else 0,
          dev.ptr(mu), dev.ptr(var), dev.ptr(sd))
     if not to_host:
         return dict(mu=mu, var=var, sd=sd)

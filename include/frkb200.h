@@ -33,6 +33,7 @@ extern "C" {
 
 typedef struct frk_ctx frk_ctx;       /* device + stream + scratch workspace        */
 typedef struct frk_basis frk_basis;   /* device-resident basis + cell lists          */
+typedef struct frk_rowbuckets frk_rowbuckets;   /* row buckets + ELL tiles of one CSR basis matrix */
 typedef struct frk_model frk_model;   /* device-resident SRE object (S, Z, X, Ve, Vfs + the r-sized slots) */
 
 /* SRE(K_type=): R/SRE.R:322; only these two are legal for method = "EM" (R/check_args.R:184-187) */
@@ -166,16 +167,19 @@ int frk_gram_rhs(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int 
  *   d_lid[nnz] : for every stored entry, its position in its bucket's column list (one byte)            */
 int frk_csr_bucket_rows(frk_ctx *ctx, int64_t n, const int *d_rowptr, const int *d_col, int ncols,
                         int *d_perm, int *d_bptr, int *d_ucol, int *d_nU, unsigned char *d_lid);
+/* Owning handle: the bucket arrays above plus a bucket-ordered, entry-major copy of the matrix in tiles of 32 rows
+ * ("ELL tiles": val[e][lane], lid[e][lane]) that the per-iteration kernels read with coalesced bulk copies.        */
+int frk_rowbuckets_create(frk_ctx *ctx, int64_t n, int ncols, const int *d_rowptr, const int *d_col,
+                          const double *d_val, frk_rowbuckets **out);
+int frk_rowbuckets_destroy(frk_rowbuckets *bk);
 /* frk_gram_rhs / frk_quadform_spmv with row buckets (same results up to fp64 summation order) */
 int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int *d_col,
-                          const double *d_val, const int *d_perm, const int *d_bptr, const int *d_ucol,
-                          const int *d_nU, const unsigned char *d_lid, const double *d_z,
+                          const double *d_val, const frk_rowbuckets *bk, const double *d_z,
                           const double *d_X, int p, const double *h_alpha, const double *d_ve,
                           const double *d_vfs, double sigma2fs, double *d_acc);
 int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const int *d_rowptr, const int *d_col,
-                               const double *d_val, const int *d_perm, const int *d_bptr,
-                               const int *d_ucol, const int *d_nU, const unsigned char *d_lid,
-                               const double *d_M, const double *d_mu, double *d_q, double *d_t);
+                               const double *d_val, const frk_rowbuckets *bk, const double *d_M,
+                               const double *d_mu, double *d_q, double *d_t);
 
 /* ---- gather-based sparse quadratic form + SpMV: R/SREutils.R:286-300 (.batch_compute_var,
  *      rowSums((S0 Cov) * S0)), R/SREfit.R:332-334 (Omega_diag1), S %*% mu_eta.
@@ -299,11 +303,10 @@ int frk_model_set(frk_model *mdl, const char *slot, const double *h_in);
 int frk_model_slot_device(frk_model *mdl, const char *slot, double **d_out);
 /* .SRE.predict_EM at n BAUs (R/SREpredict.R:243-375; predict_BAUs = TRUE, covariances = FALSE) with
  * .batch_compute_var (R/SREutils.R:245-305).  S0 (n x r device CSR) comes with its row buckets
- * (frk_csr_bucket_rows); d_XBAU n x p column-major; d_fs[n]; d_obs_bau[m] = BAU row of every observation.
+ * (frk_rowbuckets_create); d_XBAU n x p column-major; d_fs[n]; d_obs_bau[m] = BAU row of every observation.
  * obs_fs != 0 or sigma2fs == 0: stored posterior; else the joint (eta, xi) solve at the final parameters.      */
 int frk_model_predict(frk_model *mdl, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
-                      const int *d_perm0, const int *d_bptr0, const int *d_ucol0, const int *d_nU0,
-                      const unsigned char *d_lid0, const double *d_XBAU, const double *d_fs,
+                      const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs,
                       const int *d_obs_bau, int obs_fs, double *d_mu, double *d_var, double *d_sd);
 /* stats::optim(method = "Nelder-Mead", control = list(maxit, reltol)) and stats::uniroot (default tol) as used by
  * the M-step (R/SREfit.R:618-621, :386-388); exported so that the iterate path can be tested on its own.       */

@@ -209,9 +209,7 @@ def test_gram_and_quadform_kernels(dev, btype, nres):
     G_ref = (So.T @ sp.diags(1 / d) @ So).toarray()
     b_ref = So.T @ (rho / d)
     dz, dX, dve, dvfs = dev.upload(z), dev.upload(X), dev.upload(ve), dev.upload(vfs)
-    bk = Sg.buckets(dev)
-    pm = dev.download(Sg._buckets["perm"], m); bp = dev.download(Sg._buckets["bptr"], r + 1)
-    assert sorted(pm.tolist()) == list(range(m)) and bp[0] == 0 and bp[-1] == m
+    bk = [Sg.buckets(dev)]
     for bucketed in (False, True):
         acc = dev.zeros(r * r + r + 2)
         args = [dev.ctx, m, r, dev.ptr(Sg.rowptr), dev.ptr(Sg.col), dev.ptr(Sg.val)]

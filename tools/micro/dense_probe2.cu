@@ -2,72 +2,123 @@
 #include "../../frk_b200/csrc/dense.cu"
 __global__ void empty_k() {}
 __global__ void __launch_bounds__(BLK_T) potf2_timed(double *__restrict__ A, int lda, int kb, int col_offset, double *__restrict__ status, long long *ts) {
-    __shared__ double colbuf[2][NB];
-    __shared__ double rdiag[2];
-    __shared__ double rsq[NB];
-    __shared__ double slog[BLK_T / 32];
-    long long t0 = clock64();
-    const int i = threadIdx.x / SPLIT, h = threadIdx.x % SPLIT;
-    double a[NBQ];
+    __shared__ double a[NB][NB + 1];
+    __shared__ double ld[PB][PB + 1];      // factor of the current 16 x 16 diagonal sub-block
+    __shared__ double rdg[PB];             // reciprocals of its diagonal
+    __shared__ int sbad;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    long long T0 = clock64(), ta = 0, tb = 0, tc = 0, tl, tt;
+    {   // load (lower triangle; identity padding beyond kb); all loads in flight before the stores
+        double v[NB * NB / BLK_T];
 #pragma unroll
-    for (int kk = 0; kk < NBQ; kk++) {
-        const int k = kk * SPLIT + h;
-        a[kk] = (i < kb && k < kb && k <= i) ? A[i + (size_t)k * lda] : (k == i ? 1.0 : 0.0);
-    }
-    __syncthreads(); long long t1 = clock64();
-    int bad = 0;
-#pragma unroll
-    for (int jj = 0; jj < NBQ; jj++) {                 // columns j = 4*jj + hh; a[jj] is lane hh's entry of column j
-#pragma unroll 1
-        for (int hh = 0; hh < SPLIT; hh++) {
-            const int j = jj * SPLIT + hh;
-            if (h == hh) {
-                const double v = a[jj];                // unscaled column j (rows i < j hold don't-care values)
-                colbuf[j & 1][i] = v;
-                if (i == j) rdiag[j & 1] = (v > 0.0) ? __drcp_rn(v) : -1.0;     // also catches NaN
-            }
-            __syncthreads();
-            const double rd = rdiag[j & 1];
-            if (rd < 0.0) { bad = j + 1; break; }      // uniform: not positive definite
-            const double c = colbuf[j & 1][i] * rd;
-            const double *cb = &colbuf[j & 1][h];
-            if (h > hh) a[jj] -= c * cb[jj * SPLIT];
-#pragma unroll
-            for (int kk = jj + 1; kk < NBQ; kk++) a[kk] -= c * cb[kk * SPLIT];   // entries with k > i are never read
+        for (int q = 0; q < NB * NB / BLK_T; q++) {
+            const int idx = tid + q * BLK_T, i = idx % NB, k = idx / NB;
+            v[q] = (i < kb && k < kb && k <= i) ? A[i + (size_t)k * lda] : (i == k ? 1.0 : 0.0);
         }
-        if (bad) break;
+#pragma unroll
+        for (int q = 0; q < NB * NB / BLK_T; q++) {
+            const int idx = tid + q * BLK_T, i = idx % NB, k = idx / NB;
+            a[i][k] = v[q];
+        }
     }
-    long long t2 = clock64();
-    if (bad) {
-        if (threadIdx.x == 0 && status[1] == 0.0) status[1] = (double)(col_offset + bad);
+    if (tid == 0) sbad = 0;
+    __syncthreads();
+    double lg = 0.0;
+    tl = clock64() - T0;
+    for (int J = 0; J < NB; J += PB) {
+        tt = clock64();
+        // (a) 16 x 16 diagonal sub-block: warp 0, lane = row, registers + shuffles
+        if (wid == 0) {
+            const int i = lane & (PB - 1);
+            double d[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) d[k] = a[J + i][J + k];
+            int bad = 0;
+#pragma unroll
+            for (int j = 0; j < PB; j++) {
+                const double piv = __shfl_sync(0xffffffffu, d[j], j);
+                if (!(piv > 0.0)) { if (!bad) bad = J + j + 1; }       // uniform; also catches NaN
+                const double rs = rsqrt(piv);
+                const double lij = (i == j) ? piv * rs : d[j] * rs;
+                d[j] = lij;
+#pragma unroll
+                for (int k = j + 1; k < PB; k++) d[k] -= lij * __shfl_sync(0xffffffffu, lij, k);   // entries with k > i are never used
+            }
+            if (lane < PB) {
+#pragma unroll
+                for (int k = 0; k < PB; k++) { ld[i][k] = (k <= i) ? d[k] : 0.0; a[J + i][J + k] = (k <= i) ? d[k] : 0.0; }
+#pragma unroll
+                for (int k = 0; k < PB; k++) if (k == i) { rdg[i] = 1.0 / d[k]; if (J + i < kb) lg += log(d[k]); }
+            }
+            if (lane == 0 && bad) sbad = bad;
+        }
+        __syncthreads();
+        ta += clock64() - tt; tt = clock64();
+        if (sbad) break;
+        const int nbelow = NB - J - PB;
+        if (nbelow <= 0) break;
+        // (b) rows below the sub-block: x L_D' = p, one thread per row, right-looking
+        if (tid < nbelow) {
+            const int row = J + PB + tid;
+            double x[PB];
+#pragma unroll
+            for (int c = 0; c < PB; c++) x[c] = a[row][J + c];
+#pragma unroll
+            for (int c = 0; c < PB; c++) {
+                const double xc = x[c] * rdg[c];
+                x[c] = xc;
+#pragma unroll
+                for (int k = c + 1; k < PB; k++) x[k] -= xc * ld[k][c];
+            }
+#pragma unroll
+            for (int c = 0; c < PB; c++) a[row][J + c] = x[c];
+        }
+        __syncthreads();
+        tb += clock64() - tt; tt = clock64();
+        // (c) trailing update of the block: a[i][k] -= sum_c x[i][c] x[k][c], J+16 <= k <= i < 64; 16 x 16 threads x (<=3 x 3)
+        {
+            const int ty = tid >> 4, tx = tid & 15, base = J + PB, nt = nbelow / PB;   // nt = 3, 2, 1
+            double acc[3][3];
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) acc[ii][kk] = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < PB; c++) {
+                double xi[3], xk[3];
+#pragma unroll
+                for (int ii = 0; ii < 3; ii++) xi[ii] = ii < nt ? a[base + ty + PB * ii][J + c] : 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) xk[kk] = kk < nt ? a[base + tx + PB * kk][J + c] : 0.0;
+#pragma unroll
+                for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                    for (int kk = 0; kk < 3; kk++) acc[ii][kk] += xi[ii] * xk[kk];
+            }
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) {
+                    const int i = base + ty + PB * ii, k = base + tx + PB * kk;
+                    if (ii < nt && kk < nt && k <= i) a[i][k] -= acc[ii][kk];
+                }
+        }
+        __syncthreads();
+        tc += clock64() - tt;
+    }
+    if (sbad) {
+        if (tid == 0 && status[1] == 0.0) status[1] = (double)(col_offset + sbad);
         return;
     }
-    // d_i sits on the diagonal (lane h = i % 4 of row i): scale column j by 1/sqrt(d_j)
-    double lg = 0.0;
-#pragma unroll
-    for (int kk = 0; kk < NBQ; kk++) {
-        if (kk * SPLIT + h == i) {
-            const double sq = sqrt(a[kk]);
-            rsq[i] = 1.0 / sq;
-            a[kk] = sq;
-            lg = (i < kb) ? log(sq) : 0.0;
-        }
+    for (int idx = tid; idx < NB * NB; idx += BLK_T) {
+        const int i = idx % NB, k = idx / NB;
+        if (i < kb && k < kb && k <= i) A[i + (size_t)k * lda] = a[i][k];
     }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < NBQ; kk++) {
-        const int k = kk * SPLIT + h;
-        if (i < kb && k < kb && k <= i) A[i + (size_t)k * lda] = (k == i) ? a[kk] : a[kk] * rsq[k];
+    if (wid == 0) {
+        lg = warp_sum(lg);
+        if (lane == 0) status[0] += lg;
     }
-    lg = warp_sum(lg);
-    if ((threadIdx.x & 31) == 0) slog[threadIdx.x >> 5] = lg;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < BLK_T / 32; w++) t += slog[w];
-        status[0] += t;
-    }
-    if (threadIdx.x == 0) { ts[0] = t1 - t0; ts[1] = t2 - t1; ts[2] = clock64() - t2; }
+    if (tid == 0) { ts[0] = tl; ts[1] = ta; ts[2] = tb; ts[3] = tc; ts[4] = clock64() - T0; }
 }
 
 int main() {
@@ -89,7 +140,7 @@ int main() {
         cudaEventRecord(e0); for (int i = 0; i < N; i++) trsm_rows_kernel<false><<<20, BLK_T>>>(A, r, A + 2048, r, 1280, 64, r); report("trsm_rows<false> 20 CTAs");
         cudaEventRecord(e0); for (int i = 0; i < N; i++) trsm_rows_kernel<false><<<50, BLK_T>>>(A, r, A + 64, r, 3200, 64, r); report("trsm_rows<false> 50 CTAs");
     }
-    { long long *ts; cudaMallocManaged(&ts, 64); for (int w = 0; w < 3; w++) { potf2_timed<<<1, BLK_T>>>(A + 64 + 64 * (size_t)r, r, 64, 0, st, ts); cudaDeviceSynchronize(); printf("potf2 cycles: load %lld  loop %lld  epilogue %lld\n", ts[0], ts[1], ts[2]); } }
+    { long long *ts; cudaMallocManaged(&ts, 64); for (int w = 0; w < 3; w++) { potf2_timed<<<1, BLK_T>>>(A + 64 + 64 * (size_t)r, r, 64, 0, st, ts); cudaDeviceSynchronize(); printf("potf2 cycles: load %lld  (a) %lld  (b) %lld  (c) %lld  total %lld\n", ts[0], ts[1], ts[2], ts[3], ts[4]); } }
     cudaFuncSetAttribute(dgemm_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     for (int K : {64, 256}) for (int gx : {9, 25}) for (int gy : {1, 3, 50}) {
         GemmArgs g = gemm_args(gx * 128, gy * 64, K, -1.0, A, r, A + 64, r, 1.0, A + 1024 * (size_t)r, r);
