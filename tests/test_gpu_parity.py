@@ -297,3 +297,95 @@ def test_predict_closed_form_matches_general(dev):
     pg = F.predict(Mg, obs_fs=False)
     np.testing.assert_allclose(pg["var"], var, rtol=1e-7)
     np.testing.assert_allclose(pg["mu"], mu, rtol=1e-7, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs 2 and 4 on the reference's own data (fixtures: tests/golden/*.npz, tools/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+import os
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _isea3h():
+    z = np.load(os.path.join(GOLD, "isea3h_centroids.npz"))
+    return {r: np.column_stack([z["lon"][z["res"] == r], z["lat"][z["res"] == r]]) for r in range(6)}
+
+
+@pytest.mark.parametrize("K_type", ["block-exponential", "unstructured"])
+def test_config2_airs_sphere(dev, K_type):
+    """BASELINE config 2 (scaled to the fixture): AIRS_05_2003 day 1 (13,911 soundings, std = co2std -> heteroscedastic / uniroot
+    branch), sphere(), ISEA3H bisquare basis nres = 3 (r = 1176), f = co2avgret ~ lat + 1, BAUs = ISEA3H resolution-5 cells
+    represented by their centroids (observation -> BAU by nearest centroid on the host, identical for oracle and device: BAU
+    construction and point-in-hexagon are outside the device path, SURVEY.md s8 'next' #2)."""
+    import frk_b200 as F
+    a = np.load(os.path.join(GOLD, "airs_day1.npz"))
+    isea = _isea3h()
+    ll = np.column_stack([a["lon"], a["lat"]])
+    cen = isea[5]
+    ob = O.auto_basis(O.sphere(), ll, nres=3, isea3h=isea, isea3h_lo=2)
+    assert ob.n == 1176
+    # nearest centroid = largest dot product of unit normals
+    def nrm(x):
+        lo, la = np.radians(x[:, 0]), np.radians(x[:, 1])
+        return np.column_stack([np.cos(la) * np.cos(lo), np.cos(la) * np.sin(lo), np.sin(la)])
+    bau = np.argmax(nrm(ll) @ nrm(cen).T, axis=1).astype(np.int32)
+    uo, means, _ = O.bin_mean(bau, np.column_stack([a["co2avgret"], a["co2std"]]))
+    X_BAU = np.column_stack([np.ones(len(cen)), cen[:, 1]])
+    Mo = O.SRE(ob, cen, np.ones(len(cen)), uo, means[:, 0], means[:, 1], X=X_BAU[uo], X_BAU=X_BAU, K_type=K_type)
+    baus = F.PointBAUs(cen.copy())
+    baus["fs"] = 1.0
+    baus["lat"] = cen[:, 1]
+    data = F.SpatialPointsDataFrame(ll, {"co2avgret": a["co2avgret"], "std": a["co2std"], "bau": bau.astype(np.float64)})
+    Mg = F.SRE("co2avgret ~ lat + 1", data, _mk_basis(F, ob), baus, est_error=False, K_type=K_type)
+    assert np.array_equal(dev.download(Mg.obs_bau, Mg.m), uo) and not Mg.homoscedastic
+    np.testing.assert_allclose(Mg.S.to_scipy(dev).toarray(), Mo.S.toarray(), rtol=1e-9, atol=1e-13)
+    O.SRE_fit(Mo, n_EM=3, tol=0.0)
+    F.SRE_fit(Mg, n_EM=3, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=1e-6)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-6)
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pg = F.predict(Mg, obs_fs=obs_fs)
+        np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7)
+        np.testing.assert_allclose(pg["var"], po[1], rtol=1e-6)
+
+
+def test_config4_noaa_spacetime_tensor_basis(dev):
+    """BASELINE config 4 (scaled): NOAA_df_1990 Tmax, July 1993 (4,122 obs, 133 stations), space x time tensor basis
+    (bisquare on the plane, nres = 2) x (Gaussian in time, loc = seq(2, 28, 4), scale = 3; vignettes/FRK_intro.Rnw:748-782),
+    1 deg x 1 deg x 1 day BAUs, std = 2, K_type = "unstructured".  Rows have ~80 non-zeros and bucket unions > 64 columns,
+    so the Gram and quadratic-form kernels run their direct paths."""
+    import frk_b200 as F
+    n = np.load(os.path.join(GOLD, "noaa_jul1993.npz"))
+    xyt = np.column_stack([n["lon"], n["lat"], n["day"]])
+    ob1 = O.auto_basis(O.plane(), xyt[:, :2], regular=1, nres=2)
+    ob2 = O.local_basis(O.real_line(), np.arange(2.0, 29.0, 4.0)[:, None], np.full(7, 3.0), "Gaussian")
+    ot = O.TensorP_Basis(ob1, ob2)
+    gx = np.arange(np.floor(n["lon"].min()), np.ceil(n["lon"].max()) + 1)
+    gy = np.arange(np.floor(n["lat"].min()), np.ceil(n["lat"].max()) + 1)
+    gt = np.arange(1.0, 32.0)
+    T, Y, X = np.meshgrid(gt, gy, gx, indexing="ij")                 # space fastest, time slowest (R/geometryfns.R:979-980)
+    cen = np.column_stack([X.ravel(), Y.ravel(), T.ravel()])
+    ix = np.rint(n["lon"] - gx[0]).astype(int); iy = np.rint(n["lat"] - gy[0]).astype(int); it = np.rint(n["day"] - 1).astype(int)
+    bau = (ix + len(gx) * (iy + len(gy) * it)).astype(np.int32)
+    uo, means, _ = O.bin_mean(bau, np.column_stack([n["z"], np.full(len(bau), 2.0)]))
+    Mo = O.SRE(ot, cen, np.ones(len(cen)), uo, means[:, 0], means[:, 1], K_type="unstructured")
+    baus = F.PointBAUs(cen.copy())
+    baus["fs"] = 1.0
+    data = F.SpatialPointsDataFrame(xyt, {"z": n["z"], "std": np.full(len(bau), 2.0), "bau": bau.astype(np.float64)})
+    gtb = F.TensorP(_mk_basis(F, ob1), _mk_basis(F, ob2))
+    Mg = F.SRE("z ~ 1", data, gtb, baus, est_error=False, K_type="unstructured")
+    assert Mg.r == ot.n == ob1.n * 7 and np.array_equal(dev.download(Mg.obs_bau, Mg.m), uo)
+    assert _same_pattern(Mo.S, Mg.S.to_scipy(dev))
+    O.SRE_fit(Mo, n_EM=3, tol=0.0)
+    F.SRE_fit(Mg, n_EM=3, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-8, atol=1e-12)
+    po = O.predict(Mo, obs_fs=False)
+    pg = F.predict(Mg, obs_fs=False)
+    np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(pg["var"], po[1], rtol=1e-7)
+    with pytest.raises(F.FRKError, match="tensor-product"):
+        F.SRE("z ~ 1", data, gtb, baus, est_error=False, K_type="block-exponential")
