@@ -471,14 +471,6 @@ extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *
 constexpr int QE_WARPS = 4, QE_T = QE_WARPS * 32;
 constexpr int QF_LD = UMAX + 1;
 
-struct QuadSmem {
-    double sval[QE_WARPS][KMAX][32];          // per-warp staged tile, entry-major (a verbatim copy of the ELL tile)
-    double MU[UMAX][QF_LD];
-    double muU[UMAX];
-    unsigned char slid[QE_WARPS][KMAX][32];
-    int ucol[UMAX];
-};
-
 __device__ __forceinline__ void cpa16(void *dst, const void *src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
@@ -507,21 +499,40 @@ __device__ __forceinline__ void quad_row_direct(int row, int r, const int *__res
     }
 }
 
-// One CTA per bucket (grid-stride), M[U,U] staged once per bucket; each warp owns ELL tiles of 32 rows: the tile is copied
-// verbatim into the warp's shared-memory slot with 16-byte cp.async, then lane = row evaluates
-// q = 2 sum_a v_a (M_aa v_a / 2 + sum_{b>a} M_ab v_b) from shared memory.  No block-wide barrier inside the tile loop.
-__global__ void __launch_bounds__(QE_T) quadform_ell_kernel(int nbuckets, const int *__restrict__ bptr, const int *__restrict__ perm,
-                                                            const int *__restrict__ ucol_all, const int *__restrict__ nU_all,
-                                                            const int *__restrict__ btile, const int *__restrict__ tile_K,
-                                                            const int *__restrict__ tile_off, const double *__restrict__ ell_val,
-                                                            const unsigned char *__restrict__ ell_lid, int r,
-                                                            const int *__restrict__ rowptr, const int *__restrict__ col,
-                                                            const double *__restrict__ val, const double *__restrict__ M,
-                                                            const double *__restrict__ mu, double *__restrict__ q,
-                                                            double *__restrict__ t) {
+// One CTA per bucket (grid-stride).  Within a bucket every row lives on the bucket's <= 64 columns U, so for a tile of
+// 32 rows the quadratic forms are the row sums of (X M[U,U]) o X with X the 32 x |U| densified tile: a small dense fp64
+// product that runs on the tensor cores (DMMA m8n8k4), the one place on this path where the dense panel IS the bottleneck
+// (the gather formulation is bound by shared-memory latency, not by HBM).  M is symmetric, so only the block-upper-triangular
+// part of M[U,U] (8-column blocks, off-diagonal blocks doubled when staged) is multiplied: 168 instead of 288 DMMAs per tile
+// at |U| = 48.  Each warp owns ELL tiles; lane = row while densifying (and for t = s'mu), DMMA fragment layout afterwards.
+constexpr int QD_LDX = 36;                   // X is stored TRANSPOSED, Xt[col][row]: lane = row scatters are conflict-free, and with a
+                                             // stride of 36 both the A fragments and the epilogue reads hit every bank pair at most twice
+constexpr int QD_LDM = UMAX + 8;             // 72: M row stride (= 8 mod 16 -> the 32 B-fragment addresses cover the 16 bank pairs twice)
+
+struct QuadDmmaSmem {
+    double Xt[QE_WARPS][UMAX][QD_LDX];
+    double MU[UMAX][QD_LDM];                 // MU[k][n], k-block < n-block doubled, k-block > n-block unused
+    double muU[UMAX];
+    int ucol[UMAX];
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(QE_T, 2) quadform_ell_kernel(int nbuckets, const int *__restrict__ bptr, const int *__restrict__ perm,
+                                                               const int *__restrict__ ucol_all, const int *__restrict__ nU_all,
+                                                               const int *__restrict__ btile, const int *__restrict__ tile_K,
+                                                               const int *__restrict__ tile_off, const double *__restrict__ ell_val,
+                                                               const unsigned char *__restrict__ ell_lid, int r,
+                                                               const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                               const double *__restrict__ val, const double *__restrict__ M,
+                                                               const double *__restrict__ mu, double *__restrict__ q,
+                                                               double *__restrict__ t) {
     extern __shared__ __align__(16) unsigned char qsm_raw[];
-    QuadSmem &S = *reinterpret_cast<QuadSmem *>(qsm_raw);
+    QuadDmmaSmem &S = *reinterpret_cast<QuadDmmaSmem *>(qsm_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane >> 2, tg = lane & 3;
     for (int b = blockIdx.x; b < nbuckets; b += gridDim.x) {
         const int r0 = bptr[b], r1 = bptr[b + 1];
         if (r1 <= r0) continue;
@@ -530,17 +541,24 @@ __global__ void __launch_bounds__(QE_T) quadform_ell_kernel(int nbuckets, const 
             for (int pr = r0 + wid; pr < r1; pr += QE_WARPS) quad_row_direct(perm[pr], r, rowptr, col, val, M, mu, q, t, lane);
             continue;
         }
+        const int nblk = (nU + 7) >> 3, Up = nblk * 8;
         __syncthreads();
         if (threadIdx.x < nU) S.ucol[threadIdx.x] = ucol_all[(size_t)b * UMAX + threadIdx.x];
         __syncthreads();
-        if (M) {
-            for (int idx = threadIdx.x; idx < nU * nU; idx += QE_T) {
-                const int la = idx % nU, lb = idx / nU;
-                S.MU[lb][la] = __ldg(M + S.ucol[la] + (size_t)r * S.ucol[lb]);
+        if (M) {                                                   // stage the block-upper part of M[U,U]; zero padding
+            for (int idx = threadIdx.x; idx < Up * Up; idx += QE_T) {
+                const int n = idx % Up, k = idx / Up;
+                double v = 0.0;
+                if (k < nU && n < nU && (k >> 3) <= (n >> 3)) {
+                    v = __ldg(M + S.ucol[n] + (size_t)r * S.ucol[k]);
+                    if ((k >> 3) < (n >> 3)) v *= 2.0;
+                }
+                S.MU[k][n] = v;
             }
         }
-        if (threadIdx.x < nU) S.muU[threadIdx.x] = mu ? __ldg(mu + S.ucol[threadIdx.x]) : 0.0;
+        if (threadIdx.x < UMAX) S.muU[threadIdx.x] = (mu && threadIdx.x < nU) ? __ldg(mu + S.ucol[threadIdx.x]) : 0.0;
         __syncthreads();
+        double (*Xt)[QD_LDX] = S.Xt[wid];
         const int t0 = btile[b], t1 = btile[b + 1];
         for (int tl = t0 + wid; tl < t1; tl += QE_WARPS) {
             const int K = tile_K[tl];
@@ -550,39 +568,76 @@ __global__ void __launch_bounds__(QE_T) quadform_ell_kernel(int nbuckets, const 
                 for (int rl = 0; rl < nrows; rl++) quad_row_direct(__shfl_sync(0xffffffffu, row, rl), r, rowptr, col, val, M, mu, q, t, lane);
                 continue;
             }
+            // densify: zero the Up x 32 tile, then lane = row scatters its entries (padding entries carry val = 0)
+            for (int idx = lane; idx < Up * 16; idx += 32) {
+                const int cc = idx >> 4, rr = (idx & 15) * 2;
+                *reinterpret_cast<double2 *>(&Xt[cc][rr]) = make_double2(0.0, 0.0);
+            }
             const size_t off = (size_t)tile_off[tl];
-            {
-                const double *sv = ell_val + off;
-                double *dv = &S.sval[wid][0][0];
-                for (int c = lane; c < K * 16; c += 32) cpa16(dv + c * 2, sv + c * 2);
-                const unsigned char *sl = ell_lid + off;
-                unsigned char *dl = &S.slid[wid][0][0];
-                for (int c = lane; c < K * 2; c += 32) cpa16(dl + c * 16, sl + c * 16);
-                asm volatile("cp.async.commit_group;\n" ::);
+            if (tl + QE_WARPS < t1) {                              // pull this warp's next tile towards L2 while this one is processed
+                const size_t noff = (size_t)tile_off[tl + QE_WARPS];
+                const int nK = max(tile_K[tl + QE_WARPS], 0);
+                const char *pv = reinterpret_cast<const char *>(ell_val + noff);
+                for (int c = lane; c < nK * 2; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + (size_t)c * 128));
+                if (lane < (nK + 3) / 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(ell_lid + noff + (size_t)lane * 128));
             }
-            int k = 0;
-            if (row >= 0) k = rowptr[row + 1] - rowptr[row];
-            asm volatile("cp.async.wait_group 0;\n" ::);
             __syncwarp();
-            if (row >= 0) {
-                double qq = 0.0, tt = 0.0;
-                for (int a = 0; a < k; a++) {
-                    const int la = S.slid[wid][a][lane];
-                    const double va = S.sval[wid][a][lane];
-                    const double *Mr = S.MU[la];
-                    double p0a = 0.5 * Mr[la] * va, p1a = 0.0;
-                    int bb = a + 1;
-                    for (; bb + 1 < k; bb += 2) {
-                        p0a += Mr[S.slid[wid][bb][lane]] * S.sval[wid][bb][lane];
-                        p1a += Mr[S.slid[wid][bb + 1][lane]] * S.sval[wid][bb + 1][lane];
-                    }
-                    if (bb < k) p0a += Mr[S.slid[wid][bb][lane]] * S.sval[wid][bb][lane];
-                    qq += va * (p0a + p1a);
-                    tt += va * S.muU[la];
+            double tt = 0.0;
+            {   // coalesced reads of the entry-major tile: ALL (<= 40) entries of the row in flight before the first scatter
+                double v[KMAX];
+                unsigned char l[KMAX];
+#pragma unroll
+                for (int e = 0; e < KMAX; e++) {
+                    v[e] = 0.0; l[e] = 0;
+                    if (e < K) { v[e] = ell_val[off + (size_t)e * 32 + lane]; l[e] = ell_lid[off + (size_t)e * 32 + lane]; }
                 }
-                if (q && M) q[row] = 2.0 * qq;
-                if (t && mu) t[row] = tt;
+#pragma unroll
+                for (int e = 0; e < KMAX; e++)
+                    if (e < K && v[e] != 0.0) { Xt[l[e]][lane] = v[e]; tt += v[e] * S.muU[l[e]]; }
             }
+            __syncwarp();
+            if (M) {
+                double acc[4][UMAX / 8][2];
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < UMAX / 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+                for (int ks = 0; ks < 2 * nblk; ks++) {            // k-step of 4 columns; contributes to n-blocks >= ks/2
+                    double a[4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; mt++) a[mt] = Xt[4 * ks + tg][8 * mt + g];
+#pragma unroll
+                    for (int nt = 0; nt < UMAX / 8; nt++) {
+                        if (nt >= (ks >> 1) && nt < nblk) {
+                            const double bf = S.MU[4 * ks + tg][8 * nt + g];
+#pragma unroll
+                            for (int mt = 0; mt < 4; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf);
+                        }
+                    }
+                }
+                // q_row = sum_n Y[row][n] X[row][n]; this lane holds Y[8mt + g][8nt + 2tg + {0,1}]
+                double qs[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < UMAX / 8; nt++)
+                        if (nt < nblk)
+                            qs[mt] += acc[mt][nt][0] * Xt[8 * nt + 2 * tg][8 * mt + g] + acc[mt][nt][1] * Xt[8 * nt + 2 * tg + 1][8 * mt + g];
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++) {
+                    qs[mt] += __shfl_xor_sync(0xffffffffu, qs[mt], 1);
+                    qs[mt] += __shfl_xor_sync(0xffffffffu, qs[mt], 2);
+                }
+                // row 8mt + g is complete on the 4 lanes of group g: lane tg == mt stores it
+                if (q) {
+#pragma unroll
+                    for (int mt = 0; mt < 4; mt++) {
+                        const int rr = __shfl_sync(0xffffffffu, row, 8 * mt + g);
+                        if (tg == mt && rr >= 0) q[rr] = qs[mt];
+                    }
+                }
+            }
+            if (t && mu && row >= 0) t[row] = tt;
             __syncwarp();
         }
     }
@@ -595,11 +650,11 @@ extern "C" int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const 
     if (n == 0) return 0;
     static bool attr = false;
     if (!attr) {
-        FRK_CHECK_CUDA(cudaFuncSetAttribute(quadform_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QuadSmem)));
+        FRK_CHECK_CUDA(cudaFuncSetAttribute(quadform_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QuadDmmaSmem)));
         attr = true;
     }
     unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 16);
-    FRK_LAUNCH(ctx, quadform_ell_kernel, grid, QE_T, sizeof(QuadSmem), r, bk->bptr, bk->perm, bk->ucol, bk->nU, bk->btile, bk->tile_K,
+    FRK_LAUNCH(ctx, quadform_ell_kernel, grid, QE_T, sizeof(QuadDmmaSmem), r, bk->bptr, bk->perm, bk->ucol, bk->nU, bk->btile, bk->tile_K,
                bk->tile_off, bk->ell_val, bk->ell_lid, r, d_rowptr, d_col, d_val, d_M, d_mu, d_q, d_t);
     return 0;
 }
