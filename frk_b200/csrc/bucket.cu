@@ -520,6 +520,46 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Y = X MU (block-upper part) for one 32-row tile and q_row = sum_n Y[row][n] X[row][n], NBLK 8-column blocks.
+// On return qs[mt] holds the finished sum for row 8 mt + g on all four lanes of group g.
+template <int NBLK>
+__device__ __forceinline__ void tile_dmma(const double (*Xt)[QD_LDX], const double (*MU)[QD_LDM], int g, int tg, double qs[4]) {
+    double acc[4][NBLK][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NBLK; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    const double *xa = &Xt[tg][g];
+    const double *mb = &MU[tg][g];
+#pragma unroll
+    for (int ks = 0; ks < 2 * NBLK; ks++) {                        // k-step of 4 columns; contributes to n-blocks >= ks/2
+        double a[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) a[mt] = xa[(4 * ks) * QD_LDX + 8 * mt];
+#pragma unroll
+        for (int nt = ks / 2; nt < NBLK; nt++) {
+            const double bf = mb[(4 * ks) * QD_LDM + 8 * nt];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf);
+        }
+    }
+    // this lane holds Y[8mt + g][8nt + 2tg + {0,1}]
+    const double *xe = &Xt[2 * tg][g];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NBLK; nt++) {
+            s0 += acc[mt][nt][0] * xe[(8 * nt) * QD_LDX + 8 * mt];
+            s1 += acc[mt][nt][1] * xe[(8 * nt + 1) * QD_LDX + 8 * mt];
+        }
+        double v = s0 + s1;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        qs[mt] = v;
+    }
+}
+
 __global__ void __launch_bounds__(QE_T, 2) quadform_ell_kernel(int nbuckets, const int *__restrict__ bptr, const int *__restrict__ perm,
                                                                const int *__restrict__ ucol_all, const int *__restrict__ nU_all,
                                                                const int *__restrict__ btile, const int *__restrict__ tile_K,
@@ -597,36 +637,16 @@ __global__ void __launch_bounds__(QE_T, 2) quadform_ell_kernel(int nbuckets, con
             }
             __syncwarp();
             if (M) {
-                double acc[4][UMAX / 8][2];
-#pragma unroll
-                for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < UMAX / 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-                for (int ks = 0; ks < 2 * nblk; ks++) {            // k-step of 4 columns; contributes to n-blocks >= ks/2
-                    double a[4];
-#pragma unroll
-                    for (int mt = 0; mt < 4; mt++) a[mt] = Xt[4 * ks + tg][8 * mt + g];
-#pragma unroll
-                    for (int nt = 0; nt < UMAX / 8; nt++) {
-                        if (nt >= (ks >> 1) && nt < nblk) {
-                            const double bf = S.MU[4 * ks + tg][8 * nt + g];
-#pragma unroll
-                            for (int mt = 0; mt < 4; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf);
-                        }
-                    }
-                }
-                // q_row = sum_n Y[row][n] X[row][n]; this lane holds Y[8mt + g][8nt + 2tg + {0,1}]
-                double qs[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < UMAX / 8; nt++)
-                        if (nt < nblk)
-                            qs[mt] += acc[mt][nt][0] * Xt[8 * nt + 2 * tg][8 * mt + g] + acc[mt][nt][1] * Xt[8 * nt + 2 * tg + 1][8 * mt + g];
-#pragma unroll
-                for (int mt = 0; mt < 4; mt++) {
-                    qs[mt] += __shfl_xor_sync(0xffffffffu, qs[mt], 1);
-                    qs[mt] += __shfl_xor_sync(0xffffffffu, qs[mt], 2);
+                double qs[4];
+                switch (nblk) {                                    // compile-time block counts: no predicates or address math in the loops
+                    case 1: tile_dmma<1>(Xt, S.MU, g, tg, qs); break;
+                    case 2: tile_dmma<2>(Xt, S.MU, g, tg, qs); break;
+                    case 3: tile_dmma<3>(Xt, S.MU, g, tg, qs); break;
+                    case 4: tile_dmma<4>(Xt, S.MU, g, tg, qs); break;
+                    case 5: tile_dmma<5>(Xt, S.MU, g, tg, qs); break;
+                    case 6: tile_dmma<6>(Xt, S.MU, g, tg, qs); break;
+                    case 7: tile_dmma<7>(Xt, S.MU, g, tg, qs); break;
+                    default: tile_dmma<8>(Xt, S.MU, g, tg, qs); break;
                 }
                 // row 8mt + g is complete on the 4 lanes of group g: lane tg == mt stores it
                 if (q) {
