@@ -183,9 +183,11 @@ extern "C" int frk_csr_bucket_rows(frk_ctx *ctx, int64_t n, const int *d_rowptr,
 
 // ---------------------------------------------------------------------------------
 // frk_rowbuckets: the bucket arrays plus a bucket-ordered, transposed copy of the matrix ("ELL tiles").
-// A tile is 32 consecutive rows of a bucket (in perm order) stored entry-major: val[e][lane], lid[e][lane] for
-// e < K_tile = the longest row of the tile (shorter rows padded with val = 0, lid = 0).  A warp reads a tile with
-// fully coalesced 16-byte cp.async copies -- no per-row pointer chasing in the per-iteration kernels.
+// A tile is 32 consecutive rows of a bucket (in perm order) stored entry-major in lane-interleaved vectors:
+// val as double2 [K/2][32] (entries 2j, 2j+1 of a row adjacent), lid as uchar4 [K/4][32]; K = the longest row of the
+// tile rounded up to a multiple of 4.  Shorter rows are padded with val = 0 and the lid of their LAST real entry: a
+// consumer that scatters from the last entry to the first needs no test for padding.  A warp reads a tile with fully
+// coalesced 16-byte / 4-byte loads -- no per-row pointer chasing in the per-iteration kernels.
 // ---------------------------------------------------------------------------------
 struct frk_rowbuckets {
     frk_ctx *ctx = nullptr;
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(256) ell_tile_K_kernel(int ncols, const int *_
             if (p < r1) { const int row = perm[p]; k = rowptr[row + 1] - rowptr[row]; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, o));
+            k = (k + 3) & ~3;
             if (lane == 0) { tile_K[t] = k > KMAX ? -1 : k; tile_len[t] = k > KMAX ? 0 : k * 32; }
         }
     }
@@ -241,9 +244,10 @@ __global__ void __launch_bounds__(256) ell_fill_kernel(int ncols, const int *__r
             int beg = 0, k = 0;
             if (p < r1) { const int row = perm[p]; beg = rowptr[row]; k = rowptr[row + 1] - beg; }
             const size_t off = (size_t)tile_off[t];
+            const unsigned char padl = k > 0 ? lid[beg + k - 1] : (unsigned char)0;
             for (int e = 0; e < K; e++) {
-                ell_val[off + (size_t)e * 32 + lane] = e < k ? val[beg + e] : 0.0;
-                ell_lid[off + (size_t)e * 32 + lane] = e < k ? lid[beg + e] : (unsigned char)0;
+                ell_val[off + (size_t)(e >> 1) * 64 + lane * 2 + (e & 1)] = e < k ? val[beg + e] : 0.0;
+                ell_lid[off + (size_t)(e >> 2) * 128 + lane * 4 + (e & 3)] = e < k ? lid[beg + e] : padl;
             }
         }
     }
@@ -623,17 +627,25 @@ __global__ void __launch_bounds__(QE_T, 2) quadform_ell_kernel(int nbuckets, con
             }
             __syncwarp();
             double tt = 0.0;
-            {   // coalesced reads of the entry-major tile: ALL (<= 40) entries of the row in flight before the first scatter
-                double v[KMAX];
-                unsigned char l[KMAX];
+            {   // coalesced vector reads of the tile: ALL (<= 40) entries of the row in flight before the first scatter
+                const double2 *pv = reinterpret_cast<const double2 *>(ell_val + off) + lane;
+                const uchar4 *pl = reinterpret_cast<const uchar4 *>(ell_lid + off) + lane;
+                double2 v[KMAX / 2];
+                uchar4 l[KMAX / 4];
 #pragma unroll
-                for (int e = 0; e < KMAX; e++) {
-                    v[e] = 0.0; l[e] = 0;
-                    if (e < K) { v[e] = ell_val[off + (size_t)e * 32 + lane]; l[e] = ell_lid[off + (size_t)e * 32 + lane]; }
-                }
+                for (int j = 0; j < KMAX / 4; j++)
+                    if (4 * j < K) { v[2 * j] = pv[(2 * j) * 32]; v[2 * j + 1] = pv[(2 * j + 1) * 32]; l[j] = pl[j * 32]; }
+                double *xs = &Xt[0][lane];
+                double ta = 0.0, tb = 0.0;
 #pragma unroll
-                for (int e = 0; e < KMAX; e++)
-                    if (e < K && v[e] != 0.0) { Xt[l[e]][lane] = v[e]; tt += v[e] * S.muU[l[e]]; }
+                for (int j = KMAX / 4 - 1; j >= 0; j--)            // last entry first: padding (val 0 at the last real column) gets overwritten
+                    if (4 * j < K) {
+                        xs[l[j].w * QD_LDX] = v[2 * j + 1].y; ta += v[2 * j + 1].y * S.muU[l[j].w];
+                        xs[l[j].z * QD_LDX] = v[2 * j + 1].x; tb += v[2 * j + 1].x * S.muU[l[j].z];
+                        xs[l[j].y * QD_LDX] = v[2 * j].y;     ta += v[2 * j].y * S.muU[l[j].y];
+                        xs[l[j].x * QD_LDX] = v[2 * j].x;     tb += v[2 * j].x * S.muU[l[j].x];
+                    }
+                tt = ta + tb;
             }
             __syncwarp();
             if (M) {
