@@ -98,12 +98,15 @@ SIGNATURES = {
     "frk_block_gather": (c_int, [vp, c_int, vp, c_int, vp, vp]),
     "frk_block_scatter": (c_int, [vp, c_int, vp, c_int, vp, vp]),
     "frk_block_gather_outer": (c_int, [vp, c_int, vp, vp, c_int, vp, vp]),
+    "frk_kron_dot": (c_int, [vp, c_int, c_int, vp, vp, vp, p_dbl]),
+    "frk_kron_scatter": (c_int, [vp, c_int, c_int, c_int, vp, vp, c_dbl, vp, vp]),
     "frk_dgemm_nt": (c_int, [vp, c_int, c_int, c_int, c_dbl, vp, c_int, vp, c_int, c_dbl, vp, c_int]),
     "frk_dgemm": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_dbl, vp, c_int, vp, c_int, c_dbl, vp, c_int]),
     "frk_model_create": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, ALLREDUCE_FN, vp, C.POINTER(vp)]),
     "frk_model_create_host": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "frk_model_destroy": (c_int, [vp]),
     "frk_model_set_blocks": (c_int, [vp, c_int, vp, C.POINTER(vp)]),
+    "frk_model_set_blocks_tensor": (c_int, [vp, c_int, c_int, c_int, vp, C.POINTER(vp), vp]),
     "frk_model_init": (c_int, [vp]),
     "frk_model_em_fit": (c_int, [vp, c_int, c_dbl, c_int, c_int, vp, vp, c_int, c_dbl, vp, p_int]),
     "frk_model_loglik": (c_int, [vp, p_dbl]),

@@ -775,3 +775,58 @@ extern "C" int frk_add_diag(frk_ctx *ctx, int r, const double *d_diag, double *d
     FRK_LAUNCH(ctx, add_diag_kernel, (unsigned)cdiv(r, 256), 256, 0, r, d_diag, d_A);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// Kronecker helpers for the block-exponential K of a tensor-product (space x time) basis, R/SREfit.R:496-514,627-649:
+// the (n_t n_s) x (n_t n_s) matrices kronecker(At, As) (time slowest, space fastest) are never formed.
+// ---------------------------------------------------------------------------------
+// partial sums of sum_{a,b} At[ta,tb] As[sa,sb] E[a,b],  a = sa + ns*ta   (sum(diag2(kronecker(Qi1,Qi2), eta2, symm=TRUE)))
+__global__ void __launch_bounds__(256) kron_dot_partial_kernel(int nt, int ns, const double *__restrict__ At, const double *__restrict__ As,
+                                                               const double *__restrict__ E, double *__restrict__ part) {
+    const int64_t n = (int64_t)nt * ns, nn = n * n;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)(i % n), b = (int)(i / n);
+        s += __ldg(At + a / ns + (size_t)nt * (b / ns)) * __ldg(As + a % ns + (size_t)ns * (b % ns)) * E[i];
+    }
+    __shared__ double sh[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0;
+        for (int w = 0; w < 8; w++) v += sh[w];
+        part[blockIdx.x] = v;
+    }
+}
+
+extern "C" int frk_kron_dot(frk_ctx *ctx, int nt, int ns, const double *d_At, const double *d_As, const double *d_E, double *h_out) {
+    FRK_REQUIRE(ctx && d_At && d_As && d_E && h_out && nt > 0 && ns > 0, "frk_kron_dot: bad argument");
+    const int64_t nn = (int64_t)nt * ns * nt * ns;
+    const int nblocks = (int)std::min<int64_t>(cdiv(nn, 256), 1024);
+    double *part = ctx->d_small, *out = ctx->d_small + 2048;
+    FRK_LAUNCH(ctx, kron_dot_partial_kernel, nblocks, 256, 0, nt, ns, d_At, d_As, d_E, part);
+    FRK_LAUNCH(ctx, dot_final_kernel, 1, 32, 0, nblocks, part, out);
+    FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned, out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *h_out = ctx->h_pinned[0];
+    return 0;
+}
+
+// A[idx[a], idx[b]] = scale * At[ta,tb] * As[sa,sb]   (K_i = kronecker(exp(-Dt/tau2), exp(-Ds/tau1)) / omega_i placed by bdiag +
+// reverse_permute, R/SREfit.R:627-649; idx = the ascending tensor columns of the resolution: space fastest, time slowest)
+__global__ void kron_scatter_kernel(int r, int nt, int ns, const double *__restrict__ At, const double *__restrict__ As, double scale,
+                                    const int *__restrict__ idx, double *__restrict__ A) {
+    const int64_t n = (int64_t)nt * ns, nn = n * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)(i % n), b = (int)(i / n);
+        A[idx[a] + (size_t)idx[b] * r] = scale * __ldg(At + a / ns + (size_t)nt * (b / ns)) * __ldg(As + a % ns + (size_t)ns * (b % ns));
+    }
+}
+
+extern "C" int frk_kron_scatter(frk_ctx *ctx, int r, int nt, int ns, const double *d_At, const double *d_As, double scale,
+                                const int *d_idx, double *d_A) {
+    FRK_REQUIRE(ctx && d_At && d_As && d_idx && d_A && nt > 0 && ns > 0, "frk_kron_scatter: bad argument");
+    FRK_LAUNCH(ctx, kron_scatter_kernel, ctx->sm_count * 8, 256, 0, r, nt, ns, d_At, d_As, scale, d_idx, d_A);
+    return 0;
+}

@@ -26,6 +26,10 @@ struct Block {                    // one resolution of the block-exponential K
     int *d_ix = nullptr;
     double *D = nullptr, *eta2 = nullptr, *Ki = nullptr, *Kinv = nullptr, *work = nullptr, *KinvBest = nullptr;
     double D01 = 0.0;
+    // tensor-product basis: n_i = ns * nt, K_i = kronecker(exp(-Dt/tau_t), exp(-D/tau_s)) (D = spatial distances, ns x ns)
+    int ns = 0, nt = 0;
+    double *Ks = nullptr, *Qs = nullptr, *ws = nullptr, *QsBest = nullptr;     // ns x ns
+    double *Kt = nullptr, *Qt = nullptr, *wt = nullptr, *QtBest = nullptr;     // nt x nt
 };
 
 }  // namespace
@@ -52,6 +56,9 @@ struct frk_model {
     // block-exponential K
     std::vector<Block> blocks;
     double max_l = 0.0;
+    bool tensor = false;
+    double *Dt = nullptr;          // nt x nt temporal distances (tensor bases)
+    double Dt01 = 0.0;
     std::vector<double> taus, omegas;
     // multi-rank reduction hook
     frk_allreduce_fn allreduce = nullptr;
@@ -410,6 +417,53 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         RC(frk_dot(ctx, (int64_t)nn, B.Kinv, B.eta2, &trc));
         const double omega = ni / (k00 * trc);                       // (K/k00)^-1 = k00 K^-1
         M->omegas.push_back(omega);
+        if (M->tensor) {
+            // f_tau(tau_s, tau_t), :496-514: K_i^-1 = kronecker(Kt^-1, Ks^-1), log|K_i| = ns log|Kt| + nt log|Ks|
+            const int ns = B.ns, nt = B.nt;
+            const size_t nss = (size_t)ns * ns, ntt = (size_t)nt * nt;
+            double bestF = std::numeric_limits<double>::infinity(), bestTs = -1.0, bestTt = -1.0, bestLd = 0.0;
+            auto f_tau2 = [&](const double *tau, double &fval) -> int {
+                if (tau[0] <= 1e-10 || tau[1] <= 1e-10) { fval = std::numeric_limits<double>::infinity(); return 0; }
+                double ldt, lds, trk;
+                RC(frk_exp_kernel(ctx, (int64_t)ntt, M->Dt, tau[1], 1.0, B.Kt));
+                RC(chol2inv_logdet(ctx, nt, B.Kt, B.Qt, B.wt, &ldt));
+                RC(frk_exp_kernel(ctx, (int64_t)nss, B.D, tau[0], 1.0, B.Ks));
+                RC(chol2inv_logdet(ctx, ns, B.Ks, B.Qs, B.ws, &lds));
+                RC(frk_kron_dot(ctx, nt, ns, B.Qt, B.Qs, B.eta2, &trk));
+                const double det_part = 0.5 * (ns * (-ldt) + nt * (-lds));
+                fval = -(det_part - omega / 2.0 * trk);
+                if (fval < bestF) {
+                    bestF = fval; bestTs = tau[0]; bestTt = tau[1]; bestLd = ns * ldt + nt * lds;
+                    FRK_CHECK_CUDA(cudaMemcpyAsync(B.QsBest, B.Qs, nss * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                    FRK_CHECK_CUDA(cudaMemcpyAsync(B.QtBest, B.Qt, ntt * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                }
+                return 0;
+            };
+            // start values, :596-617: Ki[1,2] (space) and Ki[1, 1 + ns] (time) of the current correlation matrix
+            double kt = 0.0;
+            RC(frk_block_gather(ctx, r, M->Khat, ni, B.d_ix, B.Ki));           // (Kinv above may have overwritten nothing of Ki, but be explicit)
+            RC(frk_d2h(ctx, &kt, B.Ki + (size_t)ns * ni, sizeof(double)));       // element (1, 1 + ns)
+            double p0 = 1e-9, p1;
+            if (ns > 1) { const double v = -B.D01 / std::log(k01 / k00); p0 = (v > 1e-9) ? v : 1e-9; }
+            { const double v = -M->Dt01 / std::log(kt / k00); p1 = (v > 1e-9) ? v : 1e-9; }
+            if (!std::isfinite(p1) || p1 == 1e-9) p1 = 1.0;
+            if (!std::isfinite(p0) || p0 == 1e-9) p0 = M->max_l / 10.0;
+            NMResult nm;
+            RC(nmmin(f_tau2, std::vector<double>{p0, p1}, nm, 100, 1e-4));
+            M->taus.push_back(nm.x[0]); M->taus.push_back(nm.x[1]);
+            if (bestTs != nm.x[0] || bestTt != nm.x[1]) {
+                bestF = std::numeric_limits<double>::infinity();
+                double f;
+                RC(f_tau2(nm.x.data(), f));
+                FRK_REQUIRE(bestTs == nm.x[0] && bestTt == nm.x[1], "block-exponential update: tau cannot be evaluated");
+            }
+            RC(frk_exp_kernel(ctx, (int64_t)ntt, M->Dt, nm.x[1], 1.0, B.Kt));
+            RC(frk_exp_kernel(ctx, (int64_t)nss, B.D, nm.x[0], 1.0, B.Ks));
+            RC(frk_kron_scatter(ctx, r, nt, ns, B.Kt, B.Ks, 1.0 / omega, B.d_ix, Knew));         // :627-649
+            RC(frk_kron_scatter(ctx, r, nt, ns, B.QtBest, B.QsBest, omega, B.d_ix, Kinvnew));
+            logdetK += bestLd - ni * std::log(omega);
+            continue;
+        }
         // f_tau, :485-529.  The inverse and log-determinant at the best tau seen are kept: Nelder-Mead returns its lowest
         // vertex, i.e. an evaluated point, so K_i(tau*)^-1 and log|K_i(tau*)| need no further factorisation.
         double bestF = std::numeric_limits<double>::infinity(), bestTau = -1.0, bestLogdet = 0.0;
@@ -618,6 +672,37 @@ extern "C" int frk_model_set_blocks(frk_model *M, int nres, const int *h_res, co
         FRK_CHECK_CUDA(cudaMemcpy(B.D, h_D[i - 1], nn * sizeof(double), cudaMemcpyHostToDevice));
         B.D01 = B.ni > 1 ? h_D[i - 1][B.ni] : 0.0;                   // D[1,2] (column-major, symmetric)
         if (i == 1) { double mx = 0; for (size_t k = 0; k < nn; k++) mx = std::max(mx, h_D[0][k]); M->max_l = mx; }
+        M->blocks.push_back(B);
+    }
+    return 0;
+}
+
+extern "C" int frk_model_set_blocks_tensor(frk_model *M, int nres, int r_s, int r_t, const int *h_res_s, const double *const *h_Ds,
+                                           const double *h_Dt) {
+    FRK_REQUIRE(M && nres > 0 && h_res_s && h_Ds && h_Dt && r_s > 0 && r_t > 1, "frk_model_set_blocks_tensor: bad argument");
+    FRK_REQUIRE((int64_t)r_s * r_t == M->r, "frk_model_set_blocks_tensor: r_s * r_t = %d * %d does not match r = %d", r_s, r_t, M->r);
+    FRK_REQUIRE(M->blocks.empty(), "frk_model_set_blocks_tensor: already set");
+    M->tensor = true;
+    const size_t ntt = (size_t)r_t * r_t;
+    RC(dalloc(M, &M->Dt, ntt));
+    FRK_CHECK_CUDA(cudaMemcpy(M->Dt, h_Dt, ntt * sizeof(double), cudaMemcpyHostToDevice));
+    M->Dt01 = h_Dt[r_t];                                             // D[1,2]
+    for (int i = 1; i <= nres; i++) {
+        std::vector<int> is, ix;
+        for (int j = 0; j < r_s; j++) if (h_res_s[j] == i) is.push_back(j);
+        FRK_REQUIRE(!is.empty(), "frk_model_set_blocks_tensor: resolution %d has no basis function", i);
+        for (int t = 0; t < r_t; t++) for (int j : is) ix.push_back(j + r_s * t);   // ascending tensor columns: space fastest
+        Block B;
+        B.ns = (int)is.size(); B.nt = r_t; B.ni = (int)ix.size(); B.ix0 = ix[0];
+        const size_t nn = (size_t)B.ni * B.ni, nss = (size_t)B.ns * B.ns;
+        RC(dalloc(M, &B.d_ix, ix.size())); RC(dalloc(M, &B.D, nss)); RC(dalloc(M, &B.eta2, nn)); RC(dalloc(M, &B.Ki, nn));
+        RC(dalloc(M, &B.Kinv, nn)); RC(dalloc(M, &B.work, nn));
+        RC(dalloc(M, &B.Ks, nss)); RC(dalloc(M, &B.Qs, nss)); RC(dalloc(M, &B.ws, nss)); RC(dalloc(M, &B.QsBest, nss));
+        RC(dalloc(M, &B.Kt, ntt)); RC(dalloc(M, &B.Qt, ntt)); RC(dalloc(M, &B.wt, ntt)); RC(dalloc(M, &B.QtBest, ntt));
+        FRK_CHECK_CUDA(cudaMemcpy(B.d_ix, ix.data(), ix.size() * sizeof(int), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(B.D, h_Ds[i - 1], nss * sizeof(double), cudaMemcpyHostToDevice));
+        B.D01 = B.ns > 1 ? h_Ds[i - 1][B.ns] : 0.0;
+        if (i == 1) { double mx = 0; for (size_t k = 0; k < nss; k++) mx = std::max(mx, h_Ds[0][k]); M->max_l = mx; }
         M->blocks.push_back(B);
     }
     return 0;

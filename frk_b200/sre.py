@@ -160,9 +160,6 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
             raise ValueError(f"covariate {c!r} is not a field of the BAUs (covariates must be known at every BAU)")
     if not intercept and not covs:
         raise FRKError("a model without fixed effects is not on the device path (at least an intercept is needed)")
-    if K_type == "block-exponential" and isinstance(basis, TensorP_Basis):
-        raise FRKError("K_type='block-exponential' with a tensor-product basis is not on the device path yet; "
-                       "use K_type='unstructured'")
     dev = dev or get_device()
     t0 = time.time()
     r = basis.n
@@ -222,7 +219,17 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
     mdl = SREModel(dev, f, basis, BAUs, K_type, N, lo, hi, m, S0, S, obs_bau, Z, X, X_BAU, Ve, Vfs, fs_BAU, p)
     mdl._keep = binned                                            # Z / obs_bau are views into these buffers
     mdl.h2d_bytes = h2d
-    if K_type == "block-exponential":                             # BuildD(basis), R/SRE.R:424
+    if K_type == "block-exponential" and isinstance(basis, TensorP_Basis):     # BuildD(basis) = list(Basis1 = ..., Basis2 = ...)
+        D = BuildD(basis)
+        mdl.D_basis = [np.asfortranarray(d, dtype=np.float64) for d in D["Basis1"]]
+        Dt = np.asfortranarray(D["Basis2"][0], dtype=np.float64)
+        res_s = np.ascontiguousarray(basis.Basis1.res, dtype=np.int32)
+        ptrs = (vp * len(mdl.D_basis))(*[vp(d.ctypes.data) for d in mdl.D_basis])
+        call("frk_model_set_blocks_tensor", mdl.handle, len(mdl.D_basis), basis.Basis1.n, basis.Basis2.n, vp(res_s.ctypes.data), ptrs,
+             vp(Dt.ctypes.data))
+        mdl.h2d_bytes += sum(d.nbytes for d in mdl.D_basis) + Dt.nbytes
+        mdl._tensor = True
+    elif K_type == "block-exponential":                           # BuildD(basis), R/SRE.R:424
         mdl.D_basis = [np.asfortranarray(D, dtype=np.float64) for D in BuildD(basis)]
         res = np.ascontiguousarray(basis.res, dtype=np.int32)
         ptrs = (vp * len(mdl.D_basis))(*[vp(D.ctypes.data) for D in mdl.D_basis])
@@ -267,7 +274,8 @@ def SRE_fit(mdl: SREModel, n_EM: int = 100, tol: float = 0.01, method: str = "EM
                         llk=llk[:nit].copy(), sigma2fshat_equal_0=int(s2 == 0))
     if mdl.K_type == "block-exponential":
         nres = len(mdl.D_basis)
-        mdl.info_fit["tau"] = mdl.get("tau")[:nres].tolist()
+        ntau = nres * (2 if getattr(mdl, "_tensor", False) else 1)
+        mdl.info_fit["tau"] = mdl.get("tau")[:ntau].tolist()
         mdl.info_fit["omega"] = mdl.get("omega")[:nres].tolist()
     return mdl
 

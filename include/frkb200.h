@@ -262,6 +262,11 @@ int frk_block_scatter(frk_ctx *ctx, int r, double *d_A, int ni, const int *d_idx
 /* out[i + ni*j] = x[idx[i]]*x[idx[j]] + A[idx[i], idx[j]]  (eta2 blocks, R/SREfit.R:459-464) */
 int frk_block_gather_outer(frk_ctx *ctx, int r, const double *d_A, const double *d_x, int ni,
                            const int *d_idx, double *d_out);
+/* Kronecker helpers for the block-exponential K of a tensor-product basis (time slowest, space fastest; R/SREfit.R:496-514,
+ * 627-649); kronecker(At, As) is never formed.  *h_out = sum(kronecker(At, As) * E);  A[idx[a], idx[b]] = scale * kron(At, As)[a, b]. */
+int frk_kron_dot(frk_ctx *ctx, int nt, int ns, const double *d_At, const double *d_As, const double *d_E, double *h_out);
+int frk_kron_scatter(frk_ctx *ctx, int r, int nt, int ns, const double *d_At, const double *d_As, double scale,
+                     const int *d_idx, double *d_A);
 /* C(MxN, ldc) = beta*C + alpha * A(MxK, lda) * B(NxK, ldb)'  -- the fp64 tensor-core GEMM all
  * blocked factorisations are built from (exported for tests and the fp64 peak probe).       */
 int frk_dgemm_nt(frk_ctx *ctx, int M, int N, int K, double alpha, const double *d_A, int lda,
@@ -286,6 +291,11 @@ int frk_model_destroy(frk_model *mdl);
 /* BuildD() (R/basisfns.R:1131-1153) for K_type = "block-exponential": h_res[r] 1-based resolution of every basis
  * function, h_D[i] the r_i x r_i centroid distance matrix of resolution i+1 (column-major, host).              */
 int frk_model_set_blocks(frk_model *mdl, int nres, const int *h_res, const double *const *h_D);
+/* the same for a TensorP_Basis (space x time): r = r_s * r_t, tensor column = j_s + r_s * j_t (R/basisfns.R:821-822);
+ * h_res_s[r_s] spatial resolutions, h_Ds[i] the spatial distance matrices per resolution (D_basis$Basis1), h_Dt the
+ * r_t x r_t temporal one (D_basis$Basis2[[1]]).  tau_i = (spatial, temporal) by 2-D Nelder-Mead.                     */
+int frk_model_set_blocks_tensor(frk_model *mdl, int nres, int r_s, int r_t, const int *h_res_s,
+                                const double *const *h_Ds, const double *h_Dt);
 /* .EM_initialise (R/SRE.R:704-731) */
 int frk_model_init(frk_model *mdl);
 /* .EM_fit (R/SREfit.R:78-160): up to n_EM iterations of logLik + E-step + M-step; stops when the log-likelihood

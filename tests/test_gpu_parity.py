@@ -387,5 +387,12 @@ def test_config4_noaa_spacetime_tensor_basis(dev):
     pg = F.predict(Mg, obs_fs=False)
     np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-8)
     np.testing.assert_allclose(pg["var"], po[1], rtol=1e-7)
-    with pytest.raises(F.FRKError, match="tensor-product"):
-        F.SRE("z ~ 1", data, gtb, baus, est_error=False, K_type="block-exponential")
+    # block-exponential K for the tensor basis: kronecker(time, space) blocks, 2-D Nelder-Mead per resolution (R/SREfit.R:496-514)
+    Mo2 = O.SRE(ot, cen, np.ones(len(cen)), uo, means[:, 0], means[:, 1], K_type="block-exponential")
+    Mg2 = F.SRE("z ~ 1", data, gtb, baus, est_error=False, K_type="block-exponential")
+    O.SRE_fit(Mo2, n_EM=3, tol=0.0)
+    F.SRE_fit(Mg2, n_EM=3, tol=0.0)
+    np.testing.assert_allclose(Mg2.info_fit["llk"], Mo2.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg2.info_fit["tau"], np.concatenate(Mo2.info_fit["tau"]), rtol=1e-6)
+    np.testing.assert_allclose(Mg2.get("Khat"), Mo2.Khat, rtol=1e-6, atol=1e-9 * abs(Mo2.Khat).max())
+    np.testing.assert_allclose(F.predict(Mg2, obs_fs=False)["var"], O.predict(Mo2, obs_fs=False)[1], rtol=1e-6)
