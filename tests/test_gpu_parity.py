@@ -396,3 +396,74 @@ def test_config4_noaa_spacetime_tensor_basis(dev):
     np.testing.assert_allclose(Mg2.info_fit["tau"], np.concatenate(Mo2.info_fit["tau"]), rtol=1e-6)
     np.testing.assert_allclose(Mg2.get("Khat"), Mo2.Khat, rtol=1e-6, atol=1e-9 * abs(Mo2.Khat).max())
     np.testing.assert_allclose(F.predict(Mg2, obs_fs=False)["var"], O.predict(Mo2, obs_fs=False)[1], rtol=1e-6)
+
+
+def test_fit_options_and_slot_roundtrip(dev):
+    """SRE.fit options on the device path: ridge lambda (unstructured K, R/SREfit.R:664-694), known_sigma2fs (:288-293), early stop on
+    tol (:110-114), logLik(), and resuming EM from slots pushed back through frk_model_set (the S4 object is the checkpoint)."""
+    import frk_b200 as F
+    # ridge, scalar and per-resolution
+    for lam in (0.3, np.array([0.1, 0.7])):
+        Mo, Mg = _setup_plane(F, K_type="unstructured", hetero=True)
+        O.SRE_fit(Mo, n_EM=3, tol=0.0, lam=lam)
+        F.SRE_fit(Mg, n_EM=3, tol=0.0, lambda_=lam)
+        np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+        np.testing.assert_allclose(Mg.get("Khat"), Mo.Khat, rtol=1e-7, atol=1e-10 * abs(Mo.Khat).max())
+    # known sigma2fs
+    Mo, Mg = _setup_plane(F, K_type="block-exponential", hetero=True)
+    O.SRE_fit(Mo, n_EM=3, tol=0.0, known_sigma2fs=0.05)
+    F.SRE_fit(Mg, n_EM=3, tol=0.0, known_sigma2fs=0.05)
+    assert Mg.sigma2fshat == 0.05
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(F.loglik(Mg), O.loglik(Mo), rtol=RTOL)
+    # early stop: same number of iterations, converged flag
+    Mo, Mg = _setup_plane(F, K_type="unstructured")
+    O.SRE_fit(Mo, n_EM=50, tol=2.0)
+    F.SRE_fit(Mg, n_EM=50, tol=2.0)
+    assert Mg.info_fit["num_iterations"] == Mo.info_fit["num_iterations"] < 50 and Mg.info_fit["converged"] == 1
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    # resume: 2 + 2 iterations through a slot round trip == 4 iterations
+    _, Ma = _setup_plane(F, K_type="block-exponential", hetero=True)
+    _, Mb = _setup_plane(F, K_type="block-exponential", hetero=True)
+    F.SRE_fit(Ma, n_EM=4, tol=0.0)
+    F.SRE_fit(Mb, n_EM=2, tol=0.0)
+    slots = {k: Mb.get(k) for k in ("mu_eta", "S_eta", "Q_eta", "Khat_inv", "Khat", "alphahat")}
+    s2 = Mb.sigma2fshat
+    _, Mc = _setup_plane(F, K_type="block-exponential", hetero=True)
+    for k in ("mu_eta", "S_eta", "Q_eta", "Khat_inv", "alphahat", "Khat"):
+        Mc.set(k, slots[k])
+    Mc.set("sigma2fshat", [s2])
+    F.SRE_fit(Mc, n_EM=2, tol=0.0)
+    np.testing.assert_allclose(Mc.info_fit["llk"], Ma.info_fit["llk"][2:], rtol=1e-9)
+    np.testing.assert_allclose(Mc.sigma2fshat, Ma.sigma2fshat, rtol=1e-6)
+
+
+def test_degenerate_inputs(dev):
+    """empty and ragged inputs: no points, points outside every BAU, a basis function that no point touches, a single observation per
+    call of the host-buffer entry points."""
+    import ctypes as C
+    import frk_b200 as F
+    from frk_b200._lib import call, vp
+    gb = F.auto_BAUs(F.plane(), cellsize=0.1, xlims=(0, 1), ylims=(0, 1))
+    gb["fs"] = 1.0
+    basis = F.auto_basis(F.plane(), np.array([[0.0, 0.0], [1.0, 1.0]]), nres=1)
+    out = F.map_data_to_BAUs(F.SpatialPointsDataFrame(np.zeros((0, 2)), {"z": np.zeros(0), "std": np.zeros(0)}), gb, ["z", "std"], dev)
+    assert out["m"] == 0
+    xy = np.array([[5.0, 5.0], [-3.0, 0.2]])
+    with pytest.raises(F.FRKError, match="no observation falls inside a BAU"):
+        F.SRE("z ~ 1", F.SpatialPointsDataFrame(xy, {"z": np.ones(2), "std": np.ones(2)}), basis, gb, est_error=False)
+    # rows far from every centroid are empty rows of S0; normalisation leaves them empty (xx == 0 -> 1, R/SRE.R:418)
+    far = np.array([[50.0, 50.0], [0.5, 0.5]])
+    S = F.eval_basis_device(basis, far, dev, normalise=True).to_scipy(dev)
+    assert S[0].nnz == 0 and abs(np.sqrt((S[1].toarray() ** 2).sum()) - 1.0) < 1e-15
+    # quadform through the host-buffer entry point with an empty row
+    r = basis.n
+    Mm = _dense_case(r, 1)
+    q = np.zeros(2); t = np.zeros(2); mu = np.arange(r, dtype=float)
+    Mf = np.asfortranarray(Mm)
+    call("frk_quadform_host", dev.ctx, 2, r, vp(S.indptr.ctypes.data), vp(S.indices.ctypes.data), vp(S.data.ctypes.data),
+         vp(Mf.ctypes.data), vp(mu.ctypes.data), vp(q.ctypes.data), vp(t.ctypes.data))
+    d = S.toarray()
+    np.testing.assert_allclose(q, np.einsum("ij,jk,ik->i", d, Mm, d), rtol=1e-12)
+    np.testing.assert_allclose(t, d @ mu, rtol=1e-12)
+    assert q[0] == 0.0 and t[0] == 0.0
