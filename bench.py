@@ -316,23 +316,27 @@ def run_b200(args):
                     "share_of_step": round(g["ms"] / tot_ms, 4), "note": "latency-bound (sequential column dependency), not throughput-bound"}
 
     # ---- (C) end to end through the public host-buffer API -------------------------------------------
+    # one untimed pass first (it allocates the pinned result buffers and fills the allocator pools), then the timed pass
     del mdl
     torch.cuda.empty_cache()
-    barrier()
-    t0 = time.perf_counter()
-    m2 = F.SRE("z ~ 1", data, basis, BAUs, est_error=False, K_type=args.k_type, dev=dev)
-    F.SRE_fit(m2, n_EM=args.steps, tol=0.0)
-    slots = {k: m2.get(k) for k in ("mu_eta", "S_eta", "Khat", "Khat_inv")}
-    barrier()
-    t_fit_e2e = max_over_ranks(time.perf_counter() - t0)
-    h2d_fit, d2h_fit = m2.h2d_bytes, m2.d2h_bytes
-    t0 = time.perf_counter()
-    pr = F.predict(m2, obs_fs=False, to_host=True)
-    barrier()
-    t_pred_e2e = max_over_ranks(time.perf_counter() - t0)
-    d2h_pred = 3 * 8 * (m2.hi - m2.lo)
-    finite = bool(np.isfinite(pr["mu"]).all() and (pr["var"] > 0).all())
-    m_binned = m2.m_total
+    for timed in (False, True):
+        barrier()
+        t0 = time.perf_counter()
+        m2 = F.SRE("z ~ 1", data, basis, BAUs, est_error=False, K_type=args.k_type, dev=dev)
+        F.SRE_fit(m2, n_EM=args.steps, tol=0.0)
+        slots = {k: m2.get(k) for k in ("mu_eta", "S_eta", "Khat", "Khat_inv")}
+        barrier()
+        t_fit_e2e = max_over_ranks(time.perf_counter() - t0)
+        h2d_fit, d2h_fit = m2.h2d_bytes, m2.d2h_bytes
+        t0 = time.perf_counter()
+        pr = F.predict(m2, obs_fs=False, to_host=True)
+        barrier()
+        t_pred_e2e = max_over_ranks(time.perf_counter() - t0)
+        d2h_pred = 3 * 8 * (m2.hi - m2.lo)
+        finite = bool(np.isfinite(pr["mu"]).all() and (pr["var"] > 0).all())
+        m_binned = m2.m_total
+        if not timed:
+            del m2, slots, pr
 
     # ---- (E) CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
@@ -349,7 +353,7 @@ def run_b200(args):
                             "e2e": {"value": N / t_pred_e2e, "unit": "BAUs/s", "d2h_bytes": d2h_pred * world, "results_ok": finite}},
                 "e2e": {"value": args.steps / t_fit_e2e, "unit": "EM iters/s", "h2d_bytes_per_step": h2d_fit / args.steps,
                         "d2h_bytes_per_step": d2h_fit / args.steps,
-                        "what": f"SRE() from pinned host arrays + SRE_fit({args.steps} EM iterations) + fitted r x r slots back to host, wall clock"},
+                        "what": f"SRE() from pinned host arrays + SRE_fit({args.steps} EM iterations from .EM_initialise) + fitted slots (mu_eta, S_eta, Khat, Khat_inv) back to pinned host memory, wall clock, after one untimed pass"},
                 "gpu_launches": int(launches), "clocks": clk, "llk_last": llk_tail}
         if roof:
             line["roofline"] = roof

@@ -55,6 +55,7 @@ SIGNATURES = {
     "frk_profile_report": (c_int, [vp, C.c_char_p, C.c_size_t]),
     "frk_basis_create": (c_int, [vp, c_int, c_dbl, c_int, c_int, c_int, vp, vp, vp, C.POINTER(vp)]),
     "frk_basis_destroy": (c_int, [vp]),
+    "frk_basis_dist_matrix": (c_int, [vp, vp, c_int, vp, vp]),
     "frk_basis_n": (c_int, [vp]),
     "frk_basis_dim": (c_int, [vp]),
     "frk_eval_basis_count": (c_int, [vp, vp, c_i64, vp, c_i64, vp, p_i64]),
@@ -106,6 +107,7 @@ SIGNATURES = {
     "frk_model_create_host": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "frk_model_destroy": (c_int, [vp]),
     "frk_model_set_blocks": (c_int, [vp, c_int, vp, C.POINTER(vp)]),
+    "frk_model_set_blocks_basis": (c_int, [vp, c_int, vp, vp]),
     "frk_model_set_blocks_tensor": (c_int, [vp, c_int, c_int, c_int, vp, C.POINTER(vp), vp]),
     "frk_model_init": (c_int, [vp]),
     "frk_model_em_fit": (c_int, [vp, c_int, c_dbl, c_int, c_int, vp, vp, c_int, c_dbl, vp, p_int]),

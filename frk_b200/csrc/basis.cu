@@ -564,3 +564,26 @@ extern "C" int frk_csr_row_normalise(frk_ctx *ctx, int64_t n, const int *d_rowpt
     FRK_LAUNCH(ctx, row_normalise_kernel, (unsigned)cdiv(n, 256), 256, 0, n, d_rowptr, d_val);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// BuildD (R/basisfns.R:1131-1153): centroid-to-centroid distance matrix of one resolution, D[a + ni*b] =
+// distance(centroid idx[a], centroid idx[b]) in the reference's operation order (distR / dist_sphere).
+// ---------------------------------------------------------------------------------
+template <int MAN>
+__global__ void basis_dist_matrix_kernel(BasisDev B, int ni, const int *__restrict__ idx, double *__restrict__ D) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)ni * ni; t += (int64_t)gridDim.x * blockDim.x) {
+        const int ja = idx[t % ni], jb = idx[t / ni];
+        PointCoord p;
+        p.a = __ldg(B.c0 + ja); p.b = __ldg(B.c1 + ja); p.c = __ldg(B.c2 + ja); p.u = p.v = 0;
+        D[t] = basis_dist<MAN>(p, B, jb);
+    }
+}
+
+extern "C" int frk_basis_dist_matrix(frk_ctx *ctx, const frk_basis *b, int ni, const int *d_idx, double *d_D) {
+    FRK_REQUIRE(ctx && b && d_idx && d_D && ni > 0, "frk_basis_dist_matrix: bad argument");
+    const unsigned grid = ctx->sm_count * 8;
+    if (b->dev.manifold == FRK_SPHERE) FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_SPHERE>, grid, 256, 0, b->dev, ni, d_idx, d_D);
+    else if (b->dev.manifold == FRK_PLANE) FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_PLANE>, grid, 256, 0, b->dev, ni, d_idx, d_D);
+    else FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_REAL_LINE>, grid, 256, 0, b->dev, ni, d_idx, d_D);
+    return 0;
+}

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) ell_fill_kernel(int ncols, const int *__r
 template <typename T>
 static int rb_alloc(frk_rowbuckets *B, T **out, size_t n) {
     void *p = nullptr;
-    FRK_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
+    FRK_CHECK_CUDA(cudaMallocAsync(&p, std::max<size_t>(n * sizeof(T), 16), B->ctx->stream));   // pooled
     B->allocs.push_back(p);
     *out = (T *)p;
     return 0;
@@ -266,7 +266,7 @@ extern "C" int frk_rowbuckets_destroy(frk_rowbuckets *B) {
     if (!B) return 0;
     cudaSetDevice(B->ctx->device);
     cudaStreamSynchronize(B->ctx->stream);
-    for (void *p : B->allocs) cudaFree(p);
+    for (void *p : B->allocs) cudaFreeAsync(p, B->ctx->stream);
     delete B;
     return 0;
 }

@@ -73,7 +73,7 @@ namespace {
 template <typename T>
 int dalloc(frk_model *M, T **out, size_t n) {
     void *p = nullptr;
-    FRK_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 8)));
+    FRK_CHECK_CUDA(cudaMallocAsync(&p, std::max<size_t>(n * sizeof(T), 16), M->ctx->stream));   // pooled: re-creating a model is cheap
     M->allocs.push_back(p);
     *out = (T *)p;
     return 0;
@@ -648,15 +648,15 @@ extern "C" int frk_model_destroy(frk_model *M) {
     if (!M) return 0;
     cudaSetDevice(M->ctx->device);
     cudaStreamSynchronize(M->ctx->stream);
-    for (void *p : M->allocs) cudaFree(p);
+    for (void *p : M->allocs) cudaFreeAsync(p, M->ctx->stream);
     frk_rowbuckets_destroy(M->bk);
     delete M;
     return 0;
 }
 
 // per-resolution index sets and centroid distance matrices (BuildD, R/basisfns.R:1131-1153) for K_type = "block-exponential"
-extern "C" int frk_model_set_blocks(frk_model *M, int nres, const int *h_res, const double *const *h_D) {
-    FRK_REQUIRE(M && nres > 0 && h_res && h_D, "frk_model_set_blocks: bad argument");
+static int set_blocks_impl(frk_model *M, int nres, const int *h_res, const double *const *h_D, const frk_basis *basis) {
+    FRK_REQUIRE(M && nres > 0 && h_res, "frk_model_set_blocks: bad argument");
     FRK_REQUIRE(M->blocks.empty(), "frk_model_set_blocks: already set");
     const int r = M->r;
     for (int i = 1; i <= nres; i++) {
@@ -668,13 +668,31 @@ extern "C" int frk_model_set_blocks(frk_model *M, int nres, const int *h_res, co
         const size_t nn = (size_t)B.ni * B.ni;
         RC(dalloc(M, &B.d_ix, ix.size())); RC(dalloc(M, &B.D, nn)); RC(dalloc(M, &B.eta2, nn)); RC(dalloc(M, &B.Ki, nn));
         RC(dalloc(M, &B.Kinv, nn)); RC(dalloc(M, &B.work, nn)); RC(dalloc(M, &B.KinvBest, nn));
-        FRK_CHECK_CUDA(cudaMemcpy(B.d_ix, ix.data(), ix.size() * sizeof(int), cudaMemcpyHostToDevice));
-        FRK_CHECK_CUDA(cudaMemcpy(B.D, h_D[i - 1], nn * sizeof(double), cudaMemcpyHostToDevice));
-        B.D01 = B.ni > 1 ? h_D[i - 1][B.ni] : 0.0;                   // D[1,2] (column-major, symmetric)
-        if (i == 1) { double mx = 0; for (size_t k = 0; k < nn; k++) mx = std::max(mx, h_D[0][k]); M->max_l = mx; }
+        FRK_CHECK_CUDA(cudaMemcpyAsync(B.d_ix, ix.data(), ix.size() * sizeof(int), cudaMemcpyHostToDevice, M->ctx->stream));
+        FRK_CHECK_CUDA(cudaStreamSynchronize(M->ctx->stream));       // ix is a temporary
+        if (h_D) {
+            FRK_CHECK_CUDA(cudaMemcpyAsync(B.D, h_D[i - 1], nn * sizeof(double), cudaMemcpyHostToDevice, M->ctx->stream));
+            B.D01 = B.ni > 1 ? h_D[i - 1][B.ni] : 0.0;               // D[1,2] (column-major, symmetric)
+            if (i == 1) { double mx = 0; for (size_t k = 0; k < nn; k++) mx = std::max(mx, h_D[0][k]); M->max_l = mx; }
+        } else {                                                     // BuildD on the device from the basis' centroid table
+            RC(frk_basis_dist_matrix(M->ctx, basis, B.ni, B.d_ix, B.D));
+            if (B.ni > 1) RC(frk_d2h(M->ctx, &B.D01, B.D + B.ni, sizeof(double)));
+            if (i == 1) { double st[4]; RC(frk_vec_stats(M->ctx, (int64_t)nn, B.D, 0.0, st)); M->max_l = st[3]; }
+        }
         M->blocks.push_back(B);
     }
     return 0;
+}
+
+extern "C" int frk_model_set_blocks(frk_model *M, int nres, const int *h_res, const double *const *h_D) {
+    FRK_REQUIRE(h_D, "frk_model_set_blocks: bad argument");
+    return set_blocks_impl(M, nres, h_res, h_D, nullptr);
+}
+
+// BuildD on the device: the distance matrices come from the basis' own centroid table (same arithmetic as eval_basis)
+extern "C" int frk_model_set_blocks_basis(frk_model *M, int nres, const int *h_res, const frk_basis *basis) {
+    FRK_REQUIRE(basis && frk_basis_n(basis) == (M ? M->r : -1), "frk_model_set_blocks_basis: the basis does not match the model");
+    return set_blocks_impl(M, nres, h_res, nullptr, basis);
 }
 
 extern "C" int frk_model_set_blocks_tensor(frk_model *M, int nres, int r_s, int r_t, const int *h_res_s, const double *const *h_Ds,

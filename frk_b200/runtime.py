@@ -54,10 +54,16 @@ class Device:
             call("frk_sync", self.ctx)      # flat may be a temporary
         return out
 
+    def host_buffer(self, n: int, dtype=np.float64) -> np.ndarray:
+        """Pinned host array (the memory belongs to a torch tensor that the returned array keeps alive): D2H copies of the
+        r x r slots and of the N-sized prediction vectors run at PCIe speed instead of through a pageable bounce buffer."""
+        td = {np.float64: self.torch.float64, np.int32: self.torch.int32, np.int64: self.torch.int64}[dtype]
+        return self.torch.empty(int(max(n, 1)), dtype=td, pin_memory=True).numpy()[:int(n)]
+
     def download(self, t, n: Optional[int] = None) -> np.ndarray:
         n = t.numel() if n is None else int(n)
         npdt = {8: {True: np.float64, False: np.int64}, 4: {False: np.int32}}[t.element_size()][t.is_floating_point()]
-        out = np.empty(n, dtype=npdt)
+        out = self.host_buffer(n, npdt) if n * t.element_size() >= (1 << 20) else np.empty(n, dtype=npdt)
         if n:
             call("frk_d2h", self.ctx, vp(out.ctypes.data), self.ptr(t), out.nbytes)
         return out

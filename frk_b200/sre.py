@@ -96,11 +96,12 @@ class SREModel:
         """Host copy of a slot (what the R shim writes back into the S4 object); r x r slots as (r, r) arrays."""
         n = {"mu_eta": self.r, "alphahat": self.p, "sigma2fshat": 1, "m_total": 1, "homoscedastic": 1,
              "tau": 16, "omega": 16}.get(name, self.r * self.r)
-        out = np.zeros(n)
+        big = name in ("S_eta", "Q_eta", "Khat", "Khat_inv")
+        out = self.dev.host_buffer(n) if big else np.zeros(n)       # pinned staging for the r x r slots
         call("frk_model_get", self.handle, name.encode(), vp(out.ctypes.data))
-        if name in ("S_eta", "Q_eta", "Khat", "Khat_inv"):
+        if big:
             self.d2h_bytes += out.nbytes
-            return out.reshape(self.r, self.r).T.copy()
+            return out.reshape(self.r, self.r)                      # symmetric: column-major == row-major
         return out
 
     def set(self, name: str, value) -> None:
@@ -229,12 +230,10 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
              vp(Dt.ctypes.data))
         mdl.h2d_bytes += sum(d.nbytes for d in mdl.D_basis) + Dt.nbytes
         mdl._tensor = True
-    elif K_type == "block-exponential":                           # BuildD(basis), R/SRE.R:424
-        mdl.D_basis = [np.asfortranarray(D, dtype=np.float64) for D in BuildD(basis)]
+    elif K_type == "block-exponential":                           # BuildD(basis), R/SRE.R:424 -- on the device, from the basis handle
         res = np.ascontiguousarray(basis.res, dtype=np.int32)
-        ptrs = (vp * len(mdl.D_basis))(*[vp(D.ctypes.data) for D in mdl.D_basis])
-        call("frk_model_set_blocks", mdl.handle, len(mdl.D_basis), vp(res.ctypes.data), ptrs)
-        mdl.h2d_bytes += sum(D.nbytes for D in mdl.D_basis)
+        mdl.D_basis = [None] * basis.nres                         # (host copies on demand: frk_b200.BuildD(basis))
+        call("frk_model_set_blocks_basis", mdl.handle, basis.nres, vp(res.ctypes.data), basis.handle(dev))
     call("frk_model_init", mdl.handle)                            # .EM_initialise, R/SRE.R:656,704-731
     mdl.info_fit["time_SRE"] = time.time() - t0
     return mdl

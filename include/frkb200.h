@@ -81,6 +81,8 @@ int frk_basis_create(frk_ctx *ctx, int manifold, double radius, int type, int d,
                      const double *h_loc, const double *h_scale, const int *h_res,
                      frk_basis **out);
 int frk_basis_destroy(frk_basis *b);
+/* BuildD (R/basisfns.R:1131-1153) for the ni centroids d_idx: d_D[a + ni*b] = distance(centroid idx[a], centroid idx[b]) */
+int frk_basis_dist_matrix(frk_ctx *ctx, const frk_basis *b, int ni, const int *d_idx, double *d_D);
 int frk_basis_n(const frk_basis *b);     /* number of basis functions r     */
 int frk_basis_dim(const frk_basis *b);   /* manifold dimension d (1 or 2)    */
 
@@ -291,6 +293,9 @@ int frk_model_destroy(frk_model *mdl);
 /* BuildD() (R/basisfns.R:1131-1153) for K_type = "block-exponential": h_res[r] 1-based resolution of every basis
  * function, h_D[i] the r_i x r_i centroid distance matrix of resolution i+1 (column-major, host).              */
 int frk_model_set_blocks(frk_model *mdl, int nres, const int *h_res, const double *const *h_D);
+/* BuildD on the device: the per-resolution distance matrices are computed from the basis' own centroid table with the
+ * arithmetic of distR / dist_sphere (no r_i x r_i host matrices, no upload).                                          */
+int frk_model_set_blocks_basis(frk_model *mdl, int nres, const int *h_res, const frk_basis *basis);
 /* the same for a TensorP_Basis (space x time): r = r_s * r_t, tensor column = j_s + r_s * j_t (R/basisfns.R:821-822);
  * h_res_s[r_s] spatial resolutions, h_Ds[i] the spatial distance matrices per resolution (D_basis$Basis1), h_Dt the
  * r_t x r_t temporal one (D_basis$Basis2[[1]]).  tau_i = (spatial, temporal) by 2-D Nelder-Mead.                     */
