@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -30,6 +31,10 @@ struct frk_ctx {
     std::vector<frk_prof_rec> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
     std::map<std::string, frk_prof_stat> prof_stats;
+    // CUDA-graph cache for the launch-latency-bound factorisations: key = (op, r, pointers)
+    bool use_graphs = true;
+    struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; };
+    std::map<std::array<uintptr_t, 5>, GraphEntry> graphs;
 };
 
 int frk_prof_begin(frk_ctx *ctx, const char *name, cudaEvent_t *e1);   // records e0; returns 0

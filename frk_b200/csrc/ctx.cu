@@ -51,6 +51,7 @@ extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     frk_prof_harvest(ctx);
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -152,6 +153,12 @@ extern "C" int frk_profile_report(frk_ctx *ctx, char *buf, size_t cap) {
     out += "]";
     FRK_REQUIRE(out.size() + 1 <= cap, "frk_profile_report: buffer too small (%zu needed)", out.size() + 1);
     memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
+extern "C" int frk_use_graphs(frk_ctx *ctx, int enable) {
+    FRK_REQUIRE(ctx, "frk_use_graphs: NULL ctx");
+    ctx->use_graphs = enable != 0;
     return 0;
 }
 

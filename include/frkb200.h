@@ -70,6 +70,8 @@ int64_t frk_launch_count(frk_ctx *ctx);
 /* Per-kernel device timing for bench.py's roofline: while enabled every launch is bracketed by CUDA events
  * on the ctx stream; the report is a JSON array of {kernel, launches, ms, flops, bytes} where flops/bytes
  * are the ALGORITHMIC work declared at the launch site.  Enabling clears earlier statistics. */
+/* The factorisations replay cached CUDA graphs of their launch sequences (default on; off while profiling). */
+int frk_use_graphs(frk_ctx *ctx, int enable);
 int frk_profile(frk_ctx *ctx, int enable);
 int frk_profile_report(frk_ctx *ctx, char *buf, size_t cap);
 
