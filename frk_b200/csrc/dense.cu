@@ -115,7 +115,8 @@ __device__ __forceinline__ void load_tile(double *s, const double *__restrict__ 
 template <bool A_KC, bool B_KC, bool ALIGN16>
 __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double gsm[];
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // tiles whose k-range ends at their last row (triangular A) are heaviest at the bottom: schedule those first
+    const int m0 = (p.k_to_m ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * BM, n0 = blockIdx.y * BN;
     if (p.lower && n0 >= m0 + BM) return;
     const int z = blockIdx.z;
     const int M = (z == p.nbatch - 1) ? p.M_last : p.M;
