@@ -66,6 +66,9 @@ SIGNATURES = {
     "frk_csr_row_normalise": (c_int, [vp, c_i64, vp, vp]),
     "frk_grid_lookup": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, vp]),
     "frk_grid_lookup_range": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, c_int, c_int, c_int, vp]),
+    "frk_polygons_create": (c_int, [vp, c_int, vp, vp, vp, C.POINTER(vp)]),
+    "frk_polygons_destroy": (c_int, [vp]),
+    "frk_polygon_lookup": (c_int, [vp, vp, c_i64, vp, c_i64, c_int, c_int, vp]),
     "frk_bin_mean": (c_int, [vp, c_i64, vp, c_i64, c_int, vp, vp, vp, vp, p_i64]),
     "frk_grid_centroids": (c_int, [vp, c_i64, c_i64, c_int, vp, vp, vp]),
     "frk_csr_gather_count": (c_int, [vp, c_i64, vp, vp, vp, p_i64]),

@@ -188,3 +188,142 @@ extern "C" int frk_grid_centroids(frk_ctx *ctx, int64_t lo, int64_t hi, int nx, 
     FRK_LAUNCH(ctx, grid_centroids_kernel, grid, 256, 0, lo, n, nx, d_xgrid, d_ygrid, d_out);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// map_data_to_BAUs for polygon BAUs (ISEA3H hexagons): over(SpatialPoints, SpatialPolygons), R/geometryfns.R:1266,1680.
+// sp is not vendored; its point.in.polygon (pip.c InPoly) is O'Rourke's crossing test, restated: shift the ring so that the
+// point is the origin, count edges crossing the positive / negative x axis with x = (x_i y_{i-1} - x_{i-1} y_i) / (y_{i-1} - y_i).
+// Interior, edge and vertex all count as "in"; the first polygon in index order wins.  A uniform cell grid over the polygons'
+// bounding boxes (built on the host at frk_polygons_create) gives each point its ascending candidate list.
+// ---------------------------------------------------------------------------------
+struct frk_polygons {
+    frk_ctx *ctx = nullptr;
+    int npoly = 0;
+    double x0 = 0, y0 = 0, hx = 1, hy = 1;
+    int nx = 1, ny = 1;
+    int *ptr = nullptr, *cell_start = nullptr, *cand = nullptr;
+    double *vx = nullptr, *vy = nullptr, *bbox = nullptr;     // bbox: xmin, xmax, ymin, ymax per polygon
+    std::vector<void *> allocs;
+};
+
+__device__ __forceinline__ int in_poly_dev(double px, double py, const double *__restrict__ vx, const double *__restrict__ vy, int n) {
+    int rcross = 0, lcross = 0;
+    double x1 = __dsub_rn(__ldg(vx + n - 1), px), y1 = __dsub_rn(__ldg(vy + n - 1), py);     // vertex i-1
+    for (int i = 0; i < n; i++) {
+        const double x = __dsub_rn(__ldg(vx + i), px), y = __dsub_rn(__ldg(vy + i), py);
+        if (x == 0.0 && y == 0.0) return 3;
+        const bool rstrad = (y > 0) != (y1 > 0), lstrad = (y < 0) != (y1 < 0);
+        if (rstrad || lstrad) {
+            const double xc = __ddiv_rn(__dsub_rn(__dmul_rn(x, y1), __dmul_rn(x1, y)), __dsub_rn(y1, y));
+            if (rstrad && xc > 0) rcross++;
+            if (lstrad && xc < 0) lcross++;
+        }
+        x1 = x; y1 = y;
+    }
+    if ((rcross & 1) != (lcross & 1)) return 2;
+    return (rcross & 1) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) polygon_lookup_kernel(int64_t n, const double *__restrict__ xy, int64_t ld, double x0, double y0,
+                                                             double hx, double hy, int nx, int ny, const int *__restrict__ cell_start,
+                                                             const int *__restrict__ cand, const int *__restrict__ ptr,
+                                                             const double *__restrict__ vx, const double *__restrict__ vy,
+                                                             const double *__restrict__ bbox, int lo, int hi, int *__restrict__ bau) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double px = xy[i], py = xy[i + ld];
+        int out = -1;
+        double fx = floor((px - x0) / hx), fy = floor((py - y0) / hy);
+        if (fx == (double)nx && px == x0 + hx * nx) fx = nx - 1;       // closed upper edges of the covered rectangle
+        if (fy == (double)ny && py == y0 + hy * ny) fy = ny - 1;
+        if (fx >= 0 && fx < nx && fy >= 0 && fy < ny) {                // NaN fails every test -> NA
+            const int64_t c = (int64_t)fy * nx + (int64_t)fx;
+            for (int k = cell_start[c]; k < cell_start[c + 1]; k++) {
+                const int pid = __ldg(cand + k);
+                const double *bb = bbox + 4 * (size_t)pid;
+                if (px < __ldg(bb) || px > __ldg(bb + 1) || py < __ldg(bb + 2) || py > __ldg(bb + 3)) continue;
+                const int b = ptr[pid];
+                if (in_poly_dev(px, py, vx + b, vy + b, ptr[pid + 1] - b) != 0) { out = pid; break; }
+            }
+        }
+        if (out >= 0) out = (out >= lo && out < hi) ? out - lo : -1;
+        bau[i] = out;
+    }
+}
+
+extern "C" int frk_polygons_destroy(frk_polygons *P) {
+    if (!P) return 0;
+    cudaSetDevice(P->ctx->device);
+    cudaStreamSynchronize(P->ctx->stream);
+    for (void *p : P->allocs) cudaFree(p);
+    delete P;
+    return 0;
+}
+
+extern "C" int frk_polygons_create(frk_ctx *ctx, int npoly, const int *h_ptr, const double *h_vx, const double *h_vy, frk_polygons **out) {
+    FRK_REQUIRE(ctx && out && npoly > 0 && h_ptr && h_vx && h_vy, "frk_polygons_create: bad argument");
+    frk_polygons *P = new frk_polygons();
+    P->ctx = ctx; P->npoly = npoly;
+    const int nv = h_ptr[npoly];
+    std::vector<double> bbox(4 * (size_t)npoly);
+    double X0 = 1e300, X1 = -1e300, Y0 = 1e300, Y1 = -1e300, wsum = 0, hsum = 0;
+    for (int k = 0; k < npoly; k++) {
+        FRK_REQUIRE(h_ptr[k + 1] - h_ptr[k] >= 3, "frk_polygons_create: polygon %d has fewer than 3 vertices", k + 1);
+        double a = 1e300, b = -1e300, c = 1e300, d = -1e300;
+        for (int v = h_ptr[k]; v < h_ptr[k + 1]; v++) { a = std::min(a, h_vx[v]); b = std::max(b, h_vx[v]); c = std::min(c, h_vy[v]); d = std::max(d, h_vy[v]); }
+        bbox[4 * k] = a; bbox[4 * k + 1] = b; bbox[4 * k + 2] = c; bbox[4 * k + 3] = d;
+        X0 = std::min(X0, a); X1 = std::max(X1, b); Y0 = std::min(Y0, c); Y1 = std::max(Y1, d);
+        wsum += b - a; hsum += d - c;
+    }
+    // cells about the size of an average polygon, at most 2048 x 2048
+    const double W = std::max(X1 - X0, 1e-300), H = std::max(Y1 - Y0, 1e-300);
+    P->nx = std::max(1, std::min(2048, (int)std::floor(W / std::max(wsum / npoly, W / 2048))));
+    P->ny = std::max(1, std::min(2048, (int)std::floor(H / std::max(hsum / npoly, H / 2048))));
+    P->x0 = X0; P->y0 = Y0; P->hx = W / P->nx; P->hy = H / P->ny;
+    const int64_t ncell = (int64_t)P->nx * P->ny;
+    std::vector<int> start(ncell + 1, 0), cnt(ncell, 0), cand;
+    auto range = [&](double lo, double hi, double o, double h, int n, int &i0, int &i1) {
+        i0 = std::max(0, (int)std::floor((lo - o) / h) - 1);
+        i1 = std::min(n - 1, (int)std::floor((hi - o) / h) + 1);
+    };
+    for (int pass = 0; pass < 2; pass++) {
+        for (int k = 0; k < npoly; k++) {                              // ascending k -> ascending candidate lists
+            int ix0, ix1, iy0, iy1;
+            range(bbox[4 * k], bbox[4 * k + 1], P->x0, P->hx, P->nx, ix0, ix1);
+            range(bbox[4 * k + 2], bbox[4 * k + 3], P->y0, P->hy, P->ny, iy0, iy1);
+            for (int iy = iy0; iy <= iy1; iy++)
+                for (int ix = ix0; ix <= ix1; ix++) {
+                    const int64_t c = (int64_t)iy * P->nx + ix;
+                    if (pass == 0) start[c + 1]++;
+                    else cand[start[c] + cnt[c]++] = k;
+                }
+        }
+        if (pass == 0) {
+            for (int64_t c = 0; c < ncell; c++) start[c + 1] += start[c];
+            cand.resize(start[ncell]);
+        }
+    }
+    auto up = [&](const void *h, size_t bytes, void **d) -> int {
+        FRK_CHECK_CUDA(cudaMalloc(d, std::max<size_t>(bytes, 8)));
+        P->allocs.push_back(*d);
+        FRK_CHECK_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    int rc = 0;
+    rc = rc || up(h_ptr, (size_t)(npoly + 1) * sizeof(int), (void **)&P->ptr) || up(h_vx, (size_t)nv * sizeof(double), (void **)&P->vx) ||
+         up(h_vy, (size_t)nv * sizeof(double), (void **)&P->vy) || up(bbox.data(), bbox.size() * sizeof(double), (void **)&P->bbox) ||
+         up(start.data(), start.size() * sizeof(int), (void **)&P->cell_start) || up(cand.data(), cand.size() * sizeof(int), (void **)&P->cand);
+    if (rc) { frk_polygons_destroy(P); return 1; }
+    *out = P;
+    return 0;
+}
+
+// d_bau[i] = 0-based polygon (BAU) row of point i relative to bau_lo, -1 for NA (outside every polygon, or outside [bau_lo, bau_hi))
+extern "C" int frk_polygon_lookup(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy, int bau_lo, int bau_hi,
+                                  int *d_bau) {
+    FRK_REQUIRE(ctx && P && d_bau && (n == 0 || d_xy), "frk_polygon_lookup: NULL argument");
+    if (n == 0) return 0;
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, polygon_lookup_kernel, grid, 256, 0, n, d_xy, ld_xy, P->x0, P->y0, P->hx, P->hy, P->nx, P->ny, P->cell_start, P->cand,
+               P->ptr, P->vx, P->vy, P->bbox, bau_lo, bau_hi, d_bau);
+    return 0;
+}

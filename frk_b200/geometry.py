@@ -169,6 +169,36 @@ class PointBAUs:
         return self.fields[k]
 
 
+@dataclass
+class PolygonBAUs(PointBAUs):
+    """SpatialPolygonsDataFrame BAUs (e.g. ISEA3H hexagons from auto_BAUs(sphere(), type = "hex"), R/geometryfns.R:765-800): polygon k
+    is the ring ``vx/vy[ptr[k]:ptr[k+1]]``; ``coords`` are the centroids that SRE() evaluates the basis at (R/SRE.R:412).  The
+    point-in-polygon lookup of map_data_to_BAUs runs on the device (frk_polygon_lookup).  BAU *construction* (DGGRID, dateline
+    splitting with sf) stays outside: the rings are an input."""
+    ptr: np.ndarray = None
+    vx: np.ndarray = None
+    vy: np.ndarray = None
+    _handle: object = field(default=None, repr=False, compare=False)
+
+    def handle(self, dev):
+        if self._handle is None:
+            ptr = np.ascontiguousarray(self.ptr, dtype=np.int32)
+            vx = np.ascontiguousarray(self.vx, dtype=np.float64)
+            vy = np.ascontiguousarray(self.vy, dtype=np.float64)
+            h = vp()
+            call("frk_polygons_create", dev.ctx, len(ptr) - 1, vp(ptr.ctypes.data), vp(vx.ctypes.data), vp(vy.ctypes.data), C.byref(h))
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                from ._lib import lib
+                lib.frk_polygons_destroy(self._handle)
+        except Exception:
+            pass
+
+
 def _seq_by(a: float, b: float, by: float) -> np.ndarray:
     n = int(math.floor((b - a) / by + 1e-10))        # seq.default(from, to, by)
     return a + np.arange(n + 1, dtype=np.float64) * by
@@ -227,6 +257,10 @@ def map_data_to_BAUs(data: SpatialPointsDataFrame, BAUs, columns, dev: Optional[
         # BAUs are in expand.grid order, so sp's top-down cell index maps to the BAU row by formula
         call("frk_grid_lookup_range", dev.ctx, n, dev.ptr(d_xy), n, vp(off.ctypes.data), vp(cs.ctypes.data),
              vp(dm.ctypes.data), vp(None), 1, int(lo), int(hi), dev.ptr(d_bau))
+    elif isinstance(BAUs, PolygonBAUs):
+        d_xy = dev.upload(data.coords[:, :2])
+        d_bau = dev.empty(max(n, 1), "i4")
+        call("frk_polygon_lookup", dev.ctx, BAUs.handle(dev), n, dev.ptr(d_xy), n, int(lo), int(hi), dev.ptr(d_bau))
     else:
         if "bau" not in data.data:
             raise FRKError("point-in-polygon lookup for non-grid BAUs is not on the device path; "

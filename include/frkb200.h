@@ -33,6 +33,7 @@ extern "C" {
 
 typedef struct frk_ctx frk_ctx;       /* device + stream + scratch workspace        */
 typedef struct frk_basis frk_basis;   /* device-resident basis + cell lists          */
+typedef struct frk_polygons frk_polygons;       /* polygon BAUs (rings) + candidate cell lists  */
 typedef struct frk_rowbuckets frk_rowbuckets;   /* row buckets + ELL tiles of one CSR basis matrix */
 typedef struct frk_model frk_model;   /* device-resident SRE object (S, Z, X, Ve, Vfs + the r-sized slots) */
 
@@ -126,6 +127,15 @@ int frk_grid_lookup_range(frk_ctx *ctx, int64_t n, const double *d_xy, int64_t l
                           const double *h_offset, const double *h_cellsize, const int *h_dims,
                           const int *d_cell2bau, int expand_grid_order, int bau_lo, int bau_hi,
                           int *d_bau);
+/* map_data_to_BAUs for polygon BAUs (ISEA3H hexagons): over(SpatialPoints, SpatialPolygons), R/geometryfns.R:1266,1680.
+ * Polygon k is the ring h_vx/h_vy[h_ptr[k] .. h_ptr[k+1]) (no holes).  A point belongs to the first polygon (in index order)
+ * whose interior, edge or vertex contains it (sp's point.in.polygon != 0; O'Rourke's crossing test); -1 = NA.
+ * Rows outside [bau_lo, bau_hi) become NA and the rest are returned relative to bau_lo (row-partitioned runs).          */
+int frk_polygons_create(frk_ctx *ctx, int npoly, const int *h_ptr, const double *h_vx, const double *h_vy,
+                        frk_polygons **out);
+int frk_polygons_destroy(frk_polygons *P);
+int frk_polygon_lookup(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy,
+                       int bau_lo, int bau_hi, int *d_bau);
 /* group_by(BAU) %>% summarise_all(mean): R/geometryfns.R:1286-1302.  d_vals: n x ncols
  * column-major (ld n).  Outputs (capacity n rows): d_obs_bau[m] ascending BAU rows,
  * d_means m x ncols column-major with leading dimension n, d_counts[m].  Returns m.

@@ -535,6 +535,55 @@ def points_to_BAUs(xy: np.ndarray, baus: GridBAUs, cell2bau: Optional[np.ndarray
     return out.astype(np.int32)
 
 
+def in_poly(px: float, py: float, vx: np.ndarray, vy: np.ndarray) -> int:
+    """sp::point.in.polygon for one point and one ring: 0 outside, 1 inside, 2 on an edge, 3 on a vertex.
+
+    sp is not vendored in the reference (unpinned CRAN dependency); its pip.c ``InPoly`` is O'Rourke's crossing test
+    ("Computational Geometry in C", 2nd ed., code 7.13), restated here: shift the ring so that the point is the origin,
+    count the edges that cross the positive / negative x axis, using x = (x_i y_{i-1} - x_{i-1} y_i) / (y_{i-1} - y_i).
+    Every operation is a single IEEE operation, in this order (the CUDA kernel uses the same order without FMA)."""
+    n = len(vx)
+    x = vx - px
+    y = vy - py
+    rcross = lcross = 0
+    for i in range(n):
+        if x[i] == 0.0 and y[i] == 0.0:
+            return 3
+        i1 = (i + n - 1) % n
+        rstrad = (y[i] > 0) != (y[i1] > 0)
+        lstrad = (y[i] < 0) != (y[i1] < 0)
+        if rstrad or lstrad:
+            xc = (x[i] * y[i1] - x[i1] * y[i]) / (y[i1] - y[i])
+            if rstrad and xc > 0:
+                rcross += 1
+            if lstrad and xc < 0:
+                lcross += 1
+    if (rcross % 2) != (lcross % 2):
+        return 2
+    return 1 if (rcross % 2) == 1 else 0
+
+
+def points_to_polygon_BAUs(xy: np.ndarray, ptr: np.ndarray, vx: np.ndarray, vy: np.ndarray) -> np.ndarray:
+    """over(SpatialPoints, SpatialPolygons) as map_data_to_BAUs uses it (R/geometryfns.R:1266,1680): the index of the polygon that
+    contains the point (interior, edge or vertex all count: point.in.polygon != 0), -1 (NA) if none.  A point on a shared edge
+    belongs to the FIRST polygon in index order here -- sp's tie rule is flagged "to verify against real sp" (SURVEY.md s8(c));
+    polygons are single rings without holes (ISEA3H cells).  Bounding boxes are a pre-filter only."""
+    xy = np.asarray(xy, dtype=np.float64)
+    npoly = len(ptr) - 1
+    xmin = np.array([vx[ptr[k]:ptr[k + 1]].min() for k in range(npoly)]); xmax = np.array([vx[ptr[k]:ptr[k + 1]].max() for k in range(npoly)])
+    ymin = np.array([vy[ptr[k]:ptr[k + 1]].min() for k in range(npoly)]); ymax = np.array([vy[ptr[k]:ptr[k + 1]].max() for k in range(npoly)])
+    out = np.full(len(xy), -1, dtype=np.int32)
+    for i, (px, py) in enumerate(xy):
+        if not (np.isfinite(px) and np.isfinite(py)):
+            continue
+        cand = np.nonzero((px >= xmin) & (px <= xmax) & (py >= ymin) & (py <= ymax))[0]
+        for k in cand:
+            if in_poly(px, py, vx[ptr[k]:ptr[k + 1]], vy[ptr[k]:ptr[k + 1]]) != 0:
+                out[i] = k
+                break
+    return out
+
+
 def bin_mean(bau: np.ndarray, cols: np.ndarray):
     """map_data_to_BAUs: drop NA, group by BAU, mean of every numeric column
     (R/geometryfns.R:1277-1302).  Rows are returned in ascending BAU index (the reference

@@ -467,3 +467,39 @@ def test_degenerate_inputs(dev):
     np.testing.assert_allclose(q, np.einsum("ij,jk,ik->i", d, Mm, d), rtol=1e-12)
     np.testing.assert_allclose(t, d @ mu, rtol=1e-12)
     assert q[0] == 0.0 and t[0] == 0.0
+
+
+def test_polygon_bau_lookup_and_fit_on_hexagons(dev):
+    """map_data_to_BAUs for polygon BAUs: AIRS day-1 soundings -> ISEA3H resolution-4 hexagons (the reference's
+    own cells, tests/golden/isea3h_res4_polygons.npz) on the device vs. the restated sp::over (bit-exact indices, incl. points on
+    vertices / edges / outside), then SRE -> EM -> predict on those BAUs."""
+    import frk_b200 as F
+    g = np.load(os.path.join(GOLD, "isea3h_res4_polygons.npz"))
+    a = np.load(os.path.join(GOLD, "airs_day1.npz"))
+    ll = np.column_stack([a["lon"], a["lat"]])[::3]
+    # special points: a vertex, an edge midpoint, a centroid, far outside, NaN
+    p0 = g["ptr"][100]
+    extra = np.array([[g["vx"][p0], g["vy"][p0]], [0.5 * (g["vx"][p0] + g["vx"][p0 + 1]), 0.5 * (g["vy"][p0] + g["vy"][p0 + 1])],
+                      [g["cx"][5], g["cy"][5]], [500.0, 0.0], [np.nan, 10.0]])
+    pts = np.vstack([extra, ll])
+    ref = O.points_to_polygon_BAUs(pts, g["ptr"], g["vx"], g["vy"])
+    cen = np.column_stack([g["cx"], g["cy"]])
+    baus = F.PolygonBAUs(cen.copy(), ptr=g["ptr"], vx=g["vx"], vy=g["vy"])
+    baus["fs"] = 1.0
+    z = np.concatenate([np.full(5, 375.0), a["co2avgret"][::3]]); sd = np.concatenate([np.ones(5), a["co2std"][::3]])
+    data = F.SpatialPointsDataFrame(pts, {"co2avgret": z, "std": sd})
+    out = F.map_data_to_BAUs(data, baus, ["co2avgret", "std"], dev)
+    got = dev.download(out["bau"], len(pts))
+    assert np.array_equal(got, ref)
+    assert ref[2] == 5 and ref[3] == -1 and ref[4] == -1 and ref[0] >= 0 and ref[1] >= 0
+    # full fit on the hexagon BAUs
+    isea = _isea3h()
+    ob = O.auto_basis(O.sphere(), ll, nres=2, isea3h=isea, isea3h_lo=2)
+    uo, means, _ = O.bin_mean(ref, np.column_stack([z, sd]))
+    Mo = O.SRE(ob, cen, np.ones(len(cen)), uo, means[:, 0], means[:, 1], K_type="block-exponential")
+    Mg = F.SRE("co2avgret ~ 1", data, _mk_basis(F, ob), baus, est_error=False, K_type="block-exponential")
+    assert np.array_equal(dev.download(Mg.obs_bau, Mg.m), uo)
+    O.SRE_fit(Mo, n_EM=3, tol=0.0)
+    F.SRE_fit(Mg, n_EM=3, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(F.predict(Mg)["var"], O.predict(Mo)[1], rtol=1e-6)

@@ -173,3 +173,23 @@ def test_bin_mean_groups_and_means():
     u, mth, c = O.bin_mean(bau, cols)
     assert u.tolist() == [1, 3, 7] and c.tolist() == [2, 3, 1]
     np.testing.assert_allclose(mth, [[(2 + 8) / 2, (3 + 9) / 2], [(0 + 4 + 12) / 3, (1 + 5 + 13) / 3], [10, 11]])
+
+
+def test_point_in_polygon_classification_and_hexagon_tiling():
+    """point.in.polygon semantics (0 outside, 1 inside, 2 edge, 3 vertex) on a square, and test_BAUs.R:121-139's property on the
+    reference's own ISEA3H cells: every point (away from the dateline cells dropped from the fixture) falls in exactly one hexagon."""
+    vx = np.array([0.0, 1.0, 1.0, 0.0, 0.0]); vy = np.array([0.0, 0.0, 1.0, 1.0, 0.0])
+    assert O.in_poly(0.5, 0.5, vx, vy) == 1 and O.in_poly(1.5, 0.5, vx, vy) == 0
+    assert O.in_poly(1.0, 0.5, vx, vy) == 2 and O.in_poly(1.0, 1.0, vx, vy) == 3 and O.in_poly(0.5, 0.0, vx, vy) == 2
+    g = np.load(os.path.join(GOLD, "isea3h_res4_polygons.npz"))
+    rng = np.random.default_rng(0)
+    pts = np.column_stack([rng.uniform(-150, 150, 400), np.degrees(np.arcsin(rng.uniform(-0.9, 0.9, 400)))])[:120]
+    idx = O.points_to_polygon_BAUs(pts, g["ptr"], g["vx"], g["vy"])
+    assert (idx >= 0).all()
+    for i in range(0, 120, 17):          # exactly one polygon contains the point
+        hits = [k for k in range(len(g["ptr"]) - 1)
+                if O.in_poly(pts[i, 0], pts[i, 1], g["vx"][g["ptr"][k]:g["ptr"][k + 1]], g["vy"][g["ptr"][k]:g["ptr"][k + 1]]) != 0]
+        assert hits == [idx[i]]
+    # the cell's own centroid is inside it
+    cidx = O.points_to_polygon_BAUs(np.column_stack([g["cx"], g["cy"]])[::13], g["ptr"], g["vx"], g["vy"])
+    assert np.array_equal(cidx, np.arange(len(g["cx"]))[::13])

@@ -1,6 +1,7 @@
 """Generates the committed fixtures under tests/golden/ (run in the build container, where /root/reference exists).
 
   isea3h_centroids.npz  ISEA3H centroids, resolutions 0..5, from the reference's data/isea3h.rda (R/datadoc.R:56-68)
+  isea3h_res4_polygons.npz  the 780 resolution-4 cells that do not straddle the dateline, as polygon rings (hexagon BAUs)
   airs_day1.npz         AIRS_05_2003 day 1: lon, lat, co2avgret, co2std   (data/AIRS_05_2003.rda, R/datadoc.R:5-20)
   noaa_jul1993.npz      NOAA_df_1990, Tmax, July 1993: lon, lat, day, z    (data/NOAA_df_1990.rda; vignettes/FRK_intro.Rnw:690-700)
   c1_oracle.json        oracle outputs on BASELINE config 1 (log-likelihood traces etc.) -- pins the oracle against drift.
@@ -24,6 +25,21 @@ d = data_frame(read_rda(f"{REF}/isea3h.rda"))
 keep = (d["centroid"] == 1) & (d["res"] <= 5)
 np.savez_compressed(f"{OUT}/isea3h_centroids.npz", lon=d["lon"][keep], lat=d["lat"][keep], res=d["res"][keep].astype(np.int32))
 print("isea3h centroids per res:", np.bincount(d["res"][d["centroid"] == 1]))
+
+# ISEA3H resolution-4 cells as polygon rings (hexagon BAUs; auto_BAUs(sphere, type = "hex"), R/geometryfns.R:765-800), without the
+# dateline-straddling cells that the reference splits with sf (R/geometryfns.R:1816-1935, out of scope)
+m4 = d["res"] == 4
+ids = d["id"][m4].astype(int); lon4 = d["lon"][m4]; lat4 = d["lat"][m4]; cen4 = d["centroid"][m4]
+ptr, vx, vy, cx, cy, kept_ids = [0], [], [], [], [], []
+for k_ in np.unique(ids):
+    sel = (ids == k_) & (cen4 == 0)
+    if lon4[sel].max() - lon4[sel].min() > 180:
+        continue
+    vx += lon4[sel].tolist(); vy += lat4[sel].tolist(); ptr.append(len(vx)); kept_ids.append(k_)
+    c_ = (ids == k_) & (cen4 == 1); cx.append(lon4[c_][0]); cy.append(lat4[c_][0])
+np.savez_compressed(f"{OUT}/isea3h_res4_polygons.npz", ptr=np.array(ptr, dtype=np.int32), vx=np.array(vx), vy=np.array(vy),
+                    cx=np.array(cx), cy=np.array(cy), id=np.array(kept_ids, dtype=np.int32))
+print("ISEA3H res-4 polygons kept:", len(kept_ids))
 
 a = data_frame(read_rda(f"{REF}/AIRS_05_2003.rda"))
 k = a["day"] == 1
