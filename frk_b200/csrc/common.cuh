@@ -17,6 +17,8 @@ struct frk_prof_stat { int64_t launches = 0; double ms = 0, flops = 0, bytes = 0
 struct frk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // side stream: the bulk of potrf's inner update runs beside the next diagonal factorisation
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sm_count = 148;
     int64_t launches = 0;
     // growable scratch (device) + small pinned host staging

@@ -40,6 +40,9 @@ extern "C" int frk_ctx_create(int device, void *stream, frk_ctx **out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
     }
+    FRK_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     FRK_CHECK_CUDA(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
     FRK_CHECK_CUDA(cudaMalloc((void **)&c->d_small, 4096 * sizeof(double)));
     *out = c;
@@ -53,6 +56,9 @@ extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     frk_prof_harvest(ctx);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_small) cudaFree(ctx->d_small);

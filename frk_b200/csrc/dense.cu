@@ -36,6 +36,7 @@ struct GemmArgs {
     const double *B; int ldb;
     double *C; int ldc;
     int lower;                       // only tiles touching the lower triangle; elements above the diagonal are not stored
+    int lower_off;                   // the diagonal sits lower_off columns to the right of C's origin: keep col <= row + lower_off
     int k_from_m, k_from_n, k_to_m;  // triangular operands: start k at the tile's first row / column, stop at its last row
     long long sA, sB, sC;            // batch strides (elements) for blockIdx.z
     int nbatch, M_last, K_last;      // the last batch entry may be ragged: its M and K
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double gsm[];
     // tiles whose k-range ends at their last row (triangular A) are heaviest at the bottom: schedule those first
     const int m0 = (p.k_to_m ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * BM, n0 = blockIdx.y * BN;
-    if (p.lower && n0 >= m0 + BM) return;
+    if (p.lower && n0 >= m0 + BM + p.lower_off) return;
     const int z = blockIdx.z;
     const int M = (z == p.nbatch - 1) ? p.M_last : p.M;
     const int K = (z == p.nbatch - 1) ? p.K_last : p.K;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
             for (int e = 0; e < 2; e++) {
                 const int colc = n0 + wn * 32 + j * 8 + tg * 2 + e;
                 if (colc >= p.N) continue;
-                if (p.lower && colc > row) continue;
+                if (p.lower && colc > row + p.lower_off) continue;
                 double *c = Cm + row + (size_t)colc * p.ldc;
                 double v = p.alpha * acc[i][j][e];
                 if (p.beta != 0.0) v += p.beta * (*c);
@@ -275,8 +276,14 @@ constexpr int SPLIT = 4, NBQ = NB / SPLIT, BLK_T = NB * SPLIT;
 // shared-memory round trip on the per-column critical path (pivot -> rsqrt -> scale -> update).  The rows below it are
 // solved one thread per row, and the rest of the block is updated by all 256 threads.
 constexpr int PB = 16;
-__global__ void __launch_bounds__(BLK_T) potf2_kernel(double *__restrict__ A, int lda, int kb, int col_offset, double *__restrict__ status) {
-    __shared__ double a[NB][NB + 1];
+constexpr size_t POTF2_SMEM = 2 * NB * (NB + 1) * sizeof(double);
+// Optional pre-update (look-ahead): before factoring, a -= Ptop Ptop' with Ptop the kb x kprev block of the panel just solved
+// (the rows that face this diagonal block), so that the bulk of the panel's update can run beside this kernel.
+__global__ void __launch_bounds__(BLK_T) potf2_kernel(double *__restrict__ A, int lda, int kb, int col_offset, double *__restrict__ status,
+                                                      const double *__restrict__ Ptop, int ldp, int kprev) {
+    extern __shared__ __align__(16) double potf2_smem[];
+    double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potf2_smem);
+    double (*pt)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potf2_smem + NB * (NB + 1));     // pt[c][i] = Ptop[i][c]
     __shared__ double ld[PB][PB + 1];      // factor of the current 16 x 16 diagonal sub-block
     __shared__ double rdg[PB];             // reciprocals of its diagonal
     __shared__ int sbad;
@@ -296,6 +303,51 @@ __global__ void __launch_bounds__(BLK_T) potf2_kernel(double *__restrict__ A, in
     }
     if (tid == 0) sbad = 0;
     __syncthreads();
+    if (Ptop) {                                                    // a[i][k] -= sum_c Ptop[i][c] Ptop[k][c], k <= i
+        // stage Ptop (kb x kprev, kprev <= 64) with all loads in flight, then 16 x 16 threads, 4 x 4 blocks (blocks above the diagonal skipped)
+        {
+            double v[NB * NB / BLK_T];
+#pragma unroll
+            for (int q = 0; q < NB * NB / BLK_T; q++) {
+                const int idx = tid + q * BLK_T, i = idx % NB, c = idx / NB;
+                v[q] = (i < kb && c < kprev) ? Ptop[i + (size_t)c * ldp] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < NB * NB / BLK_T; q++) {
+                const int idx = tid + q * BLK_T, i = idx % NB, c = idx / NB;
+                pt[c][i] = v[q];
+            }
+        }
+        __syncthreads();
+        const int ty = tid >> 4, tx = tid & 15;
+        if (tx <= ty) {
+            double acc[4][4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) acc[ii][kk] = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < kprev; c++) {
+                double xi[4], xk[4];
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++) xi[ii] = pt[c][4 * ty + ii];
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) xk[kk] = pt[c][4 * tx + kk];
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) acc[ii][kk] += xi[ii] * xk[kk];
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const int i = 4 * ty + ii, k = 4 * tx + kk;
+                    if (k <= i) a[i][k] -= acc[ii][kk];
+                }
+        }
+        __syncthreads();
+    }
     double lg = 0.0;
     for (int J = 0; J < NB; J += PB) {
         // (a) 16 x 16 diagonal sub-block: warp 0, lane = row, registers + shuffles
@@ -493,6 +545,7 @@ static int gemm_set_attrs() {
     FRK_GEMM_ATTR(false, false, true); FRK_GEMM_ATTR(false, false, false); FRK_GEMM_ATTR(false, true, true); FRK_GEMM_ATTR(false, true, false);
     FRK_GEMM_ATTR(true, false, true); FRK_GEMM_ATTR(true, false, false); FRK_GEMM_ATTR(true, true, true); FRK_GEMM_ATTR(true, true, false);
 #undef FRK_GEMM_ATTR
+    FRK_CHECK_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
     done = true;
     return 0;
 }
@@ -532,22 +585,39 @@ static int run_graphed(frk_ctx *ctx, const std::array<uintptr_t, 5> &key, F enqu
 static int potrf_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
     FRK_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(double), ctx->stream));
     const size_t ld = (size_t)r;
+    cudaStream_t main = ctx->stream, side = ctx->stream2;
+    const bool fork = main != nullptr && side != nullptr;             // (the legacy default stream cannot fork)
     for (int J = 0; J < r; J += NBO) {
         const int Jend = std::min(r, J + NBO);
+        FRK_LAUNCH(ctx, potf2_kernel, 1, BLK_T, POTF2_SMEM, d_A + J + J * ld, r, std::min(NB, r - J), J, status, (const double *)nullptr, 0, 0);
         for (int o = J; o < Jend; o += NB) {
             const int kb = std::min(NB, r - o), below = r - o - kb;
-            double *Ajj = d_A + o + o * ld;
-            FRK_LAUNCH(ctx, potf2_kernel, 1, BLK_T, 0, Ajj, r, kb, o, status);
             if (below <= 0) continue;
+            double *Ajj = d_A + o + o * ld;
             double *P = d_A + (o + kb) + o * ld;                       // below x kb panel
             FRK_WORK(ctx, (double)below * kb * kb, 0);
             FRK_LAUNCH(ctx, trsm_rows_kernel<false>, (unsigned)cdiv(below, NB), BLK_T, 0, Ajj, r, P, r, below, kb, r);
             const int ncols = Jend - (o + kb);                         // remaining columns of the outer panel
-            if (ncols > 0) {                                           // A[o+kb.., o+kb..Jend) -= P P[0:ncols,:]'
-                GemmArgs g = gemm_args(below, ncols, kb, -1.0, P, r, P, r, 1.0, d_A + (o + kb) + (o + kb) * ld, r);
-                g.lower = 1;
-                if (int rc = launch_gemm(ctx, g, false, false, 2.0 * below * ncols * kb - (double)ncols * ncols * kb, "dgemm_kernel[potrf inner rank-64]")) return rc;
+            if (ncols <= 0) continue;
+            // Look-ahead inside the panel.  The next diagonal block (o+kb) takes its rank-kb update inside its own factorisation
+            // kernel (from the kb2 rows of P that face it); everything else of the update, rows >= o+kb+kb2, runs beside it.
+            const int kb2 = std::min(NB, r - (o + kb)), rest = below - kb2;
+            if (rest > 0) {
+                if (fork) {
+                    FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, main));
+                    FRK_CHECK_CUDA(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+                    ctx->stream = side;
+                }
+                // C[rows >= o+kb+kb2, cols o+kb .. Jend) -= P[rows >= o+kb+kb2, :] P[0:ncols, :]'; the diagonal is kb2 columns to the right
+                GemmArgs g = gemm_args(rest, ncols, kb, -1.0, P + kb2, r, P, r, 1.0, d_A + (o + kb + kb2) + (o + kb) * ld, r);
+                g.lower = 1; g.lower_off = kb2;
+                const int rc = launch_gemm(ctx, g, false, false, 2.0 * rest * ncols * kb, "dgemm_kernel[potrf inner rank-64]");
+                ctx->stream = main;
+                if (rc) return rc;
+                if (fork) FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_join, side));
             }
+            FRK_LAUNCH(ctx, potf2_kernel, 1, BLK_T, POTF2_SMEM, d_A + (o + kb) + (o + kb) * ld, r, kb2, o + kb, status, (const double *)P, r, kb);
+            if (rest > 0 && fork) FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_join, 0));
         }
         const int below = r - Jend, kw = Jend - J;
         if (below > 0) {                                               // trailing lower SYRK with the whole outer panel
@@ -563,6 +633,7 @@ static int potrf_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
 extern "C" int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet) {
     FRK_REQUIRE(ctx && d_A && r > 0, "frk_potrf: bad argument");
     double *status = ctx->d_small + 4096 - 8;
+    if (int rc = gemm_set_attrs()) return rc;
     if (int rc = run_graphed(ctx, {1, (uintptr_t)r, (uintptr_t)d_A, 0, 0}, [&]() { return potrf_enqueue(ctx, r, d_A, status); })) return rc;
     FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned, status, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));

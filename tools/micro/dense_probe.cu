@@ -10,13 +10,14 @@ int main() {
     for (size_t i = 0; i < (size_t)r * r; i++) h[i] = 0.001;
     for (int i = 0; i < r; i++) h[i + (size_t)i * r] = 4.0;
     cudaMemcpy(A, h, (size_t)r * r * 8, cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms; const int N = 200;
     auto report = [&](const char *nm) { cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
         printf("%-40s %.2f us per launch (%s)\n", nm, 1e3 * ms / N, cudaGetErrorString(cudaGetLastError())); };
     for (int w = 0; w < 2; w++) {
         cudaEventRecord(e0); for (int i = 0; i < N; i++) empty_k<<<1, 32>>>(); report("empty kernel");
-        cudaEventRecord(e0); for (int i = 0; i < N; i++) potf2_kernel<<<1, BLK_T>>>(A + 64 + 64 * (size_t)r, r, 64, 0, st); report("potf2 (same block, refactoring L: fine)");
+        cudaEventRecord(e0); for (int i = 0; i < N; i++) potf2_kernel<<<1, BLK_T, POTF2_SMEM>>>(A + 64 + 64 * (size_t)r, r, 64, 0, st, (const double *)nullptr, 0, 0); report("potf2 (same block, refactoring L: fine)");
         cudaEventRecord(e0); for (int i = 0; i < N; i++) trsm_rows_kernel<false><<<20, BLK_T>>>(A, r, A + 2048, r, 1280, 64, r); report("trsm_rows<false> 20 CTAs");
         cudaEventRecord(e0); for (int i = 0; i < N; i++) trsm_rows_kernel<false><<<50, BLK_T>>>(A, r, A + 64, r, 3200, 64, r); report("trsm_rows<false> 50 CTAs");
     }
