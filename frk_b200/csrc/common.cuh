@@ -18,7 +18,8 @@ struct frk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;      // side stream: the bulk of potrf's inner update runs beside the next diagonal factorisation
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream3 = nullptr;      // second side stream: the rest of the trailing SYRK overlaps the whole next panel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_panel = nullptr, ev_next = nullptr, ev_rest[2] = {nullptr, nullptr};
     int sm_count = 148;
     int64_t launches = 0;
     // growable scratch (device) + small pinned host staging

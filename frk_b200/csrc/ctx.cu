@@ -43,6 +43,11 @@ extern "C" int frk_ctx_create(int device, void *stream, frk_ctx **out) {
     FRK_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    FRK_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
+    FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_next, cudaEventDisableTiming));
+    FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_rest[0], cudaEventDisableTiming));
+    FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_rest[1], cudaEventDisableTiming));
     FRK_CHECK_CUDA(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
     FRK_CHECK_CUDA(cudaMalloc((void **)&c->d_small, 4096 * sizeof(double)));
     *out = c;
@@ -59,6 +64,11 @@ extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream3) { cudaStreamSynchronize(ctx->stream3); cudaStreamDestroy(ctx->stream3); }
+    if (ctx->ev_panel) cudaEventDestroy(ctx->ev_panel);
+    if (ctx->ev_next) cudaEventDestroy(ctx->ev_next);
+    if (ctx->ev_rest[0]) cudaEventDestroy(ctx->ev_rest[0]);
+    if (ctx->ev_rest[1]) cudaEventDestroy(ctx->ev_rest[1]);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_small) cudaFree(ctx->d_small);

@@ -304,40 +304,47 @@ __global__ void __launch_bounds__(BLK_T) potf2_kernel(double *__restrict__ A, in
     if (tid == 0) sbad = 0;
     __syncthreads();
     if (Ptop) {                                                    // a[i][k] -= sum_c Ptop[i][c] Ptop[k][c], k <= i
-        // stage Ptop (kb x kprev, kprev <= 64) with all loads in flight, then 16 x 16 threads, 4 x 4 blocks (blocks above the diagonal skipped)
-        {
-            double v[NB * NB / BLK_T];
+        // Ptop is kb x kprev; staged 64 columns at a time with all loads in flight, then 16 x 16 threads, 4 x 4 blocks
+        // (blocks above the diagonal skipped)
+        const int ty = tid >> 4, tx = tid & 15;
+        double acc[4][4];
 #pragma unroll
-            for (int q = 0; q < NB * NB / BLK_T; q++) {
-                const int idx = tid + q * BLK_T, i = idx % NB, c = idx / NB;
-                v[q] = (i < kb && c < kprev) ? Ptop[i + (size_t)c * ldp] : 0.0;
+        for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) acc[ii][kk] = 0.0;
+        for (int c0 = 0; c0 < kprev; c0 += NB) {
+            const int kc = min(NB, kprev - c0);
+            {
+                double v[NB * NB / BLK_T];
+#pragma unroll
+                for (int q = 0; q < NB * NB / BLK_T; q++) {
+                    const int idx = tid + q * BLK_T, i = idx % NB, c = idx / NB;
+                    v[q] = (i < kb && c < kc) ? Ptop[i + (size_t)(c0 + c) * ldp] : 0.0;
+                }
+                __syncthreads();                                   // previous chunk fully consumed
+#pragma unroll
+                for (int q = 0; q < NB * NB / BLK_T; q++) {
+                    const int idx = tid + q * BLK_T, i = idx % NB, c = idx / NB;
+                    pt[c][i] = v[q];
+                }
             }
+            __syncthreads();
+            if (tx <= ty) {
+#pragma unroll 4
+                for (int c = 0; c < kc; c++) {
+                    double xi[4], xk[4];
 #pragma unroll
-            for (int q = 0; q < NB * NB / BLK_T; q++) {
-                const int idx = tid + q * BLK_T, i = idx % NB, c = idx / NB;
-                pt[c][i] = v[q];
+                    for (int ii = 0; ii < 4; ii++) xi[ii] = pt[c][4 * ty + ii];
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) xk[kk] = pt[c][4 * tx + kk];
+#pragma unroll
+                    for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) acc[ii][kk] += xi[ii] * xk[kk];
+                }
             }
         }
-        __syncthreads();
-        const int ty = tid >> 4, tx = tid & 15;
         if (tx <= ty) {
-            double acc[4][4];
-#pragma unroll
-            for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) acc[ii][kk] = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < kprev; c++) {
-                double xi[4], xk[4];
-#pragma unroll
-                for (int ii = 0; ii < 4; ii++) xi[ii] = pt[c][4 * ty + ii];
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) xk[kk] = pt[c][4 * tx + kk];
-#pragma unroll
-                for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) acc[ii][kk] += xi[ii] * xk[kk];
-            }
 #pragma unroll
             for (int ii = 0; ii < 4; ii++)
 #pragma unroll
@@ -582,14 +589,29 @@ static int run_graphed(frk_ctx *ctx, const std::array<uintptr_t, 5> &key, F enqu
     return 0;
 }
 
+// Launch sequence of the two-level right-looking Cholesky with look-ahead on three streams (one CUDA graph with parallel branches
+// when captured).  Per 256-wide outer panel J:
+//   main : potf2'(first diagonal block; its rank-256 update from panel J-1 happens inside the kernel)
+//          then for each 64-wide inner block: trsm -> potf2'(next diagonal block, rank-64 update inside) ...
+//   side : the rest of each inner rank-64 update, beside the next diagonal factorisation;
+//          NP = update of the next panel's columns with the whole panel J, beside the first diagonal factorisation of panel J+1
+//   side2: the rest of the trailing SYRK (columns beyond the next panel), beside the whole of panel J+1.
 static int potrf_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
     FRK_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(double), ctx->stream));
     const size_t ld = (size_t)r;
-    cudaStream_t main = ctx->stream, side = ctx->stream2;
-    const bool fork = main != nullptr && side != nullptr;             // (the legacy default stream cannot fork)
+    cudaStream_t main = ctx->stream, side = ctx->stream2, side2 = ctx->stream3;
+    const bool fork = main != nullptr && side != nullptr && side2 != nullptr;   // (the legacy default stream cannot fork)
+    // rest(p) = the part of panel p's trailing update beyond the next panel (side2); it records ev_rest[p & 1].  Panel p+2 (its
+    // first potf2' and the NP that feeds it) is the first consumer, so two alternating events keep rest(p) overlapped with panel p+1.
+    int pidx = 0;                              // index of the current outer panel
+    bool have_rest[2] = {false, false};        // ev_rest[i] holds a recorded rest-SYRK
+    const double *Pprev = nullptr;             // panel J-1 rows facing the first diagonal block of panel J (for its pre-update)
+    int kprev = 0;
     for (int J = 0; J < r; J += NBO) {
         const int Jend = std::min(r, J + NBO);
-        FRK_LAUNCH(ctx, potf2_kernel, 1, BLK_T, POTF2_SMEM, d_A + J + J * ld, r, std::min(NB, r - J), J, status, (const double *)nullptr, 0, 0);
+        if (fork && have_rest[pidx & 1]) FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_rest[pidx & 1], 0));   // rest(pidx-2) reached this panel
+        FRK_LAUNCH(ctx, potf2_kernel, 1, BLK_T, POTF2_SMEM, d_A + J + J * ld, r, std::min(NB, r - J), J, status, Pprev, r, kprev);
+        if (J > 0 && fork) FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_next, 0));            // the panel's columns got NP(J-1)
         for (int o = J; o < Jend; o += NB) {
             const int kb = std::min(NB, r - o), below = r - o - kb;
             if (below <= 0) continue;
@@ -619,14 +641,52 @@ static int potrf_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
             FRK_LAUNCH(ctx, potf2_kernel, 1, BLK_T, POTF2_SMEM, d_A + (o + kb) + (o + kb) * ld, r, kb2, o + kb, status, (const double *)P, r, kb);
             if (rest > 0 && fork) FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_join, 0));
         }
+        // trailing update with the whole outer panel (rows >= Jend): first diagonal block of the next panel -> inside its potf2';
+        // the rest of the next panel's columns (NP) -> side; everything beyond the next panel -> side2
         const int below = r - Jend, kw = Jend - J;
-        if (below > 0) {                                               // trailing lower SYRK with the whole outer panel
-            const double *P = d_A + Jend + J * ld;
+        Pprev = nullptr; kprev = 0;
+        if (below <= 0) { pidx++; continue; }
+        const double *P = d_A + Jend + J * ld;
+        if (!fork) {                                                   // sequential: one lower SYRK
             GemmArgs g = gemm_args(below, below, kw, -1.0, P, r, P, r, 1.0, d_A + Jend + Jend * ld, r);
             g.lower = 1;
             if (int rc = launch_gemm(ctx, g, false, false, (double)below * (below + 1.0) * kw, "dgemm_kernel[potrf outer SYRK]")) return rc;
+            pidx++;
+            continue;
         }
+        Pprev = P; kprev = kw;
+        const int kb0 = std::min(NB, below), npan = std::min(NBO, below), beyond = below - npan;
+        FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_panel, main));
+        if (below - kb0 > 0) {                                         // NP: rows >= Jend+kb0, cols [Jend, Jend+npan), diagonal kb0 to the right
+            FRK_CHECK_CUDA(cudaStreamWaitEvent(side, ctx->ev_panel, 0));
+            if (have_rest[(pidx + 1) & 1]) FRK_CHECK_CUDA(cudaStreamWaitEvent(side, ctx->ev_rest[(pidx + 1) & 1], 0));   // rest(pidx-1) reached those columns
+            GemmArgs g = gemm_args(below - kb0, npan, kw, -1.0, P + kb0, r, P, r, 1.0, d_A + (Jend + kb0) + Jend * ld, r);
+            g.lower = 1; g.lower_off = kb0;
+            ctx->stream = side;
+            const int rc = launch_gemm(ctx, g, false, false, 2.0 * (below - kb0) * npan * kw, "dgemm_kernel[potrf next-panel update]");
+            ctx->stream = main;
+            if (rc) return rc;
+        }
+        FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_next, side));          // (recorded even when NP is empty: main always waits on it)
+        if (beyond > 0) {                                              // rest: rows, cols >= Jend+npan
+            FRK_CHECK_CUDA(cudaStreamWaitEvent(side2, ctx->ev_panel, 0));
+            const double *P2 = P + npan;
+            GemmArgs g = gemm_args(beyond, beyond, kw, -1.0, P2, r, P2, r, 1.0, d_A + (Jend + npan) + (Jend + npan) * ld, r);
+            g.lower = 1;
+            ctx->stream = side2;
+            const int rc = launch_gemm(ctx, g, false, false, (double)beyond * (beyond + 1.0) * kw, "dgemm_kernel[potrf outer SYRK]");
+            ctx->stream = main;
+            if (rc) return rc;
+            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_rest[pidx & 1], side2));
+            have_rest[pidx & 1] = true;
+        } else {
+            have_rest[pidx & 1] = false;
+        }
+        pidx++;
     }
+    if (fork)                                                        // join side2 (in-order: the later event covers the earlier)
+        for (int i = 0; i < 2; i++)
+            if (have_rest[i]) FRK_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_rest[i], 0));
     return 0;
 }
 
