@@ -40,10 +40,12 @@ extern "C" int frk_ctx_create(int device, void *stream, frk_ctx **out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
     }
-    FRK_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;                                      // critical-path branch high, bulk trailing update low
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    FRK_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
     FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    FRK_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    FRK_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_lo));
     FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
     FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_next, cudaEventDisableTiming));
     FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_rest[0], cudaEventDisableTiming));

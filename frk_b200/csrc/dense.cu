@@ -113,12 +113,14 @@ __device__ __forceinline__ void load_tile(double *s, const double *__restrict__ 
     }
 }
 
-template <bool A_KC, bool B_KC, bool ALIGN16>
+// BM_ = 128 (default) or 64: the small tile spreads skinny / small products (panel updates) over twice as many SMs
+template <bool A_KC, bool B_KC, bool ALIGN16, int BM_>
 __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
+    constexpr int WM = BM_ / 32, WN = 8 / WM, WTN = BN / WN, NJ = WTN / 8;   // warps along m / n, warp tile width, n-fragments per warp
     extern __shared__ __align__(16) double gsm[];
     // tiles whose k-range ends at their last row (triangular A) are heaviest at the bottom: schedule those first
-    const int m0 = (p.k_to_m ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * BM, n0 = blockIdx.y * BN;
-    if (p.lower && n0 >= m0 + BM + p.lower_off) return;
+    const int m0 = (p.k_to_m ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * BM_, n0 = blockIdx.y * BN;
+    if (p.lower && n0 >= m0 + BM_ + p.lower_off) return;
     const int z = blockIdx.z;
     const int M = (z == p.nbatch - 1) ? p.M_last : p.M;
     const int K = (z == p.nbatch - 1) ? p.K_last : p.K;
@@ -127,21 +129,21 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
     const double *__restrict__ B = p.B + (size_t)z * p.sB;
     double *__restrict__ Cm = p.C + (size_t)z * p.sC;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int wm = wid & 3, wn = wid >> 2;
+    const int wm = wid % WM, wn = wid / WM;
     const int g = lane >> 2, tg = lane & 3;
 
     int kbeg = 0;
     if (p.k_from_m) kbeg = max(kbeg, m0);
     if (p.k_from_n) kbeg = max(kbeg, n0);
     kbeg = (kbeg / BK) * BK;
-    const int kend = p.k_to_m ? min(K, m0 + BM) : K;
+    const int kend = p.k_to_m ? min(K, m0 + BM_) : K;
     const int nk = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
 
-    double acc[4][4][2];
+    double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto stageA = [&](int s) { return gsm + (size_t)s * STAGE_DOUBLES; };
     auto stageB = [&](int s) { return gsm + (size_t)s * STAGE_DOUBLES + A_STAGE; };
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
         if (s < nk) {
-            load_tile<BM, LDSA, A_KC, ALIGN16>(stageA(s), A, p.lda, m0, M, kbeg + s * BK, kend);
+            load_tile<BM_, LDSA, A_KC, ALIGN16>(stageA(s), A, p.lda, m0, M, kbeg + s * BK, kend);
             load_tile<BN, LDSB, B_KC, ALIGN16>(stageB(s), B, p.ldb, n0, p.N, kbeg + s * BK, kend);
         }
         cp_async_commit();
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
         {
             int nxt = kt + STAGES - 1;
             if (nxt < nk) {
-                load_tile<BM, LDSA, A_KC, ALIGN16>(stageA(nxt % STAGES), A, p.lda, m0, M, kbeg + nxt * BK, kend);
+                load_tile<BM_, LDSA, A_KC, ALIGN16>(stageA(nxt % STAGES), A, p.lda, m0, M, kbeg + nxt * BK, kend);
                 load_tile<BN, LDSB, B_KC, ALIGN16>(stageB(nxt % STAGES), B, p.ldb, n0, p.N, kbeg + nxt * BK, kend);
             }
             cp_async_commit();
@@ -169,17 +171,17 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
         const double *sB = stageB(kt % STAGES);
 #pragma unroll
         for (int k4 = 0; k4 < BK / 4; k4++) {
-            double a[4], b[4];
+            double a[4], b[NJ];
 #pragma unroll
             for (int i = 0; i < 4; i++)
                 a[i] = A_KC ? sA[(wm * 32 + i * 8 + g) * LDSK + k4 * 4 + tg] : sA[(k4 * 4 + tg) * LDSA + wm * 32 + i * 8 + g];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                b[j] = B_KC ? sB[(wn * 32 + j * 8 + g) * LDSK + k4 * 4 + tg] : sB[(k4 * 4 + tg) * LDSB + wn * 32 + j * 8 + g];
+            for (int j = 0; j < NJ; j++)
+                b[j] = B_KC ? sB[(wn * WTN + j * 8 + g) * LDSK + k4 * 4 + tg] : sB[(k4 * 4 + tg) * LDSB + wn * WTN + j * 8 + g];
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_async_wait<0>();
@@ -190,10 +192,10 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
         const int row = m0 + wm * 32 + i * 8 + g;
         if (row >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NJ; j++) {
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int colc = n0 + wn * 32 + j * 8 + tg * 2 + e;
+                const int colc = n0 + wn * WTN + j * 8 + tg * 2 + e;
                 if (colc >= p.N) continue;
                 if (p.lower && colc > row + p.lower_off) continue;
                 double *c = Cm + row + (size_t)colc * p.ldc;
@@ -207,23 +209,26 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
 
 template <bool A_KC, bool B_KC>
 static int launch_gemm_t(frk_ctx *ctx, const GemmArgs &a, bool al) {
-    static bool attr = false;
-    if (!attr) {
-        FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_kernel<A_KC, B_KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_kernel<A_KC, B_KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        attr = true;
-    }
-    dim3 grid((unsigned)cdiv(a.M, BM), (unsigned)cdiv(a.N, BN), (unsigned)a.nbatch);
+    // 64-row tiles when 128-row tiles would leave SMs idle (fewer CTAs than SMs): skinny panel updates, small matrices
+    const int64_t ctas128 = cdiv(a.M, 128) * cdiv(a.N, BN) * (int64_t)a.nbatch;
+    const bool small = ctas128 < ctx->sm_count;
+    const int bm = small ? 64 : 128;
+    dim3 grid((unsigned)cdiv(a.M, bm), (unsigned)cdiv(a.N, BN), (unsigned)a.nbatch);
     const double fl = ctx->next_flops;
     const char *tg = ctx->next_tag;
-    if (al) { FRK_LAUNCH(ctx, (dgemm_kernel<A_KC, B_KC, true>), grid, GEMM_T, GEMM_SMEM, a); }
-    else    { FRK_WORK(ctx, fl, 0); FRK_TAG(ctx, tg); FRK_LAUNCH(ctx, (dgemm_kernel<A_KC, B_KC, false>), grid, GEMM_T, GEMM_SMEM, a); }
+    if (al && !small)       { FRK_LAUNCH(ctx, (dgemm_kernel<A_KC, B_KC, true, 128>), grid, GEMM_T, GEMM_SMEM, a); }
+    else if (al && small)   { FRK_LAUNCH(ctx, (dgemm_kernel<A_KC, B_KC, true, 64>), grid, GEMM_T, GEMM_SMEM, a); }
+    else if (!small)        { FRK_WORK(ctx, fl, 0); FRK_TAG(ctx, tg); FRK_LAUNCH(ctx, (dgemm_kernel<A_KC, B_KC, false, 128>), grid, GEMM_T, GEMM_SMEM, a); }
+    else                    { FRK_WORK(ctx, fl, 0); FRK_TAG(ctx, tg); FRK_LAUNCH(ctx, (dgemm_kernel<A_KC, B_KC, false, 64>), grid, GEMM_T, GEMM_SMEM, a); }
     return 0;
 }
+
+static int gemm_set_attrs();
 
 // flops: the ALGORITHMIC count of the operation this launch performs (passed by the caller)
 static int launch_gemm(frk_ctx *ctx, GemmArgs a, bool a_kc, bool b_kc, double flops, const char *tag = "dgemm_kernel") {
     if (a.M <= 0 || a.N <= 0) return 0;
+    if (int rc = gemm_set_attrs()) return rc;
     if (a.nbatch <= 0) { a.nbatch = 1; a.M_last = a.M; a.K_last = a.K; }
     FRK_WORK(ctx, flops, 0);
     FRK_TAG(ctx, tag);
@@ -548,7 +553,8 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(int r, double *__rest
 static int gemm_set_attrs() {
     static bool done = false;
     if (done) return 0;
-#define FRK_GEMM_ATTR(a, b, c) FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_kernel<a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM))
+#define FRK_GEMM_ATTR(a, b, c) FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_kernel<a, b, c, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM)); \
+                               FRK_CHECK_CUDA(cudaFuncSetAttribute(dgemm_kernel<a, b, c, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM))
     FRK_GEMM_ATTR(false, false, true); FRK_GEMM_ATTR(false, false, false); FRK_GEMM_ATTR(false, true, true); FRK_GEMM_ATTR(false, true, false);
     FRK_GEMM_ATTR(true, false, true); FRK_GEMM_ATTR(true, false, false); FRK_GEMM_ATTR(true, true, true); FRK_GEMM_ATTR(true, true, false);
 #undef FRK_GEMM_ATTR

@@ -27,7 +27,7 @@ class Device:
         self.tdev = torch.device("cuda", index)
         # a real (non-default) stream, made current for torch as well: libfrkb200 captures its factorisation launch sequences into
         # CUDA graphs, which the legacy default stream does not allow; torch allocations / NCCL calls stay ordered with the kernels
-        self.stream = torch.cuda.Stream(device=index)
+        self.stream = torch.cuda.Stream(device=index, priority=-1)
         torch.cuda.set_stream(self.stream)
         ctx = vp()
         call("frk_ctx_create", index, vp(self.stream.cuda_stream), C.byref(ctx))

@@ -21,12 +21,12 @@ int main() {
         cudaEventRecord(e0); for (int i = 0; i < N; i++) trsm_rows_kernel<false><<<20, BLK_T>>>(A, r, A + 2048, r, 1280, 64, r); report("trsm_rows<false> 20 CTAs");
         cudaEventRecord(e0); for (int i = 0; i < N; i++) trsm_rows_kernel<false><<<50, BLK_T>>>(A, r, A + 64, r, 3200, 64, r); report("trsm_rows<false> 50 CTAs");
     }
-    cudaFuncSetAttribute(dgemm_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaFuncSetAttribute(dgemm_kernel<false, false, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     for (int K : {64, 256}) for (int gx : {9, 25}) for (int gy : {1, 3, 50}) {
         GemmArgs g = gemm_args(gx * 128, gy * 64, K, -1.0, A, r, A + 64, r, 1.0, A + 1024 * (size_t)r, r);
         if (gy * 64 + 1024 > r || gx * 128 > r) continue;
         dim3 grid(gx, gy, 1);
-        cudaEventRecord(e0); for (int i = 0; i < N; i++) dgemm_kernel<false, false, true><<<grid, GEMM_T, GEMM_SMEM>>>(g);
+        cudaEventRecord(e0); for (int i = 0; i < N; i++) dgemm_kernel<false, false, true, 128><<<grid, GEMM_T, GEMM_SMEM>>>(g);
         char nm[64]; snprintf(nm, 64, "dgemm NT K=%d grid %dx%d", K, gx, gy); report(nm);
     }
     return 0;
