@@ -126,7 +126,7 @@ def run_reference(args):
             "cpu_baseline": {"value": res["iters_per_s"], "unit": "EM iters/s", "cores": res["cores"], "kind": "port",
                              "sample": res["sample"]},
             "e2e": {"value": res["iters_per_s"], "unit": "EM iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -368,9 +368,14 @@ def run_b200(args):
             line["kernels"] = kernels[:12]
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            del m2, slots, pr
+            barrier()
+            dist.destroy_process_group()
+        except Exception as e:      # the result line is already out; never fail the run on teardown
+            print(f"teardown: {e!r}", file=sys.stderr, flush=True)
 
 
 def main():
