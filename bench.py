@@ -126,7 +126,7 @@ def run_reference(args):
             "cpu_baseline": {"value": res["iters_per_s"], "unit": "EM iters/s", "cores": res["cores"], "kind": "port",
                              "sample": res["sample"]},
             "e2e": {"value": res["iters_per_s"], "unit": "EM iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -197,6 +197,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = F.get_device(local)
+    _dbg("device + process group up")
 
     def barrier():
         if world > 1:
@@ -236,6 +237,7 @@ def run_b200(args):
     launches = dev.launches() - l0
     llk_tail = [float(v) for v in mdl.info_fit["llk"][-2:]]
 
+    _dbg("EM timed")
     # ---- (B) device-resident prediction ---------------------------------------------------------------
     for _ in range(2):
         F.predict(mdl, obs_fs=False, to_host=False)
@@ -345,6 +347,7 @@ def run_b200(args):
         if not timed:
             del m2, slots, pr
 
+    _dbg("e2e done")
     # ---- (E) CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,7 +371,8 @@ def run_b200(args):
             line["kernels"] = kernels[:12]
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        _emit(line)
+    _dbg("line printed")
     if world > 1:
         try:
             del m2, slots, pr
@@ -378,7 +382,31 @@ def run_b200(args):
             print(f"teardown: {e!r}", file=sys.stderr, flush=True)
 
 
+def _dbg(msg):
+    if os.environ.get("FRK_BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} pid {os.getpid()} t={time.time():.3f}] {msg}", file=sys.stderr, flush=True)
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Libraries (NCCL's version banner, BLAS warnings) sometimes write to fd 1; the contract is ONE JSON line on stdout.  Keep a
+    private copy of the real stdout for the result line and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _guard_stdout()
+    _dbg("start")
     args = parse()
     if args.impl == "reference":
         run_reference(args)
