@@ -61,6 +61,8 @@ struct frk_model {
     double Dt01 = 0.0;
     std::vector<double> taus, omegas;
     // multi-rank reduction hook
+    int rank = 0, world = 1;
+    bool spec_emulate = false;     // evaluate every speculative candidate on this rank (single-GPU test of the multi-rank logic)
     frk_allreduce_fn allreduce = nullptr;
     void *user = nullptr;
     std::vector<void *> allocs;
@@ -323,6 +325,99 @@ int zeroin(const std::function<int(double, double &)> &f, double lower, double u
 }
 
 // ---------------------------------------------------------------------------------
+// Speculative Nelder-Mead over the ranks of a row-partitioned run.
+// Every f_tau evaluation is a replicated r_i x r_i factorisation, so on W > 1 GPUs the ranks would all compute the same thing.
+// Instead, whenever Nelder-Mead asks for a point that has not been evaluated, the points it may ask for NEXT are predicted by
+// re-running nmmin on the host against the values known so far plus hypothetical outcomes ("lower than everything" / "higher
+// than everything") for the unknown ones; rank k evaluates candidate k, one small all-reduce shares the values, and nmmin continues
+// from the cache.  The iterate path -- hence every result -- is identical to the sequential one; only wall time changes.
+// ---------------------------------------------------------------------------------
+struct SpecNM {
+    frk_model *M;
+    std::function<int(const double *, double &)> eval;      // evaluates on THIS rank (and tracks the rank-local best)
+    int dim, maxit;
+    double reltol;
+    std::vector<double> par0;
+    std::vector<std::vector<double>> pts;
+    std::vector<double> fv;
+    std::vector<int> owner;
+
+    int find(const double *x) const {
+        for (size_t i = 0; i < pts.size(); i++) {
+            bool eq = true;
+            for (int d = 0; d < dim; d++) eq = eq && pts[i][d] == x[d];
+            if (eq) return (int)i;
+        }
+        return -1;
+    }
+
+    // points nmmin may request after `x`, under hypothetical outcomes for the unknown ones (breadth first, at most `want`)
+    void candidates(const double *x, size_t want, std::vector<std::vector<double>> &batch) const {
+        std::vector<std::string> queue = {"L", "H"};
+        for (size_t qi = 0; qi < queue.size() && batch.size() < want && qi < 64; qi++) {
+            const std::string hyp = queue[qi];
+            std::vector<std::vector<double>> hp;
+            std::vector<double> hf;
+            size_t used = 0;
+            std::vector<double> cand;
+            auto sim = [&](const double *y, double &f) -> int {
+                const int i = find(y);
+                if (i >= 0) { f = fv[i]; return 0; }
+                for (size_t j = 0; j < hp.size(); j++) {
+                    bool eq = true;
+                    for (int d = 0; d < dim; d++) eq = eq && hp[j][d] == y[d];
+                    if (eq) { f = hf[j]; return 0; }
+                }
+                if (used < hyp.size()) {
+                    double lo = 0.0, hi = 0.0;
+                    bool any = false;
+                    auto upd = [&](double v) { if (std::isfinite(v)) { lo = any ? std::min(lo, v) : v; hi = any ? std::max(hi, v) : v; any = true; } };
+                    for (double v : fv) upd(v);
+                    for (double v : hf) upd(v);
+                    f = hyp[used] == 'L' ? lo - 1.0 - 1e-3 * std::fabs(lo) : hi + 1.0 + 1e-3 * std::fabs(hi);
+                    used++;
+                    hp.emplace_back(y, y + dim); hf.push_back(f);
+                    return 0;
+                }
+                cand.assign(y, y + dim);
+                return 99;                                  // the next point the real run would ask for under this hypothesis
+            };
+            NMResult tmp;
+            const int rc = nmmin(sim, par0, tmp, maxit, reltol);
+            if (rc == 99) {
+                bool dup = find(cand.data()) >= 0;
+                for (auto &b : batch) { bool eq = true; for (int d = 0; d < dim; d++) eq = eq && b[d] == cand[d]; dup = dup || eq; }
+                if (!dup) batch.push_back(cand);
+                queue.push_back(hyp + "L");
+                queue.push_back(hyp + "H");
+            }
+        }
+        (void)x;
+    }
+
+    int operator()(const double *x, double &f) {
+        int i = find(x);
+        if (i >= 0) { f = fv[i]; return 0; }
+        const int W = M->spec_emulate ? std::max(M->world, 1) : M->world;
+        std::vector<std::vector<double>> batch = {std::vector<double>(x, x + dim)};
+        if (W > 1) candidates(x, (size_t)W, batch);
+        std::vector<double> fl(batch.size(), 0.0);
+        for (size_t k = 0; k < batch.size(); k++) {
+            if (M->spec_emulate || W == 1 || (int)k == M->rank) {
+                double v;
+                RC(eval(batch[k].data(), v));
+                fl[k] = v;
+            }
+        }
+        if (W > 1 && !M->spec_emulate) RC(reduce_host(M, fl.data(), (int64_t)fl.size(), 0));
+        for (size_t k = 0; k < batch.size(); k++) { pts.push_back(batch[k]); fv.push_back(fl[k]); owner.push_back((int)k); }
+        i = find(x);
+        f = fv[i];
+        return 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------
 // E-step + log-likelihood
 // ---------------------------------------------------------------------------------
 // acc = [upper(S'D^-1 S) | S'D^-1 rho | rho'D^-1 rho | sum log d], summed over ranks
@@ -449,13 +544,27 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
             if (!std::isfinite(p1) || p1 == 1e-9) p1 = 1.0;
             if (!std::isfinite(p0) || p0 == 1e-9) p0 = M->max_l / 10.0;
             NMResult nm;
-            RC(nmmin(f_tau2, std::vector<double>{p0, p1}, nm, 100, 1e-4));
+            SpecNM spec{M, f_tau2, 2, 100, 1e-4, std::vector<double>{p0, p1}};
+            RC(nmmin(std::ref(spec), spec.par0, nm, 100, 1e-4));
             M->taus.push_back(nm.x[0]); M->taus.push_back(nm.x[1]);
-            if (bestTs != nm.x[0] || bestTt != nm.x[1]) {
-                bestF = std::numeric_limits<double>::infinity();
-                double f;
-                RC(f_tau2(nm.x.data(), f));
-                FRK_REQUIRE(bestTs == nm.x[0] && bestTt == nm.x[1], "block-exponential update: tau cannot be evaluated");
+            const bool shared = M->world > 1 && !M->spec_emulate;
+            const int own = shared ? spec.owner[spec.find(nm.x.data())] : M->rank;
+            if (own == M->rank) {
+                if (bestTs != nm.x[0] || bestTt != nm.x[1]) {
+                    bestF = std::numeric_limits<double>::infinity();
+                    double f;
+                    RC(f_tau2(nm.x.data(), f));
+                    FRK_REQUIRE(bestTs == nm.x[0] && bestTt == nm.x[1], "block-exponential update: tau cannot be evaluated");
+                }
+            } else {
+                FRK_CHECK_CUDA(cudaMemsetAsync(B.QsBest, 0, nss * sizeof(double), ctx->stream));
+                FRK_CHECK_CUDA(cudaMemsetAsync(B.QtBest, 0, ntt * sizeof(double), ctx->stream));
+                bestLd = 0.0;
+            }
+            if (shared) {
+                RC(reduce_dev(M, B.QsBest, (int64_t)nss));
+                RC(reduce_dev(M, B.QtBest, (int64_t)ntt));
+                RC(reduce_host(M, &bestLd, 1, 0));
             }
             RC(frk_exp_kernel(ctx, (int64_t)ntt, M->Dt, nm.x[1], 1.0, B.Kt));
             RC(frk_exp_kernel(ctx, (int64_t)nss, B.D, nm.x[0], 1.0, B.Ks));
@@ -487,14 +596,26 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         }
         if (!std::isfinite(par0) || par0 == 1e-9) par0 = M->max_l / 10.0;
         NMResult nm;
-        RC(nmmin(f_tau, std::vector<double>{par0}, nm, 100, 1e-4));   // optim(): Nelder-Mead, :618-621
+        SpecNM spec{M, f_tau, 1, 100, 1e-4, std::vector<double>{par0}};
+        RC(nmmin(std::ref(spec), spec.par0, nm, 100, 1e-4));         // optim(): Nelder-Mead, :618-621 (candidates spread over the ranks)
         const double tau = nm.x[0];
         M->taus.push_back(tau);
-        if (bestTau != tau) {                                        // (does not happen with nmmin's acceptance rules; kept for safety)
-            bestF = std::numeric_limits<double>::infinity();
-            double f;
-            RC(f_tau(&tau, f));
-            FRK_REQUIRE(bestTau == tau, "block-exponential update: tau = %g cannot be evaluated", tau);
+        const bool shared = M->world > 1 && !M->spec_emulate;
+        const int own = shared ? spec.owner[spec.find(&tau)] : M->rank;
+        if (own == M->rank) {
+            if (bestTau != tau) {                                    // ties only: re-evaluate so that KinvBest belongs to tau
+                bestF = std::numeric_limits<double>::infinity();
+                double f;
+                RC(f_tau(&tau, f));
+                FRK_REQUIRE(bestTau == tau, "block-exponential update: tau = %g cannot be evaluated", tau);
+            }
+        } else {
+            FRK_CHECK_CUDA(cudaMemsetAsync(B.KinvBest, 0, nn * sizeof(double), ctx->stream));
+            bestLogdet = 0.0;
+        }
+        if (shared) {                                                // broadcast from the owner: sum with zeros elsewhere
+            RC(reduce_dev(M, B.KinvBest, (int64_t)nn));
+            RC(reduce_host(M, &bestLogdet, 1, 0));
         }
         RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau, 1.0 / omega, B.Ki));       // K_i = exp(-D_i/tau_i)/omega_i, :625-637
         RC(frk_block_scatter(ctx, r, Knew, ni, B.d_ix, B.Ki));
@@ -651,6 +772,15 @@ extern "C" int frk_model_destroy(frk_model *M) {
     for (void *p : M->allocs) cudaFreeAsync(p, M->ctx->stream);
     frk_rowbuckets_destroy(M->bk);
     delete M;
+    return 0;
+}
+
+// this rank's position in a row-partitioned run (enables the speculative Nelder-Mead); emulate != 0: evaluate all of a pretend
+// world's candidates on this rank (tests the logic on one GPU)
+extern "C" int frk_model_set_parallel(frk_model *M, int rank, int world, int emulate) {
+    FRK_REQUIRE(M && world >= 1 && rank >= 0 && rank < world, "frk_model_set_parallel: bad argument");
+    FRK_REQUIRE(emulate || world == 1 || M->allreduce, "frk_model_set_parallel: world > 1 needs the all-reduce hook");
+    M->rank = emulate ? 0 : rank; M->world = world; M->spec_emulate = emulate != 0;
     return 0;
 }
 

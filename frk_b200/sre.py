@@ -81,6 +81,8 @@ class SREModel:
         call("frk_model_create", dev.ctx, m, self.r, p, dev.ptr(S.rowptr), dev.ptr(S.col), dev.ptr(S.val), dev.ptr(Z), dev.ptr(X),
              dev.ptr(Ve), dev.ptr(Vfs), self._hook, vp(None), C.byref(h))
         self.handle = h
+        if dev.world > 1:
+            call("frk_model_set_parallel", h, dev.rank, dev.world, 0)
         self.D_basis = None
 
     def __del__(self):

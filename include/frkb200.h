@@ -302,6 +302,10 @@ int frk_model_create_host(frk_ctx *ctx, int64_t m, int r, int p, const int *h_ro
                           const double *h_val, const double *h_Z, const double *h_X, const double *h_Ve,
                           const double *h_Vfs, frk_model **out);
 int frk_model_destroy(frk_model *mdl);
+/* Position of this rank in a row-partitioned run.  With world > 1 the Nelder-Mead candidates of the block-exponential M-step (each a
+ * replicated r_i x r_i factorisation) are predicted ahead and spread over the ranks; the iterate path and all results are identical to
+ * the sequential run.  emulate != 0 evaluates a pretend world's candidates on this one rank (for tests).                              */
+int frk_model_set_parallel(frk_model *mdl, int rank, int world, int emulate);
 /* BuildD() (R/basisfns.R:1131-1153) for K_type = "block-exponential": h_res[r] 1-based resolution of every basis
  * function, h_D[i] the r_i x r_i centroid distance matrix of resolution i+1 (column-major, host).              */
 int frk_model_set_blocks(frk_model *mdl, int nres, const int *h_res, const double *const *h_D);

@@ -503,3 +503,24 @@ def test_polygon_bau_lookup_and_fit_on_hexagons(dev):
     F.SRE_fit(Mg, n_EM=3, tol=0.0)
     np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
     np.testing.assert_allclose(F.predict(Mg)["var"], O.predict(Mo)[1], rtol=1e-6)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_speculative_nelder_mead_matches_sequential(dev, world):
+    """Multi-rank logic on one GPU: with frk_model_set_parallel(emulate) the Nelder-Mead candidates of a pretend `world` are predicted
+    and evaluated in batches; the iterate path (tau, omega, log-likelihood trace, K) must be that of the sequential run (up to the
+    1e-13 run-to-run noise of the Gram kernel's fp64 atomics)."""
+    import frk_b200 as F
+    from frk_b200._lib import call
+    _, Ma = _setup_plane(F, K_type="block-exponential", hetero=True)
+    _, Mb = _setup_plane(F, K_type="block-exponential", hetero=True)
+    call("frk_model_set_parallel", Mb.handle, 0, world, 1)
+    F.SRE_fit(Ma, n_EM=5, tol=0.0)
+    F.SRE_fit(Mb, n_EM=5, tol=0.0)
+    np.testing.assert_allclose(Mb.info_fit["llk"], Ma.info_fit["llk"], rtol=1e-11)
+    np.testing.assert_allclose(Mb.info_fit["tau"], Ma.info_fit["tau"], rtol=1e-10)
+    np.testing.assert_allclose(Mb.info_fit["omega"], Ma.info_fit["omega"], rtol=1e-10)
+    Ka, Kb = Ma.get("Khat"), Mb.get("Khat")
+    np.testing.assert_allclose(Kb, Ka, rtol=1e-9, atol=1e-12 * abs(Ka).max())
+    Ia, Ib = Ma.get("Khat_inv"), Mb.get("Khat_inv")
+    np.testing.assert_allclose(Ib, Ia, rtol=1e-8, atol=1e-11 * abs(Ia).max())
