@@ -236,6 +236,7 @@ def run_b200(args):
     t_em = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     launches = dev.launches() - l0
     llk_tail = [float(v) for v in mdl.info_fit["llk"][-2:]]
+    nm_stats = mdl.info_fit.get("nm_stats")
 
     _dbg("EM timed")
     # ---- (B) device-resident prediction ---------------------------------------------------------------
@@ -364,7 +365,7 @@ def run_b200(args):
                 "e2e": {"value": args.steps / t_fit_e2e, "unit": "EM iters/s", "h2d_bytes_per_step": h2d_fit / args.steps,
                         "d2h_bytes_per_step": d2h_fit / args.steps,
                         "what": f"SRE() from pinned host arrays + SRE_fit({args.steps} EM iterations from .EM_initialise) + fitted slots (mu_eta, S_eta, Khat, Khat_inv) back to pinned host memory, wall clock, after one untimed pass"},
-                "gpu_launches": int(launches), "clocks": clk, "llk_last": llk_tail}
+                "gpu_launches": int(launches), "clocks": clk, "llk_last": llk_tail, "nelder_mead_last_mstep": nm_stats}
         if roof:
             line["roofline"] = roof
         if kernels:

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 #include <limits>
 
@@ -60,6 +61,7 @@ struct frk_model {
     double *Dt = nullptr;          // nt x nt temporal distances (tensor bases)
     double Dt01 = 0.0;
     std::vector<double> taus, omegas;
+    double nm_requests = 0, nm_rounds = 0, nm_evals = 0;   // Nelder-Mead statistics of the last M-step (distinct points asked, batches, points evaluated)
     // multi-rank reduction hook
     int rank = 0, world = 1;
     bool spec_emulate = false;     // evaluate every speculative candidate on this rank (single-GPU test of the multi-rank logic)
@@ -353,8 +355,10 @@ struct SpecNM {
 
     // points nmmin may request after `x`, under hypothetical outcomes for the unknown ones (breadth first, at most `want`)
     void candidates(const double *x, size_t want, std::vector<std::vector<double>> &batch) const {
-        std::vector<std::string> queue = {"L", "H"};
-        for (size_t qi = 0; qi < queue.size() && batch.size() < want && qi < 64; qi++) {
+        // outcomes for an unknown point: H = worse than everything known, M = between the best and the worst, L = better than everything.
+        // Breadth first, "worse" first: near convergence (tau starts at the previous optimum) new points are usually worse than the best.
+        std::vector<std::string> queue = {"H", "M", "L"};
+        for (size_t qi = 0; qi < queue.size() && batch.size() < want && qi < 400; qi++) {
             const std::string hyp = queue[qi];
             std::vector<std::vector<double>> hp;
             std::vector<double> hf;
@@ -374,7 +378,7 @@ struct SpecNM {
                     auto upd = [&](double v) { if (std::isfinite(v)) { lo = any ? std::min(lo, v) : v; hi = any ? std::max(hi, v) : v; any = true; } };
                     for (double v : fv) upd(v);
                     for (double v : hf) upd(v);
-                    f = hyp[used] == 'L' ? lo - 1.0 - 1e-3 * std::fabs(lo) : hi + 1.0 + 1e-3 * std::fabs(hi);
+                    f = hyp[used] == 'L' ? lo - 1.0 - 1e-3 * std::fabs(lo) : hyp[used] == 'H' ? hi + 1.0 + 1e-3 * std::fabs(hi) : 0.5 * (lo + hi);
                     used++;
                     hp.emplace_back(y, y + dim); hf.push_back(f);
                     return 0;
@@ -388,8 +392,9 @@ struct SpecNM {
                 bool dup = find(cand.data()) >= 0;
                 for (auto &b : batch) { bool eq = true; for (int d = 0; d < dim; d++) eq = eq && b[d] == cand[d]; dup = dup || eq; }
                 if (!dup) batch.push_back(cand);
-                queue.push_back(hyp + "L");
                 queue.push_back(hyp + "H");
+                queue.push_back(hyp + "M");
+                queue.push_back(hyp + "L");
             }
         }
         (void)x;
@@ -397,7 +402,10 @@ struct SpecNM {
 
     int operator()(const double *x, double &f) {
         int i = find(x);
+        M->nm_requests += 1;
         if (i >= 0) { f = fv[i]; return 0; }
+        M->nm_rounds += 1;
+        static const bool dbg = getenv("FRK_SPEC_DEBUG") != nullptr;
         const int W = M->spec_emulate ? std::max(M->world, 1) : M->world;
         std::vector<std::vector<double>> batch = {std::vector<double>(x, x + dim)};
         if (W > 1) candidates(x, (size_t)W, batch);
@@ -410,7 +418,13 @@ struct SpecNM {
             }
         }
         if (W > 1 && !M->spec_emulate) RC(reduce_host(M, fl.data(), (int64_t)fl.size(), 0));
+        if (dbg && M->rank == 0) {
+            fprintf(stderr, "[spec] miss at %.10g (known %zu) batch:", x[0], pts.size());
+            for (size_t k = 0; k < batch.size(); k++) fprintf(stderr, " %.10g->%.8g", batch[k][0], fl[k]);
+            fprintf(stderr, "\n");
+        }
         for (size_t k = 0; k < batch.size(); k++) { pts.push_back(batch[k]); fv.push_back(fl[k]); owner.push_back((int)k); }
+        M->nm_evals += (double)batch.size();
         i = find(x);
         f = fv[i];
         return 0;
@@ -488,6 +502,7 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
     FRK_REQUIRE(!M->blocks.empty(), "K_type = \"block-exponential\" needs the per-resolution distance matrices (frk_model_set_blocks)");
     // K_new is assembled in w1 and K_new^-1 in w2 (both free here); the old Khat / Khat_inv are read for omega and the start values
     M->taus.clear(); M->omegas.clear();
+    M->nm_requests = M->nm_rounds = M->nm_evals = 0;
     double *Knew = M->w1, *Kinvnew = M->w2;
     FRK_CHECK_CUDA(cudaMemsetAsync(Knew, 0, rr * sizeof(double), ctx->stream));
     FRK_CHECK_CUDA(cudaMemsetAsync(Kinvnew, 0, rr * sizeof(double), ctx->stream));
@@ -936,6 +951,7 @@ extern "C" int frk_model_get(frk_model *M, const char *slot, double *h_out) {
     if (!strcmp(slot, "m_total")) { h_out[0] = M->m_total; return 0; }
     if (!strcmp(slot, "homoscedastic")) { h_out[0] = M->homoscedastic ? 1.0 : 0.0; return 0; }
     if (!strcmp(slot, "tau")) { for (size_t i = 0; i < M->taus.size(); i++) h_out[i] = M->taus[i]; return 0; }
+    if (!strcmp(slot, "nm_stats")) { h_out[0] = M->nm_requests; h_out[1] = M->nm_rounds; h_out[2] = M->nm_evals; return 0; }
     if (!strcmp(slot, "omega")) { for (size_t i = 0; i < M->omegas.size(); i++) h_out[i] = M->omegas[i]; return 0; }
     size_t n = 0;
     double *p = slot_ptr(M, slot, &n);
