@@ -21,7 +21,6 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
-import math
 import os
 import subprocess
 import sys
@@ -188,7 +187,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import frk_b200 as F
-    from frk_b200._lib import call, lib
+    from frk_b200._lib import call
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -16,7 +16,6 @@ NCCL) and for the O(p^2) M-step moments.
 from __future__ import annotations
 
 import ctypes as C
-import math
 import re
 import time
 from typing import Optional
@@ -25,27 +24,9 @@ import numpy as np
 
 from . import _lib
 from ._lib import FRKError, call, c_i64, vp
-from .basis import Basis, BuildD, DeviceCSR, TensorP_Basis, eval_basis_device
-from .geometry import GridBAUs, PointBAUs, SpatialPointsDataFrame, map_data_to_BAUs
+from .basis import BuildD, DeviceCSR, TensorP_Basis, eval_basis_device
+from .geometry import GridBAUs, SpatialPointsDataFrame, map_data_to_BAUs
 from .runtime import Device, get_device, partition_rows
-
-_DBL4 = C.c_double * 4
-
-
-# ---------------------------------------------------------------------------------------
-# small helpers around the C ABI
-# ---------------------------------------------------------------------------------------
-
-def _alpha_ptr(alpha: np.ndarray):
-    a = np.ascontiguousarray(alpha, dtype=np.float64)
-    return a, vp(a.ctypes.data)
-
-
-def _vec_stats(dev: Device, t, n: int, shift: float = 0.0):
-    out = _DBL4()
-    call("frk_vec_stats", dev.ctx, int(n), dev.ptr(t), float(shift), out)
-    return np.array(out[:], dtype=np.float64)
-
 
 def _parse_formula(f: str):
     """``z ~ 1``, ``co2avgret ~ lat + 1``, ``z ~ -1 + x`` ...  (stats::model.frame as SRE() uses it,
