@@ -97,6 +97,7 @@ SIGNATURES = {
     "frk_sym_from_upper_add": (c_int, [vp, c_int, vp, vp, vp]),
     "frk_scaled_identity": (c_int, [vp, c_int, c_dbl, vp]),
     "frk_add_diag": (c_int, [vp, c_int, vp, vp]),
+    "frk_add_scaled_outer": (c_int, [vp, c_int, vp, vp, c_dbl, vp]),
     "frk_add_outer": (c_int, [vp, c_int, vp, vp, vp]),
     "frk_exp_kernel": (c_int, [vp, c_i64, vp, c_dbl, c_dbl, vp]),
     "frk_dot": (c_int, [vp, c_i64, vp, vp, p_dbl]),

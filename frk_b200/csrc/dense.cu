@@ -826,6 +826,19 @@ __global__ void add_outer_kernel(int r, const double *__restrict__ A, const doub
     }
 }
 
+__global__ void add_scaled_outer_kernel(int r, const double *__restrict__ A, const double *__restrict__ x, double alpha, double *__restrict__ out) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)r * r; idx += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(idx % r), j = (int)(idx / r);
+        out[idx] = A[idx] + alpha * (x[i] * x[j]);
+    }
+}
+
+extern "C" int frk_add_scaled_outer(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double alpha, double *d_out) {
+    FRK_REQUIRE(ctx && d_A && d_x && d_out && r > 0, "frk_add_scaled_outer: bad argument");
+    FRK_LAUNCH(ctx, add_scaled_outer_kernel, ctx->sm_count * 8, 256, 0, r, d_A, d_x, alpha, d_out);
+    return 0;
+}
+
 extern "C" int frk_add_outer(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double *d_out) {
     FRK_REQUIRE(ctx && d_A && d_x && d_out && r > 0, "frk_add_outer: bad argument");
     FRK_LAUNCH(ctx, add_outer_kernel, ctx->sm_count * 8, 256, 0, r, d_A, d_x, d_out);

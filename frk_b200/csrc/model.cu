@@ -50,7 +50,7 @@ struct frk_model {
     double *acc = nullptr, *w1 = nullptr, *w2 = nullptr, *vec = nullptr, *t = nullptr, *q = nullptr;
     // host state
     double alpha[MAXP_M] = {0, 0, 0, 0};
-    double sigma2fs = 0.0, logdetK = 0.0;
+    double sigma2fs = 0.0, logdetK = 0.0, logdetQ = 0.0;   // logdetQ: log|Q_eta| of the last E-step into the slots
     double m_total = 0.0, Ve0 = 0.0, Vfs0 = 0.0;
     bool homoscedastic = false, all_vfs_zero = false, initialised = false;
     bool khat_block_diag = false;   // Khat is block diagonal by resolution AND Khat_inv = chol2inv(chol(Khat)) (init / block-exponential update)
@@ -454,6 +454,7 @@ int posterior(frk_model *M, const double *alpha, double sigma2fs, double *Q_out,
     RC(frk_sym_from_upper_add(ctx, r, M->acc, M->Khat_inv, Q_out));
     FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, Q_out, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     RC(frk_potrf(ctx, r, M->w1, &out[0]));
+    if (Q_out == M->Q_eta) M->logdetQ = out[0];
     RC(frk_potri(ctx, r, M->w1, Sig_out, M->w2));
     RC(frk_symv(ctx, r, Sig_out, b, mu_out));
     // || (rDinv S) solve(R) ||^2 with solve(R)' = L^-1 left in w2 by potri   (R/SREfit.R:211)
@@ -496,7 +497,17 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
             RC(chol2inv_logdet(ctx, r, M->Khat, M->w1, M->w2, &ld));
             RC(frk_add_diag(ctx, r, M->vec, M->w1));
             RC(chol2inv_logdet(ctx, r, M->w1, M->Khat, M->w2, &ld));
+            return 0;
         }
+        // Khat_inv = chol2inv(chol(K)) (:273) without a factorisation: S_eta = Q_eta^-1 was just computed by the E-step, so by
+        // Sherman-Morrison (S_eta + mu mu')^-1 = Q - (Q mu)(Q mu)' / (1 + mu'Q mu) and log|K| = -log|Q| + log(1 + mu'Q mu).
+        double s1;
+        RC(frk_symv(ctx, r, M->Q_eta, M->mu_eta, M->vec));
+        RC(frk_dot(ctx, r, M->vec, M->mu_eta, &s1));
+        RC(frk_add_scaled_outer(ctx, r, M->Q_eta, M->vec, -1.0 / (1.0 + s1), M->Khat_inv));
+        M->logdetK = -M->logdetQ + std::log1p(s1);
+        M->khat_block_diag = false;
+        have_inverse = true;
         return 0;
     }
     FRK_REQUIRE(!M->blocks.empty(), "K_type = \"block-exponential\" needs the per-resolution distance matrices (frk_model_set_blocks)");

@@ -265,6 +265,8 @@ int frk_scaled_identity(frk_ctx *ctx, int r, double value, double *d_A);
 int frk_add_diag(frk_ctx *ctx, int r, const double *d_diag, double *d_A);
 /* out = A + x x'   (S_eta + tcrossprod(mu_eta), R/SREfit.R:332,689) */
 int frk_add_outer(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double *d_out);
+/* out = A + alpha x x'   (Sherman-Morrison form of Khat_inv for the unstructured K, R/SREfit.R:273,689) */
+int frk_add_scaled_outer(frk_ctx *ctx, int r, const double *d_A, const double *d_x, double alpha, double *d_out);
 /* out = exp(-D / tau) * scale   (block-exponential K_i, R/SREfit.R:517,631) */
 int frk_exp_kernel(frk_ctx *ctx, int64_t n, const double *d_D, double tau, double scale, double *d_out);
 /* *h_out = sum(A * B) elementwise over n entries (sum(diag2(.,., symm=TRUE)), R/SREfit.R:478,524) */
