@@ -84,6 +84,7 @@ SIGNATURES = {
     "frk_vec_stats": (c_int, [vp, c_i64, vp, c_dbl, vp]),
     "frk_square": (c_int, [vp, c_i64, vp, vp]),
     "frk_recip": (c_int, [vp, c_i64, vp, vp]),
+    "frk_fill": (c_int, [vp, c_i64, c_dbl, vp]),
     "frk_scale": (c_int, [vp, c_i64, c_dbl, vp]),
     "frk_gather_rows": (c_int, [vp, c_i64, c_int, vp, vp, c_i64, vp, c_i64]),
     "frk_predict_finalize": (c_int, [vp, c_i64, c_int, c_dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

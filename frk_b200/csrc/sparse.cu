@@ -418,3 +418,16 @@ extern "C" int frk_scale(frk_ctx *ctx, int64_t n, double alpha, double *d_x) {
     FRK_LAUNCH(ctx, scale_kernel, grid, 256, 0, n, alpha, d_x);
     return 0;
 }
+
+// x[i] = value   (the intercept column of the model matrix at the BAUs, R/SRE.R:464-465)
+__global__ void fill_kernel(int64_t n, double value, double *__restrict__ x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = value;
+}
+
+extern "C" int frk_fill(frk_ctx *ctx, int64_t n, double value, double *d_x) {
+    FRK_REQUIRE(ctx && (n == 0 || d_x), "frk_fill: NULL argument");
+    if (n == 0) return 0;
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, fill_kernel, grid, 256, 0, n, value, d_x);
+    return 0;
+}

@@ -268,8 +268,12 @@ def map_data_to_BAUs(data: SpatialPointsDataFrame, BAUs, columns, dev: Optional[
         b = np.asarray(data.data["bau"]).astype(np.int64)
         b = np.where((b >= lo) & (b < hi), b - lo, -1)     # host: the lookup itself was done on the host
         d_bau = dev.upload(b.astype(np.int32))
-    vals = np.column_stack([data.data[c] for c in columns]) if ncols else np.zeros((n, 0))
-    d_vals = dev.upload(vals)
+    d_vals = dev.empty(max(n * ncols, 1))                          # n x ncols column-major, one H2D per column (no host-side stacking)
+    for k, c in enumerate(columns):
+        colv = np.ascontiguousarray(data.data[c], dtype=np.float64)
+        if n:
+            call("frk_h2d", dev.ctx, dev.ptr(d_vals, k * n), vp(colv.ctypes.data), colv.nbytes)
+    call("frk_sync", dev.ctx)
     d_obs = dev.empty(max(n, 1), "i4")
     d_means = dev.empty(max(n * ncols, 1), "f8")
     d_cnt = dev.empty(max(n, 1), "i4")

@@ -190,11 +190,19 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
     fs_host = np.ascontiguousarray(BAUs.fields["fs"][lo:hi], dtype=np.float64)
     fs_BAU = dev.upload(fs_host)
     h2d += fs_host.nbytes
-    xcols = ([np.ones(nloc)] if intercept else []) + [np.asarray(BAUs.fields[c][lo:hi], dtype=np.float64) for c in covs]
-    p = len(xcols)
-    X_BAU_host = np.column_stack(xcols) if nloc else np.zeros((0, p))
-    X_BAU = dev.upload(X_BAU_host)
-    h2d += X_BAU_host.nbytes
+    p = (1 if intercept else 0) + len(covs)
+    X_BAU = dev.empty(max(nloc * p, 1))                           # model matrix at this rank's BAUs, column-major (nloc x p)
+    k = 0
+    if intercept:                                                 # the intercept column is generated on the device
+        call("frk_fill", dev.ctx, nloc, 1.0, dev.ptr(X_BAU))
+        k = 1
+    for c in covs:
+        colv = np.ascontiguousarray(BAUs.fields[c][lo:hi], dtype=np.float64)
+        if nloc:
+            call("frk_h2d", dev.ctx, dev.ptr(X_BAU, k * nloc), vp(colv.ctypes.data), colv.nbytes)
+            call("frk_sync", dev.ctx)
+        h2d += colv.nbytes
+        k += 1
     Vfs = dev.empty(max(m, 1))                                    # Vfs = diag(fs[bau]), R/SRE.R:498
     call("frk_gather_rows", dev.ctx, m, 1, dev.ptr(obs_bau), dev.ptr(fs_BAU), nloc, dev.ptr(Vfs), m)
     X = dev.empty(max(m * p, 1))                                  # model matrix at the observed BAUs, :464-465

@@ -221,6 +221,8 @@ int frk_square(frk_ctx *ctx, int64_t n, const double *d_a, double *d_out);
 int frk_recip(frk_ctx *ctx, int64_t n, const double *d_a, double *d_out);
 /* x *= alpha  (K_i^-1 = omega_i exp(-D_i/tau_i)^-1, R/SREfit.R:625-637) */
 int frk_scale(frk_ctx *ctx, int64_t n, double alpha, double *d_x);
+/* x[i] = value  (intercept column of the model matrix at the BAUs, R/SRE.R:464-465) */
+int frk_fill(frk_ctx *ctx, int64_t n, double value, double *d_x);
 /* dst[j, c] = src[idx[j], c] for ncols column-major columns: Vfs = fs[bau] (R/SRE.R:498) and the model
  * matrix X at the observed BAUs (R/SRE.R:464-465)                                                */
 int frk_gather_rows(frk_ctx *ctx, int64_t m, int ncols, const int *d_idx, const double *d_src,
