@@ -125,6 +125,11 @@ def auto_basis(manifold: Manifold, data, regular: int = 1, nres: int = 3, prune:
     other implementation can reproduce -- pass the coordinates you want the ranges taken from).
     Sphere placement needs the ISEA3H centroids (``isea3h`` = {resolution: (n x 2) lon/lat}).
     """
+    if manifold.kind in ("STplane", "STsphere"):
+        # the reference builds TensorP(auto_basis(<spatial>), 10 Gaussian time functions) from the STIDF's
+        # time stamps (R/basisfns.R:243-289); there is no spacetime container here, so be explicit
+        raise FRKError("auto_basis on a space-time manifold: build TensorP(auto_basis(plane()|sphere(), ...), "
+                       "local_basis(real_line(), ...)) explicitly; local_basis(STplane()|STsphere(), ...) is supported")
     if prune:
         raise FRKError("auto_basis(prune > 0) is deprecated in the reference and not on the device path")
     if not regular and manifold.kind == "plane":

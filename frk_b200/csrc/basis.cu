@@ -28,7 +28,8 @@ struct GroupDev {
 struct BasisDev {
     int r, ngroups, manifold, type, d;
     double radius;
-    const double *c0, *c1, *c2;   // plane/line: x,(y); sphere: unit normal of the centroid
+    const double *c0, *c1, *c2;   // plane/line/STplane: x,(y),(t); sphere/STsphere: unit normal of the centroid
+    const double *c3;             // STsphere: time coordinate of the centroid
     const double *scale;
     GroupDev g[MAXG];
 };
@@ -196,10 +197,11 @@ int upload(frk_basis *b, const std::vector<T> &v, const T **out) {
 extern "C" int frk_basis_create(frk_ctx *ctx, int manifold, double radius, int type, int d, int r,
                                 const double *h_loc, const double *h_scale, const int *h_res, frk_basis **out) {
     FRK_REQUIRE(ctx && out && h_loc && h_scale, "frk_basis_create: NULL argument");
-    FRK_REQUIRE(manifold == FRK_REAL_LINE || manifold == FRK_PLANE || manifold == FRK_SPHERE,
-                "frk_basis_create: unsupported manifold %d (only real_line, plane, sphere; custom measures are refused, no CPU fallback)", manifold);
+    FRK_REQUIRE(manifold >= FRK_REAL_LINE && manifold <= FRK_STSPHERE,
+                "frk_basis_create: unsupported manifold %d (only real_line, plane, sphere, STplane, STsphere; custom measures are refused, no CPU fallback)", manifold);
     FRK_REQUIRE(type >= FRK_BISQUARE && type <= FRK_MATERN32, "frk_basis_create: unknown basis type %d", type);
-    int dexp = manifold == FRK_REAL_LINE ? 1 : 2;
+    const bool on_sphere = manifold == FRK_SPHERE || manifold == FRK_STSPHERE;
+    int dexp = manifold == FRK_REAL_LINE ? 1 : (manifold >= FRK_STPLANE ? 3 : 2);
     FRK_REQUIRE(d == dexp, "number of columns in loc (%d) needs to be the same as the number of manifold dimensions (%d)", d, dexp);
     FRK_REQUIRE(r > 0, "frk_basis_create: need at least one basis function");
     for (int j = 0; j < r; j++)
@@ -212,19 +214,25 @@ extern "C" int frk_basis_create(frk_ctx *ctx, int manifold, double radius, int t
     D.r = r; D.manifold = manifold; D.type = type; D.d = d; D.radius = radius;
 
     // centroid table
-    std::vector<double> c0(r), c1(r, 0.0), c2(r, 0.0), sc(h_scale, h_scale + r);
-    if (manifold == FRK_SPHERE) {
+    std::vector<double> c0(r), c1(r, 0.0), c2(r, 0.0), c3(r, 0.0), sc(h_scale, h_scale + r);
+    if (on_sphere) {
         for (int j = 0; j < r; j++) {
             // x2 * pi/180; n2 = (cos(lat)cos(lon), cos(lat)sin(lon), sin(lat))   R/geometryfns.R:1727,1732
             double lon = (h_loc[j] * M_PI) / 180.0, lat = (h_loc[j + r] * M_PI) / 180.0;
             double cl = std::cos(lat);
             c0[j] = cl * std::cos(lon); c1[j] = cl * std::sin(lon); c2[j] = std::sin(lat);
+            if (d > 2) c3[j] = h_loc[j + 2 * (size_t)r];
         }
     } else {
-        for (int j = 0; j < r; j++) { c0[j] = h_loc[j]; if (d > 1) c1[j] = h_loc[j + r]; }
+        for (int j = 0; j < r; j++) {
+            c0[j] = h_loc[j];
+            if (d > 1) c1[j] = h_loc[j + r];
+            if (d > 2) c2[j] = h_loc[j + 2 * (size_t)r];
+        }
     }
     int rc = 0;
-    rc |= upload(b, c0, &D.c0); rc |= upload(b, c1, &D.c1); rc |= upload(b, c2, &D.c2); rc |= upload(b, sc, &D.scale);
+    rc |= upload(b, c0, &D.c0); rc |= upload(b, c1, &D.c1); rc |= upload(b, c2, &D.c2); rc |= upload(b, c3, &D.c3);
+    rc |= upload(b, sc, &D.scale);
     if (rc) { frk_basis_destroy(b); return rc; }
 
     // groups = resolutions, in order of first appearance
@@ -249,8 +257,9 @@ extern "C" int frk_basis_create(frk_ctx *ctx, int manifold, double radius, int t
     for (size_t g = 0; g < members.size(); g++) {
         HostGroup hg;
         if (type != FRK_BISQUARE) build_all(members[g], hg);
-        else if (manifold == FRK_SPHERE) build_sphere(members[g], h_loc, r, h_scale, radius, hg);
-        else build_euclid(members[g], d, h_loc, r, h_scale, hg);
+        // space-time: dist >= spatial dist, so the spatial cell list (time ignored) is a valid superset
+        else if (on_sphere) build_sphere(members[g], h_loc, r, h_scale, radius, hg);
+        else build_euclid(members[g], std::min(d, 2), h_loc, r, h_scale, hg);
         GroupDev &G = D.g[g];
         G.x0 = hg.x0; G.y0 = hg.y0; G.hx = hg.hx; G.hy = hg.hy; G.nx = hg.nx; G.ny = hg.ny; G.all = hg.all;
         rc |= upload(b, hg.start, &G.cell_start);
@@ -276,12 +285,18 @@ extern "C" int frk_basis_dim(const frk_basis *b) { return b ? b->dev.d : -1; }
 // ---------------------------------------------------------------------------------
 // device: distance + basis function in the reference's operation order
 // ---------------------------------------------------------------------------------
-struct PointCoord { double a, b, c; double u, v; };   // (a,b,c) distance operand; (u,v) cell-lookup coords
+struct PointCoord { double a, b, c, t; double u, v; };   // (a,b,c,t) distance operand; (u,v) cell-lookup coords
+
+template <int MAN> struct man_traits {
+    static constexpr bool sphere = MAN == FRK_SPHERE || MAN == FRK_STSPHERE;
+    static constexpr bool line = MAN == FRK_REAL_LINE;
+};
 
 template <int MAN>
 __device__ __forceinline__ PointCoord load_point(const double *__restrict__ s, int64_t ld, int64_t i) {
     PointCoord p;
-    if (MAN == FRK_SPHERE) {
+    p.t = 0;
+    if (man_traits<MAN>::sphere) {
         double lon = s[i], lat = s[i + ld];
         double lo = __ddiv_rn(__dmul_rn(lon, M_PI), 180.0);    // x1 * pi/180, R/geometryfns.R:1726
         double la = __ddiv_rn(__dmul_rn(lat, M_PI), 180.0);
@@ -291,6 +306,9 @@ __device__ __forceinline__ PointCoord load_point(const double *__restrict__ s, i
         p.a = __dmul_rn(cl, co); p.b = __dmul_rn(cl, so); p.c = sl;   // :1731
         p.u = lon - 360.0 * floor((lon + 180.0) / 360.0);
         p.v = lat;
+        if (MAN == FRK_STSPHERE) p.t = s[i + 2 * ld];
+    } else if (MAN == FRK_STPLANE) {
+        p.a = s[i]; p.b = s[i + ld]; p.c = s[i + 2 * ld]; p.u = p.a; p.v = p.b;
     } else if (MAN == FRK_PLANE) {
         p.a = s[i]; p.b = s[i + ld]; p.c = 0; p.u = p.a; p.v = p.b;
     } else {
@@ -301,12 +319,21 @@ __device__ __forceinline__ PointCoord load_point(const double *__restrict__ s, i
 
 template <int MAN>
 __device__ __forceinline__ double basis_dist(const PointCoord &p, const BasisDev &B, int j) {
-    if (MAN == FRK_SPHERE) {
+    if (man_traits<MAN>::sphere) {
         // tcrossprod(n1,n2) in reference-BLAS order ((a1 b1)+a2 b2)+a3 b3, clamp, R*acos   :1733-1738
         double t = __dadd_rn(__dadd_rn(__dmul_rn(p.a, __ldg(B.c0 + j)), __dmul_rn(p.b, __ldg(B.c1 + j))),
                              __dmul_rn(p.c, __ldg(B.c2 + j)));
         if (fabs(t) > 1.0) t = t > 0 ? 1.0 : -1.0;
-        return __dmul_rn(B.radius, acos(t));
+        const double sd = __dmul_rn(B.radius, acos(t));
+        if (MAN == FRK_SPHERE) return sd;
+        // gc_dist_time: sqrt(spatdist^2 + tdist^2), tdist = distR(t1,t2) = sqrt((t1-t2)^2)   R/geometryfns.R:181-189
+        const double dt = __dsub_rn(p.t, __ldg(B.c3 + j));
+        const double td = __dsqrt_rn(__dmul_rn(dt, dt));
+        return __dsqrt_rn(__dadd_rn(__dmul_rn(sd, sd), __dmul_rn(td, td)));
+    } else if (MAN == FRK_STPLANE) {
+        // Euclid_dist(dim=3L): distR over three columns, Reduce("+") left to right   R/geometryfns.R:217-218
+        double dx = __dsub_rn(p.a, __ldg(B.c0 + j)), dy = __dsub_rn(p.b, __ldg(B.c1 + j)), dt = __dsub_rn(p.c, __ldg(B.c2 + j));
+        return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dt, dt)));
     } else if (MAN == FRK_PLANE) {
         // sqrt(Reduce("+", (x1_d - x2_d)^2)), R/geometryfns.R:217-218
         double dx = __dsub_rn(p.a, __ldg(B.c0 + j)), dy = __dsub_rn(p.b, __ldg(B.c1 + j));
@@ -340,7 +367,7 @@ __device__ __forceinline__ void cand_range(const GroupDev &G, const PointCoord &
     if (G.all) { beg = G.cell_start[0]; end = G.cell_start[1]; return; }
     double fx = floor((p.u - G.x0) / G.hx);
     double fy = MAN == FRK_REAL_LINE ? 0.0 : floor((p.v - G.y0) / G.hy);
-    if (MAN == FRK_SPHERE) {   // closed domain: clamp the upper edges (lat = 90) into the last cell
+    if (man_traits<MAN>::sphere) {   // closed domain: clamp the upper edges (lat = 90) into the last cell
         if (fx >= G.nx) fx = G.nx - 1;
         if (fy >= G.ny) fy = G.ny - 1;
         if (fx < 0) fx = 0;
@@ -488,9 +515,13 @@ extern "C" int frk_eval_basis_count(frk_ctx *ctx, const frk_basis *b, int64_t n,
     int *counts = nullptr;
     FRK_CHECK_CUDA(cudaMallocAsync((void **)&counts, n * sizeof(int), ctx->stream));
     int rc;
-    if (b->dev.manifold == FRK_SPHERE) rc = launch_count<FRK_SPHERE>(ctx, b, n, d_s, ld_s, counts);
-    else if (b->dev.manifold == FRK_PLANE) rc = launch_count<FRK_PLANE>(ctx, b, n, d_s, ld_s, counts);
-    else rc = launch_count<FRK_REAL_LINE>(ctx, b, n, d_s, ld_s, counts);
+    switch (b->dev.manifold) {
+        case FRK_SPHERE:   rc = launch_count<FRK_SPHERE>(ctx, b, n, d_s, ld_s, counts); break;
+        case FRK_PLANE:    rc = launch_count<FRK_PLANE>(ctx, b, n, d_s, ld_s, counts); break;
+        case FRK_STPLANE:  rc = launch_count<FRK_STPLANE>(ctx, b, n, d_s, ld_s, counts); break;
+        case FRK_STSPHERE: rc = launch_count<FRK_STSPHERE>(ctx, b, n, d_s, ld_s, counts); break;
+        default:           rc = launch_count<FRK_REAL_LINE>(ctx, b, n, d_s, ld_s, counts); break;
+    }
     if (!rc) rc = frk_exclusive_scan_i32(ctx, counts, n, d_rowptr, h_nnz);
     cudaFreeAsync(counts, ctx->stream);
     return rc;
@@ -500,9 +531,13 @@ extern "C" int frk_eval_basis_fill(frk_ctx *ctx, const frk_basis *b, int64_t n, 
                                    const int *d_rowptr, int *d_col, double *d_val, int normalise) {
     FRK_REQUIRE(ctx && b && d_rowptr, "frk_eval_basis_fill: NULL argument");
     if (n == 0) return 0;
-    if (b->dev.manifold == FRK_SPHERE) return launch_fill<FRK_SPHERE>(ctx, b, n, d_s, ld_s, d_rowptr, d_col, d_val, normalise);
-    if (b->dev.manifold == FRK_PLANE) return launch_fill<FRK_PLANE>(ctx, b, n, d_s, ld_s, d_rowptr, d_col, d_val, normalise);
-    return launch_fill<FRK_REAL_LINE>(ctx, b, n, d_s, ld_s, d_rowptr, d_col, d_val, normalise);
+    switch (b->dev.manifold) {
+        case FRK_SPHERE:   return launch_fill<FRK_SPHERE>(ctx, b, n, d_s, ld_s, d_rowptr, d_col, d_val, normalise);
+        case FRK_PLANE:    return launch_fill<FRK_PLANE>(ctx, b, n, d_s, ld_s, d_rowptr, d_col, d_val, normalise);
+        case FRK_STPLANE:  return launch_fill<FRK_STPLANE>(ctx, b, n, d_s, ld_s, d_rowptr, d_col, d_val, normalise);
+        case FRK_STSPHERE: return launch_fill<FRK_STSPHERE>(ctx, b, n, d_s, ld_s, d_rowptr, d_col, d_val, normalise);
+        default:           return launch_fill<FRK_REAL_LINE>(ctx, b, n, d_s, ld_s, d_rowptr, d_col, d_val, normalise);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -574,7 +609,7 @@ __global__ void basis_dist_matrix_kernel(BasisDev B, int ni, const int *__restri
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)ni * ni; t += (int64_t)gridDim.x * blockDim.x) {
         const int ja = idx[t % ni], jb = idx[t / ni];
         PointCoord p;
-        p.a = __ldg(B.c0 + ja); p.b = __ldg(B.c1 + ja); p.c = __ldg(B.c2 + ja); p.u = p.v = 0;
+        p.a = __ldg(B.c0 + ja); p.b = __ldg(B.c1 + ja); p.c = __ldg(B.c2 + ja); p.t = __ldg(B.c3 + ja); p.u = p.v = 0;
         D[t] = basis_dist<MAN>(p, B, jb);
     }
 }
@@ -582,8 +617,12 @@ __global__ void basis_dist_matrix_kernel(BasisDev B, int ni, const int *__restri
 extern "C" int frk_basis_dist_matrix(frk_ctx *ctx, const frk_basis *b, int ni, const int *d_idx, double *d_D) {
     FRK_REQUIRE(ctx && b && d_idx && d_D && ni > 0, "frk_basis_dist_matrix: bad argument");
     const unsigned grid = ctx->sm_count * 8;
-    if (b->dev.manifold == FRK_SPHERE) FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_SPHERE>, grid, 256, 0, b->dev, ni, d_idx, d_D);
-    else if (b->dev.manifold == FRK_PLANE) FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_PLANE>, grid, 256, 0, b->dev, ni, d_idx, d_D);
-    else FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_REAL_LINE>, grid, 256, 0, b->dev, ni, d_idx, d_D);
+    switch (b->dev.manifold) {
+        case FRK_SPHERE:   FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_SPHERE>, grid, 256, 0, b->dev, ni, d_idx, d_D); break;
+        case FRK_PLANE:    FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_PLANE>, grid, 256, 0, b->dev, ni, d_idx, d_D); break;
+        case FRK_STPLANE:  FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_STPLANE>, grid, 256, 0, b->dev, ni, d_idx, d_D); break;
+        case FRK_STSPHERE: FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_STSPHERE>, grid, 256, 0, b->dev, ni, d_idx, d_D); break;
+        default:           FRK_LAUNCH(ctx, basis_dist_matrix_kernel<FRK_REAL_LINE>, grid, 256, 0, b->dev, ni, d_idx, d_D); break;
+    }
     return 0;
 }

@@ -16,12 +16,12 @@ import numpy as np
 from ._lib import FRKError, call, c_i64, vp
 from .runtime import Device, get_device
 
-FRK_REAL_LINE, FRK_PLANE, FRK_SPHERE = 1, 2, 3
+FRK_REAL_LINE, FRK_PLANE, FRK_SPHERE, FRK_STPLANE, FRK_STSPHERE = 1, 2, 3, 4, 5
 
 
 @dataclass(frozen=True)
 class Manifold:
-    """real_line() / plane() / sphere(radius)  (R/geometryfns.R:19-189).
+    """real_line() / plane() / sphere(radius) / STplane() / STsphere(radius)  (R/geometryfns.R:19-189).
 
     Only the built-in measures exist on the device; a custom ``measure@dist`` has no CUDA
     kernel and is refused (north_star: no CPU fallback)."""
@@ -30,11 +30,12 @@ class Manifold:
 
     @property
     def dim(self) -> int:
-        return 1 if self.kind == "real_line" else 2
+        return {"real_line": 1, "plane": 2, "sphere": 2, "STplane": 3, "STsphere": 3}[self.kind]
 
     @property
     def code(self) -> int:
-        return {"real_line": FRK_REAL_LINE, "plane": FRK_PLANE, "sphere": FRK_SPHERE}[self.kind]
+        return {"real_line": FRK_REAL_LINE, "plane": FRK_PLANE, "sphere": FRK_SPHERE,
+                "STplane": FRK_STPLANE, "STsphere": FRK_STSPHERE}[self.kind]
 
 
 def real_line() -> Manifold:
@@ -52,12 +53,29 @@ def sphere(radius: float = 6371.0) -> Manifold:
     return Manifold("sphere", float(radius))
 
 
+def STplane() -> Manifold:
+    """STplane(): plane x time with Euclid_dist(dim=3L), R/geometryfns.R:60-80."""
+    return Manifold("STplane")
+
+
+def STsphere(radius: float = 6371.0) -> Manifold:
+    """STsphere(radius=6371): measure gc_dist_time, R/geometryfns.R:120-134,181-189."""
+    if not radius > 0:
+        raise ValueError("radius needs to be positive")
+    return Manifold("STsphere", float(radius))
+
+
 def host_distance(m: Manifold, x1: np.ndarray, x2: np.ndarray) -> np.ndarray:
     """distance(manifold, x1, x2) for r-sized inputs (basis placement, BuildD); the reference keeps
     these on the host as well (R/basisfns.R:485-490,1131-1153).  Same operation order as
     distR / dist_sphere (R/geometryfns.R:202-219,1717-1740)."""
     x1 = np.asarray(x1, dtype=np.float64)
     x2 = np.asarray(x2, dtype=np.float64)
+    if m.kind == "STsphere":   # gc_dist_time: sqrt(spatdist^2 + tdist^2), R/geometryfns.R:181-189
+        sd = host_distance(Manifold("sphere", m.radius), x1[:, :2], x2[:, :2])
+        dt = x1[:, 2][:, None] - x2[:, 2][None, :]
+        td = np.sqrt(dt * dt)
+        return np.sqrt(sd * sd + td * td)
     if m.kind == "sphere":
         def normals(x):
             xr = (x * np.pi) / 180.0

@@ -48,7 +48,7 @@ typedef int (*frk_allreduce_fn)(void *user, double *buf, int64_t n, int on_devic
 typedef double (*frk_objective_fn)(void *user, int n, const double *x);
 
 /* manifold(): R/geometryfns.R:19-189 */
-enum { FRK_REAL_LINE = 1, FRK_PLANE = 2, FRK_SPHERE = 3 };
+enum { FRK_REAL_LINE = 1, FRK_PLANE = 2, FRK_SPHERE = 3, FRK_STPLANE = 4, FRK_STSPHERE = 5 };
 /* local_basis(type=): R/basisfns.R:99-146 */
 enum { FRK_BISQUARE = 0, FRK_GAUSSIAN = 1, FRK_EXP = 2, FRK_MATERN32 = 3 };
 

@@ -104,17 +104,20 @@ def gc_dist_time(x1: np.ndarray, x2: np.ndarray, R: Optional[float] = None) -> n
 
 @dataclass
 class Manifold:
-    """real_line / plane / sphere (R/geometryfns.R:19-189).  ``radius`` only for the sphere."""
-    kind: str                      # "real_line" | "plane" | "sphere"
+    """real_line / plane / sphere / STplane / STsphere (R/geometryfns.R:19-189).  ``radius`` only on spheres."""
+    kind: str                      # "real_line" | "plane" | "sphere" | "STplane" | "STsphere"
     radius: float = EARTH_RADIUS
 
     @property
     def dim(self) -> int:
-        return {"real_line": 1, "plane": 2, "sphere": 2}[self.kind]
+        return {"real_line": 1, "plane": 2, "sphere": 2, "STplane": 3, "STsphere": 3}[self.kind]
 
     def distance(self, x1, x2=None):
         if self.kind == "sphere":
             return dist_sphere(x1, x2, R=self.radius)
+        if self.kind == "STsphere":
+            x1 = np.asarray(x1, dtype=np.float64)
+            return gc_dist_time(x1, x1 if x2 is None else np.asarray(x2, dtype=np.float64), R=self.radius)
         return distR(x1, x2)
 
 
@@ -128,6 +131,16 @@ def plane():
 
 def sphere(radius: float = EARTH_RADIUS):
     return Manifold("sphere", radius)
+
+
+def STplane():
+    """plane x time, Euclid_dist(dim=3L) (R/geometryfns.R:60-80)."""
+    return Manifold("STplane")
+
+
+def STsphere(radius: float = EARTH_RADIUS):
+    """sphere x time, gc_dist_time (R/geometryfns.R:120-134)."""
+    return Manifold("STsphere", radius)
 
 # --------------------------------------------------------------------------
 # A.2 basis functions
@@ -279,7 +292,7 @@ def eval_basis_dense(basis: Basis, s: np.ndarray) -> np.ndarray:
     s = s[:, :d]
     n, r = s.shape[0], basis.n
     out = np.empty((n, r), dtype=np.float64)
-    if basis.manifold.kind == "sphere":
+    if basis.manifold.kind in ("sphere", "STsphere"):
         a1, a2, a3 = _unit_normals(s)
         b1, b2, b3 = _unit_normals(basis.loc)
         CH = 256
@@ -288,6 +301,10 @@ def eval_basis_dense(basis: Basis, s: np.ndarray) -> np.ndarray:
             delta = (a1[:, None] * b1[None, j0:j1] + a2[:, None] * b2[None, j0:j1]) + a3[:, None] * b3[None, j0:j1]
             delta = np.where(np.abs(delta) > 1.0, np.sign(delta), delta)
             y = basis.manifold.radius * np.arccos(delta)
+            if basis.manifold.kind == "STsphere":     # gc_dist_time, R/geometryfns.R:181-189
+                dt = s[:, 2][:, None] - basis.loc[None, j0:j1, 2]
+                td = np.sqrt(dt * dt)
+                y = np.sqrt(y * y + td * td)
             out[:, j0:j1] = basis_fn(basis.type, y, basis.scale[None, j0:j1])
         return out
     CH = 256

@@ -15,13 +15,15 @@
 }
 
 .frkb200_manifold <- function(m) {
+  ## STsphere does not inherit from sphere (nor STplane from plane) in FRK's class tree: test the ST classes first
+  if (is(m, "STplane")) 4L else if (is(m, "STsphere")) 5L else
   if (is(m, "real_line")) 1L else if (is(m, "plane")) 2L else if (is(m, "sphere")) 3L else
-    stop("frkb200: only real_line(), plane() and sphere() with their built-in measures are on the device path")
+    stop("frkb200: only real_line(), plane(), sphere(), STplane() and STsphere() with their built-in measures are on the device path")
 }
 
 .frkb200_handle <- function(basis) {
   .Call("frkb200_basis_create", .frkb200_manifold(basis@manifold),
-        if (is(basis@manifold, "sphere")) basis@manifold@radius else 0,
+        if (is(basis@manifold, "sphere") || is(basis@manifold, "STsphere")) basis@manifold@radius else 0,
         .frkb200_basis_type(basis@fn[[1]]), as.matrix(basis@df[, seq_len(dimensions(basis@manifold)), drop = FALSE]),
         as.numeric(basis@df$scale), as.integer(basis@df$res))
 }

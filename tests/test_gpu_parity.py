@@ -14,7 +14,8 @@ RTOL = 1e-9
 
 
 def _mk_basis(F, ob):
-    man = {"plane": F.plane(), "real_line": F.real_line(), "sphere": F.sphere(ob.manifold.radius)}[ob.manifold.kind]
+    man = {"plane": F.plane(), "real_line": F.real_line(), "sphere": F.sphere(ob.manifold.radius),
+           "STplane": F.STplane(), "STsphere": F.STsphere(ob.manifold.radius)}[ob.manifold.kind]
     return F.Basis(man, ob.loc.copy(), ob.scale.copy(), ob.res.copy(), ob.type, ob.regular)
 
 
@@ -81,6 +82,56 @@ def test_eval_basis_sphere(dev, btype):
         vals = np.maximum(abs(S_o[bad.row, bad.col]).A1, abs(S_g[bad.row, bad.col]).A1)
         assert vals.max() < 1e-20, "pattern differs away from the support edge"
     np.testing.assert_allclose(S_g.toarray(), S_o.toarray(), rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("btype", ["bisquare", "Gaussian"])
+def test_eval_basis_STplane(dev, btype):
+    """local_basis(STplane()): Euclid_dist(dim=3L) = distR over (x, y, t) -- +,-,*,sqrt only, so bit-exact for bisquare."""
+    import frk_b200 as F
+    rng = np.random.default_rng(21)
+    s = np.column_stack([rng.uniform(0, 10, 3000), rng.uniform(0, 5, 3000), rng.uniform(0, 30, 3000)])
+    gx, gy, gt = np.meshgrid(np.linspace(0, 10, 9), np.linspace(0, 5, 5), np.linspace(0, 30, 7), indexing="ij")
+    loc = np.column_stack([gx.ravel(), gy.ravel(), gt.ravel()])
+    loc = np.vstack([loc, loc[::7] + 0.3])                        # a second, coarser "resolution" with a larger support
+    scale = np.concatenate([np.full(315, 2.5), np.full(45, 6.0)])
+    res = np.concatenate([np.full(315, 2), np.full(45, 1)])
+    ob = O.local_basis(O.STplane(), loc, scale, btype, res=res)
+    s = np.vstack([s, loc[:5], loc[:3] + [2.5, 0, 0]])           # centroids and points exactly on a support edge
+    S_o = O.eval_basis(ob, s).tocsr()
+    S_g = F.eval_basis(_mk_basis(F, ob), s, dev)
+    assert _same_pattern(S_o, S_g)
+    if btype == "bisquare":
+        assert np.array_equal(S_o.data, S_g.data)
+    else:
+        np.testing.assert_allclose(S_g.data, S_o.data, rtol=RTOL, atol=0)
+
+
+def test_eval_basis_STsphere(dev):
+    """local_basis(STsphere()): gc_dist_time = sqrt(gc^2 + dt^2), R/geometryfns.R:181-189."""
+    import frk_b200 as F
+    ll, _ = sphere_points(3000, seed=12)
+    rng = np.random.default_rng(13)
+    s = np.column_stack([ll, rng.uniform(0, 10, ll.shape[0])])
+    cent = pseudo_isea3h()[2]
+    loc = np.vstack([np.column_stack([cent, np.full(len(cent), t)]) for t in (1.0, 5.0, 9.0)])
+    ob = O.local_basis(O.STsphere(), loc, np.full(loc.shape[0], 2500.0), "bisquare")
+    s = np.vstack([s, loc[:4], [[0.0, 90.0, 5.0], [180.0, 0.0, 1.0], [-180.0, 0.0, 9.0]]])
+    S_o = O.eval_basis(ob, s).tocsr()
+    S_g = F.eval_basis(_mk_basis(F, ob), s, dev)
+    if not _same_pattern(S_o, S_g):           # libm vs CUDA acos: only exact ties on the support edge may flip
+        bad = abs((S_o != 0).astype(int) - (S_g != 0).astype(int)).tocoo()
+        vals = np.maximum(abs(S_o[bad.row, bad.col]).A1, abs(S_g[bad.row, bad.col]).A1)
+        assert vals.max() < 1e-20, "pattern differs away from the support edge"
+    assert S_g.nnz > 0
+    np.testing.assert_allclose(S_g.toarray(), S_o.toarray(), rtol=1e-9, atol=1e-13)
+    # KAT-3 through the device distance kernel: unit sphere, (-90,0,0) <-> (90,0,2) is sqrt(pi^2 + 2^2)  (test_domains.R:32-36)
+    kb = F.local_basis(F.STsphere(1.0), np.array([[-90.0, 0.0, 0.0], [90.0, 0.0, 2.0]]), [1.0, 1.0])
+    from frk_b200._lib import call
+    idx, dD = dev.upload(np.array([0, 1], dtype=np.int32)), dev.empty(4, "f8")
+    call("frk_basis_dist_matrix", dev.ctx, kb.handle(dev), 2, dev.ptr(idx), dev.ptr(dD))
+    D = dev.download(dD).reshape(2, 2)
+    assert abs(D[0, 1] - np.sqrt(np.pi ** 2 + 4.0)) <= 2e-15 and D[0, 1] == D[1, 0] and D[0, 0] == 0.0
+    np.testing.assert_allclose(D, F.BuildD(kb)[0], rtol=0, atol=2e-15)
 
 
 def test_tensor_basis(dev):

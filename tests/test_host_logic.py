@@ -95,3 +95,22 @@ def test_SRE_argument_checks_run_before_any_device_work():
         F.SRE("z ~ 1", data, basis, gb, est_error=False, K_type="precision")
     with pytest.raises(F.FRKError, match="no CPU fallback"):       # no device -> loud failure, never a CPU path
         F.SRE("z ~ 1", data, basis, gb, est_error=False)
+
+
+def test_space_time_manifolds():
+    """dimensions(STplane()) == dimensions(STsphere()) == 3 (test_domains.R:10-11); unit-sphere space-time distance
+    (-90,0,0) <-> (90,0,2) is sqrt(pi^2 + 2^2) (test_domains.R:32-36) through the host mirror used by BuildD."""
+    import math
+    import frk_b200 as F
+    from frk_b200.geometry import host_distance
+    assert F.STplane().dim == 3 and F.STsphere().dim == 3
+    x = np.array([[-90.0, 0.0, 0.0], [90.0, 0.0, 2.0]])
+    assert host_distance(F.STsphere(1.0), x, x)[0, 1] == math.sqrt(math.pi ** 2 + 2 ** 2)
+    y = np.array([[0.0, 0.0, 0.0], [1.0, 2.0, 2.0]])
+    assert host_distance(F.STplane(), y, y)[0, 1] == 3.0
+    with pytest.raises(ValueError, match="number of columns in loc"):
+        F.local_basis(F.STplane(), np.zeros((2, 2)), [1.0, 1.0])
+    with pytest.raises(F.FRKError, match="space-time manifold"):
+        F.auto_basis(F.STplane(), y)
+    with pytest.raises(ValueError):
+        F.STsphere(-1.0)
