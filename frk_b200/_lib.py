@@ -64,6 +64,7 @@ SIGNATURES = {
     "frk_csr_tensor_count": (c_int, [vp, c_i64, vp, vp, vp, p_i64]),
     "frk_csr_tensor_fill": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_csr_row_normalise": (c_int, [vp, c_i64, vp, vp]),
+    "frk_st_bau_index": (c_int, [vp, c_i64, vp, vp, c_int, vp, c_i64, c_i64, c_i64, vp]),
     "frk_grid_lookup": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, vp]),
     "frk_grid_lookup_range": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, c_int, c_int, c_int, vp]),
     "frk_polygons_create": (c_int, [vp, c_int, vp, vp, vp, C.POINTER(vp)]),

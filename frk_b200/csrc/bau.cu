@@ -46,6 +46,48 @@ extern "C" int frk_grid_lookup_range(frk_ctx *ctx, int64_t n, const double *d_xy
 }
 
 // ---------------------------------------------------------------------------------
+// map_data_to_BAUs(ST) R/geometryfns.R:1419-1547: time slice i holds the data with t1_i <= time < t1_{i+1}; the last slice takes
+// everything from its start on (:1462-1468); each slice is then binned in space.  With the ST BAUs ordered space-fastest
+// (auto_BAUs, :979-980) that is one combined index  bau = spatial + ns * slice.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) st_bau_index_kernel(int64_t n, const int *__restrict__ sp, const double *__restrict__ t, int nt,
+                                                           const double *__restrict__ brk, int64_t ns, int64_t lo, int64_t hi,
+                                                           int *__restrict__ bau) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ti = t[i];
+        const int s = sp[i];
+        int out = -1;
+        if (s >= 0 && ti >= __ldg(brk)) {            // NaN and times before the first interval -> NA
+            int a = 0, b = nt;                       // largest a with brk[a] <= ti
+            while (b - a > 1) {
+                int mid = (a + b) >> 1;
+                if (__ldg(brk + mid) <= ti) a = mid; else b = mid;
+            }
+            const int64_t g = (int64_t)s + ns * a;
+            if (g >= lo && g < hi) out = (int)(g - lo);
+        }
+        bau[i] = out;
+    }
+}
+
+extern "C" int frk_st_bau_index(frk_ctx *ctx, int64_t n, const int *d_spatial, const double *d_time, int nt, const double *h_breaks,
+                                int64_t ns, int64_t bau_lo, int64_t bau_hi, int *d_bau) {
+    FRK_REQUIRE(ctx && h_breaks && d_bau && (n == 0 || (d_spatial && d_time)), "frk_st_bau_index: NULL argument");
+    FRK_REQUIRE(nt > 0 && ns > 0, "frk_st_bau_index: need at least one time interval and one spatial BAU");
+    FRK_REQUIRE(ns * (int64_t)nt < 2147483647LL, "frk_st_bau_index: too many space-time BAUs for int32");
+    for (int k = 1; k < nt; k++) FRK_REQUIRE(h_breaks[k] > h_breaks[k - 1], "frk_st_bau_index: interval starts must be increasing");
+    if (n == 0) return 0;
+    double *d_brk = nullptr;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&d_brk, nt * sizeof(double), ctx->stream));
+    // pageable source: the copy is staged before the call returns, so h_breaks may be freed by the caller
+    FRK_CHECK_CUDA(cudaMemcpyAsync(d_brk, h_breaks, nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, st_bau_index_kernel, grid, 256, 0, n, d_spatial, d_time, nt, d_brk, ns, bau_lo, bau_hi, d_bau);
+    cudaFreeAsync(d_brk, ctx->stream);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // binning: deterministic counting sort by BAU, then per-BAU mean in ascending point order
 // ---------------------------------------------------------------------------------
 __global__ void bin_count_kernel(int64_t n, const int *__restrict__ bau, int *__restrict__ cnt) {

@@ -217,6 +217,45 @@ class PolygonBAUs(PointBAUs):
             pass
 
 
+@dataclass
+class STBAUs:
+    """STFDF BAUs: ``spatial`` BAUs (grid, polygon or point) x ``times`` (ascending interval starts, numeric), space running
+    fastest -- auto_BAUs(STplane()/STsphere()), R/geometryfns.R:871-991.  BAU row i is spatial BAU ``i % ns`` in time interval
+    ``i // ns``; its time coordinate for eval_basis is the reference's ``t = rep(1:nt, each = ns)`` (:974-975)."""
+    spatial: object
+    times: np.ndarray
+    fields: Dict[str, np.ndarray] = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.times = np.ascontiguousarray(self.times, dtype=np.float64)
+        if self.times.ndim != 1 or len(self.times) == 0 or np.any(np.diff(self.times) <= 0):
+            raise ValueError("times needs to be a non-empty increasing vector of interval starts")
+
+    @property
+    def ns(self):
+        return len(self.spatial)
+
+    @property
+    def nt(self):
+        return len(self.times)
+
+    def __len__(self):
+        return self.ns * self.nt
+
+    def centroids(self, lo: int = 0, hi: Optional[int] = None) -> np.ndarray:
+        hi = len(self) if hi is None else hi
+        idx = np.arange(lo, hi)
+        sp_i = idx % self.ns
+        cs = self.spatial.centroids()
+        return np.column_stack([cs[sp_i], (idx // self.ns + 1).astype(np.float64)])
+
+    def __setitem__(self, k, v):
+        self.fields[k] = np.broadcast_to(np.asarray(v, dtype=np.float64), (len(self),)).copy()
+
+    def __getitem__(self, k):
+        return self.fields[k]
+
+
 def _seq_by(a: float, b: float, by: float) -> np.ndarray:
     n = int(math.floor((b - a) / by + 1e-10))        # seq.default(from, to, by)
     return a + np.arange(n + 1, dtype=np.float64) * by
@@ -268,6 +307,21 @@ def map_data_to_BAUs(data: SpatialPointsDataFrame, BAUs, columns, dev: Optional[
     ncols = len(columns)
     nbau = len(BAUs)
     lo, hi = (0, nbau) if row_range is None else row_range
+    if isinstance(BAUs, STBAUs):
+        # every time slice binned in space (R/geometryfns.R:1419-1547): spatial lookup over all spatial BAUs, then the combined index
+        if data.coords.shape[1] < 3:
+            raise ValueError("space-time BAUs need data coordinates (x, y, time)")
+        d_bau = _spatial_lookup(dev, data, BAUs.spatial, n, 0, BAUs.ns)
+        d_t = dev.upload(data.coords[:, 2])
+        call("frk_st_bau_index", dev.ctx, n, dev.ptr(d_bau), dev.ptr(d_t), BAUs.nt, vp(BAUs.times.ctypes.data), BAUs.ns,
+             int(lo), int(hi), dev.ptr(d_bau))
+    else:
+        d_bau = _spatial_lookup(dev, data, BAUs, n, lo, hi)
+    return _bin(dev, data, columns, d_bau, n, ncols, lo, hi)
+
+
+def _spatial_lookup(dev, data, BAUs, n, lo, hi):
+    """per-point BAU row in [lo, hi) relative to lo, -1 = NA (sp::over, R/geometryfns.R:1266)."""
     if isinstance(BAUs, GridBAUs):
         d_xy = dev.upload(data.coords[:, :2])
         d_bau = dev.empty(max(n, 1), "i4")
@@ -286,6 +340,11 @@ def map_data_to_BAUs(data: SpatialPointsDataFrame, BAUs, columns, dev: Optional[
         b = np.asarray(data.data["bau"]).astype(np.int64)
         b = np.where((b >= lo) & (b < hi), b - lo, -1)     # host: the lookup itself was done on the host
         d_bau = dev.upload(b.astype(np.int32))
+    return d_bau
+
+
+def _bin(dev, data, columns, d_bau, n, ncols, lo, hi):
+    """group_by(BAU) %>% summarise_all(mean), R/geometryfns.R:1286-1302."""
     d_vals = dev.empty(max(n * ncols, 1))                          # n x ncols column-major, one H2D per column (no host-side stacking)
     for k, c in enumerate(columns):
         colv = np.ascontiguousarray(data.data[c], dtype=np.float64)

@@ -136,6 +136,13 @@ int frk_polygons_create(frk_ctx *ctx, int npoly, const int *h_ptr, const double 
 int frk_polygons_destroy(frk_polygons *P);
 int frk_polygon_lookup(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy,
                        int bau_lo, int bau_hi, int *d_bau);
+/* map_data_to_BAUs(ST): R/geometryfns.R:1419-1547.  Space-time BAUs are ns spatial BAUs x nt time intervals, space fastest
+ * (auto_BAUs, R/geometryfns.R:971-980); h_breaks[nt] are the interval starts time(sp_pols).  d_spatial[n] is the per-point
+ * spatial BAU (from frk_grid_lookup / frk_polygon_lookup, -1 = NA), d_time[n] the observation times in the units of h_breaks.
+ * Slice i takes t1_i <= time < t1_{i+1}; the last slice takes every time >= its start (:1462-1468); earlier than the first
+ * start -> NA.  d_bau = spatial + ns*slice, restricted to [bau_lo, bau_hi) and relative to bau_lo (may alias d_spatial).  */
+int frk_st_bau_index(frk_ctx *ctx, int64_t n, const int *d_spatial, const double *d_time, int nt, const double *h_breaks,
+                     int64_t ns, int64_t bau_lo, int64_t bau_hi, int *d_bau);
 /* group_by(BAU) %>% summarise_all(mean): R/geometryfns.R:1286-1302.  d_vals: n x ncols
  * column-major (ld n).  Outputs (capacity n rows): d_obs_bau[m] ascending BAU rows,
  * d_means m x ncols column-major with leading dimension n, d_counts[m].  Returns m.

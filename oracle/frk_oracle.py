@@ -601,6 +601,23 @@ def points_to_polygon_BAUs(xy: np.ndarray, ptr: np.ndarray, vx: np.ndarray, vy: 
     return out
 
 
+def st_bau_index(spatial: np.ndarray, time: np.ndarray, breaks: np.ndarray, ns: int) -> np.ndarray:
+    """map_data_to_BAUs(ST), R/geometryfns.R:1419-1547: for BAU time point i the data with
+    ``time >= t1 & time < t2`` (t2 = next BAU time; for the last one t2 = last(endTime) + 1, i.e. everything from t1 on,
+    :1455-1470) are binned in space; ST BAUs are numbered space-fastest (:971-980).  Plain loop over the time points, as in
+    the reference's lapply."""
+    spatial = np.asarray(spatial, dtype=np.int64)
+    time = np.asarray(time, dtype=np.float64)
+    out = np.full(time.shape[0], -1, dtype=np.int64)
+    nt = len(breaks)
+    for i in range(nt):
+        t1 = breaks[i]
+        sel = (time >= t1) & (time < breaks[i + 1]) if i < nt - 1 else (time >= t1)
+        sel &= spatial >= 0
+        out[sel] = spatial[sel] + ns * i
+    return out.astype(np.int32)
+
+
 def bin_mean(bau: np.ndarray, cols: np.ndarray):
     """map_data_to_BAUs: drop NA, group by BAU, mean of every numeric column
     (R/geometryfns.R:1277-1302).  Rows are returned in ascending BAU index (the reference

@@ -440,13 +440,54 @@ def test_config4_noaa_spacetime_tensor_basis(dev):
     np.testing.assert_allclose(pg["var"], po[1], rtol=1e-7)
     # block-exponential K for the tensor basis: kronecker(time, space) blocks, 2-D Nelder-Mead per resolution (R/SREfit.R:496-514)
     Mo2 = O.SRE(ot, cen, np.ones(len(cen)), uo, means[:, 0], means[:, 1], K_type="block-exponential")
-    Mg2 = F.SRE("z ~ 1", data, gtb, baus, est_error=False, K_type="block-exponential")
+    # ... and through the space-time BAU container: grid lookup + time slicing on the device instead of the precomputed index
+    stb = F.STBAUs(F.GridBAUs(gx, gy, np.array([1.0, 1.0])), gt)
+    stb["fs"] = 1.0
+    assert len(stb) == len(cen) and np.array_equal(stb.centroids(), cen)
+    data2 = F.SpatialPointsDataFrame(xyt, {"z": n["z"], "std": np.full(len(bau), 2.0)})
+    Mg2 = F.SRE("z ~ 1", data2, gtb, stb, est_error=False, K_type="block-exponential")
+    assert np.array_equal(dev.download(Mg2.obs_bau, Mg2.m), uo)
     O.SRE_fit(Mo2, n_EM=3, tol=0.0)
     F.SRE_fit(Mg2, n_EM=3, tol=0.0)
     np.testing.assert_allclose(Mg2.info_fit["llk"], Mo2.info_fit["llk"], rtol=RTOL)
     np.testing.assert_allclose(Mg2.info_fit["tau"], np.concatenate(Mo2.info_fit["tau"]), rtol=1e-6)
     np.testing.assert_allclose(Mg2.get("Khat"), Mo2.Khat, rtol=1e-6, atol=1e-9 * abs(Mo2.Khat).max())
     np.testing.assert_allclose(F.predict(Mg2, obs_fs=False)["var"], O.predict(Mo2, obs_fs=False)[1], rtol=1e-6)
+
+
+def test_map_data_to_ST_BAUs(dev):
+    """map_data_to_BAUs(ST) (R/geometryfns.R:1419-1547): irregular interval starts, observations before the first start (NA), on an
+    interval boundary (belongs to the later slice), after the last start (lumped into the last slice), outside the spatial grid
+    (NA); row-partitioned ranges reproduce the same table piecewise.  Index work: bit-exact."""
+    import frk_b200 as F
+    rng = np.random.default_rng(31)
+    nobs = 20000
+    xy = rng.uniform(-0.2, 1.2, (nobs, 2))
+    brk = np.array([0.0, 1.0, 2.5, 2.75, 7.0, 11.0])
+    t = rng.uniform(-1.0, 15.0, nobs)
+    t[:len(brk)] = brk                                             # exactly on the boundaries
+    t[len(brk)] = np.nextafter(brk[2], -np.inf)
+    z = rng.standard_normal(nobs)
+    grid = F.GridBAUs(np.linspace(0.025, 0.975, 20), np.linspace(0.05, 0.95, 10), np.array([0.05, 0.1]))
+    stb = F.STBAUs(grid, brk)
+    sp_idx = O.points_to_BAUs(xy, O.GridBAUs(grid.xgrid, grid.ygrid, np.asarray(grid.cellsize)))
+    want = O.st_bau_index(sp_idx, t, brk, len(grid))
+    assert (want < 0).any() and (want >= len(grid) * (len(brk) - 1)).any()
+    data = F.SpatialPointsDataFrame(np.column_stack([xy, t]), {"z": z})
+    out = F.map_data_to_BAUs(data, stb, ["z"], dev)
+    assert np.array_equal(dev.download(out["bau"], nobs), want)
+    uo, means, cnt = O.bin_mean(want, z)
+    assert out["m"] == len(uo) and np.array_equal(dev.download(out["obs_bau"], out["m"]), uo)
+    assert np.array_equal(dev.download(out["counts"], out["m"]), cnt)
+    np.testing.assert_allclose(dev.download(out["means"], out["m"]), means[:, 0], rtol=1e-12, atol=1e-15)
+    # two row ranges (the multi-GPU partition) give the same table in pieces
+    cut = len(stb) // 2 + 7
+    a = F.map_data_to_BAUs(data, stb, ["z"], dev, row_range=(0, cut))
+    b = F.map_data_to_BAUs(data, stb, ["z"], dev, row_range=(cut, len(stb)))
+    both = np.concatenate([dev.download(a["obs_bau"], a["m"]), dev.download(b["obs_bau"], b["m"]) + cut])
+    assert np.array_equal(both, uo)
+    with pytest.raises(ValueError, match="increasing"):
+        F.STBAUs(grid, [0.0, 0.0, 1.0])
 
 
 def test_fit_options_and_slot_roundtrip(dev):
