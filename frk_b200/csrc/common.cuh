@@ -17,6 +17,7 @@ struct frk_prof_stat { int64_t launches = 0; double ms = 0, flops = 0, bytes = 0
 struct frk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = false;             // lane contexts (frk_ctx_create_lane) own their main stream
     cudaStream_t stream2 = nullptr;      // side stream: the bulk of potrf's inner update runs beside the next diagonal factorisation
     cudaStream_t stream3 = nullptr;      // second side stream: the rest of the trailing SYRK overlaps the whole next panel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_panel = nullptr, ev_next = nullptr, ev_rest[2] = {nullptr, nullptr};
@@ -79,6 +80,10 @@ void frk_set_error(const char *fmt, ...);
 #define FRK_WORK(ctx, fl, by) do { (ctx)->next_flops = (double)(fl); (ctx)->next_bytes = (double)(by); } while (0)
 
 int frk_scratch(frk_ctx *ctx, size_t bytes, void **out);   // grow-only scratch buffer
+
+// a second context on the parent's device with its own streams, events, staging and graph cache: independent work (e.g. the
+// speculative Nelder-Mead evaluations of one M-step) is enqueued on lanes and runs concurrently with the parent's stream
+int frk_ctx_create_lane(const frk_ctx *parent, frk_ctx **out);
 
 // exclusive scan of int32 counts[n] -> out[n+1] (out[n] = total); total also returned to host
 int frk_exclusive_scan_i32(frk_ctx *ctx, const int *d_in, int64_t n, int *d_out, int64_t *h_total);

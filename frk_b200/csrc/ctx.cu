@@ -56,6 +56,22 @@ extern "C" int frk_ctx_create(int device, void *stream, frk_ctx **out) {
     return 0;
 }
 
+int frk_ctx_create_lane(const frk_ctx *parent, frk_ctx **out) {
+    FRK_REQUIRE(parent && out, "frk_ctx_create_lane: NULL argument");
+    FRK_CHECK_CUDA(cudaSetDevice(parent->device));
+    // a lane's main stream carries the critical path of its factorisations (potf2 / trsm chain): highest priority, like stream2
+    cudaStream_t s = nullptr;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    FRK_CHECK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));
+    frk_ctx *c = nullptr;
+    if (int rc = frk_ctx_create(parent->device, (void *)s, &c)) { cudaStreamDestroy(s); return rc; }
+    c->own_stream = true;
+    c->use_graphs = parent->use_graphs;
+    *out = c;
+    return 0;
+}
+
 extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
@@ -74,6 +90,7 @@ extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_small) cudaFree(ctx->d_small);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
 }

@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <functional>
 #include <limits>
+#include <string>
+#include <thread>
 
 namespace {
 
@@ -61,13 +63,19 @@ struct frk_model {
     double *Dt = nullptr;          // nt x nt temporal distances (tensor bases)
     double Dt01 = 0.0;
     std::vector<double> taus, omegas;
-    double nm_requests = 0, nm_rounds = 0, nm_evals = 0;   // Nelder-Mead statistics of the last M-step (distinct points asked, batches, points evaluated)
+    double nm_requests = 0, nm_rounds = 0, nm_evals = 0, nm_reevals = 0;   // Nelder-Mead statistics of the last M-step (distinct points asked, batches, points evaluated)
     // multi-rank reduction hook
     int rank = 0, world = 1;
     bool spec_emulate = false;     // evaluate every speculative candidate on this rank (single-GPU test of the multi-rank logic)
     frk_allreduce_fn allreduce = nullptr;
     void *user = nullptr;
     std::vector<void *> allocs;
+    // lanes: extra contexts on this GPU that evaluate speculative Nelder-Mead candidates concurrently (a factorisation is latency
+    // bound and fills a fraction of the SMs, so a few of them side by side cost little more than one)
+    int lanes = 1;
+    struct Lane { frk_ctx *ctx = nullptr; double *Ki = nullptr, *Kinv = nullptr, *work = nullptr; size_t cap = 0; };
+    std::vector<Lane> lane;          // lane[0] is unused (the model's own context and block buffers)
+    cudaEvent_t ev_lane = nullptr;
 };
 
 namespace {
@@ -336,10 +344,15 @@ int zeroin(const std::function<int(double, double &)> &f, double lower, double u
 // ---------------------------------------------------------------------------------
 struct SpecNM {
     frk_model *M;
-    std::function<int(const double *, double &)> eval;      // evaluates on THIS rank (and tracks the rank-local best)
+    // evaluates nb <= lanes points on THIS rank, concurrently on the lanes (and tracks the rank-local best)
+    std::function<int(int nb, const double *const *, double *)> eval;
     int dim, maxit;
     double reltol;
     std::vector<double> par0;
+    int lanes = 1;
+    // called for every point Nelder-Mead actually asks for (cache hit or not), in request order: the caller keeps the by-products
+    // (inverse, log-determinant) of the best REQUESTED point -- a speculative point that is never requested cannot be the result
+    std::function<int(const double *, double)> requested;
     std::vector<std::vector<double>> pts;
     std::vector<double> fv;
     std::vector<int> owner;
@@ -403,31 +416,37 @@ struct SpecNM {
     int operator()(const double *x, double &f) {
         int i = find(x);
         M->nm_requests += 1;
-        if (i >= 0) { f = fv[i]; return 0; }
+        if (i >= 0) { f = fv[i]; return requested ? requested(x, f) : 0; }
         M->nm_rounds += 1;
         static const bool dbg = getenv("FRK_SPEC_DEBUG") != nullptr;
-        const int W = M->spec_emulate ? std::max(M->world, 1) : M->world;
+        // candidate k goes to rank k % world (the likeliest ones spread over the GPUs first), lane k / world
+        const int world = std::max(M->world, 1);
+        const int L = std::max(lanes, 1), W = world * L;
         std::vector<std::vector<double>> batch = {std::vector<double>(x, x + dim)};
         if (W > 1) candidates(x, (size_t)W, batch);
         std::vector<double> fl(batch.size(), 0.0);
-        for (size_t k = 0; k < batch.size(); k++) {
-            if (M->spec_emulate || W == 1 || (int)k == M->rank) {
-                double v;
-                RC(eval(batch[k].data(), v));
-                fl[k] = v;
-            }
+        std::vector<size_t> mine;
+        for (size_t k = 0; k < batch.size(); k++)
+            if (M->spec_emulate || (int)(k % world) == M->rank) mine.push_back(k);
+        for (size_t c0 = 0; c0 < mine.size(); c0 += (size_t)L) {
+            const int nb = (int)std::min<size_t>((size_t)L, mine.size() - c0);
+            const double *ptsv[16];
+            double fvv[16];
+            for (int j = 0; j < nb; j++) ptsv[j] = batch[mine[c0 + j]].data();
+            RC(eval(nb, ptsv, fvv));
+            for (int j = 0; j < nb; j++) fl[mine[c0 + j]] = fvv[j];
         }
-        if (W > 1 && !M->spec_emulate) RC(reduce_host(M, fl.data(), (int64_t)fl.size(), 0));
+        if (world > 1 && !M->spec_emulate) RC(reduce_host(M, fl.data(), (int64_t)fl.size(), 0));
         if (dbg && M->rank == 0) {
             fprintf(stderr, "[spec] miss at %.10g (known %zu) batch:", x[0], pts.size());
             for (size_t k = 0; k < batch.size(); k++) fprintf(stderr, " %.10g->%.8g", batch[k][0], fl[k]);
             fprintf(stderr, "\n");
         }
-        for (size_t k = 0; k < batch.size(); k++) { pts.push_back(batch[k]); fv.push_back(fl[k]); owner.push_back((int)k); }
+        for (size_t k = 0; k < batch.size(); k++) { pts.push_back(batch[k]); fv.push_back(fl[k]); owner.push_back((int)(k % world)); }
         M->nm_evals += (double)batch.size();
         i = find(x);
         f = fv[i];
-        return 0;
+        return requested ? requested(x, f) : 0;
     }
 };
 
@@ -477,6 +496,27 @@ int chol2inv_logdet(frk_ctx *ctx, int n, double *A, double *Ainv, double *work, 
     return frk_potri(ctx, n, A, Ainv, work);
 }
 
+// lane contexts and their n x n work buffers (created on first use, grown to the largest block)
+int prepare_lanes(frk_model *M, size_t nn) {
+    if ((int)M->lane.size() < M->lanes) M->lane.resize(M->lanes);
+    if (!M->ev_lane) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_lane, cudaEventDisableTiming));
+    for (int l = 1; l < M->lanes; l++) {
+        frk_model::Lane &ln = M->lane[l];
+        if (!ln.ctx) RC(frk_ctx_create_lane(M->ctx, &ln.ctx));
+        if (ln.cap < nn) {
+            for (double **p : {&ln.Ki, &ln.Kinv, &ln.work}) {
+                if (*p) { FRK_CHECK_CUDA(cudaStreamSynchronize(ln.ctx->stream)); FRK_CHECK_CUDA(cudaFree(*p)); *p = nullptr; }
+                FRK_CHECK_CUDA(cudaMalloc((void **)p, nn * sizeof(double)));
+            }
+            ln.cap = nn;
+            // the graph cache is keyed by pointers: stale entries for the freed buffers must go
+            for (auto &kv : ln.ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
+            ln.ctx->graphs.clear();
+        }
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------
 // M-step
 // ---------------------------------------------------------------------------------
@@ -513,7 +553,7 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
     FRK_REQUIRE(!M->blocks.empty(), "K_type = \"block-exponential\" needs the per-resolution distance matrices (frk_model_set_blocks)");
     // K_new is assembled in w1 and K_new^-1 in w2 (both free here); the old Khat / Khat_inv are read for omega and the start values
     M->taus.clear(); M->omegas.clear();
-    M->nm_requests = M->nm_rounds = M->nm_evals = 0;
+    M->nm_requests = M->nm_rounds = M->nm_evals = M->nm_reevals = 0;
     double *Knew = M->w1, *Kinvnew = M->w2;
     FRK_CHECK_CUDA(cudaMemsetAsync(Knew, 0, rr * sizeof(double), ctx->stream));
     FRK_CHECK_CUDA(cudaMemsetAsync(Kinvnew, 0, rr * sizeof(double), ctx->stream));
@@ -570,7 +610,11 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
             if (!std::isfinite(p1) || p1 == 1e-9) p1 = 1.0;
             if (!std::isfinite(p0) || p0 == 1e-9) p0 = M->max_l / 10.0;
             NMResult nm;
-            SpecNM spec{M, f_tau2, 2, 100, 1e-4, std::vector<double>{p0, p1}};
+            auto f_tau2_batch = [&](int nb, const double *const *pts, double *fv) -> int {
+                for (int j = 0; j < nb; j++) RC(f_tau2(pts[j], fv[j]));
+                return 0;
+            };
+            SpecNM spec{M, f_tau2_batch, 2, 100, 1e-4, std::vector<double>{p0, p1}};
             RC(nmmin(std::ref(spec), spec.par0, nm, 100, 1e-4));
             M->taus.push_back(nm.x[0]); M->taus.push_back(nm.x[1]);
             const bool shared = M->world > 1 && !M->spec_emulate;
@@ -602,16 +646,63 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         // f_tau, :485-529.  The inverse and log-determinant at the best tau seen are kept: Nelder-Mead returns its lowest
         // vertex, i.e. an evaluated point, so K_i(tau*)^-1 and log|K_i(tau*)| need no further factorisation.
         double bestF = std::numeric_limits<double>::infinity(), bestTau = -1.0, bestLogdet = 0.0;
-        auto f_tau = [&](const double *tau, double &fval) -> int {
-            if (tau[0] <= 1e-10) { fval = std::numeric_limits<double>::infinity(); return 0; }
-            RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau[0], 1.0, B.Ki));
-            double logdetKi, t;
-            RC(chol2inv_logdet(ctx, ni, B.Ki, B.Kinv, B.work, &logdetKi));
-            RC(frk_dot(ctx, (int64_t)nn, B.Kinv, B.eta2, &t));
+        const int nlanes = ctx->profiling ? 1 : M->lanes;           // per-kernel profiling times one stream: keep everything on it
+        if (nlanes > 1) RC(prepare_lanes(M, nn));
+        // one evaluation on lane l (0 = this context and the block's own buffers); no shared state is written
+        auto f_tau_lane = [&](int l, double tau, double &fval, double &logdetKi) -> int {
+            if (tau <= 1e-10) { fval = std::numeric_limits<double>::infinity(); logdetKi = 0.0; return 0; }
+            frk_ctx *c = l ? M->lane[l].ctx : ctx;
+            double *Ki = l ? M->lane[l].Ki : B.Ki, *Kinv = l ? M->lane[l].Kinv : B.Kinv, *work = l ? M->lane[l].work : B.work;
+            double t;
+            RC(frk_exp_kernel(c, (int64_t)nn, B.D, tau, 1.0, Ki));
+            RC(chol2inv_logdet(c, ni, Ki, Kinv, work, &logdetKi));
+            RC(frk_dot(c, (int64_t)nn, Kinv, B.eta2, &t));
             fval = -(0.5 * (-logdetKi) - omega / 2.0 * t);
-            if (fval < bestF) {
-                bestF = fval; bestTau = tau[0]; bestLogdet = logdetKi;
-                FRK_CHECK_CUDA(cudaMemcpyAsync(B.KinvBest, B.Kinv, nn * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            return 0;
+        };
+        double lanePt[16], laneLd[16];                              // what each lane's Kinv buffer currently holds
+        bool laneValid[16] = {false};
+        auto f_tau = [&](int nb, const double *const *pts, double *fv) -> int {
+            double ldv[16];
+            int rcs[16] = {0};
+            std::string errs[16];
+            if (nb > 1) {
+                // the lanes start once this stream has produced eta2_i (and saved the best inverse so far out of their buffers)
+                FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));
+                for (int l = 1; l < nb; l++) FRK_CHECK_CUDA(cudaStreamWaitEvent(M->lane[l].ctx->stream, M->ev_lane, 0));
+                std::vector<std::thread> th;
+                for (int l = 1; l < nb; l++) {
+                    th.emplace_back([&, l]() {
+                        cudaSetDevice(ctx->device);               // the current device is per host thread
+                        rcs[l] = f_tau_lane(l, pts[l][0], fv[l], ldv[l]);
+                        if (rcs[l]) errs[l] = frk_last_error();   // the message is thread-local: carry it over
+                    });
+                }
+                rcs[0] = f_tau_lane(0, pts[0][0], fv[0], ldv[0]);
+                for (auto &t : th) t.join();
+                for (int l = 1; l < nb; l++) {
+                    ctx->launches += M->lane[l].ctx->launches;
+                    M->lane[l].ctx->launches = 0;
+                }
+                for (int l = 0; l < nb; l++)
+                    if (rcs[l]) { if (l) frk_set_error("%s", errs[l].c_str()); return rcs[l]; }
+            } else {
+                RC(f_tau_lane(0, pts[0][0], fv[0], ldv[0]));
+            }
+            for (int l = 0; l < nb; l++) { lanePt[l] = pts[l][0]; laneLd[l] = ldv[l]; laneValid[l] = std::isfinite(fv[l]); }
+            return 0;
+        };
+        // Nelder-Mead returns its lowest vertex, a REQUESTED point: keep the inverse of the best requested point while it is still
+        // in a lane buffer (every lane has been synchronised by its last frk_dot; the next batch starts after this copy)
+        auto on_request = [&](const double *x, double f) -> int {
+            if (!(f < bestF)) return 0;
+            bestF = f; bestTau = -1.0;
+            for (int l = 0; l < nlanes; l++) {
+                if (!laneValid[l] || lanePt[l] != x[0]) continue;
+                const double *src = l ? M->lane[l].Kinv : B.Kinv;
+                FRK_CHECK_CUDA(cudaMemcpyAsync(B.KinvBest, src, nn * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                bestTau = x[0]; bestLogdet = laneLd[l];
+                break;
             }
             return 0;
         };
@@ -622,17 +713,20 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         }
         if (!std::isfinite(par0) || par0 == 1e-9) par0 = M->max_l / 10.0;
         NMResult nm;
-        SpecNM spec{M, f_tau, 1, 100, 1e-4, std::vector<double>{par0}};
-        RC(nmmin(std::ref(spec), spec.par0, nm, 100, 1e-4));         // optim(): Nelder-Mead, :618-621 (candidates spread over the ranks)
+        SpecNM spec{M, f_tau, 1, 100, 1e-4, std::vector<double>{par0}, nlanes, on_request};
+        RC(nmmin(std::ref(spec), spec.par0, nm, 100, 1e-4));         // optim(): Nelder-Mead, :618-621 (candidates spread over ranks and lanes)
         const double tau = nm.x[0];
         M->taus.push_back(tau);
         const bool shared = M->world > 1 && !M->spec_emulate;
         const int own = shared ? spec.owner[spec.find(&tau)] : M->rank;
         if (own == M->rank) {
-            if (bestTau != tau) {                                    // ties only: re-evaluate so that KinvBest belongs to tau
+            if (bestTau != tau) {                                    // ties / unrequested speculative points: re-evaluate so that KinvBest belongs to tau
                 bestF = std::numeric_limits<double>::infinity();
                 double f;
-                RC(f_tau(&tau, f));
+                const double *pt = &tau;
+                RC(f_tau(1, &pt, &f));
+                RC(on_request(pt, f));
+                M->nm_reevals += 1;
                 FRK_REQUIRE(bestTau == tau, "block-exponential update: tau = %g cannot be evaluated", tau);
             }
         } else {
@@ -797,6 +891,13 @@ extern "C" int frk_model_destroy(frk_model *M) {
     cudaStreamSynchronize(M->ctx->stream);
     for (void *p : M->allocs) cudaFreeAsync(p, M->ctx->stream);
     frk_rowbuckets_destroy(M->bk);
+    for (auto &ln : M->lane) {
+        if (!ln.ctx) continue;
+        cudaStreamSynchronize(ln.ctx->stream);
+        for (double *p : {ln.Ki, ln.Kinv, ln.work}) if (p) cudaFree(p);
+        frk_ctx_destroy(ln.ctx);
+    }
+    if (M->ev_lane) cudaEventDestroy(M->ev_lane);
     delete M;
     return 0;
 }
@@ -807,6 +908,13 @@ extern "C" int frk_model_set_parallel(frk_model *M, int rank, int world, int emu
     FRK_REQUIRE(M && world >= 1 && rank >= 0 && rank < world, "frk_model_set_parallel: bad argument");
     FRK_REQUIRE(emulate || world == 1 || M->allreduce, "frk_model_set_parallel: world > 1 needs the all-reduce hook");
     M->rank = emulate ? 0 : rank; M->world = world; M->spec_emulate = emulate != 0;
+    return 0;
+}
+
+// number of concurrent evaluation lanes on this GPU for the block-exponential Nelder-Mead (1 = strictly sequential)
+extern "C" int frk_model_set_lanes(frk_model *M, int lanes) {
+    FRK_REQUIRE(M && lanes >= 1 && lanes <= 8, "frk_model_set_lanes: lanes must be in 1..8");
+    M->lanes = lanes;
     return 0;
 }
 
@@ -962,7 +1070,7 @@ extern "C" int frk_model_get(frk_model *M, const char *slot, double *h_out) {
     if (!strcmp(slot, "m_total")) { h_out[0] = M->m_total; return 0; }
     if (!strcmp(slot, "homoscedastic")) { h_out[0] = M->homoscedastic ? 1.0 : 0.0; return 0; }
     if (!strcmp(slot, "tau")) { for (size_t i = 0; i < M->taus.size(); i++) h_out[i] = M->taus[i]; return 0; }
-    if (!strcmp(slot, "nm_stats")) { h_out[0] = M->nm_requests; h_out[1] = M->nm_rounds; h_out[2] = M->nm_evals; return 0; }
+    if (!strcmp(slot, "nm_stats")) { h_out[0] = M->nm_requests; h_out[1] = M->nm_rounds; h_out[2] = M->nm_evals; h_out[3] = M->nm_reevals; return 0; }
     if (!strcmp(slot, "omega")) { for (size_t i = 0; i < M->omegas.size(); i++) h_out[i] = M->omegas[i]; return 0; }
     size_t n = 0;
     double *p = slot_ptr(M, slot, &n);

@@ -78,7 +78,7 @@ class SREModel:
     def get(self, name: str) -> np.ndarray:
         """Host copy of a slot (what the R shim writes back into the S4 object); r x r slots as (r, r) arrays."""
         n = {"mu_eta": self.r, "alphahat": self.p, "sigma2fshat": 1, "m_total": 1, "homoscedastic": 1,
-             "tau": 16, "omega": 16, "nm_stats": 3}.get(name, self.r * self.r)
+             "tau": 16, "omega": 16, "nm_stats": 4}.get(name, self.r * self.r)
         big = name in ("S_eta", "Q_eta", "Khat", "Khat_inv")
         out = self.dev.host_buffer(n) if big else np.zeros(n)       # pinned staging for the r x r slots
         call("frk_model_get", self.handle, name.encode(), vp(out.ctypes.data))
@@ -242,11 +242,19 @@ def loglik(mdl: SREModel) -> float:
 # ---------------------------------------------------------------------------------------
 
 def SRE_fit(mdl: SREModel, n_EM: int = 100, tol: float = 0.01, method: str = "EM", lambda_=0.0,
-            known_sigma2fs=None, print_lik: bool = False) -> SREModel:
+            known_sigma2fs=None, print_lik: bool = False, lanes: Optional[int] = None) -> SREModel:
     """SRE.fit(object, n_EM, tol, method = "EM", lambda, print_lik, known_sigma2fs), R/SREfit.R:3-160: one
-    ``frk_model_em_fit`` call.  Calling it again continues from the current slots, as in R."""
+    ``frk_model_em_fit`` call.  Calling it again continues from the current slots, as in R.
+
+    ``lanes`` (not in the reference): how many of the block-exponential Nelder-Mead's candidate points are factorised side by side
+    on this GPU (``frk_model_set_lanes``); the iterates and results are those of the sequential algorithm for any value.  Two
+    candidates per round is the measured optimum on B200 (more cost more than the rounds they save), so the default is 2 on one GPU
+    and 1 in a row-partitioned run, where the ranks already split the candidates."""
     if method != "EM":
         raise FRKError("only method = \"EM\" (Gaussian data, identity link) is on the device path")
+    if lanes is None:
+        lanes = 2 if mdl.dev.world == 1 else 1
+    call("frk_model_set_lanes", mdl.handle, int(lanes))
     t0 = time.time()
     lam = np.atleast_1d(np.asarray(lambda_, dtype=np.float64)).copy()
     res = np.ascontiguousarray(mdl.basis.res, dtype=np.int32)
@@ -267,7 +275,7 @@ def SRE_fit(mdl: SREModel, n_EM: int = 100, tol: float = 0.01, method: str = "EM
         ntau = nres * (2 if getattr(mdl, "_tensor", False) else 1)
         mdl.info_fit["tau"] = mdl.get("tau")[:ntau].tolist()
         mdl.info_fit["omega"] = mdl.get("omega")[:nres].tolist()
-        mdl.info_fit["nm_stats"] = dict(zip(("requests", "rounds", "evaluated"), mdl.get("nm_stats").tolist()))   # last M-step
+        mdl.info_fit["nm_stats"] = dict(zip(("requests", "rounds", "evaluated", "re_evaluated"), mdl.get("nm_stats").tolist()))   # last M-step
     return mdl
 
 

@@ -317,6 +317,11 @@ int frk_model_destroy(frk_model *mdl);
  * replicated r_i x r_i factorisation) are predicted ahead and spread over the ranks; the iterate path and all results are identical to
  * the sequential run.  emulate != 0 evaluates a pretend world's candidates on this one rank (for tests).                              */
 int frk_model_set_parallel(frk_model *mdl, int rank, int world, int emulate);
+/* Concurrent evaluation lanes on this GPU for the block-exponential Nelder-Mead of .update_K (R/SREfit.R:618-621): each f_tau
+ * evaluation is a latency-bound r_i x r_i factorisation, so up to `lanes` of the points Nelder-Mead may ask for next are evaluated
+ * side by side on separate streams (combined with the ranks of a row-partitioned run: world x lanes candidates per round).
+ * The sequence of iterates, hence every result, is that of the sequential algorithm.  Default 1.                                  */
+int frk_model_set_lanes(frk_model *mdl, int lanes);
 /* BuildD() (R/basisfns.R:1131-1153) for K_type = "block-exponential": h_res[r] 1-based resolution of every basis
  * function, h_D[i] the r_i x r_i centroid distance matrix of resolution i+1 (column-major, host).              */
 int frk_model_set_blocks(frk_model *mdl, int nres, const int *h_res, const double *const *h_D);
@@ -339,7 +344,8 @@ int frk_model_em_fit(frk_model *mdl, int n_EM, double tol, int K_type, int nlamb
 /* logLik(SRE) at the current slots (R/SREutils.R:22-32 -> .loglik.ind R/SREfit.R:174-220) */
 int frk_model_loglik(frk_model *mdl, double *h_out);
 /* slot access: "mu_eta" (r), "S_eta", "Q_eta", "Khat", "Khat_inv" (r x r column-major), "alphahat" (p),
- * "sigma2fshat" (1); read-only: "m_total", "homoscedastic", "tau", "omega" (per resolution, last M-step)       */
+ * "sigma2fshat" (1); read-only: "m_total", "homoscedastic", "tau", "omega" (per resolution, last M-step),
+ * "nm_stats" (4: Nelder-Mead points requested / evaluation rounds / points evaluated / re-evaluations, last M-step)  */
 int frk_model_get(frk_model *mdl, const char *slot, double *h_out);
 int frk_model_set(frk_model *mdl, const char *slot, const double *h_in);
 int frk_model_slot_device(frk_model *mdl, const char *slot, double **d_out);

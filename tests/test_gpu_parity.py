@@ -607,8 +607,8 @@ def test_speculative_nelder_mead_matches_sequential(dev, world):
     _, Ma = _setup_plane(F, K_type="block-exponential", hetero=True)
     _, Mb = _setup_plane(F, K_type="block-exponential", hetero=True)
     call("frk_model_set_parallel", Mb.handle, 0, world, 1)
-    F.SRE_fit(Ma, n_EM=5, tol=0.0)
-    F.SRE_fit(Mb, n_EM=5, tol=0.0)
+    F.SRE_fit(Ma, n_EM=5, tol=0.0, lanes=1)                         # strictly sequential Nelder-Mead
+    F.SRE_fit(Mb, n_EM=5, tol=0.0, lanes=1)
     np.testing.assert_allclose(Mb.info_fit["llk"], Ma.info_fit["llk"], rtol=1e-11)
     np.testing.assert_allclose(Mb.info_fit["tau"], Ma.info_fit["tau"], rtol=1e-10)
     np.testing.assert_allclose(Mb.info_fit["omega"], Ma.info_fit["omega"], rtol=1e-10)
@@ -616,3 +616,33 @@ def test_speculative_nelder_mead_matches_sequential(dev, world):
     np.testing.assert_allclose(Kb, Ka, rtol=1e-9, atol=1e-12 * abs(Ka).max())
     Ia, Ib = Ma.get("Khat_inv"), Mb.get("Khat_inv")
     np.testing.assert_allclose(Ib, Ia, rtol=1e-8, atol=1e-11 * abs(Ia).max())
+
+
+@pytest.mark.parametrize("lanes,world", [(2, 1), (3, 1), (4, 1), (3, 2)])
+def test_nelder_mead_lanes_match_sequential(dev, lanes, world):
+    """frk_model_set_lanes: candidate points of the block-exponential Nelder-Mead factorised side by side on separate streams (host
+    threads, one context per lane), alone and combined with the (emulated) ranks of a partitioned run.  Same iterate path as the
+    sequential run: Nelder-Mead asks for the same number of distinct points, and tau / omega / llk / K / K^-1 agree to the Gram
+    kernel's run-to-run noise."""
+    import frk_b200 as F
+    from frk_b200._lib import call
+    _, Ma = _setup_plane(F, K_type="block-exponential", hetero=True)
+    _, Mb = _setup_plane(F, K_type="block-exponential", hetero=True)
+    if world > 1:
+        call("frk_model_set_parallel", Mb.handle, 0, world, 1)
+    F.SRE_fit(Ma, n_EM=5, tol=0.0, lanes=1)
+    F.SRE_fit(Mb, n_EM=5, tol=0.0, lanes=lanes)
+    sa, sb = Ma.info_fit["nm_stats"], Mb.info_fit["nm_stats"]
+    assert sb["requests"] == sa["requests"] and sb["rounds"] <= sa["rounds"] and sb["evaluated"] >= sa["evaluated"]
+    assert sb["rounds"] < sa["rounds"], "speculation never saved a round"
+    np.testing.assert_allclose(Mb.info_fit["llk"], Ma.info_fit["llk"], rtol=1e-11)
+    np.testing.assert_allclose(Mb.info_fit["tau"], Ma.info_fit["tau"], rtol=1e-10)
+    np.testing.assert_allclose(Mb.info_fit["omega"], Ma.info_fit["omega"], rtol=1e-10)
+    Ka, Kb = Ma.get("Khat"), Mb.get("Khat")
+    np.testing.assert_allclose(Kb, Ka, rtol=1e-9, atol=1e-12 * abs(Ka).max())
+    Ia, Ib = Ma.get("Khat_inv"), Mb.get("Khat_inv")
+    np.testing.assert_allclose(Ib, Ia, rtol=1e-8, atol=1e-11 * abs(Ia).max())
+    # a second fit on the same model re-uses the lane contexts and their graph caches
+    F.SRE_fit(Ma, n_EM=2, tol=0.0, lanes=1)
+    F.SRE_fit(Mb, n_EM=2, tol=0.0, lanes=lanes)
+    np.testing.assert_allclose(Mb.info_fit["llk"], Ma.info_fit["llk"], rtol=1e-11)
