@@ -39,6 +39,8 @@ struct frk_ctx {
     bool use_graphs = true;
     struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; };
     std::map<std::array<uintptr_t, 5>, GraphEntry> graphs;
+    // lane contexts (frk_ctx_lane): created on first use, kept for the life of this context so that models come and go cheaply
+    std::vector<frk_ctx *> lanes_hi, lanes_lo;
 };
 
 int frk_prof_begin(frk_ctx *ctx, const char *name, cudaEvent_t *e1);   // records e0; returns 0
@@ -83,7 +85,9 @@ int frk_scratch(frk_ctx *ctx, size_t bytes, void **out);   // grow-only scratch 
 
 // a second context on the parent's device with its own streams, events, staging and graph cache: independent work (e.g. the
 // speculative Nelder-Mead evaluations of one M-step) is enqueued on lanes and runs concurrently with the parent's stream
-int frk_ctx_create_lane(const frk_ctx *parent, frk_ctx **out);
+int frk_ctx_create_lane(const frk_ctx *parent, bool high_priority, frk_ctx **out);
+// lane `idx` of `parent` (cached in the parent, destroyed with it)
+int frk_ctx_lane(frk_ctx *parent, int idx, bool high_priority, frk_ctx **out);
 
 // exclusive scan of int32 counts[n] -> out[n+1] (out[n] = total); total also returned to host
 int frk_exclusive_scan_i32(frk_ctx *ctx, const int *d_in, int64_t n, int *d_out, int64_t *h_total);

@@ -56,14 +56,15 @@ extern "C" int frk_ctx_create(int device, void *stream, frk_ctx **out) {
     return 0;
 }
 
-int frk_ctx_create_lane(const frk_ctx *parent, frk_ctx **out) {
+int frk_ctx_create_lane(const frk_ctx *parent, bool high_priority, frk_ctx **out) {
     FRK_REQUIRE(parent && out, "frk_ctx_create_lane: NULL argument");
     FRK_CHECK_CUDA(cudaSetDevice(parent->device));
-    // a lane's main stream carries the critical path of its factorisations (potf2 / trsm chain): highest priority, like stream2
+    // a lane that factorises carries a critical path (potf2 / trsm chain) on its main stream: highest priority, like stream2;
+    // a lane for bulk work beside a latency-bound phase gets the lowest
     cudaStream_t s = nullptr;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    FRK_CHECK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));
+    FRK_CHECK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? prio_hi : prio_lo));
     frk_ctx *c = nullptr;
     if (int rc = frk_ctx_create(parent->device, (void *)s, &c)) { cudaStreamDestroy(s); return rc; }
     c->own_stream = true;
@@ -72,10 +73,22 @@ int frk_ctx_create_lane(const frk_ctx *parent, frk_ctx **out) {
     return 0;
 }
 
+int frk_ctx_lane(frk_ctx *parent, int idx, bool high_priority, frk_ctx **out) {
+    FRK_REQUIRE(parent && out && idx >= 0 && idx < 64, "frk_ctx_lane: bad argument");
+    std::vector<frk_ctx *> &v = high_priority ? parent->lanes_hi : parent->lanes_lo;
+    if ((int)v.size() <= idx) v.resize(idx + 1, nullptr);
+    if (!v[idx]) { if (int rc = frk_ctx_create_lane(parent, high_priority, &v[idx])) return rc; }
+    v[idx]->use_graphs = parent->use_graphs;
+    *out = v[idx];
+    return 0;
+}
+
 extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (frk_ctx *l : ctx->lanes_hi) frk_ctx_destroy(l);
+    for (frk_ctx *l : ctx->lanes_lo) frk_ctx_destroy(l);
     frk_prof_harvest(ctx);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);

@@ -76,6 +76,8 @@ struct frk_model {
     struct Lane { frk_ctx *ctx = nullptr; double *Ki = nullptr, *Kinv = nullptr, *work = nullptr; size_t cap = 0; };
     std::vector<Lane> lane;          // lane[0] is unused (the model's own context and block buffers)
     cudaEvent_t ev_lane = nullptr;
+    frk_ctx *aux = nullptr;          // low-priority lane: the sigma2fs quadratic form runs beside the (latency-bound) K update
+    cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
 };
 
 namespace {
@@ -496,22 +498,21 @@ int chol2inv_logdet(frk_ctx *ctx, int n, double *A, double *Ainv, double *work, 
     return frk_potri(ctx, n, A, Ainv, work);
 }
 
-// lane contexts and their n x n work buffers (created on first use, grown to the largest block)
+// lane contexts (cached in the parent context) and their n x n work buffers (pooled allocations, grown to the largest block)
 int prepare_lanes(frk_model *M, size_t nn) {
     if ((int)M->lane.size() < M->lanes) M->lane.resize(M->lanes);
     if (!M->ev_lane) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_lane, cudaEventDisableTiming));
     for (int l = 1; l < M->lanes; l++) {
         frk_model::Lane &ln = M->lane[l];
-        if (!ln.ctx) RC(frk_ctx_create_lane(M->ctx, &ln.ctx));
+        if (!ln.ctx) RC(frk_ctx_lane(M->ctx, l - 1, true, &ln.ctx));
         if (ln.cap < nn) {
+            // allocated and freed in the order of the model's own stream; every lane evaluation starts after an event on that stream
+            // and is synchronised before it returns, so the buffers are idle here
             for (double **p : {&ln.Ki, &ln.Kinv, &ln.work}) {
-                if (*p) { FRK_CHECK_CUDA(cudaStreamSynchronize(ln.ctx->stream)); FRK_CHECK_CUDA(cudaFree(*p)); *p = nullptr; }
-                FRK_CHECK_CUDA(cudaMalloc((void **)p, nn * sizeof(double)));
+                if (*p) FRK_CHECK_CUDA(cudaFreeAsync(*p, M->ctx->stream));
+                FRK_CHECK_CUDA(cudaMallocAsync((void **)p, nn * sizeof(double), M->ctx->stream));
             }
             ln.cap = nn;
-            // the graph cache is keyed by pointers: stale entries for the freed buffers must go
-            for (auto &kv : ln.ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
-            ln.ctx->graphs.clear();
         }
     }
     return 0;
@@ -757,6 +758,23 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
     const size_t rr = (size_t)r * r;
     const double sigma2fs = M->sigma2fs;
     bool have_inverse = false;
+    // Omega_diag1 = rowSums((S R_eta')^2) = s_j'(S_eta + mu mu')s_j = q_j + t_j^2,  t = S mu_eta     :332-334
+    // It reads only the E-step's S_eta / mu_eta, so with lanes enabled it is enqueued on a low-priority lane first and fills the SMs
+    // the block-exponential Nelder-Mead (one latency-bound factorisation chain after another) leaves idle.
+    const bool beside = K_type == FRK_K_BLOCK_EXPONENTIAL && M->lanes > 1 && !ctx->profiling && ctx->stream != nullptr;
+    if (beside) {
+        if (!M->aux) {
+            RC(frk_ctx_lane(ctx, 0, false, &M->aux));
+            FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_aux0, cudaEventDisableTiming));
+            FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_aux1, cudaEventDisableTiming));
+        }
+        FRK_CHECK_CUDA(cudaEventRecord(M->ev_aux0, ctx->stream));
+        FRK_CHECK_CUDA(cudaStreamWaitEvent(M->aux->stream, M->ev_aux0, 0));
+        RC(frk_quadform_spmv_bucketed(M->aux, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
+        FRK_CHECK_CUDA(cudaEventRecord(M->ev_aux1, M->aux->stream));
+        ctx->launches += M->aux->launches;
+        M->aux->launches = 0;
+    }
     RC(update_K(M, K_type, nlambda, lambda, h_res, have_inverse));   // :270-272
     if (!have_inverse) {
         FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, M->Khat, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -765,9 +783,8 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
     }
     const bool est = !known;
     double s2new = est ? sigma2fs : known_sigma2fs;
-    // Omega_diag1 = rowSums((S R_eta')^2) = s_j'(S_eta + mu mu')s_j = q_j + t_j^2,  t = S mu_eta     :332-334
-    RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk,
-                                  M->S_eta, M->mu_eta, M->q, M->t));
+    if (beside) FRK_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, M->ev_aux1, 0));
+    else RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
     double al[MAXP_M];
     MSums s;
     double swo;
@@ -894,10 +911,12 @@ extern "C" int frk_model_destroy(frk_model *M) {
     for (auto &ln : M->lane) {
         if (!ln.ctx) continue;
         cudaStreamSynchronize(ln.ctx->stream);
-        for (double *p : {ln.Ki, ln.Kinv, ln.work}) if (p) cudaFree(p);
-        frk_ctx_destroy(ln.ctx);
+        for (double *p : {ln.Ki, ln.Kinv, ln.work}) if (p) cudaFreeAsync(p, M->ctx->stream);
     }
     if (M->ev_lane) cudaEventDestroy(M->ev_lane);
+    if (M->aux) cudaStreamSynchronize(M->aux->stream);          // the lane contexts themselves belong to M->ctx
+    if (M->ev_aux0) cudaEventDestroy(M->ev_aux0);
+    if (M->ev_aux1) cudaEventDestroy(M->ev_aux1);
     delete M;
     return 0;
 }
