@@ -86,6 +86,12 @@ int frk_scratch(frk_ctx *ctx, size_t bytes, void **out);   // grow-only scratch 
 // a second context on the parent's device with its own streams, events, staging and graph cache: independent work (e.g. the
 // speculative Nelder-Mead evaluations of one M-step) is enqueued on lanes and runs concurrently with the parent's stream
 int frk_ctx_create_lane(const frk_ctx *parent, bool high_priority, frk_ctx **out);
+// enqueue-only halves of frk_potrf / frk_dot (dense.cu): results are staged in the context's pinned buffer and read after a stream
+// synchronisation, so that one host thread can keep several contexts busy at once
+int frk_potrf_async(frk_ctx *ctx, int r, double *d_A);
+int frk_potrf_finish(frk_ctx *ctx, double *h_logdet);
+int frk_dot_async(frk_ctx *ctx, int64_t n, const double *d_A, const double *d_B);
+static constexpr int FRK_PINNED_DOT = 4080;          // slot of frk_dot_async's result in frk_ctx::h_pinned
 // lane `idx` of `parent` (cached in the parent, destroyed with it)
 int frk_ctx_lane(frk_ctx *parent, int idx, bool high_priority, frk_ctx **out);
 

@@ -696,16 +696,28 @@ static int potrf_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
     return 0;
 }
 
-extern "C" int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet) {
+// enqueue only: factor + {sum log diag, first bad column} -> ctx->h_pinned[4088..4089]; read them with frk_potrf_finish once the
+// stream has been synchronised (lets several contexts factorise side by side from one host thread)
+int frk_potrf_async(frk_ctx *ctx, int r, double *d_A) {
     FRK_REQUIRE(ctx && d_A && r > 0, "frk_potrf: bad argument");
     double *status = ctx->d_small + 4096 - 8;
     if (int rc = gemm_set_attrs()) return rc;
     if (int rc = run_graphed(ctx, {1, (uintptr_t)r, (uintptr_t)d_A, 0, 0}, [&]() { return potrf_enqueue(ctx, r, d_A, status); })) return rc;
-    FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned, status, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    FRK_REQUIRE(ctx->h_pinned[1] == 0.0, "the leading minor of order %d is not positive definite", (int)ctx->h_pinned[1]);
-    if (h_logdet) *h_logdet = 2.0 * ctx->h_pinned[0];
+    FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned + 4096 - 8, status, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
+}
+
+int frk_potrf_finish(frk_ctx *ctx, double *h_logdet) {
+    const double *st = ctx->h_pinned + 4096 - 8;
+    FRK_REQUIRE(st[1] == 0.0, "the leading minor of order %d is not positive definite", (int)st[1]);
+    if (h_logdet) *h_logdet = 2.0 * st[0];
+    return 0;
+}
+
+extern "C" int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet) {
+    if (int rc = frk_potrf_async(ctx, r, d_A)) return rc;
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return frk_potrf_finish(ctx, h_logdet);
 }
 
 // chol2inv.  d_work receives X = L^-1 (lower triangular, zeros above the diagonal).
@@ -880,16 +892,23 @@ __global__ void dot_final_kernel(int nblocks, const double *__restrict__ part, d
     }
 }
 
-extern "C" int frk_dot(frk_ctx *ctx, int64_t n, const double *d_A, const double *d_B, double *h_out) {
-    FRK_REQUIRE(ctx && d_A && d_B && h_out, "frk_dot: NULL argument");
-    if (n == 0) { *h_out = 0.0; return 0; }
+// enqueue only: the result lands in ctx->h_pinned[4080] (valid once the stream has been synchronised)
+int frk_dot_async(frk_ctx *ctx, int64_t n, const double *d_A, const double *d_B) {
+    FRK_REQUIRE(ctx && d_A && d_B, "frk_dot: NULL argument");
+    if (n == 0) { ctx->h_pinned[4080] = 0.0; return 0; }
     const int nblocks = (int)std::min<int64_t>(cdiv(n, 256), 1024);
     double *part = ctx->d_small, *out = ctx->d_small + 2048;
     FRK_LAUNCH(ctx, dot_partial_kernel, nblocks, 256, 0, n, d_A, d_B, part);
     FRK_LAUNCH(ctx, dot_final_kernel, 1, 32, 0, nblocks, part, out);
-    FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned, out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned + 4080, out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+extern "C" int frk_dot(frk_ctx *ctx, int64_t n, const double *d_A, const double *d_B, double *h_out) {
+    FRK_REQUIRE(h_out, "frk_dot: NULL argument");
+    if (int rc = frk_dot_async(ctx, n, d_A, d_B)) return rc;
     FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    *h_out = ctx->h_pinned[0];
+    *h_out = ctx->h_pinned[4080];
     return 0;
 }
 

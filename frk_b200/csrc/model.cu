@@ -17,8 +17,6 @@
 #include <cstdlib>
 #include <functional>
 #include <limits>
-#include <string>
-#include <thread>
 
 namespace {
 
@@ -649,48 +647,47 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         double bestF = std::numeric_limits<double>::infinity(), bestTau = -1.0, bestLogdet = 0.0;
         const int nlanes = ctx->profiling ? 1 : M->lanes;           // per-kernel profiling times one stream: keep everything on it
         if (nlanes > 1) RC(prepare_lanes(M, nn));
-        // one evaluation on lane l (0 = this context and the block's own buffers); no shared state is written
-        auto f_tau_lane = [&](int l, double tau, double &fval, double &logdetKi) -> int {
-            if (tau <= 1e-10) { fval = std::numeric_limits<double>::infinity(); logdetKi = 0.0; return 0; }
+        // Enqueue one evaluation on lane l (0 = this context and the block's own buffers): K_i(tau), its factor, inverse and
+        // tr(K_i^-1 eta2_i); nothing is synchronised, the scalars land in the lane's pinned staging buffer.
+        auto f_tau_enqueue = [&](int l, double tau) -> int {
             frk_ctx *c = l ? M->lane[l].ctx : ctx;
             double *Ki = l ? M->lane[l].Ki : B.Ki, *Kinv = l ? M->lane[l].Kinv : B.Kinv, *work = l ? M->lane[l].work : B.work;
-            double t;
             RC(frk_exp_kernel(c, (int64_t)nn, B.D, tau, 1.0, Ki));
-            RC(chol2inv_logdet(c, ni, Ki, Kinv, work, &logdetKi));
-            RC(frk_dot(c, (int64_t)nn, Kinv, B.eta2, &t));
-            fval = -(0.5 * (-logdetKi) - omega / 2.0 * t);
-            return 0;
+            RC(frk_potrf_async(c, ni, Ki));
+            RC(frk_potri(c, ni, Ki, Kinv, work));                    // (on a non-PD matrix this computes garbage that is discarded below)
+            return frk_dot_async(c, (int64_t)nn, Kinv, B.eta2);
         };
         double lanePt[16], laneLd[16];                              // what each lane's Kinv buffer currently holds
         bool laneValid[16] = {false};
         auto f_tau = [&](int nb, const double *const *pts, double *fv) -> int {
-            double ldv[16];
-            int rcs[16] = {0};
-            std::string errs[16];
             if (nb > 1) {
                 // the lanes start once this stream has produced eta2_i (and saved the best inverse so far out of their buffers)
                 FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));
                 for (int l = 1; l < nb; l++) FRK_CHECK_CUDA(cudaStreamWaitEvent(M->lane[l].ctx->stream, M->ev_lane, 0));
-                std::vector<std::thread> th;
-                for (int l = 1; l < nb; l++) {
-                    th.emplace_back([&, l]() {
-                        cudaSetDevice(ctx->device);               // the current device is per host thread
-                        rcs[l] = f_tau_lane(l, pts[l][0], fv[l], ldv[l]);
-                        if (rcs[l]) errs[l] = frk_last_error();   // the message is thread-local: carry it over
-                    });
-                }
-                rcs[0] = f_tau_lane(0, pts[0][0], fv[0], ldv[0]);
-                for (auto &t : th) t.join();
-                for (int l = 1; l < nb; l++) {
-                    ctx->launches += M->lane[l].ctx->launches;
-                    M->lane[l].ctx->launches = 0;
-                }
-                for (int l = 0; l < nb; l++)
-                    if (rcs[l]) { if (l) frk_set_error("%s", errs[l].c_str()); return rcs[l]; }
-            } else {
-                RC(f_tau_lane(0, pts[0][0], fv[0], ldv[0]));
             }
-            for (int l = 0; l < nb; l++) { lanePt[l] = pts[l][0]; laneLd[l] = ldv[l]; laneValid[l] = std::isfinite(fv[l]); }
+            bool live[16];
+            int rc = 0;
+            for (int l = 0; l < nb && !rc; l++) {
+                live[l] = pts[l][0] > 1e-10;
+                if (live[l]) rc = f_tau_enqueue(l, pts[l][0]);
+            }
+            // every lane that was started is drained before returning, error or not
+            for (int l = 0; l < nb; l++) {
+                frk_ctx *c = l ? M->lane[l].ctx : ctx;
+                if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) { frk_set_error("lane %d: stream synchronisation failed", l); rc = 1; }
+                if (l) { ctx->launches += c->launches; c->launches = 0; }
+            }
+            if (rc) return rc;
+            for (int l = 0; l < nb; l++) {
+                laneValid[l] = false;
+                if (!live[l]) { fv[l] = std::numeric_limits<double>::infinity(); continue; }
+                frk_ctx *c = l ? M->lane[l].ctx : ctx;
+                double logdetKi;
+                RC(frk_potrf_finish(c, &logdetKi));
+                const double t = c->h_pinned[FRK_PINNED_DOT];
+                fv[l] = -(0.5 * (-logdetKi) - omega / 2.0 * t);
+                lanePt[l] = pts[l][0]; laneLd[l] = logdetKi; laneValid[l] = std::isfinite(fv[l]);
+            }
             return 0;
         };
         // Nelder-Mead returns its lowest vertex, a REQUESTED point: keep the inverse of the best requested point while it is still

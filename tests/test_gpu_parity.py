@@ -620,8 +620,8 @@ def test_speculative_nelder_mead_matches_sequential(dev, world):
 
 @pytest.mark.parametrize("lanes,world", [(2, 1), (3, 1), (4, 1), (3, 2)])
 def test_nelder_mead_lanes_match_sequential(dev, lanes, world):
-    """frk_model_set_lanes: candidate points of the block-exponential Nelder-Mead factorised side by side on separate streams (host
-    threads, one context per lane), alone and combined with the (emulated) ranks of a partitioned run.  Same iterate path as the
+    """frk_model_set_lanes: candidate points of the block-exponential Nelder-Mead factorised side by side on separate streams (one
+    context per lane, all enqueued from one host thread), alone and combined with the (emulated) ranks of a partitioned run.  Same iterate path as the
     sequential run: Nelder-Mead asks for the same number of distinct points, and tau / omega / llk / K / K^-1 agree to the Gram
     kernel's run-to-run noise."""
     import frk_b200 as F
