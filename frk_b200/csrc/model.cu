@@ -756,9 +756,9 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
     const double sigma2fs = M->sigma2fs;
     bool have_inverse = false;
     // Omega_diag1 = rowSums((S R_eta')^2) = s_j'(S_eta + mu mu')s_j = q_j + t_j^2,  t = S mu_eta     :332-334
-    // It reads only the E-step's S_eta / mu_eta, so with lanes enabled it is enqueued on a low-priority lane first and fills the SMs
+    // It reads only the E-step's S_eta / mu_eta, so it is enqueued on a low-priority lane first and fills the SMs
     // the block-exponential Nelder-Mead (one latency-bound factorisation chain after another) leaves idle.
-    const bool beside = K_type == FRK_K_BLOCK_EXPONENTIAL && M->lanes > 1 && !ctx->profiling && ctx->stream != nullptr;
+    const bool beside = K_type == FRK_K_BLOCK_EXPONENTIAL && !ctx->profiling && ctx->stream != nullptr;
     if (beside) {
         if (!M->aux) {
             RC(frk_ctx_lane(ctx, 0, false, &M->aux));
