@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <functional>
 #include <limits>
+#include <memory>
+#include <string>
 
 namespace {
 
@@ -71,8 +73,6 @@ struct frk_model {
     // lanes: extra contexts on this GPU that evaluate speculative Nelder-Mead candidates concurrently (a factorisation is latency
     // bound and fills a fraction of the SMs, so a few of them side by side cost little more than one)
     int lanes = 1;
-    struct Lane { frk_ctx *ctx = nullptr; double *Ki = nullptr, *Kinv = nullptr, *work = nullptr; size_t cap = 0; };
-    std::vector<Lane> lane;          // lane[0] is unused (the model's own context and block buffers)
     cudaEvent_t ev_lane = nullptr;
     frk_ctx *aux = nullptr;          // low-priority lane: the sigma2fs quadratic form runs beside the (latency-bound) K update
     cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
@@ -413,6 +413,21 @@ struct SpecNM {
         (void)x;
     }
 
+    // Replay nmmin against the values known so far.  0: Nelder-Mead finished (res); 99: `need` is the first point it asks for that
+    // has no value yet.  Every point it asks for is reported to `requested` (repeats included, in request order).
+    std::vector<char> seen;
+    int replay(std::vector<double> &need, NMResult &res) {
+        auto sim = [&](const double *y, double &f) -> int {
+            const int i = find(y);
+            if (i < 0) { need.assign(y, y + dim); return 99; }
+            f = fv[i];
+            if ((int)seen.size() <= i) seen.resize(i + 1, 0);
+            if (!seen[i]) { seen[i] = 1; M->nm_requests += 1; }
+            return requested ? requested(y, f) : 0;
+        };
+        return nmmin(sim, par0, res, maxit, reltol);
+    }
+
     int operator()(const double *x, double &f) {
         int i = find(x);
         M->nm_requests += 1;
@@ -496,22 +511,216 @@ int chol2inv_logdet(frk_ctx *ctx, int n, double *A, double *Ainv, double *work, 
     return frk_potri(ctx, n, A, Ainv, work);
 }
 
-// lane contexts (cached in the parent context) and their n x n work buffers (pooled allocations, grown to the largest block)
-int prepare_lanes(frk_model *M, size_t nn) {
-    if ((int)M->lane.size() < M->lanes) M->lane.resize(M->lanes);
+// ---------------------------------------------------------------------------------
+// Block-exponential K, plain bases: the per-resolution Nelder-Mead runs (optim(), R/SREfit.R:618-621) are independent, and every
+// f_tau evaluation is a latency-bound r_i x r_i factorisation that fills a fraction of the GPU.  So the runs advance in LOCKSTEP:
+// each round, every unfinished run is replayed against the values known so far until it asks for a point without a value; that
+// point plus the points it may ask for next (SpecNM::candidates) are evaluated -- all resolutions, all candidates, side by side on
+// lane contexts of this GPU and spread over the ranks -- and ONE all-reduce shares the values.  Each run sees exactly the values
+// the sequential algorithm would: the iterates are identical.
+// ---------------------------------------------------------------------------------
+struct NMSlot {                    // one concurrent evaluation: context + buffers, and what its Kinv currently holds
+    frk_ctx *ctx = nullptr;
+    double *Ki = nullptr, *Kinv = nullptr, *work = nullptr;
+    double pt = 0.0, ld = 0.0;
+    bool valid = false, used = false;
+    int k = -1;
+};
+
+struct BlkNM {
+    Block *B = nullptr;
+    double omega = 0.0;
+    double bestF = std::numeric_limits<double>::infinity(), bestTau = -1.0, bestLogdet = 0.0;
+    bool done = false;
+    NMResult nm;
+    std::unique_ptr<SpecNM> spec;
+    std::vector<std::vector<double>> batch;
+    std::vector<double> fl;
+    std::vector<NMSlot> slot;
+};
+
+// K_i(tau), its factor, inverse and tr(K_i^-1 eta2_i) on the slot's context; enqueue only, the scalars land in the context's
+// pinned staging buffer (on a non-PD matrix the inverse is garbage that is discarded when the status is read)
+int f_tau_enqueue(const Block &B, NMSlot &s, double tau) {
+    const size_t nn = (size_t)B.ni * B.ni;
+    RC(frk_exp_kernel(s.ctx, (int64_t)nn, B.D, tau, 1.0, s.Ki));
+    RC(frk_potrf_async(s.ctx, B.ni, s.Ki));
+    RC(frk_potri(s.ctx, B.ni, s.Ki, s.Kinv, s.work));
+    return frk_dot_async(s.ctx, (int64_t)nn, s.Kinv, B.eta2);
+}
+
+int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, double *Knew, double *Kinvnew, double &logdetK) {
+    frk_ctx *ctx = M->ctx;
+    const int r = M->r, nblk = (int)nmb.size();
+    const int world = std::max(M->world, 1);
+    const bool one_stream = ctx->profiling || ctx->stream == nullptr;   // per-kernel profiling times one stream: keep everything on it
+    const int L = one_stream ? 1 : std::max(M->lanes, 1);
+    const int W = world * L;
+    const bool shared = world > 1 && !M->spec_emulate;
+    constexpr int LCAP = 8;                                             // slot (block j, lane c) -> lane context j*LCAP + c: stable, so graph caches hit
     if (!M->ev_lane) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_lane, cudaEventDisableTiming));
-    for (int l = 1; l < M->lanes; l++) {
-        frk_model::Lane &ln = M->lane[l];
-        if (!ln.ctx) RC(frk_ctx_lane(M->ctx, l - 1, true, &ln.ctx));
-        if (ln.cap < nn) {
-            // allocated and freed in the order of the model's own stream; every lane evaluation starts after an event on that stream
-            // and is synchronised before it returns, so the buffers are idle here
-            for (double **p : {&ln.Ki, &ln.Kinv, &ln.work}) {
-                if (*p) FRK_CHECK_CUDA(cudaFreeAsync(*p, M->ctx->stream));
-                FRK_CHECK_CUDA(cudaMallocAsync((void **)p, nn * sizeof(double), M->ctx->stream));
+
+    for (int j = 0; j < nblk; j++) {
+        BlkNM &S = *nmb[j];
+        Block &B = *S.B;
+        const size_t nn = (size_t)B.ni * B.ni;
+        S.slot.resize(L);
+        for (int c = 0; c < L; c++) {
+            NMSlot &s = S.slot[c];
+            const int q = j * LCAP + c;
+            if (one_stream || q == 0) {
+                s.ctx = ctx; s.Ki = B.Ki; s.Kinv = B.Kinv; s.work = B.work;
+            } else {
+                // a lane context serves one (resolution, lane) pair and keeps its buffers in its own grow-only scratch: the
+                // pointers -- hence the cached CUDA graphs -- survive from one model to the next
+                RC(frk_ctx_lane(ctx, q - 1, true, &s.ctx));
+                void *buf = nullptr;
+                RC(frk_scratch(s.ctx, 3 * nn * sizeof(double), &buf));
+                s.Ki = (double *)buf; s.Kinv = s.Ki + nn; s.work = s.Kinv + nn;
             }
-            ln.cap = nn;
         }
+        // Nelder-Mead returns its lowest vertex, a REQUESTED point (a speculative point that is never requested cannot be the result):
+        // keep the inverse of the best requested point while it is still in a slot (slots are drained before any replay; the next
+        // round starts after this copy)
+        BlkNM *Sp = &S;
+        S.spec->requested = [M, Sp](const double *x, double f) -> int {
+            if (!(f < Sp->bestF)) return 0;
+            Sp->bestF = f; Sp->bestTau = -1.0;
+            const size_t nn2 = (size_t)Sp->B->ni * Sp->B->ni;
+            for (NMSlot &s : Sp->slot) {
+                if (!s.valid || s.pt != x[0]) continue;
+                FRK_CHECK_CUDA(cudaMemcpyAsync(Sp->B->KinvBest, s.Kinv, nn2 * sizeof(double), cudaMemcpyDeviceToDevice, M->ctx->stream));
+                Sp->bestTau = x[0]; Sp->bestLogdet = s.ld;
+                break;
+            }
+            return 0;
+        };
+    }
+
+    // evaluate, for every block with a batch, the candidates with index in [k0, k0 + L) of this rank's share; drain; read the values
+    auto run_chunk = [&](int chunk) -> int {
+        FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));      // the lanes start once this stream has produced eta2 / saved the best inverses
+        int rc = 0;
+        for (int j = 0; j < nblk && !rc; j++) {
+            BlkNM &S = *nmb[j];
+            for (int c = 0; c < L && !rc; c++) {
+                NMSlot &s = S.slot[c];
+                s.used = false;
+                if (S.done) continue;
+                const int k = M->spec_emulate ? chunk * L + c : c * world + M->rank;    // candidate k -> rank k % world, lane k / world
+                if (k >= (int)S.batch.size()) continue;
+                s.k = k; s.valid = false;
+                const double tau = S.batch[k][0];
+                if (tau <= 1e-10) { S.fl[k] = std::numeric_limits<double>::infinity(); continue; }
+                if (s.ctx != ctx) FRK_CHECK_CUDA(cudaStreamWaitEvent(s.ctx->stream, M->ev_lane, 0));
+                rc = f_tau_enqueue(*S.B, s, tau);
+                s.used = true; s.pt = tau;
+            }
+        }
+        // every context that was started is drained before returning, error or not
+        for (int j = 0; j < nblk; j++)
+            for (NMSlot &s : nmb[j]->slot) {
+                if (!s.used) continue;
+                if (cudaStreamSynchronize(s.ctx->stream) != cudaSuccess && !rc) { frk_set_error("f_tau lane: stream synchronisation failed"); rc = 1; }
+                if (s.ctx != ctx) { ctx->launches += s.ctx->launches; s.ctx->launches = 0; }
+            }
+        if (rc) return rc;
+        for (int j = 0; j < nblk; j++) {
+            BlkNM &S = *nmb[j];
+            for (NMSlot &s : S.slot) {
+                if (!s.used) continue;
+                double logdetKi;
+                RC(frk_potrf_finish(s.ctx, &logdetKi));
+                const double t = s.ctx->h_pinned[FRK_PINNED_DOT];
+                const double f = -(0.5 * (-logdetKi) - S.omega / 2.0 * t);
+                S.fl[s.k] = f; s.ld = logdetKi; s.valid = std::isfinite(f);
+            }
+        }
+        return 0;
+    };
+
+    for (;;) {
+        // 1. what does each run ask for next?
+        size_t maxbatch = 0;
+        for (int j = 0; j < nblk; j++) {
+            BlkNM &S = *nmb[j];
+            S.batch.clear();
+            S.fl.clear();
+            if (S.done) continue;
+            std::vector<double> need;
+            const int rc = S.spec->replay(need, S.nm);
+            if (rc == 0) { S.done = true; continue; }
+            if (rc != 99) return rc;
+            S.batch.push_back(need);
+            if (W > 1) S.spec->candidates(need.data(), (size_t)W, S.batch);
+            S.fl.assign(S.batch.size(), 0.0);
+            maxbatch = std::max(maxbatch, S.batch.size());
+        }
+        if (maxbatch == 0) break;
+        M->nm_rounds += 1;
+        // 2. evaluate (one chunk, unless a pretend world is emulated on this rank)
+        const int nchunks = M->spec_emulate ? (int)((maxbatch + L - 1) / L) : 1;
+        for (int ch = 0; ch < nchunks; ch++) RC(run_chunk(ch));
+        // 3. share the values of all resolutions with one all-reduce
+        if (shared) {
+            std::vector<double> all;
+            for (int j = 0; j < nblk; j++) all.insert(all.end(), nmb[j]->fl.begin(), nmb[j]->fl.end());
+            // a value is +inf on its owner and 0 elsewhere -> the sum is right; (tau <= 1e-10 is +inf on every rank: inf + inf = inf)
+            for (int j = 0, o = 0; j < nblk; j++)
+                for (size_t k = 0; k < nmb[j]->fl.size(); k++, o++)
+                    if ((int)(k % world) != M->rank) all[o] = 0.0;
+            RC(reduce_host(M, all.data(), (int64_t)all.size(), 0));
+            for (int j = 0, o = 0; j < nblk; j++)
+                for (size_t k = 0; k < nmb[j]->fl.size(); k++, o++) nmb[j]->fl[k] = all[o];
+        }
+        // 4. into the caches
+        for (int j = 0; j < nblk; j++) {
+            BlkNM &S = *nmb[j];
+            for (size_t k = 0; k < S.batch.size(); k++) {
+                S.spec->pts.push_back(S.batch[k]); S.spec->fv.push_back(S.fl[k]); S.spec->owner.push_back((int)(k % world));
+            }
+            M->nm_evals += (double)S.batch.size();
+        }
+    }
+
+    // K_i = exp(-D_i/tau_i)/omega_i and its inverse into place, :625-637
+    for (int j = 0; j < nblk; j++) {
+        BlkNM &S = *nmb[j];
+        Block &B = *S.B;
+        const int ni = B.ni;
+        const size_t nn = (size_t)ni * ni;
+        const double tau = S.nm.x[0], omega = S.omega;
+        M->taus.push_back(tau);
+        const int own = shared ? S.spec->owner[S.spec->find(&tau)] : M->rank;
+        if (own == M->rank) {
+            if (S.bestTau != tau) {        // its inverse is no longer in a slot (ties, or a point evaluated rounds before it was requested)
+                S.bestF = std::numeric_limits<double>::infinity();
+                NMSlot &s = S.slot[0];
+                s.valid = false;
+                RC(f_tau_enqueue(B, s, tau));
+                FRK_CHECK_CUDA(cudaStreamSynchronize(s.ctx->stream));
+                if (s.ctx != ctx) { ctx->launches += s.ctx->launches; s.ctx->launches = 0; }
+                double logdetKi;
+                RC(frk_potrf_finish(s.ctx, &logdetKi));
+                const double f = -(0.5 * (-logdetKi) - omega / 2.0 * s.ctx->h_pinned[FRK_PINNED_DOT]);
+                s.pt = tau; s.ld = logdetKi; s.valid = std::isfinite(f);
+                RC(S.spec->requested(&tau, f));
+                M->nm_reevals += 1;
+                FRK_REQUIRE(S.bestTau == tau, "block-exponential update: tau = %g cannot be evaluated", tau);
+            }
+        } else {
+            FRK_CHECK_CUDA(cudaMemsetAsync(B.KinvBest, 0, nn * sizeof(double), ctx->stream));
+            S.bestLogdet = 0.0;
+        }
+        if (shared) {                                                // broadcast from the owner: sum with zeros elsewhere
+            RC(reduce_dev(M, B.KinvBest, (int64_t)nn));
+            RC(reduce_host(M, &S.bestLogdet, 1, 0));
+        }
+        RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau, 1.0 / omega, B.Ki));
+        RC(frk_block_scatter(ctx, r, Knew, ni, B.d_ix, B.Ki));
+        RC(frk_scale(ctx, (int64_t)nn, omega, B.KinvBest));                       // K_i^-1 = omega_i exp(-D_i/tau_i)^-1
+        RC(frk_block_scatter(ctx, r, Kinvnew, ni, B.d_ix, B.KinvBest));
+        logdetK += S.bestLogdet - ni * std::log(omega);
     }
     return 0;
 }
@@ -557,6 +766,7 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
     FRK_CHECK_CUDA(cudaMemsetAsync(Knew, 0, rr * sizeof(double), ctx->stream));
     FRK_CHECK_CUDA(cudaMemsetAsync(Kinvnew, 0, rr * sizeof(double), ctx->stream));
     double logdetK = 0.0;
+    std::vector<std::unique_ptr<BlkNM>> nmb;     // per-resolution Nelder-Mead state (plain bases)
     for (Block &B : M->blocks) {
         const int ni = B.ni;
         const size_t nn = (size_t)ni * ni;
@@ -642,105 +852,19 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
             logdetK += bestLd - ni * std::log(omega);
             continue;
         }
-        // f_tau, :485-529.  The inverse and log-determinant at the best tau seen are kept: Nelder-Mead returns its lowest
-        // vertex, i.e. an evaluated point, so K_i(tau*)^-1 and log|K_i(tau*)| need no further factorisation.
-        double bestF = std::numeric_limits<double>::infinity(), bestTau = -1.0, bestLogdet = 0.0;
-        const int nlanes = ctx->profiling ? 1 : M->lanes;           // per-kernel profiling times one stream: keep everything on it
-        if (nlanes > 1) RC(prepare_lanes(M, nn));
-        // Enqueue one evaluation on lane l (0 = this context and the block's own buffers): K_i(tau), its factor, inverse and
-        // tr(K_i^-1 eta2_i); nothing is synchronised, the scalars land in the lane's pinned staging buffer.
-        auto f_tau_enqueue = [&](int l, double tau) -> int {
-            frk_ctx *c = l ? M->lane[l].ctx : ctx;
-            double *Ki = l ? M->lane[l].Ki : B.Ki, *Kinv = l ? M->lane[l].Kinv : B.Kinv, *work = l ? M->lane[l].work : B.work;
-            RC(frk_exp_kernel(c, (int64_t)nn, B.D, tau, 1.0, Ki));
-            RC(frk_potrf_async(c, ni, Ki));
-            RC(frk_potri(c, ni, Ki, Kinv, work));                    // (on a non-PD matrix this computes garbage that is discarded below)
-            return frk_dot_async(c, (int64_t)nn, Kinv, B.eta2);
-        };
-        double lanePt[16], laneLd[16];                              // what each lane's Kinv buffer currently holds
-        bool laneValid[16] = {false};
-        auto f_tau = [&](int nb, const double *const *pts, double *fv) -> int {
-            if (nb > 1) {
-                // the lanes start once this stream has produced eta2_i (and saved the best inverse so far out of their buffers)
-                FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));
-                for (int l = 1; l < nb; l++) FRK_CHECK_CUDA(cudaStreamWaitEvent(M->lane[l].ctx->stream, M->ev_lane, 0));
-            }
-            bool live[16];
-            int rc = 0;
-            for (int l = 0; l < nb && !rc; l++) {
-                live[l] = pts[l][0] > 1e-10;
-                if (live[l]) rc = f_tau_enqueue(l, pts[l][0]);
-            }
-            // every lane that was started is drained before returning, error or not
-            for (int l = 0; l < nb; l++) {
-                frk_ctx *c = l ? M->lane[l].ctx : ctx;
-                if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) { frk_set_error("lane %d: stream synchronisation failed", l); rc = 1; }
-                if (l) { ctx->launches += c->launches; c->launches = 0; }
-            }
-            if (rc) return rc;
-            for (int l = 0; l < nb; l++) {
-                laneValid[l] = false;
-                if (!live[l]) { fv[l] = std::numeric_limits<double>::infinity(); continue; }
-                frk_ctx *c = l ? M->lane[l].ctx : ctx;
-                double logdetKi;
-                RC(frk_potrf_finish(c, &logdetKi));
-                const double t = c->h_pinned[FRK_PINNED_DOT];
-                fv[l] = -(0.5 * (-logdetKi) - omega / 2.0 * t);
-                lanePt[l] = pts[l][0]; laneLd[l] = logdetKi; laneValid[l] = std::isfinite(fv[l]);
-            }
-            return 0;
-        };
-        // Nelder-Mead returns its lowest vertex, a REQUESTED point: keep the inverse of the best requested point while it is still
-        // in a lane buffer (every lane has been synchronised by its last frk_dot; the next batch starts after this copy)
-        auto on_request = [&](const double *x, double f) -> int {
-            if (!(f < bestF)) return 0;
-            bestF = f; bestTau = -1.0;
-            for (int l = 0; l < nlanes; l++) {
-                if (!laneValid[l] || lanePt[l] != x[0]) continue;
-                const double *src = l ? M->lane[l].Kinv : B.Kinv;
-                FRK_CHECK_CUDA(cudaMemcpyAsync(B.KinvBest, src, nn * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-                bestTau = x[0]; bestLogdet = laneLd[l];
-                break;
-            }
-            return 0;
-        };
+        // f_tau, :485-529: deferred -- the Nelder-Mead runs of all resolutions advance together below
         double par0 = 1e-9;                                          // :608-614
         if (ni > 1) {
             const double v = -B.D01 / std::log(k01 / k00);
             par0 = (v > 1e-9) ? v : 1e-9;                            // max(v, 1e-9); NaN -> 1e-9
         }
         if (!std::isfinite(par0) || par0 == 1e-9) par0 = M->max_l / 10.0;
-        NMResult nm;
-        SpecNM spec{M, f_tau, 1, 100, 1e-4, std::vector<double>{par0}, nlanes, on_request};
-        RC(nmmin(std::ref(spec), spec.par0, nm, 100, 1e-4));         // optim(): Nelder-Mead, :618-621 (candidates spread over ranks and lanes)
-        const double tau = nm.x[0];
-        M->taus.push_back(tau);
-        const bool shared = M->world > 1 && !M->spec_emulate;
-        const int own = shared ? spec.owner[spec.find(&tau)] : M->rank;
-        if (own == M->rank) {
-            if (bestTau != tau) {                                    // ties / unrequested speculative points: re-evaluate so that KinvBest belongs to tau
-                bestF = std::numeric_limits<double>::infinity();
-                double f;
-                const double *pt = &tau;
-                RC(f_tau(1, &pt, &f));
-                RC(on_request(pt, f));
-                M->nm_reevals += 1;
-                FRK_REQUIRE(bestTau == tau, "block-exponential update: tau = %g cannot be evaluated", tau);
-            }
-        } else {
-            FRK_CHECK_CUDA(cudaMemsetAsync(B.KinvBest, 0, nn * sizeof(double), ctx->stream));
-            bestLogdet = 0.0;
-        }
-        if (shared) {                                                // broadcast from the owner: sum with zeros elsewhere
-            RC(reduce_dev(M, B.KinvBest, (int64_t)nn));
-            RC(reduce_host(M, &bestLogdet, 1, 0));
-        }
-        RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau, 1.0 / omega, B.Ki));       // K_i = exp(-D_i/tau_i)/omega_i, :625-637
-        RC(frk_block_scatter(ctx, r, Knew, ni, B.d_ix, B.Ki));
-        RC(frk_scale(ctx, (int64_t)nn, omega, B.KinvBest));                       // K_i^-1 = omega_i exp(-D_i/tau_i)^-1
-        RC(frk_block_scatter(ctx, r, Kinvnew, ni, B.d_ix, B.KinvBest));
-        logdetK += bestLogdet - ni * std::log(omega);
+        nmb.emplace_back(new BlkNM());
+        BlkNM &S = *nmb.back();
+        S.B = &B; S.omega = omega;
+        S.spec.reset(new SpecNM{M, nullptr, 1, 100, 1e-4, std::vector<double>{par0}});
     }
+    if (!M->tensor) RC(blockexp_lockstep(M, nmb, Knew, Kinvnew, logdetK));
     FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat, Knew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat_inv, Kinvnew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     M->logdetK = logdetK;
@@ -905,11 +1029,6 @@ extern "C" int frk_model_destroy(frk_model *M) {
     cudaStreamSynchronize(M->ctx->stream);
     for (void *p : M->allocs) cudaFreeAsync(p, M->ctx->stream);
     frk_rowbuckets_destroy(M->bk);
-    for (auto &ln : M->lane) {
-        if (!ln.ctx) continue;
-        cudaStreamSynchronize(ln.ctx->stream);
-        for (double *p : {ln.Ki, ln.Kinv, ln.work}) if (p) cudaFreeAsync(p, M->ctx->stream);
-    }
     if (M->ev_lane) cudaEventDestroy(M->ev_lane);
     if (M->aux) cudaStreamSynchronize(M->aux->stream);          // the lane contexts themselves belong to M->ctx
     if (M->ev_aux0) cudaEventDestroy(M->ev_aux0);
