@@ -13,12 +13,14 @@
 // the same chol2inv(chol(Khat))), and the M-step's Khat_inv factorisation supplies the next log|K|.
 #include "common.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <functional>
 #include <limits>
 #include <memory>
 #include <string>
+#include <thread>
 
 namespace {
 
@@ -74,6 +76,7 @@ struct frk_model {
     // bound and fills a fraction of the SMs, so a few of them side by side cost little more than one)
     int lanes = 1;
     cudaEvent_t ev_lane = nullptr;
+    double t_phase[4] = {0, 0, 0, 0};   // FRK_PHASE_DEBUG: host seconds in posterior / update_K / rest of the M-step / Nelder-Mead rounds
     frk_ctx *aux = nullptr;          // low-priority lane: the sigma2fs quadratic form runs beside the (latency-bound) K update
     cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
 };
@@ -81,6 +84,8 @@ struct frk_model {
 namespace {
 
 #define RC(expr) do { if (int _rc = (expr)) return _rc; } while (0)
+
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 template <typename T>
 int dalloc(frk_model *M, T **out, size_t n) {
@@ -530,6 +535,9 @@ struct NMSlot {                    // one concurrent evaluation: context + buffe
 struct BlkNM {
     Block *B = nullptr;
     double omega = 0.0;
+    int rounds = 0;
+    cudaEvent_t ev_copy = nullptr;      // "the best inverse has been copied out of the slots" (recorded on slot 0's stream)
+    ~BlkNM() { if (ev_copy) cudaEventDestroy(ev_copy); }
     double bestF = std::numeric_limits<double>::infinity(), bestTau = -1.0, bestLogdet = 0.0;
     bool done = false;
     NMResult nm;
@@ -582,14 +590,16 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
         // Nelder-Mead returns its lowest vertex, a REQUESTED point (a speculative point that is never requested cannot be the result):
         // keep the inverse of the best requested point while it is still in a slot (slots are drained before any replay; the next
         // round starts after this copy)
+        if (!S.ev_copy) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&S.ev_copy, cudaEventDisableTiming));
         BlkNM *Sp = &S;
-        S.spec->requested = [M, Sp](const double *x, double f) -> int {
+        S.spec->requested = [Sp](const double *x, double f) -> int {
             if (!(f < Sp->bestF)) return 0;
             Sp->bestF = f; Sp->bestTau = -1.0;
             const size_t nn2 = (size_t)Sp->B->ni * Sp->B->ni;
             for (NMSlot &s : Sp->slot) {
                 if (!s.valid || s.pt != x[0]) continue;
-                FRK_CHECK_CUDA(cudaMemcpyAsync(Sp->B->KinvBest, s.Kinv, nn2 * sizeof(double), cudaMemcpyDeviceToDevice, M->ctx->stream));
+                FRK_CHECK_CUDA(cudaMemcpyAsync(Sp->B->KinvBest, s.Kinv, nn2 * sizeof(double), cudaMemcpyDeviceToDevice,
+                                               Sp->slot[0].ctx->stream));
                 Sp->bestTau = x[0]; Sp->bestLogdet = s.ld;
                 break;
             }
@@ -597,92 +607,165 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
         };
     }
 
-    // evaluate, for every block with a batch, the candidates with index in [k0, k0 + L) of this rank's share; drain; read the values
-    auto run_chunk = [&](int chunk) -> int {
-        FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));      // the lanes start once this stream has produced eta2 / saved the best inverses
-        int rc = 0;
-        for (int j = 0; j < nblk && !rc; j++) {
-            BlkNM &S = *nmb[j];
-            for (int c = 0; c < L && !rc; c++) {
-                NMSlot &s = S.slot[c];
-                s.used = false;
-                if (S.done) continue;
-                const int k = M->spec_emulate ? chunk * L + c : c * world + M->rank;    // candidate k -> rank k % world, lane k / world
-                if (k >= (int)S.batch.size()) continue;
-                s.k = k; s.valid = false;
-                const double tau = S.batch[k][0];
-                if (tau <= 1e-10) { S.fl[k] = std::numeric_limits<double>::infinity(); continue; }
-                if (s.ctx != ctx) FRK_CHECK_CUDA(cudaStreamWaitEvent(s.ctx->stream, M->ev_lane, 0));
-                rc = f_tau_enqueue(*S.B, s, tau);
-                s.used = true; s.pt = tau;
-            }
-        }
-        // every context that was started is drained before returning, error or not
-        for (int j = 0; j < nblk; j++)
-            for (NMSlot &s : nmb[j]->slot) {
-                if (!s.used) continue;
-                if (cudaStreamSynchronize(s.ctx->stream) != cudaSuccess && !rc) { frk_set_error("f_tau lane: stream synchronisation failed"); rc = 1; }
-                if (s.ctx != ctx) { ctx->launches += s.ctx->launches; s.ctx->launches = 0; }
-            }
-        if (rc) return rc;
-        for (int j = 0; j < nblk; j++) {
-            BlkNM &S = *nmb[j];
-            for (NMSlot &s : S.slot) {
-                if (!s.used) continue;
-                double logdetKi;
-                RC(frk_potrf_finish(s.ctx, &logdetKi));
-                const double t = s.ctx->h_pinned[FRK_PINNED_DOT];
-                const double f = -(0.5 * (-logdetKi) - S.omega / 2.0 * t);
-                S.fl[s.k] = f; s.ld = logdetKi; s.valid = std::isfinite(f);
-            }
+    // ---- building blocks of a round, per resolution j ----
+    // what does run j ask for next?  false: it has finished
+    auto begin_round = [&](int j, bool &active) -> int {
+        BlkNM &S = *nmb[j];
+        S.batch.clear();
+        S.fl.clear();
+        active = false;
+        if (S.done) return 0;
+        std::vector<double> need;
+        const int rc = S.spec->replay(need, S.nm);        // (also saves the best requested inverse out of the slots, on slot 0's stream)
+        if (rc == 0) { S.done = true; return 0; }
+        if (rc != 99) return rc;
+        S.batch.push_back(need);
+        if (W > 1) S.spec->candidates(need.data(), (size_t)W, S.batch);
+        S.fl.assign(S.batch.size(), 0.0);
+        S.rounds += 1;
+        active = true;
+        return 0;
+    };
+    // enqueue this rank's share of run j's batch: candidate k -> rank k % world, lane k / world (a pretend world is walked in chunks)
+    auto enqueue = [&](int j, int chunk) -> int {
+        BlkNM &S = *nmb[j];
+        // the slots' buffers may be overwritten once the copies of the last replay (slot 0's stream) have been made
+        FRK_CHECK_CUDA(cudaEventRecord(S.ev_copy, S.slot[0].ctx->stream));
+        for (int c = 0; c < L; c++) {
+            NMSlot &s = S.slot[c];
+            s.used = false;
+            const int k = M->spec_emulate ? chunk * L + c : c * world + M->rank;
+            if (k >= (int)S.batch.size()) continue;
+            s.k = k; s.valid = false;
+            const double tau = S.batch[k][0];
+            if (tau <= 1e-10) { S.fl[k] = std::numeric_limits<double>::infinity(); continue; }
+            if (c > 0) FRK_CHECK_CUDA(cudaStreamWaitEvent(s.ctx->stream, S.ev_copy, 0));
+            s.used = true; s.pt = tau;
+            RC(f_tau_enqueue(*S.B, s, tau));
         }
         return 0;
     };
+    auto finished = [&](int j) -> bool {                 // non-blocking: have all of run j's evaluations completed?
+        for (NMSlot &s : nmb[j]->slot)
+            if (s.used && cudaStreamQuery(s.ctx->stream) != cudaSuccess) return false;
+        return true;
+    };
+    auto drain = [&](int j) -> int {
+        int rc = 0;
+        for (NMSlot &s : nmb[j]->slot) {
+            if (!s.used) continue;
+            if (cudaStreamSynchronize(s.ctx->stream) != cudaSuccess && !rc) { frk_set_error("f_tau lane: stream synchronisation failed"); rc = 1; }
+            if (s.ctx != ctx) { ctx->launches += s.ctx->launches; s.ctx->launches = 0; }
+        }
+        return rc;
+    };
+    auto collect = [&](int j) -> int {                   // after drain: read the values out of the contexts' pinned staging
+        BlkNM &S = *nmb[j];
+        for (NMSlot &s : S.slot) {
+            if (!s.used) continue;
+            s.used = false;
+            double logdetKi;
+            RC(frk_potrf_finish(s.ctx, &logdetKi));
+            const double t = s.ctx->h_pinned[FRK_PINNED_DOT];
+            const double f = -(0.5 * (-logdetKi) - S.omega / 2.0 * t);
+            S.fl[s.k] = f; s.ld = logdetKi; s.valid = std::isfinite(f);
+        }
+        return 0;
+    };
+    auto commit = [&](int j) {                           // the round's values into run j's cache
+        BlkNM &S = *nmb[j];
+        for (size_t k = 0; k < S.batch.size(); k++) {
+            S.spec->pts.push_back(S.batch[k]); S.spec->fv.push_back(S.fl[k]); S.spec->owner.push_back((int)(k % world));
+        }
+        M->nm_evals += (double)S.batch.size();
+    };
 
-    for (;;) {
-        // 1. what does each run ask for next?
-        size_t maxbatch = 0;
-        for (int j = 0; j < nblk; j++) {
-            BlkNM &S = *nmb[j];
-            S.batch.clear();
-            S.fl.clear();
-            if (S.done) continue;
-            std::vector<double> need;
-            const int rc = S.spec->replay(need, S.nm);
-            if (rc == 0) { S.done = true; continue; }
-            if (rc != 99) return rc;
-            S.batch.push_back(need);
-            if (W > 1) S.spec->candidates(need.data(), (size_t)W, S.batch);
-            S.fl.assign(S.batch.size(), 0.0);
-            maxbatch = std::max(maxbatch, S.batch.size());
+    const double tr0 = now_s();
+    // every lane starts once this stream has produced eta2 of all resolutions
+    FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));
+    for (int j = 0; j < nblk; j++)
+        for (NMSlot &s : nmb[j]->slot)
+            if (s.ctx != ctx) FRK_CHECK_CUDA(cudaStreamWaitEvent(s.ctx->stream, M->ev_lane, 0));
+
+    if (!shared && !M->spec_emulate && !one_stream) {
+        // One rank: the runs advance INDEPENDENTLY -- a small resolution goes through all of its rounds while one evaluation of the
+        // largest is in flight.  The host polls the lanes and feeds whichever run has its values.
+        std::vector<char> inflight(nblk, 0);
+        int live = 0, rc = 0;
+        for (int j = 0; j < nblk && !rc; j++) {
+            bool active = false;
+            rc = begin_round(j, active);
+            if (!rc && active) { rc = enqueue(j, 0); inflight[j] = 1; live++; }
         }
-        if (maxbatch == 0) break;
-        M->nm_rounds += 1;
-        // 2. evaluate (one chunk, unless a pretend world is emulated on this rank)
-        const int nchunks = M->spec_emulate ? (int)((maxbatch + L - 1) / L) : 1;
-        for (int ch = 0; ch < nchunks; ch++) RC(run_chunk(ch));
-        // 3. share the values of all resolutions with one all-reduce
-        if (shared) {
-            std::vector<double> all;
-            for (int j = 0; j < nblk; j++) all.insert(all.end(), nmb[j]->fl.begin(), nmb[j]->fl.end());
-            // a value is +inf on its owner and 0 elsewhere -> the sum is right; (tau <= 1e-10 is +inf on every rank: inf + inf = inf)
-            for (int j = 0, o = 0; j < nblk; j++)
-                for (size_t k = 0; k < nmb[j]->fl.size(); k++, o++)
-                    if ((int)(k % world) != M->rank) all[o] = 0.0;
-            RC(reduce_host(M, all.data(), (int64_t)all.size(), 0));
-            for (int j = 0, o = 0; j < nblk; j++)
-                for (size_t k = 0; k < nmb[j]->fl.size(); k++, o++) nmb[j]->fl[k] = all[o];
-        }
-        // 4. into the caches
-        for (int j = 0; j < nblk; j++) {
-            BlkNM &S = *nmb[j];
-            for (size_t k = 0; k < S.batch.size(); k++) {
-                S.spec->pts.push_back(S.batch[k]); S.spec->fv.push_back(S.fl[k]); S.spec->owner.push_back((int)(k % world));
+        while (live > 0 && !rc) {
+            bool progressed = false;
+            for (int j = 0; j < nblk && !rc; j++) {
+                if (!inflight[j] || !finished(j)) continue;
+                progressed = true;
+                inflight[j] = 0; live--;
+                if ((rc = drain(j)) || (rc = collect(j))) break;
+                commit(j);
+                bool active = false;
+                rc = begin_round(j, active);
+                if (!rc && active) { rc = enqueue(j, 0); inflight[j] = 1; live++; }
             }
-            M->nm_evals += (double)S.batch.size();
+            if (!progressed) std::this_thread::yield();
+        }
+        for (int j = 0; j < nblk; j++) if (inflight[j]) drain(j);     // error path: leave nothing running
+        if (rc) return rc;
+        for (int j = 0; j < nblk; j++) M->nm_rounds = std::max(M->nm_rounds, (double)nmb[j]->rounds);
+    } else {
+        // Several ranks (or a pretend world): LOCKSTEP, so that every rank issues the same all-reduces in the same order
+        for (;;) {
+            size_t maxbatch = 0;
+            for (int j = 0; j < nblk; j++) {
+                bool active = false;
+                RC(begin_round(j, active));
+                if (active) maxbatch = std::max(maxbatch, nmb[j]->batch.size());
+            }
+            if (maxbatch == 0) break;
+            M->nm_rounds += 1;
+            const int nchunks = M->spec_emulate ? (int)((maxbatch + L - 1) / L) : 1;
+            for (int ch = 0; ch < nchunks; ch++) {
+                int rc = 0;
+                if (one_stream) {      // every slot is this context (one pinned staging buffer): one resolution at a time
+                    for (int j = 0; j < nblk && !rc; j++) {
+                        if (nmb[j]->batch.empty()) continue;
+                        rc = enqueue(j, ch);
+                        const int rd = drain(j);
+                        if (!rc) rc = rd;
+                        if (!rc) rc = collect(j);
+                    }
+                    if (rc) return rc;
+                    continue;
+                }
+                for (int j = 0; j < nblk && !rc; j++) if (!nmb[j]->batch.empty()) rc = enqueue(j, ch);
+                for (int j = 0; j < nblk; j++) { const int rd = drain(j); if (!rc) rc = rd; }    // drained error or not
+                if (rc) return rc;
+                for (int j = 0; j < nblk; j++) RC(collect(j));
+            }
+            if (shared) {     // the values of all resolutions in one all-reduce (a value is set on its owner and 0 elsewhere)
+                std::vector<double> all;
+                for (int j = 0; j < nblk; j++) all.insert(all.end(), nmb[j]->fl.begin(), nmb[j]->fl.end());
+                RC(reduce_host(M, all.data(), (int64_t)all.size(), 0));
+                for (int j = 0, o = 0; j < nblk; j++)
+                    for (size_t k = 0; k < nmb[j]->fl.size(); k++, o++) nmb[j]->fl[k] = all[o];
+            }
+            for (int j = 0; j < nblk; j++) commit(j);
         }
     }
-
+    // the saved inverses (slot 0's stream of each resolution) and the slots themselves are consumed on this context's stream below
+    for (int j = 0; j < nblk; j++) {
+        FRK_CHECK_CUDA(cudaEventRecord(nmb[j]->ev_copy, nmb[j]->slot[0].ctx->stream));
+        FRK_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, nmb[j]->ev_copy, 0));
+    }
+    M->t_phase[3] += now_s() - tr0;
+    static const bool rounds_dbg = getenv("FRK_PHASE_DEBUG") != nullptr;
+    if (rounds_dbg && M->rank == 0) {
+        fprintf(stderr, "[frk nm] %.3f ms;", 1e3 * (now_s() - tr0));
+        for (int j = 0; j < nblk; j++) fprintf(stderr, " block %d (n=%d): %d rounds, %zu points;", j, nmb[j]->B->ni, nmb[j]->rounds, nmb[j]->spec->pts.size());
+        fprintf(stderr, "\n");
+    }
     // K_i = exp(-D_i/tau_i)/omega_i and its inverse into place, :625-637
     for (int j = 0; j < nblk; j++) {
         BlkNM &S = *nmb[j];
@@ -705,6 +788,7 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
                 const double f = -(0.5 * (-logdetKi) - omega / 2.0 * s.ctx->h_pinned[FRK_PINNED_DOT]);
                 s.pt = tau; s.ld = logdetKi; s.valid = std::isfinite(f);
                 RC(S.spec->requested(&tau, f));
+                FRK_CHECK_CUDA(cudaStreamSynchronize(s.ctx->stream));            // (the copy above went to this slot's stream)
                 M->nm_reevals += 1;
                 FRK_REQUIRE(S.bestTau == tau, "block-exponential update: tau = %g cannot be evaluated", tau);
             }
@@ -896,7 +980,11 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
         ctx->launches += M->aux->launches;
         M->aux->launches = 0;
     }
+    const double tk0 = now_s();
     RC(update_K(M, K_type, nlambda, lambda, h_res, have_inverse));   // :270-272
+    const double tk1 = now_s();
+    M->t_phase[1] += tk1 - tk0;
+    struct Rest { frk_model *M; double t0; ~Rest() { M->t_phase[2] += now_s() - t0; } } rest_timer{M, tk1};
     if (!have_inverse) {
         FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, M->Khat, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         RC(chol2inv_logdet(ctx, r, M->w1, M->Khat_inv, M->w2, &M->logdetK));   // Khat_inv = chol2inv(chol(K)), :273
@@ -1161,15 +1249,23 @@ extern "C" int frk_model_em_fit(frk_model *M, int n_EM, double tol, int K_type, 
                 "K_type needs to be \"block-exponential\" or \"unstructured\" for method = \"EM\"");
     if (known_sigma2fs_given) M->sigma2fs = known_sigma2fs;          // R/SREfit.R:19
     int i = 0;
+    static const bool phase_dbg = getenv("FRK_PHASE_DEBUG") != nullptr;
+    for (int k = 0; k < 4; k++) M->t_phase[k] = 0.0;
     for (i = 0; i < n_EM; i++) {
         double o[4];
+        const double t0 = now_s();
         RC(posterior(M, M->alpha, M->sigma2fs, M->Q_eta, M->S_eta, M->mu_eta, o));   // logLik + E-step, :105-106
         h_llk[i] = llk_from(M, o);
+        M->t_phase[0] += now_s() - t0;
         RC(mstep(M, K_type, nlambda, h_lambda, h_res, known_sigma2fs_given, known_sigma2fs));   // :107
         if (i > 0 && std::fabs(h_llk[i] - h_llk[i - 1]) < tol) { i++; break; }    // :110-114
     }
     *h_niter = std::min(i, n_EM);
     FRK_CHECK_CUDA(cudaStreamSynchronize(M->ctx->stream));
+    if (phase_dbg && M->rank == 0 && *h_niter > 0)
+        fprintf(stderr, "[frk phases] per iteration over %d: posterior %.3f ms, update_K %.3f ms (Nelder-Mead rounds %.3f), rest of M-step %.3f ms\n",
+                *h_niter, 1e3 * M->t_phase[0] / *h_niter, 1e3 * M->t_phase[1] / *h_niter, 1e3 * M->t_phase[3] / *h_niter,
+                1e3 * M->t_phase[2] / *h_niter);
     return 0;
 }
 
