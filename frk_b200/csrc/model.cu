@@ -77,8 +77,10 @@ struct frk_model {
     int lanes = 1;
     cudaEvent_t ev_lane = nullptr;
     double t_phase[4] = {0, 0, 0, 0};   // FRK_PHASE_DEBUG: host seconds in posterior / update_K / rest of the M-step / Nelder-Mead rounds
-    frk_ctx *aux = nullptr;          // low-priority lane: the sigma2fs quadratic form runs beside the (latency-bound) K update
+    frk_ctx *aux = nullptr;          // low-priority lane: the sigma2fs update and the next Gram run beside the (latency-bound) K update
     cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
+    bool gram_early = false;         // acc already holds the Gram for (gram_alpha, gram_s2): enqueued on aux, completion = ev_aux1
+    double gram_alpha[MAXP_M] = {0, 0, 0, 0}, gram_s2 = 0.0;
 };
 
 namespace {
@@ -146,10 +148,10 @@ int solve_small(int p, const double *A, const double *b, double *x) {
 struct MSums { double uxx[16], uxz[4], sv, w0, wx[4], wxx[16]; };
 
 // R/SREfit.R:335-356,391-405,408-417: the row sums behind J(sigma2fs), alpha and the closed-form sigma2fs
-int mstep_sums(frk_model *M, double sigma2fs, int mode, MSums &s) {
+int mstep_sums(frk_model *M, frk_ctx *c, double sigma2fs, int mode, MSums &s) {
     const int p = M->p, ns = 2 * p * p + 2 * p + 2;
     double out[2 * 16 + 2 * 4 + 2];
-    RC(frk_mstep_sums(M->ctx, M->m, p, M->X, M->Z, M->t, M->q, M->Ve, M->Vfs, sigma2fs, mode, out));
+    RC(frk_mstep_sums(c, M->m, p, M->X, M->Z, M->t, M->q, M->Ve, M->Vfs, sigma2fs, mode, out));
     RC(reduce_host(M, out, ns, 0));                                  // O(p^2) doubles
     int o = 0;
     for (int i = 0; i < p * p; i++) s.uxx[i] = out[o++];
@@ -161,8 +163,8 @@ int mstep_sums(frk_model *M, double sigma2fs, int mode, MSums &s) {
 }
 
 // alpha = (sum u x x')^-1 sum u x (z - t);  sumwOm = sum w Omega(alpha)
-int gls_and_sums(frk_model *M, double s2, int mode, double *al, MSums &s, double &sumwOm) {
-    RC(mstep_sums(M, s2, mode, s));
+int gls_and_sums(frk_model *M, frk_ctx *c, double s2, int mode, double *al, MSums &s, double &sumwOm) {
+    RC(mstep_sums(M, c, s2, mode, s));
     RC(solve_small(M->p, s.uxx, s.uxz, al));
     const int p = M->p;
     double lin = 0.0, quad = 0.0;
@@ -476,6 +478,13 @@ struct SpecNM {
 // acc = [upper(S'D^-1 S) | S'D^-1 rho | rho'D^-1 rho | sum log d], summed over ranks
 int gram(frk_model *M, const double *alpha, double sigma2fs) {
     const size_t n = (size_t)M->r * M->r + M->r + 2;
+    if (M->gram_early) {              // computed beside the previous K update for exactly these parameters?
+        M->gram_early = false;
+        bool same = sigma2fs == M->gram_s2;
+        for (int i = 0; i < M->p; i++) same = same && alpha[i] == M->gram_alpha[i];
+        FRK_CHECK_CUDA(cudaStreamWaitEvent(M->ctx->stream, M->ev_aux1, 0));       // either way acc is not touched before aux is done
+        if (same) return 0;
+    }
     FRK_CHECK_CUDA(cudaMemsetAsync(M->acc, 0, n * sizeof(double), M->ctx->stream));
     RC(frk_gram_rhs_bucketed(M->ctx, M->m, M->r, M->rowptr, M->col, M->val, M->bk,
                              M->Z, M->X, M->p, alpha, M->Ve, M->Vfs, sigma2fs, M->acc));
@@ -557,7 +566,8 @@ int f_tau_enqueue(const Block &B, NMSlot &s, double tau) {
     return frk_dot_async(s.ctx, (int64_t)nn, s.Kinv, B.eta2);
 }
 
-int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, double *Knew, double *Kinvnew, double &logdetK) {
+int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, double *Knew, double *Kinvnew, double &logdetK,
+                      const std::function<int()> &side_work) {
     frk_ctx *ctx = M->ctx;
     const int r = M->r, nblk = (int)nmb.size();
     const int world = std::max(M->world, 1);
@@ -697,6 +707,9 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
             rc = begin_round(j, active);
             if (!rc && active) { rc = enqueue(j, 0); inflight[j] = 1; live++; }
         }
+        // with the first evaluations in flight the host is free: the rest of the M-step (sigma2fs, alpha) and the next iteration's
+        // Gram matrix are driven from here, on their own low-priority lane
+        if (!rc && side_work) rc = side_work();
         while (live > 0 && !rc) {
             bool progressed = false;
             for (int j = 0; j < nblk && !rc; j++) {
@@ -812,7 +825,8 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
 // ---------------------------------------------------------------------------------
 // M-step
 // ---------------------------------------------------------------------------------
-int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const int *h_res, bool &have_inverse) {
+int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const int *h_res, bool &have_inverse,
+             const std::function<int()> &side_work) {
     have_inverse = false;
     frk_ctx *ctx = M->ctx;
     const int r = M->r;
@@ -948,7 +962,7 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         S.B = &B; S.omega = omega;
         S.spec.reset(new SpecNM{M, nullptr, 1, 100, 1e-4, std::vector<double>{par0}});
     }
-    if (!M->tensor) RC(blockexp_lockstep(M, nmb, Knew, Kinvnew, logdetK));
+    if (!M->tensor) RC(blockexp_lockstep(M, nmb, Knew, Kinvnew, logdetK, side_work));
     FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat, Knew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat_inv, Kinvnew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     M->logdetK = logdetK;
@@ -980,8 +994,76 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
         ctx->launches += M->aux->launches;
         M->aux->launches = 0;
     }
+    const bool est = !known;
+    bool sigma_done = false;
+    // sigma2fs and alpha (:275-430).  Everything here depends on the E-step only, not on K: with `beside` it runs on the aux lane
+    // (after the quadratic form) while the Nelder-Mead evaluations are in flight, and is followed there by the NEXT iteration's Gram.
+    auto sigma_update = [&]() -> int {
+        sigma_done = true;
+        frk_ctx *c = beside ? M->aux : ctx;
+        double s2new = est ? sigma2fs : known_sigma2fs;
+        if (!beside) RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
+        double al[MAXP_M];
+        MSums s;
+        double swo;
+        auto J = [&](double s2, double &val) -> int {                    // :335-356
+            if (s2 < 0) { val = std::numeric_limits<double>::infinity(); return 0; }
+            double a2[MAXP_M]; MSums ss; double sw;
+            RC(gls_and_sums(M, c, s2, 0, a2, ss, sw));
+            val = -(-0.5 * ss.sv + 0.5 * sw);
+            return 0;
+        };
+        auto sgn = [](double v) { return (v > 0) - (v < 0); };
+        if (!M->all_vfs_zero) {
+            if (!M->homoscedastic) {
+                if (est) {
+                    double amp = 10.0;
+                    bool ok = false;
+                    while (!ok) {                                        // :368-380
+                        amp *= 10;
+                        double j1, j2;
+                        RC(J(sigma2fs / amp, j1));
+                        RC(J(sigma2fs * amp, j2));
+                        if (sgn(j1) != sgn(j2) || std::isnan(j1) || std::isnan(j2)) ok = true;
+                        if (amp > 1e9) ok = true;
+                    }
+                    if (amp > 1e9) s2new = 0.0;
+                    else RC(zeroin(J, sigma2fs / amp, sigma2fs * amp, s2new));   // uniroot, :386-388
+                }
+                RC(gls_and_sums(M, c, s2new, 0, al, s, swo));            // :391-400
+            } else {
+                RC(gls_and_sums(M, c, 0.0, 1, al, s, swo));              // :404-405
+                if (est) {
+                    s2new = 1.0 / M->Vfs0 * (swo / M->m_total - M->Ve0); // :408-417
+                    if (s2new < 0) s2new = 0.0;
+                }
+            }
+        } else {                                                         // :424-428
+            RC(gls_and_sums(M, c, 0.0, 0, al, s, swo));
+            if (est) s2new = 0.0;
+        }
+        for (int i = 0; i < p; i++) M->alpha[i] = al[i];
+        M->sigma2fs = s2new;
+        if (beside && !M->allreduce) {
+            // the next E-step's Gram matrix (R/SREfit.R:252) needs only these two: enqueue it behind the sums, beside the K update
+            const size_t n = rr + r + 2;
+            FRK_CHECK_CUDA(cudaMemsetAsync(M->acc, 0, n * sizeof(double), c->stream));
+            RC(frk_gram_rhs_bucketed(c, M->m, r, M->rowptr, M->col, M->val, M->bk, M->Z, M->X, p, M->alpha, M->Ve, M->Vfs,
+                                     M->sigma2fs, M->acc));
+            M->gram_early = true;
+            M->gram_s2 = M->sigma2fs;
+            for (int i = 0; i < p; i++) M->gram_alpha[i] = M->alpha[i];
+        }
+        if (beside) {
+            FRK_CHECK_CUDA(cudaEventRecord(M->ev_aux1, c->stream));
+            ctx->launches += c->launches;
+            c->launches = 0;
+        }
+        return 0;
+    };
     const double tk0 = now_s();
-    RC(update_K(M, K_type, nlambda, lambda, h_res, have_inverse));   // :270-272
+    // (the callback is only used where the host is otherwise idle: one rank, plain basis, lanes available)
+    RC(update_K(M, K_type, nlambda, lambda, h_res, have_inverse, beside ? std::function<int()>(sigma_update) : std::function<int()>()));   // :270-272
     const double tk1 = now_s();
     M->t_phase[1] += tk1 - tk0;
     struct Rest { frk_model *M; double t0; ~Rest() { M->t_phase[2] += now_s() - t0; } } rest_timer{M, tk1};
@@ -990,51 +1072,8 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
         RC(chol2inv_logdet(ctx, r, M->w1, M->Khat_inv, M->w2, &M->logdetK));   // Khat_inv = chol2inv(chol(K)), :273
         M->khat_block_diag = false;
     }
-    const bool est = !known;
-    double s2new = est ? sigma2fs : known_sigma2fs;
-    if (beside) FRK_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, M->ev_aux1, 0));
-    else RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
-    double al[MAXP_M];
-    MSums s;
-    double swo;
-    auto J = [&](double s2, double &val) -> int {                    // :335-356
-        if (s2 < 0) { val = std::numeric_limits<double>::infinity(); return 0; }
-        double a2[MAXP_M]; MSums ss; double sw;
-        RC(gls_and_sums(M, s2, 0, a2, ss, sw));
-        val = -(-0.5 * ss.sv + 0.5 * sw);
-        return 0;
-    };
-    auto sgn = [](double v) { return (v > 0) - (v < 0); };
-    if (!M->all_vfs_zero) {
-        if (!M->homoscedastic) {
-            if (est) {
-                double amp = 10.0;
-                bool ok = false;
-                while (!ok) {                                        // :368-380
-                    amp *= 10;
-                    double j1, j2;
-                    RC(J(sigma2fs / amp, j1));
-                    RC(J(sigma2fs * amp, j2));
-                    if (sgn(j1) != sgn(j2) || std::isnan(j1) || std::isnan(j2)) ok = true;
-                    if (amp > 1e9) ok = true;
-                }
-                if (amp > 1e9) s2new = 0.0;
-                else RC(zeroin(J, sigma2fs / amp, sigma2fs * amp, s2new));   // uniroot, :386-388
-            }
-            RC(gls_and_sums(M, s2new, 0, al, s, swo));               // :391-400
-        } else {
-            RC(gls_and_sums(M, 0.0, 1, al, s, swo));                 // :404-405
-            if (est) {
-                s2new = 1.0 / M->Vfs0 * (swo / M->m_total - M->Ve0); // :408-417
-                if (s2new < 0) s2new = 0.0;
-            }
-        }
-    } else {                                                         // :424-428
-        RC(gls_and_sums(M, 0.0, 0, al, s, swo));
-        if (est) s2new = 0.0;
-    }
-    for (int i = 0; i < p; i++) M->alpha[i] = al[i];
-    M->sigma2fs = s2new;
+    if (!sigma_done) RC(sigma_update());
+    if (beside && !M->gram_early) FRK_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, M->ev_aux1, 0));
     return 0;
 }
 
@@ -1114,11 +1153,11 @@ extern "C" int frk_model_create_host(frk_ctx *ctx, int64_t m, int r, int p, cons
 extern "C" int frk_model_destroy(frk_model *M) {
     if (!M) return 0;
     cudaSetDevice(M->ctx->device);
-    cudaStreamSynchronize(M->ctx->stream);
+    if (M->aux) cudaStreamSynchronize(M->aux->stream);          // nothing of this model may still be running on the lanes when its
+    cudaStreamSynchronize(M->ctx->stream);                      // buffers go back to the pool (the lane contexts belong to M->ctx)
     for (void *p : M->allocs) cudaFreeAsync(p, M->ctx->stream);
     frk_rowbuckets_destroy(M->bk);
     if (M->ev_lane) cudaEventDestroy(M->ev_lane);
-    if (M->aux) cudaStreamSynchronize(M->aux->stream);          // the lane contexts themselves belong to M->ctx
     if (M->ev_aux0) cudaEventDestroy(M->ev_aux0);
     if (M->ev_aux1) cudaEventDestroy(M->ev_aux1);
     delete M;
@@ -1235,7 +1274,7 @@ extern "C" int frk_model_init(frk_model *M) {
     // alpha = (X'X)^-1 X'Z: the mode-1 moments with t = 0
     FRK_CHECK_CUDA(cudaMemsetAsync(M->t, 0, std::max<int64_t>(M->m, 1) * sizeof(double), ctx->stream));
     MSums s;
-    RC(mstep_sums(M, 0.0, 1, s));
+    RC(mstep_sums(M, M->ctx, 0.0, 1, s));
     RC(solve_small(M->p, s.uxx, s.uxz, M->alpha));
     M->initialised = true;
     return 0;
@@ -1261,6 +1300,7 @@ extern "C" int frk_model_em_fit(frk_model *M, int n_EM, double tol, int K_type, 
         if (i > 0 && std::fabs(h_llk[i] - h_llk[i - 1]) < tol) { i++; break; }    // :110-114
     }
     *h_niter = std::min(i, n_EM);
+    if (M->aux) FRK_CHECK_CUDA(cudaStreamSynchronize(M->aux->stream));   // (an early Gram for the next call may still be in flight)
     FRK_CHECK_CUDA(cudaStreamSynchronize(M->ctx->stream));
     if (phase_dbg && M->rank == 0 && *h_niter > 0)
         fprintf(stderr, "[frk phases] per iteration over %d: posterior %.3f ms, update_K %.3f ms (Nelder-Mead rounds %.3f), rest of M-step %.3f ms\n",
