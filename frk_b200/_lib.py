@@ -57,6 +57,8 @@ SIGNATURES = {
     "frk_basis_create": (c_int, [vp, c_int, c_dbl, c_int, c_int, c_int, vp, vp, vp, C.POINTER(vp)]),
     "frk_basis_destroy": (c_int, [vp]),
     "frk_basis_dist_matrix": (c_int, [vp, vp, c_int, vp, vp]),
+    "frk_basis_nn_dist": (c_int, [vp, vp, c_int, vp]),
+    "frk_csr_colsums": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp]),
     "frk_basis_n": (c_int, [vp]),
     "frk_basis_dim": (c_int, [vp]),
     "frk_eval_basis_count": (c_int, [vp, vp, c_i64, vp, c_i64, vp, p_i64]),

@@ -115,23 +115,42 @@ def _seq_len(a, b, n):
     return a + np.arange(n, dtype=np.float64) * ((b - a) / (n - 1))
 
 
+def _nn_scale_device(dev: Device, manifold: Manifold, this: np.ndarray, zero_is_inf: bool) -> np.ndarray:
+    """distance to the nearest other centroid on the device (frk_basis_nn_dist), R/basisfns.R:485-511."""
+    k = this.shape[0]
+    tmp = Basis(manifold, this, np.ones(k), np.ones(k, dtype=np.int32), "Gaussian", 0)    # non-compact type: no cell lists are built
+    out = dev.empty(k)
+    call("frk_basis_nn_dist", dev.ctx, tmp.handle(dev), 1 if zero_is_inf else 0, dev.ptr(out))
+    return dev.download(out, k)
+
+
+def _colsums_device(dev: Device, basis, coords: np.ndarray) -> np.ndarray:
+    """colSums(eval_basis(basis, coords)) on the device, R/basisfns.R:543."""
+    S = eval_basis_device(basis, coords, dev)
+    out = dev.empty(basis.n)
+    call("frk_csr_colsums", dev.ctx, S.n, S.ncol, dev.ptr(S.rowptr), dev.ptr(S.col), dev.ptr(S.val), dev.ptr(out))
+    return dev.download(out, basis.n)
+
+
 def auto_basis(manifold: Manifold, data, regular: int = 1, nres: int = 3, prune: float = 0, type: str = "bisquare",
                isea3h_lo: int = 2, scale_aperture: Optional[float] = None, isea3h: Optional[dict] = None,
-               subsamp: Optional[int] = None) -> Basis:
+               subsamp: Optional[int] = None, dev: Optional[Device] = None) -> Basis:
     """auto_basis() regular placement, R/basisfns.R:218-585.
 
-    Deterministic subset of the reference: ``prune`` must be 0 and the placement uses all data
-    coordinates (the reference subsamples 10,000 points with R's RNG when n > subsamp, which no
-    other implementation can reproduce -- pass the coordinates you want the ranges taken from).
-    Sphere placement needs the ISEA3H centroids (``isea3h`` = {resolution: (n x 2) lon/lat}).
+    The placement uses all data coordinates (the reference subsamples 10,000 points with R's RNG when n > subsamp, which no
+    other implementation can reproduce -- pass the coordinates you want the ranges taken from).  ``prune > 0`` (deprecated in
+    the reference, still used by its vignettes): basis functions with colSums(eval_basis(., data)) < prune are removed and the
+    scales re-derived (:536-553) -- eval_basis and the column sums run on the device, as does the nearest-centroid search for
+    resolutions with >= 5000 centroids (:497-509).  Sphere placement needs the ISEA3H centroids (``isea3h`` = {resolution:
+    (n x 2) lon/lat}).
     """
     if manifold.kind in ("STplane", "STsphere"):
         # the reference builds TensorP(auto_basis(<spatial>), 10 Gaussian time functions) from the STIDF's
         # time stamps (R/basisfns.R:243-289); there is no spacetime container here, so be explicit
         raise FRKError("auto_basis on a space-time manifold: build TensorP(auto_basis(plane()|sphere(), ...), "
                        "local_basis(real_line(), ...)) explicitly; local_basis(STplane()|STsphere(), ...) is supported")
-    if prune:
-        raise FRKError("auto_basis(prune > 0) is deprecated in the reference and not on the device path")
+    if prune < 0:
+        raise ValueError("prune needs to be greater than zero")
     if not regular and manifold.kind == "plane":
         raise FRKError("irregular placement needs fmesher (host geometry, out of scope); use regular >= 1")
     if type not in BASIS_TYPES:
@@ -141,6 +160,7 @@ def auto_basis(manifold: Manifold, data, regular: int = 1, nres: int = 3, prune:
         coords = coords[:, None]
     if scale_aperture is None:
         scale_aperture = 1.0 if manifold.kind == "sphere" else 1.25
+    mult = 1.5 if type == "bisquare" else 0.7
     xr = (coords[:, 0].min(), coords[:, 0].max())
     yr = (coords[:, 1].min(), coords[:, 1].max()) if coords.shape[1] > 1 else (0.0, 0.0)
     if manifold.kind == "plane":
@@ -165,18 +185,41 @@ def auto_basis(manifold: Manifold, data, regular: int = 1, nres: int = 3, prune:
             if isea3h is None:
                 raise FRKError("auto_basis on the sphere needs the ISEA3H centroids (isea3h=...)")
             this = np.asarray(isea3h[i + isea3h_lo - 1], dtype=np.float64)
-        k = this.shape[0]
-        if k == 1:
-            base = np.array([max(xr[1] - xr[0], yr[1] - yr[0]) / 2.0])
-        elif k < 5000:
-            D = host_distance(manifold, this, this)
-            np.fill_diagonal(D, np.inf)
-            base = D.min(axis=1) * scale_aperture
-        else:
-            base = np.full(k, min(abs(xg[1] - xg[0]), abs(yg[1] - yg[0]))) * scale_aperture
+        base = np.zeros(0)
+        for j in (1, 2):                                   # twice when pruning: the scales are re-derived from the survivors
+            k = this.shape[0]
+            if k == 0:
+                base = np.zeros(0)
+                break
+            if k == 1:
+                base = np.array([max(xr[1] - xr[0], yr[1] - yr[0]) / 2.0])
+            elif k < 5000:
+                D = host_distance(manifold, this, this)
+                np.fill_diagonal(D, np.inf)
+                base = D.min(axis=1) * scale_aperture
+            elif not prune and regular and manifold.kind == "plane":
+                base = np.full(k, min(abs(xg[1] - xg[0]), abs(yg[1] - yg[0]))) * scale_aperture
+            else:                                          # :497-509, batched in the reference; one kernel here
+                base = _nn_scale_device(dev or get_device(), manifold, this, zero_is_inf=True) * scale_aperture
+            if not prune:
+                break
+            if j == 1:
+                cand = Basis(manifold, this, mult * base, np.full(k, i, dtype=np.int32), type, int(regular))
+                keep = ~(_colsums_device(dev or get_device(), cand, coords[:, :manifold.dim]) < prune)
+                if not keep.any():
+                    import warnings
+                    warnings.warn("prune is too large -- all functions at a resolution removed. "
+                                  "Consider also removing number of resolutions.")
+                if keep.all():
+                    break                                  # nothing removed: the second pass would reproduce the same scales
+                this = this[keep]
+        if this.shape[0] == 0:
+            continue
         locs.append(this)
-        scales.append((1.5 if type == "bisquare" else 0.7) * base)
-        ress.append(np.full(k, i, dtype=np.int32))
+        scales.append(mult * base)
+        ress.append(np.full(this.shape[0], i, dtype=np.int32))
+    if not locs:
+        raise FRKError("auto_basis: prune removed every basis function")
     return Basis(manifold, np.vstack(locs), np.concatenate(scales), np.concatenate(ress), type, int(regular))
 
 

@@ -626,3 +626,55 @@ extern "C" int frk_basis_dist_matrix(frk_ctx *ctx, const frk_basis *b, int ni, c
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// auto_basis helpers: nearest-centroid distance (scale rule) and column sums (pruning)
+// ---------------------------------------------------------------------------------
+template <int MAN>
+__global__ void __launch_bounds__(128) nn_dist_kernel(BasisDev B, int zero_is_inf, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.r) return;
+    PointCoord p;
+    p.a = __ldg(B.c0 + i); p.b = __ldg(B.c1 + i); p.c = __ldg(B.c2 + i); p.t = __ldg(B.c3 + i); p.u = p.v = 0;
+    double best = __longlong_as_double(0x7ff0000000000000LL);   // +Inf
+    for (int j = 0; j < B.r; j++) {
+        if (!zero_is_inf && j == i) continue;
+        const double y = basis_dist<MAN>(p, B, j);
+        if (zero_is_inf && y == 0.0) continue;
+        best = fmin(best, y);
+    }
+    out[i] = best;
+}
+
+extern "C" int frk_basis_nn_dist(frk_ctx *ctx, const frk_basis *b, int zero_is_inf, double *d_out) {
+    FRK_REQUIRE(ctx && b && d_out, "frk_basis_nn_dist: NULL argument");
+    const unsigned grid = (unsigned)cdiv(b->dev.r, 128);
+    switch (b->dev.manifold) {
+        case FRK_SPHERE:   FRK_LAUNCH(ctx, nn_dist_kernel<FRK_SPHERE>, grid, 128, 0, b->dev, zero_is_inf, d_out); break;
+        case FRK_PLANE:    FRK_LAUNCH(ctx, nn_dist_kernel<FRK_PLANE>, grid, 128, 0, b->dev, zero_is_inf, d_out); break;
+        case FRK_STPLANE:  FRK_LAUNCH(ctx, nn_dist_kernel<FRK_STPLANE>, grid, 128, 0, b->dev, zero_is_inf, d_out); break;
+        case FRK_STSPHERE: FRK_LAUNCH(ctx, nn_dist_kernel<FRK_STSPHERE>, grid, 128, 0, b->dev, zero_is_inf, d_out); break;
+        default:           FRK_LAUNCH(ctx, nn_dist_kernel<FRK_REAL_LINE>, grid, 128, 0, b->dev, zero_is_inf, d_out); break;
+    }
+    return 0;
+}
+
+// one warp per row chunk; fp64 atomics (the sums feed a threshold test, not the model)
+__global__ void __launch_bounds__(256) csr_colsums_kernel(int64_t nnz, const int *__restrict__ col, const double *__restrict__ val,
+                                                          double *__restrict__ out) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(out + col[k], val[k]);
+}
+
+extern "C" int frk_csr_colsums(frk_ctx *ctx, int64_t n, int ncol, const int *d_rowptr, const int *d_col, const double *d_val, double *d_out) {
+    FRK_REQUIRE(ctx && d_rowptr && d_out && ncol > 0 && n >= 0, "frk_csr_colsums: bad argument");
+    FRK_CHECK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)ncol * sizeof(double), ctx->stream));
+    if (n == 0) return 0;
+    int nnz = 0;
+    FRK_CHECK_CUDA(cudaMemcpyAsync(&nnz, d_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nnz == 0) return 0;
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(nnz, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, csr_colsums_kernel, grid, 256, 0, (int64_t)nnz, d_col, d_val, d_out);
+    return 0;
+}

@@ -657,8 +657,8 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
     };
     auto finished = [&](int j) -> bool {                 // non-blocking: have all of run j's evaluations completed?
         for (NMSlot &s : nmb[j]->slot)
-            if (s.used && cudaStreamQuery(s.ctx->stream) != cudaSuccess) return false;
-        return true;
+            if (s.used && cudaStreamQuery(s.ctx->stream) == cudaErrorNotReady) return false;
+        return true;                                     // completed -- or failed, which drain() reports (never spin on an error)
     };
     auto drain = [&](int j) -> int {
         int rc = 0;

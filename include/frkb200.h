@@ -86,6 +86,10 @@ int frk_basis_create(frk_ctx *ctx, int manifold, double radius, int type, int d,
 int frk_basis_destroy(frk_basis *b);
 /* BuildD (R/basisfns.R:1131-1153) for the ni centroids d_idx: d_D[a + ni*b] = distance(centroid idx[a], centroid idx[b]) */
 int frk_basis_dist_matrix(frk_ctx *ctx, const frk_basis *b, int ni, const int *d_idx, double *d_D);
+/* auto_basis scale rule (R/basisfns.R:485-511): d_out[i] = distance from centroid i to its nearest other centroid, in the manifold's
+ * measure.  zero_is_inf = 0: only the centroid itself is excluded (diag(D) <- Inf, :488-490); != 0: every zero distance is
+ * (D[D == 0] <- Inf, the batched branch for >= 5000 centroids, :497-509).  Inf when there is no other centroid.               */
+int frk_basis_nn_dist(frk_ctx *ctx, const frk_basis *b, int zero_is_inf, double *d_out);
 int frk_basis_n(const frk_basis *b);     /* number of basis functions r     */
 int frk_basis_dim(const frk_basis *b);   /* manifold dimension d (1 or 2)    */
 
@@ -108,6 +112,9 @@ int frk_csr_tensor_fill(frk_ctx *ctx, int64_t n, int r1,
                         const int *d_rowptr1, const int *d_col1, const double *d_val1,
                         const int *d_rowptr2, const int *d_col2, const double *d_val2,
                         const int *d_rowptr, int *d_col, double *d_val);
+/* colSums(S) of a CSR matrix into d_out[ncol] (zeroed here): the influence of the data on each basis function that
+ * auto_basis(prune > 0) thresholds, R/basisfns.R:536-553 */
+int frk_csr_colsums(frk_ctx *ctx, int64_t n, int ncol, const int *d_rowptr, const int *d_col, const double *d_val, double *d_out);
 /* SRE() row normalisation on an existing CSR: R/SRE.R:416-421 */
 int frk_csr_row_normalise(frk_ctx *ctx, int64_t n, const int *d_rowptr, double *d_val);
 

@@ -235,8 +235,8 @@ def _r_round(x: float) -> int:
 
 def auto_basis(manifold: Manifold, coords: np.ndarray, regular: int = 1, nres: int = 3,
                type: str = "bisquare", isea3h_lo: int = 2, scale_aperture: Optional[float] = None,
-               isea3h: Optional[dict] = None) -> Basis:
-    """Regular placement, R/basisfns.R:358-585 (prune=0, subsamp>=n, no buffer).
+               isea3h: Optional[dict] = None, prune: float = 0) -> Basis:
+    """Regular placement, R/basisfns.R:358-585 (subsamp>=n, no buffer), including the deprecated ``prune`` refinement (:479-553).
 
     ``isea3h``: {res: (n_res x 2) lon/lat centroids} from data/isea3h.rda for the sphere.
     """
@@ -253,6 +253,7 @@ def auto_basis(manifold: Manifold, coords: np.ndarray, regular: int = 1, nres: i
         else:
             nx = regular
             ny = nx * asp
+    mult = 1.5 if type == "bisquare" else 0.7                             # :532
     locs, scales, ress = [], [], []
     for i in range(1, nres + 1):
         xgrid = ygrid = None
@@ -265,21 +266,44 @@ def auto_basis(manifold: Manifold, coords: np.ndarray, regular: int = 1, nres: i
             this = _seq_len(xrange_[0], xrange_[1], i * regular)[:, None]  # :468
         else:
             this = np.asarray(isea3h[i + isea3h_lo - 1], dtype=np.float64)  # :472-474
-        nloc = this.shape[0]
-        if nloc == 1:                                                      # :482-483
-            base = np.array([max(xrange_[1] - xrange_[0], yrange_[1] - yrange_[0]) / 2.0])
-        elif nloc < 5000:                                                  # :485-490
-            D = manifold.distance(this, this)
-            np.fill_diagonal(D, np.inf)
-            base = D.min(axis=1) * scale_aperture
-        else:                                                              # :492-495 (regular, no prune)
-            diffx = abs(xgrid[1] - xgrid[0])
-            diffy = abs(ygrid[1] - ygrid[0])
-            base = np.full(nloc, min(diffx, diffy)) * scale_aperture
-        mult = 1.5 if type == "bisquare" else 0.7                         # :532
+        base = np.zeros(0)
+        for j in (1, 2):                                                   # :479 "go over this twice for refinement when pruning"
+            nloc = this.shape[0]
+            if nloc == 0:
+                base = np.zeros(0)
+                break
+            if nloc == 1:                                                  # :482-483
+                base = np.array([max(xrange_[1] - xrange_[0], yrange_[1] - yrange_[0]) / 2.0])
+            elif nloc < 5000:                                              # :485-490
+                D = manifold.distance(this, this)
+                np.fill_diagonal(D, np.inf)
+                base = D.min(axis=1) * scale_aperture
+            elif not prune and regular:                                    # :492-495
+                diffx = abs(xgrid[1] - xgrid[0])
+                diffy = abs(ygrid[1] - ygrid[0])
+                base = np.full(nloc, min(diffx, diffy)) * scale_aperture
+            else:                                                          # :497-509, batches of 5000 rows against all centroids
+                parts = []
+                for i0 in range(0, nloc, 5000):
+                    D = manifold.distance(this[i0:i0 + 5000], this)
+                    D[D == 0] = np.inf
+                    parts.append(D.min(axis=1) * scale_aperture)
+                base = np.concatenate(parts)
+            if not (prune > 0):                                            # :551-553
+                break
+            if j == 1:                                                     # :536-549
+                cand = Basis(manifold, this, mult * base, np.full(nloc, i, dtype=np.int32), type, int(regular))
+                cs = np.zeros(nloc)
+                for r0 in range(0, coords.shape[0], 2000):
+                    cs += eval_basis_dense(cand, coords[r0:r0 + 2000]).sum(axis=0)
+                rm = cs < prune
+                if rm.any():
+                    this = this[~rm]
+        if this.shape[0] == 0:
+            continue
         locs.append(this)
         scales.append(mult * base)
-        ress.append(np.full(nloc, i, dtype=np.int32))
+        ress.append(np.full(this.shape[0], i, dtype=np.int32))
     return Basis(manifold, np.vstack(locs), np.concatenate(scales), np.concatenate(ress), type, int(regular))
 
 

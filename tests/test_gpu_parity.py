@@ -134,6 +134,60 @@ def test_eval_basis_STsphere(dev):
     np.testing.assert_allclose(D, F.BuildD(kb)[0], rtol=0, atol=2e-15)
 
 
+@pytest.mark.parametrize("regular,nres,prune", [(1, 3, 2.0), (1, 4, 0.5), (1, 4, 0.05)])
+def test_auto_basis_prune_plane(dev, regular, nres, prune):
+    """auto_basis(prune > 0), R/basisfns.R:479-553: functions with colSums(eval_basis(., data)) < prune are removed and the scales
+    re-derived from the survivors.  eval_basis + column sums on the device; with nres = 4 the finest resolution has 6561 >= 5000
+    centroids, so the nearest-centroid search is the device kernel (D == 0 -> Inf rule of the batched branch, :497-509); with
+    prune = 0.05 more than 5000 survive, so the FINAL scales come from that kernel too.
+    Plane distances are +,-,*,sqrt only: centroids, resolutions AND scales must be bit-identical to the restated reference."""
+    import frk_b200 as F
+    rng = np.random.default_rng(41)
+    xy = np.vstack([rng.uniform(0, 1, (3000, 2)) ** 2, [[0.0, 0.0], [1.0, 1.0]]])      # dense near the origin, empty elsewhere
+    ob = O.auto_basis(O.plane(), xy, regular=regular, nres=nres, prune=prune)
+    full = O.auto_basis(O.plane(), xy, regular=regular, nres=nres)
+    gb = F.auto_basis(F.plane(), xy, regular=regular, nres=nres, prune=prune, dev=dev)
+    assert ob.n < full.n and gb.n == ob.n
+    assert np.array_equal(gb.loc, ob.loc) and np.array_equal(gb.res, ob.res)
+    assert np.array_equal(gb.scale, ob.scale)
+    # the pruned basis goes through eval_basis like any other
+    S_o = O.eval_basis(ob, xy[:500]).tocsr()
+    S_g = F.eval_basis(gb, xy[:500], dev)
+    assert _same_pattern(S_o, S_g) and np.array_equal(S_o.data, S_g.data)
+
+
+def test_auto_basis_prune_sphere_and_nn_kernel(dev):
+    """prune on the sphere (ISEA3H-like centroids), and frk_basis_nn_dist against the restated distance matrices for both
+    exclusion rules (diag(D) <- Inf vs D[D == 0] <- Inf) with a duplicated centroid in the set."""
+    import frk_b200 as F
+    from frk_b200._lib import call
+    ll, _ = sphere_points(3000, seed=17)
+    ll = ll[ll[:, 1] > 0]                                            # northern hemisphere only: southern functions get pruned
+    iso = pseudo_isea3h()
+    ob = O.auto_basis(O.sphere(), ll, nres=3, isea3h=iso, isea3h_lo=1, prune=1.0)
+    gb = F.auto_basis(F.sphere(), ll, nres=3, isea3h=iso, isea3h_lo=1, prune=1.0, dev=dev)
+    assert gb.n == ob.n < sum(len(iso[k]) for k in (1, 2, 3))
+    assert np.array_equal(gb.loc, ob.loc) and np.array_equal(gb.res, ob.res) and np.array_equal(gb.scale, ob.scale)
+    cen = np.vstack([iso[2], iso[2][:1]])                            # one duplicate
+    for man_o, man_g, pts in ((O.sphere(), F.sphere(), cen), (O.plane(), F.plane(), cen / 10.0)):
+        D = man_o.distance(pts, pts)
+        tmp = F.Basis(man_g, pts.copy(), np.ones(len(pts)), np.ones(len(pts), dtype=np.int32), "Gaussian", 0)
+        out = dev.empty(len(pts))
+        for zero_is_inf in (0, 1):
+            Dm = D.copy()
+            if zero_is_inf:
+                Dm[Dm == 0] = np.inf
+            else:
+                np.fill_diagonal(Dm, np.inf)
+            call("frk_basis_nn_dist", dev.ctx, tmp.handle(dev), zero_is_inf, dev.ptr(out))
+            got = dev.download(out, len(pts))
+            if man_o.kind == "plane":
+                assert np.array_equal(got, Dm.min(axis=1))
+            else:
+                np.testing.assert_allclose(got, Dm.min(axis=1), rtol=1e-12, atol=1e-9)
+            assert (got[0] == 0.0) == (not zero_is_inf)              # the duplicate is at distance 0 unless zeros are excluded
+
+
 def test_tensor_basis(dev):
     import frk_b200 as F
     xy, _ = readme_points(800, seed=8)
