@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--predict-reps", type=int, default=5)
+    ap.add_argument("--distribute-nm", action="store_true", help="spread the Nelder-Mead candidates over the ranks (default: replicated on local lanes)")
     ap.add_argument("--lanes", type=int, default=None, help="concurrent Nelder-Mead evaluation lanes per GPU (frk_model_set_lanes)")
     return ap.parse_args()
 
@@ -70,7 +71,8 @@ def config(args, r, n_bau, m):
             "n_obs": args.n_obs, "r": r, "n_bau": n_bau, "m_binned": m, "K_type": args.k_type,
             "cache": "inputs larger than L2 (S 0.37 GB, six r x r fp64 matrices 86 MB each, S0 4 GB); no L2 flush",
             "partition": "BAU rows block-partitioned over ranks; r-sized state replicated",
-            "nm_lanes": args.lanes if args.lanes else (2 if args.gpus == 1 else 1)}
+            "nm_lanes": args.lanes if args.lanes else (1 if (args.distribute_nm and args.gpus > 1) else 2),
+            "nm_distributed": bool(args.distribute_nm and args.gpus > 1)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -224,14 +226,14 @@ def run_b200(args):
 
     # ---- (A) device-resident EM iterations --------------------------------------------------------
     mdl = F.SRE("z ~ 1", data, basis, BAUs, est_error=False, K_type=args.k_type, dev=dev)
-    F.SRE_fit(mdl, n_EM=args.warmup, tol=0.0, lanes=args.lanes)
+    F.SRE_fit(mdl, n_EM=args.warmup, tol=0.0, lanes=args.lanes, distribute_nm=args.distribute_nm)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     l0 = dev.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    F.SRE_fit(mdl, n_EM=args.steps, tol=0.0, lanes=args.lanes)
+    F.SRE_fit(mdl, n_EM=args.steps, tol=0.0, lanes=args.lanes, distribute_nm=args.distribute_nm)
     e1.record()
     barrier()
     t_em = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
@@ -265,7 +267,7 @@ def run_b200(args):
     if not args.no_profile:
         fp64_peak = fp64_peak_probe(torch, dev.tdev)
         call("frk_profile", dev.ctx, 1)
-        F.SRE_fit(mdl, n_EM=2, tol=0.0, lanes=args.lanes)
+        F.SRE_fit(mdl, n_EM=2, tol=0.0, lanes=args.lanes, distribute_nm=args.distribute_nm)
         n_f_tau_launch_iters = 2
         F.predict(mdl, obs_fs=False, to_host=False)
         buf = C.create_string_buffer(1 << 16)
@@ -334,7 +336,7 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         m2 = F.SRE("z ~ 1", data, basis, BAUs, est_error=False, K_type=args.k_type, dev=dev)
-        F.SRE_fit(m2, n_EM=args.steps, tol=0.0, lanes=args.lanes)
+        F.SRE_fit(m2, n_EM=args.steps, tol=0.0, lanes=args.lanes, distribute_nm=args.distribute_nm)
         slots = {k: m2.get(k) for k in ("mu_eta", "S_eta", "Khat", "Khat_inv")}
         barrier()
         t_fit_e2e = max_over_ranks(time.perf_counter() - t0)

@@ -69,6 +69,8 @@ struct frk_model {
     // multi-rank reduction hook
     int rank = 0, world = 1;
     bool spec_emulate = false;     // evaluate every speculative candidate on this rank (single-GPU test of the multi-rank logic)
+    bool nm_distribute = false;    // spread the Nelder-Mead candidates over the ranks (else: every rank evaluates them on its own lanes,
+                                   // replicated and deterministic like the rest of the r-sized work, with no exchange at all)
     frk_allreduce_fn allreduce = nullptr;
     void *user = nullptr;
     std::vector<void *> allocs;
@@ -109,6 +111,10 @@ int reduce_host(frk_model *M, double *h_buf, int64_t n, int op) {
     FRK_REQUIRE(M->allreduce(M->user, h_buf, n, 0, op) == 0, "all-reduce callback failed (host buffer)");
     return 0;
 }
+
+// ranks that share the Nelder-Mead candidates (1: replicated evaluation on local lanes)
+inline int nm_world(const frk_model *M) { return (M->nm_distribute || M->spec_emulate) ? std::max(M->world, 1) : 1; }
+inline int nm_rank(const frk_model *M) { return (M->nm_distribute && !M->spec_emulate) ? M->rank : 0; }
 
 // sum, sum of squares about `shift`, min, max over ALL ranks' rows
 int global_stats(frk_model *M, const double *d_x, double shift, double out[4]) {
@@ -442,14 +448,14 @@ struct SpecNM {
         M->nm_rounds += 1;
         static const bool dbg = getenv("FRK_SPEC_DEBUG") != nullptr;
         // candidate k goes to rank k % world (the likeliest ones spread over the GPUs first), lane k / world
-        const int world = std::max(M->world, 1);
+        const int world = nm_world(M);
         const int L = std::max(lanes, 1), W = world * L;
         std::vector<std::vector<double>> batch = {std::vector<double>(x, x + dim)};
         if (W > 1) candidates(x, (size_t)W, batch);
         std::vector<double> fl(batch.size(), 0.0);
         std::vector<size_t> mine;
         for (size_t k = 0; k < batch.size(); k++)
-            if (M->spec_emulate || (int)(k % world) == M->rank) mine.push_back(k);
+            if (M->spec_emulate || (int)(k % world) == nm_rank(M)) mine.push_back(k);
         for (size_t c0 = 0; c0 < mine.size(); c0 += (size_t)L) {
             const int nb = (int)std::min<size_t>((size_t)L, mine.size() - c0);
             const double *ptsv[16];
@@ -483,7 +489,7 @@ int gram(frk_model *M, const double *alpha, double sigma2fs) {
         bool same = sigma2fs == M->gram_s2;
         for (int i = 0; i < M->p; i++) same = same && alpha[i] == M->gram_alpha[i];
         FRK_CHECK_CUDA(cudaStreamWaitEvent(M->ctx->stream, M->ev_aux1, 0));       // either way acc is not touched before aux is done
-        if (same) return 0;
+        if (same) return reduce_dev(M, M->acc, (int64_t)n);                         // (this rank's rows: the exchange happens here)
     }
     FRK_CHECK_CUDA(cudaMemsetAsync(M->acc, 0, n * sizeof(double), M->ctx->stream));
     RC(frk_gram_rhs_bucketed(M->ctx, M->m, M->r, M->rowptr, M->col, M->val, M->bk,
@@ -570,7 +576,7 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
                       const std::function<int()> &side_work) {
     frk_ctx *ctx = M->ctx;
     const int r = M->r, nblk = (int)nmb.size();
-    const int world = std::max(M->world, 1);
+    const int world = nm_world(M);
     const bool one_stream = ctx->profiling || ctx->stream == nullptr;   // per-kernel profiling times one stream: keep everything on it
     const int L = one_stream ? 1 : std::max(M->lanes, 1);
     const int W = world * L;
@@ -644,7 +650,7 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
         for (int c = 0; c < L; c++) {
             NMSlot &s = S.slot[c];
             s.used = false;
-            const int k = M->spec_emulate ? chunk * L + c : c * world + M->rank;
+            const int k = M->spec_emulate ? chunk * L + c : c * world + nm_rank(M);
             if (k >= (int)S.batch.size()) continue;
             s.k = k; s.valid = false;
             const double tau = S.batch[k][0];
@@ -787,8 +793,8 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
         const size_t nn = (size_t)ni * ni;
         const double tau = S.nm.x[0], omega = S.omega;
         M->taus.push_back(tau);
-        const int own = shared ? S.spec->owner[S.spec->find(&tau)] : M->rank;
-        if (own == M->rank) {
+        const int own = shared ? S.spec->owner[S.spec->find(&tau)] : nm_rank(M);
+        if (own == nm_rank(M)) {
             if (S.bestTau != tau) {        // its inverse is no longer in a slot (ties, or a point evaluated rounds before it was requested)
                 S.bestF = std::numeric_limits<double>::infinity();
                 NMSlot &s = S.slot[0];
@@ -924,9 +930,9 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
             SpecNM spec{M, f_tau2_batch, 2, 100, 1e-4, std::vector<double>{p0, p1}};
             RC(nmmin(std::ref(spec), spec.par0, nm, 100, 1e-4));
             M->taus.push_back(nm.x[0]); M->taus.push_back(nm.x[1]);
-            const bool shared = M->world > 1 && !M->spec_emulate;
-            const int own = shared ? spec.owner[spec.find(nm.x.data())] : M->rank;
-            if (own == M->rank) {
+            const bool shared = nm_world(M) > 1 && !M->spec_emulate;
+            const int own = shared ? spec.owner[spec.find(nm.x.data())] : nm_rank(M);
+            if (own == nm_rank(M)) {
                 if (bestTs != nm.x[0] || bestTt != nm.x[1]) {
                     bestF = std::numeric_limits<double>::infinity();
                     double f;
@@ -996,6 +1002,8 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
     }
     const bool est = !known;
     bool sigma_done = false;
+    // the early Gram needs this function to run BEFORE the K update finishes, i.e. as the asynchronous driver's side work
+    const bool early_gram = beside && !M->tensor && nm_world(M) == 1 && !M->spec_emulate;
     // sigma2fs and alpha (:275-430).  Everything here depends on the E-step only, not on K: with `beside` it runs on the aux lane
     // (after the quadratic form) while the Nelder-Mead evaluations are in flight, and is followed there by the NEXT iteration's Gram.
     auto sigma_update = [&]() -> int {
@@ -1044,7 +1052,7 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
         }
         for (int i = 0; i < p; i++) M->alpha[i] = al[i];
         M->sigma2fs = s2new;
-        if (beside && !M->allreduce) {
+        if (beside && early_gram) {
             // the next E-step's Gram matrix (R/SREfit.R:252) needs only these two: enqueue it behind the sums, beside the K update
             const size_t n = rr + r + 2;
             FRK_CHECK_CUDA(cudaMemsetAsync(M->acc, 0, n * sizeof(double), c->stream));
@@ -1170,6 +1178,15 @@ extern "C" int frk_model_set_parallel(frk_model *M, int rank, int world, int emu
     FRK_REQUIRE(M && world >= 1 && rank >= 0 && rank < world, "frk_model_set_parallel: bad argument");
     FRK_REQUIRE(emulate || world == 1 || M->allreduce, "frk_model_set_parallel: world > 1 needs the all-reduce hook");
     M->rank = emulate ? 0 : rank; M->world = world; M->spec_emulate = emulate != 0;
+    return 0;
+}
+
+// distribute != 0: spread the Nelder-Mead candidates of a round over the ranks (one small all-reduce per round, the winner's inverse
+// broadcast); 0 (default): every rank evaluates them on its own lanes -- replicated, deterministic, no exchange
+extern "C" int frk_model_set_nm_distribute(frk_model *M, int distribute) {
+    FRK_REQUIRE(M, "frk_model_set_nm_distribute: NULL model");
+    FRK_REQUIRE(!distribute || M->world == 1 || M->allreduce, "frk_model_set_nm_distribute: needs the all-reduce hook");
+    M->nm_distribute = distribute != 0;
     return 0;
 }
 

@@ -242,19 +242,22 @@ def loglik(mdl: SREModel) -> float:
 # ---------------------------------------------------------------------------------------
 
 def SRE_fit(mdl: SREModel, n_EM: int = 100, tol: float = 0.01, method: str = "EM", lambda_=0.0,
-            known_sigma2fs=None, print_lik: bool = False, lanes: Optional[int] = None) -> SREModel:
+            known_sigma2fs=None, print_lik: bool = False, lanes: Optional[int] = None,
+            distribute_nm: bool = False) -> SREModel:
     """SRE.fit(object, n_EM, tol, method = "EM", lambda, print_lik, known_sigma2fs), R/SREfit.R:3-160: one
     ``frk_model_em_fit`` call.  Calling it again continues from the current slots, as in R.
 
     ``lanes`` (not in the reference): how many of the block-exponential Nelder-Mead's candidate points are factorised side by side
     on this GPU (``frk_model_set_lanes``); the iterates and results are those of the sequential algorithm for any value.  Two
-    candidates per round is the measured optimum on B200 (more cost more than the rounds they save), so the default is 2 on one GPU
-    and 1 in a row-partitioned run, where the ranks already split the candidates."""
+    candidates per round is the measured optimum on B200 (more cost more than the rounds they save): the default is 2.
+    ``distribute_nm`` (row-partitioned runs): spread the candidates over the ranks instead of evaluating them, replicated, on every
+    rank's own lanes; measured slower on NVLink-connected B200s (the exchange costs more than the contention it avoids)."""
     if method != "EM":
         raise FRKError("only method = \"EM\" (Gaussian data, identity link) is on the device path")
     if lanes is None:
-        lanes = 2 if mdl.dev.world == 1 else 1
+        lanes = 1 if (distribute_nm and mdl.dev.world > 1) else 2
     call("frk_model_set_lanes", mdl.handle, int(lanes))
+    call("frk_model_set_nm_distribute", mdl.handle, 1 if distribute_nm else 0)
     t0 = time.time()
     lam = np.atleast_1d(np.asarray(lambda_, dtype=np.float64)).copy()
     res = np.ascontiguousarray(mdl.basis.res, dtype=np.int32)

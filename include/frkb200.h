@@ -329,6 +329,10 @@ int frk_model_set_parallel(frk_model *mdl, int rank, int world, int emulate);
  * side by side on separate streams (combined with the ranks of a row-partitioned run: world x lanes candidates per round).
  * The sequence of iterates, hence every result, is that of the sequential algorithm.  Default 1.                                  */
 int frk_model_set_lanes(frk_model *mdl, int lanes);
+/* Row-partitioned runs: distribute != 0 spreads those candidates over the ranks as well (world x lanes per round; one small
+ * all-reduce per round and a broadcast of the winner's inverse); 0 (default) lets every rank evaluate them on its own lanes --
+ * replicated and deterministic like the rest of the r-sized work, with no exchange.  Results are identical either way.        */
+int frk_model_set_nm_distribute(frk_model *mdl, int distribute);
 /* BuildD() (R/basisfns.R:1131-1153) for K_type = "block-exponential": h_res[r] 1-based resolution of every basis
  * function, h_D[i] the r_i x r_i centroid distance matrix of resolution i+1 (column-major, host).              */
 int frk_model_set_blocks(frk_model *mdl, int nres, const int *h_res, const double *const *h_D);
