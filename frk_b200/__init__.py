@@ -9,7 +9,7 @@ raises -- there is no CPU fallback.
 from ._lib import FRKError, LIB_PATH, lib  # noqa: F401  (raises ImportError if the .so is missing)
 from .basis import (Basis, BuildD, TensorP, TensorP_Basis, auto_basis, eval_basis, eval_basis_device,  # noqa: F401
                     local_basis, nbasis)
-from .geometry import (GridBAUs, Manifold, PointBAUs, PolygonBAUs, STBAUs, SpatialPointsDataFrame, auto_BAUs, map_data_to_BAUs,  # noqa: F401
+from .geometry import (GridBAUs, Manifold, PointBAUs, PolygonBAUs, STBAUs, SpatialPointsDataFrame, SpatialPolygonsDataFrame, auto_BAUs, map_data_to_BAUs,  # noqa: F401
                        STplane, STsphere, plane, real_line, sphere)
 from .runtime import Device, get_device, partition_rows  # noqa: F401
 from .sre import SRE, SRE_fit, SREModel, loglik, predict  # noqa: F401

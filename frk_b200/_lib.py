@@ -66,6 +66,11 @@ SIGNATURES = {
     "frk_csr_tensor_count": (c_int, [vp, c_i64, vp, vp, vp, p_i64]),
     "frk_csr_tensor_fill": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_csr_row_normalise": (c_int, [vp, c_i64, vp, vp]),
+    "frk_polygon_lookup_count": (c_int, [vp, vp, c_i64, vp, c_i64, vp, p_i64]),
+    "frk_areal_incidence": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, p_i64, p_i64]),
+    "frk_csr_aggregate_count": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, p_i64]),
+    "frk_csr_aggregate_fill": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "frk_areal_aggregate": (c_int, [vp, c_i64, vp, vp, vp, c_int, c_int, vp, c_i64, vp]),
     "frk_st_bau_index": (c_int, [vp, c_i64, vp, vp, c_int, vp, c_i64, c_i64, c_i64, vp]),
     "frk_grid_lookup": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, vp]),
     "frk_grid_lookup_range": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, c_int, c_int, c_int, vp]),

@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(256) polygon_lookup_kernel(int64_t n, const do
                                                              double hx, double hy, int nx, int ny, const int *__restrict__ cell_start,
                                                              const int *__restrict__ cand, const int *__restrict__ ptr,
                                                              const double *__restrict__ vx, const double *__restrict__ vy,
-                                                             const double *__restrict__ bbox, int lo, int hi, int *__restrict__ bau) {
+                                                             const double *__restrict__ bbox, int lo, int hi, int *__restrict__ bau,
+                                                             int *__restrict__ multi) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double px = xy[i], py = xy[i + ld];
         int out = -1;
@@ -284,7 +285,10 @@ __global__ void __launch_bounds__(256) polygon_lookup_kernel(int64_t n, const do
                 const double *bb = bbox + 4 * (size_t)pid;
                 if (px < __ldg(bb) || px > __ldg(bb + 1) || py < __ldg(bb + 2) || py > __ldg(bb + 3)) continue;
                 const int b = ptr[pid];
-                if (in_poly_dev(px, py, vx + b, vy + b, ptr[pid + 1] - b) != 0) { out = pid; break; }
+                if (in_poly_dev(px, py, vx + b, vy + b, ptr[pid + 1] - b) != 0) {
+                    if (out < 0) { out = pid; if (!multi) break; }
+                    else { atomicAdd(multi, 1); break; }                 // a second polygon holds this point too
+                }
             }
         }
         if (out >= 0) out = (out >= lo && out < hi) ? out - lo : -1;
@@ -366,6 +370,24 @@ extern "C" int frk_polygon_lookup(frk_ctx *ctx, const frk_polygons *P, int64_t n
     if (n == 0) return 0;
     unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
     FRK_LAUNCH(ctx, polygon_lookup_kernel, grid, 256, 0, n, d_xy, ld_xy, P->x0, P->y0, P->hx, P->hy, P->nx, P->ny, P->cell_start, P->cand,
-               P->ptr, P->vx, P->vy, P->bbox, bau_lo, bau_hi, d_bau);
+               P->ptr, P->vx, P->vy, P->bbox, bau_lo, bau_hi, d_bau, (int *)nullptr);
+    return 0;
+}
+
+// as frk_polygon_lookup over all polygons, and *h_multi = number of points that lie in MORE than one polygon
+extern "C" int frk_polygon_lookup_count(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy, int *d_first,
+                                        int64_t *h_multi) {
+    FRK_REQUIRE(ctx && P && d_first && h_multi && (n == 0 || d_xy), "frk_polygon_lookup_count: NULL argument");
+    *h_multi = 0;
+    if (n == 0) return 0;
+    int *cnt = (int *)(ctx->d_small + 3000);
+    FRK_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), ctx->stream));
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, polygon_lookup_kernel, grid, 256, 0, n, d_xy, ld_xy, P->x0, P->y0, P->hx, P->hy, P->nx, P->ny, P->cell_start, P->cand,
+               P->ptr, P->vx, P->vy, P->bbox, 0, 2147483647, d_first, cnt);
+    int h = 0;
+    FRK_CHECK_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *h_multi = h;
     return 0;
 }

@@ -119,6 +119,34 @@ class SpatialPointsDataFrame:
 
 
 @dataclass
+class SpatialPolygonsDataFrame:
+    """Areal observations (sp's SpatialPolygonsDataFrame as FRK uses it): polygon k is the single ring
+    ``vx/vy[ptr[k]:ptr[k+1]]`` (no holes) and ``data`` holds one value per polygon (the response, ``std``, ...).
+    An observation is the average of the process over the BAUs whose centroid lies in its polygon (BuildC,
+    R/geometryfns.R:1572-1616 with normalise_wts = TRUE, R/SRE.R:483-490)."""
+    ptr: np.ndarray
+    vx: np.ndarray
+    vy: np.ndarray
+    data: Dict[str, np.ndarray]
+
+    def __post_init__(self):
+        self.ptr = np.ascontiguousarray(self.ptr, dtype=np.int32)
+        self.vx = np.ascontiguousarray(self.vx, dtype=np.float64)
+        self.vy = np.ascontiguousarray(self.vy, dtype=np.float64)
+        n = len(self.ptr) - 1
+        if n < 1 or self.ptr[0] != 0 or np.any(np.diff(self.ptr) < 3) or self.ptr[-1] != len(self.vx) or len(self.vx) != len(self.vy):
+            raise ValueError("polygons need ptr[0] = 0, at least 3 vertices each and ptr[-1] = len(vx) = len(vy)")
+        for k, v in self.data.items():
+            v = np.asarray(v, dtype=np.float64)
+            if v.shape[0] != n:
+                raise ValueError(f"column {k!r} has {v.shape[0]} rows, expected {n}")
+            self.data[k] = v
+
+    def __len__(self):
+        return len(self.ptr) - 1
+
+
+@dataclass
 class GridBAUs:
     """SpatialPixelsDataFrame of grid BAUs on the plane (auto_BAU, R/geometryfns.R:553-697).
 

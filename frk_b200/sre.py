@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib
 from ._lib import FRKError, call, c_i64, vp
 from .basis import BuildD, DeviceCSR, TensorP_Basis, eval_basis_device
-from .geometry import GridBAUs, SpatialPointsDataFrame, map_data_to_BAUs
+from .geometry import GridBAUs, STBAUs, SpatialPointsDataFrame, SpatialPolygonsDataFrame, map_data_to_BAUs
 from .runtime import Device, get_device, partition_rows
 
 def _parse_formula(f: str):
@@ -148,6 +148,12 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
     t0 = time.time()
     r = basis.n
     N = len(BAUs)
+    areal = isinstance(data, SpatialPolygonsDataFrame)
+    if areal:
+        if dev.world > 1:
+            raise FRKError("areal (polygon) data on a row-partitioned run: footprints may straddle ranks -- not on the device path yet")
+        if isinstance(basis, TensorP_Basis) or isinstance(BAUs, STBAUs):
+            raise FRKError("areal (polygon) data in space-time (BuildC for STFDF, R/geometryfns.R:1628-1672) is not on the device path yet")
     lo, hi = partition_rows(N, dev.world, dev.rank)
     nloc = hi - lo
     h2d = 0
@@ -160,31 +166,77 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
         d_s = dev.empty(max(2 * nloc, 1))
         call("frk_grid_centroids", dev.ctx, lo, hi, BAUs.nx, dev.ptr(d_xg), dev.ptr(d_yg), dev.ptr(d_s))
         S0 = eval_basis_device(basis, (d_s, nloc, 2), dev, normalise=normalise_basis)
-        del d_s
+        if not areal:
+            del d_s
     else:
         cc = BAUs.centroids(lo, hi)
         h2d += cc.nbytes
         S0 = eval_basis_device(basis, cc, dev, normalise=normalise_basis)
+        if areal:
+            d_s = dev.upload(cc[:, :2])
 
-    # ---- bin the observations into this rank's BAUs ------------------------------------------
-    cols = [resp, "std"]
-    binned = map_data_to_BAUs(data, BAUs, cols, dev, row_range=(lo, hi))
-    h2d += data.coords[:, :2].nbytes + 8 * len(data) * len(cols)
-    m, ld = binned["m"], binned["ld"]
-    obs_bau = binned["obs_bau"][:max(m, 1)]
-    Z = binned["means"][0:max(m, 1)]                             # views into the binned table (column-major, ld = n)
-    Ve = dev.empty(max(m, 1))
-    call("frk_square", dev.ctx, m, dev.ptr(binned["means"], ld), dev.ptr(Ve))      # Ve = diag(std^2), R/SRE.R:468
+    binned = None
+    obs_bau = None
+    if areal:
+        # ---- BuildC(SpatialPolygons): BAU centroids in observation polygons, rows normalised; S = C_Z S0 ---------------
+        m = len(data)
+        hp = vp()
+        call("frk_polygons_create", dev.ctx, m, vp(data.ptr.ctypes.data), vp(data.vx.ctypes.data), vp(data.vy.ctypes.data), C.byref(hp))
+        d_group = dev.empty(max(N, 1), "i4")
+        multi = c_i64(0)
+        try:
+            call("frk_polygon_lookup_count", dev.ctx, hp, N, dev.ptr(d_s), N, dev.ptr(d_group), C.byref(multi))
+        finally:
+            _lib.lib.frk_polygons_destroy(hp)
+        h2d += data.ptr.nbytes + data.vx.nbytes + data.vy.nbytes
+        if multi.value:
+            raise FRKError(f"{multi.value} BAU centroids lie in more than one observation polygon: overlapping supports give a "
+                           "non-diagonal fine-scale covariance (R/SREfit.R:298-328), which is not on the device path yet")
+        cz_rowptr = dev.empty(m + 1, "i4")
+        cz_mem = dev.empty(max(N, 1), "i4")
+        cz_w = dev.empty(max(N, 1))
+        nmem, empty = c_i64(0), c_i64(0)
+        call("frk_areal_incidence", dev.ctx, N, dev.ptr(d_group), m, vp(None), dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(cz_w),
+             C.byref(nmem), C.byref(empty))
+        if empty.value:
+            raise FRKError(f"{empty.value} observation polygons contain no BAU centroid (supports smaller than a BAU fall back to a "
+                           "point lookup in the reference, R/geometryfns.R:1593-1598): use finer BAUs or point data for them")
+        rowptr = dev.empty(m + 1, "i4")
+        nnz = c_i64(0)
+        call("frk_csr_aggregate_count", dev.ctx, m, r, dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(S0.rowptr), dev.ptr(S0.col),
+             dev.ptr(rowptr), C.byref(nnz))
+        col = dev.empty(max(nnz.value, 1), "i4")
+        val = dev.empty(max(nnz.value, 1))
+        call("frk_csr_aggregate_fill", dev.ctx, m, r, dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(cz_w), dev.ptr(S0.rowptr),
+             dev.ptr(S0.col), dev.ptr(S0.val), dev.ptr(rowptr), dev.ptr(col), dev.ptr(val))
+        S = DeviceCSR(m, r, rowptr, col, val, nnz.value)
+        Z = dev.upload(np.ascontiguousarray(data.data[resp], dtype=np.float64))
+        d_std = dev.upload(np.ascontiguousarray(data.data["std"], dtype=np.float64))
+        h2d += 16 * m
+        Ve = dev.empty(max(m, 1))
+        call("frk_square", dev.ctx, m, dev.ptr(d_std), dev.ptr(Ve))                     # Ve = diag(std^2), R/SRE.R:468
+        obs_bau = dev.zeros(1, "i4")                                                   # (no one-BAU-per-observation map for areal data)
+        del d_s
+    else:
+        # ---- bin the observations into this rank's BAUs ------------------------------------------
+        cols = [resp, "std"]
+        binned = map_data_to_BAUs(data, BAUs, cols, dev, row_range=(lo, hi))
+        h2d += data.coords[:, :2].nbytes + 8 * len(data) * len(cols)
+        m, ld = binned["m"], binned["ld"]
+        obs_bau = binned["obs_bau"][:max(m, 1)]
+        Z = binned["means"][0:max(m, 1)]                             # views into the binned table (column-major, ld = n)
+        Ve = dev.empty(max(m, 1))
+        call("frk_square", dev.ctx, m, dev.ptr(binned["means"], ld), dev.ptr(Ve))      # Ve = diag(std^2), R/SRE.R:468
 
-    # ---- C_Z (one 1 per row) -> S = C_Z S0, Vfs = fs[bau], X = model matrix at the observed BAUs ----
-    rowptr = dev.empty(m + 1, "i4")
-    nnz = c_i64(0)
-    call("frk_csr_gather_count", dev.ctx, m, dev.ptr(obs_bau), dev.ptr(S0.rowptr), dev.ptr(rowptr), C.byref(nnz))
-    col = dev.empty(max(nnz.value, 1), "i4")
-    val = dev.empty(max(nnz.value, 1))
-    call("frk_csr_gather_fill", dev.ctx, m, dev.ptr(obs_bau), dev.ptr(S0.rowptr), dev.ptr(S0.col), dev.ptr(S0.val),
-         dev.ptr(rowptr), dev.ptr(col), dev.ptr(val))
-    S = DeviceCSR(m, r, rowptr, col, val, nnz.value)
+        # ---- C_Z (one 1 per row) -> S = C_Z S0, Vfs = fs[bau], X = model matrix at the observed BAUs ----
+        rowptr = dev.empty(m + 1, "i4")
+        nnz = c_i64(0)
+        call("frk_csr_gather_count", dev.ctx, m, dev.ptr(obs_bau), dev.ptr(S0.rowptr), dev.ptr(rowptr), C.byref(nnz))
+        col = dev.empty(max(nnz.value, 1), "i4")
+        val = dev.empty(max(nnz.value, 1))
+        call("frk_csr_gather_fill", dev.ctx, m, dev.ptr(obs_bau), dev.ptr(S0.rowptr), dev.ptr(S0.col), dev.ptr(S0.val),
+             dev.ptr(rowptr), dev.ptr(col), dev.ptr(val))
+        S = DeviceCSR(m, r, rowptr, col, val, nnz.value)
 
     # BAU-level fields for this rank: fs and covariates
     fs_host = np.ascontiguousarray(BAUs.fields["fs"][lo:hi], dtype=np.float64)
@@ -204,12 +256,19 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
         h2d += colv.nbytes
         k += 1
     Vfs = dev.empty(max(m, 1))                                    # Vfs = diag(fs[bau]), R/SRE.R:498
-    call("frk_gather_rows", dev.ctx, m, 1, dev.ptr(obs_bau), dev.ptr(fs_BAU), nloc, dev.ptr(Vfs), m)
     X = dev.empty(max(m * p, 1))                                  # model matrix at the observed BAUs, :464-465
-    call("frk_gather_rows", dev.ctx, m, p, dev.ptr(obs_bau), dev.ptr(X_BAU), nloc, dev.ptr(X), m)
+    if areal:      # diag(C_Z diag(fs) C_Z') and the BAU covariates averaged over each footprint (R/geometryfns.R:1352-1357)
+        call("frk_areal_aggregate", dev.ctx, m, dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(cz_w), 2, 1, dev.ptr(fs_BAU), nloc, dev.ptr(Vfs))
+        call("frk_areal_aggregate", dev.ctx, m, dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(cz_w), 1, p, dev.ptr(X_BAU), nloc, dev.ptr(X))
+    else:
+        call("frk_gather_rows", dev.ctx, m, 1, dev.ptr(obs_bau), dev.ptr(fs_BAU), nloc, dev.ptr(Vfs), m)
+        call("frk_gather_rows", dev.ctx, m, p, dev.ptr(obs_bau), dev.ptr(X_BAU), nloc, dev.ptr(X), m)
 
     mdl = SREModel(dev, f, basis, BAUs, K_type, N, lo, hi, m, S0, S, obs_bau, Z, X, X_BAU, Ve, Vfs, fs_BAU, p)
     mdl._keep = binned                                            # Z / obs_bau are views into these buffers
+    mdl.areal = areal
+    if areal:
+        mdl.C_Z = (cz_rowptr, cz_mem, cz_w, int(nmem.value))      # Cmat (CSR over the observations, rows normalised)
     mdl.h2d_bytes = h2d
     if K_type == "block-exponential" and isinstance(basis, TensorP_Basis):     # BuildD(basis) = list(Basis1 = ..., Basis2 = ...)
         D = BuildD(basis)
@@ -296,6 +355,9 @@ def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True):
     Returns dict(mu, var, sd) for this rank's BAU rows [lo, hi) (host arrays, or device tensors)."""
     dev = mdl.dev
     nloc = mdl.hi - mdl.lo
+    if getattr(mdl, "areal", False) and not obs_fs and mdl.sigma2fshat > 0:
+        raise FRKError("predict(obs_fs = FALSE) for areal data needs the joint (eta, xi) solve over the footprints "
+                       "(R/SREpredict.R:311-333), which is not on the device path yet: use obs_fs = TRUE")
     mu, var, sd = (dev.empty(max(nloc, 1)) for _ in range(3))
     call("frk_model_predict", mdl.handle, nloc, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
          mdl.S0.buckets(dev), dev.ptr(mdl.X_BAU), dev.ptr(mdl.fs_BAU), dev.ptr(mdl.obs_bau), 1 if obs_fs else 0,

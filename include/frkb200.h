@@ -150,6 +150,30 @@ int frk_polygon_lookup(frk_ctx *ctx, const frk_polygons *P, int64_t n, const dou
  * start -> NA.  d_bau = spatial + ns*slice, restricted to [bau_lo, bau_hi) and relative to bau_lo (may alias d_spatial).  */
 int frk_st_bau_index(frk_ctx *ctx, int64_t n, const int *d_spatial, const double *d_time, int nt, const double *h_breaks,
                      int64_t ns, int64_t bau_lo, int64_t bau_hi, int *d_bau);
+/* ---- areal (polygon-support) data: BuildC(SpatialPolygons) R/geometryfns.R:1572-1616 + SRE() R/SRE.R:472-502 ----------------
+ * d_group[N]: for every BAU the observation polygon that contains its centroid (frk_polygon_lookup over the BAU centroids;
+ * -1 = none).  frk_areal_incidence builds Cmat as CSR over the m observations: d_rowptr[m+1], d_members (BAU rows, ascending
+ * within an observation = j_idx), d_weights = BAUs$wts (d_wts, NULL = 1) divided by the row sum (normalise_wts = TRUE,
+ * R/SRE.R:483-490).  *h_empty = observations that contain no BAU centroid (the reference falls back to the BAU under the
+ * polygon's vertices, :1593-1598; the caller decides).  Footprints must not share BAUs (one group per BAU): Vfs stays diagonal. */
+int frk_areal_incidence(frk_ctx *ctx, int64_t N, const int *d_group, int64_t m, const double *d_wts, int *d_rowptr,
+                        int *d_members, double *d_weights, int64_t *h_nmem, int64_t *h_empty);
+/* S = Cmat %*% S0 (R/SRE.R:502) for a general row-weighted Cmat: two-pass CSR build, columns ascending, values summed in
+ * member order.  r <= ~25000 (per-observation accumulator in shared memory).                                                  */
+int frk_csr_aggregate_count(frk_ctx *ctx, int64_t m, int r, const int *d_cz_rowptr, const int *d_cz_members,
+                            const int *d_rowptr0, const int *d_col0, int *d_rowptr, int64_t *h_nnz);
+int frk_csr_aggregate_fill(frk_ctx *ctx, int64_t m, int r, const int *d_cz_rowptr, const int *d_cz_members,
+                           const double *d_cz_weights, const int *d_rowptr0, const int *d_col0, const double *d_val0,
+                           const int *d_rowptr, int *d_col, double *d_val);
+/* d_out[j + m*c] = sum_k w_jk^power d_in[member_k + ld_in*c]: power 1 -> X = Cmat %*% X_BAU (BAU covariates averaged over the
+ * footprint, R/geometryfns.R:1352-1357); power 2 with d_in = fs -> diag(tcrossprod(Cmat %*% Diagonal(sqrt(fs)))), R/SRE.R:498 */
+int frk_areal_aggregate(frk_ctx *ctx, int64_t m, const int *d_cz_rowptr, const int *d_cz_members, const double *d_cz_weights,
+                        int power, int ncols, const double *d_in, int64_t ld_in, double *d_out);
+/* the same lookup over all polygons, also counting the points that lie in MORE than one polygon (*h_multi): used with the
+ * BAU centroids as points and the observation polygons as polygons (over(BAU_as_points, this_poly), R/geometryfns.R:1589),
+ * where a BAU shared by two observations would make Vfs non-diagonal                                                          */
+int frk_polygon_lookup_count(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy, int *d_first,
+                             int64_t *h_multi);
 /* group_by(BAU) %>% summarise_all(mean): R/geometryfns.R:1286-1302.  d_vals: n x ncols
  * column-major (ld n).  Outputs (capacity n rows): d_obs_bau[m] ascending BAU rows,
  * d_means m x ncols column-major with leading dimension n, d_counts[m].  Returns m.

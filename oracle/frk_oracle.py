@@ -925,14 +925,40 @@ def EM_initialise(Z, X, Ve, r):
                 alphahat=alpha, sigma2fshat=float(np.mean(Ve)) / 4.0)
 
 
+def BuildC_polygons(ptr: np.ndarray, vx: np.ndarray, vy: np.ndarray, bau_xy: np.ndarray, wts: Optional[np.ndarray] = None):
+    """BuildC(data = "SpatialPolygons"), R/geometryfns.R:1572-1616: for every observation polygon i (in order) the BAUs whose
+    centroid it contains (over(BAU_as_points, this_poly) == 1: interior, edge and vertex all count), weight BAUs$wts.
+    Returns the triplets (i_idx, j_idx, x_idx), 0-based.  (The fallback for polygons that contain no centroid, :1593-1598, is not
+    restated: such inputs are refused on the device path.)"""
+    bau_xy = np.asarray(bau_xy, dtype=np.float64)
+    i_idx, j_idx, x_idx = [], [], []
+    for i in range(len(ptr) - 1):
+        px, py = vx[ptr[i]:ptr[i + 1]], vy[ptr[i]:ptr[i + 1]]
+        cand = np.nonzero((bau_xy[:, 0] >= px.min()) & (bau_xy[:, 0] <= px.max()) &
+                          (bau_xy[:, 1] >= py.min()) & (bau_xy[:, 1] <= py.max()))[0]        # bounding box: pre-filter only
+        overlap = [k for k in cand if in_poly(bau_xy[k, 0], bau_xy[k, 1], px, py) != 0]
+        i_idx += [i] * len(overlap)
+        j_idx += overlap
+        x_idx += [1.0 if wts is None else float(wts[k]) for k in overlap]
+    return np.asarray(i_idx, dtype=np.int64), np.asarray(j_idx, dtype=np.int64), np.asarray(x_idx, dtype=np.float64)
+
+
 def SRE(basis, baus_coords: np.ndarray, fs_BAU: np.ndarray, obs_bau: np.ndarray, Z: np.ndarray,
         std: np.ndarray, X: Optional[np.ndarray] = None, X_BAU: Optional[np.ndarray] = None,
-        K_type: str = "block-exponential", normalise_basis: bool = True, fast_eval: bool = False) -> SREModel:
+        K_type: str = "block-exponential", normalise_basis: bool = True, fast_eval: bool = False,
+        C: Optional[sp.spmatrix] = None) -> SREModel:
     """SRE() for binned point data, R/SRE.R:395-701.
 
     Inputs are the *binned* observations (map_data_to_BAUs output): BAU row, mean z, mean std.
     X defaults to the intercept-only model matrix (f = z ~ 1).
+
+    ``C`` (m x N incidence matrix from BuildC_polygons, un-normalised): areal data.  Rows are divided by their sums
+    (normalise_wts = TRUE, :483-490), S = Cmat %*% S0 (:502), Vfs = tcrossprod(Cmat %*% Diagonal(sqrt(fs))) (:498), which must be
+    diagonal here (supports that share no BAU), and X = Cmat %*% X_BAU (BAU covariates averaged over the support).
+    ``obs_bau`` is ignored then.
     """
+    if C is not None:
+        return _SRE_areal(basis, baus_coords, fs_BAU, sp.csr_matrix(C), Z, std, X_BAU, K_type, normalise_basis)
     N = baus_coords.shape[0]
     if fast_eval and not isinstance(basis, TensorP_Basis) and basis.type == "bisquare":
         S0 = eval_basis_fast(basis, baus_coords)
@@ -953,6 +979,38 @@ def SRE(basis, baus_coords: np.ndarray, fs_BAU: np.ndarray, obs_bau: np.ndarray,
         X_BAU = np.ones((N, 1))
     mdl = SREModel(basis=basis, S0=S0, S=S.tocsr(), obs_bau=np.asarray(obs_bau), Z=Z, X=X, X_BAU=X_BAU,
                    Ve=Ve, Vfs=Vfs, fs_BAU=np.asarray(fs_BAU, dtype=np.float64), D_basis=D_basis, K_type=K_type)
+    init = EM_initialise(Z, X, Ve, S.shape[1])
+    for k, v in init.items():
+        setattr(mdl, k, v)
+    return mdl
+
+
+def _SRE_areal(basis, baus_coords, fs_BAU, C, Z, std, X_BAU, K_type, normalise_basis) -> SREModel:
+    N = baus_coords.shape[0]
+    S0 = eval_basis(basis, baus_coords)
+    if normalise_basis:
+        S0 = normalise_rows(S0)
+    D_basis = BuildD(basis)
+    m = C.shape[0]
+    Cmat = sp.diags(1.0 / np.asarray(C.sum(axis=1)).ravel()) @ C          # Cmat / rowSums(Cmat), :487-489
+    Cmat = sp.csr_matrix(Cmat)
+    Z = np.asarray(Z, dtype=np.float64)
+    Ve = np.asarray(std, dtype=np.float64) ** 2
+    fs_BAU = np.asarray(fs_BAU, dtype=np.float64)
+    half = sp.csr_matrix(Cmat @ sp.diags(np.sqrt(fs_BAU)))
+    V = sp.csr_matrix(half @ half.T)                                      # tcrossprod(Cmat %*% Diagonal(sqrt(fs))), :498
+    off = V - sp.diags(V.diagonal())
+    if off.nnz and abs(off).max() > 0:
+        raise ValueError("supports share BAUs: Vfs is not diagonal")
+    Vfs = V.diagonal()
+    S = sp.csr_matrix(Cmat @ S0)
+    S.sort_indices()
+    if X_BAU is None:
+        X_BAU = np.ones((N, 1))
+    X = np.asarray(Cmat @ X_BAU)
+    mdl = SREModel(basis=basis, S0=S0, S=S, obs_bau=np.zeros(0, dtype=np.int64), Z=Z, X=X, X_BAU=X_BAU,
+                   Ve=Ve, Vfs=Vfs, fs_BAU=fs_BAU, D_basis=D_basis, K_type=K_type)
+    mdl.Cmat = Cmat
     init = EM_initialise(Z, X, Ve, S.shape[1])
     for k, v in init.items():
         setattr(mdl, k, v)

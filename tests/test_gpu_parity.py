@@ -700,3 +700,88 @@ def test_nelder_mead_lanes_match_sequential(dev, lanes, world):
     F.SRE_fit(Ma, n_EM=2, tol=0.0, lanes=1)
     F.SRE_fit(Mb, n_EM=2, tol=0.0, lanes=lanes)
     np.testing.assert_allclose(Mb.info_fit["llk"], Ma.info_fit["llk"], rtol=1e-11)
+
+
+def _areal_case(F, seed=51, K_type="block-exponential"):
+    """Areal observations on the unit square: 0.1 x 0.1 tiles (edges kept off the BAU centroids), each observing the average of a
+    smooth field over its footprint; one tile row left out so that some BAUs are unobserved; a covariate known at every BAU."""
+    rng = np.random.default_rng(seed)
+    xy_dom = np.array([[0.0, 0.0], [1.0, 1.0]])
+    gb = F.auto_BAUs(F.plane(), cellsize=0.02, data=F.SpatialPointsDataFrame(xy_dom, {}))
+    cen = gb.centroids()
+    gb["fs"] = 1.0 + 0.5 * (cen[:, 0] > 0.5)
+    gb["x1"] = cen[:, 0] + cen[:, 1]
+    ptr, vx, vy, z = [0], [], [], []
+    for iy in range(10):
+        for ix in range(10):
+            if iy == 4:
+                continue
+            x0, y0 = 0.1 * ix + 0.003, 0.1 * iy + 0.003
+            vx += [x0, x0 + 0.1, x0 + 0.1, x0, x0]
+            vy += [y0, y0, y0 + 0.1, y0 + 0.1, y0]
+            ptr.append(len(vx))
+            xm, ym = x0 + 0.05, y0 + 0.05
+            z.append(np.sin(6 * xm) + np.cos(5 * ym) + 0.5 * (xm + ym) + 0.1 * rng.standard_normal())
+    m = len(z)
+    std = 0.1 + 0.05 * rng.uniform(size=m)
+    data = F.SpatialPolygonsDataFrame(np.array(ptr), np.array(vx), np.array(vy), {"z": np.array(z), "std": std})
+    ob = O.auto_basis(O.plane(), cen, regular=1, nres=2)
+    i_idx, j_idx, x_idx = O.BuildC_polygons(data.ptr, data.vx, data.vy, cen)
+    Cm = sp.csr_matrix((x_idx, (i_idx, j_idx)), shape=(m, len(cen)))
+    X_BAU = np.column_stack([np.ones(len(cen)), gb["x1"]])
+    Mo = O.SRE(ob, cen, gb["fs"], None, np.array(z), std, X_BAU=X_BAU, K_type=K_type, C=Cm)
+    Mg = F.SRE("z ~ x1", data, _mk_basis(F, ob), gb, est_error=False, K_type=K_type)
+    return Mo, Mg, Cm
+
+
+@pytest.mark.parametrize("K_type", ["block-exponential", "unstructured"])
+def test_areal_data_fit_and_predict(dev, K_type):
+    """SURVEY.md section 8(f) #1, first slice: observations with polygon supports that share no BAU.  BuildC(SpatialPolygons) +
+    normalise_wts (incidence pattern and weights: exact), S = Cmat S0 (pattern exact, values to 1e-12), Vfs = diag(Cmat diag(fs)
+    Cmat'), X = Cmat X_BAU, then the unchanged EM (heteroscedastic branch: Vfs and Ve vary) and predict(obs_fs = TRUE) against
+    the restated reference; predict(obs_fs = FALSE) is refused loudly."""
+    import frk_b200 as F
+    Mo, Mg, Cm = _areal_case(F, K_type=K_type)
+    rp, mem, w, nmem = Mg.C_Z
+    Cn = sp.csr_matrix(Mo.Cmat); Cn.sort_indices()
+    assert nmem == Cn.nnz and np.array_equal(dev.download(rp, Mg.m + 1), Cn.indptr)
+    assert np.array_equal(dev.download(mem, nmem), Cn.indices)
+    np.testing.assert_allclose(dev.download(w, nmem), Cn.data, rtol=1e-15)
+    Sg = Mg.S.to_scipy(dev)
+    assert _same_pattern(Mo.S, Sg)
+    np.testing.assert_allclose(Sg.data, Mo.S.data, rtol=1e-12)
+    np.testing.assert_allclose(dev.download(Mg.Vfs, Mg.m), Mo.Vfs, rtol=1e-14)
+    np.testing.assert_allclose(dev.download(Mg.X, Mg.m * 2).reshape(2, Mg.m).T, Mo.X, rtol=1e-13)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL)
+    O.SRE_fit(Mo, n_EM=5, tol=0.0)
+    F.SRE_fit(Mg, n_EM=5, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=1e-7)
+    po = O.predict(Mo, obs_fs=True)
+    pg = F.predict(Mg, obs_fs=True)
+    np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-9 * abs(po[0]).max())
+    np.testing.assert_allclose(pg["var"], po[1], rtol=1e-7)
+    if Mg.sigma2fshat > 0:
+        with pytest.raises(F.FRKError, match="obs_fs"):
+            F.predict(Mg, obs_fs=False)
+
+
+def test_areal_data_refusals(dev):
+    """overlapping supports (non-diagonal Vfs) and supports without a BAU centroid are refused, not silently mis-fitted."""
+    import frk_b200 as F
+    gb = F.auto_BAUs(F.plane(), cellsize=0.05, data=F.SpatialPointsDataFrame(np.array([[0.0, 0.0], [1.0, 1.0]]), {}))
+    gb["fs"] = 1.0
+    basis = F.auto_basis(F.plane(), gb.centroids(), regular=1, nres=1)
+    sq = lambda x0, y0, s: ([x0, x0 + s, x0 + s, x0, x0], [y0, y0, y0 + s, y0 + s, y0])
+    def mk(squares):
+        ptr, vx, vy = [0], [], []
+        for a in squares:
+            px, py = sq(*a)
+            vx += px; vy += py; ptr.append(len(vx))
+        k = len(squares)
+        return F.SpatialPolygonsDataFrame(np.array(ptr), np.array(vx), np.array(vy), {"z": np.arange(k, dtype=float), "std": np.ones(k)})
+    with pytest.raises(F.FRKError, match="more than one observation polygon"):
+        F.SRE("z ~ 1", mk([(0.01, 0.01, 0.4), (0.21, 0.21, 0.4)]), basis, gb, est_error=False)
+    with pytest.raises(F.FRKError, match="contain no BAU centroid"):
+        F.SRE("z ~ 1", mk([(0.01, 0.01, 0.4), (0.601, 0.601, 0.01)]), basis, gb, est_error=False)
