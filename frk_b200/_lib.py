@@ -120,6 +120,7 @@ SIGNATURES = {
     "frk_model_create": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, ALLREDUCE_FN, vp, C.POINTER(vp)]),
     "frk_model_create_host": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "frk_model_destroy": (c_int, [vp]),
+    "frk_model_predict_areal": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_model_set_lanes": (c_int, [vp, c_int]),
     "frk_model_set_nm_distribute": (c_int, [vp, c_int]),
     "frk_model_set_parallel": (c_int, [vp, c_int, c_int, c_int]),

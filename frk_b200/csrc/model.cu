@@ -1435,6 +1435,100 @@ extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, 
     return rc;
 }
 
+// ---------------------------------------------------------------------------------
+// predict(obs_fs = FALSE), areal data with supports that share no BAU.  The joint (eta, xi) solve of .SRE.predict_EM
+// (R/SREpredict.R:308-333) has a closed form here: with d_j = sigma2fs * Vfs_j + Ve_j, the posterior (mu~, Sigma~) of eta at the final
+// parameters (one more E-step), S_j = row j of S = Cmat S0 and, for BAU k inside support j with weight c_jk,
+//   g_k   = sigma2fs * fs_k * c_jk / d_j
+//   E     = x_k'alpha + s_k'mu~ + g_k (Z_j - X_j alpha - S_j mu~)
+//   Var   = s_k'Sigma~ s_k - 2 g_k s_k'Sigma~ S_j' + g_k^2 S_j Sigma~ S_j' + sigma2fs fs_k - g_k^2 d_j
+// (BAUs in no support: g = 0).  One CTA per support forms v = Sigma~ S_j' in shared memory, one warp per member BAU takes s_k'v.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) areal_case2_kernel(int64_t m, int r, const int *__restrict__ crp, const int *__restrict__ mem,
+                                                          const double *__restrict__ wgt, const int *__restrict__ rpS,
+                                                          const int *__restrict__ colS, const double *__restrict__ valS,
+                                                          const int *__restrict__ rp0, const int *__restrict__ col0,
+                                                          const double *__restrict__ val0, const double *__restrict__ Sig,
+                                                          const double *__restrict__ QS, const double *__restrict__ res,
+                                                          const double *__restrict__ dj, const double *__restrict__ q,
+                                                          const double *__restrict__ fs, double sigma2fs, double *__restrict__ mu,
+                                                          double *__restrict__ var, double *__restrict__ sd) {
+    extern __shared__ __align__(16) double a2_v[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int64_t j = blockIdx.x; j < m; j += gridDim.x) {
+        for (int l = threadIdx.x; l < r; l += blockDim.x) {        // v[l] = sum_i S_ji Sigma~[l, i]  (Sigma~ symmetric: column i is contiguous)
+            double acc = 0.0;
+            for (int e = rpS[j]; e < rpS[j + 1]; e++) acc += valS[e] * Sig[(size_t)colS[e] * r + l];
+            a2_v[l] = acc;
+        }
+        __syncthreads();
+        const double Qj = QS[j], rj = res[j], d = dj[j];
+        for (int k = crp[j] + wid; k < crp[j + 1]; k += nwarp) {
+            const int b = mem[k];
+            double cr = 0.0;
+            for (int e = rp0[b] + lane; e < rp0[b + 1]; e += 32) cr += val0[e] * a2_v[col0[e]];
+            cr = warp_sum(cr);
+            if (lane == 0) {
+                const double sf = sigma2fs * fs[b], g = sf * wgt[k] / d;
+                const double v_ = q[b] - 2.0 * g * cr + g * g * Qj + sf - g * g * d;
+                mu[b] += g * rj;
+                var[b] = v_;
+                sd[b] = sqrt(v_);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void areal_dj_kernel(int64_t m, double sigma2fs, const double *__restrict__ vfs, const double *__restrict__ ve,
+                                const double *__restrict__ smuS, double *__restrict__ res, double *__restrict__ dj) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+        dj[j] = sigma2fs * vfs[j] + ve[j];
+        res[j] -= smuS[j];                                  // res came in as Z - X alpha
+    }
+}
+
+extern "C" int frk_model_predict_areal(frk_model *M, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
+                                       const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs, const int *d_cz_rowptr,
+                                       const int *d_cz_members, const double *d_cz_weights, double *d_mu, double *d_var, double *d_sd) {
+    FRK_REQUIRE(M && d_rowptr0 && bk0 && d_XBAU && d_fs && d_cz_rowptr && d_cz_members && d_cz_weights && d_mu && d_var && d_sd && n > 0,
+                "frk_model_predict_areal: bad argument");
+    FRK_REQUIRE(M->sigma2fs > 0.0, "frk_model_predict_areal: sigma2fs = 0 -- use frk_model_predict (stored posterior)");
+    FRK_REQUIRE(!M->allreduce, "frk_model_predict_areal: row-partitioned runs are not supported for areal data");
+    frk_ctx *ctx = M->ctx;
+    const int r = M->r;
+    const size_t rr = (size_t)r * r;
+    const int64_t m = M->m;
+    FRK_REQUIRE((size_t)r * sizeof(double) <= 200 * 1024, "frk_model_predict_areal: r = %d does not fit the shared-memory vector", r);
+    double *buf = nullptr;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&buf, (size_t)(3 * n + 4 * m + 2 * rr + r) * sizeof(double), ctx->stream));
+    double *xa = buf, *q = xa + n, *smu = q + n, *QS = smu + n, *smuS = QS + m, *res = smuS + m, *dj = res + m, *Q = dj + m,
+           *Sig = Q + rr, *mue = Sig + rr;
+    auto run = [&]() -> int {
+        double o[4];
+        RC(frk_xalpha(ctx, n, M->p, d_XBAU, M->alpha, xa));
+        RC(posterior(M, M->alpha, M->sigma2fs, Q, Sig, mue, o));                                   // eta | Z at the final parameters
+        RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, Sig, mue, q, smu));           // s_k'Sigma~ s_k, s_k'mu~
+        RC(frk_quadform_spmv_bucketed(ctx, m, r, M->rowptr, M->col, M->val, M->bk, Sig, mue, QS, smuS));       // S_j Sigma~ S_j', S_j mu~
+        RC(frk_resid(ctx, m, M->p, M->X, M->alpha, M->Z, nullptr, res));
+        FRK_LAUNCH(ctx, areal_dj_kernel, (unsigned)cdiv(m, 256), 256, 0, m, M->sigma2fs, M->Vfs, M->Ve, smuS, res, dj);
+        // every BAU as if unobserved (g = 0): mu = x'alpha + s'mu~, var = s'Sigma~ s + sigma2fs fs; the supports' BAUs are then corrected
+        RC(frk_predict_finalize(ctx, n, 1, M->sigma2fs, q, smu, xa, nullptr, nullptr, d_fs, d_mu, d_var, d_sd));
+        static bool attr = false;
+        if (!attr) {
+            FRK_CHECK_CUDA(cudaFuncSetAttribute(areal_case2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr = true;
+        }
+        const unsigned grid = (unsigned)std::min<int64_t>(m, (int64_t)ctx->sm_count * 4);
+        FRK_LAUNCH(ctx, areal_case2_kernel, grid, 256, (size_t)r * sizeof(double), m, r, d_cz_rowptr, d_cz_members, d_cz_weights, M->rowptr,
+                   M->col, M->val, d_rowptr0, d_col0, d_val0, Sig, QS, res, dj, q, d_fs, M->sigma2fs, d_mu, d_var, d_sd);
+        return 0;
+    };
+    const int rc = run();
+    cudaFreeAsync(buf, ctx->stream);
+    return rc;
+}
+
 // ---- the host optimisers, exported so that the CPU test-suite can pin them without a GPU --------------------
 extern "C" int frk_optim_nelder_mead(frk_objective_fn fn, void *user, int n, const double *par, int maxit, double reltol,
                                      double *x_out, double *f_out, int *count_out, int *fail_out) {

@@ -355,10 +355,17 @@ def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True):
     Returns dict(mu, var, sd) for this rank's BAU rows [lo, hi) (host arrays, or device tensors)."""
     dev = mdl.dev
     nloc = mdl.hi - mdl.lo
-    if getattr(mdl, "areal", False) and not obs_fs and mdl.sigma2fshat > 0:
-        raise FRKError("predict(obs_fs = FALSE) for areal data needs the joint (eta, xi) solve over the footprints "
-                       "(R/SREpredict.R:311-333), which is not on the device path yet: use obs_fs = TRUE")
     mu, var, sd = (dev.empty(max(nloc, 1)) for _ in range(3))
+    if getattr(mdl, "areal", False) and not obs_fs and mdl.sigma2fshat > 0:
+        cz_rowptr, cz_mem, cz_w, _ = mdl.C_Z
+        call("frk_model_predict_areal", mdl.handle, nloc, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
+             mdl.S0.buckets(dev), dev.ptr(mdl.X_BAU), dev.ptr(mdl.fs_BAU), dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(cz_w),
+             dev.ptr(mu), dev.ptr(var), dev.ptr(sd))
+        if not to_host:
+            return dict(mu=mu, var=var, sd=sd)
+        out = dict(mu=dev.download(mu, nloc), var=dev.download(var, nloc), sd=dev.download(sd, nloc))
+        mdl.d2h_bytes += 3 * 8 * nloc
+        return out
     call("frk_model_predict", mdl.handle, nloc, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
          mdl.S0.buckets(dev), dev.ptr(mdl.X_BAU), dev.ptr(mdl.fs_BAU), dev.ptr(mdl.obs_bau), 1 if obs_fs else 0,
          dev.ptr(mu), dev.ptr(var), dev.ptr(sd))

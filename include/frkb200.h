@@ -391,6 +391,12 @@ int frk_model_slot_device(frk_model *mdl, const char *slot, double **d_out);
 int frk_model_predict(frk_model *mdl, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
                       const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs,
                       const int *d_obs_bau, int obs_fs, double *d_mu, double *d_var, double *d_sd);
+/* The same for areal data whose supports share no BAU (Cmat from frk_areal_incidence), obs_fs = FALSE and sigma2fs > 0: the joint
+ * (eta, xi) solve of R/SREpredict.R:308-333 in closed form -- one more E-step, the quadratic forms over S0 and S, and one
+ * cross term s_k'Sigma S_j' per BAU inside a support.  (obs_fs = TRUE / sigma2fs = 0: frk_model_predict.)                     */
+int frk_model_predict_areal(frk_model *mdl, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
+                            const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs, const int *d_cz_rowptr,
+                            const int *d_cz_members, const double *d_cz_weights, double *d_mu, double *d_var, double *d_sd);
 /* stats::optim(method = "Nelder-Mead", control = list(maxit, reltol)) and stats::uniroot (default tol) as used by
  * the M-step (R/SREfit.R:618-621, :386-388); exported so that the iterate path can be tested on its own.       */
 int frk_optim_nelder_mead(frk_objective_fn fn, void *user, int n, const double *par, int maxit,

@@ -1245,6 +1245,8 @@ def predict(M: SREModel, obs_fs: bool = False):
         mu = Xa + S0 @ M.mu_eta
         var = batch_compute_var(S0, M.S_eta)
         return mu, var, np.sqrt(var)
+    if getattr(M, "Cmat", None) is not None:                      # areal data: no point-data shortcut -- the literal joint solve
+        return predict_general(M)
     A = np.zeros(N)
     np.add.at(A, M.obs_bau, 1.0 / M.Ve)                           # C' Ve^-1 C (diagonal)
     Q = 1.0 / (s2 * M.fs_BAU)
@@ -1269,7 +1271,8 @@ def predict_general(M: SREModel):
     S0 = np.asarray(M.S0.todense())
     N, r = S0.shape
     s2 = M.sigma2fshat
-    C = np.asarray(BuildC(M.obs_bau, N).todense())
+    Cm = getattr(M, "Cmat", None)                                 # areal data: the row-normalised incidence matrix
+    C = np.asarray(BuildC(M.obs_bau, N).todense()) if Cm is None else np.asarray(Cm.todense())
     LAMBDAinv = np.zeros((r + N, r + N))
     LAMBDAinv[:r, :r] = M.Khat_inv
     LAMBDAinv[r:, r:] = np.diag(1.0 / (s2 * M.fs_BAU))

@@ -702,26 +702,27 @@ def test_nelder_mead_lanes_match_sequential(dev, lanes, world):
     np.testing.assert_allclose(Mb.info_fit["llk"], Ma.info_fit["llk"], rtol=1e-11)
 
 
-def _areal_case(F, seed=51, K_type="block-exponential"):
+def _areal_case(F, seed=51, K_type="block-exponential", cellsize=0.02, tile=0.1, noise=0.1):
     """Areal observations on the unit square: 0.1 x 0.1 tiles (edges kept off the BAU centroids), each observing the average of a
     smooth field over its footprint; one tile row left out so that some BAUs are unobserved; a covariate known at every BAU."""
     rng = np.random.default_rng(seed)
     xy_dom = np.array([[0.0, 0.0], [1.0, 1.0]])
-    gb = F.auto_BAUs(F.plane(), cellsize=0.02, data=F.SpatialPointsDataFrame(xy_dom, {}))
+    gb = F.auto_BAUs(F.plane(), cellsize=cellsize, data=F.SpatialPointsDataFrame(xy_dom, {}))
     cen = gb.centroids()
     gb["fs"] = 1.0 + 0.5 * (cen[:, 0] > 0.5)
     gb["x1"] = cen[:, 0] + cen[:, 1]
     ptr, vx, vy, z = [0], [], [], []
-    for iy in range(10):
-        for ix in range(10):
-            if iy == 4:
+    nt = int(round(1.0 / tile))
+    for iy in range(nt):
+        for ix in range(nt):
+            if iy == nt // 2 - 1:
                 continue
-            x0, y0 = 0.1 * ix + 0.003, 0.1 * iy + 0.003
-            vx += [x0, x0 + 0.1, x0 + 0.1, x0, x0]
-            vy += [y0, y0, y0 + 0.1, y0 + 0.1, y0]
+            x0, y0 = tile * ix + 0.003, tile * iy + 0.003
+            vx += [x0, x0 + tile, x0 + tile, x0, x0]
+            vy += [y0, y0, y0 + tile, y0 + tile, y0]
             ptr.append(len(vx))
-            xm, ym = x0 + 0.05, y0 + 0.05
-            z.append(np.sin(6 * xm) + np.cos(5 * ym) + 0.5 * (xm + ym) + 0.1 * rng.standard_normal())
+            xm, ym = x0 + tile / 2, y0 + tile / 2
+            z.append(np.sin(6 * xm) + np.cos(5 * ym) + 0.5 * (xm + ym) + noise * rng.standard_normal())
     m = len(z)
     std = 0.1 + 0.05 * rng.uniform(size=m)
     data = F.SpatialPolygonsDataFrame(np.array(ptr), np.array(vx), np.array(vy), {"z": np.array(z), "std": std})
@@ -762,9 +763,28 @@ def test_areal_data_fit_and_predict(dev, K_type):
     pg = F.predict(Mg, obs_fs=True)
     np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-9 * abs(po[0]).max())
     np.testing.assert_allclose(pg["var"], po[1], rtol=1e-7)
-    if Mg.sigma2fshat > 0:
-        with pytest.raises(F.FRKError, match="obs_fs"):
-            F.predict(Mg, obs_fs=False)
+
+
+def test_areal_data_predict_case2(dev):
+    """predict(obs_fs = FALSE) for areal data: the device's closed form of the joint (eta, xi) solve (one more E-step, quadratic forms
+    over S0 and S, one cross term per BAU inside a support) against the LITERAL dense joint solve of R/SREpredict.R:308-333 restated
+    in the oracle (toy size: (r + N)^2 dense inverse).  Unobserved BAUs (the left-out tile row, the buffer) are covered too."""
+    import frk_b200 as F
+    Mo, Mg, Cm = _areal_case(F, cellsize=0.04, tile=0.2, noise=1.0)       # noisy averages -> sigma2fs > 0
+    O.SRE_fit(Mo, n_EM=4, tol=0.0)
+    F.SRE_fit(Mg, n_EM=4, tol=0.0)
+    assert Mg.sigma2fshat > 0
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    po = O.predict(Mo, obs_fs=False)
+    pg = F.predict(Mg, obs_fs=False)
+    np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-8 * abs(po[0]).max())
+    np.testing.assert_allclose(pg["var"], po[1], rtol=1e-6)
+    inside = np.asarray(Cm.sum(axis=0)).ravel() > 0
+    assert inside.any() and (~inside).any()
+    # inside a support the observation pins the AVERAGE of the process, so the fine-scale variance is only partly removed:
+    # larger than the variance with the fine-scale term observed away (obs_fs = TRUE), smaller than prior + smooth part
+    pt = F.predict(Mg, obs_fs=True)
+    assert np.all(pg["var"][inside] > pt["var"][inside])
 
 
 def test_areal_data_refusals(dev):
