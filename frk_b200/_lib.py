@@ -135,6 +135,7 @@ SIGNATURES = {
     "frk_model_slot_device": (c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "frk_model_predict": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp, vp]),
     "frk_optim_nelder_mead": (c_int, [OBJECTIVE_FN, vp, c_int, vp, c_int, c_dbl, vp, p_dbl, p_int, p_int]),
+    "frk_optim_nelder_mead_speculative": (c_int, [OBJECTIVE_FN, vp, c_int, vp, c_int, c_dbl, c_int, vp, p_dbl, p_int, p_int, p_int]),
     "frk_optim_zeroin": (c_int, [OBJECTIVE_FN, vp, c_dbl, c_dbl, p_dbl]),
     "frk_eval_basis_host": (c_int, [vp, vp, c_i64, vp, c_int, vp, vp, vp, p_i64]),
     "frk_grid_lookup_host": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, c_i64, vp]),

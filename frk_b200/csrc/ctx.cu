@@ -74,7 +74,7 @@ int frk_ctx_create_lane(const frk_ctx *parent, bool high_priority, frk_ctx **out
 }
 
 int frk_ctx_lane(frk_ctx *parent, int idx, bool high_priority, frk_ctx **out) {
-    FRK_REQUIRE(parent && out && idx >= 0 && idx < 64, "frk_ctx_lane: bad argument");
+    FRK_REQUIRE(parent && out && idx >= 0 && idx < 1024, "frk_ctx_lane: bad argument");
     std::vector<frk_ctx *> &v = high_priority ? parent->lanes_hi : parent->lanes_lo;
     if ((int)v.size() <= idx) v.resize(idx + 1, nullptr);
     if (!v[idx]) { if (int rc = frk_ctx_create_lane(parent, high_priority, &v[idx])) return rc; }

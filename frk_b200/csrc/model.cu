@@ -533,11 +533,12 @@ int chol2inv_logdet(frk_ctx *ctx, int n, double *A, double *Ainv, double *work, 
 
 // ---------------------------------------------------------------------------------
 // Block-exponential K, plain bases: the per-resolution Nelder-Mead runs (optim(), R/SREfit.R:618-621) are independent, and every
-// f_tau evaluation is a latency-bound r_i x r_i factorisation that fills a fraction of the GPU.  So the runs advance in LOCKSTEP:
-// each round, every unfinished run is replayed against the values known so far until it asks for a point without a value; that
-// point plus the points it may ask for next (SpecNM::candidates) are evaluated -- all resolutions, all candidates, side by side on
-// lane contexts of this GPU and spread over the ranks -- and ONE all-reduce shares the values.  Each run sees exactly the values
-// the sequential algorithm would: the iterates are identical.
+// f_tau evaluation is a latency-bound r_i x r_i factorisation that fills a fraction of the GPU.  So the runs advance TOGETHER:
+// an unfinished run is replayed against the values known so far until it asks for a point without a value; that point plus the
+// points it may ask for next (SpecNM::candidates) are evaluated side by side on lane contexts of this GPU.  On one rank (or with
+// the candidates replicated on every rank, the default) each run is fed as soon as its values are in; when the candidates are
+// distributed over the ranks the runs move in lockstep and ONE all-reduce per round shares the values of all resolutions.
+// Each run sees exactly the values the sequential algorithm would: the iterates are identical.
 // ---------------------------------------------------------------------------------
 struct NMSlot {                    // one concurrent evaluation: context + buffers, and what its Kinv currently holds
     frk_ctx *ctx = nullptr;
@@ -572,7 +573,7 @@ int f_tau_enqueue(const Block &B, NMSlot &s, double tau) {
     return frk_dot_async(s.ctx, (int64_t)nn, s.Kinv, B.eta2);
 }
 
-int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, double *Knew, double *Kinvnew, double &logdetK,
+int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, double *Knew, double *Kinvnew, double &logdetK,
                       const std::function<int()> &side_work) {
     frk_ctx *ctx = M->ctx;
     const int r = M->r, nblk = (int)nmb.size();
@@ -734,7 +735,7 @@ int blockexp_lockstep(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, do
         if (rc) return rc;
         for (int j = 0; j < nblk; j++) M->nm_rounds = std::max(M->nm_rounds, (double)nmb[j]->rounds);
     } else {
-        // Several ranks (or a pretend world): LOCKSTEP, so that every rank issues the same all-reduces in the same order
+        // Candidates distributed over the ranks (or a pretend world): lockstep, so that every rank issues the same all-reduces in the same order
         for (;;) {
             size_t maxbatch = 0;
             for (int j = 0; j < nblk; j++) {
@@ -968,7 +969,7 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
         S.B = &B; S.omega = omega;
         S.spec.reset(new SpecNM{M, nullptr, 1, 100, 1e-4, std::vector<double>{par0}});
     }
-    if (!M->tensor) RC(blockexp_lockstep(M, nmb, Knew, Kinvnew, logdetK, side_work));
+    if (!M->tensor) RC(blockexp_nelder_mead(M, nmb, Knew, Kinvnew, logdetK, side_work));
     FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat, Knew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     FRK_CHECK_CUDA(cudaMemcpyAsync(M->Khat_inv, Kinvnew, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     M->logdetK = logdetK;
@@ -1540,6 +1541,40 @@ extern "C" int frk_optim_nelder_mead(frk_objective_fn fn, void *user, int n, con
     if (f_out) *f_out = res.f;
     if (count_out) *count_out = res.count;
     if (fail_out) *fail_out = res.fail;
+    return 0;
+}
+
+// The speculative driver of the block-exponential M-step with a host objective: Nelder-Mead is replayed against the values known
+// so far; whenever it asks for a new point, that point and up to width-1 points it may ask for next are evaluated as one round.
+// Same result as frk_optim_nelder_mead by construction -- exported so that the CPU test-suite can check exactly that.
+extern "C" int frk_optim_nelder_mead_speculative(frk_objective_fn fn, void *user, int n, const double *par, int maxit, double reltol,
+                                                 int width, double *x_out, double *f_out, int *requests_out, int *rounds_out,
+                                                 int *evals_out) {
+    FRK_REQUIRE(fn && par && x_out && n > 0 && width >= 1 && width <= 64, "frk_optim_nelder_mead_speculative: bad argument");
+    frk_model dummy;                                   // (statistics sink only; no device work)
+    SpecNM spec{&dummy, nullptr, n, maxit, reltol, std::vector<double>(par, par + n)};
+    NMResult res;
+    int rounds = 0, evals = 0;
+    for (;;) {
+        std::vector<double> need;
+        const int rc = spec.replay(need, res);
+        if (rc == 0) break;
+        if (rc != 99) return rc;
+        std::vector<std::vector<double>> batch = {need};
+        if (width > 1) spec.candidates(need.data(), (size_t)width, batch);
+        for (auto &b : batch) {
+            spec.pts.push_back(b);
+            spec.fv.push_back(fn(user, n, b.data()));
+            spec.owner.push_back(0);
+        }
+        rounds++;
+        evals += (int)batch.size();
+    }
+    for (int i = 0; i < n; i++) x_out[i] = res.x[i];
+    if (f_out) *f_out = res.f;
+    if (requests_out) *requests_out = (int)dummy.nm_requests;
+    if (rounds_out) *rounds_out = rounds;
+    if (evals_out) *evals_out = evals;
     return 0;
 }
 

@@ -25,6 +25,20 @@ def nmmin(fn, par, maxit=100, reltol=1e-4):
     return x, f.value, cnt.value, fail.value
 
 
+def nmmin_speculative(fn, par, width, maxit=100, reltol=1e-4):
+    """The same minimisation, driven as the block-exponential M-step drives it on the device: whenever Nelder-Mead asks for a new
+    point, that point and up to ``width - 1`` points it may ask for next are evaluated in one round.  Returns
+    (x, f(x), points requested, rounds, points evaluated); x and f(x) equal :func:`nmmin`'s."""
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    n = len(par)
+    cb = OBJECTIVE_FN(lambda user, k, x: float(fn(np.ctypeslib.as_array(x, shape=(k,)).copy())))
+    x = np.zeros(n)
+    f, req, rounds, evals = C.c_double(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    call("frk_optim_nelder_mead_speculative", cb, vp(None), n, vp(par.ctypes.data), int(maxit), float(reltol), int(width),
+         vp(x.ctypes.data), C.byref(f), C.byref(req), C.byref(rounds), C.byref(evals))
+    return x, f.value, req.value, rounds.value, evals.value
+
+
 def zeroin(f, lower, upper):
     """stats::uniroot(f, c(lower, upper))$root with the default tol = .Machine$double.eps^0.25."""
     cb = OBJECTIVE_FN(lambda user, k, x: float(f(x[0])))

@@ -401,6 +401,10 @@ int frk_model_predict_areal(frk_model *mdl, int64_t n, const int *d_rowptr0, con
  * the M-step (R/SREfit.R:618-621, :386-388); exported so that the iterate path can be tested on its own.       */
 int frk_optim_nelder_mead(frk_objective_fn fn, void *user, int n, const double *par, int maxit,
                           double reltol, double *x_out, double *f_out, int *count_out, int *fail_out);
+/* The same minimisation driven the way the block-exponential M-step drives it (speculative batches of up to `width` points per
+ * round, see frk_model_set_lanes): identical result; *rounds_out <= the number of sequential evaluations.                       */
+int frk_optim_nelder_mead_speculative(frk_objective_fn fn, void *user, int n, const double *par, int maxit, double reltol,
+                                      int width, double *x_out, double *f_out, int *requests_out, int *rounds_out, int *evals_out);
 int frk_optim_zeroin(frk_objective_fn fn, void *user, double lower, double upper, double *root_out);
 
 /* ---- host-buffer entry points (what the R .Call shim binds; H2D/D2H inside) ------------ */

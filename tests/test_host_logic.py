@@ -5,7 +5,7 @@ import pytest
 import scipy.optimize as so
 
 import frk_b200 as F
-from frk_b200.optim import nmmin, zeroin
+from frk_b200.optim import nmmin, nmmin_speculative, zeroin
 from frk_b200.sre import _parse_formula
 from oracle import frk_oracle as O
 
@@ -114,3 +114,33 @@ def test_space_time_manifolds():
         F.auto_basis(F.STplane(), y)
     with pytest.raises(ValueError):
         F.STsphere(-1.0)
+
+
+@pytest.mark.parametrize("width", [1, 2, 3, 4, 8])
+def test_speculative_nelder_mead_equals_sequential(width):
+    """The driver of the block-exponential M-step (SpecNM: replay against known values, evaluate the requested point together with
+    the points Nelder-Mead may ask for next) returns bit-for-bit what plain nmmin returns -- it only groups the evaluations.
+    Objectives: the shape of f_tau (log-determinant-like + trace-like term, 1-D), a 2-D one (tensor bases), one with an infeasible
+    region (+Inf, as f_tau returns for tau <= 1e-10) and a non-smooth one."""
+    fns = [
+        (lambda x: 40.0 * np.log(x[0]) + 55.0 / x[0] if x[0] > 1e-10 else np.inf, [0.3]),
+        (lambda x: 40.0 * np.log(x[0]) + 55.0 / x[0] if x[0] > 1e-10 else np.inf, [1.375]),        # start at the optimum (a converged M-step)
+        (lambda x: (x[0] - 1.3) ** 2 + 3.0 * (x[1] + 0.4) ** 2 + 0.5 * np.sin(3 * x[0]) * x[1], [0.1, 0.1]),
+        (lambda x: abs(x[0] - 0.7) + 0.1 * abs(x[0]) ** 1.5, [5.0]),
+        (lambda x: np.inf if x[0] < 0.05 else (np.log(x[0]) ** 2 + 1.0 / (x[0] + 0.01)), [0.06]),
+    ]
+    for fn, x0 in fns:
+        calls = []
+        def counted(x, fn=fn):
+            calls.append(tuple(x))
+            return fn(x)
+        xs, fs, cnt, fail = nmmin(counted, x0)
+        seq_distinct = len(set(calls))
+        xp, fp, req, rounds, evals = nmmin_speculative(fn, x0, width)
+        assert np.array_equal(xp, xs) and fp == fs
+        assert req == seq_distinct                       # Nelder-Mead asked for the same distinct points
+        assert rounds <= seq_distinct and evals >= seq_distinct - 0
+        if width == 1:
+            assert rounds == seq_distinct == evals
+        elif seq_distinct > 3:
+            assert rounds < seq_distinct                 # speculation saved at least one round
