@@ -47,6 +47,7 @@
   for (slot in c("mu_eta", "S_eta", "Q_eta", "Khat_inv", "alphahat", "Khat"))   # Khat last: it refreshes log|K|
     .Call("frkb200_model_set", mdl, slot, as.numeric(as.matrix(slot(object, slot))))
   .Call("frkb200_model_set", mdl, "sigma2fshat", as.numeric(object@sigma2fshat))
+  .Call("frkb200_model_set_lanes", mdl, 2L)      # two Nelder-Mead candidates per round (the measured optimum on B200)
   time <- system.time(
     fit <- .Call("frkb200_em_fit", mdl, as.integer(n_EM), as.numeric(tol),
                  if (object@K_type == "unstructured") 0L else 1L, as.numeric(lambda),

@@ -113,6 +113,12 @@ SEXP frkb200_model_get(SEXP mdl, SEXP name, SEXP len) {
     return out;
 }
 
+/* execution policy of optim() inside .update_K (no reference counterpart): candidate points factorised side by side */
+SEXP frkb200_model_set_lanes(SEXP mdl, SEXP lanes) {
+    FRK_TRY(frk_model_set_lanes((frk_model *)R_ExternalPtrAddr(mdl), Rf_asInteger(lanes)), (void)0);
+    return R_NilValue;
+}
+
 /* .EM_fit (R/SREfit.R:78-160) in one call: returns list(llk = numeric(niter), niter) */
 SEXP frkb200_em_fit(SEXP mdl, SEXP n_EM, SEXP tol, SEXP K_type, SEXP lambda, SEXP res, SEXP known_sigma2fs) {
     int n = Rf_asInteger(n_EM), niter = 0, known = !Rf_isNull(known_sigma2fs);
@@ -160,6 +166,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"frkb200_model_set_blocks", (DL_FUNC)&frkb200_model_set_blocks, 3},
     {"frkb200_model_set", (DL_FUNC)&frkb200_model_set, 3},
     {"frkb200_model_get", (DL_FUNC)&frkb200_model_get, 3},
+    {"frkb200_model_set_lanes", (DL_FUNC)&frkb200_model_set_lanes, 2},
     {"frkb200_em_fit", (DL_FUNC)&frkb200_em_fit, 7},
     {"frkb200_quadform", (DL_FUNC)&frkb200_quadform, 5},
     {"frkb200_chol2inv", (DL_FUNC)&frkb200_chol2inv, 1},
