@@ -316,6 +316,16 @@ def run_b200(args):
                     "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None, "launches": g["launches"],
                     "peak_source": "cuBLAS DGEMM 8192^3 probe in this run (MEASURED_PEAKS.json has no fp64 figure)",
                     "share_of_step": round(g["ms"] / tot_ms, 4)}
+            # DRAM bytes per launch from the committed ncu capture of this command (tools/traffic_pass.sh); a recorded
+            # measurement, not taken in this run -- the operands (<= 86 MB) mostly stay in the 126 MB L2
+            tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01f_dgemm_traffic.json")
+            if args.k_type == "block-exponential" and os.path.exists(tpath):
+                try:
+                    tj = json.load(open(tpath))
+                    roof["traffic"] = tj["dram_bytes_per_launch"]
+                    roof["traffic_source"] = "profiles/r01f_dgemm_traffic.json (ncu dram__bytes_read+write over %d launches)" % tj["launches"]
+                except Exception:
+                    pass
         elif ent is not None:
             roof = {"bound": "tensor" if ent["bound"] == "fp64" else "hbm", "kernel": name, "achieved": ent["achieved"],
                     "peak": ent["peak"], "unit": ent["unit"], "frac": ent["frac"], "traffic": None, "launches": g["launches"],
