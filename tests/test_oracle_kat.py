@@ -193,3 +193,97 @@ def test_point_in_polygon_classification_and_hexagon_tiling():
     # the cell's own centroid is inside it
     cidx = O.points_to_polygon_BAUs(np.column_stack([g["cx"], g["cy"]])[::13], g["ptr"], g["vx"], g["vy"])
     assert np.array_equal(cidx, np.arange(len(g["cx"]))[::13])
+
+
+def test_st_bau_index_time_slices():
+    """map_data_to_BAUs(ST), R/geometryfns.R:1455-1470: slice i takes t1_i <= time < t1_{i+1}; the LAST slice takes everything from
+    its start on; before the first start -> NA; a spatial NA stays NA; BAU numbering is space-fastest."""
+    brk = np.array([0.0, 1.0, 2.5])
+    t = np.array([-1.0, 0.0, 0.5, 1.0, 2.5, 9.0, np.nan, 2.4999])
+    spi = np.array([0, 1, 2, 3, -1, 5, 1, 4])
+    assert O.st_bau_index(spi, t, brk, 10).tolist() == [-1, 1, 2, 13, -1, 25, -1, 14]
+
+
+def test_buildc_polygons_and_areal_sre_by_hand():
+    """BuildC(SpatialPolygons), R/geometryfns.R:1572-1616, on a 4 x 4 grid of BAU centroids (0.5 .. 3.5): polygon A = [0,2] x [0,2]
+    holds centroids (0.5|1.5, 0.5|1.5) = BAUs 0,1,4,5; polygon B = [2,4] x [0,1] holds BAUs 2,3; a centroid ON an edge counts.
+    SRE() then normalises the rows (R/SRE.R:483-490): weights 1/4 and 1/2, Vfs = sum c^2 fs, X = BAU covariate averages."""
+    gx, gy = np.meshgrid(np.arange(0.5, 4.0), np.arange(0.5, 4.0), indexing="xy")
+    cen = np.column_stack([gx.ravel(), gy.ravel()])
+    ptr = np.array([0, 5, 10, 15])
+    vx = np.array([0, 2, 2, 0, 0, 2, 4, 4, 2, 2, 0.5, 1.5, 1.5, 0.5, 0.5], dtype=float)
+    vy = np.array([0, 0, 2, 2, 0, 0, 0, 1, 1, 0, 2.5, 2.5, 3.5, 3.5, 2.5], dtype=float)        # third: edge through centroids 8,9,12,13
+    i, j, x = O.BuildC_polygons(ptr, vx, vy, cen)
+    assert i.tolist() == [0] * 4 + [1] * 2 + [2] * 4 and j.tolist() == [0, 1, 4, 5, 2, 3, 8, 9, 12, 13] and np.all(x == 1.0)
+    import scipy.sparse as sp
+    C = sp.csr_matrix((x, (i, j)), shape=(3, 16))
+    basis = O.local_basis(O.plane(), np.array([[1.0, 1.0], [3.0, 3.0]]), [3.0, 3.0], "bisquare")
+    fs = np.arange(1.0, 17.0)
+    M = O.SRE(basis, cen, fs, None, np.array([1.0, 2.0, 3.0]), np.array([0.1, 0.2, 0.3]),
+              X_BAU=np.column_stack([np.ones(16), cen[:, 0]]), K_type="unstructured", C=C)
+    np.testing.assert_allclose(M.Vfs, [(1 + 2 + 5 + 6) / 16.0, (3 + 4) / 4.0, (9 + 10 + 13 + 14) / 16.0], rtol=1e-15)
+    np.testing.assert_allclose(M.X[:, 1], [1.0, 3.0, 1.0], rtol=1e-15)
+    np.testing.assert_allclose(M.S.toarray()[1], M.S0.toarray()[[2, 3]].mean(axis=0), rtol=1e-15)
+    np.testing.assert_allclose(M.Ve, [0.01, 0.04, 0.09], rtol=1e-15)
+
+
+def test_areal_case2_closed_form_equals_joint_solve():
+    """The closed form of predict(obs_fs = FALSE) that the device implements for areal data with disjoint supports
+    (frk_model_predict_areal) against the literal joint (eta, xi) solve of R/SREpredict.R:308-333."""
+    import scipy.sparse as sp
+    baus = O.auto_BAUs_plane(np.array([[0.0, 0.0], [1.0, 1.0]]), cellsize=0.1)
+    cen = baus.centroids()
+    N = len(cen)
+    ptr, vx, vy = [0], [], []
+    for iy in range(3):
+        for ix in range(3):
+            if (ix, iy) == (1, 1):
+                continue
+            x0, y0 = 0.3 * ix + 0.013, 0.3 * iy + 0.013
+            vx += [x0, x0 + 0.3, x0 + 0.3, x0, x0]; vy += [y0, y0, y0 + 0.3, y0 + 0.3, y0]; ptr.append(len(vx))
+    i, j, x = O.BuildC_polygons(np.array(ptr), np.array(vx), np.array(vy), cen)
+    m = len(ptr) - 1
+    C = sp.csr_matrix((x, (i, j)), shape=(m, N))
+    rng = np.random.default_rng(3)
+    fs = 1.0 + 0.5 * (cen[:, 0] > 0.5)
+    M = O.SRE(O.auto_basis(O.plane(), cen, regular=1, nres=1), cen, fs, None, rng.standard_normal(m), np.full(m, 0.1),
+              X_BAU=np.column_stack([np.ones(N), cen.sum(axis=1)]), K_type="unstructured", C=C)
+    O.SRE_fit(M, n_EM=3, tol=0.0)
+    s2, a = M.sigma2fshat, M.alphahat
+    assert s2 > 0
+    mu, var, _ = O.predict(M, obs_fs=False)                       # literal (r + N) x (r + N) solve
+    d = s2 * M.Vfs + M.Ve
+    Sig = O.chol2inv(O.chol_upper(O._gram(M.S, 1.0 / d) + M.Khat_inv))
+    mut = Sig @ (M.S.T @ ((M.Z - M.X @ a) / d))
+    q, QS = O.batch_compute_var(M.S0, Sig), O.batch_compute_var(M.S, Sig)
+    res = M.Z - M.X @ a - M.S @ mut
+    mu2, var2 = M.X_BAU @ a + M.S0 @ mut, q + s2 * fs
+    V = Sig @ M.S.T.toarray()
+    Cm = sp.csr_matrix(M.Cmat)
+    S0d = M.S0.toarray()
+    for jj in range(m):
+        for kk in range(Cm.indptr[jj], Cm.indptr[jj + 1]):
+            k, c = Cm.indices[kk], Cm.data[kk]
+            g = s2 * fs[k] * c / d[jj]
+            mu2[k] += g * res[jj]
+            var2[k] = q[k] - 2 * g * (S0d[k] @ V[:, jj]) + g * g * QS[jj] + s2 * fs[k] - g * g * d[jj]
+    np.testing.assert_allclose(mu2, mu, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var2, var, rtol=1e-9)
+
+
+def test_auto_basis_prune_rule():
+    """auto_basis(prune > 0), R/basisfns.R:536-553: a resolution's function survives iff the column sum of the FIRST-pass basis over
+    the data is >= prune; scales of the survivors are then re-derived (nearest surviving centroid), centroids keep their order."""
+    rng = np.random.default_rng(5)
+    xy = np.vstack([rng.uniform(0, 1, (800, 2)) ** 2, [[0.0, 0.0], [1.0, 1.0]]])
+    full = O.auto_basis(O.plane(), xy, regular=1, nres=2)
+    pr = O.auto_basis(O.plane(), xy, regular=1, nres=2, prune=12.0)
+    cs = np.asarray(O.eval_basis(full, xy).sum(axis=0)).ravel()
+    keep = cs >= 12.0
+    assert 0 < keep.sum() < full.n and pr.n == keep.sum()
+    assert np.array_equal(pr.loc, full.loc[keep]) and np.array_equal(pr.res, full.res[keep])
+    # re-derived scales: 1.5 * 1.25 * distance to the nearest surviving centroid of the same resolution
+    for rr in (1, 2):
+        L = pr.loc[pr.res == rr]
+        D = O.distR(L, L); np.fill_diagonal(D, np.inf)
+        np.testing.assert_array_equal(pr.scale[pr.res == rr], 1.5 * (D.min(axis=1) * 1.25))
