@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--predict-reps", type=int, default=5)
+    ap.add_argument("--deterministic", action="store_true", help="fixed-order Gram flush instead of fp64 atomics (bit-reproducible runs)")
     ap.add_argument("--distribute-nm", action="store_true", help="spread the Nelder-Mead candidates over the ranks (default: replicated on local lanes)")
     ap.add_argument("--lanes", type=int, default=None, help="concurrent Nelder-Mead evaluation lanes per GPU (frk_model_set_lanes)")
     return ap.parse_args()
@@ -72,7 +73,7 @@ def config(args, r, n_bau, m):
             "cache": "inputs larger than L2 (S 0.37 GB, six r x r fp64 matrices 86 MB each, S0 4 GB); no L2 flush",
             "partition": "BAU rows block-partitioned over ranks; r-sized state replicated",
             "nm_lanes": args.lanes if args.lanes else (1 if (args.distribute_nm and args.gpus > 1) else 2),
-            "nm_distributed": bool(args.distribute_nm and args.gpus > 1)}
+            "nm_distributed": bool(args.distribute_nm and args.gpus > 1), "deterministic": bool(args.deterministic)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -200,6 +201,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = F.get_device(local)
+    if args.deterministic:
+        dev.set_deterministic(True)
     _dbg("device + process group up")
 
     def barrier():

@@ -52,6 +52,7 @@ SIGNATURES = {
     "frk_memset0": (c_int, [vp, vp, C.c_size_t]),
     "frk_launch_count": (c_i64, [vp]),
     "frk_use_graphs": (c_int, [vp, c_int]),
+    "frk_use_deterministic": (c_int, [vp, c_int]),
     "frk_profile": (c_int, [vp, c_int]),
     "frk_profile_report": (c_int, [vp, C.c_char_p, C.c_size_t]),
     "frk_basis_create": (c_int, [vp, c_int, c_dbl, c_int, c_int, c_int, vp, vp, vp, C.POINTER(vp)]),

@@ -19,6 +19,7 @@
 // is not read at all.  A bucket whose union exceeds 64 columns (or, for the quadratic form, a row with more
 // than 40 non-zeros: tensor-product bases) takes the direct kernels' arithmetic inside the same launch.
 #include "common.cuh"
+#include <cub/cub.cuh>
 
 constexpr int UMAX = 64;          // columns per bucket handled through shared memory
 constexpr int KMAX = 40;          // non-zeros per row handled by the thread-per-row quadratic form
@@ -82,12 +83,8 @@ __global__ void bucket_count_kernel(int64_t n, const int *__restrict__ rowptr, c
     }
 }
 
-__global__ void bucket_scatter_kernel(int64_t n, const int *__restrict__ key, const int *__restrict__ bptr, int *__restrict__ fill,
-                                      int *__restrict__ perm) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k = key[i];
-        perm[bptr[k] + atomicAdd(fill + k, 1)] = (int)i;
-    }
+__global__ void iota_kernel(int64_t n, int *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int)i;
 }
 
 constexpr int BU_T = 256, BU_CH = 256;
@@ -95,6 +92,7 @@ struct UnionSmem {
     int keys[HSIZE];
     int ids[HSIZE];
     int ucol[UMAX];
+    int rank[UMAX], sorted[UMAX];
     int nU;
     ChunkMeta<BU_CH> C;
 };
@@ -115,6 +113,23 @@ __global__ void __launch_bounds__(BU_T) bucket_union_kernel(int nbuckets, const 
         __syncthreads();
         for (int pass = 0; pass < 2; pass++) {       // pass 0: union; pass 1: local index of every entry
             if (pass == 1 && S.nU > UMAX) break;
+            if (pass == 1) {
+                // The ids handed out in pass 0 follow the order in which threads won their atomics.  Re-number the union in
+                // ascending column order so that the local layout -- hence every summation order downstream -- is the same in every run.
+                const int nU0 = S.nU;
+                if (threadIdx.x < nU0) {
+                    const int c = S.ucol[threadIdx.x];
+                    int rk = 0;
+                    for (int u = 0; u < nU0; u++) rk += S.ucol[u] < c;
+                    S.rank[threadIdx.x] = rk;
+                    S.sorted[rk] = c;
+                }
+                __syncthreads();
+                for (int s2 = threadIdx.x; s2 < HSIZE; s2 += BU_T)
+                    if (S.keys[s2] != -1) S.ids[s2] = S.rank[S.ids[s2]];
+                if (threadIdx.x < nU0) S.ucol[threadIdx.x] = S.sorted[threadIdx.x];
+                __syncthreads();
+            }
             for (int c0 = b0; c0 < b1; c0 += BU_CH) {
                 const int nr = min(BU_CH, b1 - c0);
                 __syncthreads();
@@ -165,15 +180,27 @@ extern "C" int frk_csr_bucket_rows(frk_ctx *ctx, int64_t n, const int *d_rowptr,
         return 0;
     }
     int *key = nullptr;
-    FRK_CHECK_CUDA(cudaMallocAsync((void **)&key, (size_t)(n + 2 * (size_t)ncols) * sizeof(int), ctx->stream));
-    int *cnt = key + n, *fill = cnt + ncols;
-    FRK_CHECK_CUDA(cudaMemsetAsync(cnt, 0, 2 * (size_t)ncols * sizeof(int), ctx->stream));
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&key, (size_t)(3 * n + (size_t)ncols) * sizeof(int), ctx->stream));
+    int *key2 = key + n, *idx = key2 + n, *cnt = idx + n;
+    FRK_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)ncols * sizeof(int), ctx->stream));
     unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
     FRK_LAUNCH(ctx, bucket_count_kernel, grid, 256, 0, n, d_rowptr, d_col, key, cnt);
     int64_t tot = 0;
     int rc = frk_exclusive_scan_i32(ctx, cnt, ncols, d_bptr, &tot);
     if (!rc) {
-        FRK_LAUNCH(ctx, bucket_scatter_kernel, grid, 256, 0, n, key, d_bptr, fill, d_perm);
+        // stable radix sort of the rows by key: within a bucket the rows stay in ascending order, so every per-bucket summation
+        // downstream runs in the same order in every run (an atomic scatter would hand out the slots in race order)
+        FRK_LAUNCH(ctx, iota_kernel, grid, 256, 0, n, idx);
+        int end_bit = 1;
+        while ((1LL << end_bit) < ncols) end_bit++;
+        size_t tmp_bytes = 0;
+        void *tmp = nullptr;
+        FRK_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, idx, d_perm, (int)n, 0, end_bit, ctx->stream));
+        FRK_CHECK_CUDA(cudaMallocAsync(&tmp, tmp_bytes, ctx->stream));
+        const cudaError_t es = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, idx, d_perm, (int)n, 0, end_bit, ctx->stream);
+        cudaFreeAsync(tmp, ctx->stream);
+        FRK_CHECK_CUDA(es);
+        ctx->launches += 1;
         FRK_LAUNCH(ctx, bucket_union_kernel, (unsigned)std::min<int64_t>(ncols, (int64_t)ctx->sm_count * 8), BU_T, 0, ncols, d_bptr,
                    d_perm, d_rowptr, d_col, d_ucol, d_nU, d_lid);
     }
@@ -202,7 +229,11 @@ struct frk_rowbuckets {
     int *tile_off = nullptr;       // [T+1] offset of the tile in ell_val / ell_lid (entries)
     double *ell_val = nullptr;
     unsigned char *ell_lid = nullptr;
-    std::vector<void *> allocs;
+    // deterministic Gram (frk_use_deterministic): per-bucket tile staging and the inverted index column -> (bucket, local id),
+    // built on first use
+    mutable double *stage = nullptr, *stage_rhs = nullptr, *stage_scal = nullptr;
+    mutable int *inv_ptr = nullptr, *inv_bucket = nullptr, *inv_lid = nullptr;
+    mutable std::vector<void *> allocs;
 };
 
 __global__ void ell_tiles_per_bucket_kernel(int ncols, const int *__restrict__ bptr, const int *__restrict__ nU, int *__restrict__ cnt) {
@@ -334,7 +365,8 @@ __global__ void __launch_bounds__(GR_T) gram_bucket_kernel(int nbuckets, const i
                                                            const double *__restrict__ val, const double *__restrict__ z,
                                                            const double *__restrict__ X, int p, AlphaB alpha,
                                                            const double *__restrict__ ve, const double *__restrict__ vfs, double sigma2fs,
-                                                           double *__restrict__ acc) {
+                                                           double *__restrict__ acc, double *__restrict__ stage,
+                                                           double *__restrict__ stage_rhs, double *__restrict__ stage_scal) {
     __shared__ GramSmem S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
@@ -423,21 +455,28 @@ __global__ void __launch_bounds__(GR_T) gram_bucket_kernel(int nbuckets, const i
                 for (int rl = 0; rl < nr; rl++) rh += S.A[rl][threadIdx.x] * S.wr[rl];
             }
         }
-        // flush: each unordered pair of local columns once, into the upper triangle (row <= col) of G
+        // flush: each unordered pair of local columns once, into the upper triangle (row <= col) of G -- or, in deterministic mode,
+        // into this bucket's staged tile (local pair (la <= lb)), which gram_ordered_flush_kernel adds in a fixed order
         if (active) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int la = ty * 4 + i, lb = tx * 4 + j;
-                    if (la < nU && lb < nU && (ty < tx || la <= lb) && t[i][j] != 0.0) {
-                        const int ca = S.ucol[la], cb = S.ucol[lb];
-                        atomicAdd(G + min(ca, cb) + (size_t)r * max(ca, cb), t[i][j]);
+                    if (la < nU && lb < nU && (ty < tx || la <= lb)) {
+                        if (stage) stage[((size_t)b * UMAX + la) * UMAX + lb] = t[i][j];
+                        else if (t[i][j] != 0.0) {
+                            const int ca = S.ucol[la], cb = S.ucol[lb];
+                            atomicAdd(G + min(ca, cb) + (size_t)r * max(ca, cb), t[i][j]);
+                        }
                     }
                 }
             }
         }
-        if (threadIdx.x < nU) atomicAdd(rhs + S.ucol[threadIdx.x], rh);
+        if (threadIdx.x < nU) {
+            if (stage) stage_rhs[(size_t)b * UMAX + threadIdx.x] = rh;
+            else atomicAdd(rhs + S.ucol[threadIdx.x], rh);
+        }
     }
     s_quad = warp_sum(s_quad);
     s_logd = warp_sum(s_logd);
@@ -447,9 +486,79 @@ __global__ void __launch_bounds__(GR_T) gram_bucket_kernel(int nbuckets, const i
     if (threadIdx.x == 0) {
         double a = 0, bsum = 0;
         for (int i = 0; i < GR_T / 32; i++) { a += S.red[i][0]; bsum += S.red[i][1]; }
-        atomicAdd(rhs + r, a);
-        atomicAdd(rhs + r + 1, bsum);
+        if (stage) { stage_scal[2 * blockIdx.x] = a; stage_scal[2 * blockIdx.x + 1] = bsum; }
+        else { atomicAdd(rhs + r, a); atomicAdd(rhs + r + 1, bsum); }
     }
+}
+
+// Deterministic flush: one warp owns row a of G.  For every bucket k (ascending) whose column set holds a, with local id la, it adds
+// the staged pair values (a, cb), cb >= a, and the right-hand-side entry; block 0 sums the per-CTA scalars in CTA order.
+__global__ void __launch_bounds__(256) gram_ordered_flush_kernel(int r, const int *__restrict__ inv_ptr, const int *__restrict__ inv_bucket,
+                                                                 const int *__restrict__ inv_lid, const int *__restrict__ ucol_all,
+                                                                 const int *__restrict__ nU_all, const double *__restrict__ stage,
+                                                                 const double *__restrict__ stage_rhs, const double *__restrict__ stage_scal,
+                                                                 int ncta, double *__restrict__ acc) {
+    const int lane = threadIdx.x & 31;
+    const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    double *G = acc, *rhs = acc + (size_t)r * r;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double q = 0.0, l = 0.0;
+        for (int c = 0; c < ncta; c++) { q += stage_scal[2 * c]; l += stage_scal[2 * c + 1]; }
+        rhs[r] += q; rhs[r + 1] += l;
+    }
+    if (a >= r) return;
+    double rh = 0.0;
+    for (int e = inv_ptr[a]; e < inv_ptr[a + 1]; e++) {
+        const int k = inv_bucket[e], la = inv_lid[e], nU = nU_all[k];
+        const int *uc = ucol_all + (size_t)k * UMAX;
+        const double *T = stage + (size_t)k * UMAX * UMAX;
+        for (int lb = lane; lb < nU; lb += 32) {
+            const int cb = uc[lb];
+            if (cb < a) continue;
+            const double v = la <= lb ? T[(size_t)la * UMAX + lb] : T[(size_t)lb * UMAX + la];
+            G[a + (size_t)r * cb] += v;                            // this warp is the only writer of row a; buckets in ascending order
+        }
+        rh += stage_rhs[(size_t)k * UMAX + la];
+    }
+    if (lane == 0) rhs[a] += rh;
+}
+
+// staging buffers and the inverted index column -> (bucket, local id) for the ordered flush; buckets with more than UMAX columns
+// (direct path: atomics) are not indexed.  Built once per row-bucket set, on the host from the device's column sets.
+static int gram_prepare_ordered(frk_ctx *ctx, const frk_rowbuckets *bk, int r) {
+    if (bk->inv_ptr) return 0;
+    std::vector<int> ucol((size_t)r * UMAX), nU(r);
+    FRK_CHECK_CUDA(cudaMemcpyAsync(ucol.data(), bk->ucol, ucol.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaMemcpyAsync(nU.data(), bk->nU, nU.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> ptr(r + 1, 0);
+    for (int k = 0; k < r; k++)
+        if (nU[k] > 0 && nU[k] <= UMAX) for (int l = 0; l < nU[k]; l++) ptr[ucol[(size_t)k * UMAX + l] + 1]++;
+    for (int a = 0; a < r; a++) ptr[a + 1] += ptr[a];
+    std::vector<int> ib(std::max(ptr[r], 1)), il(std::max(ptr[r], 1)), fill(ptr.begin(), ptr.end() - 1);
+    for (int k = 0; k < r; k++)                                   // ascending k within every column
+        if (nU[k] > 0 && nU[k] <= UMAX) for (int l = 0; l < nU[k]; l++) {
+            const int a = ucol[(size_t)k * UMAX + l], o = fill[a]++;
+            ib[o] = k; il[o] = l;
+        }
+    auto alloc = [&](void **p, size_t bytes) -> int {
+        FRK_CHECK_CUDA(cudaMallocAsync(p, std::max<size_t>(bytes, 16), ctx->stream));
+        bk->allocs.push_back(*p);
+        return 0;
+    };
+    const unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 8);
+    int *d_ptr = nullptr, *d_ib = nullptr, *d_il = nullptr;
+    if (alloc((void **)&d_ptr, ptr.size() * sizeof(int)) || alloc((void **)&d_ib, ib.size() * sizeof(int)) ||
+        alloc((void **)&d_il, il.size() * sizeof(int)) || alloc((void **)&bk->stage, (size_t)r * UMAX * UMAX * sizeof(double)) ||
+        alloc((void **)&bk->stage_rhs, (size_t)r * UMAX * sizeof(double)) || alloc((void **)&bk->stage_scal, 2 * (size_t)grid * sizeof(double)))
+        return 1;
+    FRK_CHECK_CUDA(cudaMemcpyAsync(d_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    FRK_CHECK_CUDA(cudaMemcpyAsync(d_ib, ib.data(), ib.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    FRK_CHECK_CUDA(cudaMemcpyAsync(d_il, il.data(), il.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));             // the host vectors go out of scope
+    bk->inv_bucket = d_ib; bk->inv_lid = d_il;
+    bk->inv_ptr = d_ptr;
+    return 0;
 }
 
 extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int *d_col, const double *d_val,
@@ -464,8 +573,16 @@ extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *
     AlphaB al{};
     for (int q = 0; q < p; q++) al.a[q] = h_alpha[q];
     unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 8);
+    if (!ctx->deterministic) {
+        FRK_LAUNCH(ctx, gram_bucket_kernel, grid, GR_T, 0, r, d_bptr, d_perm, d_ucol, d_nU, d_lid, m, r, d_rowptr, d_col, d_val, d_z, d_X,
+                   p, al, d_ve, d_vfs, sigma2fs, d_acc, (double *)nullptr, (double *)nullptr, (double *)nullptr);
+        return 0;
+    }
+    if (int rc = gram_prepare_ordered(ctx, bk, r)) return rc;
     FRK_LAUNCH(ctx, gram_bucket_kernel, grid, GR_T, 0, r, d_bptr, d_perm, d_ucol, d_nU, d_lid, m, r, d_rowptr, d_col, d_val, d_z, d_X,
-               p, al, d_ve, d_vfs, sigma2fs, d_acc);
+               p, al, d_ve, d_vfs, sigma2fs, d_acc, bk->stage, bk->stage_rhs, bk->stage_scal);
+    FRK_LAUNCH(ctx, gram_ordered_flush_kernel, (unsigned)cdiv((int64_t)r * 32, 256), 256, 0, r, bk->inv_ptr, bk->inv_bucket, bk->inv_lid,
+               d_ucol, d_nU, bk->stage, bk->stage_rhs, bk->stage_scal, (int)grid, d_acc);
     return 0;
 }
 

@@ -37,6 +37,7 @@ struct frk_ctx {
     std::map<std::string, frk_prof_stat> prof_stats;
     // CUDA-graph cache for the launch-latency-bound factorisations: key = (op, r, pointers)
     bool use_graphs = true;
+    bool deterministic = false;          // frk_use_deterministic: fixed-order reductions (the Gram flush) instead of fp64 atomics
     struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; };
     std::map<std::array<uintptr_t, 5>, GraphEntry> graphs;
     // lane contexts (frk_ctx_lane): created on first use, kept for the life of this context so that models come and go cheaply

@@ -79,6 +79,7 @@ int frk_ctx_lane(frk_ctx *parent, int idx, bool high_priority, frk_ctx **out) {
     if ((int)v.size() <= idx) v.resize(idx + 1, nullptr);
     if (!v[idx]) { if (int rc = frk_ctx_create_lane(parent, high_priority, &v[idx])) return rc; }
     v[idx]->use_graphs = parent->use_graphs;
+    v[idx]->deterministic = parent->deterministic;
     *out = v[idx];
     return 0;
 }
@@ -207,6 +208,16 @@ extern "C" int frk_profile_report(frk_ctx *ctx, char *buf, size_t cap) {
 extern "C" int frk_use_graphs(frk_ctx *ctx, int enable) {
     FRK_REQUIRE(ctx, "frk_use_graphs: NULL ctx");
     ctx->use_graphs = enable != 0;
+    for (frk_ctx *l : ctx->lanes_hi) if (l) l->use_graphs = ctx->use_graphs;
+    for (frk_ctx *l : ctx->lanes_lo) if (l) l->use_graphs = ctx->use_graphs;
+    return 0;
+}
+
+extern "C" int frk_use_deterministic(frk_ctx *ctx, int enable) {
+    FRK_REQUIRE(ctx, "frk_use_deterministic: NULL ctx");
+    ctx->deterministic = enable != 0;
+    for (frk_ctx *l : ctx->lanes_hi) if (l) l->deterministic = ctx->deterministic;
+    for (frk_ctx *l : ctx->lanes_lo) if (l) l->deterministic = ctx->deterministic;
     return 0;
 }
 

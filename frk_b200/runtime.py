@@ -77,6 +77,11 @@ class Device:
             return vp(None)
         return vp(t.data_ptr() + offset_elems * t.element_size())
 
+    def set_deterministic(self, on: bool = True):
+        """Run-to-run bit-reproducible results on one GPU (frk_use_deterministic): the Gram tiles are added in a fixed order
+        instead of with fp64 atomics."""
+        call("frk_use_deterministic", self.ctx, 1 if on else 0)
+
     def sync(self):
         call("frk_sync", self.ctx)
 

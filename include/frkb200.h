@@ -73,6 +73,10 @@ int64_t frk_launch_count(frk_ctx *ctx);
  * are the ALGORITHMIC work declared at the launch site.  Enabling clears earlier statistics. */
 /* The factorisations replay cached CUDA graphs of their launch sequences (default on; off while profiling). */
 int frk_use_graphs(frk_ctx *ctx, int enable);
+/* enable != 0: run-to-run bit-reproducible results on one GPU.  The only order-dependent reduction on the EM path is the flush of
+ * the per-bucket Gram tiles (fp64 atomics by default); in this mode every bucket stores its tile and a second kernel adds the
+ * tiles into S'D^-1 S in ascending bucket order, one warp owning each row (frk_gram_rhs_bucketed).  Default off.             */
+int frk_use_deterministic(frk_ctx *ctx, int enable);
 int frk_profile(frk_ctx *ctx, int enable);
 int frk_profile_report(frk_ctx *ctx, char *buf, size_t cap);
 

@@ -2,6 +2,8 @@
 seeded inputs.  Oracle provenance: CPU restatement of the cited reference lines (no R in this image).
 Bars (BASELINE.json north_star): C_Z and the S sparsity pattern bit-exact; S values, mu_eta, predictive
 variances and the log-likelihood trace within rtol 1e-9."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -805,3 +807,39 @@ def test_areal_data_refusals(dev):
         F.SRE("z ~ 1", mk([(0.01, 0.01, 0.4), (0.21, 0.21, 0.4)]), basis, gb, est_error=False)
     with pytest.raises(F.FRKError, match="contain no BAU centroid"):
         F.SRE("z ~ 1", mk([(0.01, 0.01, 0.4), (0.601, 0.601, 0.01)]), basis, gb, est_error=False)
+
+
+def test_deterministic_mode_is_bit_reproducible(dev):
+    """frk_use_deterministic: the Gram tiles are flushed in a fixed order (one warp owns a row of S'D^-1 S, buckets ascending) instead
+    of with fp64 atomics -- the only order-dependent reduction on the EM path.  Then (i) two runs agree BIT FOR BIT, (ii) so do a
+    strictly sequential Nelder-Mead and the concurrent-lanes one (the iterates are identical, not just close), and (iii) the
+    results still match the oracle; the Gram itself matches the atomics version to rounding."""
+    import frk_b200 as F
+    from frk_b200._lib import call
+    try:
+        dev.set_deterministic(True)
+        runs = []
+        for lanes in (2, 2, 1):
+            _, Mg = _setup_plane(F, m=3000, nres=3, K_type="block-exponential", hetero=True)
+            F.SRE_fit(Mg, n_EM=5, tol=0.0, lanes=lanes)
+            runs.append((Mg.info_fit["llk"].copy(), Mg.get("Khat"), Mg.get("mu_eta"), np.array(Mg.info_fit["tau"]), Mg.sigma2fshat,
+                         F.predict(Mg, obs_fs=False)["var"]))
+        for other in runs[1:]:
+            for a, b in zip(runs[0], other):
+                assert np.array_equal(np.asarray(a), np.asarray(b))
+        Mo, Mg = _setup_plane(F, m=3000, nres=3, K_type="block-exponential", hetero=True)
+        O.SRE_fit(Mo, n_EM=5, tol=0.0)
+        np.testing.assert_allclose(runs[0][0], Mo.info_fit["llk"], rtol=RTOL)
+        # the accumulator itself: ordered flush vs atomics
+        r = Mg.r
+        acc_d, acc_a = dev.zeros(r * r + r + 2), dev.zeros(r * r + r + 2)
+        alpha = np.ascontiguousarray(Mg.alphahat, dtype=np.float64)
+        args = (Mg.m, r, dev.ptr(Mg.S.rowptr), dev.ptr(Mg.S.col), dev.ptr(Mg.S.val), Mg.S.buckets(dev), dev.ptr(Mg.Z), dev.ptr(Mg.X),
+                Mg.p, alpha.ctypes.data_as(C.c_void_p), dev.ptr(Mg.Ve), dev.ptr(Mg.Vfs), 0.3)
+        call("frk_gram_rhs_bucketed", dev.ctx, *args, dev.ptr(acc_d))
+        dev.set_deterministic(False)
+        call("frk_gram_rhs_bucketed", dev.ctx, *args, dev.ptr(acc_a))
+        a_d, a_a = dev.download(acc_d), dev.download(acc_a)
+        np.testing.assert_allclose(a_d, a_a, rtol=1e-12, atol=1e-12 * abs(a_a).max())
+    finally:
+        dev.set_deterministic(False)
