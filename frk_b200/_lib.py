@@ -68,6 +68,8 @@ SIGNATURES = {
     "frk_csr_tensor_fill": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_csr_row_normalise": (c_int, [vp, c_i64, vp, vp]),
     "frk_polygon_lookup_count": (c_int, [vp, vp, c_i64, vp, c_i64, vp, p_i64]),
+    "frk_polygon_incidence_count": (c_int, [vp, vp, c_i64, vp, c_i64, vp, p_i64]),
+    "frk_polygon_incidence_fill": (c_int, [vp, vp, c_i64, vp, c_i64, vp, c_i64, vp, vp, vp, vp, p_i64]),
     "frk_areal_incidence": (c_int, [vp, c_i64, vp, c_i64, vp, vp, vp, vp, p_i64, p_i64]),
     "frk_csr_aggregate_count": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, p_i64]),
     "frk_csr_aggregate_fill": (c_int, [vp, c_i64, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -121,6 +123,7 @@ SIGNATURES = {
     "frk_model_create": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, ALLREDUCE_FN, vp, C.POINTER(vp)]),
     "frk_model_create_host": (c_int, [vp, c_i64, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "frk_model_destroy": (c_int, [vp]),
+    "frk_model_predict_polygons": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_int, c_i64, vp, vp, vp, c_i64, vp, vp, vp]),
     "frk_model_predict_areal": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_model_set_lanes": (c_int, [vp, c_int]),
     "frk_model_set_nm_distribute": (c_int, [vp, c_int]),

@@ -6,6 +6,7 @@
 // restated from its published algorithm): idx_d = round((x_d - offset_d)/cellsize_d), rows counted
 // from the top, outside -> NA.  R's round() is half-to-even == rint().
 #include "common.cuh"
+#include <cub/cub.cuh>
 
 __global__ void __launch_bounds__(256) grid_lookup_kernel(int64_t n, const double *__restrict__ xy, int64_t ld, double ox, double oy,
                                                           double cx, double cy, int nx, int ny,
@@ -390,4 +391,110 @@ extern "C" int frk_polygon_lookup_count(frk_ctx *ctx, const frk_polygons *P, int
     FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     *h_multi = h;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// General incidence of points in (possibly overlapping) polygons: BuildC(SpatialPolygons) for prediction polygons, C_P
+// (R/geometryfns.R:1572-1616, R/SREpredict.R:119-128): every polygon gets ALL the points (BAU centroids) it contains.
+// Pass 1 counts the containing polygons per point, pass 2 emits (polygon, point) pairs, a stable radix sort by polygon turns
+// them into CSR rows with ascending point index; the weights are BAUs$wts / row sum (normalise_wts).
+// ---------------------------------------------------------------------------------
+template <bool EMIT>
+__global__ void __launch_bounds__(256) polygon_incidence_kernel(int64_t n, const double *__restrict__ xy, int64_t ld, double x0, double y0,
+                                                                double hx, double hy, int nx, int ny, const int *__restrict__ cell_start,
+                                                                const int *__restrict__ cand, const int *__restrict__ ptr,
+                                                                const double *__restrict__ vx, const double *__restrict__ vy,
+                                                                const double *__restrict__ bbox, int *__restrict__ cnt_or_off,
+                                                                int *__restrict__ pid_out, int *__restrict__ pt_out, int *__restrict__ pcnt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double px = xy[i], py = xy[i + ld];
+        int k = 0;
+        const int o = EMIT ? cnt_or_off[i] : 0;
+        double fx = floor((px - x0) / hx), fy = floor((py - y0) / hy);
+        if (fx == (double)nx && px == x0 + hx * nx) fx = nx - 1;
+        if (fy == (double)ny && py == y0 + hy * ny) fy = ny - 1;
+        if (fx >= 0 && fx < nx && fy >= 0 && fy < ny) {
+            const int64_t c = (int64_t)fy * nx + (int64_t)fx;
+            for (int e = cell_start[c]; e < cell_start[c + 1]; e++) {
+                const int pid = __ldg(cand + e);
+                const double *bb = bbox + 4 * (size_t)pid;
+                if (px < __ldg(bb) || px > __ldg(bb + 1) || py < __ldg(bb + 2) || py > __ldg(bb + 3)) continue;
+                const int b = ptr[pid];
+                if (in_poly_dev(px, py, vx + b, vy + b, ptr[pid + 1] - b) != 0) {
+                    if (EMIT) { pid_out[o + k] = pid; pt_out[o + k] = (int)i; atomicAdd(pcnt + pid, 1); }
+                    k++;
+                }
+            }
+        }
+        if (!EMIT) cnt_or_off[i] = k;
+    }
+}
+
+__global__ void __launch_bounds__(256) incidence_weights_kernel(int64_t m, const int *__restrict__ rowptr, const int *__restrict__ members,
+                                                                const double *__restrict__ wts, double *__restrict__ weights,
+                                                                int *__restrict__ empty) {
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= m) return;
+    const int a = rowptr[j], b = rowptr[j + 1];
+    if (a == b) { if (lane == 0) atomicAdd(empty, 1); return; }
+    double s = 0.0;
+    for (int k = a + lane; k < b; k += 32) s += wts ? wts[members[k]] : 1.0;
+    s = warp_sum(s);
+    for (int k = a + lane; k < b; k += 32) weights[k] = (wts ? wts[members[k]] : 1.0) / s;
+}
+
+extern "C" int frk_polygon_incidence_count(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy,
+                                           int *d_ptoff, int64_t *h_npairs) {
+    FRK_REQUIRE(ctx && P && d_xy && d_ptoff && h_npairs && n > 0 && n < 2147483647LL, "frk_polygon_incidence_count: bad argument");
+    int *cnt = nullptr;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&cnt, n * sizeof(int), ctx->stream));
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, polygon_incidence_kernel<false>, grid, 256, 0, n, d_xy, ld_xy, P->x0, P->y0, P->hx, P->hy, P->nx, P->ny, P->cell_start,
+               P->cand, P->ptr, P->vx, P->vy, P->bbox, cnt, (int *)nullptr, (int *)nullptr, (int *)nullptr);
+    const int rc = frk_exclusive_scan_i32(ctx, cnt, n, d_ptoff, h_npairs);
+    cudaFreeAsync(cnt, ctx->stream);
+    return rc;
+}
+
+extern "C" int frk_polygon_incidence_fill(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy,
+                                          const int *d_ptoff, int64_t npairs, const double *d_wts, int *d_rowptr, int *d_members,
+                                          double *d_weights, int64_t *h_empty) {
+    FRK_REQUIRE(ctx && P && d_xy && d_ptoff && d_rowptr && d_members && d_weights && h_empty && n > 0 && npairs >= 0 && npairs < 2147483647LL,
+                "frk_polygon_incidence_fill: bad argument");
+    const int m = P->npoly;
+    const int64_t np1 = std::max<int64_t>(npairs, 1);
+    int *buf = nullptr;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&buf, (size_t)(3 * np1 + m + 1) * sizeof(int), ctx->stream));
+    int *pid = buf, *pid2 = pid + np1, *pt = pid2 + np1, *pcnt = pt + np1;
+    FRK_CHECK_CUDA(cudaMemsetAsync(pcnt, 0, (size_t)(m + 1) * sizeof(int), ctx->stream));
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16);
+    FRK_LAUNCH(ctx, polygon_incidence_kernel<true>, grid, 256, 0, n, d_xy, ld_xy, P->x0, P->y0, P->hx, P->hy, P->nx, P->ny, P->cell_start,
+               P->cand, P->ptr, P->vx, P->vy, P->bbox, (int *)d_ptoff, pid, pt, pcnt);
+    int rc = 0;
+    void *tmp = nullptr;
+    if (npairs > 0) {      // pairs were emitted in ascending point order: a stable sort by polygon keeps it inside every row
+        int end_bit = 1;
+        while ((1LL << end_bit) < m) end_bit++;
+        size_t tmp_bytes = 0;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, pid, pid2, pt, d_members, (int)npairs, 0, end_bit, ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tmp_bytes, ctx->stream);
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, pid, pid2, pt, d_members, (int)npairs, 0, end_bit, ctx->stream);
+        if (e != cudaSuccess) { frk_set_error("frk_polygon_incidence_fill: sort failed (%s)", cudaGetErrorString(e)); rc = 1; }
+        ctx->launches += 1;
+    }
+    int64_t tot = 0;
+    if (!rc) rc = frk_exclusive_scan_i32(ctx, pcnt, m, d_rowptr, &tot);
+    if (!rc) {
+        cudaMemsetAsync(pcnt + m, 0, sizeof(int), ctx->stream);
+        incidence_weights_kernel<<<(unsigned)cdiv((int64_t)m * 32, 256), 256, 0, ctx->stream>>>(m, d_rowptr, d_members, d_wts, d_weights, pcnt + m);
+        ctx->launches += 1;
+        int e = 0;
+        cudaMemcpyAsync(&e, pcnt + m, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { frk_set_error("frk_polygon_incidence_fill: weights kernel failed"); rc = 1; }
+        *h_empty = e;
+    }
+    if (tmp) cudaFreeAsync(tmp, ctx->stream);
+    cudaFreeAsync(buf, ctx->stream);
+    return rc;
 }

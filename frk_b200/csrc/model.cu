@@ -1530,6 +1530,102 @@ extern "C" int frk_model_predict_areal(frk_model *M, int64_t n, const int *d_row
     return rc;
 }
 
+// ---------------------------------------------------------------------------------
+// predict(newdata = <polygons>): linear combinations C_P of the BAU-level process (R/SREpredict.R:365-419).
+//   mu_P  = C_P mu_BAU
+//   obs_fs or sigma2fs == 0:  var_P = diag(C_P S0 Cov S0' C_P'),  Cov = S_eta                       (:385-391)
+//   else (Case 2, point data): the reference solves the joint system for every polygon (:392-404).  For point-referenced
+//   data xi_k | eta, Z are independent over BAUs with variance v_k = 1/(A_k + Q_k) and Y_k = (1 - a_k) s_k'eta + const + noise_k,
+//   so  var_P = s~_P' Sigma~ s~_P + sum_k c_Pk^2 v_k  with  s~_P = sum_k c_Pk (1 - a_k) s_k  (same closed form as the BAU-level Case 2).
+// ---------------------------------------------------------------------------------
+__global__ void cp_case2_kernel(int64_t mP, const int *__restrict__ rp, const int *__restrict__ mem, const double *__restrict__ w,
+                                const double *__restrict__ A, const double *__restrict__ fs, double sigma2fs, double *__restrict__ w2,
+                                double *__restrict__ extra) {
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= mP) return;
+    double e = 0.0;
+    for (int k = rp[j] + lane; k < rp[j + 1]; k += 32) {
+        const int b = mem[k];
+        const double den = A[b] + 1.0 / (sigma2fs * fs[b]);
+        w2[k] = w[k] * (1.0 - A[b] / den);
+        e += w[k] * w[k] / den;
+    }
+    e = warp_sum(e);
+    if (lane == 0) extra[j] = e;
+}
+
+__global__ void cp_finish_kernel(int64_t mP, const double *__restrict__ q, const double *__restrict__ extra, double *__restrict__ var,
+                                 double *__restrict__ sd) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < mP; j += (int64_t)gridDim.x * blockDim.x) {
+        const double v = q[j] + (extra ? extra[j] : 0.0);
+        var[j] = v;
+        sd[j] = sqrt(v);
+    }
+}
+
+extern "C" int frk_model_predict_polygons(frk_model *M, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
+                                          const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs, const int *d_obs_bau,
+                                          int obs_fs, int64_t mP, const int *d_cp_rowptr, const int *d_cp_members,
+                                          const double *d_cp_weights, int64_t cp_nnz, double *d_mu, double *d_var, double *d_sd) {
+    FRK_REQUIRE(M && d_rowptr0 && bk0 && d_XBAU && d_cp_rowptr && d_cp_members && d_cp_weights && d_mu && d_var && d_sd && n > 0 && mP > 0 &&
+                cp_nnz > 0, "frk_model_predict_polygons: bad argument");
+    FRK_REQUIRE(!M->allreduce, "frk_model_predict_polygons: row-partitioned runs are not supported (polygons may straddle ranks)");
+    frk_ctx *ctx = M->ctx;
+    const int r = M->r;
+    const size_t rr = (size_t)r * r;
+    const bool case1 = obs_fs || M->sigma2fs == 0.0;
+    FRK_REQUIRE(case1 || (d_fs && d_obs_bau), "frk_model_predict_polygons: obs_fs = FALSE needs the BAU fs field and the observation -> BAU map");
+    const int64_t m1 = std::max<int64_t>(M->m, 1);
+    double *buf = nullptr;
+    int *irp = nullptr;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&buf, (size_t)(8 * n + 2 * m1 + 3 * mP + cp_nnz + (case1 ? 0 : 2 * rr + r)) * sizeof(double), ctx->stream));
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&irp, (size_t)(mP + 1) * sizeof(int), ctx->stream));
+    double *xa = buf, *q = xa + n, *smu = q + n, *A = smu + n, *ytil = A + n, *muB = ytil + n, *varB = muB + n, *sdB = varB + n,
+           *tmp = sdB + n, *inv_ve = tmp + m1, *qP = inv_ve + m1, *extra = qP + mP, *spare = extra + mP, *w2 = spare + mP, *Q = w2 + cp_nnz;
+    int *pcol = nullptr;
+    double *pval = nullptr;
+    auto run = [&]() -> int {
+        const double *Sig = M->S_eta, *mue = M->mu_eta;
+        RC(frk_xalpha(ctx, n, M->p, d_XBAU, M->alpha, xa));
+        if (case1) {
+            RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, Sig, mue, q, smu));
+            RC(frk_predict_finalize(ctx, n, 0, M->sigma2fs, q, smu, xa, nullptr, nullptr, nullptr, muB, varB, sdB));
+        } else {
+            double o[4];
+            double *SigT = Q + rr, *mueT = SigT + rr;
+            RC(posterior(M, M->alpha, M->sigma2fs, Q, SigT, mueT, o));
+            Sig = SigT; mue = mueT;
+            RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, Sig, mue, q, smu));
+            FRK_CHECK_CUDA(cudaMemsetAsync(A, 0, 2 * n * sizeof(double), ctx->stream));
+            RC(frk_resid(ctx, M->m, M->p, M->X, M->alpha, M->Z, M->Ve, tmp));
+            RC(frk_scatter_add(ctx, M->m, d_obs_bau, tmp, ytil));
+            RC(frk_recip(ctx, M->m, M->Ve, inv_ve));
+            RC(frk_scatter_add(ctx, M->m, d_obs_bau, inv_ve, A));
+            RC(frk_predict_finalize(ctx, n, 1, M->sigma2fs, q, smu, xa, A, ytil, d_fs, muB, varB, sdB));
+            FRK_LAUNCH(ctx, cp_case2_kernel, (unsigned)cdiv(mP * 32, 256), 256, 0, mP, d_cp_rowptr, d_cp_members, d_cp_weights, A, d_fs,
+                       M->sigma2fs, w2, extra);
+        }
+        RC(frk_areal_aggregate(ctx, mP, d_cp_rowptr, d_cp_members, d_cp_weights, 1, 1, muB, n, d_mu));       // CP %*% BAUs$mu
+        // CPM = CP %*% S0 (Case 2: rows weighted by c (1 - a)), then diag2(CPM %*% Cov, t(CPM))
+        int64_t nnz = 0;
+        RC(frk_csr_aggregate_count(ctx, mP, r, d_cp_rowptr, d_cp_members, d_rowptr0, d_col0, irp, &nnz));
+        FRK_CHECK_CUDA(cudaMallocAsync((void **)&pcol, (size_t)std::max<int64_t>(nnz, 1) * sizeof(int), ctx->stream));
+        FRK_CHECK_CUDA(cudaMallocAsync((void **)&pval, (size_t)std::max<int64_t>(nnz, 1) * sizeof(double), ctx->stream));
+        RC(frk_csr_aggregate_fill(ctx, mP, r, d_cp_rowptr, d_cp_members, case1 ? d_cp_weights : w2, d_rowptr0, d_col0, d_val0, irp, pcol, pval));
+        RC(frk_quadform_spmv(ctx, mP, r, irp, pcol, pval, Sig, nullptr, qP, nullptr));
+        FRK_LAUNCH(ctx, cp_finish_kernel, (unsigned)std::min<int64_t>(cdiv(mP, 256), 4096), 256, 0, mP, qP, case1 ? (const double *)nullptr : extra,
+                   d_var, d_sd);
+        return 0;
+    };
+    const int rc = run();
+    if (pcol) cudaFreeAsync(pcol, ctx->stream);
+    if (pval) cudaFreeAsync(pval, ctx->stream);
+    cudaFreeAsync(irp, ctx->stream);
+    cudaFreeAsync(buf, ctx->stream);
+    return rc;
+}
+
 // ---- the host optimisers, exported so that the CPU test-suite can pin them without a GPU --------------------
 extern "C" int frk_optim_nelder_mead(frk_objective_fn fn, void *user, int n, const double *par, int maxit, double reltol,
                                      double *x_out, double *f_out, int *count_out, int *fail_out) {

@@ -345,7 +345,50 @@ def SRE_fit(mdl: SREModel, n_EM: int = 100, tol: float = 0.01, method: str = "EM
 # predict
 # ---------------------------------------------------------------------------------------
 
-def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True):
+def _predict_polygons(mdl: SREModel, newdata, obs_fs: bool):
+    """predict(newdata = SpatialPolygons), R/SREpredict.R:119-128,365-419: C_P over the BAU centroids, then frk_model_predict_polygons."""
+    dev = mdl.dev
+    if dev.world > 1:
+        raise FRKError("prediction over polygons on a row-partitioned run: polygons may straddle ranks -- not on the device path yet")
+    if isinstance(mdl.basis, TensorP_Basis) or isinstance(mdl.BAUs, STBAUs):
+        raise FRKError("prediction over polygons in space-time is not on the device path yet")
+    if getattr(mdl, "areal", False) and not obs_fs and mdl.sigma2fshat > 0:
+        raise FRKError("prediction over polygons with obs_fs = FALSE for areal DATA needs the covariances between the fine-scale terms "
+                       "of a support (R/SREpredict.R:392-404): not on the device path yet; use obs_fs = TRUE")
+    N = mdl.N
+    if isinstance(mdl.BAUs, GridBAUs):
+        d_xg, d_yg = dev.upload(mdl.BAUs.xgrid), dev.upload(mdl.BAUs.ygrid)
+        d_cen = dev.empty(2 * N)
+        call("frk_grid_centroids", dev.ctx, 0, N, mdl.BAUs.nx, dev.ptr(d_xg), dev.ptr(d_yg), dev.ptr(d_cen))
+    else:
+        d_cen = dev.upload(mdl.BAUs.centroids()[:, :2])
+    mP = len(newdata)
+    hp = vp()
+    call("frk_polygons_create", dev.ctx, mP, vp(newdata.ptr.ctypes.data), vp(newdata.vx.ctypes.data), vp(newdata.vy.ctypes.data), C.byref(hp))
+    try:
+        ptoff = dev.empty(N + 1, "i4")
+        npairs = c_i64(0)
+        call("frk_polygon_incidence_count", dev.ctx, hp, N, dev.ptr(d_cen), N, dev.ptr(ptoff), C.byref(npairs))
+        cp_rowptr = dev.empty(mP + 1, "i4")
+        cp_mem = dev.empty(max(npairs.value, 1), "i4")
+        cp_w = dev.empty(max(npairs.value, 1))
+        empty = c_i64(0)
+        call("frk_polygon_incidence_fill", dev.ctx, hp, N, dev.ptr(d_cen), N, dev.ptr(ptoff), npairs.value, vp(None), dev.ptr(cp_rowptr),
+             dev.ptr(cp_mem), dev.ptr(cp_w), C.byref(empty))
+    finally:
+        _lib.lib.frk_polygons_destroy(hp)
+    if empty.value or npairs.value == 0:
+        raise FRKError(f"{empty.value} prediction polygons contain no BAU centroid")
+    mu, var, sd = (dev.empty(mP) for _ in range(3))
+    call("frk_model_predict_polygons", mdl.handle, N, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val), mdl.S0.buckets(dev),
+         dev.ptr(mdl.X_BAU), dev.ptr(mdl.fs_BAU), dev.ptr(mdl.obs_bau), 1 if obs_fs else 0, mP, dev.ptr(cp_rowptr), dev.ptr(cp_mem),
+         dev.ptr(cp_w), npairs.value, dev.ptr(mu), dev.ptr(var), dev.ptr(sd))
+    mdl.d2h_bytes += 3 * 8 * mP
+    return dict(mu=dev.download(mu, mP), var=dev.download(var, mP), sd=dev.download(sd, mP),
+                C_P=(cp_rowptr, cp_mem, cp_w, int(npairs.value)))
+
+
+def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True, newdata=None):
     """predict(SRE, obs_fs) at the BAUs (newdata = NULL, covariances = FALSE): .SRE.predict_EM,
     R/SREpredict.R:243-375 with .batch_compute_var (R/SREutils.R:245-305) -- one ``frk_model_predict`` call.
 
@@ -353,6 +396,10 @@ def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True):
     obs_fs = FALSE and sigma2fs > 0: the joint (eta, xi) solve at the final parameters; for point data its
     diagonal reduces to one more E-step plus the same sparse quadratic form.
     Returns dict(mu, var, sd) for this rank's BAU rows [lo, hi) (host arrays, or device tensors)."""
+    if newdata is not None:
+        if not isinstance(newdata, SpatialPolygonsDataFrame):
+            raise FRKError("newdata must be a SpatialPolygonsDataFrame (prediction polygons); BAU-level prediction is newdata = None")
+        return _predict_polygons(mdl, newdata, obs_fs)
     dev = mdl.dev
     nloc = mdl.hi - mdl.lo
     mu, var, sd = (dev.empty(max(nloc, 1)) for _ in range(3))

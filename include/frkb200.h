@@ -178,6 +178,14 @@ int frk_areal_aggregate(frk_ctx *ctx, int64_t m, const int *d_cz_rowptr, const i
  * where a BAU shared by two observations would make Vfs non-diagonal                                                          */
 int frk_polygon_lookup_count(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy, int *d_first,
                              int64_t *h_multi);
+/* General incidence for (possibly overlapping) polygons -- the prediction polygons' C_P (BuildC, R/geometryfns.R:1572-1616;
+ * normalised as in R/SREpredict.R:119-128): every polygon gets ALL the points it contains.  _count: d_ptoff[n+1] = exclusive scan of
+ * the number of containing polygons per point, *h_npairs the total; _fill: CSR over the polygons (d_rowptr[npoly+1], d_members and
+ * d_weights[npairs], points ascending within a polygon, weights d_wts (NULL = 1) / row sum), *h_empty = polygons without a point. */
+int frk_polygon_incidence_count(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy, int *d_ptoff,
+                                int64_t *h_npairs);
+int frk_polygon_incidence_fill(frk_ctx *ctx, const frk_polygons *P, int64_t n, const double *d_xy, int64_t ld_xy, const int *d_ptoff,
+                               int64_t npairs, const double *d_wts, int *d_rowptr, int *d_members, double *d_weights, int64_t *h_empty);
 /* group_by(BAU) %>% summarise_all(mean): R/geometryfns.R:1286-1302.  d_vals: n x ncols
  * column-major (ld n).  Outputs (capacity n rows): d_obs_bau[m] ascending BAU rows,
  * d_means m x ncols column-major with leading dimension n, d_counts[m].  Returns m.
@@ -401,6 +409,13 @@ int frk_model_predict(frk_model *mdl, int64_t n, const int *d_rowptr0, const int
 int frk_model_predict_areal(frk_model *mdl, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
                             const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs, const int *d_cz_rowptr,
                             const int *d_cz_members, const double *d_cz_weights, double *d_mu, double *d_var, double *d_sd);
+/* predict(newdata = <polygons>) (R/SREpredict.R:365-419): C_P (mP x n CSR, rows normalised: frk_polygon_incidence_*) applied to the
+ * BAU-level prediction.  mu = C_P mu_BAU; var = diag(C_P S0 Cov S0' C_P') for obs_fs != 0 or sigma2fs == 0; for obs_fs == 0 with
+ * point-referenced data the joint-solve variance in closed form (rows of S0 weighted by c (1 - a_k), plus sum c^2 / (A_k + Q_k)). */
+int frk_model_predict_polygons(frk_model *mdl, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
+                               const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs, const int *d_obs_bau, int obs_fs,
+                               int64_t mP, const int *d_cp_rowptr, const int *d_cp_members, const double *d_cp_weights, int64_t cp_nnz,
+                               double *d_mu, double *d_var, double *d_sd);
 /* stats::optim(method = "Nelder-Mead", control = list(maxit, reltol)) and stats::uniroot (default tol) as used by
  * the M-step (R/SREfit.R:618-621, :386-388); exported so that the iterate path can be tested on its own.       */
 int frk_optim_nelder_mead(frk_objective_fn fn, void *user, int n, const double *par, int maxit,

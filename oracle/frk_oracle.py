@@ -1285,3 +1285,31 @@ def predict_general(M: SREModel):
     var = (np.sum((S0 @ Cov[:r, :r]) * S0, axis=1) + np.diag(Cov)[r:] + 2 * np.sum(Cov[r:, :r] * S0, axis=1))
     mu = M.X_BAU @ M.alphahat + PI @ x_mean
     return mu, var, np.sqrt(var)
+
+
+def predict_polygons(M: SREModel, CP: sp.spmatrix, obs_fs: bool = False):
+    """predict(newdata = <polygons>), R/SREpredict.R:365-419: CP = row-normalised incidence of the prediction polygons over the BAUs.
+    mu = CP %*% mu_BAU; obs_fs | sigma2fs == 0: var = diag2(CPM %*% Cov, t(CPM)) with CPM = CP %*% S0, Cov = S_eta (:385-391);
+    otherwise CPM = CP %*% [S0 I] against the full joint covariance Qx^-1 (:392-404) -- literal dense solve, toy sizes only."""
+    CP = sp.csr_matrix(CP)
+    s2 = M.sigma2fshat
+    if obs_fs or s2 == 0:
+        mu_b = M.X_BAU @ M.alphahat + M.S0 @ M.mu_eta
+        CPM = sp.csr_matrix(CP @ M.S0)
+        var = np.asarray(CPM.multiply(CPM @ M.S_eta).sum(axis=1)).ravel()
+        return CP @ mu_b, var, np.sqrt(var)
+    S0 = np.asarray(M.S0.todense())
+    N, r = S0.shape
+    Cm = getattr(M, "Cmat", None)
+    C = np.asarray(BuildC(M.obs_bau, N).todense()) if Cm is None else np.asarray(Cm.todense())
+    LAMBDAinv = np.zeros((r + N, r + N))
+    LAMBDAinv[:r, :r] = M.Khat_inv
+    LAMBDAinv[r:, r:] = np.diag(1.0 / (s2 * M.fs_BAU))
+    PI = np.hstack([S0, np.eye(N)])
+    Qx = PI.T @ (C.T @ np.diag(1.0 / M.Ve) @ C) @ PI + LAMBDAinv
+    ybar = PI.T @ C.T @ ((M.Z - M.X @ M.alphahat) / M.Ve)
+    Cov = np.linalg.inv(Qx)
+    mu_b = M.X_BAU @ M.alphahat + PI @ (Cov @ ybar)
+    CPM = np.asarray(CP.todense()) @ PI
+    var = np.sum((CPM @ Cov) * CPM, axis=1)
+    return CP @ mu_b, var, np.sqrt(var)

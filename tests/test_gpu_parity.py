@@ -843,3 +843,46 @@ def test_deterministic_mode_is_bit_reproducible(dev):
         np.testing.assert_allclose(a_d, a_a, rtol=1e-12, atol=1e-12 * abs(a_a).max())
     finally:
         dev.set_deterministic(False)
+
+
+def _pred_polygons(F, squares):
+    ptr, vx, vy = [0], [], []
+    for x0, y0, w, h in squares:
+        vx += [x0, x0 + w, x0 + w, x0, x0]
+        vy += [y0, y0, y0 + h, y0 + h, y0]
+        ptr.append(len(vx))
+    return F.SpatialPolygonsDataFrame(np.array(ptr), np.array(vx), np.array(vy), {})
+
+
+@pytest.mark.parametrize("K_type", ["unstructured", "block-exponential"])
+def test_predict_over_polygons(dev, K_type):
+    """predict(newdata = <polygons>), R/SREpredict.R:365-419, with OVERLAPPING prediction polygons (C_P rows are independent):
+    incidence C_P exact against the restated BuildC; mu = C_P mu_BAU and var = diag(C_P S0 S_eta S0' C_P') for obs_fs = TRUE; for
+    obs_fs = FALSE the device's closed form (rows weighted by c (1 - a_k) + sum c^2 / (A_k + Q_k)) against the LITERAL dense joint
+    solve with C_P [S0 I] (toy size)."""
+    import frk_b200 as F
+    Mo, Mg = _setup_plane(F, m=300, nres=1, cellsize=0.1, K_type=K_type)
+    O.SRE_fit(Mo, n_EM=3, tol=0.0)
+    F.SRE_fit(Mg, n_EM=3, tol=0.0)
+    assert Mg.sigma2fshat > 0
+    nd = _pred_polygons(F, [(0.03, 0.03, 0.5, 0.5), (0.33, 0.23, 0.6, 0.4), (0.0, 0.0, 1.0, 1.0), (0.61, 0.62, 0.21, 0.11), (-0.15, 0.4, 0.3, 0.3)])
+    cen = Mg.BAUs.centroids()
+    i, j, x = O.BuildC_polygons(nd.ptr, nd.vx, nd.vy, cen)
+    CP = sp.csr_matrix((x, (i, j)), shape=(len(nd), len(cen)))
+    CP = sp.csr_matrix(sp.diags(1.0 / np.asarray(CP.sum(axis=1)).ravel()) @ CP)
+    CP.sort_indices()
+    for obs_fs in (True, False):
+        pg = F.predict(Mg, obs_fs=obs_fs, newdata=nd)
+        rp, mem, w, nnz = pg["C_P"]
+        assert nnz == CP.nnz and np.array_equal(dev.download(rp, len(nd) + 1), CP.indptr)
+        assert np.array_equal(dev.download(mem, nnz), CP.indices)
+        np.testing.assert_allclose(dev.download(w, nnz), CP.data, rtol=1e-15)
+        po = O.predict_polygons(Mo, CP, obs_fs=obs_fs)
+        np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(pg["var"], po[1], rtol=1e-6)
+        np.testing.assert_allclose(pg["sd"], np.sqrt(po[1]), rtol=1e-6)
+    # averaging over a polygon reduces the variance below the mean BAU-level variance (positive correlation aside, never above the max)
+    pb = F.predict(Mg, obs_fs=False)
+    assert np.all(pg["var"] <= pb["var"].max() * (1 + 1e-12))
+    with pytest.raises(F.FRKError, match="no BAU centroid"):
+        F.predict(Mg, newdata=_pred_polygons(F, [(5.0, 5.0, 0.1, 0.1)]))
