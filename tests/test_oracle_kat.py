@@ -287,3 +287,36 @@ def test_auto_basis_prune_rule():
         L = pr.loc[pr.res == rr]
         D = O.distR(L, L); np.fill_diagonal(D, np.inf)
         np.testing.assert_array_equal(pr.scale[pr.res == rr], 1.5 * (D.min(axis=1) * 1.25))
+
+
+def test_polygon_prediction_closed_form_equals_joint_solve():
+    """predict(newdata = <polygons>, obs_fs = FALSE) for point data: the closed form the device implements
+    (frk_model_predict_polygons: rows of S0 weighted by c (1 - a_k), plus sum c^2 / (A_k + Q_k)) against the literal
+    C_P [S0 I] Qx^-1 [S0 I]' C_P' of R/SREpredict.R:392-404; overlapping polygons."""
+    import scipy.sparse as sp
+    from cases import readme_points
+    xy, z = readme_points(300, 1)
+    std = np.full(300, 0.5)
+    ob = O.auto_basis(O.plane(), xy, regular=1, nres=1)
+    baus = O.auto_BAUs_plane(xy, cellsize=0.1)
+    uo, means, _ = O.bin_mean(O.points_to_BAUs(xy, baus), np.column_stack([z, std]))
+    cen = baus.centroids()
+    M = O.SRE(ob, cen, np.ones(baus.n), uo, means[:, 0], means[:, 1], K_type="unstructured")
+    O.SRE_fit(M, n_EM=3, tol=0.0)
+    s2 = M.sigma2fshat
+    assert s2 > 0
+    ptr, vx, vy = [0], [], []
+    for x0, y0, w, h in [(0.03, 0.03, 0.5, 0.5), (0.33, 0.23, 0.6, 0.4), (0.0, 0.0, 1.0, 1.0)]:
+        vx += [x0, x0 + w, x0 + w, x0, x0]; vy += [y0, y0, y0 + h, y0 + h, y0]; ptr.append(len(vx))
+    i, j, x = O.BuildC_polygons(np.array(ptr), np.array(vx), np.array(vy), cen)
+    CP = sp.csr_matrix((x, (i, j)), shape=(3, len(cen)))
+    CP = sp.csr_matrix(sp.diags(1.0 / np.asarray(CP.sum(axis=1)).ravel()) @ CP)
+    mu, var, _ = O.predict_polygons(M, CP, obs_fs=False)
+    N = len(cen)
+    A = np.zeros(N); np.add.at(A, M.obs_bau, 1.0 / M.Ve)
+    Q = 1.0 / (s2 * M.fs_BAU)
+    Sig = O.chol2inv(O.chol_upper(O._gram(M.S, 1.0 / (s2 * M.Vfs + M.Ve)) + M.Khat_inv))
+    CPM = sp.csr_matrix(sp.csr_matrix(CP.multiply(1.0 - A / (A + Q))) @ M.S0)
+    var2 = np.asarray(CPM.multiply(CPM @ Sig).sum(axis=1)).ravel() + np.asarray(CP.multiply(CP) @ (1.0 / (A + Q))).ravel()
+    np.testing.assert_allclose(var2, var, rtol=1e-10)
+    np.testing.assert_allclose(CP @ O.predict(M, obs_fs=False)[0], mu, rtol=1e-10, atol=1e-12)
