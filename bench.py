@@ -32,7 +32,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "EM iters/sec (N=1e6 obs, r=3276) [+ predicted BAUs/sec over 1e7 BAUs in 'predict']"
+# BASELINE.json's metric; `value` is the EM iterations/s half (r = 3276), the predicted-BAUs/s half (1e7 BAUs) is in `predict`
+METRIC = "EM iters/sec and predicted BAUs/sec at N=1e6, r~4k, 1/2/4/8 B200 vs host R (value = EM iters/sec; BAUs/sec in 'predict')"
 
 
 def parse():
