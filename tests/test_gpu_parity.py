@@ -886,3 +886,35 @@ def test_predict_over_polygons(dev, K_type):
     assert np.all(pg["var"] <= pb["var"].max() * (1 + 1e-12))
     with pytest.raises(F.FRKError, match="no BAU centroid"):
         F.predict(Mg, newdata=_pred_polygons(F, [(5.0, 5.0, 0.1, 0.1)]))
+
+
+@pytest.mark.parametrize("K_type", ["unstructured", "block-exponential"])
+def test_config5_scaled_sphere_matern32(dev, K_type):
+    """BASELINE config 5, scaled down: points uniform on the sphere, Matern-3/2 basis (NOT compactly supported: every row of S0 is
+    dense, so the Gram / quadratic-form kernels run their direct per-row paths), two ISEA3H-like resolutions, a 5-degree lon/lat
+    grid of BAUs, EM + prediction at every BAU against the oracle."""
+    import frk_b200 as F
+    ll, z = sphere_points(3000, seed=23)
+    iso = pseudo_isea3h()
+    ob = O.auto_basis(O.sphere(), ll, nres=2, type="Matern32", isea3h=iso, isea3h_lo=1)
+    obaus = O.GridBAUs(np.arange(-177.5, 180.0, 5.0), np.arange(-87.5, 90.0, 5.0), np.array([5.0, 5.0]))
+    bau = O.points_to_BAUs(ll, obaus)
+    std = np.full(len(z), 0.3)
+    uo, means, _ = O.bin_mean(bau, np.column_stack([z, std]))
+    Mo = O.SRE(ob, obaus.centroids(), np.ones(obaus.n), uo, means[:, 0], means[:, 1], K_type=K_type)
+    gb = F.GridBAUs(obaus.xgrid.copy(), obaus.ygrid.copy(), np.array([5.0, 5.0]))
+    gb["fs"] = 1.0
+    Mg = F.SRE("z ~ 1", F.SpatialPointsDataFrame(ll, {"z": z, "std": std}), _mk_basis(F, ob), gb, est_error=False, K_type=K_type)
+    assert Mg.r == ob.n == 124 and np.array_equal(dev.download(Mg.obs_bau, Mg.m), uo)
+    Sg = Mg.S.to_scipy(dev)
+    assert Sg.nnz == Mg.m * Mg.r                                   # dense rows
+    np.testing.assert_allclose(Sg.toarray(), Mo.S.toarray(), rtol=1e-9, atol=1e-14)
+    O.SRE_fit(Mo, n_EM=4, tol=0.0)
+    F.SRE_fit(Mg, n_EM=4, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-7, atol=1e-12)
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pg = F.predict(Mg, obs_fs=obs_fs)
+        np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-8 * abs(po[0]).max())
+        np.testing.assert_allclose(pg["var"], po[1], rtol=1e-6)
