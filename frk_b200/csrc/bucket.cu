@@ -223,6 +223,8 @@ struct frk_rowbuckets {
     int *perm = nullptr, *bptr = nullptr, *ucol = nullptr, *nU = nullptr;
     unsigned char *lid = nullptr;
     // ELL tiles
+    bool dense = false;            // every row holds all ncols columns (non-compact basis functions): val IS the dense matrix, row-major;
+                                   // the Gram and the quadratic form are then plain GEMMs and no buckets are built
     int T = 0;
     int *btile = nullptr;          // [ncols+1] first tile of every bucket
     int *tile_K = nullptr;         // [T] entries per row in the tile; -1: a row is longer than KMAX (direct path)
@@ -310,6 +312,11 @@ extern "C" int frk_rowbuckets_create(frk_ctx *ctx, int64_t n, int ncols, const i
     auto fail = [&](int rc) { frk_rowbuckets_destroy(B); return rc; };
     int nnz = 0;
     if (int rc = frk_d2h(ctx, &nnz, d_rowptr + n, sizeof(int))) return fail(rc);
+    if (n > 0 && ncols > UMAX && (int64_t)nnz == n * (int64_t)ncols) {   // rows have ascending unique columns < ncols: all of them present
+        B->dense = true;
+        *out = B;
+        return 0;
+    }
     if (rb_alloc(B, &B->perm, (size_t)std::max<int64_t>(n, 1)) || rb_alloc(B, &B->bptr, (size_t)ncols + 1) ||
         rb_alloc(B, &B->ucol, (size_t)ncols * UMAX) || rb_alloc(B, &B->nU, (size_t)ncols) || rb_alloc(B, &B->lid, (size_t)std::max(nnz, 1)) ||
         rb_alloc(B, &B->btile, (size_t)ncols + 1))
@@ -561,17 +568,115 @@ static int gram_prepare_ordered(frk_ctx *ctx, const frk_rowbuckets *bk, int r) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------
+// Dense rows (basis functions without compact support: Gaussian, exponential, Matern): the CSR values are the n x r matrix in
+// row-major order, i.e. A = S' (r x n, column-major, ld r).  The Gram is then  A diag(w) A'  and the quadratic forms are the
+// column dots of A with M A -- GEMMs on the fp64 tensor path instead of r^2/2 atomics per row.  Columns are processed in chunks
+// so that the scaled copy / the product stays below ~512 MB.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_weights_kernel(int64_t c0, int64_t nc, int r, int64_t m, const double *__restrict__ A,
+                                                            const double *__restrict__ z, const double *__restrict__ X, int p, AlphaB alpha,
+                                                            const double *__restrict__ ve, const double *__restrict__ vfs, double sigma2fs,
+                                                            double *__restrict__ B, double *__restrict__ wr, double *__restrict__ part) {
+    // one warp per column (= row of S) of the chunk: B[:, i] = w_i A[:, i], wr_i = w_i rho_i; per-block partials of rho^2 w and log d
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ double sq[8], sl[8];
+    double q = 0.0, l = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + wid; i < nc; i += (int64_t)gridDim.x * 8) {
+        const int64_t row = c0 + i;
+        double rho = z[row];
+        for (int k = 0; k < p; k++) rho -= X[row + (int64_t)k * m] * alpha.a[k];
+        const double d = sigma2fs * vfs[row] + ve[row], w = 1.0 / d;
+        const double *a = A + (size_t)row * r;
+        double *b = B + (size_t)i * r;
+        for (int c = lane; c < r; c += 32) b[c] = w * a[c];
+        if (lane == 0) { wr[i] = w * rho; q += rho * rho * w; l += log(d); }
+    }
+    if (lane == 0) { sq[wid] = q; sl[wid] = l; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < 8; w++) { a += sq[w]; b += sl[w]; }
+        part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+    }
+}
+
+__global__ void dense_scalars_kernel(int nblocks, const double *__restrict__ part, double *__restrict__ out2) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int k = 0; k < nblocks; k++) { a += part[2 * k]; b += part[2 * k + 1]; }     // fixed order
+        out2[0] += a; out2[1] += b;
+    }
+}
+
+static int gram_rhs_dense(frk_ctx *ctx, int64_t m, int r, const double *A, const double *d_z, const double *d_X, int p, const AlphaB &al,
+                          const double *d_ve, const double *d_vfs, double sigma2fs, double *d_acc) {
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t)(512.0 * 1024 * 1024 / (8.0 * r))));
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(chunk, 8), (int64_t)ctx->sm_count * 8);
+    double *B = nullptr;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&B, ((size_t)chunk * r + chunk + 2 * (size_t)grid) * sizeof(double), ctx->stream));
+    double *wr = B + (size_t)chunk * r, *part = wr + chunk;
+    double *G = d_acc, *rhs = d_acc + (size_t)r * r;
+    int rc = 0;
+    for (int64_t c0 = 0; c0 < m && !rc; c0 += chunk) {
+        const int64_t nc = std::min(chunk, m - c0);
+        do {
+            FRK_LAUNCH(ctx, dense_weights_kernel, grid, 256, 0, c0, nc, r, m, A, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, B, wr, part);
+            FRK_LAUNCH(ctx, dense_scalars_kernel, 1, 32, 0, (int)grid, part, rhs + r);
+        } while (0);
+        // G += A_chunk B_chunk'  (r x r, K = nc);  rhs += A_chunk wr
+        rc = frk_dgemm_nt(ctx, r, r, (int)nc, 1.0, A + (size_t)c0 * r, r, B, r, 1.0, G, r);
+        if (!rc) rc = frk_dgemm_nt(ctx, r, 1, (int)nc, 1.0, A + (size_t)c0 * r, r, wr, 1, 1.0, rhs, r);
+    }
+    cudaFreeAsync(B, ctx->stream);
+    return rc;
+}
+
+__global__ void __launch_bounds__(256) dense_coldot_kernel(int64_t nc, int r, const double *__restrict__ A, const double *__restrict__ Y,
+                                                           const double *__restrict__ mu, double *__restrict__ q, double *__restrict__ t) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nc; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const double *a = A + (size_t)i * r;
+        double sq = 0.0, st = 0.0;
+        if (Y) { const double *y = Y + (size_t)i * r; for (int c = lane; c < r; c += 32) sq += a[c] * y[c]; }
+        if (mu) for (int c = lane; c < r; c += 32) st += a[c] * __ldg(mu + c);
+        sq = warp_sum(sq); st = warp_sum(st);
+        if (lane == 0) { if (q && Y) q[i] = sq; if (t && mu) t[i] = st; }
+    }
+}
+
+static int quadform_dense(frk_ctx *ctx, int64_t n, int r, const double *A, const double *d_M, const double *d_mu, double *d_q, double *d_t) {
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(512.0 * 1024 * 1024 / (8.0 * r))));
+    double *Y = nullptr;
+    if (d_M && d_q) FRK_CHECK_CUDA(cudaMallocAsync((void **)&Y, (size_t)chunk * r * sizeof(double), ctx->stream));
+    int rc = 0;
+    for (int64_t c0 = 0; c0 < n && !rc; c0 += chunk) {
+        const int64_t nc = std::min(chunk, n - c0);
+        const double *Ac = A + (size_t)c0 * r;
+        // Y = M A_chunk  (M symmetric r x r; A_chunk is K x N with k contiguous)
+        if (Y) rc = frk_dgemm(ctx, 0, 1, r, (int)nc, r, 1.0, d_M, r, Ac, r, 0.0, Y, r);
+        if (rc) break;
+        const unsigned grid = (unsigned)std::min<int64_t>(cdiv(nc * 32, 256), (int64_t)ctx->sm_count * 16);
+        do {
+            FRK_LAUNCH(ctx, dense_coldot_kernel, grid, 256, 0, nc, r, Ac, (const double *)Y, d_mu, d_q ? d_q + c0 : nullptr, d_t ? d_t + c0 : nullptr);
+        } while (0);
+    }
+    if (Y) cudaFreeAsync(Y, ctx->stream);
+    return rc;
+}
+
 extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int *d_col, const double *d_val,
                                      const frk_rowbuckets *bk, const double *d_z, const double *d_X, int p, const double *h_alpha,
                                      const double *d_ve, const double *d_vfs, double sigma2fs, double *d_acc) {
     FRK_REQUIRE(ctx && d_rowptr && d_acc && bk, "frk_gram_rhs_bucketed: NULL argument");
     FRK_REQUIRE(bk->n == m && bk->ncols == r, "frk_gram_rhs_bucketed: the row buckets belong to a %lld x %d matrix", (long long)bk->n, bk->ncols);
-    const int *d_perm = bk->perm, *d_bptr = bk->bptr, *d_ucol = bk->ucol, *d_nU = bk->nU;
+    const int *d_perm = bk->perm, *d_bptr = bk->bptr, *d_ucol = bk->ucol, *d_nU = bk->nU;       // (all NULL for a dense matrix)
     const unsigned char *d_lid = bk->lid;
     FRK_REQUIRE(p >= 0 && p <= MAXP_B, "frk_gram_rhs_bucketed: %d fixed effects; the device path handles at most %d", p, MAXP_B);
     if (m == 0) return 0;
     AlphaB al{};
     for (int q = 0; q < p; q++) al.a[q] = h_alpha[q];
+    if (bk->dense) return gram_rhs_dense(ctx, m, r, d_val, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, d_acc);
     unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 8);
     if (!ctx->deterministic) {
         FRK_LAUNCH(ctx, gram_bucket_kernel, grid, GR_T, 0, r, d_bptr, d_perm, d_ucol, d_nU, d_lid, m, r, d_rowptr, d_col, d_val, d_z, d_X,
@@ -797,6 +902,7 @@ extern "C" int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const 
     FRK_REQUIRE(ctx && d_rowptr && bk, "frk_quadform_spmv_bucketed: NULL argument");
     FRK_REQUIRE(bk->n == n && bk->ncols == r, "frk_quadform_spmv_bucketed: the row buckets belong to a %lld x %d matrix", (long long)bk->n, bk->ncols);
     if (n == 0) return 0;
+    if (bk->dense) return quadform_dense(ctx, n, r, d_val, d_M, d_mu, d_q, d_t);
     static bool attr = false;
     if (!attr) {
         FRK_CHECK_CUDA(cudaFuncSetAttribute(quadform_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QuadDmmaSmem)));
