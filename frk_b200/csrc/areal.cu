@@ -50,21 +50,24 @@ extern "C" int frk_areal_incidence(frk_ctx *ctx, int64_t N, const int *d_group, 
     size_t tmp_bytes = 0;
     int end_bit = 1;
     while ((1LL << end_bit) <= m) end_bit++;
-    FRK_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, idx, d_members, (int)N, 0, end_bit, ctx->stream));
     void *tmp = nullptr;
-    FRK_CHECK_CUDA(cudaMallocAsync(&tmp, tmp_bytes, ctx->stream));
-    FRK_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, idx, d_members, (int)N, 0, end_bit, ctx->stream));
+    int rc = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, idx, d_members, (int)N, 0, end_bit, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tmp_bytes, ctx->stream);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, idx, d_members, (int)N, 0, end_bit, ctx->stream);
+    if (e != cudaSuccess) { frk_set_error("frk_areal_incidence: sort failed (%s)", cudaGetErrorString(e)); rc = 1; }
     ctx->launches += 1;
-    int rc = frk_exclusive_scan_i32(ctx, cnt, m, d_rowptr, h_nmem);
+    if (!rc) rc = frk_exclusive_scan_i32(ctx, cnt, m, d_rowptr, h_nmem);
     if (!rc) {
-        FRK_CHECK_CUDA(cudaMemsetAsync(cnt + m, 0, sizeof(int), ctx->stream));
-        FRK_LAUNCH(ctx, areal_weights_kernel, (unsigned)cdiv(m * 32, 256), 256, 0, m, d_rowptr, d_members, d_wts, d_weights, cnt + m);
-        int e = 0;
-        FRK_CHECK_CUDA(cudaMemcpyAsync(&e, cnt + m, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-        *h_empty = e;
+        cudaMemsetAsync(cnt + m, 0, sizeof(int), ctx->stream);
+        areal_weights_kernel<<<(unsigned)cdiv(m * 32, 256), 256, 0, ctx->stream>>>(m, d_rowptr, d_members, d_wts, d_weights, cnt + m);
+        ctx->launches += 1;
+        int ne = 0;
+        cudaMemcpyAsync(&ne, cnt + m, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { frk_set_error("frk_areal_incidence: weights kernel failed"); rc = 1; }
+        *h_empty = ne;
     }
-    cudaFreeAsync(tmp, ctx->stream);
+    if (tmp) cudaFreeAsync(tmp, ctx->stream);
     cudaFreeAsync(key, ctx->stream);
     return rc;
 }

@@ -195,11 +195,15 @@ extern "C" int frk_csr_bucket_rows(frk_ctx *ctx, int64_t n, const int *d_rowptr,
         while ((1LL << end_bit) < ncols) end_bit++;
         size_t tmp_bytes = 0;
         void *tmp = nullptr;
-        FRK_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, idx, d_perm, (int)n, 0, end_bit, ctx->stream));
-        FRK_CHECK_CUDA(cudaMallocAsync(&tmp, tmp_bytes, ctx->stream));
-        const cudaError_t es = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, idx, d_perm, (int)n, 0, end_bit, ctx->stream);
-        cudaFreeAsync(tmp, ctx->stream);
-        FRK_CHECK_CUDA(es);
+        cudaError_t es = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, idx, d_perm, (int)n, 0, end_bit, ctx->stream);
+        if (es == cudaSuccess) es = cudaMallocAsync(&tmp, tmp_bytes, ctx->stream);
+        if (es == cudaSuccess) es = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, idx, d_perm, (int)n, 0, end_bit, ctx->stream);
+        if (tmp) cudaFreeAsync(tmp, ctx->stream);
+        if (es != cudaSuccess) {
+            cudaFreeAsync(key, ctx->stream);
+            frk_set_error("frk_csr_bucket_rows: sort failed (%s)", cudaGetErrorString(es));
+            return 1;
+        }
         ctx->launches += 1;
         FRK_LAUNCH(ctx, bucket_union_kernel, (unsigned)std::min<int64_t>(ncols, (int64_t)ctx->sm_count * 8), BU_T, 0, ncols, d_bptr,
                    d_perm, d_rowptr, d_col, d_ucol, d_nU, d_lid);
