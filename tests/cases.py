@@ -32,3 +32,24 @@ def pseudo_isea3h(seed=7):
         lon = (np.degrees(k * np.pi * (3 - np.sqrt(5))) + 180.0) % 360.0 - 180.0
         out[res] = np.column_stack([lon, lat])
     return out
+
+
+def areal_tiles(tile=0.1, noise=0.1, seed=51):
+    """Square supports tiling the unit square (edges kept off the BAU centroids), one tile row left out; each observes the average of a
+    smooth field plus noise.  Returns (ptr, vx, vy, z, std)."""
+    rng = np.random.default_rng(seed)
+    ptr, vx, vy, z = [0], [], [], []
+    nt = int(round(1.0 / tile))
+    for iy in range(nt):
+        for ix in range(nt):
+            if iy == nt // 2 - 1:
+                continue
+            x0, y0 = tile * ix + 0.003, tile * iy + 0.003
+            vx += [x0, x0 + tile, x0 + tile, x0, x0]
+            vy += [y0, y0, y0 + tile, y0 + tile, y0]
+            ptr.append(len(vx))
+            xm, ym = x0 + tile / 2, y0 + tile / 2
+            z.append(np.sin(6 * xm) + np.cos(5 * ym) + 0.5 * (xm + ym) + noise * rng.standard_normal())
+    m = len(z)
+    std = 0.1 + 0.05 * rng.uniform(size=m)
+    return np.array(ptr), np.array(vx), np.array(vy), np.array(z), std

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from cases import pseudo_isea3h, readme_points, sphere_points
+from cases import areal_tiles, pseudo_isea3h, readme_points, sphere_points
 from oracle import frk_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -707,26 +707,13 @@ def test_nelder_mead_lanes_match_sequential(dev, lanes, world):
 def _areal_case(F, seed=51, K_type="block-exponential", cellsize=0.02, tile=0.1, noise=0.1):
     """Areal observations on the unit square: 0.1 x 0.1 tiles (edges kept off the BAU centroids), each observing the average of a
     smooth field over its footprint; one tile row left out so that some BAUs are unobserved; a covariate known at every BAU."""
-    rng = np.random.default_rng(seed)
     xy_dom = np.array([[0.0, 0.0], [1.0, 1.0]])
     gb = F.auto_BAUs(F.plane(), cellsize=cellsize, data=F.SpatialPointsDataFrame(xy_dom, {}))
     cen = gb.centroids()
     gb["fs"] = 1.0 + 0.5 * (cen[:, 0] > 0.5)
     gb["x1"] = cen[:, 0] + cen[:, 1]
-    ptr, vx, vy, z = [0], [], [], []
-    nt = int(round(1.0 / tile))
-    for iy in range(nt):
-        for ix in range(nt):
-            if iy == nt // 2 - 1:
-                continue
-            x0, y0 = tile * ix + 0.003, tile * iy + 0.003
-            vx += [x0, x0 + tile, x0 + tile, x0, x0]
-            vy += [y0, y0, y0 + tile, y0 + tile, y0]
-            ptr.append(len(vx))
-            xm, ym = x0 + tile / 2, y0 + tile / 2
-            z.append(np.sin(6 * xm) + np.cos(5 * ym) + 0.5 * (xm + ym) + noise * rng.standard_normal())
+    ptr, vx, vy, z, std = areal_tiles(tile=tile, noise=noise, seed=seed)
     m = len(z)
-    std = 0.1 + 0.05 * rng.uniform(size=m)
     data = F.SpatialPolygonsDataFrame(np.array(ptr), np.array(vx), np.array(vy), {"z": np.array(z), "std": std})
     ob = O.auto_basis(O.plane(), cen, regular=1, nres=2)
     i_idx, j_idx, x_idx = O.BuildC_polygons(data.ptr, data.vx, data.vy, cen)

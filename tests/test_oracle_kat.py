@@ -320,3 +320,21 @@ def test_polygon_prediction_closed_form_equals_joint_solve():
     var2 = np.asarray(CPM.multiply(CPM @ Sig).sum(axis=1)).ravel() + np.asarray(CP.multiply(CP) @ (1.0 / (A + Q))).ravel()
     np.testing.assert_allclose(var2, var, rtol=1e-10)
     np.testing.assert_allclose(CP @ O.predict(M, obs_fs=False)[0], mu, rtol=1e-10, atol=1e-12)
+
+
+def test_widening_golden_fixture():
+    """tests/golden/widening_oracle.json (tools/make_golden_widening.py): the oracle's outputs for areal data, prediction polygons,
+    auto_basis pruning and space-time slicing -- pins the ORACLE against drift (these are not reference outputs)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_widening", os.path.join(os.path.dirname(GOLD), "..", "tools", "make_golden_widening.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.build()
+    gold = json.load(open(os.path.join(GOLD, "widening_oracle.json")))
+    assert now.keys() == gold.keys()
+    for sect in gold:
+        for k, v in gold[sect].items():
+            if isinstance(v, (int,)) or (isinstance(v, list) and v and isinstance(v[0], int)):
+                assert now[sect][k] == v, (sect, k)
+            else:
+                np.testing.assert_allclose(now[sect][k], v, rtol=1e-8, err_msg=f"{sect}.{k}")
