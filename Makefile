@@ -6,7 +6,7 @@ NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
 SRC       := frk_b200/csrc
 OBJ       := $(SRC)/build
 LIB       := frk_b200/libfrkb200.so
-CUS       := ctx basis bau sparse bucket dense model areal host_api
+CUS       := ctx comm basis bau sparse bucket dense model areal host_api
 
 all: $(LIB)
 

@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--deterministic", action="store_true", help="fixed-order Gram flush instead of fp64 atomics (bit-reproducible runs)")
     ap.add_argument("--distribute-nm", action="store_true", help="spread the Nelder-Mead candidates over the ranks (default: replicated on local lanes)")
     ap.add_argument("--lanes", type=int, default=None, help="concurrent Nelder-Mead evaluation lanes per GPU (frk_model_set_lanes)")
+    ap.add_argument("--comm", default="nccl", choices=["nccl", "hook"],
+                    help="multi-GPU reductions: the library's own NCCL communicator (frk_comm_init) or the torch.distributed hook")
+    ap.add_argument("--parity-tol", type=float, default=1e-9, help="relative tolerance of the in-run parity check against the oracle")
     return ap.parse_args()
 
 
@@ -93,11 +96,11 @@ def cpu_em(args, budget_s, max_steps, warmup=0):
     uo, means, _ = O.bin_mean(bau, np.column_stack([z, std]))
     cc = np.column_stack([ba.xgrid[uo % ba.nx], ba.ygrid[uo // ba.nx]])
     M = O.SRE(ob, cc, np.ones(len(uo)), np.arange(len(uo)), means[:, 0], means[:, 1], K_type=args.k_type, fast_eval=True)
-    times = []
+    times, llk = [], []
     t_all = time.time()
     for it in range(warmup + max_steps):
         t0 = time.time()
-        O.loglik(M); O.Estep(M); O.Mstep(M)
+        llk.append(float(O.loglik(M))); O.Estep(M); O.Mstep(M)
         dt = time.time() - t0
         if it >= warmup:
             times.append(dt)
@@ -112,7 +115,11 @@ def cpu_em(args, budget_s, max_steps, warmup=0):
     mu = S0s @ M.mu_eta
     tp = time.time() - t0
     blas = [f"{d.get('internal_api')}:{d.get('num_threads')}" for d in threadpool_info()]
-    return dict(iters=len(times), s_per_iter=float(np.mean(times)), iters_per_s=len(times) / float(np.sum(times)),
+    # what the GPU arm is compared with (parity): the trace from .EM_initialise and the state after len(llk) iterations
+    oracle = dict(llk=llk, alpha=np.asarray(M.alphahat, dtype=np.float64).ravel(), sigma2fs=float(M.sigma2fshat),
+                  mu_eta=np.asarray(M.mu_eta).ravel(), S_eta_diag=np.diag(M.S_eta).copy(), bau_idx=idx,
+                  mu=float(np.asarray(M.alphahat).ravel()[0]) + mu, var=v)
+    return dict(oracle=oracle, iters=len(times), s_per_iter=float(np.mean(times)), iters_per_s=len(times) / float(np.sum(times)),
                 predict_baus_per_s=nb / tp, cores=os.cpu_count(), blas=blas, r=ob.n, n_bau=ba.n, m=len(uo),
                 sample=f"{len(times)} full EM iteration(s) (loglik+E+M, K_type={args.k_type}) at m={len(uo)}, r={ob.n} "
                        f"after {warmup} warm-up; predict on a {nb}-BAU sample; NumPy/SciPy oracle, BLAS threads {blas}")
@@ -202,6 +209,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = F.get_device(local)
+    if world > 1 and args.comm == "nccl":
+        dev.init_comm()      # the library's own NCCL communicator carries every reduction of the fit; torch's group only times / barriers
     if args.deterministic:
         dev.set_deterministic(True)
     _dbg("device + process group up")
@@ -244,6 +253,15 @@ def run_b200(args):
     launches = dev.launches() - l0
     llk_tail = [float(v) for v in mdl.info_fit["llk"][-2:]]
     nm_stats = mdl.info_fit.get("nm_stats")
+    # per-iteration times of the NEXT iterations (one call each): `value` depends on which iterations are timed, because the
+    # Nelder-Mead rounds of the M-step shrink as tau converges
+    iter_ms = []
+    for _ in range(5):
+        e0.record()
+        F.SRE_fit(mdl, n_EM=1, tol=0.0, lanes=args.lanes, distribute_nm=args.distribute_nm)
+        e1.record()
+        torch.cuda.synchronize()
+        iter_ms.append(round(e0.elapsed_time(e1), 3))
 
     _dbg("EM timed")
     # ---- (B) device-resident prediction ---------------------------------------------------------------
@@ -342,6 +360,38 @@ def run_b200(args):
                     "traffic": None, "launches": g["launches"], "peak_source": "cuBLAS DGEMM 8192^3 probe in this run",
                     "share_of_step": round(g["ms"] / tot_ms, 4), "note": "latency-bound (sequential column dependency), not throughput-bound"}
 
+    # ---- (D2) the setup kernels of SRE(): eval_basis -> CSR, point -> BAU lookup, binning (north_star items 1-2) --------------
+    setup = []
+    if not args.no_profile:
+        nloc = mdl.hi - mdl.lo
+        call("frk_profile", dev.ctx, 1)
+        ms = F.SRE("z ~ 1", data, basis, BAUs, est_error=False, K_type=args.k_type, dev=dev)
+        ms.S0.buckets(dev)
+        buf = C.create_string_buffer(1 << 16)
+        call("frk_profile_report", dev.ctx, buf, len(buf))
+        call("frk_profile", dev.ctx, 0)
+        rep = {k["kernel"]: k for k in json.loads(buf.value.decode())}
+        nobs_loc = len(z) if world == 1 else None
+        # algorithmic bytes: eval_basis N*8d + (N+1)*4 + nnz*12; lookup 20 B/point
+        alg = {"eval_basis (count/scan/fill or one pass)": (nloc * 16 + (nloc + 1) * 4 + ms.S0.nnz * 12,
+                                                             [k for k in rep if k.startswith("eval_")]),
+               "grid_lookup_kernel": ((20 * nobs_loc) if nobs_loc else 0, ["grid_lookup_kernel"]),
+               "bin_* (counting sort + per-BAU means)": (0, [k for k in rep if k.startswith("bin_")]),
+               "gather_count/fill (S = C_Z S0)": (ms.S.nnz * 24 + ms.m * 8, [k for k in rep if k.startswith("gather_")]),
+               "row buckets + ELL tiles (bucket_*, ell_*)": (0, [k for k in rep if k.startswith(("bucket_", "ell_"))])}
+        for name, (by, ks) in alg.items():
+            t = sum(rep[k]["ms"] for k in ks if k in rep)
+            if t <= 0:
+                continue
+            ent = {"kernel": name, "ms": round(t, 3), "launches": int(sum(rep[k]["launches"] for k in ks if k in rep))}
+            if by:
+                ent.update(bound="hbm", algorithmic_bytes=int(by), achieved=by / (t * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
+                           frac=by / (t * 1e-3) / 1e9 / hbm_peak)
+            setup.append(ent)
+        setup.append({"kernel": "all SRE() + bucket kernels", "ms": round(sum(k["ms"] for k in rep.values()), 3),
+                      "launches": int(sum(k["launches"] for k in rep.values()))})
+        del ms
+
     # ---- (C) end to end through the public host-buffer API -------------------------------------------
     # one untimed pass first (it allocates the pinned result buffers and fills the allocator pools), then the timed pass
     del mdl
@@ -366,12 +416,43 @@ def run_b200(args):
             del m2, slots, pr
 
     _dbg("e2e done")
-    # ---- (E) CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
-    cpu = None
+    llk_trace = [float(v) for v in m2.info_fit["llk"]]           # from .EM_initialise (the e2e pass): what the parity checks read
+    # ---- (E) CPU baseline (rank 0, N = 1 only) + parity of THIS configuration against it -------------------
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_em(args, budget_s=args.cpu_budget, max_steps=2, warmup=0)
         cpu = {"value": res["iters_per_s"], "unit": "EM iters/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
                "predict_baus_per_s": res["predict_baus_per_s"]}
+        # the oracle ran k full-size EM iterations from .EM_initialise on the identical inputs: compare the log-likelihood trace,
+        # and the state after exactly k iterations (alpha, sigma2fs, mu_eta, diag S_eta, predict mu / var on its 1e5-BAU sample)
+        orc = res["oracle"]
+        k = len(orc["llk"])
+        m3 = F.SRE("z ~ 1", data, basis, BAUs, est_error=False, K_type=args.k_type, dev=dev)
+        F.SRE_fit(m3, n_EM=k, tol=0.0, lanes=args.lanes)
+        pr3 = F.predict(m3, obs_fs=True, to_host=True)
+        rel = lambda g, o: float(np.max(np.abs(np.asarray(g) - np.asarray(o))) / np.max(np.abs(np.asarray(o))))
+        parity = {"against": "oracle (NumPy/SciPy restatement of the reference; parity unpinned by reference-held vectors), full C3 size",
+                  "iters": k, "tol": args.parity_tol,
+                  "llk_rel": float(max(abs(g - o) / abs(o) for g, o in zip(m3.info_fit["llk"], orc["llk"]))),
+                  "llk_gpu": [float(v) for v in m3.info_fit["llk"]], "llk_oracle": orc["llk"],
+                  "alpha_rel": rel(m3.alphahat, orc["alpha"]), "sigma2fs_rel": rel([m3.sigma2fshat], [orc["sigma2fs"]]),
+                  "mu_eta_rel": rel(m3.get("mu_eta"), orc["mu_eta"]), "S_eta_diag_rel": rel(np.diag(m3.get("S_eta")), orc["S_eta_diag"]),
+                  "mu_rel": rel(pr3["mu"][orc["bau_idx"]], orc["mu"]), "var_rel": rel(pr3["var"][orc["bau_idx"]], orc["var"]),
+                  "norm": "max |gpu - oracle| / max |oracle| per quantity; llk: worst relative error over the iterations"}
+        parity["ok"] = bool(all(parity[q] <= args.parity_tol for q in
+                                ("llk_rel", "alpha_rel", "sigma2fs_rel", "mu_eta_rel", "S_eta_diag_rel", "mu_rel", "var_rel")))
+        del m3, pr3
+    elif rank == 0:
+        # no oracle run here (N > 1 or --no-cpu-baseline): compare the trace with the committed single-GPU trace of this configuration
+        gpath = os.path.join(ROOT, "tests", "golden", "c3_llk_trace_n1.json")
+        default_cfg = (args.n_obs, args.grid, args.regular, args.nres, args.k_type) == (1_000_000, 3163, 2, 3, "block-exponential")
+        if default_cfg and os.path.exists(gpath):
+            ref = json.load(open(gpath))["llk"]
+            kk = min(len(ref), len(llk_trace))
+            parity = {"against": "tests/golden/c3_llk_trace_n1.json (single-GPU trace of this configuration from .EM_initialise)",
+                      "iters": kk, "tol": 1e-11,
+                      "llk_rel": float(max(abs(g - o) / abs(o) for g, o in zip(llk_trace[:kk], ref[:kk])))}
+            parity["ok"] = bool(parity["llk_rel"] <= 1e-11)
 
     if rank == 0:
         line = {"metric": METRIC, "value": args.steps / t_em, "unit": "EM iters/s", "n_gpus": world, "steps": args.steps,
@@ -382,15 +463,26 @@ def run_b200(args):
                 "e2e": {"value": args.steps / t_fit_e2e, "unit": "EM iters/s", "h2d_bytes_per_step": h2d_fit / args.steps,
                         "d2h_bytes_per_step": d2h_fit / args.steps,
                         "what": f"SRE() from pinned host arrays + SRE_fit({args.steps} EM iterations from .EM_initialise) + fitted slots (mu_eta, S_eta, Khat, Khat_inv) back to pinned host memory, wall clock, after one untimed pass"},
-                "gpu_launches": int(launches), "clocks": clk, "llk_last": llk_tail, "nelder_mead_last_mstep": nm_stats}
+                "gpu_launches": int(launches), "clocks": clk, "llk_last": llk_tail, "nelder_mead_last_mstep": nm_stats,
+                "ms_per_iteration_next5": iter_ms, "llk_trace_from_init": llk_trace,
+                "comm": (args.comm if world > 1 else None)}
+        if parity:
+            line["parity"] = parity
         if roof:
             line["roofline"] = roof
         if kernels:
             line["kernels"] = kernels[:12]
+        if setup:
+            line["setup_kernels"] = setup
+        line["e2e"]["predict_baus_per_s"] = N / t_pred_e2e
+        line["config"]["predict_baus_per_s_device"] = N / t_pred
         if cpu:
             line["cpu_baseline"] = cpu
         _emit(line)
     _dbg("line printed")
+    if rank == 0 and parity and not parity["ok"]:
+        print(f"PARITY FAILED: {json.dumps({k: v for k, v in parity.items() if k.endswith('_rel')})}", file=sys.stderr, flush=True)
+        _EXIT[0] = 3
     if world > 1:
         try:
             del m2, slots, pr
@@ -406,6 +498,7 @@ def _dbg(msg):
 
 
 _REAL_STDOUT = None
+_EXIT = [0]
 
 
 def _guard_stdout():
@@ -430,6 +523,8 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+    if _EXIT[0]:
+        sys.exit(_EXIT[0])
 
 
 if __name__ == "__main__":

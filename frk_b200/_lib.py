@@ -55,6 +55,14 @@ SIGNATURES = {
     "frk_use_deterministic": (c_int, [vp, c_int]),
     "frk_profile": (c_int, [vp, c_int]),
     "frk_profile_report": (c_int, [vp, C.c_char_p, C.c_size_t]),
+    "frk_comm_unique_id": (c_int, [vp]),
+    "frk_comm_init": (c_int, [vp, c_int, c_int, vp]),
+    "frk_comm_destroy": (c_int, [vp]),
+    "frk_comm_rank": (c_int, [vp]),
+    "frk_comm_world": (c_int, [vp]),
+    "frk_comm_allreduce": (c_int, [vp, vp, c_i64, c_int]),
+    "frk_comm_allreduce_host": (c_int, [vp, vp, c_i64, c_int]),
+    "frk_comm_broadcast": (c_int, [vp, vp, c_i64, c_int]),
     "frk_basis_create": (c_int, [vp, c_int, c_dbl, c_int, c_int, c_int, vp, vp, vp, C.POINTER(vp)]),
     "frk_basis_destroy": (c_int, [vp]),
     "frk_basis_dist_matrix": (c_int, [vp, vp, c_int, vp, vp]),
@@ -138,6 +146,7 @@ SIGNATURES = {
     "frk_model_set": (c_int, [vp, C.c_char_p, vp]),
     "frk_model_slot_device": (c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "frk_model_predict": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp, vp]),
+    "frk_model_predict_host": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, c_i64, vp, vp, vp, vp, vp, vp]),
     "frk_optim_nelder_mead": (c_int, [OBJECTIVE_FN, vp, c_int, vp, c_int, c_dbl, vp, p_dbl, p_int, p_int]),
     "frk_optim_nelder_mead_speculative": (c_int, [OBJECTIVE_FN, vp, c_int, vp, c_int, c_dbl, c_int, vp, p_dbl, p_int, p_int, p_int]),
     "frk_optim_zeroin": (c_int, [OBJECTIVE_FN, vp, c_dbl, c_dbl, p_dbl]),

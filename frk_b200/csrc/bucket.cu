@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(GR_T) gram_bucket_kernel(int nbuckets, const i
         if (b1 <= b0) continue;
         const int nU = nU_all[b];
         if (nU > UMAX) {
-            // direct path: one warp per row, one fp64 atomic per (row, pair)
+            // direct path: one warp per row, one fp64 atomic per (row, pair) -- also in deterministic mode (frk_use_deterministic
+            // fixes the order of the staged buckets only; rows wider than UMAX columns are summed in atomic order)
             for (int pr = b0 + wid; pr < b1; pr += GR_T / 32) {
                 const int row = perm[pr], beg = rowptr[row], k = rowptr[row + 1] - beg;
                 double rho = z[row];
@@ -400,7 +401,10 @@ __global__ void __launch_bounds__(GR_T) gram_bucket_kernel(int nbuckets, const i
                 for (int a = 0; a < k; a++) {
                     const int ca = col[beg + a];
                     const double wa = w * val[beg + a];
-                    for (int bb = a + lane; bb < k; bb += 32) atomicAdd(G + ca + (size_t)r * col[beg + bb], wa * val[beg + bb]);
+                    for (int bb = a + lane; bb < k; bb += 32) {     // upper triangle whatever the column order of the caller's CSR
+                        const int cb = col[beg + bb];
+                        atomicAdd(G + min(ca, cb) + (size_t)r * max(ca, cb), wa * val[beg + bb]);
+                    }
                 }
             }
             continue;

@@ -42,7 +42,15 @@ struct frk_ctx {
     std::map<std::array<uintptr_t, 5>, GraphEntry> graphs;
     // lane contexts (frk_ctx_lane): created on first use, kept for the life of this context so that models come and go cheaply
     std::vector<frk_ctx *> lanes_hi, lanes_lo;
+    // in-library NCCL communicator (comm.cu): row-partitioned runs without a host-language reduction hook
+    void *comm = nullptr;                // ncclComm_t
+    int comm_rank = 0, comm_world = 1;
+    double *comm_h = nullptr, *comm_d = nullptr;   // pinned / device staging for the small host-side reductions
+    cudaStream_t comm_stream = nullptr;  // ... which run on their own stream: they carry host data and must not queue behind a factorisation
 };
+static constexpr int FRK_COMM_STAGE = 4096;
+int frk_pack_upper(frk_ctx *ctx, int r, const double *d_G, double *d_P);      // column j, rows 0..j -> P[j(j+1)/2 + i]
+int frk_unpack_upper(frk_ctx *ctx, int r, const double *d_P, double *d_G);
 
 int frk_prof_begin(frk_ctx *ctx, const char *name, cudaEvent_t *e1);   // records e0; returns 0
 int frk_prof_harvest(frk_ctx *ctx);
@@ -91,6 +99,7 @@ int frk_ctx_create_lane(const frk_ctx *parent, bool high_priority, frk_ctx **out
 // synchronisation, so that one host thread can keep several contexts busy at once
 int frk_potrf_async(frk_ctx *ctx, int r, double *d_A);
 int frk_potrf_finish(frk_ctx *ctx, double *h_logdet);
+int frk_potrf_status(frk_ctx *ctx, double *h_logdet);   // non-failing: order of the first bad leading minor, 0 if positive definite
 int frk_dot_async(frk_ctx *ctx, int64_t n, const double *d_A, const double *d_B);
 static constexpr int FRK_PINNED_DOT = 4080;          // slot of frk_dot_async's result in frk_ctx::h_pinned
 // lane `idx` of `parent` (cached in the parent, destroyed with it)

@@ -88,6 +88,7 @@ extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    frk_comm_destroy(ctx);
     for (frk_ctx *l : ctx->lanes_hi) frk_ctx_destroy(l);
     for (frk_ctx *l : ctx->lanes_lo) frk_ctx_destroy(l);
     frk_prof_harvest(ctx);
@@ -121,6 +122,7 @@ extern "C" int frk_malloc(frk_ctx *ctx, size_t bytes, void **d_out) {
 }
 
 extern "C" int frk_free(frk_ctx *ctx, void *d_ptr) {
+    FRK_CHECK_CUDA(cudaSetDevice(ctx->device));
     FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     FRK_CHECK_CUDA(cudaFree(d_ptr));
     return 0;

@@ -714,6 +714,13 @@ int frk_potrf_finish(frk_ctx *ctx, double *h_logdet) {
     return 0;
 }
 
+// same, without failing: returns the order of the first non-positive leading minor (0: positive definite)
+int frk_potrf_status(frk_ctx *ctx, double *h_logdet) {
+    const double *st = ctx->h_pinned + 4096 - 8;
+    if (h_logdet) *h_logdet = 2.0 * st[0];
+    return (int)st[1];
+}
+
 extern "C" int frk_potrf(frk_ctx *ctx, int r, double *d_A, double *h_logdet) {
     if (int rc = frk_potrf_async(ctx, r, d_A)) return rc;
     FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -100,15 +100,46 @@ int dalloc(frk_model *M, T **out, size_t n) {
     return 0;
 }
 
+// Row-partitioned runs: the caller's reduction hook if one was given, else the context's own NCCL communicator (comm.cu)
+inline bool multi_rank(const frk_model *M) { return M->allreduce != nullptr || M->ctx->comm != nullptr; }
+
 int reduce_dev(frk_model *M, double *d_buf, int64_t n) {
-    if (!M->allreduce) return 0;
-    FRK_REQUIRE(M->allreduce(M->user, d_buf, n, 1, 0) == 0, "all-reduce callback failed (device buffer)");
-    return 0;
+    if (M->allreduce) {
+        FRK_REQUIRE(M->allreduce(M->user, d_buf, n, 1, 0) == 0, "all-reduce callback failed (device buffer)");
+        return 0;
+    }
+    return frk_comm_allreduce(M->ctx, d_buf, n, 0);
 }
 
 int reduce_host(frk_model *M, double *h_buf, int64_t n, int op) {
-    if (!M->allreduce) return 0;
-    FRK_REQUIRE(M->allreduce(M->user, h_buf, n, 0, op) == 0, "all-reduce callback failed (host buffer)");
+    if (M->allreduce) {
+        FRK_REQUIRE(M->allreduce(M->user, h_buf, n, 0, op) == 0, "all-reduce callback failed (host buffer)");
+        return 0;
+    }
+    return frk_comm_allreduce_host(M->ctx, h_buf, n, op);
+}
+
+// d_buf (valid on rank `root` of the Nelder-Mead world) to every rank: ncclBroadcast on the communicator; through a
+// reduction hook it is a sum with zeros elsewhere
+int bcast_dev(frk_model *M, double *d_buf, int64_t n, int root, bool mine) {
+    if (!M->allreduce && M->ctx->comm) return frk_comm_broadcast(M->ctx, d_buf, n, root);
+    if (!mine) FRK_CHECK_CUDA(cudaMemsetAsync(d_buf, 0, (size_t)n * sizeof(double), M->ctx->stream));
+    return reduce_dev(M, d_buf, n);
+}
+
+// acc = [upper(G) full r x r storage | rhs r | 2 scalars] summed over the ranks; what travels is the packed upper triangle
+int reduce_gram(frk_model *M) {
+    if (!multi_rank(M)) return 0;
+    const int r = M->r;
+    const size_t rr = (size_t)r * r, np = (size_t)r * (r + 1) / 2, tail = (size_t)r + 2;
+    void *raw = nullptr;
+    RC(frk_scratch(M->ctx, (np + tail) * sizeof(double), &raw));
+    double *P = (double *)raw;
+    RC(frk_pack_upper(M->ctx, r, M->acc, P));
+    FRK_CHECK_CUDA(cudaMemcpyAsync(P + np, M->acc + rr, tail * sizeof(double), cudaMemcpyDeviceToDevice, M->ctx->stream));
+    RC(reduce_dev(M, P, (int64_t)(np + tail)));
+    RC(frk_unpack_upper(M->ctx, r, P, M->acc));
+    FRK_CHECK_CUDA(cudaMemcpyAsync(M->acc + rr, P + np, tail * sizeof(double), cudaMemcpyDeviceToDevice, M->ctx->stream));
     return 0;
 }
 
@@ -119,7 +150,7 @@ inline int nm_rank(const frk_model *M) { return (M->nm_distribute && !M->spec_em
 // sum, sum of squares about `shift`, min, max over ALL ranks' rows
 int global_stats(frk_model *M, const double *d_x, double shift, double out[4]) {
     RC(frk_vec_stats(M->ctx, M->m, d_x, shift, out));
-    if (M->allreduce) {
+    if (multi_rank(M)) {
         double s[2] = {out[0], out[1]}, mn[1] = {-out[2]}, mx[1] = {out[3]};
         RC(reduce_host(M, s, 2, 0));
         RC(reduce_host(M, mn, 1, 1));
@@ -370,6 +401,14 @@ struct SpecNM {
     std::vector<double> fv;
     std::vector<int> owner;
 
+    // A value of NaN marks a point whose K_i(tau) could not be factorised.  Speculative candidates are evaluated as a matter of
+    // course, so such a failure must not abort the fit: it is an error only if Nelder-Mead actually ASKS for the point -- exactly
+    // when the reference's chol() inside optim()'s objective would have stopped (R/SREfit.R:503,517).
+    int check_requested(const double *x, double f) const {
+        FRK_REQUIRE(!std::isnan(f), "block-exponential update: K_i(tau = %g) is not positive definite (chol failed at a requested point)", x[0]);
+        return 0;
+    }
+
     int find(const double *x) const {
         for (size_t i = 0; i < pts.size(); i++) {
             bool eq = true;
@@ -434,6 +473,7 @@ struct SpecNM {
             const int i = find(y);
             if (i < 0) { need.assign(y, y + dim); return 99; }
             f = fv[i];
+            RC(check_requested(y, f));
             if ((int)seen.size() <= i) seen.resize(i + 1, 0);
             if (!seen[i]) { seen[i] = 1; M->nm_requests += 1; }
             return requested ? requested(y, f) : 0;
@@ -444,7 +484,7 @@ struct SpecNM {
     int operator()(const double *x, double &f) {
         int i = find(x);
         M->nm_requests += 1;
-        if (i >= 0) { f = fv[i]; return requested ? requested(x, f) : 0; }
+        if (i >= 0) { f = fv[i]; RC(check_requested(x, f)); return requested ? requested(x, f) : 0; }
         M->nm_rounds += 1;
         static const bool dbg = getenv("FRK_SPEC_DEBUG") != nullptr;
         // candidate k goes to rank k % world (the likeliest ones spread over the GPUs first), lane k / world
@@ -474,6 +514,7 @@ struct SpecNM {
         M->nm_evals += (double)batch.size();
         i = find(x);
         f = fv[i];
+        RC(check_requested(x, f));
         return requested ? requested(x, f) : 0;
     }
 };
@@ -489,12 +530,12 @@ int gram(frk_model *M, const double *alpha, double sigma2fs) {
         bool same = sigma2fs == M->gram_s2;
         for (int i = 0; i < M->p; i++) same = same && alpha[i] == M->gram_alpha[i];
         FRK_CHECK_CUDA(cudaStreamWaitEvent(M->ctx->stream, M->ev_aux1, 0));       // either way acc is not touched before aux is done
-        if (same) return reduce_dev(M, M->acc, (int64_t)n);                         // (this rank's rows: the exchange happens here)
+        if (same) return reduce_gram(M);                                            // (this rank's rows: the exchange happens here)
     }
     FRK_CHECK_CUDA(cudaMemsetAsync(M->acc, 0, n * sizeof(double), M->ctx->stream));
     RC(frk_gram_rhs_bucketed(M->ctx, M->m, M->r, M->rowptr, M->col, M->val, M->bk,
                              M->Z, M->X, M->p, alpha, M->Ve, M->Vfs, sigma2fs, M->acc));
-    return reduce_dev(M, M->acc, (int64_t)n);                         // the ONE large exchange per EM iteration
+    return reduce_gram(M);                                            // the ONE large exchange per EM iteration
 }
 
 // Q = S'D^-1 S + Khat_inv; Sigma = chol2inv(chol(Q)); mu = Sigma S'D^-1 rho   (R/SREfit.R:252-254)
@@ -528,6 +569,15 @@ double llk_from(const frk_model *M, const double o[4]) {
 
 int chol2inv_logdet(frk_ctx *ctx, int n, double *A, double *Ainv, double *work, double *logdet) {
     RC(frk_potrf(ctx, n, A, logdet));
+    return frk_potri(ctx, n, A, Ainv, work);
+}
+
+// same, but a matrix that is not positive definite is reported through *bad (order of the failing minor) instead of an error
+int chol2inv_logdet_soft(frk_ctx *ctx, int n, double *A, double *Ainv, double *work, double *logdet, int *bad) {
+    RC(frk_potrf_async(ctx, n, A));
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *bad = frk_potrf_status(ctx, logdet);
+    if (*bad) return 0;
     return frk_potri(ctx, n, A, Ainv, work);
 }
 
@@ -682,9 +732,10 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
             if (!s.used) continue;
             s.used = false;
             double logdetKi;
-            RC(frk_potrf_finish(s.ctx, &logdetKi));
+            // a candidate that cannot be factorised is only a failed guess unless Nelder-Mead asks for it (SpecNM::check_requested)
+            const int bad = frk_potrf_status(s.ctx, &logdetKi);
             const double t = s.ctx->h_pinned[FRK_PINNED_DOT];
-            const double f = -(0.5 * (-logdetKi) - S.omega / 2.0 * t);
+            const double f = bad ? std::numeric_limits<double>::quiet_NaN() : -(0.5 * (-logdetKi) - S.omega / 2.0 * t);
             S.fl[s.k] = f; s.ld = logdetKi; s.valid = std::isfinite(f);
         }
         return 0;
@@ -813,11 +864,10 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
                 FRK_REQUIRE(S.bestTau == tau, "block-exponential update: tau = %g cannot be evaluated", tau);
             }
         } else {
-            FRK_CHECK_CUDA(cudaMemsetAsync(B.KinvBest, 0, nn * sizeof(double), ctx->stream));
             S.bestLogdet = 0.0;
         }
-        if (shared) {                                                // broadcast from the owner: sum with zeros elsewhere
-            RC(reduce_dev(M, B.KinvBest, (int64_t)nn));
+        if (shared) {                                                // from the owner to everybody
+            RC(bcast_dev(M, B.KinvBest, (int64_t)nn, own, own == nm_rank(M)));
             RC(reduce_host(M, &S.bestLogdet, 1, 0));
         }
         RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau, 1.0 / omega, B.Ki));
@@ -900,10 +950,13 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
             auto f_tau2 = [&](const double *tau, double &fval) -> int {
                 if (tau[0] <= 1e-10 || tau[1] <= 1e-10) { fval = std::numeric_limits<double>::infinity(); return 0; }
                 double ldt, lds, trk;
+                int bad = 0;
                 RC(frk_exp_kernel(ctx, (int64_t)ntt, M->Dt, tau[1], 1.0, B.Kt));
-                RC(chol2inv_logdet(ctx, nt, B.Kt, B.Qt, B.wt, &ldt));
+                RC(chol2inv_logdet_soft(ctx, nt, B.Kt, B.Qt, B.wt, &ldt, &bad));
+                if (bad) { fval = std::numeric_limits<double>::quiet_NaN(); return 0; }   // an error only if requested (SpecNM)
                 RC(frk_exp_kernel(ctx, (int64_t)nss, B.D, tau[0], 1.0, B.Ks));
-                RC(chol2inv_logdet(ctx, ns, B.Ks, B.Qs, B.ws, &lds));
+                RC(chol2inv_logdet_soft(ctx, ns, B.Ks, B.Qs, B.ws, &lds, &bad));
+                if (bad) { fval = std::numeric_limits<double>::quiet_NaN(); return 0; }
                 RC(frk_kron_dot(ctx, nt, ns, B.Qt, B.Qs, B.eta2, &trk));
                 const double det_part = 0.5 * (ns * (-ldt) + nt * (-lds));
                 fval = -(det_part - omega / 2.0 * trk);
@@ -941,13 +994,11 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
                     FRK_REQUIRE(bestTs == nm.x[0] && bestTt == nm.x[1], "block-exponential update: tau cannot be evaluated");
                 }
             } else {
-                FRK_CHECK_CUDA(cudaMemsetAsync(B.QsBest, 0, nss * sizeof(double), ctx->stream));
-                FRK_CHECK_CUDA(cudaMemsetAsync(B.QtBest, 0, ntt * sizeof(double), ctx->stream));
                 bestLd = 0.0;
             }
             if (shared) {
-                RC(reduce_dev(M, B.QsBest, (int64_t)nss));
-                RC(reduce_dev(M, B.QtBest, (int64_t)ntt));
+                RC(bcast_dev(M, B.QsBest, (int64_t)nss, own, own == nm_rank(M)));
+                RC(bcast_dev(M, B.QtBest, (int64_t)ntt, own, own == nm_rank(M)));
                 RC(reduce_host(M, &bestLd, 1, 0));
             }
             RC(frk_exp_kernel(ctx, (int64_t)ntt, M->Dt, nm.x[1], 1.0, B.Kt));
@@ -1102,6 +1153,7 @@ static int model_common_init(frk_model *M) {
     FRK_CHECK_CUDA(cudaMemsetAsync(M->t, 0, std::max<int64_t>(M->m, 1) * sizeof(double), M->ctx->stream));
     // row buckets of S
     RC(frk_rowbuckets_create(M->ctx, M->m, r, M->rowptr, M->col, M->val, &M->bk));
+    if (!M->allreduce && M->ctx->comm) { M->rank = M->ctx->comm_rank; M->world = M->ctx->comm_world; }
     // totals and the homoscedasticity test all(a == a[1]) & all(b == b[1])   (R/SREfit.R:278-280)
     double mt[1] = {(double)M->m};
     RC(reduce_host(M, mt, 1, 0));
@@ -1177,7 +1229,7 @@ extern "C" int frk_model_destroy(frk_model *M) {
 // world's candidates on this rank (tests the logic on one GPU)
 extern "C" int frk_model_set_parallel(frk_model *M, int rank, int world, int emulate) {
     FRK_REQUIRE(M && world >= 1 && rank >= 0 && rank < world, "frk_model_set_parallel: bad argument");
-    FRK_REQUIRE(emulate || world == 1 || M->allreduce, "frk_model_set_parallel: world > 1 needs the all-reduce hook");
+    FRK_REQUIRE(emulate || world == 1 || multi_rank(M), "frk_model_set_parallel: world > 1 needs the all-reduce hook or frk_comm_init");
     M->rank = emulate ? 0 : rank; M->world = world; M->spec_emulate = emulate != 0;
     return 0;
 }
@@ -1186,7 +1238,7 @@ extern "C" int frk_model_set_parallel(frk_model *M, int rank, int world, int emu
 // broadcast); 0 (default): every rank evaluates them on its own lanes -- replicated, deterministic, no exchange
 extern "C" int frk_model_set_nm_distribute(frk_model *M, int distribute) {
     FRK_REQUIRE(M, "frk_model_set_nm_distribute: NULL model");
-    FRK_REQUIRE(!distribute || M->world == 1 || M->allreduce, "frk_model_set_nm_distribute: needs the all-reduce hook");
+    FRK_REQUIRE(!distribute || M->world == 1 || multi_rank(M), "frk_model_set_nm_distribute: needs the all-reduce hook or frk_comm_init");
     M->nm_distribute = distribute != 0;
     return 0;
 }
@@ -1495,7 +1547,7 @@ extern "C" int frk_model_predict_areal(frk_model *M, int64_t n, const int *d_row
     FRK_REQUIRE(M && d_rowptr0 && bk0 && d_XBAU && d_fs && d_cz_rowptr && d_cz_members && d_cz_weights && d_mu && d_var && d_sd && n > 0,
                 "frk_model_predict_areal: bad argument");
     FRK_REQUIRE(M->sigma2fs > 0.0, "frk_model_predict_areal: sigma2fs = 0 -- use frk_model_predict (stored posterior)");
-    FRK_REQUIRE(!M->allreduce, "frk_model_predict_areal: row-partitioned runs are not supported for areal data");
+    FRK_REQUIRE(!multi_rank(M), "frk_model_predict_areal: row-partitioned runs are not supported for areal data");
     frk_ctx *ctx = M->ctx;
     const int r = M->r;
     const size_t rr = (size_t)r * r;
@@ -1570,7 +1622,7 @@ extern "C" int frk_model_predict_polygons(frk_model *M, int64_t n, const int *d_
                                           const double *d_cp_weights, int64_t cp_nnz, double *d_mu, double *d_var, double *d_sd) {
     FRK_REQUIRE(M && d_rowptr0 && bk0 && d_XBAU && d_cp_rowptr && d_cp_members && d_cp_weights && d_mu && d_var && d_sd && n > 0 && mP > 0 &&
                 cp_nnz > 0, "frk_model_predict_polygons: bad argument");
-    FRK_REQUIRE(!M->allreduce, "frk_model_predict_polygons: row-partitioned runs are not supported (polygons may straddle ranks)");
+    FRK_REQUIRE(!multi_rank(M), "frk_model_predict_polygons: row-partitioned runs are not supported (polygons may straddle ranks)");
     frk_ctx *ctx = M->ctx;
     const int r = M->r;
     const size_t rr = (size_t)r * r;
@@ -1623,6 +1675,76 @@ extern "C" int frk_model_predict_polygons(frk_model *M, int64_t n, const int *d_
     if (pval) cudaFreeAsync(pval, ctx->stream);
     cudaFreeAsync(irp, ctx->stream);
     cudaFreeAsync(buf, ctx->stream);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// predict() from HOST buffers: what the R `.Call` shim binds for .SRE.predict_EM (R/SREpredict.R:243-420).  Uploads S0 (host CSR,
+// the dgRMatrix slots of object@S0), builds its row buckets, runs the matching device prediction and downloads mu / var / sd.
+//   h_cp_* given (mP > 0)            -> prediction over polygons  (frk_model_predict_polygons, :378-419), outputs have length mP
+//   h_cz_* given, !obs_fs, s2fs > 0  -> areal data, Case 2        (frk_model_predict_areal, :308-333), length n
+//   else                             -> BAU level                 (frk_model_predict), length n; h_obs_bau needed for Case 2
+// ---------------------------------------------------------------------------------
+extern "C" int frk_model_predict_host(frk_model *M, int64_t n, const int *h_rowptr0, const int *h_col0, const double *h_val0,
+                                      const double *h_XBAU, const double *h_fs, const int *h_obs_bau, const int *h_cz_rowptr,
+                                      const int *h_cz_members, const double *h_cz_weights, int obs_fs, int64_t mP,
+                                      const int *h_cp_rowptr, const int *h_cp_members, const double *h_cp_weights, double *h_mu,
+                                      double *h_var, double *h_sd) {
+    FRK_REQUIRE(M && h_rowptr0 && h_col0 && h_val0 && h_XBAU && h_mu && h_var && h_sd && n > 0, "frk_model_predict_host: bad argument");
+    frk_ctx *ctx = M->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t nnz = h_rowptr0[n], m = M->m;
+    const bool polygons = mP > 0 && h_cp_rowptr && h_cp_members && h_cp_weights;
+    const bool areal = h_cz_rowptr && h_cz_members && h_cz_weights;
+    const int64_t cz_nnz = areal ? h_cz_rowptr[m] : 0, cp_nnz = polygons ? h_cp_rowptr[mP] : 0, nout = polygons ? mP : n;
+    std::vector<void *> bufs;
+    frk_rowbuckets *bk = nullptr;
+    auto up = [&](const void *h, size_t bytes, void **d) -> int {
+        *d = nullptr;
+        if (!h) return 0;
+        FRK_CHECK_CUDA(cudaMallocAsync(d, std::max<size_t>(bytes, 16), st));
+        bufs.push_back(*d);
+        FRK_CHECK_CUDA(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    auto run = [&]() -> int {
+        void *rp, *cl, *vl, *xb, *fs, *ob, *czr, *czm, *czw, *cpr, *cpm, *cpw, *out;
+        RC(up(h_rowptr0, (size_t)(n + 1) * sizeof(int), &rp));
+        RC(up(h_col0, (size_t)nnz * sizeof(int), &cl));
+        RC(up(h_val0, (size_t)nnz * sizeof(double), &vl));
+        RC(up(h_XBAU, (size_t)n * M->p * sizeof(double), &xb));
+        RC(up(h_fs, (size_t)n * sizeof(double), &fs));
+        RC(up(h_obs_bau, (size_t)std::max<int64_t>(m, 1) * sizeof(int), &ob));
+        RC(up(areal ? h_cz_rowptr : nullptr, (size_t)(m + 1) * sizeof(int), &czr));
+        RC(up(areal ? h_cz_members : nullptr, (size_t)cz_nnz * sizeof(int), &czm));
+        RC(up(areal ? h_cz_weights : nullptr, (size_t)cz_nnz * sizeof(double), &czw));
+        RC(up(polygons ? h_cp_rowptr : nullptr, (size_t)(mP + 1) * sizeof(int), &cpr));
+        RC(up(polygons ? h_cp_members : nullptr, (size_t)cp_nnz * sizeof(int), &cpm));
+        RC(up(polygons ? h_cp_weights : nullptr, (size_t)cp_nnz * sizeof(double), &cpw));
+        FRK_CHECK_CUDA(cudaMallocAsync(&out, (size_t)3 * nout * sizeof(double), st));
+        bufs.push_back(out);
+        double *mu = (double *)out, *var = mu + nout, *sd = var + nout;
+        RC(frk_rowbuckets_create(ctx, n, M->r, (const int *)rp, (const int *)cl, (const double *)vl, &bk));
+        if (polygons) {
+            RC(frk_model_predict_polygons(M, n, (const int *)rp, (const int *)cl, (const double *)vl, bk, (const double *)xb, (const double *)fs,
+                                          (const int *)ob, obs_fs, mP, (const int *)cpr, (const int *)cpm, (const double *)cpw, cp_nnz, mu, var, sd));
+        } else if (areal && !obs_fs && M->sigma2fs > 0.0) {
+            RC(frk_model_predict_areal(M, n, (const int *)rp, (const int *)cl, (const double *)vl, bk, (const double *)xb, (const double *)fs,
+                                       (const int *)czr, (const int *)czm, (const double *)czw, mu, var, sd));
+        } else {
+            RC(frk_model_predict(M, n, (const int *)rp, (const int *)cl, (const double *)vl, bk, (const double *)xb, (const double *)fs,
+                                 (const int *)ob, obs_fs, mu, var, sd));
+        }
+        FRK_CHECK_CUDA(cudaMemcpyAsync(h_mu, mu, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+        FRK_CHECK_CUDA(cudaMemcpyAsync(h_var, var, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+        FRK_CHECK_CUDA(cudaMemcpyAsync(h_sd, sd, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+        FRK_CHECK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    };
+    const int rc = run();
+    if (rc) cudaStreamSynchronize(st);
+    if (bk) frk_rowbuckets_destroy(bk);
+    for (void *p : bufs) cudaFreeAsync(p, st);
     return rc;
 }
 

@@ -32,6 +32,48 @@ class Device:
         ctx = vp()
         call("frk_ctx_create", index, vp(self.stream.cuda_stream), C.byref(ctx))
         self.ctx = ctx
+        self.has_comm = False
+
+    # ---- in-library NCCL (frk_comm_*): no torch, no Python in the data path of the reductions -------------------
+    def init_comm(self, rank: Optional[int] = None, world: Optional[int] = None, id_file: Optional[str] = None):
+        """Give the context its own NCCL communicator.  The 128-byte unique id travels from rank 0 to the others either through the
+        already initialised ``torch.distributed`` group (any backend -- rendezvous only) or, with ``id_file``, through a file
+        (what an R / MPI host would do).  Models created afterwards reduce over the communicator instead of the Python hook."""
+        import time as _time
+        d = self.torch.distributed
+        have_pg = d.is_available() and d.is_initialized()
+        rank = (d.get_rank() if have_pg else 0) if rank is None else int(rank)
+        world = (d.get_world_size() if have_pg else 1) if world is None else int(world)
+        if world <= 1:
+            return self
+        uid = C.create_string_buffer(128)
+        if id_file is not None:
+            if rank == 0:
+                call("frk_comm_unique_id", uid)
+                with open(id_file + ".tmp", "wb") as fh:
+                    fh.write(uid.raw)
+                os.replace(id_file + ".tmp", id_file)
+            else:
+                t0 = _time.time()
+                while not os.path.exists(id_file):
+                    if _time.time() - t0 > 120:
+                        raise FRKError(f"init_comm: no unique id at {id_file} after 120 s")
+                    _time.sleep(0.01)
+                with open(id_file, "rb") as fh:
+                    uid.raw = fh.read(128)
+        else:
+            if not have_pg:
+                raise FRKError("init_comm: needs an initialised torch.distributed group or id_file to share the NCCL unique id")
+            box = [None]
+            if rank == 0:
+                call("frk_comm_unique_id", uid)
+                box = [uid.raw]
+            d.broadcast_object_list(box, src=0)
+            uid.raw = box[0]
+        call("frk_comm_init", self.ctx, rank, world, uid)
+        self.has_comm = True
+        self._comm_rank, self._comm_world = rank, world
+        return self
 
     # ---- memory (torch-owned) ------------------------------------------------------
     def empty(self, n, dtype="f8"):
@@ -91,11 +133,15 @@ class Device:
     # ---- distributed plumbing --------------------------------------------------------
     @property
     def world(self) -> int:
+        if self.has_comm:
+            return self._comm_world
         d = self.torch.distributed
         return d.get_world_size() if d.is_available() and d.is_initialized() else 1
 
     @property
     def rank(self) -> int:
+        if self.has_comm:
+            return self._comm_rank
         d = self.torch.distributed
         return d.get_rank() if d.is_available() and d.is_initialized() else 0
 
@@ -119,12 +165,18 @@ class Device:
             try:
                 d = torch.distributed
                 rop = d.ReduceOp.SUM if op == 0 else d.ReduceOp.MAX
+                nccl = d.get_backend() == "nccl"
                 if on_device:
                     t = torch.as_tensor(_View(buf, n), device=tdev)
-                    d.all_reduce(t, op=rop)
+                    if nccl:
+                        d.all_reduce(t, op=rop)
+                    else:                       # gloo (several ranks sharing one GPU in the tests): through the host
+                        hcpu = t.cpu()
+                        d.all_reduce(hcpu, op=rop)
+                        t.copy_(hcpu)
                 else:
                     h = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(int(n),))
-                    t = torch.as_tensor(h.copy(), device=tdev)
+                    t = torch.as_tensor(h.copy(), device=tdev if nccl else "cpu")
                     d.all_reduce(t, op=rop)
                     h[:] = t.cpu().numpy()
                 return 0

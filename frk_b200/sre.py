@@ -57,7 +57,8 @@ class SREModel:
         self.info_fit: dict = {}
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self._hook = dev.allreduce_hook() if dev.world > 1 else _lib.ALLREDUCE_FN()     # must outlive the model
+        # row-partitioned runs: the context's own NCCL communicator if it has one (Device.init_comm), else the Python reduction hook
+        self._hook = dev.allreduce_hook() if (dev.world > 1 and not dev.has_comm) else _lib.ALLREDUCE_FN()     # must outlive the model
         h = vp()
         call("frk_model_create", dev.ctx, m, self.r, p, dev.ptr(S.rowptr), dev.ptr(S.col), dev.ptr(S.val), dev.ptr(Z), dev.ptr(X),
              dev.ptr(Ve), dev.ptr(Vfs), self._hook, vp(None), C.byref(h))

@@ -80,6 +80,24 @@ int frk_use_deterministic(frk_ctx *ctx, int enable);
 int frk_profile(frk_ctx *ctx, int enable);
 int frk_profile_report(frk_ctx *ctx, char *buf, size_t cap);
 
+/* ---- multi-GPU: the context holds the NCCL communicator -------------------------------
+ * One process per GPU.  Rank 0 calls frk_comm_unique_id and hands the FRK_COMM_ID_BYTES bytes to the other ranks by any means
+ * the host language has (a file, MPI, a socket); every rank then calls frk_comm_init on its context.  A frk_model created on
+ * such a context with allreduce == NULL sums its row-partitioned quantities over the communicator -- per EM iteration ONE fp64
+ * ncclAllReduce of [packed upper triangle of S'D^-1 S | S'D^-1 rho | rho'D^-1 rho | sum log d] (r(r+1)/2 + r + 2 doubles: the row sums
+ * crossprod() forms in R/SREfit.R:194,252,254) plus O(p^2)-double all-reduces of the M-step moments (:335-356).  No host
+ * language is involved in the data path.  libnccl.so.2 is opened with dlopen on first use (FRKB200_NCCL_LIB overrides).       */
+#define FRK_COMM_ID_BYTES 128
+int frk_comm_unique_id(void *out128);
+int frk_comm_init(frk_ctx *ctx, int rank, int world, const void *id128);
+int frk_comm_destroy(frk_ctx *ctx);
+int frk_comm_rank(const frk_ctx *ctx);
+int frk_comm_world(const frk_ctx *ctx);
+/* in place on the ctx stream; op: 0 = sum, 1 = max.  No-ops on a context without a communicator. */
+int frk_comm_allreduce(frk_ctx *ctx, double *d_buf, int64_t n, int op);
+int frk_comm_allreduce_host(frk_ctx *ctx, double *h_buf, int64_t n, int op);   /* synchronises */
+int frk_comm_broadcast(frk_ctx *ctx, double *d_buf, int64_t n, int root);
+
 /* ---- basis: local_basis()/Basis object, R/basisfns.R:99-146, R/AllClass.R:78 -----
  * h_loc: r x d column-major centroids; h_scale: r; h_res: r (1-based resolution).
  * radius: sphere radius (R/geometryfns.R:97), ignored otherwise.
@@ -430,6 +448,15 @@ int frk_optim_zeroin(frk_objective_fn fn, void *user, double lower, double upper
 /* eval_basis on host coordinates -> host CSR.  Call with h_col == NULL to get nnz only.     */
 int frk_eval_basis_host(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *h_s,
                         int normalise, int *h_rowptr, int *h_col, double *h_val, int64_t *h_nnz);
+/* .SRE.predict_EM (R/SREpredict.R:243-420) from host buffers -- what the R shim binds for predict().  S0 as host CSR (the
+ * dgRMatrix slots of object@S0, 0-based), h_XBAU n x p column-major, h_fs[n]; h_obs_bau[m] (0-based BAU row of every observation,
+ * point data; may be NULL for obs_fs != 0) or the incidence CSR of Cmat for areal data (h_cz_*, may be NULL); mP > 0 with h_cp_*:
+ * prediction over polygons (C_P as CSR, rows normalised), outputs of length mP; otherwise outputs of length n.           */
+int frk_model_predict_host(frk_model *mdl, int64_t n, const int *h_rowptr0, const int *h_col0, const double *h_val0,
+                           const double *h_XBAU, const double *h_fs, const int *h_obs_bau, const int *h_cz_rowptr,
+                           const int *h_cz_members, const double *h_cz_weights, int obs_fs, int64_t mP,
+                           const int *h_cp_rowptr, const int *h_cp_members, const double *h_cp_weights, double *h_mu,
+                           double *h_var, double *h_sd);
 int frk_grid_lookup_host(frk_ctx *ctx, int64_t n, const double *h_xy, const double *h_offset,
                          const double *h_cellsize, const int *h_dims, const int *h_cell2bau,
                          int64_t ncell, int *h_bau);

@@ -11,10 +11,14 @@ typedef int Rboolean;
 #define INTSXP 13
 #define REALSXP 14
 #define VECSXP 19
+#define RAWSXP 24
+typedef unsigned char Rbyte;
 extern SEXP R_NilValue;
 extern int NA_INTEGER;
 int *INTEGER(SEXP);
 double *REAL(SEXP);
+Rbyte *RAW(SEXP);
+int Rf_asLogical(SEXP);
 SEXP VECTOR_ELT(SEXP, R_xlen_t);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 SEXP STRING_ELT(SEXP, R_xlen_t);

@@ -76,3 +76,57 @@ def test_r_call_shim_type_checks_against_the_header():
                         "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "src", "frkb200_R.c")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_overlay_calls_match_the_registered_routines():
+    """r/R/overlay.R cannot run here (no R): check statically that every `.Call("<routine>", ...)` it makes is registered in the shim's
+    R_CallMethodDef table with the same number of arguments, that every registered routine has a definition with that many SEXP
+    parameters, and that the overlay replaces the predict path as a whole (no stop() on the default predict())."""
+    import re
+    shim = open(os.path.join(ROOT, "r", "src", "frkb200_R.c")).read()
+    over = open(os.path.join(ROOT, "r", "R", "overlay.R")).read()
+    reg = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(frkb200_\w+)",\s*\(DL_FUNC\)&\w+,\s*(\d+)\}', shim)}
+    assert len(reg) >= 15
+    for name, nargs in reg.items():
+        m = re.search(r"SEXP\s+" + name + r"\s*\(([^)]*)\)", shim)
+        assert m, f"{name} registered but not defined"
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == nargs, f"{name}: {len(params)} parameters, registered with {nargs}"
+
+    def call_args(src, start):           # number of top-level arguments of the call whose '(' is at `start`
+        depth, n, i, any_tok = 0, 0, start, False
+        in_str = None
+        while i < len(src):
+            ch = src[i]
+            if in_str:
+                if ch == "\\":
+                    i += 1
+                elif ch == in_str:
+                    in_str = None
+            elif ch in "\"'":
+                in_str = ch; any_tok = True
+            elif ch == "#":                # R comment: skip to the end of the line
+                while i < len(src) and src[i] != "\n":
+                    i += 1
+            elif ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    return n + (1 if any_tok else 0)
+            elif ch == "," and depth == 1:
+                n += 1
+            elif not ch.isspace():
+                any_tok = True
+            i += 1
+        raise AssertionError("unbalanced call")
+    calls = list(re.finditer(r'\.Call\("(frkb200_\w+)"', over))
+    assert calls
+    for m in calls:
+        name = m.group(1)
+        assert name in reg, f"overlay calls {name}, which the shim does not register"
+        nargs = call_args(over, m.start() + len(".Call")) - 1          # minus the routine name
+        assert nargs == reg[name], f"overlay passes {nargs} arguments to {name}, registered with {reg[name]}"
+    assert 'assignInNamespace(".SRE.predict_EM"' in over and "frkb200_model_predict" in over
+    body = over[over.index(".frkb200_batch_compute_var <- function"):over.index("frkb200_enable <- function")]
+    assert "stop(" not in body, "the default predict() (fs_in_process = TRUE) must not hit a stop()"

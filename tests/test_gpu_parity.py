@@ -13,6 +13,17 @@ from oracle import frk_oracle as O
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
+# sigma2fs / alpha in the heteroscedastic branch are the output of uniroot with tol = eps^0.25 = 1.2e-4 (R/SREfit.R:386): the root
+# itself is only defined to that tolerance, and everything downstream of it inherits a fraction of that slack.
+RTOL_UNIROOT = 1e-7
+
+
+def close(got, ref, rtol=RTOL):
+    """north_star's bar: relative tolerance 1e-9 in fp64 -- relative to the size of the quantity (max |ref|) for vectors and matrices
+    (entries that cancel to ~0 carry no relative information), element-wise for everything bounded away from zero."""
+    ref = np.asarray(ref, dtype=np.float64)
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * float(np.max(np.abs(ref))) if ref.size else 0.0)
+
 
 
 def _mk_basis(F, ob):
@@ -382,16 +393,18 @@ def test_em_fit_and_predict_readme(dev, K_type, hetero):
     O.SRE_fit(Mo, n_EM=n_EM, tol=0.0)
     F.SRE_fit(Mg, n_EM=n_EM, tol=0.0)
     np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
-    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-7 if hetero else RTOL)   # uniroot tol = eps^0.25
-    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=1e-7 if hetero else RTOL)
-    scale = abs(Mo.mu_eta).max()
-    np.testing.assert_allclose(Mg.get("mu_eta"), Mo.mu_eta, rtol=1e-7, atol=1e-9 * scale)
+    tol = RTOL_UNIROOT if hetero else RTOL
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=tol)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=tol)
+    close(Mg.get("mu_eta"), Mo.mu_eta, tol)
+    close(Mg.get("S_eta"), Mo.S_eta, tol)                     # Sigma_eta itself, not only functionals of it
+    close(Mg.get("Khat"), Mo.Khat, max(tol, 1e-8) if K_type == "block-exponential" else tol)   # tau: optim(reltol = 1e-4) end point
     for obs_fs in (True, False):
         po = O.predict(Mo, obs_fs=obs_fs)
         pg = F.predict(Mg, obs_fs=obs_fs)
-        np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-9 * abs(po[0]).max())
-        np.testing.assert_allclose(pg["var"], po[1], rtol=1e-7)
-        np.testing.assert_allclose(pg["sd"], po[2], rtol=1e-7)
+        close(pg["mu"], po[0], tol)
+        np.testing.assert_allclose(pg["var"], po[1], rtol=tol)
+        np.testing.assert_allclose(pg["sd"], po[2], rtol=tol)
 
 
 def test_predict_closed_form_matches_general(dev):
@@ -402,8 +415,8 @@ def test_predict_closed_form_matches_general(dev):
     F.SRE_fit(Mg, n_EM=3, tol=0.0)
     mu, var, sd = O.predict_general(Mo)
     pg = F.predict(Mg, obs_fs=False)
-    np.testing.assert_allclose(pg["var"], var, rtol=1e-7)
-    np.testing.assert_allclose(pg["mu"], mu, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(pg["var"], var, rtol=1e-9)
+    close(pg["mu"], mu, 1e-9)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -450,13 +463,13 @@ def test_config2_airs_sphere(dev, K_type):
     O.SRE_fit(Mo, n_EM=3, tol=0.0)
     F.SRE_fit(Mg, n_EM=3, tol=0.0)
     np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
-    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=1e-6)
-    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-6)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL_UNIROOT)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=RTOL_UNIROOT)
     for obs_fs in (True, False):
         po = O.predict(Mo, obs_fs=obs_fs)
         pg = F.predict(Mg, obs_fs=obs_fs)
-        np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7)
-        np.testing.assert_allclose(pg["var"], po[1], rtol=1e-6)
+        np.testing.assert_allclose(pg["mu"], po[0], rtol=RTOL_UNIROOT)
+        np.testing.assert_allclose(pg["var"], po[1], rtol=RTOL_UNIROOT)
 
 
 def test_config4_noaa_spacetime_tensor_basis(dev):
@@ -492,8 +505,8 @@ def test_config4_noaa_spacetime_tensor_basis(dev):
     np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-8, atol=1e-12)
     po = O.predict(Mo, obs_fs=False)
     pg = F.predict(Mg, obs_fs=False)
-    np.testing.assert_allclose(pg["mu"], po[0], rtol=1e-7, atol=1e-8)
-    np.testing.assert_allclose(pg["var"], po[1], rtol=1e-7)
+    close(pg["mu"], po[0], 1e-9)
+    np.testing.assert_allclose(pg["var"], po[1], rtol=1e-9)
     # block-exponential K for the tensor basis: kronecker(time, space) blocks, 2-D Nelder-Mead per resolution (R/SREfit.R:496-514)
     Mo2 = O.SRE(ot, cen, np.ones(len(cen)), uo, means[:, 0], means[:, 1], K_type="block-exponential")
     # ... and through the space-time BAU container: grid lookup + time slicing on the device instead of the precomputed index

@@ -1,0 +1,236 @@
+"""GPU parity, second file (round 2): the configurations at their STATED size, the M-step corner branches, and the dense kernels at the
+benchmarked r.  Same provenance note as test_gpu_parity.py: the oracle is a CPU restatement of the cited reference lines (no R in this
+image); EM numerics are parity-unpinned by reference-held vectors."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cases import readme_points
+from oracle import frk_oracle as O
+from test_gpu_parity import GOLD, RTOL, RTOL_UNIROOT, _isea3h, _mk_basis, _same_pattern, close
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------------------------------------------------
+# dense kernels at the benchmarked size (C3: r = 3276, finest block 2916) and beyond
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("r", [2916, 3276, 4100])
+def test_chol2inv_at_benchmark_size(dev, r):
+    from frk_b200._lib import call, vp
+    rng = np.random.default_rng(r)
+    A = rng.standard_normal((r, r + 5))
+    A = A @ A.T + r * np.eye(r)
+    Ainv = np.empty_like(A)
+    ld = C.c_double(0)
+    Af = np.asfortranarray(A)
+    call("frk_chol2inv_host", dev.ctx, r, vp(Af.ctypes.data), vp(Ainv.ctypes.data), C.byref(ld))
+    ref = O.chol2inv(O.chol_upper(A))
+    close(Ainv.T, ref, 1e-11)
+    np.testing.assert_allclose(ld.value, np.linalg.slogdet(A)[1], rtol=1e-12)
+    assert np.array_equal(Ainv, Ainv.T)
+
+
+def test_chol2inv_exponential_covariance_2916(dev):
+    """The matrix the block-exponential M-step factorises at C3: exp(-D / tau) for the 54 x 54 centroid grid of resolution 3
+    (R/SREfit.R:503,517-519) -- far worse conditioned than a random Wishart matrix."""
+    from frk_b200._lib import call, vp
+    g = (np.arange(54) + 0.5) / 54
+    X, Y = np.meshgrid(g, g)
+    P = np.column_stack([X.ravel(), Y.ravel()])
+    D = np.sqrt(((P[:, None, :] - P[None, :, :]) ** 2).sum(-1))
+    for tau in (0.02, 0.15):
+        K = np.exp(-D / tau)
+        Kinv = np.empty_like(K)
+        ld = C.c_double(0)
+        call("frk_chol2inv_host", dev.ctx, len(K), vp(np.asfortranarray(K).ctypes.data), vp(Kinv.ctypes.data), C.byref(ld))
+        ref = O.chol2inv(O.chol_upper(K))
+        close(Kinv.T, ref, 1e-9)
+        np.testing.assert_allclose(ld.value, np.linalg.slogdet(K)[1], rtol=1e-10)
+        # what f_tau consumes: tr(K^-1 E) for a PSD E
+        E = np.exp(-D / 0.05) * 0.7
+        np.testing.assert_allclose(np.sum(Kinv.T * E), np.sum(ref * E), rtol=1e-9)
+
+
+def test_block_exponential_iteration_at_r3276(dev):
+    """One-and-a-half EM iterations with the BENCHMARKED basis (auto_basis(plane, nres = 3, regular = 2): r = 3276 = 36 + 324 + 2916)
+    on a problem small enough in m for the oracle: log-likelihood trace, tau, mu_eta, Sigma_eta, K and predictive variances."""
+    import frk_b200 as F
+    xy, z = readme_points(30000, seed=21)
+    std = np.full(len(z), 0.5)
+    ob = O.auto_basis(O.plane(), np.array([[0.0, 0.0], [1.0, 1.0]]), regular=2, nres=3)
+    assert ob.n == 3276
+    ba = O.auto_BAUs_plane(xy, cellsize=1.0 / 299, xlims=(0, 1), ylims=(0, 1))
+    uo, means, _ = O.bin_mean(O.points_to_BAUs(xy, ba), np.column_stack([z, std]))
+    Mo = O.SRE(ob, ba.centroids(), np.ones(ba.n), uo, means[:, 0], means[:, 1], K_type="block-exponential")
+    gb = F.auto_BAUs(F.plane(), cellsize=1.0 / 299, xlims=(0, 1), ylims=(0, 1))
+    gb["fs"] = 1.0
+    Mg = F.SRE("z ~ 1", F.SpatialPointsDataFrame(xy, {"z": z, "std": std}), _mk_basis(F, ob), gb, est_error=False, K_type="block-exponential")
+    assert np.array_equal(dev.download(Mg.obs_bau, Mg.m), Mo.obs_bau) and _same_pattern(Mo.S, Mg.S.to_scipy(dev))
+    O.SRE_fit(Mo, n_EM=2, tol=0.0)
+    F.SRE_fit(Mg, n_EM=2, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.info_fit["tau"], np.concatenate([np.atleast_1d(t) for t in Mo.info_fit["tau"]]), rtol=1e-7)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=RTOL)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL)
+    close(Mg.get("mu_eta"), Mo.mu_eta)
+    close(Mg.get("S_eta"), Mo.S_eta)
+    close(Mg.get("Khat"), Mo.Khat, 1e-7)
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pg = F.predict(Mg, obs_fs=obs_fs)
+        close(pg["mu"], po[0])
+        np.testing.assert_allclose(pg["var"], po[1], rtol=RTOL)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 2 at its stated size
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K_type", ["block-exponential", "unstructured"])
+def test_config2_airs_full_size_hexagon_BAUs(dev, K_type):
+    """BASELINE config 2 as stated: AIRS_05_2003 days 1-3 (all 43,059 soundings; std = co2std -> heteroscedastic / uniroot branch),
+    sphere(), ISEA3H bisquare basis nres = 3 (r = 1176), f = co2avgret ~ lat + 1, BAUs = the reference's own ISEA3H resolution-6
+    hexagons (tests/golden/isea3h_res6_polygons.npz: 7204 of the 7292 cells, the 88 dateline-straddling ones -- split with sf in the
+    reference, BAU construction -- left out).  Point -> hexagon lookup on the device, bit-exact against the restated sp::over."""
+    import frk_b200 as F
+    g = np.load(os.path.join(GOLD, "isea3h_res6_polygons.npz"))
+    a = np.load(os.path.join(GOLD, "airs_days123.npz"))
+    assert len(a["lon"]) == 43059 and len(g["ptr"]) - 1 == 7204
+    ll = np.column_stack([a["lon"], a["lat"]])
+    cen = np.column_stack([g["cx"], g["cy"]])
+    isea = _isea3h()
+    ob = O.auto_basis(O.sphere(), ll, nres=3, isea3h=isea, isea3h_lo=2)
+    assert ob.n == 1176
+    ref = O.points_to_polygon_BAUs(ll, g["ptr"], g["vx"], g["vy"])
+    uo, means, _ = O.bin_mean(ref, np.column_stack([a["co2avgret"], a["co2std"]]))
+    X_BAU = np.column_stack([np.ones(len(cen)), cen[:, 1]])
+    Mo = O.SRE(ob, cen, np.ones(len(cen)), uo, means[:, 0], means[:, 1], X=X_BAU[uo], X_BAU=X_BAU, K_type=K_type)
+    baus = F.PolygonBAUs(cen.copy(), ptr=g["ptr"], vx=g["vx"], vy=g["vy"])
+    baus["fs"] = 1.0
+    baus["lat"] = cen[:, 1]
+    data = F.SpatialPointsDataFrame(ll, {"co2avgret": a["co2avgret"], "std": a["co2std"]})
+    out = F.map_data_to_BAUs(data, baus, ["co2avgret", "std"], dev)
+    assert np.array_equal(dev.download(out["bau"], len(ll)), ref)                      # C_Z: bit-exact
+    Mg = F.SRE("co2avgret ~ lat + 1", data, _mk_basis(F, ob), baus, est_error=False, K_type=K_type)
+    assert np.array_equal(dev.download(Mg.obs_bau, Mg.m), uo) and not Mg.homoscedastic
+    close(Mg.S.to_scipy(dev).toarray(), Mo.S.toarray(), 1e-9)
+    n_EM = 4
+    O.SRE_fit(Mo, n_EM=n_EM, tol=0.0)
+    F.SRE_fit(Mg, n_EM=n_EM, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL_UNIROOT)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=RTOL_UNIROOT)
+    close(Mg.get("mu_eta"), Mo.mu_eta, RTOL_UNIROOT)
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pg = F.predict(Mg, obs_fs=obs_fs)
+        np.testing.assert_allclose(pg["mu"], po[0], rtol=RTOL_UNIROOT)
+        np.testing.assert_allclose(pg["var"], po[1], rtol=RTOL_UNIROOT)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# M-step corner branches (R/SREfit.R:377-384, :424-428) and prediction after sigma2fs = 0
+# ---------------------------------------------------------------------------------------------------------
+def _plane_case(F, m, seed, std, fs=1.0, K_type="unstructured", nres=2, cellsize=0.02):
+    xy, z = readme_points(m, seed)
+    ob = O.auto_basis(O.plane(), xy, regular=1, nres=nres)
+    obaus = O.auto_BAUs_plane(xy, cellsize=cellsize)
+    uo, means, _ = O.bin_mean(O.points_to_BAUs(xy, obaus), np.column_stack([z, std]))
+    fsv = np.full(obaus.n, fs)
+    Mo = O.SRE(ob, obaus.centroids(), fsv, uo, means[:, 0], means[:, 1], K_type=K_type)
+    gb = F.auto_BAUs(F.plane(), cellsize=cellsize, data=F.SpatialPointsDataFrame(xy, {}))
+    gb["fs"] = fs
+    Mg = F.SRE("z ~ 1", F.SpatialPointsDataFrame(xy, {"z": z, "std": std}), _mk_basis(F, ob), gb, est_error=False, K_type=K_type)
+    return Mo, Mg
+
+
+@pytest.mark.parametrize("K_type", ["unstructured", "block-exponential"])
+def test_mstep_no_fine_scale_branch(dev, K_type):
+    """all(Vfs == 0) (BAUs$fs = 0): alpha by GLS with D = Ve, sigma2fs <- 0 (R/SREfit.R:424-428); predict then takes the
+    sigma2fs == 0 path (R/SREpredict.R:334-361) for both values of obs_fs."""
+    import frk_b200 as F
+    std = 0.3 + 0.4 * np.random.default_rng(7).uniform(size=1200)          # heteroscedastic Ve: the GLS weights matter
+    Mo, Mg = _plane_case(F, 1200, 31, std, fs=0.0, K_type=K_type)
+    O.SRE_fit(Mo, n_EM=4, tol=0.0)
+    F.SRE_fit(Mg, n_EM=4, tol=0.0)
+    assert Mg.sigma2fshat == 0.0 == Mo.sigma2fshat and Mg.info_fit["sigma2fshat_equal_0"] == 1
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL)
+    close(Mg.get("mu_eta"), Mo.mu_eta)
+    close(Mg.get("S_eta"), Mo.S_eta)
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pg = F.predict(Mg, obs_fs=obs_fs)
+        close(pg["mu"], po[0])
+        np.testing.assert_allclose(pg["var"], po[1], rtol=RTOL)
+
+
+def test_mstep_bracket_give_up_sets_sigma2fs_to_zero(dev):
+    """Heteroscedastic branch where J(sigma2fs) never changes sign (the stated measurement error already exceeds the residual
+    variance): the bracket search runs to amp > 1e9 and gives up with sigma2fs <- 0 (R/SREfit.R:368-384); the fit continues and
+    predict(obs_fs = FALSE) runs with sigma2fshat = 0 (tests/testthat/test_sre_polygon_predict.R:51-55 does the same by assignment)."""
+    import frk_b200 as F
+    std = 1.5 + 1.0 * np.random.default_rng(9).uniform(size=1500)           # noise in z is 0.5
+    Mo, Mg = _plane_case(F, 1500, 33, std, K_type="unstructured")
+    assert not Mg.homoscedastic
+    O.SRE_fit(Mo, n_EM=4, tol=0.0)
+    F.SRE_fit(Mg, n_EM=4, tol=0.0)
+    assert Mo.sigma2fshat == 0.0, "the case is meant to hit the give-up branch"
+    assert Mg.sigma2fshat == 0.0 and Mg.info_fit["sigma2fshat_equal_0"] == 1
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL)
+    close(Mg.get("mu_eta"), Mo.mu_eta)
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pg = F.predict(Mg, obs_fs=obs_fs)
+        close(pg["mu"], po[0])
+        np.testing.assert_allclose(pg["var"], po[1], rtol=RTOL)
+
+
+def test_predict_after_assigning_sigma2fs_zero(dev):
+    """tests/testthat/test_sre_polygon_predict.R:51-55: S@sigma2fshat <- 0 after the fit, then predict."""
+    import frk_b200 as F
+    Mo, Mg = _plane_case(F, 1000, 1, np.full(1000, 0.5), K_type="block-exponential")
+    O.SRE_fit(Mo, n_EM=3, tol=0.0)
+    F.SRE_fit(Mg, n_EM=3, tol=0.0)
+    Mo.sigma2fshat = 0.0
+    Mg.set("sigma2fshat", [0.0])
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pg = F.predict(Mg, obs_fs=obs_fs)
+        close(pg["mu"], po[0])
+        np.testing.assert_allclose(pg["var"], po[1], rtol=RTOL)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the host-buffer predict entry point the R shim binds (frkb200_model_predict -> frk_model_predict_host)
+# ---------------------------------------------------------------------------------------------------------
+def test_predict_host_entry_point_matches_device_predict(dev):
+    """.SRE.predict_EM through the entry point of the R overlay: S0 / X_BAU / fs / obs_bau as HOST arrays (what object@S0, the BAU
+    data frame and object@Cmat hold in R) give the same mu / var / sd as the device-resident predict and the oracle."""
+    import frk_b200 as F
+    from frk_b200._lib import call, vp
+    Mo, Mg = _plane_case(F, 1500, 41, 0.3 + 0.4 * np.random.default_rng(5).uniform(size=1500), K_type="block-exponential")
+    O.SRE_fit(Mo, n_EM=3, tol=0.0)
+    F.SRE_fit(Mg, n_EM=3, tol=0.0)
+    S0 = Mg.S0.to_scipy(dev).tocsr()
+    S0.sort_indices()
+    n = S0.shape[0]
+    rp, cj, x = S0.indptr.astype(np.int32), S0.indices.astype(np.int32), S0.data.astype(np.float64)
+    X = np.ones(n)
+    fs = np.ones(n)
+    ob = np.ascontiguousarray(dev.download(Mg.obs_bau, Mg.m), dtype=np.int32)
+    for obs_fs in (0, 1):
+        mu, var, sd = np.empty(n), np.empty(n), np.empty(n)
+        call("frk_model_predict_host", Mg.handle, n, vp(rp.ctypes.data), vp(cj.ctypes.data), vp(x.ctypes.data), vp(X.ctypes.data),
+             vp(fs.ctypes.data), vp(ob.ctypes.data), vp(None), vp(None), vp(None), obs_fs, 0, vp(None), vp(None), vp(None),
+             vp(mu.ctypes.data), vp(var.ctypes.data), vp(sd.ctypes.data))
+        pg = F.predict(Mg, obs_fs=bool(obs_fs))
+        np.testing.assert_array_equal(mu, pg["mu"])
+        np.testing.assert_array_equal(var, pg["var"])
+        po = O.predict(Mo, obs_fs=bool(obs_fs))
+        close(mu, po[0], RTOL_UNIROOT)
+        np.testing.assert_allclose(var, po[1], rtol=RTOL_UNIROOT)
+        np.testing.assert_allclose(sd, np.sqrt(po[1]), rtol=RTOL_UNIROOT)
