@@ -532,6 +532,300 @@ __global__ void __launch_bounds__(BLK_T) trsm_rows_kernel(const double *__restri
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Panel Cholesky, second generation: 128-wide panels, THREE kernels on the critical path per panel instead of eight.
+//   D  diag128_kernel        one CTA factors the 128 x 128 diagonal block entirely in shared memory:
+//                            potf2(64) -> 64-row triangular solve -> rank-64 update -> potf2(64)
+//   S  panel_solve128_kernel rows below the block, 64 rows per CTA, four lanes per row: X0 = P0 L00^-T by substitution,
+//                            P1 -= X0 L10' in registers (the row's X0 is exchanged by shuffles), X1 = P1 L11^-T
+//   U  dgemm_kernel          the next panel's 128 columns take their rank-128 update (critical path)
+//   R  dgemm_kernel          everything beyond the next panel (lower SYRK, rank 128) on a low-priority side stream,
+//                            overlapping the next panel's D and S
+// The column-sequential work (two 64 x 64 factorisations) stays what it was; what goes away are five of the eight dependent
+// launches per 128 columns, each of which re-loaded its operands from L2 and paid a launch gap.
+// ---------------------------------------------------------------------------------
+constexpr int DP = 128;                       // panel width
+constexpr int DLD = DP + 1;                   // row stride of the block in shared memory (odd: the 4 lanes of a row / 16 rows of a warp spread over banks)
+constexpr size_t DIAG_SMEM = (size_t)DP * DLD * sizeof(double);
+
+// Cholesky of the 64 x 64 block a[o .. o+64)[o .. o+64) held in shared memory (row i at a + i * DLD), in place, lower triangle.
+// Same algorithm as potf2_kernel: four 16-column steps; the 16 x 16 diagonal sub-block is factored by warp 0 in registers with
+// shuffles, the rows below it are solved one thread per row, the rest of the block is updated by all 256 threads.
+// Returns (uniformly) 0 or the 1-based column (within the 64) of the first non-positive pivot.
+__device__ __forceinline__ int potf2_64_smem(double *__restrict__ a, int o, double (*ld)[PB + 1], double *rdg, int *sbad) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#define A_(i, k) a[(size_t)(o + (i)) * DLD + o + (k)]
+    for (int J = 0; J < NB; J += PB) {
+        if (wid == 0) {
+            const int i = lane & (PB - 1);
+            double d[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) d[k] = A_(J + i, J + k);
+            int bad = 0;
+#pragma unroll
+            for (int j = 0; j < PB; j++) {
+                const double piv = __shfl_sync(0xffffffffu, d[j], j);
+                if (!(piv > 0.0)) { if (!bad) bad = J + j + 1; }
+                const double rs = rsqrt(piv);
+                const double lij = (i == j) ? piv * rs : d[j] * rs;
+                d[j] = lij;
+#pragma unroll
+                for (int k = j + 1; k < PB; k++) d[k] -= lij * __shfl_sync(0xffffffffu, lij, k);
+            }
+            if (lane < PB) {
+#pragma unroll
+                for (int k = 0; k < PB; k++) { ld[i][k] = (k <= i) ? d[k] : 0.0; A_(J + i, J + k) = (k <= i) ? d[k] : 0.0; }
+                double dii = 1.0;
+#pragma unroll
+                for (int k = 0; k < PB; k++) dii = (k == i) ? d[k] : dii;
+                rdg[i] = 1.0 / dii;
+            }
+            if (lane == 0 && bad) *sbad = bad;
+        }
+        __syncthreads();
+        if (*sbad) break;
+        const int nbelow = NB - J - PB;
+        if (nbelow <= 0) break;
+        if (tid < nbelow) {
+            const int row = J + PB + tid;
+            double x[PB];
+#pragma unroll
+            for (int c = 0; c < PB; c++) x[c] = A_(row, J + c);
+#pragma unroll
+            for (int c = 0; c < PB; c++) {
+                const double xc = x[c] * rdg[c];
+                x[c] = xc;
+#pragma unroll
+                for (int k = c + 1; k < PB; k++) x[k] -= xc * ld[k][c];
+            }
+#pragma unroll
+            for (int c = 0; c < PB; c++) A_(row, J + c) = x[c];
+        }
+        __syncthreads();
+        {
+            const int ty = tid >> 4, tx = tid & 15, base = J + PB, nt = nbelow / PB;
+            double acc[3][3];
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) acc[ii][kk] = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < PB; c++) {
+                double xi[3], xk[3];
+#pragma unroll
+                for (int ii = 0; ii < 3; ii++) xi[ii] = ii < nt ? A_(base + ty + PB * ii, J + c) : 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) xk[kk] = kk < nt ? A_(base + tx + PB * kk, J + c) : 0.0;
+#pragma unroll
+                for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                    for (int kk = 0; kk < 3; kk++) acc[ii][kk] += xi[ii] * xk[kk];
+            }
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) {
+                    const int i = base + ty + PB * ii, k = base + tx + PB * kk;
+                    if (ii < nt && kk < nt && k <= i) A_(i, k) -= acc[ii][kk];
+                }
+        }
+        __syncthreads();
+    }
+#undef A_
+    return *sbad;
+}
+
+// D: Cholesky of the nb x nb (nb <= 128) diagonal block at A, in place (lower triangle).
+// status[0] += sum(log(diag L)); status[1] = first failing (1-based, global) column, untouched if ok.
+__global__ void __launch_bounds__(BLK_T) diag128_kernel(double *__restrict__ A, int lda, int nb, int col_offset, double *__restrict__ status) {
+    extern __shared__ __align__(16) double dsm[];
+    double *a = dsm;                                   // a[i * DLD + k]
+    __shared__ double ld[PB][PB + 1];
+    __shared__ double rdg[PB];
+    __shared__ double rd[NB];
+    __shared__ int sbad;
+    __shared__ double slog[BLK_T / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) sbad = 0;
+    // load the lower triangle (identity padding beyond nb): a column of the block is contiguous in global memory; 16 loads in flight per thread
+    for (int q0 = 0; q0 < DP * DP / BLK_T; q0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int idx = tid + (q0 + q) * BLK_T, i = idx % DP, k = idx / DP;
+            v[q] = (i < nb && k < nb && k <= i) ? A[i + (size_t)k * lda] : (i == k ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int idx = tid + (q0 + q) * BLK_T, i = idx % DP, k = idx / DP;
+            a[(size_t)i * DLD + k] = v[q];
+        }
+    }
+    __syncthreads();
+    int bad = potf2_64_smem(a, 0, ld, rdg, &sbad);
+    if (!bad && nb > NB) {
+        // rows 64..127: X = A10 L00^-T (four lanes per row, right-looking substitution; the lanes of a row own the columns c = 4 kk + h)
+        if (tid < NB) rd[tid] = __drcp_rn(a[(size_t)tid * DLD + tid]);
+        __syncthreads();
+        {
+            const int t = tid / SPLIT, h = tid % SPLIT, lane_base = lane & ~(SPLIT - 1);
+            double *xr = a + (size_t)(NB + t) * DLD;
+            double x[NBQ];
+#pragma unroll
+            for (int kk = 0; kk < NBQ; kk++) x[kk] = xr[kk * SPLIT + h];
+#pragma unroll
+            for (int cc = 0; cc < NBQ; cc++) {
+#pragma unroll 1
+                for (int hh = 0; hh < SPLIT; hh++) {
+                    const int c = cc * SPLIT + hh;
+                    double xc = x[cc] * rd[c];
+                    if (h == hh) x[cc] = xc;
+                    xc = __shfl_sync(0xffffffffu, xc, lane_base + hh);
+                    const double *lc = a + c;                                   // L00[k][c] = a[k * DLD + c]
+                    if (h > hh) x[cc] -= xc * lc[(size_t)(cc * SPLIT + h) * DLD];
+#pragma unroll
+                    for (int kk = cc + 1; kk < NBQ; kk++) x[kk] -= xc * lc[(size_t)(kk * SPLIT + h) * DLD];
+                }
+            }
+            __syncthreads();                                                    // (everybody has read its row before anybody writes -- rows are private, but keep the phases apart)
+#pragma unroll
+            for (int kk = 0; kk < NBQ; kk++) xr[kk * SPLIT + h] = x[kk];
+        }
+        __syncthreads();
+        // A11 -= X X' (lower): 16 x 16 threads, rows ty + 16 ii, columns tx + 16 kk
+        {
+            const int ty = tid >> 4, tx = tid & 15;
+            double acc[4][4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) acc[ii][kk] = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < NB; c++) {
+                double xi[4], xk[4];
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++) xi[ii] = a[(size_t)(NB + ty + 16 * ii) * DLD + c];
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) xk[kk] = a[(size_t)(NB + tx + 16 * kk) * DLD + c];
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) acc[ii][kk] += xi[ii] * xk[kk];
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const int i = NB + ty + 16 * ii, k = NB + tx + 16 * kk;
+                    if (k <= i) a[(size_t)i * DLD + k] -= acc[ii][kk];
+                }
+        }
+        __syncthreads();
+        bad = potf2_64_smem(a, NB, ld, rdg, &sbad);
+        if (bad) bad += NB;
+    }
+    if (bad) {
+        if (tid == 0 && status[1] == 0.0) status[1] = (double)(col_offset + bad);
+        return;
+    }
+    for (int idx = tid; idx < DP * DP; idx += BLK_T) {
+        const int i = idx % DP, k = idx / DP;
+        if (i < nb && k < nb && k <= i) A[i + (size_t)k * lda] = a[(size_t)i * DLD + k];
+    }
+    double lg = tid < nb ? log(a[(size_t)tid * DLD + tid]) : 0.0;             // (BLK_T = 256 >= 128 diagonal entries)
+    lg = warp_sum(lg);
+    if (lane == 0) slog[wid] = lg;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < BLK_T / 32; w++) s += slog[w];
+        status[0] += s;
+    }
+}
+
+// S: the rows below a factored 128 x 128 diagonal block.  P (Mp x 128, column-major, ldp) <- P L^-T with L = [L00 0; L10 L11]:
+//   X0 = P0 L00^-T;  P1 -= X0 L10';  X1 = P1 L11^-T.   64 rows per CTA, four lanes per row (lane h owns the columns 4 kk + h of
+// each half: 2 x 16 registers).  The three 64 x 64 blocks of L are staged transposed in shared memory (Lt[c][k] = L[k][c]) so that the
+// four lanes of a row read four consecutive doubles and all rows of a warp read the same address.
+constexpr int SLD = NB + 4;
+constexpr size_t SOLVE_SMEM = (size_t)3 * NB * SLD * sizeof(double);
+__global__ void __launch_bounds__(BLK_T) panel_solve128_kernel(const double *__restrict__ L, int ldl, double *__restrict__ P, int ldp, int Mp) {
+    extern __shared__ __align__(16) double ssm[];
+    double *Lt0 = ssm, *Lt1 = ssm + NB * SLD, *Ct = ssm + 2 * NB * SLD;        // Lt0[c][k] = L00[k][c], Lt1 = L11 likewise, Ct[k][c] = L10[c][k]
+    __shared__ double rd0[NB], rd1[NB];
+    const int tid = threadIdx.x;
+    for (int q0 = 0; q0 < NB * NB / BLK_T; q0 += 8) {                          // 3 x 8 loads in flight per thread
+        double v0[8], v1[8], v2[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int idx = tid + (q0 + q) * BLK_T, k = idx % NB, c = idx / NB; // element (row k, column c) of each block: k contiguous in global memory
+            v0[q] = (c <= k) ? L[k + (size_t)c * ldl] : 0.0;
+            v1[q] = (c <= k) ? L[(NB + k) + (size_t)(NB + c) * ldl] : 0.0;
+            v2[q] = L[(NB + k) + (size_t)c * ldl];                             // L10[k][c]
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int idx = tid + (q0 + q) * BLK_T, k = idx % NB, c = idx / NB;
+            Lt0[c * SLD + k] = v0[q];
+            Lt1[c * SLD + k] = v1[q];
+            Ct[c * SLD + k] = v2[q];                                           // Ct[c][k] = L10[k][c]: row c of Ct holds column c of L10
+            if (k == c) { rd0[c] = __drcp_rn(v0[q]); rd1[c] = __drcp_rn(v1[q]); }
+        }
+    }
+    const int t = tid / SPLIT, h = tid % SPLIT, lane_base = (tid & 31) & ~(SPLIT - 1);
+    const int row = blockIdx.x * NB + t;
+    const bool live = row < Mp;
+    double x[NBQ], y[NBQ];
+#pragma unroll
+    for (int kk = 0; kk < NBQ; kk++) {
+        const int c = kk * SPLIT + h;
+        x[kk] = live ? P[row + (size_t)c * ldp] : 0.0;
+        y[kk] = live ? P[row + (size_t)(NB + c) * ldp] : 0.0;
+    }
+    __syncthreads();
+    // X0 = P0 L00^-T and, column by column, P1 -= x_c * L10[:, c]
+#pragma unroll
+    for (int cc = 0; cc < NBQ; cc++) {
+#pragma unroll 1
+        for (int hh = 0; hh < SPLIT; hh++) {
+            const int c = cc * SPLIT + hh;
+            double xc = x[cc] * rd0[c];
+            if (h == hh) x[cc] = xc;
+            xc = __shfl_sync(0xffffffffu, xc, lane_base + hh);
+            const double *lt = Lt0 + c * SLD + h;
+            if (h > hh) x[cc] -= xc * lt[cc * SPLIT];
+#pragma unroll
+            for (int kk = cc + 1; kk < NBQ; kk++) x[kk] -= xc * lt[kk * SPLIT];
+            const double *ct = Ct + c * SLD + h;                                // L10[4 kk + h][c]
+#pragma unroll
+            for (int kk = 0; kk < NBQ; kk++) y[kk] -= xc * ct[kk * SPLIT];
+        }
+    }
+    // X1 = P1 L11^-T
+#pragma unroll
+    for (int cc = 0; cc < NBQ; cc++) {
+#pragma unroll 1
+        for (int hh = 0; hh < SPLIT; hh++) {
+            const int c = cc * SPLIT + hh;
+            double yc = y[cc] * rd1[c];
+            if (h == hh) y[cc] = yc;
+            yc = __shfl_sync(0xffffffffu, yc, lane_base + hh);
+            const double *lt = Lt1 + c * SLD + h;
+            if (h > hh) y[cc] -= yc * lt[cc * SPLIT];
+#pragma unroll
+            for (int kk = cc + 1; kk < NBQ; kk++) y[kk] -= yc * lt[kk * SPLIT];
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int kk = 0; kk < NBQ; kk++) {
+            const int c = kk * SPLIT + h;
+            P[row + (size_t)c * ldp] = x[kk];
+            P[row + (size_t)(NB + c) * ldp] = y[kk];
+        }
+    }
+}
+
 // mirror: A[j,i] = A[i,j] for i > j (32x32 tiles through shared memory, coalesced both ways)
 __global__ void __launch_bounds__(256) mirror_lower_kernel(int r, double *__restrict__ A) {
     __shared__ double t[32][33];
@@ -559,6 +853,8 @@ static int gemm_set_attrs() {
     FRK_GEMM_ATTR(true, false, true); FRK_GEMM_ATTR(true, false, false); FRK_GEMM_ATTR(true, true, true); FRK_GEMM_ATTR(true, true, false);
 #undef FRK_GEMM_ATTR
     FRK_CHECK_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
+    FRK_CHECK_CUDA(cudaFuncSetAttribute(diag128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+    FRK_CHECK_CUDA(cudaFuncSetAttribute(panel_solve128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     done = true;
     return 0;
 }
@@ -696,13 +992,73 @@ static int potrf_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
     return 0;
 }
 
+// Launch sequence of the 128-wide panel Cholesky (see diag128_kernel).  Per panel p (columns J .. J+128):
+//   main : D(p) -> S(p) -> [wait R(p-1)] -> U(p): columns of panel p+1, rows >= J+128
+//   side : [wait S(p)] R(p): rows and columns >= J+256 (lower SYRK, rank 128); R(p) runs beside D(p+1), S(p+1).
+// U(p+1) and R(p) update overlapping regions (columns of panel p+2), hence the wait; everything else that runs concurrently
+// touches disjoint blocks.  Replayed as one CUDA graph with two branches.
+static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
+    FRK_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(double), ctx->stream));
+    const size_t ld = (size_t)r;
+    cudaStream_t main = ctx->stream, side = ctx->stream3;
+    const bool fork = main != nullptr && side != nullptr;
+    bool have_rest[2] = {false, false};
+    int pidx = 0;
+    for (int J = 0; J < r; J += DP, pidx++) {
+        const int nb = std::min(DP, r - J), below = r - J - nb;
+        FRK_WORK(ctx, (double)nb * nb * nb / 3.0, 0);
+        FRK_LAUNCH(ctx, diag128_kernel, 1, BLK_T, DIAG_SMEM, d_A + J + J * ld, r, nb, J, status);
+        if (below <= 0) break;
+        double *P = d_A + (J + nb) + J * ld;                           // below x 128
+        FRK_WORK(ctx, (double)below * nb * nb, 0);
+        FRK_LAUNCH(ctx, panel_solve128_kernel, (unsigned)cdiv(below, NB), BLK_T, SOLVE_SMEM, (const double *)(d_A + J + J * ld), r, P, r, below);
+        const int npan = std::min(DP, below), beyond = below - npan;
+        if (!fork) {                                                   // sequential: one lower SYRK over everything below
+            GemmArgs g = gemm_args(below, below, nb, -1.0, P, r, P, r, 1.0, d_A + (J + nb) + (J + nb) * ld, r);
+            g.lower = 1;
+            if (int rc = launch_gemm(ctx, g, false, false, (double)below * (below + 1.0) * nb, "dgemm_kernel[potrf trailing SYRK]")) return rc;
+            continue;
+        }
+        if (beyond > 0) {                                              // R(p) on the side stream
+            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_panel, main));
+            FRK_CHECK_CUDA(cudaStreamWaitEvent(side, ctx->ev_panel, 0));
+            const double *P2 = P + npan;
+            GemmArgs g = gemm_args(beyond, beyond, nb, -1.0, P2, r, P2, r, 1.0, d_A + (J + nb + npan) + (J + nb + npan) * ld, r);
+            g.lower = 1;
+            ctx->stream = side;
+            const int rc = launch_gemm(ctx, g, false, false, (double)beyond * (beyond + 1.0) * nb, "dgemm_kernel[potrf trailing SYRK]");
+            ctx->stream = main;
+            if (rc) return rc;
+            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_rest[pidx & 1], side));
+        }
+        if (have_rest[(pidx + 1) & 1]) FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_rest[(pidx + 1) & 1], 0));   // R(p-1) reached these columns
+        have_rest[pidx & 1] = beyond > 0;
+        {   // U(p): next panel's columns, rows >= J+nb (lower part: the diagonal starts at the block's origin)
+            GemmArgs g = gemm_args(below, npan, nb, -1.0, P, r, P, r, 1.0, d_A + (J + nb) + (J + nb) * ld, r);
+            g.lower = 1;
+            if (int rc = launch_gemm(ctx, g, false, false, 2.0 * below * npan * nb - (double)npan * npan * nb, "dgemm_kernel[potrf next-panel update]")) return rc;
+        }
+    }
+    if (fork)
+        for (int i = 0; i < 2; i++)
+            if (have_rest[i]) FRK_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_rest[i], 0));
+    return 0;
+}
+
+// FRK_POTRF_V1=1 selects the first-generation launch sequence (64-wide steps, look-ahead on three branches) for A/B timing
+static bool potrf_use_v1() {
+    static const bool v1 = getenv("FRK_POTRF_V1") != nullptr;
+    return v1;
+}
+
 // enqueue only: factor + {sum log diag, first bad column} -> ctx->h_pinned[4088..4089]; read them with frk_potrf_finish once the
 // stream has been synchronised (lets several contexts factorise side by side from one host thread)
 int frk_potrf_async(frk_ctx *ctx, int r, double *d_A) {
     FRK_REQUIRE(ctx && d_A && r > 0, "frk_potrf: bad argument");
     double *status = ctx->d_small + 4096 - 8;
     if (int rc = gemm_set_attrs()) return rc;
-    if (int rc = run_graphed(ctx, {1, (uintptr_t)r, (uintptr_t)d_A, 0, 0}, [&]() { return potrf_enqueue(ctx, r, d_A, status); })) return rc;
+    if (int rc = run_graphed(ctx, {1, (uintptr_t)r, (uintptr_t)d_A, 0, 0},
+                             [&]() { return potrf_use_v1() ? potrf_enqueue(ctx, r, d_A, status) : potrf2_enqueue(ctx, r, d_A, status); })) return rc;
     FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned + 4096 - 8, status, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
@@ -891,11 +1247,18 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(int64_t n, const doubl
     }
 }
 
-__global__ void dot_final_kernel(int nblocks, const double *__restrict__ part, double *__restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double v = 0;
-        for (int b = 0; b < nblocks; b++) v += part[b];
-        *out = v;
+// fixed-order tree over <= 1024 partial sums: 256 threads take 4 each (stride 256), then warp / block reduction
+__global__ void __launch_bounds__(256) dot_final_kernel(int nblocks, const double *__restrict__ part, double *__restrict__ out) {
+    __shared__ double sh[8];
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) v += part[b];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sh[w];
+        *out = t;
     }
 }
 
@@ -906,7 +1269,7 @@ int frk_dot_async(frk_ctx *ctx, int64_t n, const double *d_A, const double *d_B)
     const int nblocks = (int)std::min<int64_t>(cdiv(n, 256), 1024);
     double *part = ctx->d_small, *out = ctx->d_small + 2048;
     FRK_LAUNCH(ctx, dot_partial_kernel, nblocks, 256, 0, n, d_A, d_B, part);
-    FRK_LAUNCH(ctx, dot_final_kernel, 1, 32, 0, nblocks, part, out);
+    FRK_LAUNCH(ctx, dot_final_kernel, 1, 256, 0, nblocks, part, out);
     FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned + 4080, out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
@@ -1039,7 +1402,7 @@ extern "C" int frk_kron_dot(frk_ctx *ctx, int nt, int ns, const double *d_At, co
     const int nblocks = (int)std::min<int64_t>(cdiv(nn, 256), 1024);
     double *part = ctx->d_small, *out = ctx->d_small + 2048;
     FRK_LAUNCH(ctx, kron_dot_partial_kernel, nblocks, 256, 0, nt, ns, d_At, d_As, d_E, part);
-    FRK_LAUNCH(ctx, dot_final_kernel, 1, 32, 0, nblocks, part, out);
+    FRK_LAUNCH(ctx, dot_final_kernel, 1, 256, 0, nblocks, part, out);
     FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned, out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     *h_out = ctx->h_pinned[0];

@@ -45,7 +45,8 @@ def test_chol2inv_exponential_covariance_2916(dev):
         K = np.exp(-D / tau)
         Kinv = np.empty_like(K)
         ld = C.c_double(0)
-        call("frk_chol2inv_host", dev.ctx, len(K), vp(np.asfortranarray(K).ctypes.data), vp(Kinv.ctypes.data), C.byref(ld))
+        Kf = np.asfortranarray(K)                       # (keep the array alive across the call)
+        call("frk_chol2inv_host", dev.ctx, len(K), vp(Kf.ctypes.data), vp(Kinv.ctypes.data), C.byref(ld))
         ref = O.chol2inv(O.chol_upper(K))
         close(Kinv.T, ref, 1e-9)
         np.testing.assert_allclose(ld.value, np.linalg.slogdet(K)[1], rtol=1e-10)
