@@ -52,6 +52,7 @@ extern "C" int frk_ctx_create(int device, void *stream, frk_ctx **out) {
     FRK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_rest[1], cudaEventDisableTiming));
     FRK_CHECK_CUDA(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
     FRK_CHECK_CUDA(cudaMalloc((void **)&c->d_small, 4096 * sizeof(double)));
+    FRK_CHECK_CUDA(cudaMalloc((void **)&c->d_winv, 2 * 64 * 64 * sizeof(double)));
     *out = c;
     return 0;
 }
@@ -105,6 +106,7 @@ extern "C" int frk_ctx_destroy(frk_ctx *ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_small) cudaFree(ctx->d_small);
+    if (ctx->d_winv) cudaFree(ctx->d_winv);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -533,121 +533,237 @@ __global__ void __launch_bounds__(BLK_T) trsm_rows_kernel(const double *__restri
 }
 
 // ---------------------------------------------------------------------------------
-// Panel Cholesky, second generation: 128-wide panels, THREE kernels on the critical path per panel instead of eight.
+// Panel Cholesky, second generation: 128-wide panels, TWO or three kernels on the critical path per panel instead of eight.
 //   D  diag128_kernel        one CTA factors the 128 x 128 diagonal block entirely in shared memory:
-//                            potf2(64) -> 64-row triangular solve -> rank-64 update -> potf2(64)
-//   S  panel_solve128_kernel rows below the block, 64 rows per CTA, four lanes per row: X0 = P0 L00^-T by substitution,
-//                            P1 -= X0 L10' in registers (the row's X0 is exchanged by shuffles), X1 = P1 L11^-T
-//   U  dgemm_kernel          the next panel's 128 columns take their rank-128 update (critical path)
-//   R  dgemm_kernel          everything beyond the next panel (lower SYRK, rank 128) on a low-priority side stream,
-//                            overlapping the next panel's D and S
-// The column-sequential work (two 64 x 64 factorisations) stays what it was; what goes away are five of the eight dependent
-// launches per 128 columns, each of which re-loaded its operands from L2 and paid a launch gap.
+//                            potf2(64) -> W00 = L00^-1 -> L10 = A10 W00' -> A11 -= L10 L10' -> potf2(64) -> W11 = L11^-1
+//   S  panel_solve128_kernel rows below the block, 64 rows per CTA:  X0 = P0 W00';  P1 -= X0 L10';  X1 = P1 W11'
+//   U  dgemm_kernel          the next diagonal block takes its rank-128 update (critical path); the rest of the next panel's
+//                            columns on a side stream beside D of the next panel
+//   R  dgemm_kernel          everything beyond the next panel (lower SYRK, rank 128) on a low-priority side stream
+// Only the 16 x 16 diagonal sub-blocks are factored column by column (one warp, registers + shuffles).  Everything else --
+// including the triangular solves, which are products with explicit inverses of 16 x 16 / 64 x 64 triangular blocks -- is a
+// small dense product on the fp64 tensor cores (DMMA m8n8k4) with both operands in shared memory.  Measured before this
+// formulation: the substitution loops were bound by shared-memory bandwidth (one LDS per FMA), 26 us for the panel solve.
 // ---------------------------------------------------------------------------------
-constexpr int DP = 128;                       // panel width
-constexpr int DLD = DP + 1;                   // row stride of the block in shared memory (odd: the 4 lanes of a row / 16 rows of a warp spread over banks)
-constexpr size_t DIAG_SMEM = (size_t)DP * DLD * sizeof(double);
+// phase timestamps of the last diag / panel-solve launch (clock64 of CTA 0, thread 0): tools/dense_phase_probe.py
+__device__ long long g_dbg_clk[32];
+#define DBG_CLK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_dbg_clk[slot] = clock64(); } while (0)
+extern "C" int frk_debug_clocks(long long *h_out32) {
+    FRK_CHECK_CUDA(cudaDeviceSynchronize());
+    FRK_CHECK_CUDA(cudaMemcpyFromSymbol(h_out32, g_dbg_clk, sizeof(long long) * 32));
+    return 0;
+}
 
-// Cholesky of the 64 x 64 block a[o .. o+64)[o .. o+64) held in shared memory (row i at a + i * DLD), in place, lower triangle.
-// Same algorithm as potf2_kernel: four 16-column steps; the 16 x 16 diagonal sub-block is factored by warp 0 in registers with
-// shuffles, the rows below it are solved one thread per row, the rest of the block is updated by all 256 threads.
+constexpr int DP = 128;                       // panel width
+// All blocks live COLUMN-MAJOR in shared memory: element (i, j) at j * LD + i, with LD = 4 (mod 16) doubles.  With that stride the
+// 32 addresses of a DMMA fragment load -- 8 consecutive (g) in one direction, 4 strided (tg) in the other, whichever operand and
+// orientation -- fall on every 8-byte bank pair exactly twice: two wavefronts, the minimum for 256 bytes.
+constexpr int MLD = DP + 4;                   // 132: the 128 x 128 diagonal block
+constexpr int WLD = NB + 4;                   // 68:  64-row blocks
+constexpr int NWARP = BLK_T / 32;
+
+// 1 / sqrt(x) without a branch, so that the compiler can interleave it with independent work: the hardware approximation
+// (MUFU.RSQ64H, ~2^-22) followed by ONE third-order step  y (1 + e/2 + 3 e^2 / 8),  e = 1 - x y^2  (remaining error ~ e^3 ~ 2^-66).
+// Valid for normal positive x; callers treat pivots that are not > 1e-290 as "not positive definite" before using the result.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
+}
+
+// Cholesky of a 16 x 16 block by one warp: lane (& 15) = row, d[k] = a[row][k] in registers, columns exchanged by shuffles.
+// The column-sequential chain is  rsqrt(pivot_j) -> l_{j+1,j} -> pivot_{j+1} -> rsqrt(pivot_{j+1}):  every lane computes the NEXT
+// pivot itself from two values of row j+1 fetched before column j is scaled, so the reciprocal square root of column j+1 is in
+// flight while the rank-1 update of column j (15 shuffles + 15 FMAs) is still being applied.  The next-pivot expression is the same
+// fma the owner lane applies, so the value is identical to the one the plain right-looking loop would produce.
+// rdiag (if given) receives 1 / L[j][j].  Returns 0 or the (1-based) index of the first pivot that is not > 1e-290 (also catches NaN).
+__device__ __forceinline__ int warp_potf2_16(double d[PB], int i, double *rdiag) {
+    int bad = 0;
+    double piv = __shfl_sync(0xffffffffu, d[0], 0);
+    double rs = rsqrt_fast(piv);
+#pragma unroll
+    for (int j = 0; j < PB; j++) {
+        if (!(piv > 1e-290)) { if (!bad) bad = j + 1; }
+        double piv_next = 1.0, rs_next = 1.0;
+        if (j + 1 < PB) {
+            const double t1 = __shfl_sync(0xffffffffu, d[j], j + 1);          // a_{j+1,j} and a_{j+1,j+1}, updated through column j-1
+            const double t2 = __shfl_sync(0xffffffffu, d[j + 1 < PB ? j + 1 : j], j + 1);
+            const double l = t1 * rs;
+            piv_next = fma(-l, l, t2);
+            rs_next = rsqrt_fast(piv_next);
+        }
+        if (rdiag && i == j) rdiag[j] = rs;
+        const double lij = (i == j) ? piv * rs : d[j] * rs;
+        d[j] = lij;
+#pragma unroll
+        for (int k = j + 1; k < PB; k++) d[k] = fma(-lij, __shfl_sync(0xffffffffu, lij, k), d[k]);   // entries with k > i are never used
+        piv = piv_next;
+        rs = rs_next;
+    }
+    return bad;
+}
+
+// Inverse of a 16 x 16 lower-triangular block: lane j (< 16) computes column j of the inverse by forward substitution on e_j.
+// L(i,k) at L[k * ldl + i] (all lanes read the same element: broadcast), rdiag[k] = 1 / L(k,k); W(i,j) -> W[j * ldw + i].
+__device__ __forceinline__ void tri_inv16(const double *__restrict__ L, int ldl, const double *__restrict__ rdiag, double *__restrict__ W, int ldw, int j) {
+    double s[PB];
+#pragma unroll
+    for (int i = 0; i < PB; i++) s[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < PB; k++) {
+        const double xk = s[k] * rdiag[k];
+        s[k] = xk;
+#pragma unroll
+        for (int i = k + 1; i < PB; i++) s[i] = fma(-L[k * ldl + i], xk, s[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < PB; i++) W[j * ldw + i] = s[i];                          // rows i < j come out as exact zeros
+}
+
+// ---- small dense products on the fp64 tensor cores, operands in shared memory (column-major, LD = 4 mod 16) ----
+//   C(m, n) = beta * C(m, n) + alpha * sum_k A(m, k) * Bop(k, n)      A(m,k) at A[k*lda + m];  C(m,n) at C[n*ldc + m]
+//   BT = 0:  Bop(k, n) = B(n, k), read at B[k*ldb + n]   ("A B'")          BT = 1:  Bop(k, n) = B(k, n), read at B[n*ldb + k]   ("A B")
+// The M x N result is cut into (8 MF) x (8 NF) warp tiles dealt round-robin to the warps of the CTA.
+// k-ranges per tile (multiples of 4 by construction: all block sizes are multiples of 8):
+//   KEND_N: k < n0 + 8 NF  (B(n,k) = 0 for k > n: lower-triangular B in the A B' form)
+//   KBEG_N: k >= n0         (B(k,n) = 0 for k < n: lower-triangular B in the A B form)
+//   KEND_M: k < m0 + 8 MF  (A(m,k) = 0 for k > m: lower-triangular A)
+//   C_LOWER: tiles entirely above the diagonal are skipped (entries above the diagonal inside a kept tile are still written)
+// INPLACE: C may alias A or B -- every warp keeps its (single) tile in registers until all warps are done reading; requires
+// #tiles <= #warps.  The function ends with a __syncthreads() in every case.
+enum { KEND_N = 1, KBEG_N = 2, KEND_M = 4, C_LOWER = 8 };
+
+template <int MF, int NF, int BT, int FLAGS, bool INPLACE>
+__device__ __forceinline__ void smem_gemm(int M, int N, int K, double alpha, const double *__restrict__ A, int lda, const double *__restrict__ B,
+                                          int ldb, double beta, double *C, int ldc) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
+    const int tm = M / (8 * MF), tn = N / (8 * NF), ntask = tm * tn;
+    for (int task = wid; task < (INPLACE ? NWARP : ntask); task += NWARP) {
+        const bool live = task < ntask;
+        const int m0 = live ? (task % tm) * 8 * MF : 0, n0 = live ? (task / tm) * 8 * NF : 0;
+        const bool skip = !live || ((FLAGS & C_LOWER) && n0 > m0 + 8 * MF - 1);
+        double acc[MF][NF][2];
+#pragma unroll
+        for (int i = 0; i < MF; i++)
+#pragma unroll
+            for (int j = 0; j < NF; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        if (!skip) {
+            int kbeg = 0, kend = K;
+            if (FLAGS & KBEG_N) kbeg = n0;
+            if (FLAGS & KEND_N) kend = min(kend, n0 + 8 * NF);
+            if (FLAGS & KEND_M) kend = min(kend, m0 + 8 * MF);
+            const double *pa = A + (size_t)tg * lda + m0 + g;
+            const double *pb = BT ? B + (size_t)(n0 + g) * ldb + tg : B + (size_t)tg * ldb + n0 + g;
+#pragma unroll 2
+            for (int k0 = kbeg; k0 < kend; k0 += 4) {
+                double a[MF], b[NF];
+#pragma unroll
+                for (int i = 0; i < MF; i++) a[i] = pa[(size_t)k0 * lda + 8 * i];
+#pragma unroll
+                for (int j = 0; j < NF; j++) b[j] = BT ? pb[(size_t)(8 * j) * ldb + k0] : pb[(size_t)k0 * ldb + 8 * j];
+#pragma unroll
+                for (int i = 0; i < MF; i++)
+#pragma unroll
+                    for (int j = 0; j < NF; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        if (INPLACE) __syncthreads();
+        if (!skip) {
+#pragma unroll
+            for (int i = 0; i < MF; i++)
+#pragma unroll
+                for (int j = 0; j < NF; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        double *c = C + (size_t)(n0 + 8 * j + 2 * tg + e) * ldc + m0 + 8 * i + g;
+                        const double v = alpha * acc[i][j][e];
+                        *c = beta != 0.0 ? fma(beta, *c, v) : v;
+                    }
+        }
+    }
+    __syncthreads();
+}
+
+// Cholesky of the 64 x 64 block at a (column-major, lda), in place (lower triangle; the strict upper triangle of each 16 x 16
+// diagonal sub-block is zeroed), plus the inverses of its four 16 x 16 diagonal sub-blocks into W (column-major, ldw, same positions).
+// Four 16-column steps: warp 0 factors the diagonal sub-block and inverts it; the rows below are solved as a product with that
+// inverse and the rest of the block is updated, both on the tensor cores.
 // Returns (uniformly) 0 or the 1-based column (within the 64) of the first non-positive pivot.
-__device__ __forceinline__ int potf2_64_smem(double *__restrict__ a, int o, double (*ld)[PB + 1], double *rdg, int *sbad) {
+__device__ __forceinline__ int potf2_64_smem(double *a, int lda, double *W, int ldw, double *rdiag, int *sbad) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-#define A_(i, k) a[(size_t)(o + (i)) * DLD + o + (k)]
     for (int J = 0; J < NB; J += PB) {
+        double *ajj = a + (size_t)J * lda + J;
         if (wid == 0) {
             const int i = lane & (PB - 1);
             double d[PB];
 #pragma unroll
-            for (int k = 0; k < PB; k++) d[k] = A_(J + i, J + k);
-            int bad = 0;
-#pragma unroll
-            for (int j = 0; j < PB; j++) {
-                const double piv = __shfl_sync(0xffffffffu, d[j], j);
-                if (!(piv > 0.0)) { if (!bad) bad = J + j + 1; }
-                const double rs = rsqrt(piv);
-                const double lij = (i == j) ? piv * rs : d[j] * rs;
-                d[j] = lij;
-#pragma unroll
-                for (int k = j + 1; k < PB; k++) d[k] -= lij * __shfl_sync(0xffffffffu, lij, k);
-            }
+            for (int k = 0; k < PB; k++) d[k] = ajj[(size_t)k * lda + i];
+            if (J == 0) DBG_CLK(16);
+            int bad = warp_potf2_16(d, i, lane < PB ? rdiag + J : nullptr);
+            if (J == 0) DBG_CLK(17);
             if (lane < PB) {
 #pragma unroll
-                for (int k = 0; k < PB; k++) { ld[i][k] = (k <= i) ? d[k] : 0.0; A_(J + i, J + k) = (k <= i) ? d[k] : 0.0; }
-                double dii = 1.0;
-#pragma unroll
-                for (int k = 0; k < PB; k++) dii = (k == i) ? d[k] : dii;
-                rdg[i] = 1.0 / dii;
+                for (int k = 0; k < PB; k++) ajj[(size_t)k * lda + i] = (k <= i) ? d[k] : 0.0;
             }
-            if (lane == 0 && bad) *sbad = bad;
+            if (lane == 0 && bad) *sbad = J + bad;
+            __syncwarp();
+            if (J == 0) DBG_CLK(18);
+            if (lane < PB) tri_inv16(ajj, lda, rdiag + J, W + (size_t)J * ldw + J, ldw, lane);
+            if (J == 0) DBG_CLK(19);
         }
         __syncthreads();
+        if (J == 0) DBG_CLK(20);
         if (*sbad) break;
         const int nbelow = NB - J - PB;
         if (nbelow <= 0) break;
-        if (tid < nbelow) {
-            const int row = J + PB + tid;
-            double x[PB];
-#pragma unroll
-            for (int c = 0; c < PB; c++) x[c] = A_(row, J + c);
-#pragma unroll
-            for (int c = 0; c < PB; c++) {
-                const double xc = x[c] * rdg[c];
-                x[c] = xc;
-#pragma unroll
-                for (int k = c + 1; k < PB; k++) x[k] -= xc * ld[k][c];
-            }
-#pragma unroll
-            for (int c = 0; c < PB; c++) A_(row, J + c) = x[c];
-        }
-        __syncthreads();
-        {
-            const int ty = tid >> 4, tx = tid & 15, base = J + PB, nt = nbelow / PB;
-            double acc[3][3];
-#pragma unroll
-            for (int ii = 0; ii < 3; ii++)
-#pragma unroll
-                for (int kk = 0; kk < 3; kk++) acc[ii][kk] = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < PB; c++) {
-                double xi[3], xk[3];
-#pragma unroll
-                for (int ii = 0; ii < 3; ii++) xi[ii] = ii < nt ? A_(base + ty + PB * ii, J + c) : 0.0;
-#pragma unroll
-                for (int kk = 0; kk < 3; kk++) xk[kk] = kk < nt ? A_(base + tx + PB * kk, J + c) : 0.0;
-#pragma unroll
-                for (int ii = 0; ii < 3; ii++)
-#pragma unroll
-                    for (int kk = 0; kk < 3; kk++) acc[ii][kk] += xi[ii] * xk[kk];
-            }
-#pragma unroll
-            for (int ii = 0; ii < 3; ii++)
-#pragma unroll
-                for (int kk = 0; kk < 3; kk++) {
-                    const int i = base + ty + PB * ii, k = base + tx + PB * kk;
-                    if (ii < nt && kk < nt && k <= i) A_(i, k) -= acc[ii][kk];
-                }
-        }
-        __syncthreads();
+        // rows below: X = A_below W16'   (nbelow x 16 x 16, in place)
+        smem_gemm<2, 2, 0, 0, true>(nbelow, PB, PB, 1.0, ajj + PB, lda, W + (size_t)J * ldw + J, ldw, 0.0, ajj + PB, lda);
+        if (J == 0) DBG_CLK(21);
+        // rest of the block: A(i,k) -= sum_c X(i,c) X(k,c), lower
+        smem_gemm<2, 2, 0, C_LOWER, false>(nbelow, nbelow, PB, -1.0, ajj + PB, lda, ajj + PB, lda, 1.0, ajj + (size_t)PB * lda + PB, lda);
+        if (J == 0) DBG_CLK(22);
     }
-#undef A_
     return *sbad;
 }
 
-// D: Cholesky of the nb x nb (nb <= 128) diagonal block at A, in place (lower triangle).
+// W (64 x 64, column-major, ldw) holds the inverses of the four 16 x 16 diagonal blocks of the lower-triangular L (column-major, ldl)
+// and zeros elsewhere in its lower part; complete it to W = L^-1 by doubling:  W21 = -W22 (L21 W11)  for 16 -> 32 -> 64.
+// T (>= 32 x 32, column-major, ldt) is scratch.
+__device__ __forceinline__ void tri_inv64_finish(const double *L, int ldl, double *W, int ldw, double *T, int ldt) {
+    for (int b = PB; b < NB; b *= 2) {
+        for (int o = 0; o < NB; o += 2 * b) {          // pairs: sequential (there are at most two and T is shared)
+            const double *L21 = L + (size_t)o * ldl + o + b;
+            double *W11 = W + (size_t)o * ldw + o, *W22 = W + (size_t)(o + b) * ldw + o + b, *W21 = W + (size_t)o * ldw + o + b;
+            // T = L21 W11        (W11 lower: k >= n)
+            smem_gemm<2, 2, 1, KBEG_N, false>(b, b, b, 1.0, L21, ldl, W11, ldw, 0.0, T, ldt);
+            // W21 = -W22 T       (W22 lower: k <= m)
+            smem_gemm<2, 2, 1, KEND_M, false>(b, b, b, -1.0, W22, ldw, T, ldt, 0.0, W21, ldw);
+        }
+    }
+}
+
+constexpr size_t DIAG_SMEM = ((size_t)DP * MLD + (size_t)NB * WLD + (size_t)32 * 36) * sizeof(double);
+
+// D: Cholesky of the nb x nb (nb <= 128) diagonal block at A, in place (lower triangle), and the inverses of its two 64 x 64
+// diagonal blocks into Winv (2 x 64 x 64, column-major, ld 64) for the panel solve.
 // status[0] += sum(log(diag L)); status[1] = first failing (1-based, global) column, untouched if ok.
-__global__ void __launch_bounds__(BLK_T) diag128_kernel(double *__restrict__ A, int lda, int nb, int col_offset, double *__restrict__ status) {
+__global__ void __launch_bounds__(BLK_T) diag128_kernel(double *__restrict__ A, int lda, int nb, int col_offset, double *__restrict__ status,
+                                                        double *__restrict__ Winv) {
     extern __shared__ __align__(16) double dsm[];
-    double *a = dsm;                                   // a[i * DLD + k]
-    __shared__ double ld[PB][PB + 1];
-    __shared__ double rdg[PB];
-    __shared__ double rd[NB];
+    double *a = dsm;                                   // a[j * MLD + i]
+    double *W = dsm + (size_t)DP * MLD;                // W[j * WLD + i]
+    double *T = W + (size_t)NB * WLD;                  // T[j * 36 + i]
+    __shared__ double rdiag[NB];
     __shared__ int sbad;
-    __shared__ double slog[BLK_T / 32];
+    __shared__ double slog[NWARP];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) sbad = 0;
-    // load the lower triangle (identity padding beyond nb): a column of the block is contiguous in global memory; 16 loads in flight per thread
+    DBG_CLK(0);
+    // load (lower triangle; zeros above, identity padding beyond nb): columns are contiguous on both sides; 16 loads in flight
     for (int q0 = 0; q0 < DP * DP / BLK_T; q0 += 16) {
         double v[16];
 #pragma unroll
@@ -658,71 +774,32 @@ __global__ void __launch_bounds__(BLK_T) diag128_kernel(double *__restrict__ A, 
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             const int idx = tid + (q0 + q) * BLK_T, i = idx % DP, k = idx / DP;
-            a[(size_t)i * DLD + k] = v[q];
+            a[(size_t)k * MLD + i] = v[q];
         }
     }
+    for (int idx = tid; idx < NB * WLD; idx += BLK_T) W[idx] = 0.0;
     __syncthreads();
-    int bad = potf2_64_smem(a, 0, ld, rdg, &sbad);
+    DBG_CLK(1);
+    int bad = potf2_64_smem(a, MLD, W, WLD, rdiag, &sbad);
+    DBG_CLK(2);
     if (!bad && nb > NB) {
-        // rows 64..127: X = A10 L00^-T (four lanes per row, right-looking substitution; the lanes of a row own the columns c = 4 kk + h)
-        if (tid < NB) rd[tid] = __drcp_rn(a[(size_t)tid * DLD + tid]);
+        tri_inv64_finish(a, MLD, W, WLD, T, 36);                                     // W = L00^-1
+        for (int idx = tid; idx < NB * NB; idx += BLK_T) Winv[idx] = W[(size_t)(idx / NB) * WLD + idx % NB];
+        DBG_CLK(3);
+        // L10 = A10 W00'   (W00 lower: k <= n), in place
+        smem_gemm<2, 4, 0, KEND_N, true>(NB, NB, NB, 1.0, a + NB, MLD, W, WLD, 0.0, a + NB, MLD);
+        // A11 -= L10 L10'  (lower)
+        smem_gemm<2, 4, 0, C_LOWER, false>(NB, NB, NB, -1.0, a + NB, MLD, a + NB, MLD, 1.0, a + (size_t)NB * MLD + NB, MLD);
+        for (int idx = tid; idx < NB * WLD; idx += BLK_T) W[idx] = 0.0;
         __syncthreads();
-        {
-            const int t = tid / SPLIT, h = tid % SPLIT, lane_base = lane & ~(SPLIT - 1);
-            double *xr = a + (size_t)(NB + t) * DLD;
-            double x[NBQ];
-#pragma unroll
-            for (int kk = 0; kk < NBQ; kk++) x[kk] = xr[kk * SPLIT + h];
-#pragma unroll
-            for (int cc = 0; cc < NBQ; cc++) {
-#pragma unroll 1
-                for (int hh = 0; hh < SPLIT; hh++) {
-                    const int c = cc * SPLIT + hh;
-                    double xc = x[cc] * rd[c];
-                    if (h == hh) x[cc] = xc;
-                    xc = __shfl_sync(0xffffffffu, xc, lane_base + hh);
-                    const double *lc = a + c;                                   // L00[k][c] = a[k * DLD + c]
-                    if (h > hh) x[cc] -= xc * lc[(size_t)(cc * SPLIT + h) * DLD];
-#pragma unroll
-                    for (int kk = cc + 1; kk < NBQ; kk++) x[kk] -= xc * lc[(size_t)(kk * SPLIT + h) * DLD];
-                }
-            }
-            __syncthreads();                                                    // (everybody has read its row before anybody writes -- rows are private, but keep the phases apart)
-#pragma unroll
-            for (int kk = 0; kk < NBQ; kk++) xr[kk * SPLIT + h] = x[kk];
-        }
-        __syncthreads();
-        // A11 -= X X' (lower): 16 x 16 threads, rows ty + 16 ii, columns tx + 16 kk
-        {
-            const int ty = tid >> 4, tx = tid & 15;
-            double acc[4][4];
-#pragma unroll
-            for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) acc[ii][kk] = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < NB; c++) {
-                double xi[4], xk[4];
-#pragma unroll
-                for (int ii = 0; ii < 4; ii++) xi[ii] = a[(size_t)(NB + ty + 16 * ii) * DLD + c];
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) xk[kk] = a[(size_t)(NB + tx + 16 * kk) * DLD + c];
-#pragma unroll
-                for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) acc[ii][kk] += xi[ii] * xk[kk];
-            }
-#pragma unroll
-            for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
-                    const int i = NB + ty + 16 * ii, k = NB + tx + 16 * kk;
-                    if (k <= i) a[(size_t)i * DLD + k] -= acc[ii][kk];
-                }
-        }
-        __syncthreads();
-        bad = potf2_64_smem(a, NB, ld, rdg, &sbad);
+        DBG_CLK(4);
+        bad = potf2_64_smem(a + (size_t)NB * MLD + NB, MLD, W, WLD, rdiag, &sbad);
         if (bad) bad += NB;
+        DBG_CLK(5);
+        if (!bad) {
+            tri_inv64_finish(a + (size_t)NB * MLD + NB, MLD, W, WLD, T, 36);         // W = L11^-1
+            for (int idx = tid; idx < NB * NB; idx += BLK_T) Winv[NB * NB + idx] = W[(size_t)(idx / NB) * WLD + idx % NB];
+        }
     }
     if (bad) {
         if (tid == 0 && status[1] == 0.0) status[1] = (double)(col_offset + bad);
@@ -730,100 +807,114 @@ __global__ void __launch_bounds__(BLK_T) diag128_kernel(double *__restrict__ A, 
     }
     for (int idx = tid; idx < DP * DP; idx += BLK_T) {
         const int i = idx % DP, k = idx / DP;
-        if (i < nb && k < nb && k <= i) A[i + (size_t)k * lda] = a[(size_t)i * DLD + k];
+        if (i < nb && k < nb && k <= i) A[i + (size_t)k * lda] = a[(size_t)k * MLD + i];
     }
-    double lg = tid < nb ? log(a[(size_t)tid * DLD + tid]) : 0.0;             // (BLK_T = 256 >= 128 diagonal entries)
+    double lg = tid < nb ? log(a[(size_t)tid * MLD + tid]) : 0.0;                 // (BLK_T = 256 >= 128 diagonal entries)
     lg = warp_sum(lg);
     if (lane == 0) slog[wid] = lg;
     __syncthreads();
     if (tid == 0) {
         double s = 0.0;
-        for (int w = 0; w < BLK_T / 32; w++) s += slog[w];
+        for (int w = 0; w < NWARP; w++) s += slog[w];
         status[0] += s;
     }
+    DBG_CLK(6);
 }
 
 // S: the rows below a factored 128 x 128 diagonal block.  P (Mp x 128, column-major, ldp) <- P L^-T with L = [L00 0; L10 L11]:
-//   X0 = P0 L00^-T;  P1 -= X0 L10';  X1 = P1 L11^-T.   64 rows per CTA, four lanes per row (lane h owns the columns 4 kk + h of
-// each half: 2 x 16 registers).  The three 64 x 64 blocks of L are staged transposed in shared memory (Lt[c][k] = L[k][c]) so that the
-// four lanes of a row read four consecutive doubles and all rows of a warp read the same address.
-constexpr int SLD = NB + 4;
-constexpr size_t SOLVE_SMEM = (size_t)3 * NB * SLD * sizeof(double);
-__global__ void __launch_bounds__(BLK_T) panel_solve128_kernel(const double *__restrict__ L, int ldl, double *__restrict__ P, int ldp, int Mp) {
+//   X0 = P0 W00';  P1 -= X0 L10';  X1 = P1 W11'     (W00 = L00^-1, W11 = L11^-1 from diag128_kernel; L10 read from the factor)
+// 64 rows per CTA; the row tile and the three 64 x 64 blocks sit in shared memory, all three steps are DMMA products.
+constexpr size_t SOLVE_SMEM = ((size_t)DP * WLD + (size_t)3 * NB * WLD) * sizeof(double);
+__global__ void __launch_bounds__(BLK_T) panel_solve128_kernel(const double *__restrict__ L, int ldl, const double *__restrict__ Winv,
+                                                               double *__restrict__ P, int ldp, int Mp) {
     extern __shared__ __align__(16) double ssm[];
-    double *Lt0 = ssm, *Lt1 = ssm + NB * SLD, *Ct = ssm + 2 * NB * SLD;        // Lt0[c][k] = L00[k][c], Lt1 = L11 likewise, Ct[k][c] = L10[c][k]
-    __shared__ double rd0[NB], rd1[NB];
+    double *X = ssm;                                   // X[c * WLD + row]: 64 rows x 128 columns
+    double *W0 = ssm + (size_t)DP * WLD, *W1 = W0 + (size_t)NB * WLD, *C10 = W1 + (size_t)NB * WLD;
     const int tid = threadIdx.x;
-    for (int q0 = 0; q0 < NB * NB / BLK_T; q0 += 8) {                          // 3 x 8 loads in flight per thread
-        double v0[8], v1[8], v2[8];
+    const int row0 = blockIdx.x * NB, nrow = min(NB, Mp - row0);
+    DBG_CLK(8);
+    for (int q0 = 0; q0 < NB * NB / BLK_T; q0 += 8) {                          // 5 x 8 loads in flight per thread
+        double v0[8], v1[8], v2[8], p0[8], p1[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            const int idx = tid + (q0 + q) * BLK_T, k = idx % NB, c = idx / NB; // element (row k, column c) of each block: k contiguous in global memory
-            v0[q] = (c <= k) ? L[k + (size_t)c * ldl] : 0.0;
-            v1[q] = (c <= k) ? L[(NB + k) + (size_t)(NB + c) * ldl] : 0.0;
-            v2[q] = L[(NB + k) + (size_t)c * ldl];                             // L10[k][c]
+            const int idx = tid + (q0 + q) * BLK_T, i = idx % NB, c = idx / NB; // element (i, c) of each block: i contiguous in global memory
+            v0[q] = Winv[idx];
+            v1[q] = Winv[NB * NB + idx];
+            v2[q] = L[(NB + i) + (size_t)c * ldl];                              // L10(i, c)
+            p0[q] = i < nrow ? P[row0 + i + (size_t)c * ldp] : 0.0;
+            p1[q] = i < nrow ? P[row0 + i + (size_t)(NB + c) * ldp] : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            const int idx = tid + (q0 + q) * BLK_T, k = idx % NB, c = idx / NB;
-            Lt0[c * SLD + k] = v0[q];
-            Lt1[c * SLD + k] = v1[q];
-            Ct[c * SLD + k] = v2[q];                                           // Ct[c][k] = L10[k][c]: row c of Ct holds column c of L10
-            if (k == c) { rd0[c] = __drcp_rn(v0[q]); rd1[c] = __drcp_rn(v1[q]); }
+            const int idx = tid + (q0 + q) * BLK_T, i = idx % NB, c = idx / NB;
+            W0[c * WLD + i] = v0[q];
+            W1[c * WLD + i] = v1[q];
+            C10[c * WLD + i] = v2[q];
+            X[c * WLD + i] = p0[q];
+            X[(NB + c) * WLD + i] = p1[q];
         }
-    }
-    const int t = tid / SPLIT, h = tid % SPLIT, lane_base = (tid & 31) & ~(SPLIT - 1);
-    const int row = blockIdx.x * NB + t;
-    const bool live = row < Mp;
-    double x[NBQ], y[NBQ];
-#pragma unroll
-    for (int kk = 0; kk < NBQ; kk++) {
-        const int c = kk * SPLIT + h;
-        x[kk] = live ? P[row + (size_t)c * ldp] : 0.0;
-        y[kk] = live ? P[row + (size_t)(NB + c) * ldp] : 0.0;
     }
     __syncthreads();
-    // X0 = P0 L00^-T and, column by column, P1 -= x_c * L10[:, c]
+    DBG_CLK(9);
+    smem_gemm<2, 4, 0, KEND_N, true>(NB, NB, NB, 1.0, X, WLD, W0, WLD, 0.0, X, WLD);                                   // X0 = P0 W00'
+    smem_gemm<2, 4, 0, 0, false>(NB, NB, NB, -1.0, X, WLD, C10, WLD, 1.0, X + (size_t)NB * WLD, WLD);                  // P1 -= X0 L10'
+    DBG_CLK(10);
+    smem_gemm<2, 4, 0, KEND_N, true>(NB, NB, NB, 1.0, X + (size_t)NB * WLD, WLD, W1, WLD, 0.0, X + (size_t)NB * WLD, WLD);   // X1 = P1 W11'
+    DBG_CLK(11);
+    for (int idx = tid; idx < NB * DP; idx += BLK_T) {
+        const int i = idx % NB, c = idx / NB;
+        if (i < nrow) P[row0 + i + (size_t)c * ldp] = X[c * WLD + i];
+    }
+    DBG_CLK(12);
+}
+
+// U_diag: the next diagonal block (np x np, np <= 128, lower) takes its rank-128 update from the rows of the panel that face it:
+//   C(i, j) -= sum_k X(i, k) X(j, k),  X = P[0 : np, 0 : 128].
+// One CTA per 32 x 32 tile of the lower triangle (10 for np = 128): the two 32-row slabs of X go to shared memory, the tile is
+// updated in place in global memory.  On the critical path of the factorisation: ~6 us instead of ~20 for the general GEMM kernel.
+constexpr int UT = 32, ULD = UT + 4;          // tile size; slab stride 36 = 4 (mod 16)
+constexpr size_t UDIAG_SMEM = (size_t)2 * DP * ULD * sizeof(double);
+__global__ void __launch_bounds__(BLK_T) next_diag_update_kernel(const double *__restrict__ X, int ldx, double *__restrict__ Cg, int ldc, int np) {
+    extern __shared__ __align__(16) double usm[];
+    double *Xa = usm, *Xb = usm + (size_t)DP * ULD;    // Xa[k * ULD + i] = X(i0 + i, k), Xb likewise for the column slab
+    // tile index -> (bi, bj), bj <= bi
+    int bi = 0, t = blockIdx.x;
+    while (t > bi) { t -= bi + 1; bi++; }
+    const int bj = t, i0 = bi * UT, j0 = bj * UT, tid = threadIdx.x;
+    for (int q0 = 0; q0 < UT * DP / BLK_T; q0 += 8) {
+        double va[8], vb[8];
 #pragma unroll
-    for (int cc = 0; cc < NBQ; cc++) {
-#pragma unroll 1
-        for (int hh = 0; hh < SPLIT; hh++) {
-            const int c = cc * SPLIT + hh;
-            double xc = x[cc] * rd0[c];
-            if (h == hh) x[cc] = xc;
-            xc = __shfl_sync(0xffffffffu, xc, lane_base + hh);
-            const double *lt = Lt0 + c * SLD + h;
-            if (h > hh) x[cc] -= xc * lt[cc * SPLIT];
+        for (int q = 0; q < 8; q++) {
+            const int idx = tid + (q0 + q) * BLK_T, i = idx % UT, k = idx / UT;
+            va[q] = i0 + i < np ? X[i0 + i + (size_t)k * ldx] : 0.0;
+            vb[q] = j0 + i < np ? X[j0 + i + (size_t)k * ldx] : 0.0;
+        }
 #pragma unroll
-            for (int kk = cc + 1; kk < NBQ; kk++) x[kk] -= xc * lt[kk * SPLIT];
-            const double *ct = Ct + c * SLD + h;                                // L10[4 kk + h][c]
-#pragma unroll
-            for (int kk = 0; kk < NBQ; kk++) y[kk] -= xc * ct[kk * SPLIT];
+        for (int q = 0; q < 8; q++) {
+            const int idx = tid + (q0 + q) * BLK_T, i = idx % UT, k = idx / UT;
+            Xa[k * ULD + i] = va[q];
+            Xb[k * ULD + i] = vb[q];
         }
     }
-    // X1 = P1 L11^-T
-#pragma unroll
-    for (int cc = 0; cc < NBQ; cc++) {
-#pragma unroll 1
-        for (int hh = 0; hh < SPLIT; hh++) {
-            const int c = cc * SPLIT + hh;
-            double yc = y[cc] * rd1[c];
-            if (h == hh) y[cc] = yc;
-            yc = __shfl_sync(0xffffffffu, yc, lane_base + hh);
-            const double *lt = Lt1 + c * SLD + h;
-            if (h > hh) y[cc] -= yc * lt[cc * SPLIT];
-#pragma unroll
-            for (int kk = cc + 1; kk < NBQ; kk++) y[kk] -= yc * lt[kk * SPLIT];
-        }
+    __syncthreads();
+    // 32 x 32 x 128 on 8 warps: 8 x 16 warp tiles (1 x 2 fragments); rows / columns beyond np are zero-padded and not stored
+    const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, tg = lane & 3;
+    const int m0 = (wid & 3) * 8, n0 = (wid >> 2) * 16;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const double *pa = Xa + (size_t)tg * ULD + m0 + g, *pb = Xb + (size_t)tg * ULD + n0 + g;
+#pragma unroll 8
+    for (int k0 = 0; k0 < DP; k0 += 4) {
+        const double a = pa[(size_t)k0 * ULD], b0 = pb[(size_t)k0 * ULD], b1 = pb[(size_t)k0 * ULD + 8];
+        dmma(acc[0][0], acc[0][1], a, b0);
+        dmma(acc[1][0], acc[1][1], a, b1);
     }
-    if (live) {
 #pragma unroll
-        for (int kk = 0; kk < NBQ; kk++) {
-            const int c = kk * SPLIT + h;
-            P[row + (size_t)c * ldp] = x[kk];
-            P[row + (size_t)(NB + c) * ldp] = y[kk];
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int row = i0 + m0 + g, colc = j0 + n0 + 8 * j + 2 * tg + e;
+            if (row < np && colc <= row) Cg[row + (size_t)colc * ldc] -= acc[j][e];
         }
-    }
 }
 
 // mirror: A[j,i] = A[i,j] for i > j (32x32 tiles through shared memory, coalesced both ways)
@@ -855,6 +946,7 @@ static int gemm_set_attrs() {
     FRK_CHECK_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
     FRK_CHECK_CUDA(cudaFuncSetAttribute(diag128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
     FRK_CHECK_CUDA(cudaFuncSetAttribute(panel_solve128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    FRK_CHECK_CUDA(cudaFuncSetAttribute(next_diag_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UDIAG_SMEM));
     done = true;
     return 0;
 }
@@ -997,21 +1089,24 @@ static int potrf_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
 //   side : [wait S(p)] R(p): rows and columns >= J+256 (lower SYRK, rank 128); R(p) runs beside D(p+1), S(p+1).
 // U(p+1) and R(p) update overlapping regions (columns of panel p+2), hence the wait; everything else that runs concurrently
 // touches disjoint blocks.  Replayed as one CUDA graph with two branches.
-static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
+static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status, double *winv) {
     FRK_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(double), ctx->stream));
     const size_t ld = (size_t)r;
     cudaStream_t main = ctx->stream, side = ctx->stream3;
-    const bool fork = main != nullptr && side != nullptr;
+    const bool fork = main != nullptr && side != nullptr && ctx->stream2 != nullptr;
     bool have_rest[2] = {false, false};
+    bool pending_join = false;
     int pidx = 0;
     for (int J = 0; J < r; J += DP, pidx++) {
         const int nb = std::min(DP, r - J), below = r - J - nb;
         FRK_WORK(ctx, (double)nb * nb * nb / 3.0, 0);
-        FRK_LAUNCH(ctx, diag128_kernel, 1, BLK_T, DIAG_SMEM, d_A + J + J * ld, r, nb, J, status);
+        FRK_LAUNCH(ctx, diag128_kernel, 1, BLK_T, DIAG_SMEM, d_A + J + J * ld, r, nb, J, status, winv);
+        if (pending_join) { FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_join, 0)); pending_join = false; }   // rows below got U(p-1)
         if (below <= 0) break;
         double *P = d_A + (J + nb) + J * ld;                           // below x 128
         FRK_WORK(ctx, (double)below * nb * nb, 0);
-        FRK_LAUNCH(ctx, panel_solve128_kernel, (unsigned)cdiv(below, NB), BLK_T, SOLVE_SMEM, (const double *)(d_A + J + J * ld), r, P, r, below);
+        FRK_LAUNCH(ctx, panel_solve128_kernel, (unsigned)cdiv(below, NB), BLK_T, SOLVE_SMEM, (const double *)(d_A + J + J * ld), r,
+                   (const double *)winv, P, r, below);
         const int npan = std::min(DP, below), beyond = below - npan;
         if (!fork) {                                                   // sequential: one lower SYRK over everything below
             GemmArgs g = gemm_args(below, below, nb, -1.0, P, r, P, r, 1.0, d_A + (J + nb) + (J + nb) * ld, r);
@@ -1033,11 +1128,26 @@ static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status) {
         }
         if (have_rest[(pidx + 1) & 1]) FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_rest[(pidx + 1) & 1], 0));   // R(p-1) reached these columns
         have_rest[pidx & 1] = beyond > 0;
-        {   // U(p): next panel's columns, rows >= J+nb (lower part: the diagonal starts at the block's origin)
-            GemmArgs g = gemm_args(below, npan, nb, -1.0, P, r, P, r, 1.0, d_A + (J + nb) + (J + nb) * ld, r);
-            g.lower = 1;
-            if (int rc = launch_gemm(ctx, g, false, false, 2.0 * below * npan * nb - (double)npan * npan * nb, "dgemm_kernel[potrf next-panel update]")) return rc;
+        // U(p): the next panel's columns take their rank-128 update.  Only the next DIAGONAL block is on the critical path (D(p+1)
+        // needs it); the rows below it are needed by S(p+1), so they are updated on the second side stream beside D(p+1).
+        if (beyond > 0) {
+            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, main));                     // S(p) done and R(p-1) waited for
+            FRK_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            const double *P2 = P + npan;
+            GemmArgs g = gemm_args(beyond, npan, nb, -1.0, P2, r, P, r, 1.0, d_A + (J + nb + npan) + (J + nb) * ld, r);
+            ctx->stream = ctx->stream2;
+            const int rc = launch_gemm(ctx, g, false, false, 2.0 * beyond * npan * nb, "dgemm_kernel[potrf next-panel update]");
+            ctx->stream = main;
+            if (rc) return rc;
+            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
         }
+        {   // next diagonal block (npan x npan, lower)
+            const int nt = (int)cdiv(npan, UT);
+            FRK_WORK(ctx, (double)npan * (npan + 1.0) * nb, 0);
+            FRK_LAUNCH(ctx, next_diag_update_kernel, (unsigned)(nt * (nt + 1) / 2), BLK_T, UDIAG_SMEM, (const double *)P, r,
+                       d_A + (J + nb) + (J + nb) * ld, r, npan);
+        }
+        pending_join = beyond > 0;
     }
     if (fork)
         for (int i = 0; i < 2; i++)
@@ -1058,7 +1168,7 @@ int frk_potrf_async(frk_ctx *ctx, int r, double *d_A) {
     double *status = ctx->d_small + 4096 - 8;
     if (int rc = gemm_set_attrs()) return rc;
     if (int rc = run_graphed(ctx, {1, (uintptr_t)r, (uintptr_t)d_A, 0, 0},
-                             [&]() { return potrf_use_v1() ? potrf_enqueue(ctx, r, d_A, status) : potrf2_enqueue(ctx, r, d_A, status); })) return rc;
+                             [&]() { return potrf_use_v1() ? potrf_enqueue(ctx, r, d_A, status) : potrf2_enqueue(ctx, r, d_A, status, ctx->d_winv); })) return rc;
     FRK_CHECK_CUDA(cudaMemcpyAsync(ctx->h_pinned + 4096 - 8, status, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
