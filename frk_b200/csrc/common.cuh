@@ -28,7 +28,7 @@ struct frk_ctx {
     size_t scratch_bytes = 0;
     double *h_pinned = nullptr;   // 4096 doubles
     double *d_small = nullptr;    // 4096 doubles
-    double *d_winv = nullptr;     // 2 x 64 x 64: inverses of the current panel's diagonal 64 x 64 factors (potrf: diag128 -> panel solve)
+    double *d_winv = nullptr;     // 8 x 16 x 16: inverses of the 16 x 16 diagonal blocks of the current panel's factor (potrf: diag128 -> panel solve)
     // profiling
     bool profiling = false;
     double next_flops = 0, next_bytes = 0;          // algorithmic work of the next launch (FRK_WORK)

@@ -688,83 +688,72 @@ __device__ __forceinline__ void smem_gemm(int M, int N, int K, double alpha, con
     __syncthreads();
 }
 
-// Cholesky of the 64 x 64 block at a (column-major, lda), in place (lower triangle; the strict upper triangle of each 16 x 16
-// diagonal sub-block is zeroed), plus the inverses of its four 16 x 16 diagonal sub-blocks into W (column-major, ldw, same positions).
-// Four 16-column steps: warp 0 factors the diagonal sub-block and inverts it; the rows below are solved as a product with that
-// inverse and the rest of the block is updated, both on the tensor cores.
-// Returns (uniformly) 0 or the 1-based column (within the 64) of the first non-positive pivot.
-__device__ __forceinline__ int potf2_64_smem(double *a, int lda, double *W, int ldw, double *rdiag, int *sbad) {
+// Cholesky of the n x n block at a (column-major, lda; n a multiple of 16, n <= 128), in place (lower triangle; the strict upper
+// triangle of each 16 x 16 diagonal sub-block is zeroed), plus the inverses of the 16 x 16 diagonal sub-blocks into Wd (block J / 16
+// at Wd + (J / 16) * 16 * WDL, column-major with stride WDL).  16-column steps: warp 0 factors the diagonal sub-block and inverts it;
+// the rows below are solved as a product with that inverse and the rest of the block is updated, both on the tensor cores.
+// Returns (uniformly) 0 or the 1-based column of the first non-positive pivot.
+constexpr int WDL = PB + 4;                   // 20 = 4 (mod 16)
+__device__ __forceinline__ int potf2_blk_smem(double *a, int lda, int n, double *Wd, double *rdiag, int *sbad) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int J = 0; J < NB; J += PB) {
+    for (int J = 0; J < n; J += PB) {
         double *ajj = a + (size_t)J * lda + J;
+        double *wj = Wd + (size_t)(J / PB) * PB * WDL;
+        const bool stamp = J == 0;
         if (wid == 0) {
             const int i = lane & (PB - 1);
             double d[PB];
 #pragma unroll
             for (int k = 0; k < PB; k++) d[k] = ajj[(size_t)k * lda + i];
-            if (J == 0) DBG_CLK(16);
+            if (stamp) DBG_CLK(16);
             int bad = warp_potf2_16(d, i, lane < PB ? rdiag + J : nullptr);
-            if (J == 0) DBG_CLK(17);
+            if (stamp) DBG_CLK(17);
             if (lane < PB) {
 #pragma unroll
                 for (int k = 0; k < PB; k++) ajj[(size_t)k * lda + i] = (k <= i) ? d[k] : 0.0;
             }
             if (lane == 0 && bad) *sbad = J + bad;
             __syncwarp();
-            if (J == 0) DBG_CLK(18);
-            if (lane < PB) tri_inv16(ajj, lda, rdiag + J, W + (size_t)J * ldw + J, ldw, lane);
-            if (J == 0) DBG_CLK(19);
+            if (stamp) DBG_CLK(18);
+            if (lane < PB) tri_inv16(ajj, lda, rdiag + J, wj, WDL, lane);
+            if (stamp) DBG_CLK(19);
         }
         __syncthreads();
-        if (J == 0) DBG_CLK(20);
+        if (stamp) DBG_CLK(20);
         if (*sbad) break;
-        const int nbelow = NB - J - PB;
+        const int nbelow = n - J - PB;
         if (nbelow <= 0) break;
-        // rows below: X = A_below W16'   (nbelow x 16 x 16, in place)
-        smem_gemm<2, 2, 0, 0, true>(nbelow, PB, PB, 1.0, ajj + PB, lda, W + (size_t)J * ldw + J, ldw, 0.0, ajj + PB, lda);
-        if (J == 0) DBG_CLK(21);
+        // rows below: X = A_below W16'   (nbelow x 16 x 16, in place; at most 7 warp tiles)
+        smem_gemm<2, 2, 0, 0, true>(nbelow, PB, PB, 1.0, ajj + PB, lda, wj, WDL, 0.0, ajj + PB, lda);
+        if (stamp) DBG_CLK(21);
         // rest of the block: A(i,k) -= sum_c X(i,c) X(k,c), lower
         smem_gemm<2, 2, 0, C_LOWER, false>(nbelow, nbelow, PB, -1.0, ajj + PB, lda, ajj + PB, lda, 1.0, ajj + (size_t)PB * lda + PB, lda);
-        if (J == 0) DBG_CLK(22);
+        if (stamp) DBG_CLK(22);
     }
     return *sbad;
 }
 
-// W (64 x 64, column-major, ldw) holds the inverses of the four 16 x 16 diagonal blocks of the lower-triangular L (column-major, ldl)
-// and zeros elsewhere in its lower part; complete it to W = L^-1 by doubling:  W21 = -W22 (L21 W11)  for 16 -> 32 -> 64.
-// T (>= 32 x 32, column-major, ldt) is scratch.
-__device__ __forceinline__ void tri_inv64_finish(const double *L, int ldl, double *W, int ldw, double *T, int ldt) {
-    for (int b = PB; b < NB; b *= 2) {
-        for (int o = 0; o < NB; o += 2 * b) {          // pairs: sequential (there are at most two and T is shared)
-            const double *L21 = L + (size_t)o * ldl + o + b;
-            double *W11 = W + (size_t)o * ldw + o, *W22 = W + (size_t)(o + b) * ldw + o + b, *W21 = W + (size_t)o * ldw + o + b;
-            // T = L21 W11        (W11 lower: k >= n)
-            smem_gemm<2, 2, 1, KBEG_N, false>(b, b, b, 1.0, L21, ldl, W11, ldw, 0.0, T, ldt);
-            // W21 = -W22 T       (W22 lower: k <= m)
-            smem_gemm<2, 2, 1, KEND_M, false>(b, b, b, -1.0, W22, ldw, T, ldt, 0.0, W21, ldw);
-        }
-    }
-}
+constexpr size_t DIAG_SMEM = ((size_t)DP * MLD + (size_t)(DP / PB) * PB * WDL) * sizeof(double);
+constexpr int WINV_DOUBLES = (DP / PB) * PB * PB;      // 8 blocks of 16 x 16, column-major, dense
 
-constexpr size_t DIAG_SMEM = ((size_t)DP * MLD + (size_t)NB * WLD + (size_t)32 * 36) * sizeof(double);
-
-// D: Cholesky of the nb x nb (nb <= 128) diagonal block at A, in place (lower triangle), and the inverses of its two 64 x 64
-// diagonal blocks into Winv (2 x 64 x 64, column-major, ld 64) for the panel solve.
+// D: Cholesky of the nb x nb (nb <= 128) diagonal block at A, in place (lower triangle), and the inverses of its eight 16 x 16
+// diagonal sub-blocks into Winv (8 x 16 x 16, column-major) for the panel solve.
 // status[0] += sum(log(diag L)); status[1] = first failing (1-based, global) column, untouched if ok.
 __global__ void __launch_bounds__(BLK_T) diag128_kernel(double *__restrict__ A, int lda, int nb, int col_offset, double *__restrict__ status,
                                                         double *__restrict__ Winv) {
     extern __shared__ __align__(16) double dsm[];
     double *a = dsm;                                   // a[j * MLD + i]
-    double *W = dsm + (size_t)DP * MLD;                // W[j * WLD + i]
-    double *T = W + (size_t)NB * WLD;                  // T[j * 36 + i]
-    __shared__ double rdiag[NB];
+    double *Wd = dsm + (size_t)DP * MLD;               // eight 16 x 16 inverse blocks
+    __shared__ double rdiag[DP];
     __shared__ int sbad;
     __shared__ double slog[NWARP];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) sbad = 0;
     DBG_CLK(0);
-    // load (lower triangle; zeros above, identity padding beyond nb): columns are contiguous on both sides; 16 loads in flight
+    const int n16 = ((nb + PB - 1) / PB) * PB;         // identity padding up to the next multiple of 16
+    // load (lower triangle; zeros above): columns are contiguous on both sides; 16 loads in flight
     for (int q0 = 0; q0 < DP * DP / BLK_T; q0 += 16) {
+        if (q0 * BLK_T >= n16 * DP) break;             // columns beyond the block are never touched
         double v[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) {
@@ -777,37 +766,21 @@ __global__ void __launch_bounds__(BLK_T) diag128_kernel(double *__restrict__ A, 
             a[(size_t)k * MLD + i] = v[q];
         }
     }
-    for (int idx = tid; idx < NB * WLD; idx += BLK_T) W[idx] = 0.0;
     __syncthreads();
     DBG_CLK(1);
-    int bad = potf2_64_smem(a, MLD, W, WLD, rdiag, &sbad);
+    const int bad = potf2_blk_smem(a, MLD, n16, Wd, rdiag, &sbad);
     DBG_CLK(2);
-    if (!bad && nb > NB) {
-        tri_inv64_finish(a, MLD, W, WLD, T, 36);                                     // W = L00^-1
-        for (int idx = tid; idx < NB * NB; idx += BLK_T) Winv[idx] = W[(size_t)(idx / NB) * WLD + idx % NB];
-        DBG_CLK(3);
-        // L10 = A10 W00'   (W00 lower: k <= n), in place
-        smem_gemm<2, 4, 0, KEND_N, true>(NB, NB, NB, 1.0, a + NB, MLD, W, WLD, 0.0, a + NB, MLD);
-        // A11 -= L10 L10'  (lower)
-        smem_gemm<2, 4, 0, C_LOWER, false>(NB, NB, NB, -1.0, a + NB, MLD, a + NB, MLD, 1.0, a + (size_t)NB * MLD + NB, MLD);
-        for (int idx = tid; idx < NB * WLD; idx += BLK_T) W[idx] = 0.0;
-        __syncthreads();
-        DBG_CLK(4);
-        bad = potf2_64_smem(a + (size_t)NB * MLD + NB, MLD, W, WLD, rdiag, &sbad);
-        if (bad) bad += NB;
-        DBG_CLK(5);
-        if (!bad) {
-            tri_inv64_finish(a + (size_t)NB * MLD + NB, MLD, W, WLD, T, 36);         // W = L11^-1
-            for (int idx = tid; idx < NB * NB; idx += BLK_T) Winv[NB * NB + idx] = W[(size_t)(idx / NB) * WLD + idx % NB];
-        }
-    }
     if (bad) {
         if (tid == 0 && status[1] == 0.0) status[1] = (double)(col_offset + bad);
         return;
     }
-    for (int idx = tid; idx < DP * DP; idx += BLK_T) {
+    for (int idx = tid; idx < WINV_DOUBLES; idx += BLK_T) {
+        const int blk = idx / (PB * PB), e = idx % (PB * PB);
+        Winv[idx] = Wd[(size_t)blk * PB * WDL + (e / PB) * WDL + e % PB];
+    }
+    for (int idx = tid; idx < n16 * DP; idx += BLK_T) {
         const int i = idx % DP, k = idx / DP;
-        if (i < nb && k < nb && k <= i) A[i + (size_t)k * lda] = a[(size_t)k * MLD + i];
+        if (i < nb && k <= i) A[i + (size_t)k * lda] = a[(size_t)k * MLD + i];
     }
     double lg = tid < nb ? log(a[(size_t)tid * MLD + tid]) : 0.0;                 // (BLK_T = 256 >= 128 diagonal entries)
     lg = warp_sum(lg);
@@ -821,49 +794,67 @@ __global__ void __launch_bounds__(BLK_T) diag128_kernel(double *__restrict__ A, 
     DBG_CLK(6);
 }
 
-// S: the rows below a factored 128 x 128 diagonal block.  P (Mp x 128, column-major, ldp) <- P L^-T with L = [L00 0; L10 L11]:
-//   X0 = P0 W00';  P1 -= X0 L10';  X1 = P1 W11'     (W00 = L00^-1, W11 = L11^-1 from diag128_kernel; L10 read from the factor)
-// 64 rows per CTA; the row tile and the three 64 x 64 blocks sit in shared memory, all three steps are DMMA products.
-constexpr size_t SOLVE_SMEM = ((size_t)DP * WLD + (size_t)3 * NB * WLD) * sizeof(double);
+// S: the rows below a factored 128 x 128 diagonal block.  P (Mp x 128, column-major, ldp) <- P L^-T in eight 16-column steps:
+//   X_J = P_J W_J'   (W_J = inverse of the J-th 16 x 16 diagonal block of L, from diag128_kernel)
+//   P(:, c) -= X_J L(c, J)'   for the columns c to the right.
+// SR rows per CTA; the row tile, the factor L and the inverse blocks sit in shared memory; every step is a DMMA product.
+constexpr int SR = 32;                        // rows per CTA (32: ~100 CTAs at r ~ 3000, i.e. most of the SMs)
+constexpr int XLD = SR + 4;                   // 36 = 4 (mod 16)
+constexpr size_t SOLVE_SMEM = ((size_t)DP * XLD + (size_t)DP * MLD + (size_t)(DP / PB) * PB * WDL) * sizeof(double);
 __global__ void __launch_bounds__(BLK_T) panel_solve128_kernel(const double *__restrict__ L, int ldl, const double *__restrict__ Winv,
                                                                double *__restrict__ P, int ldp, int Mp) {
     extern __shared__ __align__(16) double ssm[];
-    double *X = ssm;                                   // X[c * WLD + row]: 64 rows x 128 columns
-    double *W0 = ssm + (size_t)DP * WLD, *W1 = W0 + (size_t)NB * WLD, *C10 = W1 + (size_t)NB * WLD;
+    double *X = ssm;                                   // X[c * XLD + row]: SR rows x 128 columns
+    double *Ls = X + (size_t)DP * XLD;                 // Ls[c * MLD + i]: the factor (lower part; the rest is not read)
+    double *Wd = Ls + (size_t)DP * MLD;
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * NB, nrow = min(NB, Mp - row0);
+    const int row0 = blockIdx.x * SR, nrow = min(SR, Mp - row0);
     DBG_CLK(8);
-    for (int q0 = 0; q0 < NB * NB / BLK_T; q0 += 8) {                          // 5 x 8 loads in flight per thread
-        double v0[8], v1[8], v2[8], p0[8], p1[8];
+    // the row tile: 16 loads in flight per thread
+    {
+        double v[SR * DP / BLK_T];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int idx = tid + (q0 + q) * BLK_T, i = idx % NB, c = idx / NB; // element (i, c) of each block: i contiguous in global memory
-            v0[q] = Winv[idx];
-            v1[q] = Winv[NB * NB + idx];
-            v2[q] = L[(NB + i) + (size_t)c * ldl];                              // L10(i, c)
-            p0[q] = i < nrow ? P[row0 + i + (size_t)c * ldp] : 0.0;
-            p1[q] = i < nrow ? P[row0 + i + (size_t)(NB + c) * ldp] : 0.0;
+        for (int q = 0; q < SR * DP / BLK_T; q++) {
+            const int idx = tid + q * BLK_T, i = idx % SR, c = idx / SR;
+            v[q] = i < nrow ? P[row0 + i + (size_t)c * ldp] : 0.0;
         }
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int idx = tid + (q0 + q) * BLK_T, i = idx % NB, c = idx / NB;
-            W0[c * WLD + i] = v0[q];
-            W1[c * WLD + i] = v1[q];
-            C10[c * WLD + i] = v2[q];
-            X[c * WLD + i] = p0[q];
-            X[(NB + c) * WLD + i] = p1[q];
+        for (int q = 0; q < SR * DP / BLK_T; q++) {
+            const int idx = tid + q * BLK_T, i = idx % SR, c = idx / SR;
+            X[c * XLD + i] = v[q];
         }
+    }
+    // the factor: only the rows below the 16 x 16 diagonal blocks are read (column c: rows >= 16 (c / 16 + 1))
+    for (int q0 = 0; q0 < DP * DP / BLK_T; q0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int idx = tid + (q0 + q) * BLK_T, i = idx % DP, c = idx / DP;
+            v[q] = i >= PB * (c / PB + 1) ? L[i + (size_t)c * ldl] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int idx = tid + (q0 + q) * BLK_T, i = idx % DP, c = idx / DP;
+            Ls[(size_t)c * MLD + i] = v[q];
+        }
+    }
+    for (int idx = tid; idx < WINV_DOUBLES; idx += BLK_T) {
+        const int blk = idx / (PB * PB), e = idx % (PB * PB);
+        Wd[(size_t)blk * PB * WDL + (e / PB) * WDL + e % PB] = Winv[idx];
     }
     __syncthreads();
     DBG_CLK(9);
-    smem_gemm<2, 4, 0, KEND_N, true>(NB, NB, NB, 1.0, X, WLD, W0, WLD, 0.0, X, WLD);                                   // X0 = P0 W00'
-    smem_gemm<2, 4, 0, 0, false>(NB, NB, NB, -1.0, X, WLD, C10, WLD, 1.0, X + (size_t)NB * WLD, WLD);                  // P1 -= X0 L10'
-    DBG_CLK(10);
-    smem_gemm<2, 4, 0, KEND_N, true>(NB, NB, NB, 1.0, X + (size_t)NB * WLD, WLD, W1, WLD, 0.0, X + (size_t)NB * WLD, WLD);   // X1 = P1 W11'
+    for (int J = 0; J < DP; J += PB) {
+        double *XJ = X + (size_t)J * XLD;
+        smem_gemm<2, 2, 0, 0, true>(SR, PB, PB, 1.0, XJ, XLD, Wd + (size_t)(J / PB) * PB * WDL, WDL, 0.0, XJ, XLD);          // X_J = P_J W_J'
+        const int nrest = DP - J - PB;
+        if (nrest > 0)                                                                                                        // P(:, right) -= X_J L(right, J)'
+            smem_gemm<2, 2, 0, 0, false>(SR, nrest, PB, -1.0, XJ, XLD, Ls + (size_t)J * MLD + J + PB, MLD, 1.0, XJ + (size_t)PB * XLD, XLD);
+    }
     DBG_CLK(11);
-    for (int idx = tid; idx < NB * DP; idx += BLK_T) {
-        const int i = idx % NB, c = idx / NB;
-        if (i < nrow) P[row0 + i + (size_t)c * ldp] = X[c * WLD + i];
+    for (int idx = tid; idx < SR * DP; idx += BLK_T) {
+        const int i = idx % SR, c = idx / SR;
+        if (i < nrow) P[row0 + i + (size_t)c * ldp] = X[c * XLD + i];
     }
     DBG_CLK(12);
 }
@@ -1094,6 +1085,7 @@ static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status, doub
     const size_t ld = (size_t)r;
     cudaStream_t main = ctx->stream, side = ctx->stream3;
     const bool fork = main != nullptr && side != nullptr && ctx->stream2 != nullptr;
+    static const int dbg_skip = getenv("FRK_POTRF_SKIP") ? atoi(getenv("FRK_POTRF_SKIP")) : 0;   // timing experiments only: 1 = no R / U_rest, 2 = R / U_rest on the main stream
     bool have_rest[2] = {false, false};
     bool pending_join = false;
     int pidx = 0;
@@ -1105,7 +1097,7 @@ static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status, doub
         if (below <= 0) break;
         double *P = d_A + (J + nb) + J * ld;                           // below x 128
         FRK_WORK(ctx, (double)below * nb * nb, 0);
-        FRK_LAUNCH(ctx, panel_solve128_kernel, (unsigned)cdiv(below, NB), BLK_T, SOLVE_SMEM, (const double *)(d_A + J + J * ld), r,
+        FRK_LAUNCH(ctx, panel_solve128_kernel, (unsigned)cdiv(below, SR), BLK_T, SOLVE_SMEM, (const double *)(d_A + J + J * ld), r,
                    (const double *)winv, P, r, below);
         const int npan = std::min(DP, below), beyond = below - npan;
         if (!fork) {                                                   // sequential: one lower SYRK over everything below
@@ -1114,6 +1106,13 @@ static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status, doub
             if (int rc = launch_gemm(ctx, g, false, false, (double)below * (below + 1.0) * nb, "dgemm_kernel[potrf trailing SYRK]")) return rc;
             continue;
         }
+        if (dbg_skip == 1) {
+            const int nt = (int)cdiv(npan, UT);
+            FRK_LAUNCH(ctx, next_diag_update_kernel, (unsigned)(nt * (nt + 1) / 2), BLK_T, UDIAG_SMEM, (const double *)P, r,
+                       d_A + (J + nb) + (J + nb) * ld, r, npan);
+            continue;
+        }
+        if (dbg_skip == 2) { side = main; }
         if (beyond > 0) {                                              // R(p) on the side stream
             FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_panel, main));
             FRK_CHECK_CUDA(cudaStreamWaitEvent(side, ctx->ev_panel, 0));
@@ -1131,15 +1130,16 @@ static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status, doub
         // U(p): the next panel's columns take their rank-128 update.  Only the next DIAGONAL block is on the critical path (D(p+1)
         // needs it); the rows below it are needed by S(p+1), so they are updated on the second side stream beside D(p+1).
         if (beyond > 0) {
+            cudaStream_t s2 = dbg_skip == 2 ? main : ctx->stream2;
             FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, main));                     // S(p) done and R(p-1) waited for
-            FRK_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            FRK_CHECK_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
             const double *P2 = P + npan;
             GemmArgs g = gemm_args(beyond, npan, nb, -1.0, P2, r, P, r, 1.0, d_A + (J + nb + npan) + (J + nb) * ld, r);
-            ctx->stream = ctx->stream2;
+            ctx->stream = s2;
             const int rc = launch_gemm(ctx, g, false, false, 2.0 * beyond * npan * nb, "dgemm_kernel[potrf next-panel update]");
             ctx->stream = main;
             if (rc) return rc;
-            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
+            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_join, s2));
         }
         {   // next diagonal block (npan x npan, lower)
             const int nt = (int)cdiv(npan, UT);

@@ -66,6 +66,13 @@ struct frk_model {
     double Dt01 = 0.0;
     std::vector<double> taus, omegas;
     double nm_requests = 0, nm_rounds = 0, nm_evals = 0, nm_reevals = 0;   // Nelder-Mead statistics of the last M-step (distinct points asked, batches, points evaluated)
+    double nm_prefetch_hits = 0;     // ... of which had their factorisation enqueued before the E-step (prefetch_f_tau)
+    // Prefetch: K_i(tau)^-1 and log|K_i(tau)| depend on tau only.  The first two points the NEXT M-step's Nelder-Mead will ask for
+    // (its start value and start + step) are known as soon as this M-step has assembled K, so their factorisations are enqueued on the
+    // lanes right away and run beside the next E-step's factorisation of Q instead of after it.  pre[j][c]: (active, tau) of lane c of block j.
+    struct PreSlot { bool on = false; double tau = 0.0; };
+    std::vector<std::array<PreSlot, 8>> pre;
+    bool prefetch = true;
     // multi-rank reduction hook
     int rank = 0, world = 1;
     bool spec_emulate = false;     // evaluate every speculative candidate on this rank (single-GPU test of the multi-rank logic)
@@ -590,6 +597,8 @@ int chol2inv_logdet_soft(frk_ctx *ctx, int n, double *A, double *Ainv, double *w
 // distributed over the ranks the runs move in lockstep and ONE all-reduce per round shares the values of all resolutions.
 // Each run sees exactly the values the sequential algorithm would: the iterates are identical.
 // ---------------------------------------------------------------------------------
+using Model_PreSlot = frk_model::PreSlot;
+
 struct NMSlot {                    // one concurrent evaluation: context + buffers, and what its Kinv currently holds
     frk_ctx *ctx = nullptr;
     double *Ki = nullptr, *Kinv = nullptr, *work = nullptr;
@@ -613,14 +622,75 @@ struct BlkNM {
     std::vector<NMSlot> slot;
 };
 
-// K_i(tau), its factor, inverse and tr(K_i^-1 eta2_i) on the slot's context; enqueue only, the scalars land in the context's
-// pinned staging buffer (on a non-PD matrix the inverse is garbage that is discarded when the status is read)
-int f_tau_enqueue(const Block &B, NMSlot &s, double tau) {
+// the tau-only part of an f_tau evaluation: K_i(tau), its factor and inverse on the slot's context (enqueue only; log-determinant and
+// status land in the context's pinned staging buffer; on a non-PD matrix the inverse is garbage that is discarded when the status is read)
+int f_tau_factor_enqueue(const Block &B, NMSlot &s, double tau) {
     const size_t nn = (size_t)B.ni * B.ni;
     RC(frk_exp_kernel(s.ctx, (int64_t)nn, B.D, tau, 1.0, s.Ki));
     RC(frk_potrf_async(s.ctx, B.ni, s.Ki));
-    RC(frk_potri(s.ctx, B.ni, s.Ki, s.Kinv, s.work));
-    return frk_dot_async(s.ctx, (int64_t)nn, s.Kinv, B.eta2);
+    return frk_potri(s.ctx, B.ni, s.Ki, s.Kinv, s.work);
+}
+
+// ... and tr(K_i^-1 eta2_i), which needs the current E-step
+int f_tau_enqueue(const Block &B, NMSlot &s, double tau) {
+    RC(f_tau_factor_enqueue(B, s, tau));
+    return frk_dot_async(s.ctx, (int64_t)B.ni * B.ni, s.Kinv, B.eta2);
+}
+
+constexpr int LCAP = 8;            // slot (block j, lane c) -> lane context j*LCAP + c - 1: stable, so graph caches hit
+
+// context and buffers of evaluation slot (block j, lane c)
+int nm_slot_setup(frk_model *M, int j, int c, Block &B, bool one_stream, NMSlot &s) {
+    frk_ctx *ctx = M->ctx;
+    const size_t nn = (size_t)B.ni * B.ni;
+    const int q = j * LCAP + c;
+    if (one_stream || q == 0) {
+        s.ctx = ctx; s.Ki = B.Ki; s.Kinv = B.Kinv; s.work = B.work;
+    } else {
+        // a lane context serves one (resolution, lane) pair and keeps its buffers in its own grow-only scratch: the
+        // pointers -- hence the cached CUDA graphs -- survive from one model to the next
+        RC(frk_ctx_lane(ctx, q - 1, true, &s.ctx));
+        void *buf = nullptr;
+        RC(frk_scratch(s.ctx, 3 * nn * sizeof(double), &buf));
+        s.Ki = (double *)buf; s.Kinv = s.Ki + nn; s.work = s.Kinv + nn;
+    }
+    return 0;
+}
+
+// Enqueue, on the lanes, the factorisations the next M-step will need first (see frk_model::pre).  Called when K has just been
+// assembled: the start value of optim() is read from the new K exactly as the next M-step will read it (R/SREfit.R:596-614), the
+// second point is the one nmmin builds its initial simplex with (start + 0.1 |start|).  A wrong guess costs nothing but lane time:
+// the next M-step compares tau bit for bit and evaluates normally if it differs.
+int prefetch_f_tau(frk_model *M) {
+    frk_ctx *ctx = M->ctx;
+    const int nblk = (int)M->blocks.size();
+    M->pre.assign(nblk, {});
+    const bool ok = M->prefetch && !M->tensor && M->lanes >= 2 && nm_world(M) == 1 && !M->spec_emulate && !ctx->profiling &&
+                    ctx->stream != nullptr && ctx->use_graphs;
+    if (!ok) return 0;
+    for (int j = 0; j < nblk; j++) {
+        Block &B = M->blocks[j];
+        if (B.ni < 256) continue;                                   // small blocks: nothing to hide
+        double k2[2] = {0, 0};
+        RC(frk_d2h(ctx, k2, B.Ki, 2 * sizeof(double)));             // K_i[1,1], K_i[2,1] of the K just assembled (B.Ki = exp(-D/tau)/omega)
+        const double k00 = k2[0], k01 = k2[1];
+        double par0 = 1e-9;
+        { const double v = -B.D01 / std::log(k01 / k00); par0 = (v > 1e-9) ? v : 1e-9; }
+        if (!std::isfinite(par0) || par0 == 1e-9) par0 = M->max_l / 10.0;
+        double step = 0.1 * std::fabs(par0);
+        if (step == 0.0) step = 0.1;
+        const double pts[2] = {par0, par0 + step};
+        for (int c = 0; c < 2; c++) {
+            if (j * LCAP + c == 0) continue;                        // that slot is the model's own stream and buffers
+            if (!(pts[c] > 1e-10)) continue;
+            NMSlot s;
+            RC(nm_slot_setup(M, j, c, B, false, s));
+            RC(f_tau_factor_enqueue(B, s, pts[c]));
+            M->pre[j][c].on = true;
+            M->pre[j][c].tau = pts[c];
+        }
+    }
+    return 0;
 }
 
 int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb, double *Knew, double *Kinvnew, double &logdetK,
@@ -632,7 +702,7 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
     const int L = one_stream ? 1 : std::max(M->lanes, 1);
     const int W = world * L;
     const bool shared = world > 1 && !M->spec_emulate;
-    constexpr int LCAP = 8;                                             // slot (block j, lane c) -> lane context j*LCAP + c: stable, so graph caches hit
+    if ((int)M->pre.size() != nblk) M->pre.assign(nblk, {});
     if (!M->ev_lane) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_lane, cudaEventDisableTiming));
 
     for (int j = 0; j < nblk; j++) {
@@ -640,20 +710,8 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
         Block &B = *S.B;
         const size_t nn = (size_t)B.ni * B.ni;
         S.slot.resize(L);
-        for (int c = 0; c < L; c++) {
-            NMSlot &s = S.slot[c];
-            const int q = j * LCAP + c;
-            if (one_stream || q == 0) {
-                s.ctx = ctx; s.Ki = B.Ki; s.Kinv = B.Kinv; s.work = B.work;
-            } else {
-                // a lane context serves one (resolution, lane) pair and keeps its buffers in its own grow-only scratch: the
-                // pointers -- hence the cached CUDA graphs -- survive from one model to the next
-                RC(frk_ctx_lane(ctx, q - 1, true, &s.ctx));
-                void *buf = nullptr;
-                RC(frk_scratch(s.ctx, 3 * nn * sizeof(double), &buf));
-                s.Ki = (double *)buf; s.Kinv = s.Ki + nn; s.work = s.Kinv + nn;
-            }
-        }
+        for (int c = 0; c < L; c++) RC(nm_slot_setup(M, j, c, B, one_stream, S.slot[c]));
+        (void)nn;
         // Nelder-Mead returns its lowest vertex, a REQUESTED point (a speculative point that is never requested cannot be the result):
         // keep the inverse of the best requested point while it is still in a slot (slots are drained before any replay; the next
         // round starts after this copy)
@@ -708,8 +766,17 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
             if (tau <= 1e-10) { S.fl[k] = std::numeric_limits<double>::infinity(); continue; }
             if (c > 0) FRK_CHECK_CUDA(cudaStreamWaitEvent(s.ctx->stream, S.ev_copy, 0));
             s.used = true; s.pt = tau;
-            RC(f_tau_enqueue(*S.B, s, tau));
+            Model_PreSlot &pf = M->pre[j][c];
+            if (pf.on && pf.tau == tau && !one_stream && !M->spec_emulate) {
+                // this slot's buffers already hold K_i(tau)^-1 (or it is on its way): enqueued before the E-step.  Only the trace is left.
+                RC(frk_dot_async(s.ctx, (int64_t)S.B->ni * S.B->ni, s.Kinv, S.B->eta2));
+                M->nm_prefetch_hits += 1;
+            } else {
+                RC(f_tau_enqueue(*S.B, s, tau));
+            }
+            pf.on = false;
         }
+        for (int c = L; c < 8; c++) M->pre[j][c].on = false;
         return 0;
     };
     auto finished = [&](int j) -> bool {                 // non-blocking: have all of run j's evaluations completed?
@@ -916,7 +983,7 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
     FRK_REQUIRE(!M->blocks.empty(), "K_type = \"block-exponential\" needs the per-resolution distance matrices (frk_model_set_blocks)");
     // K_new is assembled in w1 and K_new^-1 in w2 (both free here); the old Khat / Khat_inv are read for omega and the start values
     M->taus.clear(); M->omegas.clear();
-    M->nm_requests = M->nm_rounds = M->nm_evals = M->nm_reevals = 0;
+    M->nm_requests = M->nm_rounds = M->nm_evals = M->nm_reevals = M->nm_prefetch_hits = 0;
     double *Knew = M->w1, *Kinvnew = M->w2;
     FRK_CHECK_CUDA(cudaMemsetAsync(Knew, 0, rr * sizeof(double), ctx->stream));
     FRK_CHECK_CUDA(cudaMemsetAsync(Kinvnew, 0, rr * sizeof(double), ctx->stream));
@@ -1026,6 +1093,7 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
     M->logdetK = logdetK;
     M->khat_block_diag = true;
     have_inverse = true;                                             // Khat_inv = chol2inv(chol(K)) (:273) block by block
+    RC(prefetch_f_tau(M));                                           // the next M-step's first factorisations start now, beside the next E-step
     return 0;
 }
 
@@ -1216,6 +1284,12 @@ extern "C" int frk_model_destroy(frk_model *M) {
     cudaSetDevice(M->ctx->device);
     if (M->aux) cudaStreamSynchronize(M->aux->stream);          // nothing of this model may still be running on the lanes when its
     cudaStreamSynchronize(M->ctx->stream);                      // buffers go back to the pool (the lane contexts belong to M->ctx)
+    for (size_t j = 0; j < M->pre.size(); j++)                  // prefetched factorisations read this model's distance matrices
+        for (int c = 0; c < 8; c++)
+            if (M->pre[j][c].on) {
+                frk_ctx *lc = nullptr;
+                if ((int)j * 8 + c > 0 && frk_ctx_lane(M->ctx, (int)j * 8 + c - 1, true, &lc) == 0 && lc) cudaStreamSynchronize(lc->stream);
+            }
     for (void *p : M->allocs) cudaFreeAsync(p, M->ctx->stream);
     frk_rowbuckets_destroy(M->bk);
     if (M->ev_lane) cudaEventDestroy(M->ev_lane);
@@ -1412,6 +1486,7 @@ extern "C" int frk_model_get(frk_model *M, const char *slot, double *h_out) {
     if (!strcmp(slot, "homoscedastic")) { h_out[0] = M->homoscedastic ? 1.0 : 0.0; return 0; }
     if (!strcmp(slot, "tau")) { for (size_t i = 0; i < M->taus.size(); i++) h_out[i] = M->taus[i]; return 0; }
     if (!strcmp(slot, "nm_stats")) { h_out[0] = M->nm_requests; h_out[1] = M->nm_rounds; h_out[2] = M->nm_evals; h_out[3] = M->nm_reevals; return 0; }
+    if (!strcmp(slot, "nm_prefetch_hits")) { h_out[0] = M->nm_prefetch_hits; return 0; }
     if (!strcmp(slot, "omega")) { for (size_t i = 0; i < M->omegas.size(); i++) h_out[i] = M->omegas[i]; return 0; }
     size_t n = 0;
     double *p = slot_ptr(M, slot, &n);
