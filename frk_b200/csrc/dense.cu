@@ -559,7 +559,6 @@ constexpr int DP = 128;                       // panel width
 // 32 addresses of a DMMA fragment load -- 8 consecutive (g) in one direction, 4 strided (tg) in the other, whichever operand and
 // orientation -- fall on every 8-byte bank pair exactly twice: two wavefronts, the minimum for 256 bytes.
 constexpr int MLD = DP + 4;                   // 132: the 128 x 128 diagonal block
-constexpr int WLD = NB + 4;                   // 68:  64-row blocks
 constexpr int NWARP = BLK_T / 32;
 
 // 1 / sqrt(x) without a branch, so that the compiler can interleave it with independent work: the hardware approximation
@@ -584,7 +583,7 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
 __device__ __forceinline__ int warp_potf2_16(double d[PB], int i, double *rdiag) {
     int bad = 0;
     double piv = __shfl_sync(0xffffffffu, d[0], 0);
-    double rs = rsqrt_fast(piv);
+    double rs = rsqrt_fast(piv), my_rs = 1.0;
 #pragma unroll
     for (int j = 0; j < PB; j++) {
         if (!(piv > 1e-290)) { if (!bad) bad = j + 1; }
@@ -596,7 +595,7 @@ __device__ __forceinline__ int warp_potf2_16(double d[PB], int i, double *rdiag)
             piv_next = fma(-l, l, t2);
             rs_next = rsqrt_fast(piv_next);
         }
-        if (rdiag && i == j) rdiag[j] = rs;
+        my_rs = (i == j) ? rs : my_rs;
         const double lij = (i == j) ? piv * rs : d[j] * rs;
         d[j] = lij;
 #pragma unroll
@@ -604,6 +603,7 @@ __device__ __forceinline__ int warp_potf2_16(double d[PB], int i, double *rdiag)
         piv = piv_next;
         rs = rs_next;
     }
+    if (rdiag) rdiag[i] = my_rs;
     return bad;
 }
 
@@ -637,7 +637,7 @@ __device__ __forceinline__ void tri_inv16(const double *__restrict__ L, int ldl,
 // #tiles <= #warps.  The function ends with a __syncthreads() in every case.
 enum { KEND_N = 1, KBEG_N = 2, KEND_M = 4, C_LOWER = 8 };
 
-template <int MF, int NF, int BT, int FLAGS, bool INPLACE>
+template <int MF, int NF, int BT, int FLAGS, bool INPLACE, int KFIX = 0>
 __device__ __forceinline__ void smem_gemm(int M, int N, int K, double alpha, const double *__restrict__ A, int lda, const double *__restrict__ B,
                                           int ldb, double beta, double *C, int ldc) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
@@ -658,6 +658,25 @@ __device__ __forceinline__ void smem_gemm(int M, int N, int K, double alpha, con
             if (FLAGS & KEND_M) kend = min(kend, m0 + 8 * MF);
             const double *pa = A + (size_t)tg * lda + m0 + g;
             const double *pb = BT ? B + (size_t)(n0 + g) * ldb + tg : B + (size_t)tg * ldb + n0 + g;
+            if (KFIX > 0) {
+                // short fixed k-range (K = KFIX, no triangular flags): every fragment load is issued before the first DMMA, so the
+                // product costs one shared-memory latency plus the accumulation chain instead of one latency per k-step
+                constexpr int KS = KFIX > 0 ? KFIX / 4 : 1;
+                double a[KS][MF], b[KS][NF];
+#pragma unroll
+                for (int ks = 0; ks < KFIX / 4; ks++) {
+#pragma unroll
+                    for (int i = 0; i < MF; i++) a[ks][i] = pa[(size_t)(4 * ks) * lda + 8 * i];
+#pragma unroll
+                    for (int j = 0; j < NF; j++) b[ks][j] = BT ? pb[(size_t)(8 * j) * ldb + 4 * ks] : pb[(size_t)(4 * ks) * ldb + 8 * j];
+                }
+#pragma unroll
+                for (int ks = 0; ks < KFIX / 4; ks++)
+#pragma unroll
+                    for (int i = 0; i < MF; i++)
+#pragma unroll
+                        for (int j = 0; j < NF; j++) dmma(acc[i][j][0], acc[i][j][1], a[ks][i], b[ks][j]);
+            } else
 #pragma unroll 2
             for (int k0 = kbeg; k0 < kend; k0 += 4) {
                 double a[MF], b[NF];
@@ -724,10 +743,11 @@ __device__ __forceinline__ int potf2_blk_smem(double *a, int lda, int n, double 
         const int nbelow = n - J - PB;
         if (nbelow <= 0) break;
         // rows below: X = A_below W16'   (nbelow x 16 x 16, in place; at most 7 warp tiles)
-        smem_gemm<2, 2, 0, 0, true>(nbelow, PB, PB, 1.0, ajj + PB, lda, wj, WDL, 0.0, ajj + PB, lda);
+        smem_gemm<2, 2, 0, 0, true, PB>(nbelow, PB, PB, 1.0, ajj + PB, lda, wj, WDL, 0.0, ajj + PB, lda);
         if (stamp) DBG_CLK(21);
-        // rest of the block: A(i,k) -= sum_c X(i,c) X(k,c), lower
-        smem_gemm<2, 2, 0, C_LOWER, false>(nbelow, nbelow, PB, -1.0, ajj + PB, lda, ajj + PB, lda, 1.0, ajj + (size_t)PB * lda + PB, lda);
+        // rest of the block (right-looking; a left-looking variant -- one update per step with a growing k-range -- measured 5 % slower):
+        //   A(i,k) -= sum_c X(i,c) X(k,c), lower
+        smem_gemm<2, 2, 0, C_LOWER, false, PB>(nbelow, nbelow, PB, -1.0, ajj + PB, lda, ajj + PB, lda, 1.0, ajj + (size_t)PB * lda + PB, lda);
         if (stamp) DBG_CLK(22);
     }
     return *sbad;
@@ -846,10 +866,10 @@ __global__ void __launch_bounds__(BLK_T) panel_solve128_kernel(const double *__r
     DBG_CLK(9);
     for (int J = 0; J < DP; J += PB) {
         double *XJ = X + (size_t)J * XLD;
-        smem_gemm<2, 2, 0, 0, true>(SR, PB, PB, 1.0, XJ, XLD, Wd + (size_t)(J / PB) * PB * WDL, WDL, 0.0, XJ, XLD);          // X_J = P_J W_J'
+        smem_gemm<2, 2, 0, 0, true, PB>(SR, PB, PB, 1.0, XJ, XLD, Wd + (size_t)(J / PB) * PB * WDL, WDL, 0.0, XJ, XLD);      // X_J = P_J W_J'
         const int nrest = DP - J - PB;
         if (nrest > 0)                                                                                                        // P(:, right) -= X_J L(right, J)'
-            smem_gemm<2, 2, 0, 0, false>(SR, nrest, PB, -1.0, XJ, XLD, Ls + (size_t)J * MLD + J + PB, MLD, 1.0, XJ + (size_t)PB * XLD, XLD);
+            smem_gemm<2, 2, 0, 0, false, PB>(SR, nrest, PB, -1.0, XJ, XLD, Ls + (size_t)J * MLD + J + PB, MLD, 1.0, XJ + (size_t)PB * XLD, XLD);
     }
     DBG_CLK(11);
     for (int idx = tid; idx < SR * DP; idx += BLK_T) {
@@ -865,13 +885,18 @@ __global__ void __launch_bounds__(BLK_T) panel_solve128_kernel(const double *__r
 // updated in place in global memory.  On the critical path of the factorisation: ~6 us instead of ~20 for the general GEMM kernel.
 constexpr int UT = 32, ULD = UT + 4;          // tile size; slab stride 36 = 4 (mod 16)
 constexpr size_t UDIAG_SMEM = (size_t)2 * DP * ULD * sizeof(double);
-__global__ void __launch_bounds__(BLK_T) next_diag_update_kernel(const double *__restrict__ X, int ldx, double *__restrict__ Cg, int ldc, int np) {
+__global__ void __launch_bounds__(BLK_T) next_diag_update_kernel(const double *__restrict__ X, int ldx, double *__restrict__ Cg, int ldc, int np, int nk) {
     extern __shared__ __align__(16) double usm[];
     double *Xa = usm, *Xb = usm + (size_t)DP * ULD;    // Xa[k * ULD + i] = X(i0 + i, k), Xb likewise for the column slab
     // tile index -> (bi, bj), bj <= bi
     int bi = 0, t = blockIdx.x;
     while (t > bi) { t -= bi + 1; bi++; }
     const int bj = t, i0 = bi * UT, j0 = bj * UT, tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, tg = lane & 3;
+    const int m0 = (wid & 3) * 8, n0 = (wid >> 2) * 16;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int kc = 0; kc < nk; kc++, X += (size_t)DP * ldx) {          // K in chunks of 128 columns (nk = 2: the two panels of a pair)
+    if (kc) __syncthreads();
     for (int q0 = 0; q0 < UT * DP / BLK_T; q0 += 8) {
         double va[8], vb[8];
 #pragma unroll
@@ -889,9 +914,6 @@ __global__ void __launch_bounds__(BLK_T) next_diag_update_kernel(const double *_
     }
     __syncthreads();
     // 32 x 32 x 128 on 8 warps: 8 x 16 warp tiles (1 x 2 fragments); rows / columns beyond np are zero-padded and not stored
-    const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, tg = lane & 3;
-    const int m0 = (wid & 3) * 8, n0 = (wid >> 2) * 16;
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     const double *pa = Xa + (size_t)tg * ULD + m0 + g, *pb = Xb + (size_t)tg * ULD + n0 + g;
 #pragma unroll 8
     for (int k0 = 0; k0 < DP; k0 += 4) {
@@ -899,6 +921,7 @@ __global__ void __launch_bounds__(BLK_T) next_diag_update_kernel(const double *_
         dmma(acc[0][0], acc[0][1], a, b0);
         dmma(acc[1][0], acc[1][1], a, b1);
     }
+  }
 #pragma unroll
     for (int j = 0; j < 2; j++)
 #pragma unroll
@@ -1087,7 +1110,7 @@ static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status, doub
     const bool fork = main != nullptr && side != nullptr && ctx->stream2 != nullptr;
     static const int dbg_skip = getenv("FRK_POTRF_SKIP") ? atoi(getenv("FRK_POTRF_SKIP")) : 0;   // timing experiments only: 1 = no R / U_rest, 2 = R / U_rest on the main stream
     bool have_rest[2] = {false, false};
-    bool pending_join = false;
+    bool pending_join = false, rest_pending = false;
     int pidx = 0;
     for (int J = 0; J < r; J += DP, pidx++) {
         const int nb = std::min(DP, r - J), below = r - J - nb;
@@ -1106,46 +1129,53 @@ static int potrf2_enqueue(frk_ctx *ctx, int r, double *d_A, double *status, doub
             if (int rc = launch_gemm(ctx, g, false, false, (double)below * (below + 1.0) * nb, "dgemm_kernel[potrf trailing SYRK]")) return rc;
             continue;
         }
+        // The trailing matrix takes its updates in PAIRS of panels (rank 256: fewer, longer GEMMs -- the beta = 1 epilogue of the GEMM
+        // kernel costs as much as ~60 columns of k): an even panel only updates the next panel's columns (rank 128); an odd panel updates
+        // the next panel's columns with both panels of the pair and then everything beyond (R, side stream).
+        const bool odd = (pidx & 1) != 0;
+        const int kw = odd ? 2 * DP : nb;                               // columns of X in this update
+        const double *Pk = odd ? P - (size_t)DP * ld : P;              // ... starting one panel to the left for the pair
         if (dbg_skip == 1) {
             const int nt = (int)cdiv(npan, UT);
-            FRK_LAUNCH(ctx, next_diag_update_kernel, (unsigned)(nt * (nt + 1) / 2), BLK_T, UDIAG_SMEM, (const double *)P, r,
-                       d_A + (J + nb) + (J + nb) * ld, r, npan);
+            FRK_LAUNCH(ctx, next_diag_update_kernel, (unsigned)(nt * (nt + 1) / 2), BLK_T, UDIAG_SMEM, Pk, r,
+                       d_A + (J + nb) + (J + nb) * ld, r, npan, odd ? 2 : 1);
             continue;
         }
         if (dbg_skip == 2) { side = main; }
-        if (beyond > 0) {                                              // R(p) on the side stream
+        if (rest_pending) { FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_rest[0], 0)); rest_pending = false; }   // R of the previous pair reached these columns
+        if (beyond > 0 && odd) {                                       // R(pair) on the side stream: rows, columns beyond the next panel
             FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_panel, main));
             FRK_CHECK_CUDA(cudaStreamWaitEvent(side, ctx->ev_panel, 0));
-            const double *P2 = P + npan;
-            GemmArgs g = gemm_args(beyond, beyond, nb, -1.0, P2, r, P2, r, 1.0, d_A + (J + nb + npan) + (J + nb + npan) * ld, r);
+            const double *P2 = Pk + npan;
+            GemmArgs g = gemm_args(beyond, beyond, kw, -1.0, P2, r, P2, r, 1.0, d_A + (J + nb + npan) + (J + nb + npan) * ld, r);
             g.lower = 1;
             ctx->stream = side;
-            const int rc = launch_gemm(ctx, g, false, false, (double)beyond * (beyond + 1.0) * nb, "dgemm_kernel[potrf trailing SYRK]");
+            const int rc = launch_gemm(ctx, g, false, false, (double)beyond * (beyond + 1.0) * kw, "dgemm_kernel[potrf trailing SYRK]");
             ctx->stream = main;
             if (rc) return rc;
-            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_rest[pidx & 1], side));
+            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_rest[0], side));
+            rest_pending = true;
+            have_rest[0] = true;
         }
-        if (have_rest[(pidx + 1) & 1]) FRK_CHECK_CUDA(cudaStreamWaitEvent(main, ctx->ev_rest[(pidx + 1) & 1], 0));   // R(p-1) reached these columns
-        have_rest[pidx & 1] = beyond > 0;
-        // U(p): the next panel's columns take their rank-128 update.  Only the next DIAGONAL block is on the critical path (D(p+1)
-        // needs it); the rows below it are needed by S(p+1), so they are updated on the second side stream beside D(p+1).
+        // U(p): the next panel's columns.  Only the next DIAGONAL block is on the critical path (D(p+1) needs it); the rows below it
+        // are needed by S(p+1), so they are updated on the second side stream beside D(p+1).
         if (beyond > 0) {
             cudaStream_t s2 = dbg_skip == 2 ? main : ctx->stream2;
-            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, main));                     // S(p) done and R(p-1) waited for
+            FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, main));                     // S(p) done and the previous pair's R waited for
             FRK_CHECK_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
-            const double *P2 = P + npan;
-            GemmArgs g = gemm_args(beyond, npan, nb, -1.0, P2, r, P, r, 1.0, d_A + (J + nb + npan) + (J + nb) * ld, r);
+            const double *P2 = Pk + npan;
+            GemmArgs g = gemm_args(beyond, npan, kw, -1.0, P2, r, Pk, r, 1.0, d_A + (J + nb + npan) + (J + nb) * ld, r);
             ctx->stream = s2;
-            const int rc = launch_gemm(ctx, g, false, false, 2.0 * beyond * npan * nb, "dgemm_kernel[potrf next-panel update]");
+            const int rc = launch_gemm(ctx, g, false, false, 2.0 * beyond * npan * kw, "dgemm_kernel[potrf next-panel update]");
             ctx->stream = main;
             if (rc) return rc;
             FRK_CHECK_CUDA(cudaEventRecord(ctx->ev_join, s2));
         }
         {   // next diagonal block (npan x npan, lower)
             const int nt = (int)cdiv(npan, UT);
-            FRK_WORK(ctx, (double)npan * (npan + 1.0) * nb, 0);
-            FRK_LAUNCH(ctx, next_diag_update_kernel, (unsigned)(nt * (nt + 1) / 2), BLK_T, UDIAG_SMEM, (const double *)P, r,
-                       d_A + (J + nb) + (J + nb) * ld, r, npan);
+            FRK_WORK(ctx, (double)npan * (npan + 1.0) * kw, 0);
+            FRK_LAUNCH(ctx, next_diag_update_kernel, (unsigned)(nt * (nt + 1) / 2), BLK_T, UDIAG_SMEM, Pk, r,
+                       d_A + (J + nb) + (J + nb) * ld, r, npan, odd ? 2 : 1);
         }
         pending_join = beyond > 0;
     }
@@ -1203,6 +1233,13 @@ extern "C" int frk_potri(frk_ctx *ctx, int r, const double *d_L, double *d_Ainv,
                        [&]() { return potri_enqueue(ctx, r, d_L, d_Ainv, d_work); });
 }
 
+// profile names per doubling level (interned: the profiler keys on the pointer's string)
+static const char *level_tag(const char *prefix, long long b) {
+    static std::map<std::string, std::string> names;
+    const std::string key = std::string(prefix) + std::to_string(b) + "]";
+    return names.emplace(key, key).first->second.c_str();
+}
+
 static int potri_enqueue(frk_ctx *ctx, int r, const double *d_L, double *d_Ainv, double *d_work) {
     const size_t ld = (size_t)r;
     double *X = d_work, *T = d_Ainv;
@@ -1221,12 +1258,12 @@ static int potri_enqueue(frk_ctx *ctx, int r, const double *d_L, double *d_Ainv,
         {   // T = L21 X11   (X11 lower: k from the tile's first column)
             GemmArgs g = gemm_args((int)b, (int)b, (int)b, 1.0, d_L + off21, r, X, r, 0.0, T + off21, r);
             g.k_from_n = 1; g.sA = g.sB = g.sC = stride; g.nbatch = npairs; g.M_last = b2_last; g.K_last = (int)b;
-            if (int rc = launch_gemm(ctx, g, false, true, (pairs_full * b + b2_last) * (double)b * b, "dgemm_kernel[potri L21 X11]")) return rc;
+            if (int rc = launch_gemm(ctx, g, false, true, (pairs_full * b + b2_last) * (double)b * b, level_tag("dgemm_kernel[potri L21 X11 b=", b))) return rc;
         }
         {   // X21 = -X22 T  (X22 lower: k up to the tile's last row)
             GemmArgs g = gemm_args((int)b, (int)b, (int)b, -1.0, X + off22, r, T + off21, r, 0.0, X + off21, r);
             g.k_to_m = 1; g.sA = g.sB = g.sC = stride; g.nbatch = npairs; g.M_last = b2_last; g.K_last = b2_last;
-            if (int rc = launch_gemm(ctx, g, false, true, (pairs_full * b * b + (double)b2_last * b2_last) * (double)b, "dgemm_kernel[potri X22 T]")) return rc;
+            if (int rc = launch_gemm(ctx, g, false, true, (pairs_full * b * b + (double)b2_last * b2_last) * (double)b, level_tag("dgemm_kernel[potri X22 T b=", b))) return rc;
         }
     }
     // A^-1 = X' X (lower triangle; X lower -> k >= max(row, col)), then mirror

@@ -20,5 +20,5 @@ for n in (256, 3276):
     mhz = 1965.0
     us = lambda a, b: (c[b] - c[a]) / mhz
     print(f"n={n}: diag128 (last launch): load {us(0,1):.2f}  potf2 {us(1,2):.2f}  store+log {us(2,6):.2f}  total {us(0,6):.2f} us")
-    print(f"      potf2_64 (last call, first 16-column step): factor {us(16,17):.2f}  store {us(17,18):.2f}  inv16 {us(18,19):.2f}  sync {us(19,20):.2f}  rows below {us(20,21):.2f}  update {us(21,22):.2f} us")
+    print(f"      potf2 (last call, first 16-column step): factor {us(16,17):.2f}  store {us(17,18):.2f}  inv16 {us(18,19):.2f}  sync {us(19,20):.2f}  rows below {us(20,21):.2f}  update {us(21,22):.2f} us")
     print(f"      panel_solve128 (last launch, CTA 0): load {us(8,9):.2f}  8 steps {us(9,11):.2f}  store {us(11,12):.2f}  total {us(8,12):.2f} us")
