@@ -657,6 +657,18 @@ int nm_slot_setup(frk_model *M, int j, int c, Block &B, bool one_stream, NMSlot 
     return 0;
 }
 
+// Lanes of block j: the configured number.  Deeper speculation for the small resolutions (their factorisations are short
+// latency-bound chains) was measured: FRK_SMALL_LANES = 4 / 8 for blocks of <= 1024 functions make the converged iterations 4 % faster
+// (the whole Nelder-Mead run fits the first, prefetched, round) but the first ~10 iterations from .EM_initialise 3 - 6 % slower
+// (more evaluations compete with the E-step), so the default leaves them at the configured count.
+inline int block_lanes(const frk_model *M, const Block &B, bool one_stream) {
+    if (one_stream) return 1;
+    const int L = std::max(M->lanes, 1);
+    if (M->spec_emulate || L == 1) return L;                        // (L = 1: the strictly sequential reference run of the tests)
+    static const int small_lanes = getenv("FRK_SMALL_LANES") ? std::min(std::max(atoi(getenv("FRK_SMALL_LANES")), 1), LCAP) : 0;
+    return B.ni <= 1024 ? std::max(small_lanes, L) : L;
+}
+
 // Enqueue, on the lanes, the factorisations the next M-step will need first (see frk_model::pre).  Called when K has just been
 // assembled: the start value of optim() is read from the new K exactly as the next M-step will read it (R/SREfit.R:596-614), the
 // second point is the one nmmin builds its initial simplex with (start + 0.1 |start|).  A wrong guess costs nothing but lane time:
@@ -665,29 +677,39 @@ int prefetch_f_tau(frk_model *M) {
     frk_ctx *ctx = M->ctx;
     const int nblk = (int)M->blocks.size();
     M->pre.assign(nblk, {});
-    const bool ok = M->prefetch && !M->tensor && M->lanes >= 2 && nm_world(M) == 1 && !M->spec_emulate && !ctx->profiling &&
+    // candidate k of a round goes to rank k % world, lane k / world (blockexp_nelder_mead): with the candidates distributed over the
+    // ranks every rank prefetches its own share of the first two points
+    const int world = nm_world(M), rank = nm_rank(M);
+    const bool ok = M->prefetch && !M->tensor && world * std::max(M->lanes, 1) >= 2 && !M->spec_emulate && !ctx->profiling &&
                     ctx->stream != nullptr && ctx->use_graphs;
     if (!ok) return 0;
     for (int j = 0; j < nblk; j++) {
         Block &B = M->blocks[j];
-        if (B.ni < 256) continue;                                   // small blocks: nothing to hide
+        if (B.ni < 128) continue;                                   // tiny blocks: nothing to hide
+        const int L = block_lanes(M, B, false);
         double k2[2] = {0, 0};
         RC(frk_d2h(ctx, k2, B.Ki, 2 * sizeof(double)));             // K_i[1,1], K_i[2,1] of the K just assembled (B.Ki = exp(-D/tau)/omega)
         const double k00 = k2[0], k01 = k2[1];
         double par0 = 1e-9;
         { const double v = -B.D01 / std::log(k01 / k00); par0 = (v > 1e-9) ? v : 1e-9; }
         if (!std::isfinite(par0) || par0 == 1e-9) par0 = M->max_l / 10.0;
-        double step = 0.1 * std::fabs(par0);
-        if (step == 0.0) step = 0.1;
-        const double pts[2] = {par0, par0 + step};
-        for (int c = 0; c < 2; c++) {
+        // the batch of the first round, exactly as blockexp_nelder_mead will build it: the start value, then the points nmmin may
+        // ask for next under the three-outcome hypotheses (the second simplex vertex first; with more than two evaluators also the
+        // reflections that follow either outcome) -- SpecNM::candidates is deterministic and needs no function value for this
+        SpecNM spec{M, nullptr, 1, 100, 1e-4, std::vector<double>{par0}};
+        std::vector<std::vector<double>> batch = {std::vector<double>{par0}};
+        spec.candidates(&par0, (size_t)(world * L), batch);
+        for (int c = 0; c < std::min(L, LCAP); c++) {
+            const int k = c * world + rank;                         // the candidate this lane of this rank will be given
+            if (k >= (int)batch.size()) continue;
             if (j * LCAP + c == 0) continue;                        // that slot is the model's own stream and buffers
-            if (!(pts[c] > 1e-10)) continue;
+            const double tau = batch[k][0];
+            if (!(tau > 1e-10)) continue;
             NMSlot s;
             RC(nm_slot_setup(M, j, c, B, false, s));
-            RC(f_tau_factor_enqueue(B, s, pts[c]));
+            RC(f_tau_factor_enqueue(B, s, tau));
             M->pre[j][c].on = true;
-            M->pre[j][c].tau = pts[c];
+            M->pre[j][c].tau = tau;
         }
     }
     return 0;
@@ -699,8 +721,7 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
     const int r = M->r, nblk = (int)nmb.size();
     const int world = nm_world(M);
     const bool one_stream = ctx->profiling || ctx->stream == nullptr;   // per-kernel profiling times one stream: keep everything on it
-    const int L = one_stream ? 1 : std::max(M->lanes, 1);
-    const int W = world * L;
+    const int Lmax = one_stream ? 1 : std::max(M->lanes, 1);        // (the pretend-world walk of spec_emulate uses this one for every block)
     const bool shared = world > 1 && !M->spec_emulate;
     if ((int)M->pre.size() != nblk) M->pre.assign(nblk, {});
     if (!M->ev_lane) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_lane, cudaEventDisableTiming));
@@ -709,6 +730,7 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
         BlkNM &S = *nmb[j];
         Block &B = *S.B;
         const size_t nn = (size_t)B.ni * B.ni;
+        const int L = block_lanes(M, B, one_stream);
         S.slot.resize(L);
         for (int c = 0; c < L; c++) RC(nm_slot_setup(M, j, c, B, one_stream, S.slot[c]));
         (void)nn;
@@ -745,6 +767,7 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
         if (rc == 0) { S.done = true; return 0; }
         if (rc != 99) return rc;
         S.batch.push_back(need);
+        const int W = world * (int)S.slot.size();
         if (W > 1) S.spec->candidates(need.data(), (size_t)W, S.batch);
         S.fl.assign(S.batch.size(), 0.0);
         S.rounds += 1;
@@ -756,6 +779,7 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
         BlkNM &S = *nmb[j];
         // the slots' buffers may be overwritten once the copies of the last replay (slot 0's stream) have been made
         FRK_CHECK_CUDA(cudaEventRecord(S.ev_copy, S.slot[0].ctx->stream));
+        const int L = (int)S.slot.size();
         for (int c = 0; c < L; c++) {
             NMSlot &s = S.slot[c];
             s.used = false;
@@ -863,7 +887,7 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
             }
             if (maxbatch == 0) break;
             M->nm_rounds += 1;
-            const int nchunks = M->spec_emulate ? (int)((maxbatch + L - 1) / L) : 1;
+            const int nchunks = M->spec_emulate ? (int)((maxbatch + Lmax - 1) / Lmax) : 1;
             for (int ch = 0; ch < nchunks; ch++) {
                 int rc = 0;
                 if (one_stream) {      // every slot is this context (one pinned staging buffer): one resolution at a time
