@@ -55,6 +55,7 @@ SIGNATURES = {
     "frk_use_deterministic": (c_int, [vp, c_int]),
     "frk_profile": (c_int, [vp, c_int]),
     "frk_profile_report": (c_int, [vp, C.c_char_p, C.c_size_t]),
+    "frk_debug_clocks": (c_int, [vp]),
     "frk_comm_unique_id": (c_int, [vp]),
     "frk_comm_init": (c_int, [vp, c_int, c_int, vp]),
     "frk_comm_destroy": (c_int, [vp]),

@@ -79,6 +79,9 @@ int frk_use_graphs(frk_ctx *ctx, int enable);
 int frk_use_deterministic(frk_ctx *ctx, int enable);
 int frk_profile(frk_ctx *ctx, int enable);
 int frk_profile_report(frk_ctx *ctx, char *buf, size_t cap);
+/* clock64() stamps taken at the phase boundaries of the last diag128 / panel-solve launch of frk_potrf (CTA 0): 32 values; see
+ * tools/dense_phase_probe.py.  Development aid; synchronises the device. */
+int frk_debug_clocks(long long *h_out32);
 
 /* ---- multi-GPU: the context holds the NCCL communicator -------------------------------
  * One process per GPU.  Rank 0 calls frk_comm_unique_id and hands the FRK_COMM_ID_BYTES bytes to the other ranks by any means
