@@ -308,12 +308,15 @@ def run_b200(args):
             if k["flops"] > 0:
                 ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
                 ent.update(bound="fp64", achieved=ach, peak=fp64_peak, unit="TFLOP/s", frac=ach / fp64_peak)
-            elif "gram_bucket_kernel" in k["kernel"] or "quadform_ell_kernel" in k["kernel"]:
+            elif "gram_bucket_kernel" in k["kernel"] or "gram_ell_kernel" in k["kernel"] or "quadform_ell_kernel" in k["kernel"]:
                 # both ceilings: HBM (val 8 B + local id 1 B per non-zero, ...) and fp64 (the operation's own flops: 2 * sum_i nnz_i^2
                 # for the quadratic form, sum_i nnz_i (nnz_i + 1) for the Gram; lower bound nnz^2 / rows); the binding one is reported
                 if "gram" in k["kernel"]:
-                    by = gram_bytes * k["launches"]
-                    fl = k["launches"] * (mdl.S.nnz ** 2 / max(mdl.m, 1))
+                    # gram_ell_kernel: one pass = one launch per class of bucket widths; the library books the pass's bytes once
+                    passes = round(k["bytes"] / gram_bytes) if k.get("bytes", 0) > 0 else k["launches"]
+                    by = gram_bytes * passes
+                    fl = passes * (mdl.S.nnz ** 2 / max(mdl.m, 1))
+                    ent["passes"] = passes
                 else:                                               # launches: n_f_tau_launch_iters on S (M-step) + 1 on S0 (predict)
                     by = quad_S_bytes * n_f_tau_launch_iters + quad_S0_bytes
                     fl = 2.0 * (n_f_tau_launch_iters * mdl.S.nnz ** 2 / max(mdl.m, 1) + mdl.S0.nnz ** 2 / max(nloc, 1))

@@ -14,14 +14,18 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 constexpr int MAXG = 8;
 
 struct GroupDev {
     double x0, y0, hx, hy;
+    double rhx, rhy;         // 1 / hx, 1 / hy: the cell of a point is floor((u - x0) * rhx); the lists carry a margin that covers the rounding
     int nx, ny;
     const int *cell_start;   // ncell+1
     const int *cand;         // ascending centroid ids per cell
+    const double4 *cpk;      // fast bases: pk[cand[k]], sk[cand[k]] stored beside the candidate list (sequential, independent loads)
+    const double2 *csk;
     int all;                 // 1: single cell holding every centroid of the group (non-compact types)
 };
 
@@ -31,6 +35,11 @@ struct BasisDev {
     const double *c0, *c1, *c2;   // plane/line/STplane: x,(y),(t); sphere/STsphere: unit normal of the centroid
     const double *c3;             // STsphere: time coordinate of the centroid
     const double *scale;
+    // fast path (bisquare on a Euclidean manifold): per centroid {x, y, t, T} and {scale, RN(1/scale)}, T = the smallest double
+    // q with sqrt_rn(q) >= scale, so that  phi != 0  <=>  sqrt_rn(q) < scale  <=>  q < T  is decided without the square root
+    const double4 *pk;
+    const double2 *sk;
+    int fast;
     GroupDev g[MAXG];
 };
 
@@ -80,7 +89,7 @@ void build_euclid(const std::vector<int> &ids, int d, const double *loc, int r, 
     g.ny = d > 1 ? std::max(1, (int)std::ceil(hgt / h)) : 1;
     const int64_t ncell = (int64_t)g.nx * g.ny;
     std::vector<int> cnt(ncell + 1, 0);
-    const double m = 1e-9 * h;   // margin: absorbs rounding in the point's cell assignment
+    const double m = 1e-7 * h;   // margin: absorbs rounding in the point's cell assignment (floor of a product with 1 / h, up to 4e6 cells)
     for (int pass = 0; pass < 2; pass++) {
         for (int j : ids) {
             double R = scale[j], x = loc[j], y = d > 1 ? loc[j + r] : 0.0;
@@ -233,6 +242,25 @@ extern "C" int frk_basis_create(frk_ctx *ctx, int manifold, double radius, int t
     int rc = 0;
     rc |= upload(b, c0, &D.c0); rc |= upload(b, c1, &D.c1); rc |= upload(b, c2, &D.c2); rc |= upload(b, c3, &D.c3);
     rc |= upload(b, sc, &D.scale);
+    D.fast = (type == FRK_BISQUARE && !on_sphere) ? 1 : 0;
+    D.pk = nullptr; D.sk = nullptr;
+    std::vector<double4> h_pk;
+    std::vector<double2> h_sk;
+    if (D.fast) {
+        std::vector<double4> &pk = h_pk;
+        std::vector<double2> &sk = h_sk;
+        pk.resize(r); sk.resize(r);
+        for (int j = 0; j < r; j++) {
+            const double R = sc[j];
+            double T = R * R;
+            while (std::sqrt(T) >= R && T > 0) T = std::nextafter(T, 0.0);
+            while (std::sqrt(T) < R) T = std::nextafter(T, INFINITY);
+            pk[j] = make_double4(c0[j], c1[j], c2[j], T);
+            sk[j] = make_double2(R, 1.0 / R);
+        }
+        rc |= upload(b, pk, &D.pk);
+        rc |= upload(b, sk, &D.sk);
+    }
     if (rc) { frk_basis_destroy(b); return rc; }
 
     // groups = resolutions, in order of first appearance
@@ -261,9 +289,17 @@ extern "C" int frk_basis_create(frk_ctx *ctx, int manifold, double radius, int t
         else if (on_sphere) build_sphere(members[g], h_loc, r, h_scale, radius, hg);
         else build_euclid(members[g], std::min(d, 2), h_loc, r, h_scale, hg);
         GroupDev &G = D.g[g];
-        G.x0 = hg.x0; G.y0 = hg.y0; G.hx = hg.hx; G.hy = hg.hy; G.nx = hg.nx; G.ny = hg.ny; G.all = hg.all;
+        G.x0 = hg.x0; G.y0 = hg.y0; G.hx = hg.hx; G.hy = hg.hy; G.rhx = 1.0 / hg.hx; G.rhy = 1.0 / hg.hy; G.nx = hg.nx; G.ny = hg.ny; G.all = hg.all;
         rc |= upload(b, hg.start, &G.cell_start);
         rc |= upload(b, hg.cand, &G.cand);
+        G.cpk = nullptr; G.csk = nullptr;
+        if (D.fast) {
+            std::vector<double4> cpk(hg.cand.size());
+            std::vector<double2> csk(hg.cand.size());
+            for (size_t k = 0; k < hg.cand.size(); k++) { cpk[k] = h_pk[hg.cand[k]]; csk[k] = h_sk[hg.cand[k]]; }
+            rc |= upload(b, cpk, &G.cpk);
+            rc |= upload(b, csk, &G.csk);
+        }
         if (rc) { frk_basis_destroy(b); return rc; }
     }
     *out = b;
@@ -365,8 +401,8 @@ __device__ __forceinline__ double basis_phi(double y, double sc) {
 template <int MAN>
 __device__ __forceinline__ void cand_range(const GroupDev &G, const PointCoord &p, int &beg, int &end) {
     if (G.all) { beg = G.cell_start[0]; end = G.cell_start[1]; return; }
-    double fx = floor((p.u - G.x0) / G.hx);
-    double fy = MAN == FRK_REAL_LINE ? 0.0 : floor((p.v - G.y0) / G.hy);
+    double fx = floor((p.u - G.x0) * G.rhx);
+    double fy = MAN == FRK_REAL_LINE ? 0.0 : floor((p.v - G.y0) * G.rhy);
     if (man_traits<MAN>::sphere) {   // closed domain: clamp the upper edges (lat = 90) into the last cell
         if (fx >= G.nx) fx = G.nx - 1;
         if (fy >= G.ny) fy = G.ny - 1;
@@ -466,9 +502,213 @@ __global__ void __launch_bounds__(FILL_T) eval_fill_kernel(BasisDev B, int64_t n
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Second-generation kernels.  The two-pass structure stays (the caller sizes col / val from the count), but
+//  * bisquare functions on a Euclidean manifold ("fast" bases) are COUNTED without a square root or a division: the pattern is
+//    {sqrt_rn(q) < scale} = {q < T_j} with the threshold T_j tabulated at frk_basis_create, so the count pass is ~12 instructions per
+//    candidate and the expensive arithmetic (sqrt, /, the polynomial) runs once, in the fill pass, for the hits only;
+//  * y / scale is formed with the tabulated correctly rounded reciprocal and two Markstein correction steps (5 FMAs, result
+//    = RN(y / scale) exactly as __ddiv_rn gives it) instead of the 20-instruction division sequence;
+//  * the fill pass stages at most FCAP entries per row in shared memory (6.4 KB per warp instead of 72 KB per 128 rows: 32 resident
+//    warps per SM instead of 12) and flushes them, a half-warp per row, as contiguous runs of the row's CSR segment;
+//  * the row normalisation re-reads the warp's own segment (still in L2) once the row sums are complete.
+// ---------------------------------------------------------------------------------
+constexpr int FW = 4;                 // warps per block (static shared memory: 26 KB)
+constexpr int FCAP = 16, FST = FCAP + 1;
+constexpr int FU = 2;                 // candidates evaluated together (fast path)
+constexpr unsigned FULL = 0xffffffffu;
+
+// RN(a / b) from rb = RN(1 / b): q0 = RN(a rb) is within 1.5 ulp, one correction makes it faithful, and for a faithful quotient
+// Markstein's theorem gives RN(q + (a - b q) rb) = RN(a / b).  (No underflow / overflow for the operands met here.)
+__device__ __forceinline__ double div_by_recip(double a, double b, double rb) {
+    double q = __dmul_rn(a, rb);
+    double r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, rb, q);
+    r = __fma_rn(-q, b, a);
+    return __fma_rn(r, rb, q);
+}
+
+__device__ __forceinline__ double4 ldg_pk(const double4 *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+template <int MAN>
+__device__ __forceinline__ double fast_dist2(const PointCoord &p, const double4 &c) {   // the argument of distR's sqrt, same rounding
+    const double dx = __dsub_rn(p.a, c.x);
+    if (MAN == FRK_REAL_LINE) return __dmul_rn(dx, dx);
+    const double dy = __dsub_rn(p.b, c.y);
+    const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    if (MAN == FRK_PLANE) return q;
+    const double dt = __dsub_rn(p.c, c.z);
+    return __dadd_rn(q, __dmul_rn(dt, dt));
+}
+
+template <int MAN>
+__global__ void __launch_bounds__(256) eval_count_fast_kernel(BasisDev B, int64_t n, const double *__restrict__ s, int64_t ld,
+                                                              int *__restrict__ counts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const PointCoord p = load_point<MAN>(s, ld, i);
+        int cnt = 0;
+        for (int g = 0; g < B.ngroups; g++) {
+            int beg, end;
+            cand_range<MAN>(B.g[g], p, beg, end);
+            const double4 *cp = B.g[g].cpk;
+            for (int k = beg; k < end; k++) {
+                const double4 c = ldg_pk(cp + k);
+                cnt += fast_dist2<MAN>(p, c) < c.w;
+            }
+        }
+        counts[i] = cnt;
+    }
+}
+
+template <int MAN, int TYPE, bool FAST>
+__global__ void __launch_bounds__(FW * 32, 8) eval_fill_warp_kernel(BasisDev B, int64_t n, const double *__restrict__ s, int64_t ld,
+                                                                    const int *__restrict__ rowptr, int *__restrict__ col,
+                                                                    double *__restrict__ val, int normalise) {
+    __shared__ __align__(16) double sval_all[FW * 32 * FST];
+    __shared__ int scol_all[FW * 32 * FST];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
+    double *sval = sval_all + wid * 32 * FST;
+    int *scol = scol_all + wid * 32 * FST;
+    double2 *sx = reinterpret_cast<double2 *>(sval);      // (xx, 1/xx) per row; overlays the staging area once it has been flushed
+    for (int64_t row0 = ((int64_t)blockIdx.x * FW + wid) * 32; row0 < n; row0 += (int64_t)gridDim.x * FW * 32) {
+        const int64_t i = row0 + lane;
+        const bool active = i < n;
+        PointCoord p;
+        p.a = p.b = p.c = p.t = p.u = p.v = 0.0;
+        int base = 0, len = 0;
+        if (active) {
+            p = load_point<MAN>(s, ld, i);
+            base = rowptr[i];
+            len = rowptr[i + 1] - base;
+        }
+        int cnt = 0, dst = base;                       // staged entries; where the next flushed entry of this row goes
+        double ss = 0.0;
+        auto flush = [&]() {
+            __syncwarp();
+            const double *sv = sval + half * FST + l16;
+            const int *sc = scol + half * FST + l16;
+#pragma unroll
+            for (int a = 0; a < 16; a++) {
+                const int l = 2 * a + half;
+                const int c = __shfl_sync(FULL, cnt, l), b = __shfl_sync(FULL, dst, l);
+                if (l16 < c) {
+                    col[b + l16] = sc[a * 2 * FST];
+                    val[b + l16] = sv[a * 2 * FST];
+                }
+            }
+            dst += cnt;
+            cnt = 0;
+            __syncwarp();
+        };
+        auto stage = [&](double v, int j) {
+            sval[lane * FST + cnt] = v;
+            scol[lane * FST + cnt] = j;
+            ss = __dadd_rn(ss, __dmul_rn(v, v));
+            cnt++;
+        };
+        for (int g = 0; g < B.ngroups; g++) {
+            int beg = 0, end = 0;
+            if (active) cand_range<MAN>(B.g[g], p, beg, end);
+            const int nl = end - beg;
+            const int nmax = __reduce_max_sync(FULL, nl);
+            const int *cj = B.g[g].cand + beg;
+            if (FAST) {
+                const double4 *cp = B.g[g].cpk + beg;
+                const double2 *cs = B.g[g].csk + beg;
+                for (int t = 0; t < nmax; t += FU) {     // FU candidates between flush checks: their loads and their sqrt / division
+                    double4 c[FU];                       // chains are issued together
+                    double q[FU];
+                    bool any = false;
+#pragma unroll
+                    for (int u = 0; u < FU; u++) {
+                        c[u] = make_double4(0, 0, 0, -1.0);
+                        if (t + u < nl) c[u] = ldg_pk(cp + t + u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < FU; u++) {
+                        q[u] = fast_dist2<MAN>(p, c[u]);
+                        any |= q[u] < c[u].w;
+                    }
+                    if (any) {
+                        double v[FU];
+#pragma unroll
+                        for (int u = 0; u < FU; u++) {
+                            double2 sc = make_double2(1.0, 1.0);
+                            if (q[u] < c[u].w) sc = __ldg(cs + t + u);
+                            const double y = __dsqrt_rn(q[u]);
+                            const double tt = div_by_recip(y, sc.x, sc.y);
+                            const double w = __dsub_rn(1.0, __dmul_rn(tt, tt));
+                            v[u] = __dmul_rn(w, w);
+                        }
+#pragma unroll
+                        for (int u = 0; u < FU; u++)
+                            if (q[u] < c[u].w) stage(v[u], __ldg(cj + t + u));
+                    }
+                    if (__any_sync(FULL, cnt > FCAP - FU)) flush();
+                }
+            } else {
+                for (int t = 0; t < nmax; t++) {
+                    if (t < nl) {
+                        const int j = __ldg(cj + t);
+                        const double y = basis_dist<MAN>(p, B, j);
+                        const double v = basis_phi<TYPE>(y, __ldg(B.scale + j));
+                        if (v != 0.0) stage(v, j);
+                    }
+                    if (__any_sync(FULL, cnt > FCAP - 1)) flush();
+                }
+            }
+        }
+        flush();
+        if (normalise) {     // xx = sqrt(rowSums(S0*S0)); xx[xx==0] = 1; S0/xx     R/SRE.R:416-421
+            double xx = __dsqrt_rn(ss);
+            if (xx == 0.0) xx = 1.0;
+            sx[lane] = make_double2(xx, __ddiv_rn(1.0, xx));
+            const int maxlen = __reduce_max_sync(FULL, len);
+            __syncwarp();
+            for (int e0 = 0; e0 < maxlen; e0 += 48) {
+#pragma unroll 1
+                for (int a0 = 0; a0 < 16; a0 += 4) {      // four rows per half-warp at a time: twelve loads in flight per lane
+                    double vv[4][3];
+                    int bb[4], LL[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int l = 2 * (a0 + u) + half;
+                        LL[u] = __shfl_sync(FULL, len, l) - e0 - l16;
+                        bb[u] = __shfl_sync(FULL, base, l) + e0 + l16;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) vv[u][c] = 16 * c < LL[u] ? __ldcg(val + bb[u] + 16 * c) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const double2 X = sx[2 * (a0 + u) + half];
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+                            if (16 * c < LL[u]) val[bb[u] + 16 * c] = div_by_recip(vv[u][c], X.x, X.y);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// FRK_EVAL_LEGACY=1 selects the first-generation kernels (full evaluation in both passes, block-staged fill) for A/B timing
+static bool eval_legacy() {
+    static const bool v = getenv("FRK_EVAL_LEGACY") != nullptr;
+    return v;
+}
+
 template <int MAN>
 static int launch_count(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *s, int64_t ld, int *counts) {
     unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 32);
+    if (b->dev.fast && !eval_legacy()) {
+        FRK_LAUNCH(ctx, (eval_count_fast_kernel<MAN>), grid, 256, 0, b->dev, n, s, ld, counts);
+        return 0;
+    }
     switch (b->dev.type) {
         case FRK_BISQUARE: FRK_LAUNCH(ctx, (eval_count_kernel<MAN, FRK_BISQUARE>), grid, 256, 0, b->dev, n, s, ld, counts); break;
         case FRK_GAUSSIAN: FRK_LAUNCH(ctx, (eval_count_kernel<MAN, FRK_GAUSSIAN>), grid, 256, 0, b->dev, n, s, ld, counts); break;
@@ -481,6 +721,14 @@ static int launch_count(frk_ctx *ctx, const frk_basis *b, int64_t n, const doubl
 template <int MAN, int TYPE>
 static int launch_fill_t(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *s, int64_t ld, const int *rowptr,
                          int *col, double *val, int normalise) {
+    if (b->cols_sorted && !eval_legacy()) {
+        const unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, FW * 32), (int64_t)ctx->sm_count * 8 * 8);
+        if (b->dev.fast && TYPE == FRK_BISQUARE && !man_traits<MAN>::sphere)
+            FRK_LAUNCH(ctx, (eval_fill_warp_kernel<MAN, TYPE, true>), grid, FW * 32, 0, b->dev, n, s, ld, rowptr, col, val, normalise);
+        else
+            FRK_LAUNCH(ctx, (eval_fill_warp_kernel<MAN, TYPE, false>), grid, FW * 32, 0, b->dev, n, s, ld, rowptr, col, val, normalise);
+        return 0;
+    }
     const size_t smem = FILL_CAP * (sizeof(double) + sizeof(int));
     static bool attr_set = false;
     if (!attr_set) {

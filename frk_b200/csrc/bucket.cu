@@ -26,6 +26,12 @@ constexpr int KMAX = 40;          // non-zeros per row handled by the thread-per
 constexpr int HSIZE = 1024;       // open-addressing table for column -> local index (> UMAX + threads: never fills)
 constexpr int MAXP_B = 4;
 struct AlphaB { double a[MAXP_B]; };
+constexpr int QD_LDX = 36;                   // X is stored TRANSPOSED, Xt[col][row]: lane = row scatters are conflict-free, and with a
+                                             // stride of 36 both the A fragments and the epilogue reads hit every bank pair at most twice
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // ---------------------------------------------------------------------------------
 // chunk metadata: CH rows of a bucket at a time; entries of the chunk are then walked as one flat range so that
@@ -230,6 +236,10 @@ struct frk_rowbuckets {
     bool dense = false;            // every row holds all ncols columns (non-compact basis functions): val IS the dense matrix, row-major;
                                    // the Gram and the quadratic form are then plain GEMMs and no buckets are built
     int T = 0;
+    int64_t nnz = 0;
+    int max_nU = 0;                // widest column set of a non-empty bucket
+    int nblk_hist[10] = {0};       // non-empty buckets by (nU + 8) / 8 = 8-column blocks incl. the Gram kernel's virtual column
+    bool all_ell = false;          // every non-empty bucket has <= UMAX columns and every tile an ELL copy (no direct-path rows)
     int *btile = nullptr;          // [ncols+1] first tile of every bucket
     int *tile_K = nullptr;         // [T] entries per row in the tile; -1: a row is longer than KMAX (direct path)
     int *tile_off = nullptr;       // [T+1] offset of the tile in ell_val / ell_lid (entries)
@@ -264,6 +274,17 @@ __global__ void __launch_bounds__(256) ell_tile_K_kernel(int ncols, const int *_
             if (lane == 0) { tile_K[t] = k > KMAX ? -1 : k; tile_len[t] = k > KMAX ? 0 : k * 32; }
         }
     }
+}
+
+// number of buckets / tiles that need the direct path (bucket wider than UMAX columns, row longer than KMAX)
+__global__ void ell_direct_count_kernel(int ncols, const int *__restrict__ bptr, const int *__restrict__ nU, int T, const int *__restrict__ tile_K,
+                                        int *__restrict__ out) {
+    int bad = 0, mx = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncols; i += gridDim.x * blockDim.x)
+        if (bptr[i + 1] > bptr[i]) { bad += nU[i] > UMAX; mx = max(mx, nU[i]); atomicAdd(out + 2 + min((nU[i] + 8) >> 3, 9), 1); }
+    if (mx) atomicMax(out + 1, mx);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) bad += tile_K[i] < 0;
+    if (bad) atomicAdd(out, bad);
 }
 
 __global__ void __launch_bounds__(256) ell_fill_kernel(int ncols, const int *__restrict__ bptr, const int *__restrict__ btile,
@@ -316,6 +337,7 @@ extern "C" int frk_rowbuckets_create(frk_ctx *ctx, int64_t n, int ncols, const i
     auto fail = [&](int rc) { frk_rowbuckets_destroy(B); return rc; };
     int nnz = 0;
     if (int rc = frk_d2h(ctx, &nnz, d_rowptr + n, sizeof(int))) return fail(rc);
+    B->nnz = nnz;
     if (n > 0 && ncols > UMAX && (int64_t)nnz == n * (int64_t)ncols) {   // rows have ascending unique columns < ncols: all of them present
         B->dense = true;
         *out = B;
@@ -350,6 +372,19 @@ extern "C" int frk_rowbuckets_create(frk_ctx *ctx, int64_t n, int ncols, const i
         return fail(1);
     FRK_LAUNCH(ctx, ell_fill_kernel, grid, 256, 0, ncols, B->bptr, B->btile, B->perm, d_rowptr, d_val, B->lid, B->tile_K, B->tile_off,
                B->ell_val, B->ell_lid);
+    {
+        int *bad = nullptr, h_bad[12] = {1, 0};
+        FRK_CHECK_CUDA(cudaMallocAsync((void **)&bad, 12 * sizeof(int), ctx->stream));
+        FRK_CHECK_CUDA(cudaMemsetAsync(bad, 0, 12 * sizeof(int), ctx->stream));
+        FRK_LAUNCH(ctx, ell_direct_count_kernel, (unsigned)std::min<int64_t>(cdiv(std::max<int64_t>(ncols, T), 256), 1024), 256, 0, ncols, B->bptr,
+                   B->nU, (int)T, B->tile_K, bad);
+        rc = frk_d2h(ctx, h_bad, bad, 12 * sizeof(int));
+        cudaFreeAsync(bad, ctx->stream);
+        if (rc) return fail(rc);
+        B->all_ell = h_bad[0] == 0;
+        B->max_nU = h_bad[1];
+        for (int k = 0; k < 10; k++) B->nblk_hist[k] = h_bad[2 + k];
+    }
     *out = B;
     return 0;
 }
@@ -506,6 +541,181 @@ __global__ void __launch_bounds__(GR_T) gram_bucket_kernel(int nbuckets, const i
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Gram + rhs, second generation: the ELL tiles on the fp64 tensor cores.
+// One WARP per bucket (grid-stride), no block-level synchronisation.  For every 32-row tile of the bucket the warp densifies the rows
+// into Xt[column][row] (the quadratic form's layout) and accumulates the upper block-triangle of  X' diag(w) X  with DMMA m8n8k4:
+// the A fragment of block row mb and the B fragment of block column nb are the SAME shared-memory values (Xt[8 b + g][4 ks + tg]),
+// the B side multiplied by the row weight.  A virtual column holding rho (the residual) sits right after the bucket's columns, so
+// S'D^-1 rho and sum(rho^2 / d) come out of the same product as one more column.  The local |U| x |U| tile lives in registers for the
+// whole bucket and is flushed once (fp64 atomics into the upper triangle of G, or the staged tile in deterministic mode).
+// ---------------------------------------------------------------------------------
+constexpr int GE_WARPS = 4, GE_T = GE_WARPS * 32;
+constexpr int GE_MAXBLK = 7;                 // 8-column blocks held in registers per bucket (28 accumulator fragments): column sets of up to 55
+constexpr int GE_UP = GE_MAXBLK * 8;
+
+struct GramEllSmem {
+    double Xt[GE_WARPS][GE_UP][QD_LDX];
+    double w[GE_WARPS][32];
+    int ucol[GE_WARPS][UMAX];
+};
+
+template <int NBLK>
+__device__ __forceinline__ void gram_ell_bucket(GramEllSmem &S, int wid, int lane, int b, int r0, int r1, int nU, const int *__restrict__ perm,
+                                                const int *__restrict__ ucol_all, int t0, int t1, const int *__restrict__ tile_K,
+                                                const int *__restrict__ tile_off, const double *__restrict__ ell_val,
+                                                const unsigned char *__restrict__ ell_lid, int64_t m, int r, const double *__restrict__ z,
+                                                const double *__restrict__ X, int p, const AlphaB &alpha, const double *__restrict__ ve,
+                                                const double *__restrict__ vfs, double sigma2fs, double *__restrict__ acc_out,
+                                                double *__restrict__ stage, double *__restrict__ stage_rhs, double &s_quad, double &s_logd) {
+    constexpr int NACC = NBLK * (NBLK + 1) / 2;
+    const int g = lane >> 2, tg = lane & 3;
+    double (*Xt)[QD_LDX] = S.Xt[wid];
+    double *sw = S.w[wid];
+    int *ucol = S.ucol[wid];
+    for (int u = lane; u < nU; u += 32) ucol[u] = ucol_all[(size_t)b * UMAX + u];
+    double acc[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i][0] = acc[i][1] = 0.0;
+    for (int tl = t0; tl < t1; tl++) {
+        const int K = tile_K[tl];
+        const int p0 = r0 + (tl - t0) * 32, nrows = min(32, r1 - p0);
+        const int row = lane < nrows ? perm[p0 + lane] : -1;
+        const size_t off = (size_t)tile_off[tl];
+        if (tl + 1 < t1) {                                     // pull the next tile towards L2
+            const size_t noff = (size_t)tile_off[tl + 1];
+            const int nK = max(tile_K[tl + 1], 0);
+            const char *pv = reinterpret_cast<const char *>(ell_val + noff);
+            for (int c = lane; c < nK * 2; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + (size_t)c * 128));
+        }
+        const double2 *pv = reinterpret_cast<const double2 *>(ell_val + off) + lane;
+        const uchar4 *pl = reinterpret_cast<const uchar4 *>(ell_lid + off) + lane;
+        double rho = 0.0, w = 0.0;
+        if (row >= 0) {
+            rho = z[row];
+            for (int q = 0; q < p; q++) rho -= X[row + (int64_t)q * m] * alpha.a[q];
+            const double d = sigma2fs * vfs[row] + ve[row];
+            w = 1.0 / d;
+            s_logd += log(d);
+        }
+        for (int idx = lane; idx < NBLK * 8 * 16; idx += 32) {
+            const int cc = idx >> 4, rr = (idx & 15) * 2;
+            *reinterpret_cast<double2 *>(&Xt[cc][rr]) = make_double2(0.0, 0.0);
+        }
+        __syncwarp();
+        double *xs = &Xt[0][lane];
+        // entries in rounds of 16 per row (the accumulators leave room for 40 registers of tile data, not for 100); the LAST round first:
+        // padding (val 0 at the row's last real column) must be overwritten by the real entry
+        for (int j0 = ((K + 15) >> 4) * 4 - 4; j0 >= 0; j0 -= 4) {
+            double2 v[8];
+            uchar4 l[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (4 * (j0 + j) < K) { v[2 * j] = pv[(2 * (j0 + j)) * 32]; v[2 * j + 1] = pv[(2 * (j0 + j) + 1) * 32]; l[j] = pl[(j0 + j) * 32]; }
+#pragma unroll
+            for (int j = 3; j >= 0; j--)
+                if (4 * (j0 + j) < K) {
+                    xs[l[j].w * QD_LDX] = v[2 * j + 1].y;
+                    xs[l[j].z * QD_LDX] = v[2 * j + 1].x;
+                    xs[l[j].y * QD_LDX] = v[2 * j].y;
+                    xs[l[j].x * QD_LDX] = v[2 * j].x;
+                }
+        }
+        xs[nU * QD_LDX] = rho;                                 // the virtual column
+        sw[lane] = w;
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            const double wk = sw[4 * ks + tg];
+            double a[NBLK];
+#pragma unroll
+            for (int mb = 0; mb < NBLK; mb++) a[mb] = Xt[8 * mb + g][4 * ks + tg];
+#pragma unroll
+            for (int nb = 0; nb < NBLK; nb++) {
+                const double bf = a[nb] * wk;
+#pragma unroll
+                for (int mb = 0; mb <= nb; mb++) dmma884(acc[nb * (nb + 1) / 2 + mb][0], acc[nb * (nb + 1) / 2 + mb][1], a[mb], bf);
+            }
+        }
+        __syncwarp();
+    }
+    // flush: this lane holds local entries (8 mb + g, 8 nb + 2 tg + e)
+    double *G = acc_out, *rhs = acc_out + (size_t)r * r;
+#pragma unroll
+    for (int nb = 0; nb < NBLK; nb++)
+#pragma unroll
+        for (int mb = 0; mb <= nb; mb++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int la = 8 * mb + g, lb = 8 * nb + 2 * tg + e;
+                const double val = acc[nb * (nb + 1) / 2 + mb][e];
+                if (la > lb || lb > nU) continue;
+                if (lb == nU) {                                // the virtual column: right-hand side / sum(rho^2 w)
+                    if (la == nU) s_quad += val;
+                    else if (stage) stage_rhs[(size_t)b * UMAX + la] = val;
+                    else atomicAdd(rhs + ucol[la], val);
+                } else if (stage) stage[((size_t)b * UMAX + la) * UMAX + lb] = val;
+                else if (val != 0.0) {
+                    const int ca = ucol[la], cb = ucol[lb];
+                    atomicAdd(G + min(ca, cb) + (size_t)r * max(ca, cb), val);
+                }
+            }
+    __syncwarp();
+}
+
+// NBLK = blocks held in registers; the launch handles the buckets with LO < blocks <= NBLK (one instantiation per kernel: several
+// in one kernel make ptxas spill the accumulators)
+template <int NBLK>
+__global__ void __launch_bounds__(GE_T, 2) gram_ell_kernel(int lo, int nbuckets, const int *__restrict__ bptr, const int *__restrict__ perm,
+                                                           const int *__restrict__ ucol_all, const int *__restrict__ nU_all,
+                                                           const int *__restrict__ btile, const int *__restrict__ tile_K,
+                                                           const int *__restrict__ tile_off, const double *__restrict__ ell_val,
+                                                           const unsigned char *__restrict__ ell_lid, int64_t m, int r,
+                                                           const double *__restrict__ z, const double *__restrict__ X, int p, AlphaB alpha,
+                                                           const double *__restrict__ ve, const double *__restrict__ vfs, double sigma2fs,
+                                                           double *__restrict__ acc, double *__restrict__ stage,
+                                                           double *__restrict__ stage_rhs, double *__restrict__ stage_scal) {
+    extern __shared__ __align__(16) unsigned char gsm_raw[];
+    GramEllSmem &S = *reinterpret_cast<GramEllSmem *>(gsm_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gw = blockIdx.x * GE_WARPS + wid, nw = gridDim.x * GE_WARPS;
+    double s_quad = 0.0, s_logd = 0.0;
+    for (int b = gw; b < nbuckets; b += nw) {
+        const int r0 = bptr[b], r1 = bptr[b + 1];
+        if (r1 <= r0) continue;
+        const int nU = nU_all[b];
+        const int nblk = (nU + 8) >> 3;                        // blocks of 8 columns, the virtual column included
+        if (nblk <= lo || nblk > NBLK) continue;
+        gram_ell_bucket<NBLK>(S, wid, lane, b, r0, r1, nU, perm, ucol_all, btile[b], btile[b + 1], tile_K, tile_off, ell_val, ell_lid, m, r, z, X, p,
+                              alpha, ve, vfs, sigma2fs, acc, stage, stage_rhs, s_quad, s_logd);
+    }
+    // s_quad: the lane holding local entry (nU, nU) added it, one per bucket; s_logd: one term per row
+    s_quad = warp_sum(s_quad);
+    s_logd = warp_sum(s_logd);
+    if (lane == 0) {
+        if (stage) { stage_scal[2 * gw] += s_quad; stage_scal[2 * gw + 1] += s_logd; }      // (zeroed before the first class is launched)
+        else { atomicAdd(acc + (size_t)r * r + r, s_quad); atomicAdd(acc + (size_t)r * r + r + 1, s_logd); }
+    }
+}
+
+template <int NBLK>
+static int launch_gram_ell(frk_ctx *ctx, int lo, unsigned grid, int r, const frk_rowbuckets *bk, int64_t m, const double *d_z, const double *d_X,
+                           int p, const AlphaB &al, const double *d_ve, const double *d_vfs, double sigma2fs, double *d_acc, double *st,
+                           double *st_rhs, double *st_scal, double &bytes) {
+    static bool attr = false;
+    if (!attr) {
+        FRK_CHECK_CUDA(cudaFuncSetAttribute(gram_ell_kernel<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramEllSmem)));
+        attr = true;
+    }
+    FRK_TAG(ctx, "gram_ell_kernel");                        // the classes of one pass are one kernel for the profile
+    FRK_WORK(ctx, 0, bytes);                                // ... whose algorithmic bytes are booked on the first launch
+    bytes = 0;
+    FRK_LAUNCH(ctx, gram_ell_kernel<NBLK>, grid, GE_T, sizeof(GramEllSmem), lo, r, bk->bptr, bk->perm, bk->ucol, bk->nU, bk->btile, bk->tile_K,
+               bk->tile_off, bk->ell_val, bk->ell_lid, m, r, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, d_acc, st, st_rhs, st_scal);
+    return 0;
+}
+
 // Deterministic flush: one warp owns row a of G.  For every bucket k (ascending) whose column set holds a, with local id la, it adds
 // the staged pair values (a, cb), cb >= a, and the right-hand-side entry; block 0 sums the per-CTA scalars in CTA order.
 __global__ void __launch_bounds__(256) gram_ordered_flush_kernel(int r, const int *__restrict__ inv_ptr, const int *__restrict__ inv_bucket,
@@ -565,7 +775,7 @@ static int gram_prepare_ordered(frk_ctx *ctx, const frk_rowbuckets *bk, int r) {
     int *d_ptr = nullptr, *d_ib = nullptr, *d_il = nullptr;
     if (alloc((void **)&d_ptr, ptr.size() * sizeof(int)) || alloc((void **)&d_ib, ib.size() * sizeof(int)) ||
         alloc((void **)&d_il, il.size() * sizeof(int)) || alloc((void **)&bk->stage, (size_t)r * UMAX * UMAX * sizeof(double)) ||
-        alloc((void **)&bk->stage_rhs, (size_t)r * UMAX * sizeof(double)) || alloc((void **)&bk->stage_scal, 2 * (size_t)grid * sizeof(double)))
+        alloc((void **)&bk->stage_rhs, (size_t)r * UMAX * sizeof(double)) || alloc((void **)&bk->stage_scal, 2 * ((size_t)grid + 8) * sizeof(double)))
         return 1;
     FRK_CHECK_CUDA(cudaMemcpyAsync(d_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     FRK_CHECK_CUDA(cudaMemcpyAsync(d_ib, ib.data(), ib.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -686,16 +896,32 @@ extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *
     for (int q = 0; q < p; q++) al.a[q] = h_alpha[q];
     if (bk->dense) return gram_rhs_dense(ctx, m, r, d_val, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, d_acc);
     unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 8);
-    if (!ctx->deterministic) {
-        FRK_LAUNCH(ctx, gram_bucket_kernel, grid, GR_T, 0, r, d_bptr, d_perm, d_ucol, d_nU, d_lid, m, r, d_rowptr, d_col, d_val, d_z, d_X,
-                   p, al, d_ve, d_vfs, sigma2fs, d_acc, (double *)nullptr, (double *)nullptr, (double *)nullptr);
-        return 0;
+    static const bool legacy = getenv("FRK_GRAM_LEGACY") != nullptr;      // A/B timing: the first-generation (DFMA register-tile) kernel
+    const bool ell = bk->all_ell && bk->T > 0 && bk->max_nU < GE_MAXBLK * 8 && !legacy;
+    if (ell) grid = (unsigned)std::min<int64_t>(cdiv(r, GE_WARPS), (int64_t)ctx->sm_count * 2);
+    // work of the launch: val 8 B + local id 1 B per stored entry, row weights, the r x r accumulator once
+    double *st = nullptr, *st_rhs = nullptr, *st_scal = nullptr;
+    if (ctx->deterministic) {
+        if (int rc = gram_prepare_ordered(ctx, bk, r)) return rc;
+        st = bk->stage; st_rhs = bk->stage_rhs; st_scal = bk->stage_scal;
     }
-    if (int rc = gram_prepare_ordered(ctx, bk, r)) return rc;
-    FRK_LAUNCH(ctx, gram_bucket_kernel, grid, GR_T, 0, r, d_bptr, d_perm, d_ucol, d_nU, d_lid, m, r, d_rowptr, d_col, d_val, d_z, d_X,
-               p, al, d_ve, d_vfs, sigma2fs, d_acc, bk->stage, bk->stage_rhs, bk->stage_scal);
-    FRK_LAUNCH(ctx, gram_ordered_flush_kernel, (unsigned)cdiv((int64_t)r * 32, 256), 256, 0, r, bk->inv_ptr, bk->inv_bucket, bk->inv_lid,
-               d_ucol, d_nU, bk->stage, bk->stage_rhs, bk->stage_scal, (int)grid, d_acc);
+    if (ell) {
+        if (st_scal) FRK_CHECK_CUDA(cudaMemsetAsync(st_scal, 0, 2 * (size_t)grid * GE_WARPS * sizeof(double), ctx->stream));
+        // one launch per class of column-set sizes present in the matrix: <= 4, 5-6, 7 blocks of 8 columns
+        const int *h = bk->nblk_hist;
+        double bytes = (double)bk->nnz * 9 + (double)m * (4 + 8 * (3 + p)) + ((double)r * r + r) * 8;
+        if (h[0] + h[1] + h[2] + h[3] + h[4] > 0)
+            if (int rc = launch_gram_ell<4>(ctx, 0, grid, r, bk, m, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, d_acc, st, st_rhs, st_scal, bytes)) return rc;
+        if (h[5] + h[6] > 0)
+            if (int rc = launch_gram_ell<6>(ctx, 4, grid, r, bk, m, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, d_acc, st, st_rhs, st_scal, bytes)) return rc;
+        if (h[7] > 0)
+            if (int rc = launch_gram_ell<GE_MAXBLK>(ctx, 6, grid, r, bk, m, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, d_acc, st, st_rhs, st_scal, bytes)) return rc;
+    } else
+        FRK_LAUNCH(ctx, gram_bucket_kernel, grid, GR_T, 0, r, d_bptr, d_perm, d_ucol, d_nU, d_lid, m, r, d_rowptr, d_col, d_val, d_z, d_X,
+                   p, al, d_ve, d_vfs, sigma2fs, d_acc, st, st_rhs, st_scal);
+    if (ctx->deterministic)
+        FRK_LAUNCH(ctx, gram_ordered_flush_kernel, (unsigned)cdiv((int64_t)r * 32, 256), 256, 0, r, bk->inv_ptr, bk->inv_bucket, bk->inv_lid,
+                   d_ucol, d_nU, bk->stage, bk->stage_rhs, bk->stage_scal, (int)(ell ? grid * GE_WARPS : grid), d_acc);
     return 0;
 }
 
@@ -739,8 +965,6 @@ __device__ __forceinline__ void quad_row_direct(int row, int r, const int *__res
 // (the gather formulation is bound by shared-memory latency, not by HBM).  M is symmetric, so only the block-upper-triangular
 // part of M[U,U] (8-column blocks, off-diagonal blocks doubled when staged) is multiplied: 168 instead of 288 DMMAs per tile
 // at |U| = 48.  Each warp owns ELL tiles; lane = row while densifying (and for t = s'mu), DMMA fragment layout afterwards.
-constexpr int QD_LDX = 36;                   // X is stored TRANSPOSED, Xt[col][row]: lane = row scatters are conflict-free, and with a
-                                             // stride of 36 both the A fragments and the epilogue reads hit every bank pair at most twice
 constexpr int QD_LDM = UMAX + 8;             // 72: M row stride (= 8 mod 16 -> the 32 B-fragment addresses cover the 16 bank pairs twice)
 
 struct QuadDmmaSmem {
@@ -750,9 +974,6 @@ struct QuadDmmaSmem {
     int ucol[UMAX];
 };
 
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 
 // Y = X MU (block-upper part) for one 32-row tile and q_row = sum_n Y[row][n] X[row][n], NBLK 8-column blocks.
 // On return qs[mt] holds the finished sum for row 8 mt + g on all four lanes of group g.

@@ -235,3 +235,63 @@ def test_predict_host_entry_point_matches_device_predict(dev):
         close(mu, po[0], RTOL_UNIROOT)
         np.testing.assert_allclose(var, po[1], rtol=RTOL_UNIROOT)
         np.testing.assert_allclose(sd, np.sqrt(po[1]), rtol=RTOL_UNIROOT)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# eval_basis, second-generation kernels: threshold-table count, reciprocal division, multi-flush staging, in-kernel normalisation
+# ---------------------------------------------------------------------------------------------------------
+def test_eval_basis_long_rows_and_normalisation_bit_exact(dev):
+    """C3's basis shape (regular = 2, nres = 3: rows of up to ~39 entries, several staging flushes per row) on a regular BAU-like grid
+    whose points coincide with centroids and support edges; with and without the fused row normalisation (R/SRE.R:416-421)."""
+    import frk_b200 as F
+    from frk_b200.basis import eval_basis_device
+    xy, _ = readme_points(2000, seed=5)
+    ob = O.auto_basis(O.plane(), xy, regular=2, nres=3)
+    g = np.linspace(0.0, 1.0, 257)
+    s = np.column_stack([np.tile(g, len(g)), np.repeat(g, len(g))])
+    s = np.vstack([s, ob.loc, ob.loc + np.array([ob.scale, np.zeros(ob.n)]).T])      # on centroids; exactly one scale to the right
+    S_o = O.eval_basis_fast(ob, s).tocsr()
+    S_o.sort_indices()
+    assert np.diff(S_o.indptr).max() > 32
+    gb = _mk_basis(F, ob)
+    S_g = F.eval_basis(gb, s, dev)
+    assert _same_pattern(S_o, S_g)
+    assert np.array_equal(S_o.data, S_g.data)
+    S_n = eval_basis_device(gb, s, dev, normalise=True).to_scipy(dev)
+    S_on = O.normalise_rows(S_o).tocsr()
+    assert _same_pattern(S_on, S_n)
+    assert np.array_equal(S_on.data, S_n.data)
+
+
+@pytest.mark.parametrize("man", ["plane", "real_line"])
+def test_eval_basis_support_edge_ties_one_ulp(dev, man):
+    """Points whose distance to a centroid is the scale itself, or one / two ulps either side of it: the threshold table
+    (q < T  <=>  sqrt_rn(q) < scale) must reproduce the reference's  y < R  exactly."""
+    import frk_b200 as F
+    rng = np.random.default_rng(11)
+    nb = 40
+    scale = rng.uniform(0.05, 3.0, nb)
+    if man == "plane":
+        loc = rng.uniform(-50, 50, (nb, 2))
+        ob = O.local_basis(O.plane(), loc, scale, "bisquare")
+    else:
+        loc = rng.uniform(-50, 50, (nb, 1))
+        ob = O.local_basis(O.real_line(), loc, scale, "bisquare")
+    pts = []
+    for j in range(nb):
+        for k in range(-3, 4):
+            d = scale[j]
+            for _ in range(abs(k)):
+                d = np.nextafter(d, np.inf if k > 0 else 0.0)
+            if man == "plane":
+                for (a, b) in [(1.0, 0.0), (0.0, 1.0), (0.6, 0.8), (-0.8, 0.6)]:
+                    pts.append(loc[j] + d * np.array([a, b]))
+            else:
+                pts.append(loc[j] + d)
+                pts.append(loc[j] - d)
+    s = np.asarray(pts).reshape(len(pts), -1)
+    S_o = O.eval_basis(ob, s).tocsr()
+    S_o.sort_indices()
+    S_g = F.eval_basis(_mk_basis(F, ob), s, dev)
+    assert _same_pattern(S_o, S_g)
+    assert np.array_equal(S_o.data, S_g.data)
