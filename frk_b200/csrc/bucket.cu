@@ -544,12 +544,13 @@ __global__ void __launch_bounds__(GR_T) gram_bucket_kernel(int nbuckets, const i
 
 // ---------------------------------------------------------------------------------
 // Gram + rhs, second generation: the ELL tiles on the fp64 tensor cores.
-// One WARP per bucket (grid-stride), no block-level synchronisation.  For every 32-row tile of the bucket the warp densifies the rows
+// One CTA per bucket (grid-stride), the bucket's 32-row tiles dealt to its four warps.  For every tile the warp densifies the rows
 // into Xt[column][row] (the quadratic form's layout) and accumulates the upper block-triangle of  X' diag(w) X  with DMMA m8n8k4:
 // the A fragment of block row mb and the B fragment of block column nb are the SAME shared-memory values (Xt[8 b + g][4 ks + tg]),
 // the B side multiplied by the row weight.  A virtual column holding rho (the residual) sits right after the bucket's columns, so
 // S'D^-1 rho and sum(rho^2 / d) come out of the same product as one more column.  The local |U| x |U| tile lives in registers for the
-// whole bucket and is flushed once (fp64 atomics into the upper triangle of G, or the staged tile in deterministic mode).
+// whole bucket; the four warps' copies are summed through shared memory and flushed once (fp64 atomics into the upper triangle of G,
+// or the staged tile in deterministic mode).
 // ---------------------------------------------------------------------------------
 constexpr int GE_WARPS = 4, GE_T = GE_WARPS * 32;
 constexpr int GE_MAXBLK = 7;                 // 8-column blocks held in registers per bucket (28 accumulator fragments): column sets of up to 55
@@ -558,7 +559,7 @@ constexpr int GE_UP = GE_MAXBLK * 8;
 struct GramEllSmem {
     double Xt[GE_WARPS][GE_UP][QD_LDX];
     double w[GE_WARPS][32];
-    int ucol[GE_WARPS][UMAX];
+    int ucol[UMAX];
 };
 
 template <int NBLK>
@@ -573,19 +574,20 @@ __device__ __forceinline__ void gram_ell_bucket(GramEllSmem &S, int wid, int lan
     const int g = lane >> 2, tg = lane & 3;
     double (*Xt)[QD_LDX] = S.Xt[wid];
     double *sw = S.w[wid];
-    int *ucol = S.ucol[wid];
-    for (int u = lane; u < nU; u += 32) ucol[u] = ucol_all[(size_t)b * UMAX + u];
+    int *ucol = S.ucol;
+    __syncthreads();                                           // the previous bucket's flush is done with Xt and ucol
+    if ((int)threadIdx.x < nU) ucol[threadIdx.x] = ucol_all[(size_t)b * UMAX + threadIdx.x];
     double acc[NACC][2];
 #pragma unroll
     for (int i = 0; i < NACC; i++) acc[i][0] = acc[i][1] = 0.0;
-    for (int tl = t0; tl < t1; tl++) {
+    for (int tl = t0 + wid; tl < t1; tl += GE_WARPS) {         // the bucket's tiles are dealt to the CTA's warps
         const int K = tile_K[tl];
         const int p0 = r0 + (tl - t0) * 32, nrows = min(32, r1 - p0);
         const int row = lane < nrows ? perm[p0 + lane] : -1;
         const size_t off = (size_t)tile_off[tl];
-        if (tl + 1 < t1) {                                     // pull the next tile towards L2
-            const size_t noff = (size_t)tile_off[tl + 1];
-            const int nK = max(tile_K[tl + 1], 0);
+        if (tl + GE_WARPS < t1) {                              // pull this warp's next tile towards L2
+            const size_t noff = (size_t)tile_off[tl + GE_WARPS];
+            const int nK = max(tile_K[tl + GE_WARPS], 0);
             const char *pv = reinterpret_cast<const char *>(ell_val + noff);
             for (int c = lane; c < nK * 2; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + (size_t)c * 128));
         }
@@ -640,28 +642,36 @@ __device__ __forceinline__ void gram_ell_bucket(GramEllSmem &S, int wid, int lan
         }
         __syncwarp();
     }
-    // flush: this lane holds local entries (8 mb + g, 8 nb + 2 tg + e)
+    // reduce over the warps: every warp parks its fragments in its own (now idle) Xt area, fragment-major; then the CTA's threads
+    // each sum one entry over the warps and flush it.  Entry e of fragment f: local row 8 mb + e / 8, local column 8 nb + e % 8.
+    double *park = &S.Xt[wid][0][0];
+#pragma unroll
+    for (int f = 0; f < NACC; f++) {
+        park[f * 64 + g * 8 + 2 * tg] = acc[f][0];
+        park[f * 64 + g * 8 + 2 * tg + 1] = acc[f][1];
+    }
+    __syncthreads();
     double *G = acc_out, *rhs = acc_out + (size_t)r * r;
+    for (int idx = threadIdx.x; idx < NACC * 64; idx += GE_T) {
+        const int f = idx >> 6, e = idx & 63;
+        int nb = 0;
+        while ((nb + 1) * (nb + 2) / 2 <= f) nb++;
+        const int mb = f - nb * (nb + 1) / 2;
+        const int la = 8 * mb + (e >> 3), lb = 8 * nb + (e & 7);
+        if (la > lb || lb > nU) continue;
+        double val = 0.0;
 #pragma unroll
-    for (int nb = 0; nb < NBLK; nb++)
-#pragma unroll
-        for (int mb = 0; mb <= nb; mb++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int la = 8 * mb + g, lb = 8 * nb + 2 * tg + e;
-                const double val = acc[nb * (nb + 1) / 2 + mb][e];
-                if (la > lb || lb > nU) continue;
-                if (lb == nU) {                                // the virtual column: right-hand side / sum(rho^2 w)
-                    if (la == nU) s_quad += val;
-                    else if (stage) stage_rhs[(size_t)b * UMAX + la] = val;
-                    else atomicAdd(rhs + ucol[la], val);
-                } else if (stage) stage[((size_t)b * UMAX + la) * UMAX + lb] = val;
-                else if (val != 0.0) {
-                    const int ca = ucol[la], cb = ucol[lb];
-                    atomicAdd(G + min(ca, cb) + (size_t)r * max(ca, cb), val);
-                }
-            }
-    __syncwarp();
+        for (int w2 = 0; w2 < GE_WARPS; w2++) val += (&S.Xt[w2][0][0])[idx];
+        if (lb == nU) {                                        // the virtual column: right-hand side / sum(rho^2 w)
+            if (la == nU) s_quad += val;
+            else if (stage) stage_rhs[(size_t)b * UMAX + la] = val;
+            else atomicAdd(rhs + ucol[la], val);
+        } else if (stage) stage[((size_t)b * UMAX + la) * UMAX + lb] = val;
+        else if (val != 0.0) {
+            const int ca = ucol[la], cb = ucol[lb];
+            atomicAdd(G + min(ca, cb) + (size_t)r * max(ca, cb), val);
+        }
+    }
 }
 
 // NBLK = blocks held in registers; the launch handles the buckets with LO < blocks <= NBLK (one instantiation per kernel: several
@@ -679,9 +689,8 @@ __global__ void __launch_bounds__(GE_T, 2) gram_ell_kernel(int lo, int nbuckets,
     extern __shared__ __align__(16) unsigned char gsm_raw[];
     GramEllSmem &S = *reinterpret_cast<GramEllSmem *>(gsm_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int gw = blockIdx.x * GE_WARPS + wid, nw = gridDim.x * GE_WARPS;
     double s_quad = 0.0, s_logd = 0.0;
-    for (int b = gw; b < nbuckets; b += nw) {
+    for (int b = blockIdx.x; b < nbuckets; b += gridDim.x) {
         const int r0 = bptr[b], r1 = bptr[b + 1];
         if (r1 <= r0) continue;
         const int nU = nU_all[b];
@@ -690,10 +699,11 @@ __global__ void __launch_bounds__(GE_T, 2) gram_ell_kernel(int lo, int nbuckets,
         gram_ell_bucket<NBLK>(S, wid, lane, b, r0, r1, nU, perm, ucol_all, btile[b], btile[b + 1], tile_K, tile_off, ell_val, ell_lid, m, r, z, X, p,
                               alpha, ve, vfs, sigma2fs, acc, stage, stage_rhs, s_quad, s_logd);
     }
-    // s_quad: the lane holding local entry (nU, nU) added it, one per bucket; s_logd: one term per row
+    // s_quad: the thread that flushed local entry (nU, nU) added it, one per bucket; s_logd: one term per row
     s_quad = warp_sum(s_quad);
     s_logd = warp_sum(s_logd);
     if (lane == 0) {
+        const int gw = blockIdx.x * GE_WARPS + wid;
         if (stage) { stage_scal[2 * gw] += s_quad; stage_scal[2 * gw + 1] += s_logd; }      // (zeroed before the first class is launched)
         else { atomicAdd(acc + (size_t)r * r + r, s_quad); atomicAdd(acc + (size_t)r * r + r + 1, s_logd); }
     }
@@ -775,7 +785,7 @@ static int gram_prepare_ordered(frk_ctx *ctx, const frk_rowbuckets *bk, int r) {
     int *d_ptr = nullptr, *d_ib = nullptr, *d_il = nullptr;
     if (alloc((void **)&d_ptr, ptr.size() * sizeof(int)) || alloc((void **)&d_ib, ib.size() * sizeof(int)) ||
         alloc((void **)&d_il, il.size() * sizeof(int)) || alloc((void **)&bk->stage, (size_t)r * UMAX * UMAX * sizeof(double)) ||
-        alloc((void **)&bk->stage_rhs, (size_t)r * UMAX * sizeof(double)) || alloc((void **)&bk->stage_scal, 2 * ((size_t)grid + 8) * sizeof(double)))
+        alloc((void **)&bk->stage_rhs, (size_t)r * UMAX * sizeof(double)) || alloc((void **)&bk->stage_scal, 2 * (4 * (size_t)grid + 8) * sizeof(double)))
         return 1;
     FRK_CHECK_CUDA(cudaMemcpyAsync(d_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     FRK_CHECK_CUDA(cudaMemcpyAsync(d_ib, ib.data(), ib.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -898,7 +908,7 @@ extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *
     unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 8);
     static const bool legacy = getenv("FRK_GRAM_LEGACY") != nullptr;      // A/B timing: the first-generation (DFMA register-tile) kernel
     const bool ell = bk->all_ell && bk->T > 0 && bk->max_nU < GE_MAXBLK * 8 && !legacy;
-    if (ell) grid = (unsigned)std::min<int64_t>(cdiv(r, GE_WARPS), (int64_t)ctx->sm_count * 2);
+    if (ell) grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 2);
     // work of the launch: val 8 B + local id 1 B per stored entry, row weights, the r x r accumulator once
     double *st = nullptr, *st_rhs = nullptr, *st_scal = nullptr;
     if (ctx->deterministic) {
