@@ -6,11 +6,11 @@ NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
 SRC       := frk_b200/csrc
 OBJ       := $(SRC)/build
 LIB       := frk_b200/libfrkb200.so
-CUS       := ctx comm basis bau sparse bucket dense model areal host_api
+CUS       := ctx comm basis bau sparse bucket dense model areal coupled host_api
 
 all: $(LIB)
 
-$(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh include/frkb200.h
+$(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/coupled.cuh include/frkb200.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(if $(filter basis,$*),-fmad=false,) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; exit 1)
 

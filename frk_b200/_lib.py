@@ -135,6 +135,8 @@ SIGNATURES = {
     "frk_model_predict_polygons": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_int, c_i64, vp, vp, vp, c_i64, vp, vp, vp]),
     "frk_model_predict_areal": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_model_set_lanes": (c_int, [vp, c_int]),
+    "frk_model_set_vfs_csr": (c_int, [vp, vp, vp, vp]),
+    "frk_model_coupled_groups": (c_int, [vp]),
     "frk_model_set_nm_distribute": (c_int, [vp, c_int]),
     "frk_model_set_parallel": (c_int, [vp, c_int, c_int, c_int]),
     "frk_model_set_blocks": (c_int, [vp, c_int, vp, C.POINTER(vp)]),

@@ -19,6 +19,7 @@
 // is not read at all.  A bucket whose union exceeds 64 columns (or, for the quadratic form, a row with more
 // than 40 non-zeros: tensor-product bases) takes the direct kernels' arithmetic inside the same launch.
 #include "common.cuh"
+#include "coupled.cuh"
 #include <cub/cub.cuh>
 
 constexpr int UMAX = 64;          // columns per bucket handled through shared memory
@@ -386,6 +387,16 @@ extern "C" int frk_rowbuckets_create(frk_ctx *ctx, int64_t n, int ncols, const i
         for (int k = 0; k < 10; k++) B->nblk_hist[k] = h_bad[2 + k];
     }
     *out = B;
+    return 0;
+}
+
+// same pattern, new values (coupled.cu re-whitens S whenever sigma2fs changes): only the ELL copy holds values
+int frk_rowbuckets_refresh(frk_rowbuckets *B, frk_ctx *ctx, const int *d_rowptr, const double *d_val) {
+    FRK_REQUIRE(B && ctx && d_rowptr && d_val, "frk_rowbuckets_refresh: NULL argument");
+    if (B->dense || B->T == 0 || B->n == 0) return 0;
+    const unsigned grid = (unsigned)std::min<int64_t>(B->ncols, (int64_t)ctx->sm_count * 8);
+    FRK_LAUNCH(ctx, ell_fill_kernel, grid, 256, 0, B->ncols, B->bptr, B->btile, B->perm, d_rowptr, d_val, B->lid, B->tile_K, B->tile_off,
+               B->ell_val, B->ell_lid);
     return 0;
 }
 

@@ -12,6 +12,7 @@
 // .loglik.ind and .SRE.Estep.ind both form S'D^-1 S and factor K^-1 + S'D^-1 S (the reference's two K^-1 are
 // the same chol2inv(chol(Khat))), and the M-step's Khat_inv factorisation supplies the next log|K|.
 #include "common.cuh"
+#include "coupled.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -48,6 +49,7 @@ struct frk_model {
     const double *val = nullptr, *Z = nullptr, *X = nullptr, *Ve = nullptr, *Vfs = nullptr;
     bool owned = false;
     frk_rowbuckets *bk = nullptr;
+    frk_coupling *cp = nullptr;     // non-diagonal Vfs (observations coupled through shared BAUs): see coupled.cu; M->Vfs then holds diag(Vfs)
     // r-sized slots (device), replicated on every rank
     double *mu_eta = nullptr, *S_eta = nullptr, *Q_eta = nullptr, *Khat = nullptr, *Khat_inv = nullptr;
     // scratch
@@ -195,7 +197,8 @@ struct MSums { double uxx[16], uxz[4], sv, w0, wx[4], wxx[16]; };
 int mstep_sums(frk_model *M, frk_ctx *c, double sigma2fs, int mode, MSums &s) {
     const int p = M->p, ns = 2 * p * p + 2 * p + 2;
     double out[2 * 16 + 2 * 4 + 2];
-    RC(frk_mstep_sums(c, M->m, p, M->X, M->Z, M->t, M->q, M->Ve, M->Vfs, sigma2fs, mode, out));
+    if (M->cp && mode == 0) RC(frk_coupling_msums(M->cp, c, M->X, M->Z, M->t, M->Ve, sigma2fs, out));   // general J, R/SREfit.R:296-328
+    else RC(frk_mstep_sums(c, M->m, p, M->X, M->Z, M->t, M->q, M->Ve, M->Vfs, sigma2fs, mode, out));
     RC(reduce_host(M, out, ns, 0));                                  // O(p^2) doubles
     int o = 0;
     for (int i = 0; i < p * p; i++) s.uxx[i] = out[o++];
@@ -540,6 +543,15 @@ int gram(frk_model *M, const double *alpha, double sigma2fs) {
         if (same) return reduce_gram(M);                                            // (this rank's rows: the exchange happens here)
     }
     FRK_CHECK_CUDA(cudaMemsetAsync(M->acc, 0, n * sizeof(double), M->ctx->stream));
+    if (M->cp) {
+        // D = sigma2fs Vfs + Ve is block diagonal, not diagonal (R/SREfit.R:186-189,240-247): whiten with chol(D) per block, then the
+        // same kernels on (S~, Z~, X~) with unit weights; logdet(cholD) goes into the slot the weights' sum of logs would fill
+        frk_coupling *C = M->cp;
+        RC(frk_coupling_whiten(C, M->ctx, sigma2fs, M->val, M->Z, M->X, M->Ve, M->acc + (size_t)M->r * M->r + M->r + 1));
+        return frk_gram_rhs_bucketed(M->ctx, M->m, M->r, frk_coupling_rowptr(C), frk_coupling_col(C), frk_coupling_val(C),
+                                     frk_coupling_buckets(C), frk_coupling_Z(C), frk_coupling_X(C), M->p, alpha, frk_coupling_ones(C),
+                                     frk_coupling_zeros(C), 0.0, M->acc);
+    }
     RC(frk_gram_rhs_bucketed(M->ctx, M->m, M->r, M->rowptr, M->col, M->val, M->bk,
                              M->Z, M->X, M->p, alpha, M->Ve, M->Vfs, sigma2fs, M->acc));
     return reduce_gram(M);                                            // the ONE large exchange per EM iteration
@@ -1147,7 +1159,7 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
     const bool est = !known;
     bool sigma_done = false;
     // the early Gram needs this function to run BEFORE the K update finishes, i.e. as the asynchronous driver's side work
-    const bool early_gram = beside && !M->tensor && nm_world(M) == 1 && !M->spec_emulate;
+    const bool early_gram = beside && !M->tensor && nm_world(M) == 1 && !M->spec_emulate && !M->cp;
     // sigma2fs and alpha (:275-430).  Everything here depends on the E-step only, not on K: with `beside` it runs on the aux lane
     // (after the quadratic form) while the Nelder-Mead evaluations are in flight, and is followed there by the NEXT iteration's Gram.
     auto sigma_update = [&]() -> int {
@@ -1155,6 +1167,7 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
         frk_ctx *c = beside ? M->aux : ctx;
         double s2new = est ? sigma2fs : known_sigma2fs;
         if (!beside) RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
+        if (M->cp && !M->all_vfs_zero) RC(frk_coupling_cross(M->cp, c, M->rowptr, M->col, M->val, M->S_eta));   // S_c S_eta S_c' per coupled group
         double al[MAXP_M];
         MSums s;
         double swo;
@@ -1316,12 +1329,32 @@ extern "C" int frk_model_destroy(frk_model *M) {
             }
     for (void *p : M->allocs) cudaFreeAsync(p, M->ctx->stream);
     frk_rowbuckets_destroy(M->bk);
+    frk_coupling_destroy(M->cp);
     if (M->ev_lane) cudaEventDestroy(M->ev_lane);
     if (M->ev_aux0) cudaEventDestroy(M->ev_aux0);
     if (M->ev_aux1) cudaEventDestroy(M->ev_aux1);
     delete M;
     return 0;
 }
+
+// Non-diagonal Vfs (R/SRE.R:498: tcrossprod(Cmat %*% Diagonal(sqrt(fs))) when observation footprints share BAUs, or several point
+// observations sit in one BAU with average_in_BAU = FALSE): the full symmetric m x m matrix as host CSR.  The model then takes the
+// reference's general branches (R/SREfit.R:186-189, 240-252, 296-328); see coupled.cu.  Call before frk_model_init.
+extern "C" int frk_model_set_vfs_csr(frk_model *M, const int *h_rowptr, const int *h_col, const double *h_val) {
+    FRK_REQUIRE(M && h_rowptr && h_col && h_val, "frk_model_set_vfs_csr: NULL argument");
+    FRK_REQUIRE(!M->cp, "frk_model_set_vfs_csr: already set");
+    FRK_REQUIRE(!multi_rank(M) && M->world == 1, "a non-diagonal Vfs couples observations across the row partition: not on the device path (one rank only)");
+    bool offdiag = false;
+    for (int64_t i = 0; i < M->m && !offdiag; i++)
+        for (int e = h_rowptr[i]; e < h_rowptr[i + 1]; e++)
+            if (h_col[e] != i && h_val[e] != 0.0) { offdiag = true; break; }
+    if (!offdiag) return 0;                                          // isDiagonal(Vfs): the diagonal paths apply as they are
+    RC(frk_coupling_create(M->ctx, M->m, M->r, M->p, h_rowptr, h_col, h_val, M->rowptr, M->col, &M->cp));
+    M->homoscedastic = false;                                        // homoscedastic <- ... & isDiagonal(Sm@Vfs), R/SREfit.R:278-280
+    return 0;
+}
+
+extern "C" int frk_model_coupled_groups(const frk_model *M) { return (M && M->cp) ? frk_coupling_ncomp(M->cp) : 0; }
 
 // this rank's position in a row-partitioned run (enables the speculative Nelder-Mead); emulate != 0: evaluate all of a pretend
 // world's candidates on this rank (tests the logic on one GPU)

@@ -348,6 +348,17 @@ def map_data_to_BAUs(data: SpatialPointsDataFrame, BAUs, columns, dev: Optional[
     return _bin(dev, data, columns, d_bau, n, ncols, lo, hi)
 
 
+def point_BAU_index(data: SpatialPointsDataFrame, BAUs, dev: Optional[Device] = None) -> np.ndarray:
+    """BAU row of every observation (0-based; -1 = in no BAU): the sp::over step of map_data_to_BAUs (R/geometryfns.R:1266) without
+    the averaging, as average_in_BAU = FALSE keeps it (:1304-1305)."""
+    dev = dev or get_device()
+    n = len(data)
+    if isinstance(BAUs, STBAUs):
+        raise FRKError("average_in_BAU=FALSE with space-time BAUs is not on the device path")
+    d_bau = _spatial_lookup(dev, data, BAUs, n, 0, len(BAUs))
+    return dev.download(d_bau, n).astype(np.int64) if n else np.zeros(0, dtype=np.int64)
+
+
 def _spatial_lookup(dev, data, BAUs, n, lo, hi):
     """per-point BAU row in [lo, hi) relative to lo, -1 = NA (sp::over, R/geometryfns.R:1266)."""
     if isinstance(BAUs, GridBAUs):

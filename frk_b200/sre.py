@@ -128,8 +128,6 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
     if est_error:
         raise FRKError("est_error=TRUE needs the gstat variogram fit (host, third-party; out of the hot-path scope): "
                        "supply a 'std' column and est_error=FALSE")
-    if not average_in_BAU:
-        raise FRKError("average_in_BAU=FALSE gives several observations per BAU (non-diagonal C'C): not on the device path yet")
     if "std" not in data.data:
         raise ValueError("data needs a field 'std' (measurement-error standard deviation) when est_error=FALSE")
     if "fs" not in BAUs.fields:
@@ -185,20 +183,27 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
         call("frk_polygons_create", dev.ctx, m, vp(data.ptr.ctypes.data), vp(data.vx.ctypes.data), vp(data.vy.ctypes.data), C.byref(hp))
         d_group = dev.empty(max(N, 1), "i4")
         multi = c_i64(0)
+        cz_rowptr = dev.empty(m + 1, "i4")
+        nmem, empty = c_i64(0), c_i64(0)
         try:
             call("frk_polygon_lookup_count", dev.ctx, hp, N, dev.ptr(d_s), N, dev.ptr(d_group), C.byref(multi))
+            if multi.value:
+                # supports that share BAUs: the general incidence (every polygon a BAU centroid lies in), R/geometryfns.R:1572-1616
+                ptoff = dev.empty(N + 1, "i4")
+                call("frk_polygon_incidence_count", dev.ctx, hp, N, dev.ptr(d_s), N, dev.ptr(ptoff), C.byref(nmem))
+                cz_mem = dev.empty(max(nmem.value, 1), "i4")
+                cz_w = dev.empty(max(nmem.value, 1))
+                call("frk_polygon_incidence_fill", dev.ctx, hp, N, dev.ptr(d_s), N, dev.ptr(ptoff), nmem.value, vp(None), dev.ptr(cz_rowptr),
+                     dev.ptr(cz_mem), dev.ptr(cz_w), C.byref(empty))
         finally:
             _lib.lib.frk_polygons_destroy(hp)
         h2d += data.ptr.nbytes + data.vx.nbytes + data.vy.nbytes
-        if multi.value:
-            raise FRKError(f"{multi.value} BAU centroids lie in more than one observation polygon: overlapping supports give a "
-                           "non-diagonal fine-scale covariance (R/SREfit.R:298-328), which is not on the device path yet")
-        cz_rowptr = dev.empty(m + 1, "i4")
-        cz_mem = dev.empty(max(N, 1), "i4")
-        cz_w = dev.empty(max(N, 1))
-        nmem, empty = c_i64(0), c_i64(0)
-        call("frk_areal_incidence", dev.ctx, N, dev.ptr(d_group), m, vp(None), dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(cz_w),
-             C.byref(nmem), C.byref(empty))
+        overlapping = bool(multi.value)
+        if not overlapping:
+            cz_mem = dev.empty(max(N, 1), "i4")
+            cz_w = dev.empty(max(N, 1))
+            call("frk_areal_incidence", dev.ctx, N, dev.ptr(d_group), m, vp(None), dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(cz_w),
+                 C.byref(nmem), C.byref(empty))
         if empty.value:
             raise FRKError(f"{empty.value} observation polygons contain no BAU centroid (supports smaller than a BAU fall back to a "
                            "point lookup in the reference, R/geometryfns.R:1593-1598): use finer BAUs or point data for them")
@@ -221,13 +226,29 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
     else:
         # ---- bin the observations into this rank's BAUs ------------------------------------------
         cols = [resp, "std"]
-        binned = map_data_to_BAUs(data, BAUs, cols, dev, row_range=(lo, hi))
-        h2d += data.coords[:, :2].nbytes + 8 * len(data) * len(cols)
-        m, ld = binned["m"], binned["ld"]
-        obs_bau = binned["obs_bau"][:max(m, 1)]
-        Z = binned["means"][0:max(m, 1)]                             # views into the binned table (column-major, ld = n)
-        Ve = dev.empty(max(m, 1))
-        call("frk_square", dev.ctx, m, dev.ptr(binned["means"], ld), dev.ptr(Ve))      # Ve = diag(std^2), R/SRE.R:468
+        if average_in_BAU:
+            binned = map_data_to_BAUs(data, BAUs, cols, dev, row_range=(lo, hi))
+            h2d += data.coords[:, :2].nbytes + 8 * len(data) * len(cols)
+            m, ld = binned["m"], binned["ld"]
+            obs_bau = binned["obs_bau"][:max(m, 1)]
+            Z = binned["means"][0:max(m, 1)]                             # views into the binned table (column-major, ld = n)
+            Ve = dev.empty(max(m, 1))
+            call("frk_square", dev.ctx, m, dev.ptr(binned["means"], ld), dev.ptr(Ve))      # Ve = diag(std^2), R/SRE.R:468
+        else:
+            # average_in_BAU = FALSE (R/geometryfns.R:1304-1305): every observation that falls into a BAU is kept, in data order
+            if dev.world > 1:
+                raise FRKError("average_in_BAU=FALSE on a row-partitioned run is not on the device path (observations of one BAU are coupled)")
+            from .geometry import point_BAU_index
+            bau_pt = point_BAU_index(data, BAUs, dev)                    # device lookup; -1 = outside every BAU (dropped, :1271-1278)
+            keep = np.nonzero(bau_pt >= 0)[0]
+            h_obs_bau = np.ascontiguousarray(bau_pt[keep], dtype=np.int32)
+            m = len(keep)
+            obs_bau = dev.upload(h_obs_bau if m else np.zeros(1, dtype=np.int32))
+            Z = dev.upload(np.ascontiguousarray(np.asarray(data.data[resp], dtype=np.float64)[keep]) if m else np.zeros(1))
+            d_std = dev.upload(np.ascontiguousarray(np.asarray(data.data["std"], dtype=np.float64)[keep]) if m else np.zeros(1))
+            h2d += data.coords[:, :2].nbytes + 16 * len(data)
+            Ve = dev.empty(max(m, 1))
+            call("frk_square", dev.ctx, m, dev.ptr(d_std), dev.ptr(Ve))
 
         # ---- C_Z (one 1 per row) -> S = C_Z S0, Vfs = fs[bau], X = model matrix at the observed BAUs ----
         rowptr = dev.empty(m + 1, "i4")
@@ -268,6 +289,28 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
     mdl = SREModel(dev, f, basis, BAUs, K_type, N, lo, hi, m, S0, S, obs_bau, Z, X, X_BAU, Ve, Vfs, fs_BAU, p)
     mdl._keep = binned                                            # Z / obs_bau are views into these buffers
     mdl.areal = areal
+    mdl.coupled = False
+    Vcsr = None
+    if areal and overlapping:
+        # Vfs = tcrossprod(Cmat %*% Diagonal(sqrt(fs))) (R/SRE.R:498) with its off-diagonal entries: host sparse algebra on the
+        # incidence matrix, as SRE() does in R; the device takes it from there (frk_model_set_vfs_csr)
+        import scipy.sparse as sp
+        Cm = sp.csr_matrix((dev.download(cz_w, nmem.value), dev.download(cz_mem, nmem.value), dev.download(cz_rowptr, m + 1)), shape=(m, N))
+        half = sp.csr_matrix(Cm @ sp.diags(np.sqrt(fs_host)))
+        Vcsr = sp.csr_matrix(half @ half.T)
+    elif not areal and not average_in_BAU and m:
+        import scipy.sparse as sp
+        Cm = sp.csr_matrix((np.ones(m), h_obs_bau.astype(np.int64), np.arange(m + 1)), shape=(m, nloc))
+        half = sp.csr_matrix(Cm @ sp.diags(np.sqrt(fs_host)))
+        Vcsr = sp.csr_matrix(half @ half.T)
+    if Vcsr is not None:
+        Vcsr.sort_indices()
+        vrp = np.ascontiguousarray(Vcsr.indptr, dtype=np.int32)
+        vcl = np.ascontiguousarray(Vcsr.indices, dtype=np.int32)
+        vvl = np.ascontiguousarray(Vcsr.data, dtype=np.float64)
+        call("frk_model_set_vfs_csr", mdl.handle, vp(vrp.ctypes.data), vp(vcl.ctypes.data), vp(vvl.ctypes.data))
+        mdl.coupled = _lib.lib.frk_model_coupled_groups(mdl.handle) > 0
+        h2d += vrp.nbytes + vcl.nbytes + vvl.nbytes
     if areal:
         mdl.C_Z = (cz_rowptr, cz_mem, cz_w, int(nmem.value))      # Cmat (CSR over the observations, rows normalised)
     mdl.h2d_bytes = h2d
@@ -354,6 +397,9 @@ def _predict_polygons(mdl: SREModel, newdata, obs_fs: bool):
         raise FRKError("prediction over polygons on a row-partitioned run: polygons may straddle ranks -- not on the device path yet")
     if isinstance(mdl.basis, TensorP_Basis) or isinstance(mdl.BAUs, STBAUs):
         raise FRKError("prediction over polygons in space-time is not on the device path yet")
+    if getattr(mdl, "coupled", False) and not obs_fs and mdl.sigma2fshat > 0:
+        raise FRKError("predict(obs_fs = FALSE) with sigma2fs > 0 for observations coupled through shared BAUs (the joint (eta, xi) solve "
+                       "of R/SREpredict.R:308-333 with a non-diagonal C'Ve^-1 C) is not on the device path yet; use obs_fs = TRUE")
     if getattr(mdl, "areal", False) and not obs_fs and mdl.sigma2fshat > 0:
         raise FRKError("prediction over polygons with obs_fs = FALSE for areal DATA needs the covariances between the fine-scale terms "
                        "of a support (R/SREpredict.R:392-404): not on the device path yet; use obs_fs = TRUE")
@@ -405,6 +451,9 @@ def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True, newdata=N
     dev = mdl.dev
     nloc = mdl.hi - mdl.lo
     mu, var, sd = (dev.empty(max(nloc, 1)) for _ in range(3))
+    if getattr(mdl, "coupled", False) and not obs_fs and mdl.sigma2fshat > 0:
+        raise FRKError("predict(obs_fs = FALSE) with sigma2fs > 0 for observations coupled through shared BAUs (the joint (eta, xi) solve "
+                       "of R/SREpredict.R:308-333 with a non-diagonal C'Ve^-1 C) is not on the device path yet; use obs_fs = TRUE")
     if getattr(mdl, "areal", False) and not obs_fs and mdl.sigma2fshat > 0:
         cz_rowptr, cz_mem, cz_w, _ = mdl.C_Z
         call("frk_model_predict_areal", mdl.handle, nloc, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),

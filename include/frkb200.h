@@ -390,6 +390,15 @@ int frk_model_set_lanes(frk_model *mdl, int lanes);
  * all-reduce per round and a broadcast of the winner's inverse); 0 (default) lets every rank evaluate them on its own lanes --
  * replicated and deterministic like the rest of the r-sized work, with no exchange.  Results are identical either way.        */
 int frk_model_set_nm_distribute(frk_model *mdl, int distribute);
+/* Non-diagonal Vfs: observation footprints that share BAUs (overlapping areal supports, BuildC R/geometryfns.R:1572-1616), or
+ * several point observations in one BAU with average_in_BAU = FALSE.  Vfs = tcrossprod(Cmat %*% Diagonal(sqrt(fs))) (R/SRE.R:498)
+ * as the full symmetric m x m host CSR (0-based; the dgRMatrix slots of object@Vfs).  The EM then runs the reference's general
+ * branches: chol(D) in .loglik.ind / .SRE.Estep.ind (R/SREfit.R:186-189,240-252) and the general J(sigma2fs) (:296-328).  D is
+ * block diagonal over the connected groups of coupled observations; groups of up to 64 observations are handled, larger ones are
+ * refused.  A diagonal matrix is accepted and changes nothing.  One rank only.  Call before frk_model_init.                    */
+int frk_model_set_vfs_csr(frk_model *mdl, const int *h_rowptr, const int *h_col, const double *h_val);
+/* number of connected groups (0: Vfs is diagonal)                                                                               */
+int frk_model_coupled_groups(const frk_model *mdl);
 /* BuildD() (R/basisfns.R:1131-1153) for K_type = "block-exponential": h_res[r] 1-based resolution of every basis
  * function, h_D[i] the r_i x r_i centroid distance matrix of resolution i+1 (column-major, host).              */
 int frk_model_set_blocks(frk_model *mdl, int nres, const int *h_res, const double *const *h_D);

@@ -908,6 +908,7 @@ class SREModel:
     alphahat: np.ndarray = None
     sigma2fshat: float = None
     info_fit: dict = field(default_factory=dict)
+    Vmat: object = None        # dense m x m Vfs when it is NOT diagonal (footprints sharing BAUs); Vfs then holds its diagonal
 
     @property
     def r(self):
@@ -946,7 +947,7 @@ def BuildC_polygons(ptr: np.ndarray, vx: np.ndarray, vy: np.ndarray, bau_xy: np.
 def SRE(basis, baus_coords: np.ndarray, fs_BAU: np.ndarray, obs_bau: np.ndarray, Z: np.ndarray,
         std: np.ndarray, X: Optional[np.ndarray] = None, X_BAU: Optional[np.ndarray] = None,
         K_type: str = "block-exponential", normalise_basis: bool = True, fast_eval: bool = False,
-        C: Optional[sp.spmatrix] = None) -> SREModel:
+        C: Optional[sp.spmatrix] = None, allow_overlap: bool = False) -> SREModel:
     """SRE() for binned point data, R/SRE.R:395-701.
 
     Inputs are the *binned* observations (map_data_to_BAUs output): BAU row, mean z, mean std.
@@ -958,7 +959,7 @@ def SRE(basis, baus_coords: np.ndarray, fs_BAU: np.ndarray, obs_bau: np.ndarray,
     ``obs_bau`` is ignored then.
     """
     if C is not None:
-        return _SRE_areal(basis, baus_coords, fs_BAU, sp.csr_matrix(C), Z, std, X_BAU, K_type, normalise_basis)
+        return _SRE_areal(basis, baus_coords, fs_BAU, sp.csr_matrix(C), Z, std, X_BAU, K_type, normalise_basis, allow_overlap)
     N = baus_coords.shape[0]
     if fast_eval and not isinstance(basis, TensorP_Basis) and basis.type == "bisquare":
         S0 = eval_basis_fast(basis, baus_coords)
@@ -985,7 +986,7 @@ def SRE(basis, baus_coords: np.ndarray, fs_BAU: np.ndarray, obs_bau: np.ndarray,
     return mdl
 
 
-def _SRE_areal(basis, baus_coords, fs_BAU, C, Z, std, X_BAU, K_type, normalise_basis) -> SREModel:
+def _SRE_areal(basis, baus_coords, fs_BAU, C, Z, std, X_BAU, K_type, normalise_basis, allow_overlap=False) -> SREModel:
     N = baus_coords.shape[0]
     S0 = eval_basis(basis, baus_coords)
     if normalise_basis:
@@ -1000,8 +1001,11 @@ def _SRE_areal(basis, baus_coords, fs_BAU, C, Z, std, X_BAU, K_type, normalise_b
     half = sp.csr_matrix(Cmat @ sp.diags(np.sqrt(fs_BAU)))
     V = sp.csr_matrix(half @ half.T)                                      # tcrossprod(Cmat %*% Diagonal(sqrt(fs))), :498
     off = V - sp.diags(V.diagonal())
+    Vmat = None
     if off.nnz and abs(off).max() > 0:
-        raise ValueError("supports share BAUs: Vfs is not diagonal")
+        if not allow_overlap:
+            raise ValueError("supports share BAUs: Vfs is not diagonal")
+        Vmat = np.asarray(V.todense())                                    # the general branches of the EM (R/SREfit.R:186-189,240-252,296-328)
     Vfs = V.diagonal()
     S = sp.csr_matrix(Cmat @ S0)
     S.sort_indices()
@@ -1011,6 +1015,7 @@ def _SRE_areal(basis, baus_coords, fs_BAU, C, Z, std, X_BAU, K_type, normalise_b
     mdl = SREModel(basis=basis, S0=S0, S=S, obs_bau=np.zeros(0, dtype=np.int64), Z=Z, X=X, X_BAU=X_BAU,
                    Ve=Ve, Vfs=Vfs, fs_BAU=fs_BAU, D_basis=D_basis, K_type=K_type)
     mdl.Cmat = Cmat
+    mdl.Vmat = Vmat
     init = EM_initialise(Z, X, Ve, S.shape[1])
     for k, v in init.items():
         setattr(mdl, k, v)
@@ -1030,6 +1035,8 @@ def loglik(M: SREModel) -> float:
     Kinv = chol2inv(chol_K)
     resid = M.Z - M.X @ M.alphahat
     N = len(M.Z)
+    if M.Vmat is not None:
+        return _loglik_general(M, K, Kinv, resid)
     D = M.sigma2fshat * M.Vfs + M.Ve
     cholD = np.sqrt(D)
     cholDinv = 1.0 / cholD
@@ -1044,8 +1051,39 @@ def loglik(M: SREModel) -> float:
     return -0.5 * N * math.log(2 * math.pi) - 0.5 * log_det_SigmaZ - 0.5 * quad
 
 
+def _loglik_general(M: SREModel, K, Kinv, resid) -> float:
+    """.loglik.ind with a non-diagonal D: cholD <- chol(D); cholDinvT <- t(solve(cholD)), R/SREfit.R:186-189 and the lines that follow."""
+    N = len(M.Z)
+    D = M.sigma2fshat * M.Vmat + np.diag(M.Ve)
+    cholD = chol_upper(D)                                             # upper factor, D = cholD' cholD
+    cholDinvT = sla.solve_triangular(cholD, np.eye(N), lower=False).T
+    A = cholDinvT @ np.asarray(M.S.todense())
+    S_Dinv_S = A.T @ A                                                # crossprod(cholDinvT %*% S)
+    R = chol_upper(Kinv + S_Dinv_S)
+    sign, logdetK = np.linalg.slogdet(K)
+    log_det_SigmaZ = logdet(R) + logdetK + logdet(cholD)
+    wr = cholDinvT @ resid
+    rDinv = wr @ cholDinvT                                            # crossprod(cholDinvT %*% resid, cholDinvT)
+    v = M.S.T @ rDinv
+    x = sla.solve_triangular(R, v, trans="T", lower=False)
+    quad = float(wr @ wr) - float(x @ x)
+    return -0.5 * N * math.log(2 * math.pi) - 0.5 * log_det_SigmaZ - 0.5 * quad
+
+
 def Estep(M: SREModel) -> None:
     """.SRE.Estep.ind, R/SREfit.R:232-260."""
+    if M.Vmat is not None:                                            # :244-247
+        N = len(M.Z)
+        D = M.sigma2fshat * M.Vmat + np.diag(M.Ve)
+        cholD = chol_upper(D)
+        cholDinv = sla.solve_triangular(cholD, np.eye(N), lower=False)
+        Dinv = chol2inv(cholD)
+        A = cholDinv.T @ np.asarray(M.S.todense())
+        Q_eta = A.T @ A + M.Khat_inv
+        S_eta = chol2inv(chol_upper(Q_eta))
+        mu_eta = S_eta @ (M.S.T @ (Dinv @ (M.Z - M.X @ M.alphahat)))
+        M.mu_eta, M.S_eta, M.Q_eta = mu_eta, S_eta, Q_eta
+        return
     D = M.sigma2fshat * M.Vfs + M.Ve
     Dinv = 1.0 / D
     cholDinv = 1.0 / np.sqrt(D)
@@ -1147,6 +1185,8 @@ def Mstep(M: SREModel, lam=0.0, known_sigma2fs=None) -> None:
     K = update_K(M, lam)
     Khat_inv = chol2inv(chol_upper(K))
     a, b = M.Ve, M.Vfs
+    if M.Vmat is not None:
+        return _Mstep_general(M, K, Khat_inv, known_sigma2fs)
     homoscedastic = bool(np.all(a == a[0]) and np.all(b == b[0]))
     est = known_sigma2fs is None
     sigma2fs_new = sigma2fs if est else known_sigma2fs
@@ -1199,6 +1239,55 @@ def Mstep(M: SREModel, lam=0.0, known_sigma2fs=None) -> None:
     else:                                                         # :424-428
         XtD = X.T * (1.0 / a)
         alpha = np.linalg.solve(XtD @ X, XtD @ (Z - t))
+        if est:
+            sigma2fs_new = 0.0
+    M.Khat, M.Khat_inv, M.alphahat, M.sigma2fshat = K, Khat_inv, alpha, float(sigma2fs_new)
+
+
+def _Mstep_general(M: SREModel, K, Khat_inv, known_sigma2fs) -> None:
+    """.SRE.Mstep.ind when Vfs is not diagonal (diagonal_mats FALSE, hence not homoscedastic): the general J, R/SREfit.R:296-328,
+    the bracket search :366-389 and the GLS step :391-400, dense algebra (toy sizes)."""
+    mu_eta, S_eta = M.mu_eta, M.S_eta
+    sigma2fs = M.sigma2fshat
+    est = known_sigma2fs is None
+    sigma2fs_new = sigma2fs if est else known_sigma2fs
+    S, X, Z, V = np.asarray(M.S.todense()), M.X, M.Z, M.Vmat
+    Ve = np.diag(M.Ve)
+    E = S_eta + np.outer(mu_eta, mu_eta)
+
+    def gls(Dinv):
+        return np.linalg.solve(X.T @ Dinv @ X, X.T @ Dinv @ (Z - S @ mu_eta))
+
+    def J(s2):
+        if s2 < 0:
+            return np.inf
+        D = s2 * V + Ve
+        Dinv = chol2inv(chol_upper(D))
+        DinvV = Dinv @ V
+        DinvVDinv = Dinv @ V @ Dinv
+        al = gls(Dinv)
+        resid = Z - X @ al
+        Dinvr = DinvVDinv @ resid
+        DinvS = DinvVDinv @ S
+        tr1 = np.trace(DinvV)
+        tr2 = (np.sum((DinvS @ E) * S) - 2.0 * np.sum((DinvS @ mu_eta) * resid) + np.sum(Dinvr * resid))
+        return -(-0.5 * tr1 + 0.5 * tr2)
+
+    alpha = M.alphahat
+    if not np.all(np.diag(V) == 0):
+        if est:
+            amp = 10.0
+            OK = False
+            while not OK:
+                amp *= 10
+                if not (np.sign(J(sigma2fs / amp)) == np.sign(J(sigma2fs * amp))):
+                    OK = True
+                if amp > 1e9:
+                    OK = True
+            sigma2fs_new = 0.0 if amp > 1e9 else zeroin(J, sigma2fs / amp, sigma2fs * amp)
+        alpha = gls(chol2inv(chol_upper(sigma2fs_new * V + Ve)))
+    else:
+        alpha = gls(np.diag(1.0 / M.Ve))
         if est:
             sigma2fs_new = 0.0
     M.Khat, M.Khat_inv, M.alphahat, M.sigma2fshat = K, Khat_inv, alpha, float(sigma2fs_new)

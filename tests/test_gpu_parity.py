@@ -790,7 +790,8 @@ def test_areal_data_predict_case2(dev):
 
 
 def test_areal_data_refusals(dev):
-    """overlapping supports (non-diagonal Vfs) and supports without a BAU centroid are refused, not silently mis-fitted."""
+    """supports without a BAU centroid, and groups of more than 64 observations coupled through shared BAUs, are refused, not
+    silently mis-fitted (overlapping supports as such are handled: test_gpu_parity2.py::test_overlapping_areal_supports)."""
     import frk_b200 as F
     gb = F.auto_BAUs(F.plane(), cellsize=0.05, data=F.SpatialPointsDataFrame(np.array([[0.0, 0.0], [1.0, 1.0]]), {}))
     gb["fs"] = 1.0
@@ -803,8 +804,8 @@ def test_areal_data_refusals(dev):
             vx += px; vy += py; ptr.append(len(vx))
         k = len(squares)
         return F.SpatialPolygonsDataFrame(np.array(ptr), np.array(vx), np.array(vy), {"z": np.arange(k, dtype=float), "std": np.ones(k)})
-    with pytest.raises(F.FRKError, match="more than one observation polygon"):
-        F.SRE("z ~ 1", mk([(0.01, 0.01, 0.4), (0.21, 0.21, 0.4)]), basis, gb, est_error=False)
+    with pytest.raises(F.FRKError, match="coupled through shared BAUs in one connected group"):
+        F.SRE("z ~ 1", mk([(0.01 + 0.004 * k, 0.01 + 0.004 * k, 0.4) for k in range(70)]), basis, gb, est_error=False)
     with pytest.raises(F.FRKError, match="contain no BAU centroid"):
         F.SRE("z ~ 1", mk([(0.01, 0.01, 0.4), (0.601, 0.601, 0.01)]), basis, gb, est_error=False)
 

@@ -295,3 +295,115 @@ def test_eval_basis_support_edge_ties_one_ulp(dev, man):
     S_g = F.eval_basis(_mk_basis(F, ob), s, dev)
     assert _same_pattern(S_o, S_g)
     assert np.array_equal(S_o.data, S_g.data)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Non-diagonal Vfs: observations coupled through shared BAUs (R/SREfit.R:186-189, 240-252, 296-328)
+# ---------------------------------------------------------------------------------------------------------
+def _overlapping_supports(F, K_type, seed=3):
+    """Square supports on the unit square, laid out in short chains of two or three overlapping squares (connected groups of 2-3
+    observations) plus isolated ones; a covariate known at every BAU."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    gb = F.auto_BAUs(F.plane(), cellsize=0.025, data=F.SpatialPointsDataFrame(np.array([[0.0, 0.0], [1.0, 1.0]]), {}))
+    cen = gb.centroids()
+    gb["fs"] = 1.0 + 0.5 * (cen[:, 1] > 0.5)
+    gb["x1"] = cen[:, 0] - cen[:, 1]
+    ptr, vx, vy, z = [0], [], [], []
+    s = 0.11
+    for iy in range(6):
+        for ix in range(6):
+            x0, y0 = 0.004 + 0.16 * ix, 0.004 + 0.16 * iy
+            chain = (ix + iy) % 3                                     # 0: one square; 1: two overlapping; 2: three in an L
+            offs = [(0.0, 0.0)] + ([(0.04, 0.03)] if chain >= 1 else []) + ([(-0.0, 0.05)] if chain == 2 else [])
+            for dx, dy in offs:
+                a, b = x0 + dx, y0 + dy
+                vx += [a, a + s, a + s, a, a]; vy += [b, b, b + s, b + s, b]; ptr.append(len(vx))
+                xm, ym = a + s / 2, b + s / 2
+                z.append(np.sin(5 * xm) + np.cos(4 * ym) + 0.3 * (xm - ym) + 0.6 * rng.standard_normal())
+    m = len(z)
+    std = 0.1 + 0.05 * rng.uniform(size=m)
+    data = F.SpatialPolygonsDataFrame(np.array(ptr), np.array(vx), np.array(vy), {"z": np.array(z), "std": std})
+    ob = O.auto_basis(O.plane(), cen, regular=1, nres=2)
+    i_idx, j_idx, x_idx = O.BuildC_polygons(data.ptr, data.vx, data.vy, cen)
+    Cm = sp.csr_matrix((x_idx, (i_idx, j_idx)), shape=(m, len(cen)))
+    X_BAU = np.column_stack([np.ones(len(cen)), gb["x1"]])
+    Mo = O.SRE(ob, cen, gb["fs"], None, np.array(z), std, X_BAU=X_BAU, K_type=K_type, C=Cm, allow_overlap=True)
+    Mg = F.SRE("z ~ x1", data, _mk_basis(F, ob), gb, est_error=False, K_type=K_type)
+    return Mo, Mg, Cm
+
+
+@pytest.mark.parametrize("K_type", ["unstructured", "block-exponential"])
+def test_overlapping_areal_supports(dev, K_type):
+    """SURVEY.md section 8(f) #1, the remainder: supports that share BAUs.  BuildC with shared BAUs (incidence exact), S = Cmat S0,
+    the full Vfs = tcrossprod(Cmat sqrt(fs)) with its off-diagonal blocks, and the EM through the reference's GENERAL branches --
+    chol(D) in the log-likelihood and the E-step, J(sigma2fs) with Dinv %*% Vfs %*% Dinv -- against their dense restatement."""
+    import scipy.sparse as sp
+    import frk_b200 as F
+    Mo, Mg, Cm = _overlapping_supports(F, K_type)
+    assert Mo.Vmat is not None and Mg.coupled
+    rp, mem, w, nmem = Mg.C_Z
+    Cn = sp.csr_matrix(Mo.Cmat); Cn.sort_indices()
+    assert nmem == Cn.nnz and np.array_equal(dev.download(rp, Mg.m + 1), Cn.indptr)
+    assert np.array_equal(dev.download(mem, nmem), Cn.indices)
+    np.testing.assert_allclose(dev.download(w, nmem), Cn.data, rtol=1e-15)
+    Sg = Mg.S.to_scipy(dev)
+    assert _same_pattern(Mo.S, Sg)
+    np.testing.assert_allclose(Sg.data, Mo.S.data, rtol=1e-12)
+    np.testing.assert_allclose(dev.download(Mg.Vfs, Mg.m), Mo.Vfs, rtol=1e-13)
+    O.SRE_fit(Mo, n_EM=5, tol=0.0)
+    F.SRE_fit(Mg, n_EM=5, tol=0.0)
+    assert Mo.sigma2fshat > 0
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=RTOL_UNIROOT, atol=1e-12)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL_UNIROOT)
+    close(Mg.get("mu_eta"), Mo.mu_eta, RTOL_UNIROOT)
+    po = O.predict(Mo, obs_fs=True)
+    pg = F.predict(Mg, obs_fs=True)
+    close(pg["mu"], po[0], RTOL_UNIROOT)
+    close(pg["var"], po[1], RTOL_UNIROOT)
+    with pytest.raises(F.FRKError, match="coupled through shared BAUs"):
+        F.predict(Mg, obs_fs=False)
+    assert abs(F.loglik(Mg) - O.loglik(Mo)) <= RTOL * abs(O.loglik(Mo))
+
+
+def test_average_in_BAU_false(dev):
+    """SRE(average_in_BAU = FALSE), R/geometryfns.R:1304-1305: every observation is kept, several of them share a BAU, so
+    Vfs = C diag(fs) C' couples them (blocks of fs_b) and the EM takes the general branches.  Known sigma2fs as well."""
+    import scipy.sparse as sp
+    import frk_b200 as F
+    xy, z = readme_points(400, seed=21)
+    std = 0.2 + 0.1 * np.random.default_rng(2).uniform(size=len(z))
+    ob = O.auto_basis(O.plane(), xy, regular=1, nres=2)
+    obaus = O.auto_BAUs_plane(xy, cellsize=0.06)
+    b = O.points_to_BAUs(xy, obaus)
+    keep = b >= 0
+    m = int(keep.sum())
+    assert len(np.unique(b[keep])) < m                                 # several observations per BAU
+    Cm = sp.csr_matrix((np.ones(m), b[keep], np.arange(m + 1)), shape=(m, obaus.n))
+    fs = 0.5 + obaus.centroids()[:, 0]
+    Mo = O.SRE(ob, obaus.centroids(), fs, None, z[keep], std[keep], K_type="block-exponential", C=Cm, allow_overlap=True)
+    BAUs = F.auto_BAUs(F.plane(), cellsize=0.06, data=F.SpatialPointsDataFrame(xy, {}))
+    BAUs["fs"] = fs
+    Mg = F.SRE("z ~ 1", F.SpatialPointsDataFrame(xy, {"z": z, "std": std}), _mk_basis(F, ob), BAUs, est_error=False,
+               average_in_BAU=False)
+    assert Mg.m == m and Mg.coupled
+    assert np.array_equal(dev.download(Mg.obs_bau, m), b[keep])
+    O.SRE_fit(Mo, n_EM=4, tol=0.0)
+    F.SRE_fit(Mg, n_EM=4, tol=0.0)
+    np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=RTOL_UNIROOT, atol=1e-12)
+    np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=RTOL_UNIROOT)
+    pg, po = F.predict(Mg, obs_fs=True), O.predict(Mo, obs_fs=True)
+    close(pg["mu"], po[0], RTOL_UNIROOT)
+    close(pg["var"], po[1], RTOL_UNIROOT)
+    # known sigma2fs: no root search, so the full 1e-9 bar applies
+    Mo2 = O.SRE(ob, obaus.centroids(), fs, None, z[keep], std[keep], K_type="unstructured", C=Cm, allow_overlap=True)
+    Mg2 = F.SRE("z ~ 1", F.SpatialPointsDataFrame(xy, {"z": z, "std": std}), _mk_basis(F, ob), BAUs, est_error=False,
+                average_in_BAU=False, K_type="unstructured")
+    O.SRE_fit(Mo2, n_EM=3, tol=0.0, known_sigma2fs=0.05)
+    F.SRE_fit(Mg2, n_EM=3, tol=0.0, known_sigma2fs=0.05)
+    np.testing.assert_allclose(Mg2.info_fit["llk"], Mo2.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mg2.alphahat, Mo2.alphahat, rtol=RTOL)
+    close(Mg2.get("mu_eta"), Mo2.mu_eta)
+    close(Mg2.get("S_eta"), Mo2.S_eta)

@@ -338,3 +338,66 @@ def test_widening_golden_fixture():
                 assert now[sect][k] == v, (sect, k)
             else:
                 np.testing.assert_allclose(now[sect][k], v, rtol=1e-8, err_msg=f"{sect}.{k}")
+
+
+def test_general_branches_nondiagonal_Vfs_against_brute_force():
+    """The oracle's restatement of the reference's GENERAL branches (non-diagonal Vfs: footprints sharing BAUs; R/SREfit.R:186-189,
+    240-252, 296-328) pinned by independent algebra: the log-likelihood equals the dense Gaussian log-density of
+    Z ~ N(X alpha, S K S' + D); the E-step equals Gaussian conditioning; J(sigma2fs) is minus the derivative of the profiled
+    expected complete-data log-likelihood (alpha at its GLS value), checked by central differences."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    xy = rng.uniform(size=(60, 2))
+    z = np.sin(4 * xy[:, 0]) + 0.3 * rng.standard_normal(60)
+    std = 0.2 + 0.1 * rng.uniform(size=60)
+    ob = O.auto_basis(O.plane(), xy, regular=1, nres=1)
+    baus = O.auto_BAUs_plane(xy, cellsize=0.15)
+    b = O.points_to_BAUs(xy, baus)
+    keep = b >= 0
+    m = int(keep.sum())
+    Cm = sp.csr_matrix((np.ones(m), b[keep], np.arange(m + 1)), shape=(m, baus.n))
+    fs = 0.5 + baus.centroids()[:, 1]
+    M = O.SRE(ob, baus.centroids(), fs, None, z[keep], std[keep], K_type="unstructured", C=Cm, allow_overlap=True)
+    assert M.Vmat is not None and np.count_nonzero(M.Vmat - np.diag(np.diag(M.Vmat))) > 0
+    O.SRE_fit(M, n_EM=2, tol=0.0)
+    S = np.asarray(M.S.todense())
+    D = M.sigma2fshat * M.Vmat + np.diag(M.Ve)
+    Sig = S @ M.Khat @ S.T + D
+    res = M.Z - M.X @ M.alphahat
+    ll = -0.5 * (m * np.log(2 * np.pi) + np.linalg.slogdet(Sig)[1] + res @ np.linalg.solve(Sig, res))
+    assert abs(O.loglik(M) - ll) <= 1e-10 * abs(ll)
+    O.Estep(M)
+    mu = M.Khat @ S.T @ np.linalg.solve(Sig, res)
+    Se = M.Khat - M.Khat @ S.T @ np.linalg.solve(Sig, S @ M.Khat)
+    np.testing.assert_allclose(M.mu_eta, mu, rtol=1e-8, atol=1e-10 * abs(mu).max())
+    np.testing.assert_allclose(M.S_eta, Se, rtol=1e-7, atol=1e-9 * abs(Se).max())
+
+    E = M.S_eta + np.outer(M.mu_eta, M.mu_eta)
+
+    def Qprof(s2):
+        Dm = s2 * M.Vmat + np.diag(M.Ve)
+        Di = np.linalg.inv(Dm)
+        al = np.linalg.solve(M.X.T @ Di @ M.X, M.X.T @ Di @ (M.Z - S @ M.mu_eta))
+        r = M.Z - M.X @ al
+        Om = S @ E @ S.T - np.outer(S @ M.mu_eta, r) - np.outer(r, S @ M.mu_eta) + np.outer(r, r)
+        return -0.5 * np.linalg.slogdet(Dm)[1] - 0.5 * np.trace(Di @ Om)
+
+    # J as _Mstep_general evaluates it (re-stated here through the oracle's own pieces)
+    def J(s2):
+        Dm = s2 * M.Vmat + np.diag(M.Ve)
+        Di = O.chol2inv(O.chol_upper(Dm))
+        W = Di @ M.Vmat @ Di
+        al = np.linalg.solve(M.X.T @ Di @ M.X, M.X.T @ Di @ (M.Z - S @ M.mu_eta))
+        r = M.Z - M.X @ al
+        tr2 = np.sum(((W @ S) @ E) * S) - 2.0 * np.sum(((W @ S) @ M.mu_eta) * r) + np.sum((W @ r) * r)
+        return -(-0.5 * np.trace(Di @ M.Vmat) + 0.5 * tr2)
+
+    for s2 in (0.02, 0.1, 0.5):
+        h = 1e-6 * s2
+        num = (Qprof(s2 + h) - Qprof(s2 - h)) / (2 * h)
+        assert abs(-J(s2) - num) <= 1e-5 * max(abs(num), 1e-3)
+    # and the M-step's root brackets a zero of that J within uniroot's tolerance (eps^0.25 = 1.2e-4 on sigma2fs)
+    O.Mstep(M)
+    if M.sigma2fshat > 0:
+        lo, hi = max(M.sigma2fshat - 2.5e-4, 1e-12), M.sigma2fshat + 2.5e-4
+        assert np.sign(J(lo)) != np.sign(J(hi))
