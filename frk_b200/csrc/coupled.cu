@@ -317,6 +317,107 @@ __global__ void msums_finish_kernel(int grid, int ns1, const double *__restrict_
     }
 }
 
+
+// D_c^-1 of every component at sigma2fs into out (layout of Vc); part[blockIdx.x] = failure flag
+__global__ void __launch_bounds__(CP_T) dinv_kernel(int ncomp, const int *__restrict__ cptr, const int *__restrict__ cmem,
+                                                    const int64_t *__restrict__ voff, const double *__restrict__ Vc,
+                                                    const double *__restrict__ ve, double s2, double *__restrict__ out,
+                                                    double *__restrict__ part) {
+    extern __shared__ __align__(16) double csm[];
+    double *Dm = csm, *Wm = csm + NCMAX * CLD;
+    __shared__ int flag;
+    __shared__ int smem_mem[NCMAX];
+    double bad = 0.0;
+    for (int c = blockIdx.x; c < ncomp; c += gridDim.x) {
+        const int c0 = cptr[c], n = cptr[c + 1] - c0;
+        __syncthreads();
+        if (n == 1) {
+            const double d = s2 * Vc[voff[c]] + ve[cmem[c0]];
+            if (!(d > 0.0)) bad = 1.0;
+            if (threadIdx.x == 0) out[voff[c]] = 1.0 / d;
+            continue;
+        }
+        for (int a = threadIdx.x; a < n; a += blockDim.x) smem_mem[a] = cmem[c0 + a];
+        __syncthreads();
+        if (!load_and_factor(Dm, n, Vc + voff[c], smem_mem, ve, s2, &flag)) { bad = 1.0; continue; }
+        for (int j = threadIdx.x; j < n; j += blockDim.x)
+            for (int i = 0; i < n; i++) {
+                double acc = (i == j) ? 1.0 : 0.0;
+                for (int k = j; k < i; k++) acc -= Dm[i * CLD + k] * Wm[k * CLD + j];
+                Wm[i * CLD + j] = i < j ? 0.0 : acc / Dm[i * CLD + i];
+            }
+        __syncthreads();
+        double *o = out + voff[c];
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+            const int i = idx % n, j = idx / n;
+            double acc = 0.0;
+            for (int k = max(i, j); k < n; k++) acc += Wm[k * CLD + i] * Wm[k * CLD + j];
+            o[idx] = acc;
+        }
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = bad;
+}
+
+// one warp per (touched BAU, observation of its component): s_i' M s0_k with the two rows in different CSR matrices
+__global__ void __launch_bounds__(256) cross_bau_kernel(int64_t npairs, const int *__restrict__ pk, const int *__restrict__ pi, int r,
+                                                        const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+                                                        const int *__restrict__ rowptr0, const int *__restrict__ col0,
+                                                        const double *__restrict__ val0, const double *__restrict__ M, double *__restrict__ H) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < npairs; q += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int i = pi[q], k = pk[q];
+        const int bi = rowptr[i], ki = rowptr[i + 1] - bi, bk = rowptr0[k], kk = rowptr0[k + 1] - bk;
+        double tq = 0.0;
+        for (int a = 0; a < ki; a++) {
+            const double *Mc = M + (size_t)r * col[bi + a];
+            double part = 0.0;
+            for (int b = lane; b < kk; b += 32) part += __ldg(Mc + col0[bk + b]) * val0[bk + b];
+            tq += val[bi + a] * part;
+        }
+        tq = warp_sum(tq);
+        if (lane == 0) H[q] = tq;
+    }
+}
+
+// Case 2 of .SRE.predict_EM (R/SREpredict.R:308-333) for the BAUs inside observation footprints, one thread per touched BAU t:
+//   u = D_c^-1 c_k,  g = sigma2fs fs_k u  (c_k: the BAU's column of Cmat restricted to its component)
+//   mu_k  += g'(Z_c - X_c alpha - S_c mu~)
+//   var_k  = s_k'Sigma~ s_k - 2 g'h_k + g'B_c g + sigma2fs fs_k - (sigma2fs fs_k)^2 c_k'u,   h_k[a] = s_{i_a}'Sigma~ s_k
+__global__ void __launch_bounds__(128) case2_kernel(int nt, const int *__restrict__ tb_bau, const int *__restrict__ tb_comp,
+                                                    const int *__restrict__ tb_ptr, const int *__restrict__ tb_a, const double *__restrict__ tb_w,
+                                                    const int64_t *__restrict__ tb_hoff, const int *__restrict__ cptr,
+                                                    const int *__restrict__ cmem, const int64_t *__restrict__ voff,
+                                                    const double *__restrict__ Dinv, const double *__restrict__ Bc, const double *__restrict__ H,
+                                                    const double *__restrict__ res, const double *__restrict__ smuS, const double *__restrict__ q,
+                                                    const double *__restrict__ fs, double s2, double *__restrict__ mu, double *__restrict__ var, double *__restrict__ sd) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const int k = tb_bau[t], c = tb_comp[t], c0 = cptr[c], n = cptr[c + 1] - c0;
+    const double *Di = Dinv + voff[c], *B = Bc + voff[c], *h = H + tb_hoff[t];
+    const double sf = s2 * fs[k];
+    double u[NCMAX];
+    for (int a = 0; a < n; a++) {
+        double acc = 0.0;
+        for (int x = tb_ptr[t]; x < tb_ptr[t + 1]; x++) acc += Di[a + (size_t)tb_a[x] * n] * tb_w[x];
+        u[a] = acc;
+    }
+    double cu = 0.0;
+    for (int x = tb_ptr[t]; x < tb_ptr[t + 1]; x++) cu += tb_w[x] * u[tb_a[x]];
+    double ge = 0.0, gh = 0.0, gBg = 0.0;
+    for (int a = 0; a < n; a++) {
+        const double ga = sf * u[a];
+        ge += ga * (res[cmem[c0 + a]] - smuS[cmem[c0 + a]]);                 // e = Z - X alpha - S mu~
+        gh += ga * h[a];
+        double row = 0.0;
+        for (int b = 0; b < n; b++) row += B[a + (size_t)b * n] * u[b];
+        gBg += ga * sf * row;
+    }
+    const double v = q[k] - 2.0 * gh + gBg + sf - sf * sf * cu;
+    mu[k] += ge;
+    var[k] = v;
+    sd[k] = sqrt(v);
+}
+
 }  // namespace
 
 int frk_coupling_destroy(frk_coupling *C) {
@@ -510,4 +611,95 @@ int frk_coupling_msums(frk_coupling *C, frk_ctx *ctx, const double *d_X, const d
     FRK_REQUIRE(h[ns] == 0.0, "sigma2fs * Vfs + Ve is not positive definite (R: chol(D) fails, R/SREfit.R:304)");
     for (int k = 0; k < ns; k++) h_out[k] = h[k];
     return 0;
+}
+
+// Case-2 prediction (obs_fs = FALSE, sigma2fs > 0) at the BAUs that lie inside observation footprints; every other BAU keeps the
+// "unobserved" values the caller has already written.  cz_*: Cmat as device CSR over the observations (rows normalised);
+// d_Sig = Sigma~ (posterior covariance at the final parameters), d_res = Z - X alpha, d_smuS = S mu~, d_q[k] = s_k'Sigma~ s_k.
+int frk_coupling_case2(frk_coupling *C, frk_ctx *ctx, double sigma2fs, const double *d_Ve, int64_t nbau, const int *d_cz_rowptr,
+                       const int *d_cz_members, const double *d_cz_weights, const int *d_rowptr, const int *d_col, const double *d_val,
+                       const int *d_rowptr0, const int *d_col0, const double *d_val0, const double *d_Sig, const double *d_res,
+                       const double *d_smuS, const double *d_q, const double *d_fs, double *d_mu, double *d_var, double *d_sd) {
+    const int m = (int)C->m;
+    // ---- host: the touched BAUs, their components and their columns of Cmat ----
+    std::vector<int> crp(m + 1), cptr(C->ncomp + 1), cmem(m);
+    FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    FRK_CHECK_CUDA(cudaMemcpy(crp.data(), d_cz_rowptr, (size_t)(m + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    FRK_CHECK_CUDA(cudaMemcpy(cptr.data(), C->cptr, (size_t)(C->ncomp + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    FRK_CHECK_CUDA(cudaMemcpy(cmem.data(), C->cmem, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost));
+    const int nz = crp[m];
+    std::vector<int> cmemb((size_t)std::max(nz, 1));
+    std::vector<double> cw((size_t)std::max(nz, 1));
+    if (nz) {
+        FRK_CHECK_CUDA(cudaMemcpy(cmemb.data(), d_cz_members, (size_t)nz * sizeof(int), cudaMemcpyDeviceToHost));
+        FRK_CHECK_CUDA(cudaMemcpy(cw.data(), d_cz_weights, (size_t)nz * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    std::vector<int> comp_of(m), local(m);
+    for (int c = 0; c < C->ncomp; c++) for (int a = cptr[c]; a < cptr[c + 1]; a++) { comp_of[cmem[a]] = c; local[cmem[a]] = a - cptr[c]; }
+    // entries (bau, obs, weight) sorted by bau (stable: observations ascending within a BAU)
+    std::vector<int> order((size_t)nz), eobs((size_t)nz);
+    for (int i = 0; i < m; i++) for (int x = crp[i]; x < crp[i + 1]; x++) eobs[x] = i;
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cmemb[a] < cmemb[b]; });
+    std::vector<int> tb_bau, tb_comp, tb_ptr{0}, tb_a, pk, pi;
+    std::vector<double> tb_w;
+    std::vector<int64_t> tb_hoff{0};
+    for (size_t x = 0; x < order.size();) {
+        const int k = cmemb[order[x]];
+        FRK_REQUIRE(k >= 0 && k < nbau, "frk_coupling_case2: BAU index out of range in the incidence matrix");
+        const int c = comp_of[eobs[order[x]]];
+        for (; x < order.size() && cmemb[order[x]] == k; x++) {
+            FRK_REQUIRE(comp_of[eobs[order[x]]] == c, "frk_coupling_case2: the incidence matrix does not match the model's Vfs");
+            tb_a.push_back(local[eobs[order[x]]]);
+            tb_w.push_back(cw[order[x]]);
+        }
+        tb_bau.push_back(k); tb_comp.push_back(c); tb_ptr.push_back((int)tb_a.size());
+        for (int a = cptr[c]; a < cptr[c + 1]; a++) { pk.push_back(k); pi.push_back(cmem[a]); }
+        tb_hoff.push_back((int64_t)pk.size());
+    }
+    const int nt = (int)tb_bau.size();
+    if (nt == 0) return 0;
+    // ---- device ----
+    const size_t npairs = pk.size(), nv = 0;
+    (void)nv;
+    int64_t vtot = 0;
+    FRK_CHECK_CUDA(cudaMemcpy(&vtot, C->voff + C->ncomp, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    char *buf = nullptr;
+    auto al8 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t b_bau = al8(nt * sizeof(int)), b_ptr = al8((nt + 1) * sizeof(int)), b_a = al8(tb_a.size() * sizeof(int)),
+                 b_w = al8(tb_w.size() * sizeof(double)), b_hoff = al8((nt + 1) * sizeof(int64_t)), b_pk = al8(npairs * sizeof(int)),
+                 b_H = al8(npairs * sizeof(double)), b_Di = al8((size_t)vtot * sizeof(double));
+    FRK_CHECK_CUDA(cudaMalloc((void **)&buf, 2 * b_bau + b_ptr + b_a + b_w + b_hoff + 2 * b_pk + b_H + b_Di));
+    char *o = buf;
+    int *d_bau = (int *)o; o += b_bau; int *d_comp = (int *)o; o += b_bau; int *d_ptr = (int *)o; o += b_ptr; int *d_a = (int *)o; o += b_a;
+    double *d_w = (double *)o; o += b_w; int64_t *d_hoff = (int64_t *)o; o += b_hoff; int *d_pk = (int *)o; o += b_pk; int *d_pi = (int *)o; o += b_pk;
+    double *d_H = (double *)o; o += b_H; double *d_Di = (double *)o;
+    auto run = [&]() -> int {
+        FRK_CHECK_CUDA(cudaMemcpy(d_bau, tb_bau.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(d_comp, tb_comp.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(d_ptr, tb_ptr.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(d_a, tb_a.data(), tb_a.size() * sizeof(int), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(d_w, tb_w.data(), tb_w.size() * sizeof(double), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(d_hoff, tb_hoff.data(), (nt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(d_pk, pk.data(), npairs * sizeof(int), cudaMemcpyHostToDevice));
+        FRK_CHECK_CUDA(cudaMemcpy(d_pi, pi.data(), npairs * sizeof(int), cudaMemcpyHostToDevice));
+        const size_t smem = (size_t)2 * NCMAX * CLD * sizeof(double);
+        static bool attr = false;
+        if (!attr) {
+            FRK_CHECK_CUDA(cudaFuncSetAttribute(dinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+        FRK_LAUNCH(ctx, dinv_kernel, C->grid, CP_T, smem, C->ncomp, C->cptr, C->cmem, C->voff, C->Vc, d_Ve, sigma2fs, d_Di, C->part);
+        if (int rc = frk_coupling_cross(C, ctx, d_rowptr, d_col, d_val, d_Sig)) return rc;                 // B_c = S_c Sigma~ S_c'
+        const unsigned grid = (unsigned)std::min<int64_t>(cdiv((int64_t)npairs * 32, 256), (int64_t)ctx->sm_count * 16);
+        FRK_LAUNCH(ctx, cross_bau_kernel, grid, 256, 0, (int64_t)npairs, d_pk, d_pi, C->r, d_rowptr, d_col, d_val, d_rowptr0, d_col0, d_val0,
+                   d_Sig, d_H);
+        FRK_LAUNCH(ctx, case2_kernel, (unsigned)cdiv(nt, 128), 128, 0, nt, d_bau, d_comp, d_ptr, d_a, d_w, d_hoff, C->cptr, C->cmem, C->voff,
+                   d_Di, C->Bc, d_H, d_res, d_smuS, d_q, d_fs, sigma2fs, d_mu, d_var, d_sd);
+        FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    const int rc = run();
+    cudaFree(buf);
+    return rc;
 }

@@ -16,6 +16,10 @@ int frk_coupling_whiten(frk_coupling *C, frk_ctx *ctx, double sigma2fs, const do
 int frk_coupling_cross(frk_coupling *C, frk_ctx *ctx, const int *d_rowptr, const int *d_col, const double *d_val, const double *d_M);
 int frk_coupling_msums(frk_coupling *C, frk_ctx *ctx, const double *d_X, const double *d_Z, const double *d_t, const double *d_Ve,
                        double sigma2fs, double *h_out);
+int frk_coupling_case2(frk_coupling *C, frk_ctx *ctx, double sigma2fs, const double *d_Ve, int64_t nbau, const int *d_cz_rowptr,
+                       const int *d_cz_members, const double *d_cz_weights, const int *d_rowptr, const int *d_col, const double *d_val,
+                       const int *d_rowptr0, const int *d_col0, const double *d_val0, const double *d_Sig, const double *d_res,
+                       const double *d_smuS, const double *d_q, const double *d_fs, double *d_mu, double *d_var, double *d_sd);
 const int *frk_coupling_rowptr(const frk_coupling *C);
 const int *frk_coupling_col(const frk_coupling *C);
 const double *frk_coupling_val(const frk_coupling *C);

@@ -1696,9 +1696,14 @@ extern "C" int frk_model_predict_areal(frk_model *M, int64_t n, const int *d_row
         RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, Sig, mue, q, smu));           // s_k'Sigma~ s_k, s_k'mu~
         RC(frk_quadform_spmv_bucketed(ctx, m, r, M->rowptr, M->col, M->val, M->bk, Sig, mue, QS, smuS));       // S_j Sigma~ S_j', S_j mu~
         RC(frk_resid(ctx, m, M->p, M->X, M->alpha, M->Z, nullptr, res));
-        FRK_LAUNCH(ctx, areal_dj_kernel, (unsigned)cdiv(m, 256), 256, 0, m, M->sigma2fs, M->Vfs, M->Ve, smuS, res, dj);
         // every BAU as if unobserved (g = 0): mu = x'alpha + s'mu~, var = s'Sigma~ s + sigma2fs fs; the supports' BAUs are then corrected
         RC(frk_predict_finalize(ctx, n, 1, M->sigma2fs, q, smu, xa, nullptr, nullptr, d_fs, d_mu, d_var, d_sd));
+        if (M->cp) {
+            // supports that share BAUs (or several observations per BAU): the correction couples the observations of a connected group
+            return frk_coupling_case2(M->cp, ctx, M->sigma2fs, M->Ve, n, d_cz_rowptr, d_cz_members, d_cz_weights, M->rowptr, M->col, M->val,
+                                      d_rowptr0, d_col0, d_val0, Sig, res, smuS, q, d_fs, d_mu, d_var, d_sd);
+        }
+        FRK_LAUNCH(ctx, areal_dj_kernel, (unsigned)cdiv(m, 256), 256, 0, m, M->sigma2fs, M->Vfs, M->Ve, smuS, res, dj);
         static bool attr = false;
         if (!attr) {
             FRK_CHECK_CUDA(cudaFuncSetAttribute(areal_case2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

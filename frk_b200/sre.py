@@ -313,6 +313,8 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
         h2d += vrp.nbytes + vcl.nbytes + vvl.nbytes
     if areal:
         mdl.C_Z = (cz_rowptr, cz_mem, cz_w, int(nmem.value))      # Cmat (CSR over the observations, rows normalised)
+    elif mdl.coupled:                                             # average_in_BAU = FALSE: one 1 per row, several rows per BAU
+        mdl.C_Z = (dev.upload(np.arange(m + 1, dtype=np.int32)), obs_bau, dev.upload(np.ones(m)), m)
     mdl.h2d_bytes = h2d
     if K_type == "block-exponential" and isinstance(basis, TensorP_Basis):     # BuildD(basis) = list(Basis1 = ..., Basis2 = ...)
         D = BuildD(basis)
@@ -397,10 +399,7 @@ def _predict_polygons(mdl: SREModel, newdata, obs_fs: bool):
         raise FRKError("prediction over polygons on a row-partitioned run: polygons may straddle ranks -- not on the device path yet")
     if isinstance(mdl.basis, TensorP_Basis) or isinstance(mdl.BAUs, STBAUs):
         raise FRKError("prediction over polygons in space-time is not on the device path yet")
-    if getattr(mdl, "coupled", False) and not obs_fs and mdl.sigma2fshat > 0:
-        raise FRKError("predict(obs_fs = FALSE) with sigma2fs > 0 for observations coupled through shared BAUs (the joint (eta, xi) solve "
-                       "of R/SREpredict.R:308-333 with a non-diagonal C'Ve^-1 C) is not on the device path yet; use obs_fs = TRUE")
-    if getattr(mdl, "areal", False) and not obs_fs and mdl.sigma2fshat > 0:
+    if (getattr(mdl, "areal", False) or getattr(mdl, "coupled", False)) and not obs_fs and mdl.sigma2fshat > 0:
         raise FRKError("prediction over polygons with obs_fs = FALSE for areal DATA needs the covariances between the fine-scale terms "
                        "of a support (R/SREpredict.R:392-404): not on the device path yet; use obs_fs = TRUE")
     N = mdl.N
@@ -451,10 +450,7 @@ def predict(mdl: SREModel, obs_fs: bool = False, to_host: bool = True, newdata=N
     dev = mdl.dev
     nloc = mdl.hi - mdl.lo
     mu, var, sd = (dev.empty(max(nloc, 1)) for _ in range(3))
-    if getattr(mdl, "coupled", False) and not obs_fs and mdl.sigma2fshat > 0:
-        raise FRKError("predict(obs_fs = FALSE) with sigma2fs > 0 for observations coupled through shared BAUs (the joint (eta, xi) solve "
-                       "of R/SREpredict.R:308-333 with a non-diagonal C'Ve^-1 C) is not on the device path yet; use obs_fs = TRUE")
-    if getattr(mdl, "areal", False) and not obs_fs and mdl.sigma2fshat > 0:
+    if (getattr(mdl, "areal", False) or getattr(mdl, "coupled", False)) and not obs_fs and mdl.sigma2fshat > 0:
         cz_rowptr, cz_mem, cz_w, _ = mdl.C_Z
         call("frk_model_predict_areal", mdl.handle, nloc, dev.ptr(mdl.S0.rowptr), dev.ptr(mdl.S0.col), dev.ptr(mdl.S0.val),
              mdl.S0.buckets(dev), dev.ptr(mdl.X_BAU), dev.ptr(mdl.fs_BAU), dev.ptr(cz_rowptr), dev.ptr(cz_mem), dev.ptr(cz_w),

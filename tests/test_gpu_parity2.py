@@ -362,9 +362,14 @@ def test_overlapping_areal_supports(dev, K_type):
     pg = F.predict(Mg, obs_fs=True)
     close(pg["mu"], po[0], RTOL_UNIROOT)
     close(pg["var"], po[1], RTOL_UNIROOT)
-    with pytest.raises(F.FRKError, match="coupled through shared BAUs"):
-        F.predict(Mg, obs_fs=False)
     assert abs(F.loglik(Mg) - O.loglik(Mo)) <= RTOL * abs(O.loglik(Mo))
+    # Case 2 (obs_fs = FALSE, sigma2fs > 0): the joint (eta, xi) solve, R/SREpredict.R:308-333, against its literal dense restatement
+    po2 = O.predict(Mo, obs_fs=False)
+    pg2 = F.predict(Mg, obs_fs=False)
+    close(pg2["mu"], po2[0], 1e-7)
+    close(pg2["var"], po2[1], 1e-6)
+    inside = np.asarray(Cm.sum(axis=0)).ravel() > 0
+    assert inside.any() and (~inside).any()
 
 
 def test_average_in_BAU_false(dev):
@@ -397,6 +402,10 @@ def test_average_in_BAU_false(dev):
     pg, po = F.predict(Mg, obs_fs=True), O.predict(Mo, obs_fs=True)
     close(pg["mu"], po[0], RTOL_UNIROOT)
     close(pg["var"], po[1], RTOL_UNIROOT)
+    assert Mo.sigma2fshat > 0
+    pg2, po2 = F.predict(Mg, obs_fs=False), O.predict(Mo, obs_fs=False)      # literal joint solve in the oracle (predict_general)
+    close(pg2["mu"], po2[0], 1e-7)
+    close(pg2["var"], po2[1], 1e-6)
     # known sigma2fs: no root search, so the full 1e-9 bar applies
     Mo2 = O.SRE(ob, obaus.centroids(), fs, None, z[keep], std[keep], K_type="unstructured", C=Cm, allow_overlap=True)
     Mg2 = F.SRE("z ~ 1", F.SpatialPointsDataFrame(xy, {"z": z, "std": std}), _mk_basis(F, ob), BAUs, est_error=False,
