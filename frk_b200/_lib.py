@@ -136,6 +136,8 @@ SIGNATURES = {
     "frk_model_predict_areal": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_model_set_lanes": (c_int, [vp, c_int]),
     "frk_model_set_vfs_csr": (c_int, [vp, vp, vp, vp]),
+    "frk_model_create_implicit": (c_int, [vp, c_i64, c_int, vp, vp, c_i64, c_int, vp, vp, vp, vp, ALLREDUCE_FN, vp, C.POINTER(vp)]),
+    "frk_rowbuckets_create_implicit": (c_int, [vp, c_i64, vp, vp, c_i64, c_int, C.POINTER(vp)]),
     "frk_model_coupled_groups": (c_int, [vp]),
     "frk_model_set_nm_distribute": (c_int, [vp, c_int]),
     "frk_model_set_parallel": (c_int, [vp, c_int, c_int, c_int]),

@@ -267,6 +267,36 @@ class DeviceCSR:
         return sp.csr_matrix((v, c, rp), shape=(self.n, self.ncol))
 
 
+class ImplicitBasisMatrix:
+    """An n x r basis-function matrix that is never stored: row i = eval_basis(basis, coords[i, ]) (normalised if asked), evaluated in
+    chunks inside every pass over it (frk_rowbuckets_create_implicit / frk_model_create_implicit).  For bases without compact
+    support at scale -- Gaussian / exponential / Matern 3/2 give DENSE rows: 1e7 x 3608 doubles = 290 GB.  Same duck type as
+    DeviceCSR where the device path needs it (n, ncol, nnz, NULL CSR pointers, buckets())."""
+    rowptr = col = val = None
+
+    def __init__(self, basis: Basis, d_coords, n: int, ld: int, normalise: bool):
+        self.basis, self.coords, self.n, self.ld, self.normalise = basis, d_coords, int(n), int(ld), bool(normalise)
+        self.ncol = basis.n
+        self.nnz = self.n * self.ncol
+        self._buckets = None
+
+    def buckets(self, dev: Device):
+        if self._buckets is None:
+            h = vp()
+            call("frk_rowbuckets_create_implicit", dev.ctx, self.n, self.basis.handle(dev), dev.ptr(self.coords), self.ld,
+                 1 if self.normalise else 0, C.byref(h))
+            self._buckets = h
+        return self._buckets
+
+    def __del__(self):
+        try:
+            if self._buckets is not None:
+                lib.frk_rowbuckets_destroy(self._buckets)
+                self._buckets = None
+        except Exception:
+            pass
+
+
 def _eval_single(dev: Device, basis: Basis, d_s, n: int, normalise: bool) -> DeviceCSR:
     h = basis.handle(dev)
     rowptr = dev.empty(n + 1, "i4")

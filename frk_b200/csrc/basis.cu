@@ -788,6 +788,70 @@ extern "C" int frk_eval_basis_fill(frk_ctx *ctx, const frk_basis *b, int64_t n, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Dense rows on the fly (bases without compact support at scale: Gaussian / exponential / Matern on 1e7 points x r ~ 4k would be
+// hundreds of GB as a stored matrix).  One CTA per point: out[i * r + j] = phi_j(s_i) for ALL j, optionally divided by the row norm
+// (R/SRE.R:416-421).  The consumers (bucket.cu: gram_rhs_dense / quadform_dense) evaluate a chunk of rows, use it, and drop it.
+// ---------------------------------------------------------------------------------
+template <int MAN, int TYPE>
+__global__ void __launch_bounds__(256) eval_dense_rows_kernel(BasisDev B, int64_t n, const double *__restrict__ s, int64_t ld, int normalise,
+                                                              double *__restrict__ out) {
+    __shared__ double red[8];
+    __shared__ double s_xx;
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const PointCoord p = load_point<MAN>(s, ld, i);
+        double *row = out + (size_t)i * B.r;
+        double ss = 0.0;
+        for (int j = threadIdx.x; j < B.r; j += blockDim.x) {
+            const double v = basis_phi<TYPE>(basis_dist<MAN>(p, B, j), __ldg(B.scale + j));
+            row[j] = v;
+            ss += v * v;
+        }
+        if (normalise) {
+            ss = warp_sum(ss);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int w = 0; w < 8; w++) t += red[w];
+                double xx = sqrt(t);
+                s_xx = xx == 0.0 ? 1.0 : xx;
+            }
+            __syncthreads();
+            const double xx = s_xx;
+            for (int j = threadIdx.x; j < B.r; j += blockDim.x) row[j] = row[j] / xx;     // (each thread re-reads what it wrote)
+        }
+    }
+}
+
+template <int MAN>
+static int launch_dense_rows(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *s, int64_t ld, int normalise, double *out) {
+    const unsigned grid = (unsigned)std::min<int64_t>(n, (int64_t)ctx->sm_count * 16);
+    FRK_WORK(ctx, 0, (double)n * b->dev.r * 8.0);
+    switch (b->dev.type) {
+        case FRK_BISQUARE: FRK_LAUNCH(ctx, (eval_dense_rows_kernel<MAN, FRK_BISQUARE>), grid, 256, 0, b->dev, n, s, ld, normalise, out); break;
+        case FRK_GAUSSIAN: FRK_LAUNCH(ctx, (eval_dense_rows_kernel<MAN, FRK_GAUSSIAN>), grid, 256, 0, b->dev, n, s, ld, normalise, out); break;
+        case FRK_EXP:      FRK_LAUNCH(ctx, (eval_dense_rows_kernel<MAN, FRK_EXP>), grid, 256, 0, b->dev, n, s, ld, normalise, out); break;
+        default:           FRK_LAUNCH(ctx, (eval_dense_rows_kernel<MAN, FRK_MATERN32>), grid, 256, 0, b->dev, n, s, ld, normalise, out); break;
+    }
+    return 0;
+}
+
+// rows [0, n) of eval_basis(basis, s) as a dense row-major n x r block (internal: bucket.cu's implicit matrices)
+int frk_eval_basis_dense_rows(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *d_s, int64_t ld_s, int normalise, double *d_out) {
+    FRK_REQUIRE(ctx && b && d_s && d_out && n >= 0, "frk_eval_basis_dense_rows: bad argument");
+    if (n == 0) return 0;
+    switch (b->dev.manifold) {
+        case FRK_SPHERE:   return launch_dense_rows<FRK_SPHERE>(ctx, b, n, d_s, ld_s, normalise, d_out);
+        case FRK_PLANE:    return launch_dense_rows<FRK_PLANE>(ctx, b, n, d_s, ld_s, normalise, d_out);
+        case FRK_STPLANE:  return launch_dense_rows<FRK_STPLANE>(ctx, b, n, d_s, ld_s, normalise, d_out);
+        case FRK_STSPHERE: return launch_dense_rows<FRK_STSPHERE>(ctx, b, n, d_s, ld_s, normalise, d_out);
+        default:           return launch_dense_rows<FRK_REAL_LINE>(ctx, b, n, d_s, ld_s, normalise, d_out);
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // tensor-product rows and stand-alone row normalisation
 // ---------------------------------------------------------------------------------

@@ -234,6 +234,13 @@ struct frk_rowbuckets {
     int *perm = nullptr, *bptr = nullptr, *ucol = nullptr, *nU = nullptr;
     unsigned char *lid = nullptr;
     // ELL tiles
+    // implicit: dense rows that are never stored (frk_rowbuckets_create_implicit): row i = eval_basis(ibasis, icoords[i, ]), evaluated
+    // chunk by chunk inside the Gram / quadratic-form calls
+    bool implicit = false;
+    const frk_basis *ibasis = nullptr;
+    const double *icoords = nullptr;
+    int64_t ild = 0;
+    int inorm = 0;
     bool dense = false;            // every row holds all ncols columns (non-compact basis functions): val IS the dense matrix, row-major;
                                    // the Gram and the quadratic form are then plain GEMMs and no buckets are built
     int T = 0;
@@ -386,6 +393,16 @@ extern "C" int frk_rowbuckets_create(frk_ctx *ctx, int64_t n, int ncols, const i
         B->max_nU = h_bad[1];
         for (int k = 0; k < 10; k++) B->nblk_hist[k] = h_bad[2 + k];
     }
+    *out = B;
+    return 0;
+}
+
+extern "C" int frk_rowbuckets_create_implicit(frk_ctx *ctx, int64_t n, const frk_basis *basis, const double *d_coords, int64_t ld_coords,
+                                              int normalise, frk_rowbuckets **out) {
+    FRK_REQUIRE(ctx && basis && out && n >= 0 && (n == 0 || d_coords) && ld_coords >= n, "frk_rowbuckets_create_implicit: bad argument");
+    frk_rowbuckets *B = new frk_rowbuckets();
+    B->ctx = ctx; B->n = n; B->ncols = frk_basis_n(basis); B->nnz = n * (int64_t)B->ncols;
+    B->dense = true; B->implicit = true; B->ibasis = basis; B->icoords = d_coords; B->ild = ld_coords; B->inorm = normalise;
     *out = B;
     return 0;
 }
@@ -826,7 +843,7 @@ __global__ void __launch_bounds__(256) dense_weights_kernel(int64_t c0, int64_t 
         double rho = z[row];
         for (int k = 0; k < p; k++) rho -= X[row + (int64_t)k * m] * alpha.a[k];
         const double d = sigma2fs * vfs[row] + ve[row], w = 1.0 / d;
-        const double *a = A + (size_t)row * r;
+        const double *a = A + (size_t)i * r;                          // A: the chunk's rows
         double *b = B + (size_t)i * r;
         for (int c = lane; c < r; c += 32) b[c] = w * a[c];
         if (lane == 0) { wr[i] = w * rho; q += rho * rho * w; l += log(d); }
@@ -848,25 +865,34 @@ __global__ void dense_scalars_kernel(int nblocks, const double *__restrict__ par
     }
 }
 
-static int gram_rhs_dense(frk_ctx *ctx, int64_t m, int r, const double *A, const double *d_z, const double *d_X, int p, const AlphaB &al,
-                          const double *d_ve, const double *d_vfs, double sigma2fs, double *d_acc) {
+static int gram_rhs_dense(frk_ctx *ctx, const frk_rowbuckets *bk, int64_t m, int r, const double *A, const double *d_z, const double *d_X, int p,
+                          const AlphaB &al, const double *d_ve, const double *d_vfs, double sigma2fs, double *d_acc) {
+    // chunk: the scaled copy B (and, for an implicit matrix, the evaluated rows themselves) stays below ~512 MB each
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t)(512.0 * 1024 * 1024 / (8.0 * r))));
     const unsigned grid = (unsigned)std::min<int64_t>(cdiv(chunk, 8), (int64_t)ctx->sm_count * 8);
+    const bool imp = bk->implicit;
     double *B = nullptr;
-    FRK_CHECK_CUDA(cudaMallocAsync((void **)&B, ((size_t)chunk * r + chunk + 2 * (size_t)grid) * sizeof(double), ctx->stream));
-    double *wr = B + (size_t)chunk * r, *part = wr + chunk;
+    FRK_CHECK_CUDA(cudaMallocAsync((void **)&B, ((size_t)chunk * r * (imp ? 2 : 1) + chunk + 2 * (size_t)grid) * sizeof(double), ctx->stream));
+    double *wr = B + (size_t)chunk * r, *part = wr + chunk, *Aeval = part + 2 * (size_t)grid;
     double *G = d_acc, *rhs = d_acc + (size_t)r * r;
     int rc = 0;
     for (int64_t c0 = 0; c0 < m && !rc; c0 += chunk) {
         const int64_t nc = std::min(chunk, m - c0);
+        const double *Ac = imp ? nullptr : A + (size_t)c0 * r;
+        if (imp) {                                                     // evaluate-and-accumulate: the rows exist only for this chunk
+            rc = frk_eval_basis_dense_rows(ctx, bk->ibasis, nc, bk->icoords + c0, bk->ild, bk->inorm, Aeval);
+            if (rc) break;
+            Ac = Aeval;
+        }
         do {
-            FRK_LAUNCH(ctx, dense_weights_kernel, grid, 256, 0, c0, nc, r, m, A, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, B, wr, part);
+            FRK_LAUNCH(ctx, dense_weights_kernel, grid, 256, 0, c0, nc, r, m, Ac, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, B, wr, part);
             FRK_LAUNCH(ctx, dense_scalars_kernel, 1, 32, 0, (int)grid, part, rhs + r);
         } while (0);
-        // G += A_chunk B_chunk'  (r x r, K = nc);  rhs += A_chunk wr
-        rc = frk_dgemm_nt(ctx, r, r, (int)nc, 1.0, A + (size_t)c0 * r, r, B, r, 1.0, G, r);
-        if (!rc) rc = frk_dgemm_nt(ctx, r, 1, (int)nc, 1.0, A + (size_t)c0 * r, r, wr, 1, 1.0, rhs, r);
+        // G += A_chunk B_chunk'  (r x r, K = nc; symmetric: only the lower triangle is computed, mirrored below);  rhs += A_chunk wr
+        rc = frk_dsyrk_like_lower(ctx, r, (int)nc, Ac, r, B, r, G, r);
+        if (!rc) rc = frk_dgemm_nt(ctx, r, 1, (int)nc, 1.0, Ac, r, wr, 1, 1.0, rhs, r);
     }
+    if (!rc) rc = frk_mirror_lower(ctx, r, G);                         // the accumulator's consumers read the upper triangle
     cudaFreeAsync(B, ctx->stream);
     return rc;
 }
@@ -884,14 +910,18 @@ __global__ void __launch_bounds__(256) dense_coldot_kernel(int64_t nc, int r, co
     }
 }
 
-static int quadform_dense(frk_ctx *ctx, int64_t n, int r, const double *A, const double *d_M, const double *d_mu, double *d_q, double *d_t) {
+static int quadform_dense(frk_ctx *ctx, const frk_rowbuckets *bk, int64_t n, int r, const double *A, const double *d_M, const double *d_mu,
+                          double *d_q, double *d_t) {
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(512.0 * 1024 * 1024 / (8.0 * r))));
-    double *Y = nullptr;
+    const bool imp = bk->implicit;
+    double *Y = nullptr, *Aeval = nullptr;
     if (d_M && d_q) FRK_CHECK_CUDA(cudaMallocAsync((void **)&Y, (size_t)chunk * r * sizeof(double), ctx->stream));
+    if (imp) FRK_CHECK_CUDA(cudaMallocAsync((void **)&Aeval, (size_t)chunk * r * sizeof(double), ctx->stream));
     int rc = 0;
     for (int64_t c0 = 0; c0 < n && !rc; c0 += chunk) {
         const int64_t nc = std::min(chunk, n - c0);
-        const double *Ac = A + (size_t)c0 * r;
+        const double *Ac = imp ? Aeval : A + (size_t)c0 * r;
+        if (imp) { rc = frk_eval_basis_dense_rows(ctx, bk->ibasis, nc, bk->icoords + c0, bk->ild, bk->inorm, Aeval); if (rc) break; }
         // Y = M A_chunk  (M symmetric r x r; A_chunk is K x N with k contiguous)
         if (Y) rc = frk_dgemm(ctx, 0, 1, r, (int)nc, r, 1.0, d_M, r, Ac, r, 0.0, Y, r);
         if (rc) break;
@@ -901,13 +931,14 @@ static int quadform_dense(frk_ctx *ctx, int64_t n, int r, const double *A, const
         } while (0);
     }
     if (Y) cudaFreeAsync(Y, ctx->stream);
+    if (Aeval) cudaFreeAsync(Aeval, ctx->stream);
     return rc;
 }
 
 extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *d_rowptr, const int *d_col, const double *d_val,
                                      const frk_rowbuckets *bk, const double *d_z, const double *d_X, int p, const double *h_alpha,
                                      const double *d_ve, const double *d_vfs, double sigma2fs, double *d_acc) {
-    FRK_REQUIRE(ctx && d_rowptr && d_acc && bk, "frk_gram_rhs_bucketed: NULL argument");
+    FRK_REQUIRE(ctx && d_acc && bk && (d_rowptr || bk->implicit), "frk_gram_rhs_bucketed: NULL argument");
     FRK_REQUIRE(bk->n == m && bk->ncols == r, "frk_gram_rhs_bucketed: the row buckets belong to a %lld x %d matrix", (long long)bk->n, bk->ncols);
     const int *d_perm = bk->perm, *d_bptr = bk->bptr, *d_ucol = bk->ucol, *d_nU = bk->nU;       // (all NULL for a dense matrix)
     const unsigned char *d_lid = bk->lid;
@@ -915,7 +946,7 @@ extern "C" int frk_gram_rhs_bucketed(frk_ctx *ctx, int64_t m, int r, const int *
     if (m == 0) return 0;
     AlphaB al{};
     for (int q = 0; q < p; q++) al.a[q] = h_alpha[q];
-    if (bk->dense) return gram_rhs_dense(ctx, m, r, d_val, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, d_acc);
+    if (bk->dense) return gram_rhs_dense(ctx, bk, m, r, d_val, d_z, d_X, p, al, d_ve, d_vfs, sigma2fs, d_acc);
     unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count * 8);
     static const bool legacy = getenv("FRK_GRAM_LEGACY") != nullptr;      // A/B timing: the first-generation (DFMA register-tile) kernel
     const bool ell = bk->all_ell && bk->T > 0 && bk->max_nU < GE_MAXBLK * 8 && !legacy;
@@ -1149,10 +1180,10 @@ __global__ void __launch_bounds__(QE_T, 2) quadform_ell_kernel(int nbuckets, con
 
 extern "C" int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const int *d_rowptr, const int *d_col, const double *d_val,
                                           const frk_rowbuckets *bk, const double *d_M, const double *d_mu, double *d_q, double *d_t) {
-    FRK_REQUIRE(ctx && d_rowptr && bk, "frk_quadform_spmv_bucketed: NULL argument");
+    FRK_REQUIRE(ctx && bk && (d_rowptr || bk->implicit), "frk_quadform_spmv_bucketed: NULL argument");
     FRK_REQUIRE(bk->n == n && bk->ncols == r, "frk_quadform_spmv_bucketed: the row buckets belong to a %lld x %d matrix", (long long)bk->n, bk->ncols);
     if (n == 0) return 0;
-    if (bk->dense) return quadform_dense(ctx, n, r, d_val, d_M, d_mu, d_q, d_t);
+    if (bk->dense) return quadform_dense(ctx, bk, n, r, d_val, d_M, d_mu, d_q, d_t);
     static bool attr = false;
     if (!attr) {
         FRK_CHECK_CUDA(cudaFuncSetAttribute(quadform_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QuadDmmaSmem)));

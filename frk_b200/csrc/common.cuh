@@ -109,6 +109,13 @@ int frk_ctx_lane(frk_ctx *parent, int idx, bool high_priority, frk_ctx **out);
 // exclusive scan of int32 counts[n] -> out[n+1] (out[n] = total); total also returned to host
 int frk_exclusive_scan_i32(frk_ctx *ctx, const int *d_in, int64_t n, int *d_out, int64_t *h_total);
 
+// basis.cu: rows of eval_basis as a dense row-major block, evaluated on demand (implicit matrices of bucket.cu)
+int frk_eval_basis_dense_rows(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *d_s, int64_t ld_s, int normalise, double *d_out);
+
+// dense.cu
+int frk_dsyrk_like_lower(frk_ctx *ctx, int n, int K, const double *d_A, int lda, const double *d_B, int ldb, double *d_C, int ldc);
+int frk_mirror_lower(frk_ctx *ctx, int r, double *d_A);      // A[j,i] = A[i,j] for i > j
+
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers ---------------------------------------------------------------

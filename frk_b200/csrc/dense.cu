@@ -256,6 +256,20 @@ extern "C" int frk_dgemm_nt(frk_ctx *ctx, int M, int N, int K, double alpha, con
 }
 
 // general layouts (exported for the tests): transa/transb != 0 -> the operand is stored with k contiguous
+__global__ void mirror_lower_kernel(int r, double *__restrict__ A);
+
+// C(lower triangle) += A B'  for a product known to be symmetric (A diag(w) A' with B = diag(w)-scaled A): half the tiles
+int frk_dsyrk_like_lower(frk_ctx *ctx, int n, int K, const double *d_A, int lda, const double *d_B, int ldb, double *d_C, int ldc) {
+    GemmArgs g = gemm_args(n, n, K, 1.0, d_A, lda, d_B, ldb, 1.0, d_C, ldc);
+    g.lower = 1;
+    return launch_gemm(ctx, g, false, false, (double)n * (n + 1.0) * K, "dgemm_kernel[Gram A diag(w) A']");
+}
+
+int frk_mirror_lower(frk_ctx *ctx, int r, double *d_A) {
+    FRK_LAUNCH(ctx, mirror_lower_kernel, dim3((unsigned)cdiv(r, 32), (unsigned)cdiv(r, 32)), 256, 0, r, d_A);
+    return 0;
+}
+
 extern "C" int frk_dgemm(frk_ctx *ctx, int transa, int transb, int M, int N, int K, double alpha, const double *d_A, int lda,
                          const double *d_B, int ldb, double beta, double *d_C, int ldc) {
     FRK_REQUIRE(ctx && d_A && d_B && d_C, "frk_dgemm: NULL argument");

@@ -1257,7 +1257,7 @@ static int model_common_init(frk_model *M) {
     FRK_CHECK_CUDA(cudaMemsetAsync(M->q, 0, std::max<int64_t>(M->m, 1) * sizeof(double), M->ctx->stream));
     FRK_CHECK_CUDA(cudaMemsetAsync(M->t, 0, std::max<int64_t>(M->m, 1) * sizeof(double), M->ctx->stream));
     // row buckets of S
-    RC(frk_rowbuckets_create(M->ctx, M->m, r, M->rowptr, M->col, M->val, &M->bk));
+    if (!M->bk) RC(frk_rowbuckets_create(M->ctx, M->m, r, M->rowptr, M->col, M->val, &M->bk));   // (frk_model_create_implicit brings its own)
     if (!M->allreduce && M->ctx->comm) { M->rank = M->ctx->comm_rank; M->world = M->ctx->comm_world; }
     // totals and the homoscedasticity test all(a == a[1]) & all(b == b[1])   (R/SREfit.R:278-280)
     double mt[1] = {(double)M->m};
@@ -1282,6 +1282,23 @@ extern "C" int frk_model_create(frk_ctx *ctx, int64_t m, int r, int p, const int
     M->ctx = ctx; M->m = m; M->r = r; M->p = p;
     M->rowptr = d_rowptr; M->col = d_col; M->val = d_val; M->Z = d_Z; M->X = d_X; M->Ve = d_Ve; M->Vfs = d_Vfs;
     M->allreduce = allreduce; M->user = user;
+    if (int rc = model_common_init(M)) { frk_model_destroy(M); return rc; }
+    *out = M;
+    return 0;
+}
+
+// S is never stored: row j = eval_basis(basis, coords[j, ]) (normalised if asked), evaluated chunk by chunk inside every Gram /
+// quadratic-form pass.  For bases without compact support at scale (BASELINE config 5: 1e7 observations x r ~ 4k Matern functions).
+extern "C" int frk_model_create_implicit(frk_ctx *ctx, int64_t m, int p, const frk_basis *basis, const double *d_coords, int64_t ld_coords,
+                                         int normalise, const double *d_Z, const double *d_X, const double *d_Ve, const double *d_Vfs,
+                                         frk_allreduce_fn allreduce, void *user, frk_model **out) {
+    FRK_REQUIRE(ctx && out && basis && d_coords && d_Z && d_X && d_Ve && d_Vfs && m >= 0, "frk_model_create_implicit: bad argument");
+    FRK_REQUIRE(p >= 1 && p <= MAXP_M, "frk_model_create_implicit: %d fixed effects; the device path handles 1..%d", p, MAXP_M);
+    frk_model *M = new frk_model();
+    M->ctx = ctx; M->m = m; M->r = frk_basis_n(basis); M->p = p;
+    M->Z = d_Z; M->X = d_X; M->Ve = d_Ve; M->Vfs = d_Vfs;
+    M->allreduce = allreduce; M->user = user;
+    if (int rc = frk_rowbuckets_create_implicit(ctx, m, basis, d_coords, ld_coords, normalise, &M->bk)) { delete M; return rc; }
     if (int rc = model_common_init(M)) { frk_model_destroy(M); return rc; }
     *out = M;
     return 0;
@@ -1343,6 +1360,7 @@ extern "C" int frk_model_destroy(frk_model *M) {
 extern "C" int frk_model_set_vfs_csr(frk_model *M, const int *h_rowptr, const int *h_col, const double *h_val) {
     FRK_REQUIRE(M && h_rowptr && h_col && h_val, "frk_model_set_vfs_csr: NULL argument");
     FRK_REQUIRE(!M->cp, "frk_model_set_vfs_csr: already set");
+    FRK_REQUIRE(M->rowptr, "frk_model_set_vfs_csr: not available for an implicit (never stored) basis matrix");
     FRK_REQUIRE(!multi_rank(M) && M->world == 1, "a non-diagonal Vfs couples observations across the row partition: not on the device path (one rank only)");
     bool offdiag = false;
     for (int64_t i = 0; i < M->m && !offdiag; i++)
@@ -1583,7 +1601,7 @@ extern "C" int frk_model_slot_device(frk_model *M, const char *slot, double **d_
 extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, const int *d_col0, const double *d_val0,
                                  const frk_rowbuckets *bk0, const double *d_XBAU, const double *d_fs, const int *d_obs_bau,
                                  int obs_fs, double *d_mu, double *d_var, double *d_sd) {
-    FRK_REQUIRE(M && d_rowptr0 && bk0 && d_XBAU && d_mu && d_var && d_sd && n >= 0, "frk_model_predict: bad argument");
+    FRK_REQUIRE(M && bk0 && d_XBAU && d_mu && d_var && d_sd && n >= 0, "frk_model_predict: bad argument");   // (d_rowptr0 may be NULL for implicit row buckets)
     frk_ctx *ctx = M->ctx;
     const int r = M->r;
     const size_t rr = (size_t)r * r;

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import FRKError, call, c_i64, vp
-from .basis import BuildD, DeviceCSR, TensorP_Basis, eval_basis_device
+from .basis import ImplicitBasisMatrix, BuildD, DeviceCSR, TensorP_Basis, eval_basis_device
 from .geometry import GridBAUs, STBAUs, SpatialPointsDataFrame, SpatialPolygonsDataFrame, map_data_to_BAUs
 from .runtime import Device, get_device, partition_rows
 
@@ -60,8 +60,12 @@ class SREModel:
         # row-partitioned runs: the context's own NCCL communicator if it has one (Device.init_comm), else the Python reduction hook
         self._hook = dev.allreduce_hook() if (dev.world > 1 and not dev.has_comm) else _lib.ALLREDUCE_FN()     # must outlive the model
         h = vp()
-        call("frk_model_create", dev.ctx, m, self.r, p, dev.ptr(S.rowptr), dev.ptr(S.col), dev.ptr(S.val), dev.ptr(Z), dev.ptr(X),
-             dev.ptr(Ve), dev.ptr(Vfs), self._hook, vp(None), C.byref(h))
+        if isinstance(S, ImplicitBasisMatrix):
+            call("frk_model_create_implicit", dev.ctx, m, p, S.basis.handle(dev), dev.ptr(S.coords), S.ld, 1 if S.normalise else 0,
+                 dev.ptr(Z), dev.ptr(X), dev.ptr(Ve), dev.ptr(Vfs), self._hook, vp(None), C.byref(h))
+        else:
+            call("frk_model_create", dev.ctx, m, self.r, p, dev.ptr(S.rowptr), dev.ptr(S.col), dev.ptr(S.val), dev.ptr(Z), dev.ptr(X),
+                 dev.ptr(Ve), dev.ptr(Vfs), self._hook, vp(None), C.byref(h))
         self.handle = h
         if dev.world > 1:
             call("frk_model_set_parallel", h, dev.rank, dev.world, 0)
@@ -115,7 +119,8 @@ class SREModel:
 # ---------------------------------------------------------------------------------------
 
 def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = False, average_in_BAU: bool = True,
-        K_type: str = "block-exponential", normalise_basis: bool = True, dev: Optional[Device] = None) -> SREModel:
+        K_type: str = "block-exponential", normalise_basis: bool = True, dev: Optional[Device] = None,
+        implicit_basis: Optional[bool] = None) -> SREModel:
     """SRE(f, data, basis, BAUs, est_error, average_in_BAU, ..., K_type, normalise_basis), R/SRE.R:318-701
     for one point-referenced Gaussian data set.
 
@@ -156,6 +161,13 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
     lo, hi = partition_rows(N, dev.world, dev.rank)
     nloc = hi - lo
     h2d = 0
+    # Basis functions without compact support give dense rows.  Beyond ~8 GB for this rank's S0 the matrices are not stored at all:
+    # rows are evaluated in chunks inside every pass (ImplicitBasisMatrix; `implicit_basis` forces the choice either way)
+    dense_rows = (not isinstance(basis, TensorP_Basis)) and getattr(basis, "type", "bisquare") != "bisquare"
+    if implicit_basis is None:
+        implicit_basis = dense_rows and nloc * r * 8 > 8e9
+    if implicit_basis and (not dense_rows or areal or not average_in_BAU):
+        raise FRKError("implicit_basis needs a plain basis without compact support, point data and average_in_BAU = TRUE")
 
     # ---- S0 = eval_basis(basis, coordinates(BAUs)); normalise rows ------------------------
     if isinstance(BAUs, GridBAUs) and not isinstance(basis, TensorP_Basis):
@@ -164,13 +176,20 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
         h2d += 8 * (BAUs.nx + BAUs.ny)
         d_s = dev.empty(max(2 * nloc, 1))
         call("frk_grid_centroids", dev.ctx, lo, hi, BAUs.nx, dev.ptr(d_xg), dev.ptr(d_yg), dev.ptr(d_s))
-        S0 = eval_basis_device(basis, (d_s, nloc, 2), dev, normalise=normalise_basis)
-        if not areal:
+        if implicit_basis:
+            S0 = ImplicitBasisMatrix(basis, d_s, nloc, nloc, normalise_basis)
+        else:
+            S0 = eval_basis_device(basis, (d_s, nloc, 2), dev, normalise=normalise_basis)
+        if not areal and not implicit_basis:
             del d_s
     else:
         cc = BAUs.centroids(lo, hi)
         h2d += cc.nbytes
-        S0 = eval_basis_device(basis, cc, dev, normalise=normalise_basis)
+        if implicit_basis:
+            d_s = dev.upload(cc[:, :basis.manifold.dim])
+            S0 = ImplicitBasisMatrix(basis, d_s, nloc, nloc, normalise_basis)
+        else:
+            S0 = eval_basis_device(basis, cc, dev, normalise=normalise_basis)
         if areal:
             d_s = dev.upload(cc[:, :2])
 
@@ -251,14 +270,20 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
             call("frk_square", dev.ctx, m, dev.ptr(d_std), dev.ptr(Ve))
 
         # ---- C_Z (one 1 per row) -> S = C_Z S0, Vfs = fs[bau], X = model matrix at the observed BAUs ----
-        rowptr = dev.empty(m + 1, "i4")
-        nnz = c_i64(0)
-        call("frk_csr_gather_count", dev.ctx, m, dev.ptr(obs_bau), dev.ptr(S0.rowptr), dev.ptr(rowptr), C.byref(nnz))
-        col = dev.empty(max(nnz.value, 1), "i4")
-        val = dev.empty(max(nnz.value, 1))
-        call("frk_csr_gather_fill", dev.ctx, m, dev.ptr(obs_bau), dev.ptr(S0.rowptr), dev.ptr(S0.col), dev.ptr(S0.val),
-             dev.ptr(rowptr), dev.ptr(col), dev.ptr(val))
-        S = DeviceCSR(m, r, rowptr, col, val, nnz.value)
+        if implicit_basis:      # S = the rows of S0 at the observed BAUs = eval_basis at THEIR centroids: gather the coordinates instead
+            dcoord = basis.manifold.dim
+            d_sobs = dev.empty(max(m * dcoord, 1))
+            call("frk_gather_rows", dev.ctx, m, dcoord, dev.ptr(obs_bau), dev.ptr(d_s), nloc, dev.ptr(d_sobs), m)
+            S = ImplicitBasisMatrix(basis, d_sobs, m, m, normalise_basis)
+        else:
+            rowptr = dev.empty(m + 1, "i4")
+            nnz = c_i64(0)
+            call("frk_csr_gather_count", dev.ctx, m, dev.ptr(obs_bau), dev.ptr(S0.rowptr), dev.ptr(rowptr), C.byref(nnz))
+            col = dev.empty(max(nnz.value, 1), "i4")
+            val = dev.empty(max(nnz.value, 1))
+            call("frk_csr_gather_fill", dev.ctx, m, dev.ptr(obs_bau), dev.ptr(S0.rowptr), dev.ptr(S0.col), dev.ptr(S0.val),
+                 dev.ptr(rowptr), dev.ptr(col), dev.ptr(val))
+            S = DeviceCSR(m, r, rowptr, col, val, nnz.value)
 
     # BAU-level fields for this rank: fs and covariates
     fs_host = np.ascontiguousarray(BAUs.fields["fs"][lo:hi], dtype=np.float64)

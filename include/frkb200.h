@@ -390,6 +390,17 @@ int frk_model_set_lanes(frk_model *mdl, int lanes);
  * all-reduce per round and a broadcast of the winner's inverse); 0 (default) lets every rank evaluate them on its own lanes --
  * replicated and deterministic like the rest of the r-sized work, with no exchange.  Results are identical either way.        */
 int frk_model_set_nm_distribute(frk_model *mdl, int distribute);
+/* SRE object whose basis-function matrix S is never stored: row j of S is eval_basis(basis, coords[j, ]) (R/basisfns.R:709-748;
+ * rows divided by their norms if normalise != 0, R/SRE.R:416-421), evaluated in chunks inside every pass over the matrix and
+ * dropped again.  For basis functions without compact support (Gaussian, exponential, Matern 3/2), whose S is dense: 1e7 observations
+ * x r = 3608 would be 290 GB as a stored matrix (BASELINE config 5).  d_coords: the observed BAUs' coordinates, column-major with
+ * leading dimension ld_coords; the other arguments as frk_model_create.  frk_rowbuckets_create_implicit is the same for S0
+ * (prediction): pass the handle to frk_model_predict with NULL CSR pointers.                                                     */
+int frk_model_create_implicit(frk_ctx *ctx, int64_t m, int p, const frk_basis *basis, const double *d_coords, int64_t ld_coords,
+                              int normalise, const double *d_Z, const double *d_X, const double *d_Ve, const double *d_Vfs,
+                              frk_allreduce_fn allreduce, void *user, frk_model **out);
+int frk_rowbuckets_create_implicit(frk_ctx *ctx, int64_t n, const frk_basis *basis, const double *d_coords, int64_t ld_coords,
+                                   int normalise, frk_rowbuckets **out);
 /* Non-diagonal Vfs: observation footprints that share BAUs (overlapping areal supports, BuildC R/geometryfns.R:1572-1616), or
  * several point observations in one BAU with average_in_BAU = FALSE.  Vfs = tcrossprod(Cmat %*% Diagonal(sqrt(fs))) (R/SRE.R:498)
  * as the full symmetric m x m host CSR (0-based; the dgRMatrix slots of object@Vfs).  The EM then runs the reference's general

@@ -40,13 +40,17 @@
 ## parameter slots, so that an object restored with readRDS() continues where it stopped.
 .frkb200_model <- function(object) {
   if (object@fs_model != "ind") stop("frkb200: only fs_model = \"ind\" is on the device path")
-  ## the device path holds D = sigma2fs * Vfs + Ve as a diagonal: overlapping areal supports (non-diagonal Vfs, the general
-  ## J(sigma2fs) of R/SREfit.R:298-328) are refused here rather than silently fitted as if they were diagonal
-  if (!Matrix::isDiagonal(object@Ve) || !Matrix::isDiagonal(object@Vfs))
-    stop("frkb200: non-diagonal Ve / Vfs (overlapping areal supports) is not on the device path")
+  ## Ve is diagonal in every model SRE() builds (R/SRE.R:468); anything else is refused rather than fitted as if it were
+  if (!Matrix::isDiagonal(object@Ve)) stop("frkb200: a non-diagonal Ve is not on the device path")
   S <- as(object@S, "RsparseMatrix")
   mdl <- .Call("frkb200_model_create", S@p, S@j, S@x, ncol(S), as.numeric(object@Z), as.matrix(object@X),
                as.numeric(diag(object@Ve)), as.numeric(diag(object@Vfs)))
+  ## overlapping areal supports / average_in_BAU = FALSE: Vfs has off-diagonal entries and the EM takes the general branches
+  ## (chol(D), J with Dinv %*% Vfs %*% Dinv, R/SREfit.R:186-189,240-252,296-328) -- the library does too, given the sparse matrix
+  if (!Matrix::isDiagonal(object@Vfs)) {
+    V <- as(as(object@Vfs, "generalMatrix"), "RsparseMatrix")
+    .Call("frkb200_model_set_vfs", mdl, V@p, V@j, as.numeric(V@x))
+  }
   if (object@K_type == "block-exponential")
     .Call("frkb200_model_set_blocks", mdl, as.integer(object@basis@df$res), lapply(object@D_basis, as.matrix))
   for (slot in c("mu_eta", "S_eta", "Q_eta", "Khat_inv", "alphahat", "Khat"))   # Khat last: it refreshes log|K|

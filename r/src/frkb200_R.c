@@ -119,6 +119,12 @@ SEXP frkb200_model_set_blocks(SEXP mdl, SEXP res, SEXP Dlist) {
     return R_NilValue;
 }
 
+/* non-diagonal object@Vfs (overlapping areal supports, average_in_BAU = FALSE): the dgRMatrix slots p, j, x (R/SRE.R:498) */
+SEXP frkb200_model_set_vfs(SEXP mdl, SEXP p, SEXP j, SEXP x) {
+    FRK_TRY(frk_model_set_vfs_csr(model_or_error(mdl), INTEGER(p), INTEGER(j), REAL(x)), (void)0);
+    return R_NilValue;
+}
+
 /* push the slots of the S4 object (so that saveRDS()/readRDS() between SRE.fit calls resumes EM) */
 SEXP frkb200_model_set(SEXP mdl, SEXP name, SEXP value) {
     FRK_TRY(frk_model_set(model_or_error(mdl), CHAR(STRING_ELT(name, 0)), REAL(value)), (void)0);
@@ -228,6 +234,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"frkb200_grid_lookup", (DL_FUNC)&frkb200_grid_lookup, 5},
     {"frkb200_model_create", (DL_FUNC)&frkb200_model_create, 8},
     {"frkb200_model_set_blocks", (DL_FUNC)&frkb200_model_set_blocks, 3},
+    {"frkb200_model_set_vfs", (DL_FUNC)&frkb200_model_set_vfs, 4},
     {"frkb200_model_set", (DL_FUNC)&frkb200_model_set, 3},
     {"frkb200_model_get", (DL_FUNC)&frkb200_model_get, 3},
     {"frkb200_model_set_lanes", (DL_FUNC)&frkb200_model_set_lanes, 2},

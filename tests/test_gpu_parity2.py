@@ -416,3 +416,42 @@ def test_average_in_BAU_false(dev):
     np.testing.assert_allclose(Mg2.alphahat, Mo2.alphahat, rtol=RTOL)
     close(Mg2.get("mu_eta"), Mo2.mu_eta)
     close(Mg2.get("S_eta"), Mo2.S_eta)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 5 at scale: basis functions without compact support, S and S0 never stored (evaluate-and-accumulate)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K_type", ["unstructured", "block-exponential"])
+def test_implicit_basis_matrix_matches_stored(dev, K_type):
+    """SRE(implicit_basis = TRUE): the rows of S / S0 (Matern-3/2 on the sphere: dense) are evaluated in chunks inside the Gram and
+    quadratic-form passes and dropped again (frk_model_create_implicit / frk_rowbuckets_create_implicit).  Same numbers as the stored
+    dense path and as the oracle: log-likelihood trace, estimates, predictions under both obs_fs."""
+    import frk_b200 as F
+    from cases import pseudo_isea3h, sphere_points
+    ll, z = sphere_points(4000, seed=29)
+    iso = pseudo_isea3h()
+    ob = O.auto_basis(O.sphere(), ll, nres=3, type="Matern32", isea3h=iso, isea3h_lo=1)       # r = 32 + 92 + 272 = 396
+    obaus = O.GridBAUs(np.arange(-177.5, 180.0, 5.0), np.arange(-87.5, 90.0, 5.0), np.array([5.0, 5.0]))
+    bau = O.points_to_BAUs(ll, obaus)
+    std = np.full(len(z), 0.3)
+    uo, means, _ = O.bin_mean(bau, np.column_stack([z, std]))
+    Mo = O.SRE(ob, obaus.centroids(), np.ones(obaus.n), uo, means[:, 0], means[:, 1], K_type=K_type)
+    gb = F.GridBAUs(obaus.xgrid.copy(), obaus.ygrid.copy(), np.array([5.0, 5.0]))
+    gb["fs"] = 1.0
+    data = F.SpatialPointsDataFrame(ll, {"z": z, "std": std})
+    Mi = F.SRE("z ~ 1", data, _mk_basis(F, ob), gb, est_error=False, K_type=K_type, implicit_basis=True)
+    Ms = F.SRE("z ~ 1", data, _mk_basis(F, ob), gb, est_error=False, K_type=K_type, implicit_basis=False)
+    assert Mi.S.val is None and Mi.S0.val is None and Mi.S.nnz == Mi.m * Mi.r and Ms.S.val is not None
+    O.SRE_fit(Mo, n_EM=4, tol=0.0)
+    F.SRE_fit(Mi, n_EM=4, tol=0.0)
+    F.SRE_fit(Ms, n_EM=4, tol=0.0)
+    np.testing.assert_allclose(Mi.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
+    np.testing.assert_allclose(Mi.info_fit["llk"], Ms.info_fit["llk"], rtol=RTOL)      # (row norms are summed in a different order)
+    np.testing.assert_allclose(Mi.sigma2fshat, Mo.sigma2fshat, rtol=RTOL_UNIROOT, atol=1e-12)
+    close(Mi.get("mu_eta"), Ms.get("mu_eta"), 1e-8)
+    for obs_fs in (True, False):
+        po = O.predict(Mo, obs_fs=obs_fs)
+        pi, ps = F.predict(Mi, obs_fs=obs_fs), F.predict(Ms, obs_fs=obs_fs)
+        close(pi["mu"], po[0], 1e-7)
+        close(pi["var"], po[1], 1e-6)
+        close(pi["var"], ps["var"], 1e-8)
