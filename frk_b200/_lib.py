@@ -90,6 +90,7 @@ SIGNATURES = {
     "frk_polygons_destroy": (c_int, [vp]),
     "frk_polygon_lookup": (c_int, [vp, vp, c_i64, vp, c_i64, c_int, c_int, vp]),
     "frk_bin_mean": (c_int, [vp, c_i64, vp, c_i64, c_int, vp, vp, vp, vp, p_i64]),
+    "frk_bin_mean_sum": (c_int, [vp, c_i64, vp, c_i64, c_int, vp, C.c_uint, vp, vp, vp, p_i64]),
     "frk_grid_centroids": (c_int, [vp, c_i64, c_i64, c_int, vp, vp, vp]),
     "frk_csr_gather_count": (c_int, [vp, c_i64, vp, vp, vp, p_i64]),
     "frk_csr_gather_fill": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),

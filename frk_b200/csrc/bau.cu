@@ -118,7 +118,7 @@ __global__ void bin_scatter_kernel(int64_t n, const int *__restrict__ bau, const
 
 __global__ void bin_reduce_kernel(int64_t nbau, int64_t n, int ncols, const int *__restrict__ cnt, const int *__restrict__ slot,
                                   const int *__restrict__ start, int *__restrict__ members, const double *__restrict__ vals,
-                                  int *__restrict__ obs_bau, double *__restrict__ means, int *__restrict__ counts) {
+                                  unsigned sum_mask, int *__restrict__ obs_bau, double *__restrict__ means, int *__restrict__ counts) {
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbau; b += (int64_t)gridDim.x * blockDim.x) {
         int c = cnt[b];
         if (c == 0) continue;
@@ -136,6 +136,7 @@ __global__ void bin_reduce_kernel(int64_t nbau, int64_t n, int ncols, const int 
             // R's mean(): s = sum(x)/n, then s + sum(x - s)/n
             double s = 0.0;
             for (int a = 0; a < c; a++) s += v[mem[a]];
+            if (col < 32 && ((sum_mask >> col) & 1u)) { means[(int64_t)col * n + row] = s; continue; }   // sum_variables: .safe_sum, :1294-1299
             s /= (double)c;
             double t = 0.0;
             for (int a = 0; a < c; a++) t += v[mem[a]] - s;
@@ -146,7 +147,13 @@ __global__ void bin_reduce_kernel(int64_t nbau, int64_t n, int ncols, const int 
 
 extern "C" int frk_bin_mean(frk_ctx *ctx, int64_t n, const int *d_bau, int64_t nbau, int ncols, const double *d_vals,
                             int *d_obs_bau, double *d_means, int *d_counts, int64_t *h_m) {
+    return frk_bin_mean_sum(ctx, n, d_bau, nbau, ncols, d_vals, 0u, d_obs_bau, d_means, d_counts, h_m);
+}
+
+extern "C" int frk_bin_mean_sum(frk_ctx *ctx, int64_t n, const int *d_bau, int64_t nbau, int ncols, const double *d_vals, unsigned sum_mask,
+                                int *d_obs_bau, double *d_means, int *d_counts, int64_t *h_m) {
     FRK_REQUIRE(ctx && d_bau && d_obs_bau && d_means && d_counts && h_m, "frk_bin_mean: NULL argument");
+    FRK_REQUIRE(sum_mask == 0u || ncols <= 32, "frk_bin_mean_sum: sum_variables among more than 32 columns");
     FRK_REQUIRE(nbau > 0 && nbau < 2147483647LL && n < 2147483647LL, "frk_bin_mean: sizes exceed int32");
     *h_m = 0;
     if (n == 0) return 0;
@@ -166,7 +173,7 @@ extern "C" int frk_bin_mean(frk_ctx *ctx, int64_t n, const int *d_bau, int64_t n
     if (int rc = frk_exclusive_scan_i32(ctx, flag, nbau, slot, &m)) return rc;
     if (int rc = frk_exclusive_scan_i32(ctx, cnt, nbau, start, &kept)) return rc;
     FRK_LAUNCH(ctx, bin_scatter_kernel, gp, 256, 0, n, d_bau, start, fill, members);
-    FRK_LAUNCH(ctx, bin_reduce_kernel, gb, 256, 0, nbau, n, ncols, cnt, slot, start, members, d_vals, d_obs_bau, d_means, d_counts);
+    FRK_LAUNCH(ctx, bin_reduce_kernel, gb, 256, 0, nbau, n, ncols, cnt, slot, start, members, d_vals, sum_mask, d_obs_bau, d_means, d_counts);
     *h_m = m;
     return 0;
 }

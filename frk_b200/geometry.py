@@ -322,14 +322,15 @@ def auto_BAUs(manifold: Manifold, cellsize=None, data: Optional[SpatialPointsDat
 
 
 def map_data_to_BAUs(data: SpatialPointsDataFrame, BAUs, columns, dev: Optional[Device] = None,
-                     row_range=None):
+                     row_range=None, sum_variables=None):
     """map_data_to_BAUs(SpatialPoints, BAUs, average_in_BAU = TRUE), R/geometryfns.R:1222-1320.
 
     Device pipeline: integer point-in-cell lookup (sp::over on SpatialPixels) -> drop NAs ->
     group by BAU -> mean of every requested column.  Returns device tensors
     (obs_bau[m] ascending BAU rows, means (ncols x m, i.e. m x ncols column-major), counts[m]) and
     the per-point BAU index.  ``row_range=(lo,hi)`` keeps only points whose BAU is owned by this
-    rank (multi-GPU row partition) and returns BAU rows relative to ``lo``."""
+    rank (multi-GPU row partition) and returns BAU rows relative to ``lo``.  ``sum_variables``: columns that are summed over the
+    observations of a BAU rather than averaged (R/geometryfns.R:1286-1299)."""
     dev = dev or get_device()
     n = len(data)
     ncols = len(columns)
@@ -345,7 +346,7 @@ def map_data_to_BAUs(data: SpatialPointsDataFrame, BAUs, columns, dev: Optional[
              int(lo), int(hi), dev.ptr(d_bau))
     else:
         d_bau = _spatial_lookup(dev, data, BAUs, n, lo, hi)
-    return _bin(dev, data, columns, d_bau, n, ncols, lo, hi)
+    return _bin(dev, data, columns, d_bau, n, ncols, lo, hi, sum_variables)
 
 
 def point_BAU_index(data: SpatialPointsDataFrame, BAUs, dev: Optional[Device] = None) -> np.ndarray:
@@ -382,7 +383,7 @@ def _spatial_lookup(dev, data, BAUs, n, lo, hi):
     return d_bau
 
 
-def _bin(dev, data, columns, d_bau, n, ncols, lo, hi):
+def _bin(dev, data, columns, d_bau, n, ncols, lo, hi, sum_variables=None):
     """group_by(BAU) %>% summarise_all(mean), R/geometryfns.R:1286-1302."""
     d_vals = dev.empty(max(n * ncols, 1))                          # n x ncols column-major, one H2D per column (no host-side stacking)
     for k, c in enumerate(columns):
@@ -394,6 +395,11 @@ def _bin(dev, data, columns, d_bau, n, ncols, lo, hi):
     d_means = dev.empty(max(n * ncols, 1), "f8")
     d_cnt = dev.empty(max(n, 1), "i4")
     m = c_i64(0)
-    call("frk_bin_mean", dev.ctx, n, dev.ptr(d_bau), hi - lo, ncols, dev.ptr(d_vals), dev.ptr(d_obs),
+    mask = 0
+    for v in (sum_variables or []):
+        if v not in columns:
+            raise ValueError(f"sum_variables: {v!r} is not one of the binned columns")
+        mask |= 1 << list(columns).index(v)
+    call("frk_bin_mean_sum", dev.ctx, n, dev.ptr(d_bau), hi - lo, ncols, dev.ptr(d_vals), mask, dev.ptr(d_obs),
          dev.ptr(d_means), dev.ptr(d_cnt), C.byref(m))
     return dict(m=int(m.value), obs_bau=d_obs, means=d_means, ld=n, counts=d_cnt, bau=d_bau)

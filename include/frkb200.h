@@ -214,6 +214,11 @@ int frk_polygon_incidence_fill(frk_ctx *ctx, const frk_polygons *P, int64_t n, c
 int frk_bin_mean(frk_ctx *ctx, int64_t n, const int *d_bau, int64_t nbau, int ncols,
                  const double *d_vals, int *d_obs_bau, double *d_means, int *d_counts,
                  int64_t *h_m);
+/* the same with map_data_to_BAUs(sum_variables = ...) (R/geometryfns.R:1286-1299): columns whose bit is set in sum_mask are
+ * SUMMED over the observations of a BAU (.safe_sum) instead of averaged (ncols <= 32 then).                                  */
+int frk_bin_mean_sum(frk_ctx *ctx, int64_t n, const int *d_bau, int64_t nbau, int ncols,
+                     const double *d_vals, unsigned sum_mask, int *d_obs_bau, double *d_means, int *d_counts,
+                     int64_t *h_m);
 
 /* coordinates(BAUs) of a pixel grid in expand.grid order (x fastest), BAU rows [lo, hi): what SRE()
  * hands to eval_basis (R/SRE.R:412; grid layout R/geometryfns.R:629-637).  d_xgrid[nx], d_ygrid[ny]

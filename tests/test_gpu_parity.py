@@ -238,6 +238,13 @@ def test_grid_lookup_and_binning(dev):
     assert np.array_equal(dev.download(out["counts"], m), co)
     means = dev.download(out["means"]).reshape(2, -1)[:, :m].T
     np.testing.assert_allclose(means, mo, rtol=1e-12, atol=1e-15)
+    # sum_variables (R/geometryfns.R:1286-1299): the named columns are summed over the observations of a BAU, the others averaged
+    cnt_col = np.ones(len(z))
+    data2 = F.SpatialPointsDataFrame(xy, {"z": z, "k": cnt_col, "std": std})
+    out2 = F.map_data_to_BAUs(data2, gb, ["z", "k", "std"], dev, sum_variables=["k"])
+    m2 = dev.download(out2["means"]).reshape(3, -1)[:, :m].T
+    np.testing.assert_allclose(m2[:, [0, 2]], mo, rtol=1e-12, atol=1e-15)
+    assert np.array_equal(m2[:, 1], co.astype(np.float64))            # the sum of ones = the number of observations in the BAU
     # host-buffer C-ABI entry point, with an explicit cell2bau map
     import ctypes as C
     from frk_b200._lib import call, vp
