@@ -1618,6 +1618,8 @@ extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, 
         }
         // joint (eta, xi) solve at the final parameters (:308-333); for point data: one more E-step + the same quadratic form
         FRK_REQUIRE(d_fs && d_obs_bau, "frk_model_predict: obs_fs = FALSE needs the BAU fs field and the observation -> BAU map");
+        FRK_REQUIRE(!M->cp, "frk_model_predict: observations coupled through shared BAUs (non-diagonal Vfs) -- obs_fs = FALSE goes through "
+                    "frk_model_predict_areal with the incidence matrix Cmat (the one-BAU-per-observation closed form does not apply)");
         double *Q, o[4];
         FRK_CHECK_CUDA(cudaMallocAsync((void **)&Q, (2 * rr + r) * sizeof(double), ctx->stream));
         double *Sig = Q + rr, *mue = Sig + rr;
@@ -1783,6 +1785,8 @@ extern "C" int frk_model_predict_polygons(frk_model *M, int64_t n, const int *d_
     const size_t rr = (size_t)r * r;
     const bool case1 = obs_fs || M->sigma2fs == 0.0;
     FRK_REQUIRE(case1 || (d_fs && d_obs_bau), "frk_model_predict_polygons: obs_fs = FALSE needs the BAU fs field and the observation -> BAU map");
+    FRK_REQUIRE(case1 || !M->cp, "frk_model_predict_polygons: obs_fs = FALSE over polygons for observations coupled through shared BAUs is not on "
+                "the device path (the polygon variance needs the xi covariances inside a coupled group); use obs_fs = TRUE or predict at the BAUs");
     const int64_t m1 = std::max<int64_t>(M->m, 1);
     double *buf = nullptr;
     int *irp = nullptr;

@@ -100,7 +100,8 @@
   }
   X <- as.matrix(FRK:::.extract_BAU_X_matrix(object@f, BAUs))
   CZ <- as(object@Cmat, "RsparseMatrix")
-  point_data <- all(diff(CZ@p) == 1L)                           # one BAU per observation (R/geometryfns.R:1557-1568)
+  point_data <- all(diff(CZ@p) == 1L) && !anyDuplicated(CZ@j)   # one BAU per observation and one observation per BAU (R/geometryfns.R:1557-1568);
+                                                                # anything else (areal supports, average_in_BAU = FALSE) passes Cmat itself
   polygons <- !(predict_BAUs & !covariances)
   out <- .Call("frkb200_model_predict", mdl, .frkb200_csr(object@S0), X + 0, as.numeric(BAUs$fs),
                if (point_data) as.integer(CZ@j) else NULL,
