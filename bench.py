@@ -52,12 +52,19 @@ def parse():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--predict-reps", type=int, default=5)
     ap.add_argument("--deterministic", action="store_true", help="fixed-order Gram flush instead of fp64 atomics (bit-reproducible runs)")
-    ap.add_argument("--distribute-nm", action="store_true", help="spread the Nelder-Mead candidates over the ranks (default: replicated on local lanes)")
+    ap.add_argument("--distribute-nm", dest="distribute_nm", action="store_true", default=None,
+                    help="spread the Nelder-Mead candidates over the ranks (default when N > 1 with the library's NCCL communicator: "
+                         "measured 163 / 167 against 157 / 158 EM it/s replicated at N = 8 / 4, profiles/r02h_scale_modes.txt)")
+    ap.add_argument("--replicate-nm", dest="distribute_nm", action="store_false",
+                    help="every rank evaluates the Nelder-Mead candidates on its own lanes (no exchange)")
     ap.add_argument("--lanes", type=int, default=None, help="concurrent Nelder-Mead evaluation lanes per GPU (frk_model_set_lanes)")
     ap.add_argument("--comm", default="nccl", choices=["nccl", "hook"],
                     help="multi-GPU reductions: the library's own NCCL communicator (frk_comm_init) or the torch.distributed hook")
     ap.add_argument("--parity-tol", type=float, default=1e-9, help="relative tolerance of the in-run parity check against the oracle")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.distribute_nm is None:          # default: distributed candidates on several GPUs over the library's communicator
+        args.distribute_nm = int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.comm == "nccl"
+    return args
 
 
 def workload(args):
@@ -87,8 +94,11 @@ def config(args, r, n_bau, m):
 def cpu_em(args, budget_s, max_steps, warmup=0):
     """EM iterations of the oracle on the full workload (S evaluated at the occupied BAUs only; BAU-level
     prediction timed on a 1e5-BAU sample).  Returns a dict for the JSON line."""
-    from threadpoolctl import threadpool_info
+    from threadpoolctl import threadpool_info, threadpool_limits
     from oracle import frk_oracle as O
+    # all host cores whatever the launcher exported (torch.distributed.run sets OMP_NUM_THREADS=1 for every rank, which made the
+    # N >= 2 reference arms of round 1 slower than the N = 1 one): the same BLAS thread count for every N
+    threadpool_limits(limits=os.cpu_count())
     xy, z, std = workload(args)
     ob = O.auto_basis(O.plane(), np.array([[0.0, 0.0], [1.0, 1.0]]), regular=args.regular, nres=args.nres)
     ba = O.auto_BAUs_plane(xy, cellsize=1.0 / (args.grid - 1), xlims=(0, 1), ylims=(0, 1))
@@ -343,12 +353,12 @@ def run_b200(args):
                     "share_of_step": round(g["ms"] / tot_ms, 4)}
             # DRAM bytes per launch from the committed ncu capture of this command (tools/traffic_pass.sh); a recorded
             # measurement, not taken in this run -- the operands (<= 86 MB) mostly stay in the 126 MB L2
-            tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01f_dgemm_traffic.json")
+            tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02r_dgemm_traffic.json")
             if args.k_type == "block-exponential" and os.path.exists(tpath):
                 try:
                     tj = json.load(open(tpath))
                     roof["traffic"] = tj["dram_bytes_per_launch"]
-                    roof["traffic_source"] = "profiles/r01f_dgemm_traffic.json (ncu dram__bytes_read+write over %d launches)" % tj["launches"]
+                    roof["traffic_source"] = "profiles/r02r_dgemm_traffic.json (ncu dram__bytes_read+write over %d launches)" % tj["launches"]
                 except Exception:
                     pass
         elif ent is not None:
