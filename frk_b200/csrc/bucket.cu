@@ -897,37 +897,47 @@ static int gram_rhs_dense(frk_ctx *ctx, const frk_rowbuckets *bk, int64_t m, int
     return rc;
 }
 
+// q_i = a_i . y_i (square = 0: Y = M A) or y_i . y_i (square = 1: Y = L^-1 A, M = L^-T L^-1);  t_i = a_i . mu
 __global__ void __launch_bounds__(256) dense_coldot_kernel(int64_t nc, int r, const double *__restrict__ A, const double *__restrict__ Y,
-                                                           const double *__restrict__ mu, double *__restrict__ q, double *__restrict__ t) {
+                                                           const double *__restrict__ mu, double *__restrict__ q, double *__restrict__ t,
+                                                           int square) {
     const int lane = threadIdx.x & 31;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nc; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
         const double *a = A + (size_t)i * r;
         double sq = 0.0, st = 0.0;
-        if (Y) { const double *y = Y + (size_t)i * r; for (int c = lane; c < r; c += 32) sq += a[c] * y[c]; }
+        if (Y) {
+            const double *y = Y + (size_t)i * r;
+            if (square) for (int c = lane; c < r; c += 32) sq += y[c] * y[c];
+            else for (int c = lane; c < r; c += 32) sq += a[c] * y[c];
+        }
         if (mu) for (int c = lane; c < r; c += 32) st += a[c] * __ldg(mu + c);
         sq = warp_sum(sq); st = warp_sum(st);
         if (lane == 0) { if (q && Y) q[i] = sq; if (t && mu) t[i] = st; }
     }
 }
 
+// d_Linv != NULL: M = L^-T L^-1 with the lower-triangular L^-1 given (what frk_potri leaves in its work buffer): q_i = |L^-1 a_i|^2,
+// a triangular product -- half the flops of M A
 static int quadform_dense(frk_ctx *ctx, const frk_rowbuckets *bk, int64_t n, int r, const double *A, const double *d_M, const double *d_mu,
-                          double *d_q, double *d_t) {
+                          double *d_q, double *d_t, const double *d_Linv = nullptr) {
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(512.0 * 1024 * 1024 / (8.0 * r))));
     const bool imp = bk->implicit;
     double *Y = nullptr, *Aeval = nullptr;
-    if (d_M && d_q) FRK_CHECK_CUDA(cudaMallocAsync((void **)&Y, (size_t)chunk * r * sizeof(double), ctx->stream));
+    if ((d_M || d_Linv) && d_q) FRK_CHECK_CUDA(cudaMallocAsync((void **)&Y, (size_t)chunk * r * sizeof(double), ctx->stream));
     if (imp) FRK_CHECK_CUDA(cudaMallocAsync((void **)&Aeval, (size_t)chunk * r * sizeof(double), ctx->stream));
     int rc = 0;
     for (int64_t c0 = 0; c0 < n && !rc; c0 += chunk) {
         const int64_t nc = std::min(chunk, n - c0);
         const double *Ac = imp ? Aeval : A + (size_t)c0 * r;
         if (imp) { rc = frk_eval_basis_dense_rows(ctx, bk->ibasis, nc, bk->icoords + c0, bk->ild, bk->inorm, Aeval); if (rc) break; }
-        // Y = M A_chunk  (M symmetric r x r; A_chunk is K x N with k contiguous)
-        if (Y) rc = frk_dgemm(ctx, 0, 1, r, (int)nc, r, 1.0, d_M, r, Ac, r, 0.0, Y, r);
+        // Y = M A_chunk  (M symmetric r x r; A_chunk is K x N with k contiguous), or the triangular Y = L^-1 A_chunk
+        if (Y && d_Linv) rc = frk_dtrmm_lower(ctx, r, (int)nc, d_Linv, r, Ac, r, Y, r);
+        else if (Y) rc = frk_dgemm(ctx, 0, 1, r, (int)nc, r, 1.0, d_M, r, Ac, r, 0.0, Y, r);
         if (rc) break;
         const unsigned grid = (unsigned)std::min<int64_t>(cdiv(nc * 32, 256), (int64_t)ctx->sm_count * 16);
         do {
-            FRK_LAUNCH(ctx, dense_coldot_kernel, grid, 256, 0, nc, r, Ac, (const double *)Y, d_mu, d_q ? d_q + c0 : nullptr, d_t ? d_t + c0 : nullptr);
+            FRK_LAUNCH(ctx, dense_coldot_kernel, grid, 256, 0, nc, r, Ac, (const double *)Y, d_mu, d_q ? d_q + c0 : nullptr, d_t ? d_t + c0 : nullptr,
+                       d_Linv ? 1 : 0);
         } while (0);
     }
     if (Y) cudaFreeAsync(Y, ctx->stream);
@@ -1176,6 +1186,16 @@ __global__ void __launch_bounds__(QE_T, 2) quadform_ell_kernel(int nbuckets, con
             __syncwarp();
         }
     }
+}
+
+int frk_rowbuckets_is_dense(const frk_rowbuckets *bk) { return bk && bk->dense; }
+
+// dense / implicit matrices only: the quadratic forms against M = L^-T L^-1 through the triangular factor (model.cu)
+int frk_quadform_dense_factor(frk_ctx *ctx, int64_t n, int r, const double *d_val, const frk_rowbuckets *bk, const double *d_Linv,
+                              const double *d_mu, double *d_q, double *d_t) {
+    FRK_REQUIRE(ctx && bk && bk->dense && d_Linv && bk->n == n && bk->ncols == r, "frk_quadform_dense_factor: bad argument");
+    if (n == 0) return 0;
+    return quadform_dense(ctx, bk, n, r, d_val, nullptr, d_mu, d_q, d_t, d_Linv);
 }
 
 extern "C" int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const int *d_rowptr, const int *d_col, const double *d_val,

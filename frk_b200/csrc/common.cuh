@@ -115,6 +115,11 @@ int frk_eval_basis_dense_rows(frk_ctx *ctx, const frk_basis *b, int64_t n, const
 // dense.cu
 int frk_dsyrk_like_lower(frk_ctx *ctx, int n, int K, const double *d_A, int lda, const double *d_B, int ldb, double *d_C, int ldc);
 int frk_mirror_lower(frk_ctx *ctx, int r, double *d_A);      // A[j,i] = A[i,j] for i > j
+int frk_dtrmm_lower(frk_ctx *ctx, int n, int N, const double *d_X, int ldx, const double *d_B, int ldb, double *d_C, int ldc);
+// bucket.cu
+int frk_rowbuckets_is_dense(const frk_rowbuckets *bk);
+int frk_quadform_dense_factor(frk_ctx *ctx, int64_t n, int r, const double *d_val, const frk_rowbuckets *bk, const double *d_Linv,
+                              const double *d_mu, double *d_q, double *d_t);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

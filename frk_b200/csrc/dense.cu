@@ -265,6 +265,13 @@ int frk_dsyrk_like_lower(frk_ctx *ctx, int n, int K, const double *d_A, int lda,
     return launch_gemm(ctx, g, false, false, (double)n * (n + 1.0) * K, "dgemm_kernel[Gram A diag(w) A']");
 }
 
+// C (n x N) = X B with X lower triangular n x n (column-major) and B stored K x N with k contiguous: k <= the tile's last row
+int frk_dtrmm_lower(frk_ctx *ctx, int n, int N, const double *d_X, int ldx, const double *d_B, int ldb, double *d_C, int ldc) {
+    GemmArgs g = gemm_args(n, N, n, 1.0, d_X, ldx, d_B, ldb, 0.0, d_C, ldc);
+    g.k_to_m = 1;
+    return launch_gemm(ctx, g, false, true, (double)n * n * N, "dgemm_kernel[L^-1 A]");
+}
+
 int frk_mirror_lower(frk_ctx *ctx, int r, double *d_A) {
     FRK_LAUNCH(ctx, mirror_lower_kernel, dim3((unsigned)cdiv(r, 32), (unsigned)cdiv(r, 32)), 256, 0, r, d_A);
     return 0;

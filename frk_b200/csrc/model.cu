@@ -49,6 +49,8 @@ struct frk_model {
     const double *val = nullptr, *Z = nullptr, *X = nullptr, *Ve = nullptr, *Vfs = nullptr;
     bool owned = false;
     frk_rowbuckets *bk = nullptr;
+    double *Linv = nullptr;         // dense / implicit S: L^-1 of the last E-step into the slots (S_eta = L^-T L^-1), for the triangular quadratic forms
+    bool linv_valid = false;
     frk_coupling *cp = nullptr;     // non-diagonal Vfs (observations coupled through shared BAUs): see coupled.cu; M->Vfs then holds diag(Vfs)
     // r-sized slots (device), replicated on every rank
     double *mu_eta = nullptr, *S_eta = nullptr, *Q_eta = nullptr, *Khat = nullptr, *Khat_inv = nullptr;
@@ -570,6 +572,11 @@ int posterior(frk_model *M, const double *alpha, double sigma2fs, double *Q_out,
     RC(frk_potrf(ctx, r, M->w1, &out[0]));
     if (Q_out == M->Q_eta) M->logdetQ = out[0];
     RC(frk_potri(ctx, r, M->w1, Sig_out, M->w2));
+    if (Q_out == M->Q_eta && frk_rowbuckets_is_dense(M->bk)) {     // keep L^-1 beside the S_eta slot (w2 is scratch for the K update)
+        if (!M->Linv) RC(dalloc(M, &M->Linv, rr));
+        FRK_CHECK_CUDA(cudaMemcpyAsync(M->Linv, M->w2, rr * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        M->linv_valid = true;
+    }
     RC(frk_symv(ctx, r, Sig_out, b, mu_out));
     // || (rDinv S) solve(R) ||^2 with solve(R)' = L^-1 left in w2 by potri   (R/SREfit.R:211)
     RC(frk_lower_mulv(ctx, r, M->w2, b, M->vec));
@@ -1151,7 +1158,10 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
         }
         FRK_CHECK_CUDA(cudaEventRecord(M->ev_aux0, ctx->stream));
         FRK_CHECK_CUDA(cudaStreamWaitEvent(M->aux->stream, M->ev_aux0, 0));
-        RC(frk_quadform_spmv_bucketed(M->aux, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
+        if (M->linv_valid && frk_rowbuckets_is_dense(M->bk))        // dense rows: q_j = |L^-1 s_j|^2, half the flops of S_eta s_j
+            RC(frk_quadform_dense_factor(M->aux, M->m, r, M->val, M->bk, M->Linv, M->mu_eta, M->q, M->t));
+        else
+            RC(frk_quadform_spmv_bucketed(M->aux, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
         FRK_CHECK_CUDA(cudaEventRecord(M->ev_aux1, M->aux->stream));
         ctx->launches += M->aux->launches;
         M->aux->launches = 0;
@@ -1166,7 +1176,12 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
         sigma_done = true;
         frk_ctx *c = beside ? M->aux : ctx;
         double s2new = est ? sigma2fs : known_sigma2fs;
-        if (!beside) RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
+        if (!beside) {
+            if (M->linv_valid && frk_rowbuckets_is_dense(M->bk))
+                RC(frk_quadform_dense_factor(ctx, M->m, r, M->val, M->bk, M->Linv, M->mu_eta, M->q, M->t));
+            else
+                RC(frk_quadform_spmv_bucketed(ctx, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
+        }
         if (M->cp && !M->all_vfs_zero) RC(frk_coupling_cross(M->cp, c, M->rowptr, M->col, M->val, M->S_eta));   // S_c S_eta S_c' per coupled group
         double al[MAXP_M];
         MSums s;
@@ -1579,6 +1594,7 @@ extern "C" int frk_model_set(frk_model *M, const char *slot, const double *h_in)
     RC(frk_h2d(M->ctx, p, h_in, n * sizeof(double)));
     FRK_CHECK_CUDA(cudaStreamSynchronize(M->ctx->stream));
     if (!strcmp(slot, "Khat") || !strcmp(slot, "Khat_inv")) M->khat_block_diag = false;   // caller-supplied: assume nothing
+    if (!strcmp(slot, "S_eta") || !strcmp(slot, "Q_eta")) M->linv_valid = false;          // ... nor that L^-1 still belongs to S_eta
     if (!strcmp(slot, "Khat")) {                                     // keep log|K| consistent with the slot (.loglik.ind :177,197)
         const size_t rr = (size_t)M->r * M->r;
         FRK_CHECK_CUDA(cudaMemcpyAsync(M->w1, M->Khat, rr * sizeof(double), cudaMemcpyDeviceToDevice, M->ctx->stream));
@@ -1613,7 +1629,10 @@ extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, 
     auto run = [&]() -> int {
         RC(frk_xalpha(ctx, n, M->p, d_XBAU, M->alpha, xa));
         if (obs_fs || M->sigma2fs == 0.0) {                           // the stored posterior (R/SREpredict.R:334-361)
-            RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, M->S_eta, M->mu_eta, q, smu));
+            if (M->linv_valid && frk_rowbuckets_is_dense(bk0))
+                RC(frk_quadform_dense_factor(ctx, n, r, d_val0, bk0, M->Linv, M->mu_eta, q, smu));
+            else
+                RC(frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, M->S_eta, M->mu_eta, q, smu));
             return frk_predict_finalize(ctx, n, 0, M->sigma2fs, q, smu, xa, nullptr, nullptr, nullptr, d_mu, d_var, d_sd);
         }
         // joint (eta, xi) solve at the final parameters (:308-333); for point data: one more E-step + the same quadratic form
@@ -1624,7 +1643,9 @@ extern "C" int frk_model_predict(frk_model *M, int64_t n, const int *d_rowptr0, 
         FRK_CHECK_CUDA(cudaMallocAsync((void **)&Q, (2 * rr + r) * sizeof(double), ctx->stream));
         double *Sig = Q + rr, *mue = Sig + rr;
         int rc2 = posterior(M, M->alpha, M->sigma2fs, Q, Sig, mue, o);
-        if (!rc2) rc2 = frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, Sig, mue, q, smu);
+        if (!rc2 && frk_rowbuckets_is_dense(bk0))                   // (posterior left L^-1 of THIS Sig in w2)
+            rc2 = frk_quadform_dense_factor(ctx, n, r, d_val0, bk0, M->w2, mue, q, smu);
+        else if (!rc2) rc2 = frk_quadform_spmv_bucketed(ctx, n, r, d_rowptr0, d_col0, d_val0, bk0, Sig, mue, q, smu);
         cudaFreeAsync(Q, ctx->stream);
         if (rc2) return rc2;
         // A = diag(C' Ve^-1 C), ytil = C' Ve^-1 (Z - X alpha)

@@ -215,6 +215,21 @@ def get_device(index: Optional[int] = None) -> Device:
     return _DEVICE
 
 
+def partition_rows_weighted(weights, world: int, rank: int):
+    """Contiguous partition of len(weights) rows over `world` ranks with (nearly) equal weight per rank: the cut after rank k is
+    the first row at which the cumulative weight reaches (k + 1) / world of the total.  Every rank computes the same cuts from
+    the same weights.  Used when the work per BAU row is uneven (observations are not uniform over the BAU index)."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = len(w)
+    if world <= 1 or n == 0:
+        return 0, n
+    c = np.cumsum(w)
+    cuts = [0] + [int(np.searchsorted(c, c[-1] * (k + 1) / world, side="left")) + 1 for k in range(world - 1)] + [n]
+    cuts = np.minimum.accumulate(np.asarray(cuts[::-1]))[::-1]                # (monotone even with long runs of zero weight)
+    cuts = np.maximum.accumulate(np.clip(cuts, 0, n))
+    return int(cuts[rank]), int(cuts[rank + 1])
+
+
 def partition_rows(n: int, world: int, rank: int):
     """Contiguous block partition of n rows over `world` ranks: [lo, hi) for `rank`
     (BAUs block-partitioned by row range; each observation lives on the rank

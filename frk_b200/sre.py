@@ -120,7 +120,7 @@ class SREModel:
 
 def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = False, average_in_BAU: bool = True,
         K_type: str = "block-exponential", normalise_basis: bool = True, dev: Optional[Device] = None,
-        implicit_basis: Optional[bool] = None) -> SREModel:
+        implicit_basis: Optional[bool] = None, balance: str = "BAUs", obs_weight: float = 13.0) -> SREModel:
     """SRE(f, data, basis, BAUs, est_error, average_in_BAU, ..., K_type, normalise_basis), R/SRE.R:318-701
     for one point-referenced Gaussian data set.
 
@@ -159,6 +159,17 @@ def SRE(f: str, data: SpatialPointsDataFrame, basis, BAUs, est_error: bool = Fal
         if isinstance(basis, TensorP_Basis) or isinstance(BAUs, STBAUs):
             raise FRKError("areal (polygon) data in space-time (BuildC for STFDF, R/geometryfns.R:1628-1672) is not on the device path yet")
     lo, hi = partition_rows(N, dev.world, dev.rank)
+    if balance == "observations" and dev.world > 1 and not areal and not isinstance(BAUs, STBAUs):
+        # equal WORK per rank instead of equal BAU counts: a BAU row costs 1 (prediction), an observation in it `obs_weight` (the
+        # EM passes over S; 13 = ten EM iterations against one prediction pass, measured on BASELINE config 5 where the
+        # observations are uniform on the sphere but the lon/lat BAU rows are not)
+        from .geometry import point_BAU_index
+        from .runtime import partition_rows_weighted
+        b_all = point_BAU_index(data, BAUs, dev)
+        cnt = np.bincount(b_all[b_all >= 0], minlength=N).astype(np.float64)
+        lo, hi = partition_rows_weighted(1.0 + float(obs_weight) * cnt, dev.world, dev.rank)
+    elif balance not in ("BAUs", "observations"):
+        raise ValueError("balance needs to be \"BAUs\" or \"observations\"")
     nloc = hi - lo
     h2d = 0
     # Basis functions without compact support give dense rows.  Beyond ~8 GB for this rank's S0 the matrices are not stored at all:

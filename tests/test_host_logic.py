@@ -144,3 +144,19 @@ def test_speculative_nelder_mead_equals_sequential(width):
             assert rounds == seq_distinct == evals
         elif seq_distinct > 3:
             assert rounds < seq_distinct                 # speculation saved at least one round
+
+
+def test_partition_rows_weighted_balances_work():
+    """Row partition by WORK (SRE(balance = "observations")): contiguous, covering, every rank within one row's weight of the mean."""
+    from frk_b200.runtime import partition_rows, partition_rows_weighted
+    rng = np.random.default_rng(3)
+    w = 1.0 + 13.0 * rng.poisson(np.cos(np.linspace(-1.5, 1.5, 5000)) ** 2 * 3.0)       # dense in the middle, sparse at the ends
+    for world in (2, 3, 8):
+        parts = [partition_rows_weighted(w, world, k) for k in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == len(w)
+        assert all(parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+        loads = np.array([w[a:b].sum() for a, b in parts])
+        assert np.all(np.abs(loads - w.sum() / world) <= w.max() + 1e-9)
+        eq = np.array([w[slice(*partition_rows(len(w), world, k))].sum() for k in range(world)])
+        assert loads.max() <= eq.max()                                 # never worse than the equal-count partition
+    assert partition_rows_weighted(np.ones(10), 1, 0) == (0, 10)

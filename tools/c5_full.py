@@ -23,6 +23,7 @@ ap.add_argument("--nx", type=int, default=2236)
 ap.add_argument("--ny", type=int, default=1118)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--k-type", default="unstructured")
+ap.add_argument("--balance", default="observations", choices=["BAUs", "observations"])
 args = ap.parse_args()
 
 import torch  # noqa: E402
@@ -63,7 +64,7 @@ gb["fs"] = 1.0
 data = F.SpatialPointsDataFrame(ll, {"z": z, "std": np.full(n_obs, 0.3)})
 barrier()
 t0 = time.time()
-mdl = F.SRE("z ~ 1", data, basis, gb, est_error=False, K_type=args.k_type, implicit_basis=True)
+mdl = F.SRE("z ~ 1", data, basis, gb, est_error=False, K_type=args.k_type, implicit_basis=True, balance=args.balance)
 barrier()
 t1 = time.time()
 F.SRE_fit(mdl, n_EM=1, tol=0.0)              # warm-up iteration (allocator pools, CUDA graphs)
@@ -80,7 +81,7 @@ mem = torch.cuda.max_memory_allocated() / 2**30
 free, total = torch.cuda.mem_get_info()
 if rank == 0:
     print(json.dumps({"config": "C5", "n_gpus": world, "n_obs": n_obs, "r": basis.n, "n_bau": len(gb), "m_rank0": mdl.m,
-                      "K_type": args.k_type, "implicit_basis": True, "sre_s": round(t1 - t0, 3), "first_iteration_s": round(t2 - t1, 3),
+                      "K_type": args.k_type, "implicit_basis": True, "balance": args.balance, "rows_rank0": [mdl.lo, mdl.hi], "sre_s": round(t1 - t0, 3), "first_iteration_s": round(t2 - t1, 3),
                       "em_s_per_iteration": round((t3 - t2) / args.steps, 4), "em_iterations": args.steps,
                       "predict_s": round(t4 - t3, 3), "predict_baus_per_s": len(gb) / (t4 - t3),
                       "llk": [float(v) for v in mdl.info_fit["llk"]], "sigma2fshat": mdl.sigma2fshat,
