@@ -137,6 +137,7 @@ SIGNATURES = {
     "frk_model_predict_areal": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frk_model_set_lanes": (c_int, [vp, c_int]),
     "frk_model_set_vfs_csr": (c_int, [vp, vp, vp, vp]),
+    "frk_polygon_lookup_host": (c_int, [vp, c_int, vp, vp, vp, c_i64, vp, vp]),
     "frk_model_create_implicit": (c_int, [vp, c_i64, c_int, vp, vp, c_i64, c_int, vp, vp, vp, vp, ALLREDUCE_FN, vp, C.POINTER(vp)]),
     "frk_rowbuckets_create_implicit": (c_int, [vp, c_i64, vp, vp, c_i64, c_int, C.POINTER(vp)]),
     "frk_model_coupled_groups": (c_int, [vp]),

@@ -62,6 +62,28 @@ extern "C" int frk_grid_lookup_host(frk_ctx *ctx, int64_t n, const double *h_xy,
     return 0;
 }
 
+// over(SpatialPoints, SpatialPolygons BAUs) from host buffers (hexagon / irregular BAUs): the polygon index is built, used and dropped
+extern "C" int frk_polygon_lookup_host(frk_ctx *ctx, int npoly, const int *h_ptr, const double *h_vx, const double *h_vy, int64_t n,
+                                       const double *h_xy, int *h_bau) {
+    FRK_REQUIRE(ctx && h_ptr && h_vx && h_vy && h_bau && npoly > 0 && (n == 0 || h_xy), "frk_polygon_lookup_host: NULL argument");
+    if (n == 0) return 0;
+    frk_polygons *P = nullptr;
+    if (int rc = frk_polygons_create(ctx, npoly, h_ptr, h_vx, h_vy, &P)) return rc;
+    DevBuf xy(ctx->stream), out(ctx->stream);
+    auto run = [&]() -> int {
+        if (int rc = xy.alloc((size_t)n * 2 * sizeof(double))) return rc;
+        if (int rc = out.alloc((size_t)n * sizeof(int))) return rc;
+        FRK_CHECK_CUDA(cudaMemcpyAsync(xy.p, h_xy, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (int rc = frk_polygon_lookup(ctx, P, n, xy.as<double>(), n, 0, npoly, out.as<int>())) return rc;
+        FRK_CHECK_CUDA(cudaMemcpyAsync(h_bau, out.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FRK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    const int rc = run();
+    frk_polygons_destroy(P);
+    return rc;
+}
+
 extern "C" int frk_quadform_host(frk_ctx *ctx, int64_t n, int r, const int *h_rowptr, const int *h_col, const double *h_val,
                                  const double *h_M, const double *h_mu, double *h_q, double *h_t) {
     FRK_REQUIRE(ctx && h_rowptr && (h_q || h_t), "frk_quadform_host: NULL argument");

@@ -473,6 +473,10 @@ int frk_optim_nelder_mead_speculative(frk_objective_fn fn, void *user, int n, co
 int frk_optim_zeroin(frk_objective_fn fn, void *user, double lower, double upper, double *root_out);
 
 /* ---- host-buffer entry points (what the R .Call shim binds; H2D/D2H inside) ------------ */
+/* over(SpatialPoints, SpatialPolygons) for polygon BAUs (hexagons, irregular cells) from host buffers: h_xy n x 2 column-major,
+ * h_bau[n] 0-based polygon index or -1 (R/geometryfns.R:1266,1680; semantics of frk_polygon_lookup).                        */
+int frk_polygon_lookup_host(frk_ctx *ctx, int npoly, const int *h_ptr, const double *h_vx, const double *h_vy, int64_t n,
+                            const double *h_xy, int *h_bau);
 /* eval_basis on host coordinates -> host CSR.  Call with h_col == NULL to get nnz only.     */
 int frk_eval_basis_host(frk_ctx *ctx, const frk_basis *b, int64_t n, const double *h_s,
                         int normalise, int *h_rowptr, int *h_col, double *h_val, int64_t *h_nnz);

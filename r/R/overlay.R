@@ -128,6 +128,15 @@
                  as.integer(g@cells.dim), cell2bau)
     return(sp2@data[idx, , drop = FALSE])
   }
+  if (is.null(fn) && is(sp1, "SpatialPoints") && is(sp2, "SpatialPolygonsDataFrame") &&
+      all(vapply(sp2@polygons, function(p) length(p@Polygons) == 1L, TRUE))) {
+    ## polygon BAUs with one ring each (ISEA3H hexagons, BAUs_from_points): the point-in-polygon test on the device
+    rings <- lapply(sp2@polygons, function(p) p@Polygons[[1]]@coords)
+    ptr <- c(0L, cumsum(vapply(rings, nrow, 1L)))
+    xy <- do.call(rbind, rings)
+    idx <- .Call("frkb200_polygon_lookup", as.integer(ptr), as.numeric(xy[, 1]), as.numeric(xy[, 2]), coordinates(sp1) + 0)
+    return(sp2@data[idx, , drop = FALSE])
+  }
   sp::over(sp1, sp2, fn = fn)
 }
 

@@ -119,6 +119,20 @@ SEXP frkb200_model_set_blocks(SEXP mdl, SEXP res, SEXP Dlist) {
     return R_NilValue;
 }
 
+/* sp::over(SpatialPoints, SpatialPolygons BAUs): ring k = (vx, vy)[ptr[k] .. ptr[k+1]) (outer ring of BAU k, as R/geometryfns.R:1680
+ * passes them); returns the 1-based BAU row or NA */
+SEXP frkb200_polygon_lookup(SEXP ptr, SEXP vx, SEXP vy, SEXP xy) {
+    frk_ctx *ctx = ctx_or_error();
+    R_xlen_t n = Rf_nrows(xy);
+    int npoly = Rf_length(ptr) - 1;
+    int *idx = (int *)R_alloc((size_t)(n > 0 ? n : 1), sizeof(int));
+    FRK_TRY(frk_polygon_lookup_host(ctx, npoly, INTEGER(ptr), REAL(vx), REAL(vy), (int64_t)n, REAL(xy), idx), (void)0);
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, n));
+    for (R_xlen_t i = 0; i < n; i++) INTEGER(out)[i] = idx[i] < 0 ? NA_INTEGER : idx[i] + 1;
+    UNPROTECT(1);
+    return out;
+}
+
 /* non-diagonal object@Vfs (overlapping areal supports, average_in_BAU = FALSE): the dgRMatrix slots p, j, x (R/SRE.R:498) */
 SEXP frkb200_model_set_vfs(SEXP mdl, SEXP p, SEXP j, SEXP x) {
     FRK_TRY(frk_model_set_vfs_csr(model_or_error(mdl), INTEGER(p), INTEGER(j), REAL(x)), (void)0);
@@ -235,6 +249,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"frkb200_model_create", (DL_FUNC)&frkb200_model_create, 8},
     {"frkb200_model_set_blocks", (DL_FUNC)&frkb200_model_set_blocks, 3},
     {"frkb200_model_set_vfs", (DL_FUNC)&frkb200_model_set_vfs, 4},
+    {"frkb200_polygon_lookup", (DL_FUNC)&frkb200_polygon_lookup, 4},
     {"frkb200_model_set", (DL_FUNC)&frkb200_model_set, 3},
     {"frkb200_model_get", (DL_FUNC)&frkb200_model_get, 3},
     {"frkb200_model_set_lanes", (DL_FUNC)&frkb200_model_set_lanes, 2},

@@ -660,6 +660,14 @@ def test_polygon_bau_lookup_and_fit_on_hexagons(dev):
     got = dev.download(out["bau"], len(pts))
     assert np.array_equal(got, ref)
     assert ref[2] == 5 and ref[3] == -1 and ref[4] == -1 and ref[0] >= 0 and ref[1] >= 0
+    # the host-buffer entry point the R shim binds for sp::over(points, polygon BAUs)
+    from frk_b200._lib import call, vp
+    hb = np.empty(len(pts), dtype=np.int32)
+    pf = np.asfortranarray(pts)
+    ptr32, vxc, vyc = np.ascontiguousarray(g["ptr"], dtype=np.int32), np.ascontiguousarray(g["vx"], dtype=np.float64), np.ascontiguousarray(g["vy"], dtype=np.float64)
+    call("frk_polygon_lookup_host", dev.ctx, len(ptr32) - 1, vp(ptr32.ctypes.data), vp(vxc.ctypes.data), vp(vyc.ctypes.data), len(pts),
+         vp(pf.ctypes.data), vp(hb.ctypes.data))
+    assert np.array_equal(hb, ref)
     # full fit on the hexagon BAUs
     isea = _isea3h()
     ob = O.auto_basis(O.sphere(), ll, nres=2, isea3h=isea, isea3h_lo=2)
