@@ -15,8 +15,9 @@ from oracle import frk_oracle as O
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 # sigma2fs / alpha in the heteroscedastic branch are the output of uniroot with tol = eps^0.25 = 1.2e-4 (R/SREfit.R:386): the root
-# itself is only defined to that tolerance, and everything downstream of it inherits a fraction of that slack.
-RTOL_UNIROOT = 1e-7
+# itself is only defined to that tolerance.  Device and oracle run the SAME zeroin iterates on values of J that agree to ~1e-13, so
+# they stop at the same iterate: measured agreement 1e-12 .. 1e-14 (FRK_TEST_REPORT=1), and the 1e-9 bar is applied here as well.
+RTOL_UNIROOT = RTOL
 
 
 def close(got, ref, rtol=RTOL):
@@ -411,7 +412,7 @@ def test_em_fit_and_predict_readme(dev, K_type, hetero):
     np.testing.assert_allclose(Mg.alphahat, Mo.alphahat, rtol=tol)
     close(Mg.get("mu_eta"), Mo.mu_eta, tol)
     close(Mg.get("S_eta"), Mo.S_eta, tol)                     # Sigma_eta itself, not only functionals of it
-    close(Mg.get("Khat"), Mo.Khat, max(tol, 1e-8) if K_type == "block-exponential" else tol)   # tau: optim(reltol = 1e-4) end point
+    close(Mg.get("Khat"), Mo.Khat, max(tol, RTOL) if K_type == "block-exponential" else tol)   # tau: optim(reltol = 1e-4) end point
     for obs_fs in (True, False):
         po = O.predict(Mo, obs_fs=obs_fs)
         pg = F.predict(Mg, obs_fs=obs_fs)
@@ -515,7 +516,7 @@ def test_config4_noaa_spacetime_tensor_basis(dev):
     O.SRE_fit(Mo, n_EM=3, tol=0.0)
     F.SRE_fit(Mg, n_EM=3, tol=0.0)
     np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
-    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(Mg.sigma2fshat, Mo.sigma2fshat, rtol=RTOL, atol=1e-12)
     po = O.predict(Mo, obs_fs=False)
     pg = F.predict(Mg, obs_fs=False)
     close(pg["mu"], po[0], 1e-9)
@@ -532,9 +533,9 @@ def test_config4_noaa_spacetime_tensor_basis(dev):
     O.SRE_fit(Mo2, n_EM=3, tol=0.0)
     F.SRE_fit(Mg2, n_EM=3, tol=0.0)
     np.testing.assert_allclose(Mg2.info_fit["llk"], Mo2.info_fit["llk"], rtol=RTOL)
-    close(np.asarray(Mg2.info_fit["tau"]), np.concatenate(Mo2.info_fit["tau"]), 1e-6)
-    close(Mg2.get("Khat"), Mo2.Khat, 1e-6)
-    close(F.predict(Mg2, obs_fs=False)["var"], O.predict(Mo2, obs_fs=False)[1], 1e-6)
+    close(np.asarray(Mg2.info_fit["tau"]), np.concatenate(Mo2.info_fit["tau"]), RTOL)
+    close(Mg2.get("Khat"), Mo2.Khat, RTOL)
+    close(F.predict(Mg2, obs_fs=False)["var"], O.predict(Mo2, obs_fs=False)[1], RTOL)
 
 
 def test_map_data_to_ST_BAUs(dev):
@@ -582,7 +583,7 @@ def test_fit_options_and_slot_roundtrip(dev):
         O.SRE_fit(Mo, n_EM=3, tol=0.0, lam=lam)
         F.SRE_fit(Mg, n_EM=3, tol=0.0, lambda_=lam)
         np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
-        close(Mg.get("Khat"), Mo.Khat, 1e-7)
+        close(Mg.get("Khat"), Mo.Khat, RTOL)
     # known sigma2fs
     Mo, Mg = _setup_plane(F, K_type="block-exponential", hetero=True)
     O.SRE_fit(Mo, n_EM=3, tol=0.0, known_sigma2fs=0.05)
@@ -609,7 +610,7 @@ def test_fit_options_and_slot_roundtrip(dev):
     Mc.set("sigma2fshat", [s2])
     F.SRE_fit(Mc, n_EM=2, tol=0.0)
     np.testing.assert_allclose(Mc.info_fit["llk"], Ma.info_fit["llk"][2:], rtol=1e-9)
-    np.testing.assert_allclose(Mc.sigma2fshat, Ma.sigma2fshat, rtol=1e-6)
+    np.testing.assert_allclose(Mc.sigma2fshat, Ma.sigma2fshat, rtol=RTOL)
 
 
 def test_degenerate_inputs(dev):
@@ -684,7 +685,7 @@ def test_polygon_bau_lookup_and_fit_on_hexagons(dev):
     O.SRE_fit(Mo, n_EM=3, tol=0.0)
     F.SRE_fit(Mg, n_EM=3, tol=0.0)
     np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
-    close(F.predict(Mg)["var"], O.predict(Mo)[1], 1e-6)
+    close(F.predict(Mg)["var"], O.predict(Mo)[1], RTOL)
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
@@ -705,7 +706,7 @@ def test_speculative_nelder_mead_matches_sequential(dev, world):
     Ka, Kb = Ma.get("Khat"), Mb.get("Khat")
     np.testing.assert_allclose(Kb, Ka, rtol=1e-9, atol=1e-12 * abs(Ka).max())
     Ia, Ib = Ma.get("Khat_inv"), Mb.get("Khat_inv")
-    np.testing.assert_allclose(Ib, Ia, rtol=1e-8, atol=1e-11 * abs(Ia).max())
+    np.testing.assert_allclose(Ib, Ia, rtol=1e-8, atol=RTOL * abs(Ia).max())
 
 
 @pytest.mark.parametrize("lanes,world", [(2, 1), (3, 1), (4, 1), (3, 2)])
@@ -737,7 +738,7 @@ def test_nelder_mead_lanes_match_sequential(dev, lanes, world):
     Ka, Kb = Ma.get("Khat"), Mb.get("Khat")
     np.testing.assert_allclose(Kb, Ka, rtol=1e-9, atol=1e-12 * abs(Ka).max())
     Ia, Ib = Ma.get("Khat_inv"), Mb.get("Khat_inv")
-    np.testing.assert_allclose(Ib, Ia, rtol=1e-8, atol=1e-11 * abs(Ia).max())
+    np.testing.assert_allclose(Ib, Ia, rtol=1e-8, atol=RTOL * abs(Ia).max())
     # a second fit on the same model re-uses the lane contexts and their graph caches
     F.SRE_fit(Ma, n_EM=2, tol=0.0, lanes=1)
     F.SRE_fit(Mb, n_EM=2, tol=0.0, lanes=lanes)
@@ -786,12 +787,12 @@ def test_areal_data_fit_and_predict(dev, K_type):
     O.SRE_fit(Mo, n_EM=5, tol=0.0)
     F.SRE_fit(Mg, n_EM=5, tol=0.0)
     np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
-    close([Mg.sigma2fshat], [Mo.sigma2fshat], 1e-7)
-    close(Mg.alphahat, Mo.alphahat, 1e-7)
+    close([Mg.sigma2fshat], [Mo.sigma2fshat], RTOL)
+    close(Mg.alphahat, Mo.alphahat, RTOL)
     po = O.predict(Mo, obs_fs=True)
     pg = F.predict(Mg, obs_fs=True)
-    close(pg["mu"], po[0], 1e-7)
-    close(pg["var"], po[1], 1e-7)
+    close(pg["mu"], po[0], RTOL)
+    close(pg["var"], po[1], RTOL)
 
 
 def test_areal_data_predict_case2(dev):
@@ -806,8 +807,8 @@ def test_areal_data_predict_case2(dev):
     np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
     po = O.predict(Mo, obs_fs=False)
     pg = F.predict(Mg, obs_fs=False)
-    close(pg["mu"], po[0], 1e-7)
-    close(pg["var"], po[1], 1e-6)
+    close(pg["mu"], po[0], RTOL)
+    close(pg["var"], po[1], RTOL)
     inside = np.asarray(Cm.sum(axis=0)).ravel() > 0
     assert inside.any() and (~inside).any()
     # inside a support the observation pins the AVERAGE of the process, so the fine-scale variance is only partly removed:
@@ -906,9 +907,9 @@ def test_predict_over_polygons(dev, K_type):
         assert np.array_equal(dev.download(mem, nnz), CP.indices)
         np.testing.assert_allclose(dev.download(w, nnz), CP.data, rtol=1e-15)
         po = O.predict_polygons(Mo, CP, obs_fs=obs_fs)
-        close(pg["mu"], po[0], 1e-7)
-        close(pg["var"], po[1], 1e-6)
-        close(pg["sd"], np.sqrt(po[1]), 1e-6)
+        close(pg["mu"], po[0], RTOL)
+        close(pg["var"], po[1], RTOL)
+        close(pg["sd"], np.sqrt(po[1]), RTOL)
     # averaging over a polygon reduces the variance below the mean BAU-level variance (positive correlation aside, never above the max)
     pb = F.predict(Mg, obs_fs=False)
     assert np.all(pg["var"] <= pb["var"].max() * (1 + 1e-12))
@@ -940,9 +941,9 @@ def test_config5_scaled_sphere_matern32(dev, K_type):
     O.SRE_fit(Mo, n_EM=4, tol=0.0)
     F.SRE_fit(Mg, n_EM=4, tol=0.0)
     np.testing.assert_allclose(Mg.info_fit["llk"], Mo.info_fit["llk"], rtol=RTOL)
-    close([Mg.sigma2fshat], [Mo.sigma2fshat], 1e-7)
+    close([Mg.sigma2fshat], [Mo.sigma2fshat], RTOL)
     for obs_fs in (True, False):
         po = O.predict(Mo, obs_fs=obs_fs)
         pg = F.predict(Mg, obs_fs=obs_fs)
-        close(pg["mu"], po[0], 1e-7)
-        close(pg["var"], po[1], 1e-6)
+        close(pg["mu"], po[0], RTOL)
+        close(pg["var"], po[1], RTOL)
