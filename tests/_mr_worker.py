@@ -19,12 +19,16 @@ def problem():
     return xy, z, std
 
 
-def fit(F, dev, K_type, n_EM, distribute_nm=False):
+def fit(F, dev, K_type, n_EM, distribute_nm=False, balance="BAUs"):
     xy, z, std = problem()
+    if balance == "observations":            # make the load uneven over the BAU index: drop most of the points with y > 0.6
+        keep = (xy[:, 1] < 0.6) | (np.arange(len(z)) % 5 == 0)
+        xy, z, std = xy[keep], z[keep], std[keep]
     basis = F.auto_basis(F.plane(), np.array([[0.0, 0.0], [1.0, 1.0]]), regular=1, nres=3)
     BAUs = F.auto_BAUs(F.plane(), cellsize=0.01, xlims=(0, 1), ylims=(0, 1))
     BAUs["fs"] = 1.0
-    mdl = F.SRE("z ~ 1", F.SpatialPointsDataFrame(xy, {"z": z, "std": std}), basis, BAUs, est_error=False, K_type=K_type, dev=dev)
+    mdl = F.SRE("z ~ 1", F.SpatialPointsDataFrame(xy, {"z": z, "std": std}), basis, BAUs, est_error=False, K_type=K_type, dev=dev,
+                balance=balance)
     F.SRE_fit(mdl, n_EM=n_EM, tol=0.0, distribute_nm=distribute_nm)
     out = {"llk": np.asarray(mdl.info_fit["llk"]), "alpha": mdl.alphahat, "sigma2fs": np.array([mdl.sigma2fshat]),
            "mu_eta": mdl.get("mu_eta"), "S_eta_diag": np.diag(mdl.get("S_eta")).copy(), "lo": np.array([mdl.lo]), "hi": np.array([mdl.hi])}
@@ -41,6 +45,7 @@ def main():
     ap.add_argument("--k-type", default="block-exponential")
     ap.add_argument("--n-em", type=int, default=4)
     ap.add_argument("--distribute-nm", action="store_true")
+    ap.add_argument("--balance", default="BAUs")
     ap.add_argument("--out", required=True)
     a = ap.parse_args()
     import torch
@@ -56,7 +61,7 @@ def main():
     dev = F.get_device(index)
     if a.comm == "nccl":
         dev.init_comm()
-    res = fit(F, dev, a.k_type, a.n_em, a.distribute_nm)
+    res = fit(F, dev, a.k_type, a.n_em, a.distribute_nm, a.balance)
     np.savez(f"{a.out}.rank{rank}.npz", **res)
     dist.barrier()
     dist.destroy_process_group()

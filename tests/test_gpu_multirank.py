@@ -73,6 +73,21 @@ def test_two_ranks_sharing_one_gpu_match_single_rank(baseline, tmp_path, K_type)
     _check(ranks, *baseline[K_type])
 
 
+def test_work_balanced_partition_matches_single_rank(dev, tmp_path):
+    """SRE(balance = "observations"): the row partition equalises work (observations weigh 13 BAU rows), so with most observations in
+    the lower part of the domain rank 0 owns FEWER BAU rows; results equal the single-rank run of the same data."""
+    import frk_b200 as F
+    import _mr_worker as W
+    single = W.fit(F, dev, "unstructured", 3, balance="observations")
+    ranks = _launch(tmp_path, 2, ["--comm", "hook", "--same-gpu", "--k-type", "unstructured", "--n-em", "3", "--balance", "observations"])
+    cut = int(ranks[0]["hi"][0])
+    assert cut == int(ranks[1]["lo"][0]) and cut < (int(ranks[1]["hi"][0]) // 2) * 0.9
+    np.testing.assert_allclose(ranks[0]["llk"], single["llk"], rtol=1e-12)
+    for key in ("mu0", "var0", "mu1", "var1"):
+        full = np.concatenate([rk[key] for rk in ranks])
+        np.testing.assert_allclose(full, single[key], rtol=1e-8, atol=1e-8 * np.abs(single[key]).max())
+
+
 def _ngpu():
     import torch
     return torch.cuda.device_count()
