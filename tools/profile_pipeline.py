@@ -16,7 +16,7 @@ def report(tag):
     call("frk_profile_report", dev.ctx, buf, len(buf))
     rep = sorted(json.loads(buf.value.decode()), key=lambda k: -k["ms"])
     print(f"== {tag}: {sum(k['ms'] for k in rep):.2f} ms in {sum(k['launches'] for k in rep)} launches")
-    for k in rep[:14]:
+    for k in rep[:14] + [k for k in rep[14:] if "gram" in k["kernel"] or "quadform" in k["kernel"] or "eval_" in k["kernel"]]:
         print(f"   {k['kernel'][:52]:52s} n={k['launches']:5d} {k['ms']:9.3f} ms")
 for rep_i in range(2):
     call("frk_profile", dev.ctx, 1)
