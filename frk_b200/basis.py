@@ -14,7 +14,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from ._lib import FRKError, call, c_i64, lib, vp
-from .geometry import Manifold, SpatialPointsDataFrame, host_distance
+from .geometry import Manifold, SpatialPointsDataFrame, host_distance, plane, real_line
 from .runtime import Device, get_device
 
 BASIS_TYPES = ("bisquare", "Gaussian", "exp", "Matern32")
@@ -109,6 +109,11 @@ def TensorP(Basis1: Basis, Basis2: Basis) -> TensorP_Basis:
     return TensorP_Basis(Basis1, Basis2)
 
 
+# R/basisfns.R:268-283: seconds per temporal unit (months = 7 days x 52/12, years = 12 of those)
+_TUNIT_SECS = {"secs": 1.0, "mins": 60.0, "hours": 60.0 * 60, "days": 60.0 * 60 * 24, "weeks": 60.0 * 60 * 24 * 7,
+               "months": 60.0 * 60 * 24 * 7 * (52 / 12), "years": 60.0 * 60 * 24 * 7 * (52 / 12) * 12}
+
+
 def _seq_len(a, b, n):
     if n == 1:
         return np.array([a], dtype=np.float64)
@@ -134,7 +139,8 @@ def _colsums_device(dev: Device, basis, coords: np.ndarray) -> np.ndarray:
 
 def auto_basis(manifold: Manifold, data, regular: int = 1, nres: int = 3, prune: float = 0, type: str = "bisquare",
                isea3h_lo: int = 2, scale_aperture: Optional[float] = None, isea3h: Optional[dict] = None,
-               subsamp: Optional[int] = None, dev: Optional[Device] = None) -> Basis:
+               subsamp: Optional[int] = None, dev: Optional[Device] = None, tunit: Optional[str] = None,
+               end_time=None):
     """auto_basis() regular placement, R/basisfns.R:218-585.
 
     The placement uses all data coordinates (the reference subsamples 10,000 points with R's RNG when n > subsamp, which no
@@ -145,10 +151,26 @@ def auto_basis(manifold: Manifold, data, regular: int = 1, nres: int = 3, prune:
     (n x 2) lon/lat}).
     """
     if manifold.kind in ("STplane", "STsphere"):
-        # the reference builds TensorP(auto_basis(<spatial>), 10 Gaussian time functions) from the STIDF's
-        # time stamps (R/basisfns.R:243-289); there is no spacetime container here, so be explicit
-        raise FRKError("auto_basis on a space-time manifold: build TensorP(auto_basis(plane()|sphere(), ...), "
-                       "local_basis(real_line(), ...)) explicitly; local_basis(STplane()|STsphere(), ...) is supported")
+        # R/basisfns.R:243-289: TensorP(auto_basis(plane(), <spatial part>), ten Gaussian functions on the time axis).  The
+        # spatial call is made with manifold = plane() for BOTH space-time manifolds in the reference (:254); followed here.
+        if tunit is None:
+            raise ValueError("Please specify tunit (the temporal unit) if you want to construct a spatio-temporal basis. "
+                             "Note that this should be the same as the BAUs.")
+        if tunit not in _TUNIT_SECS:
+            raise ValueError("tunit should be a one of: secs, mins, hours, days, weeeks, months, years")
+        coords = data.coords if isinstance(data, SpatialPointsDataFrame) else np.asarray(data, dtype=np.float64)
+        if end_time is None:
+            if coords.shape[1] < 3:
+                raise ValueError("space-time auto_basis needs the end times (end_time=, seconds) or a third coordinate column")
+            end_time = coords[:, 2]
+        end_time = np.asarray(end_time, dtype=np.float64)
+        B_spatial = auto_basis(plane(), coords[:, :2], regular=regular, nres=nres, prune=prune, type=type, isea3h_lo=isea3h_lo,
+                               scale_aperture=1.25 if scale_aperture is None else scale_aperture,   # the default is evaluated on the ST manifold (:228)
+                               isea3h=isea3h, subsamp=subsamp, dev=dev)
+        end_loc = float(np.ceil((end_time.max() - end_time.min()) / _TUNIT_SECS[tunit]) + 1.0)      # "+ 1 as a buffer"
+        B_temporal = local_basis(real_line(), _seq_len(0.0, end_loc, 10)[:, None], np.full(10, end_loc / 10.0), "Gaussian",
+                                 regular=1)
+        return TensorP(B_spatial, B_temporal)
     if prune < 0:
         raise ValueError("prune needs to be greater than zero")
     if not regular and manifold.kind == "plane":

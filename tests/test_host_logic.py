@@ -110,7 +110,7 @@ def test_space_time_manifolds():
     assert host_distance(F.STplane(), y, y)[0, 1] == 3.0
     with pytest.raises(ValueError, match="number of columns in loc"):
         F.local_basis(F.STplane(), np.zeros((2, 2)), [1.0, 1.0])
-    with pytest.raises(F.FRKError, match="space-time manifold"):
+    with pytest.raises(ValueError, match="Please specify tunit"):                   # R/basisfns.R:245-247
         F.auto_basis(F.STplane(), y)
     with pytest.raises(ValueError):
         F.STsphere(-1.0)
@@ -160,3 +160,28 @@ def test_partition_rows_weighted_balances_work():
         eq = np.array([w[slice(*partition_rows(len(w), world, k))].sum() for k in range(world)])
         assert loads.max() <= eq.max()                                 # never worse than the equal-count partition
     assert partition_rows_weighted(np.ones(10), 1, 0) == (0, 10)
+
+
+def test_space_time_auto_basis_is_the_tensor_product_of_the_reference():
+    """auto_basis(STplane()|STsphere(), tunit=): R/basisfns.R:243-289 -- spatial auto_basis on plane() (for both manifolds, with
+    scale_aperture 1.25) x ten Gaussian functions at seq(0, end_loc, length.out = 10), scale end_loc / 10, where
+    end_loc = ceiling(time span in tunit) + 1."""
+    rng = np.random.default_rng(5)
+    xy = rng.uniform(0, 10, (400, 2))
+    secs = rng.uniform(0, 30.4 * 86400, 400)
+    for man in (F.STplane(), F.STsphere()):
+        B = F.auto_basis(man, np.column_stack([xy, secs]), regular=1, nres=2, tunit="days")
+        assert isinstance(B, F.TensorP_Basis)
+        ref = O.auto_basis(O.plane(), xy, regular=1, nres=2, scale_aperture=1.25)
+        assert np.array_equal(B.Basis1.loc, ref.loc) and np.array_equal(B.Basis1.scale, ref.scale)
+        assert B.Basis1.manifold.kind == "plane"
+        end_loc = np.ceil((secs.max() - secs.min()) / 86400.0) + 1
+        assert B.Basis2.n == 10 and B.Basis2.type == "Gaussian" and B.Basis2.manifold.kind == "real_line"
+        assert np.array_equal(B.Basis2.loc[:, 0], np.linspace(0, end_loc, 10)) or \
+            np.allclose(B.Basis2.loc[:, 0], np.linspace(0, end_loc, 10), rtol=0, atol=1e-14)
+        assert np.all(B.Basis2.scale == end_loc / 10)
+        assert B.n == ref.n * 10
+    Bw = F.auto_basis(F.STplane(), xy, nres=1, tunit="weeks", end_time=secs)
+    assert Bw.Basis2.loc[-1, 0] == np.ceil((secs.max() - secs.min()) / (7 * 86400.0)) + 1
+    with pytest.raises(ValueError, match="tunit should be"):
+        F.auto_basis(F.STplane(), xy, tunit="fortnights", end_time=secs)
