@@ -1340,6 +1340,317 @@ __global__ void __launch_bounds__(QE_T, 2) quadform_ell_kernel(int nbuckets, con
     }
 }
 
+// The same product for HALF of a 32-row tile (m-tiles 2 half, 2 half + 1): two consumer warps share one densified tile.
+// One warp cannot issue DMMAs faster than every ~32 cycles (measured: profiles/r02x), half the rate of the pipe, so it takes
+// two warps per scheduler multiplying at the same time to fill it.
+// Shared-memory layout of the warp-specialised kernel.  A 64-bit shared load is served one half-warp (g = 0..3 or 4..7, tg = 0..3)
+// per wavefront, so the 16 addresses of a half-warp must fall into 16 different bank pairs:
+//   M[U,U] fragments  MU[4ks + tg][8nt + g]:  row stride = 4 mod 16 (68)  ->  pair 4 tg + g
+//   A fragments       Xt[4ks + tg][8mt + g]:  stride 36                    ->  pair 4 tg + g
+//   epilogue          Xt[8nt + 2tg + e][8mt + g]: 72 tg = 8 tg mod 16 would collide for tg and tg + 2, so rows are stored XOR 4
+//                     in the columns with bit 2 set (Xt[c][row ^ (c & 4)]): pair 8 (tg & 1) + 4 e + (g ^ 4 (tg >> 1)), all different;
+//                     the A fragments see one value of (c & 4) per k-step and stay conflict-free.
+// (profiles/r02z: 610 wavefronts per tile for the consumers' loads against 352 ideal before this layout.)
+constexpr int QW_LDM = UMAX + 4;
+template <int NBLK>
+__device__ __forceinline__ void tile_dmma_half(const double (*Xt)[QD_LDX], const double (*MU)[QW_LDM], int g, int tg, int half, double qs[2],
+                                               double ts[2]) {
+    double acc[2][NBLK][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NBLK; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    const double *xa0 = &Xt[tg][g + 16 * half], *xa1 = &Xt[tg][(g ^ 4) + 16 * half];
+    const double *mb = &MU[tg][g];
+    const double *xe = &Xt[2 * tg][(g ^ (4 * (tg >> 1))) + 16 * half];
+    double s0[2] = {0.0, 0.0}, s1[2] = {0.0, 0.0};
+    // row sums of Y o X for column block nt (this lane: columns 8nt + 2tg + {0,1}); block nt is final after k-step 2nt + 1, so its
+    // share of the epilogue is issued one k-step later, between the DMMAs of the blocks still being accumulated
+    auto fold = [&](int nt) {
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            s0[mt] += acc[mt][nt][0] * xe[(8 * nt) * QD_LDX + 8 * mt];
+            s1[mt] += acc[mt][nt][1] * xe[(8 * nt + 1) * QD_LDX + 8 * mt];
+        }
+    };
+#pragma unroll
+    for (int ks = 0; ks < 2 * NBLK; ks++) {
+        double a[2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) a[mt] = ((ks & 1) ? xa1 : xa0)[(4 * ks) * QD_LDX + 8 * mt];
+#pragma unroll
+        for (int nt = ks / 2; nt < NBLK; nt++) {
+            const double bf = mb[(4 * ks) * QW_LDM + 8 * nt];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf);
+        }
+        if (ks >= 2 && !(ks & 1)) fold(ks / 2 - 1);
+    }
+    fold(NBLK - 1);
+    // the LAST column of the last block is never a real column here (the caller keeps one spare): MU holds mu there, X is zero, so
+    // Y[row][last] = s_row'mu comes out of the same product; lanes with tg == 3 hold it for rows 8 mt + g
+    ts[0] = acc[0][NBLK - 1][1]; ts[1] = acc[1][NBLK - 1][1];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        double v = s0[mt] + s1[mt];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        qs[mt] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Warp-specialised quadratic form (round 2, third generation).  quadform_ell_kernel above makes every warp alternate between
+// a latency-bound phase (load the ELL tile, densify it: ~1000 instructions) and a DMMA-bound one (168 DMMAs at |U| = 48), with
+// two warps per scheduler: the DMMA pipe is busy 40 % of the time.  Here ONE CTA of 12 warps owns an SM: warps 0-7 (two per
+// scheduler, each taking 16 of a tile's 32 rows) only multiply, warps 8-11 only produce -- producer p+8 feeds consumers p and
+// p+4 through a double-buffered densified tile.
+//   producer: the ELL tile (K x 32 values + K x 32 local ids, contiguous in HBM) arrives by ONE bulk-asynchronous copy pair
+//             (cp.async.bulk ... mbarrier::complete_tx::bytes); the lanes pull their row into registers, the next tile's copy is
+//             issued into the same staging area at once (so it flies while this tile is densified and while the producer waits
+//             for a free buffer), then zero + scatter into Xt[buf] and t = s'mu on the way;
+//   consumer: waits for Xt[buf], Y = X MU (block-upper) and the row sums of Y o X on the fp64 tensor cores, releases the buffer.
+// Handshakes are mbarriers in shared memory (full/empty per buffer, one transaction barrier per staging area); the CTA-wide
+// barrier is used at bucket boundaries only (M[U,U] is restaged).  Spin loops are bounded: a lost arrival traps instead of hanging.
+// ---------------------------------------------------------------------------------
+constexpr int QW_PAIRS = 4, QW_T = 3 * QW_PAIRS * 32;
+constexpr int QW_STAGE_BYTES = KMAX * 32 * 9;               // values + ids of the longest tile
+
+struct QuadWsSmem {
+    double MU[UMAX][QW_LDM];
+    double Xt[QW_PAIRS][2][UMAX][QD_LDX];
+    __align__(16) unsigned char stage[QW_PAIRS][QW_STAGE_BYTES];
+    int ucol[UMAX];
+    unsigned long long full_xt[QW_PAIRS][2], empty_xt[QW_PAIRS][2], full_ell[QW_PAIRS];
+};
+static_assert(sizeof(QuadWsSmem) <= 232448, "QuadWsSmem exceeds the 227 KB a CTA may opt into");
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = smem_u32(bar);
+    for (unsigned spin = 0;; spin++) {
+        unsigned ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 22)) __trap();                    // seconds of spinning: a handshake was lost -- fail loudly, never hang the GPU
+    }
+}
+// global -> shared bulk copy (the TMA engine, no tensor map: the tile is one contiguous range), completion counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct QuadWsArgs {
+    int nbuckets, r;
+    const int *bptr, *perm, *ucol_all, *nU_all, *btile, *tile_K, *tile_off;
+    const double *ell_val;
+    const unsigned char *ell_lid;
+    const int *rowptr, *col;
+    const double *val, *M, *mu;
+    double *q, *t;
+};
+
+// Register budgets (setmaxnreg): the kernel is compiled for 168 registers per thread (384 threads, one CTA per SM); the two consumer
+// warpgroups give registers back (the 16-row half tile needs 64 for its accumulators), the producer warpgroup takes them (a whole
+// ELL tile row -- 40 values and 40 ids -- lives in registers between the staging area and the scatter):
+// 8 warps x 32 x 136 + 4 warps x 32 x 232 = 64512 <= 65536.
+constexpr int QW_REGS_CONSUMER = 136, QW_REGS_PRODUCER = 232;
+
+// Both roles walk the same buckets and meet at the same three CTA-wide barriers per bucket (M[U,U] is restaged by all 384 threads);
+// between them a producer and its two consumers only talk through the mbarriers.
+template <bool PRODUCER>
+__device__ __forceinline__ void quadform_ws_role(const QuadWsArgs &A, QuadWsSmem &S) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int pair = wid & (QW_PAIRS - 1), half = (wid >> 2) & 1;
+    const int g = lane >> 2, tg = lane & 3;
+    const int r = A.r;
+    const int *__restrict__ tile_K = A.tile_K;
+    const int *__restrict__ tile_off = A.tile_off;
+    const int *__restrict__ perm = A.perm;
+    const double *__restrict__ M = A.M;
+    const double *__restrict__ mu = A.mu;
+    double *__restrict__ q = A.q;
+    double *__restrict__ t = A.t;
+    unsigned it = 0;                                               // tiles handed from producer to consumers so far (same count on both sides)
+    unsigned ell_it = 0;                                           // producer: bulk copies waited for so far
+    for (int b = blockIdx.x; b < A.nbuckets; b += gridDim.x) {
+        const int r0 = A.bptr[b], r1 = A.bptr[b + 1];
+        if (r1 <= r0) continue;
+        const int nU = A.nU_all[b];
+        if (nU >= UMAX) {
+            for (int pr = r0 + wid; pr < r1; pr += 3 * QW_PAIRS) quad_row_direct(perm[pr], r, A.rowptr, A.col, A.val, M, mu, q, t, lane);
+            continue;
+        }
+        const int nblk = (nU + 8) >> 3, Up = nblk * 8;              // at least one spare column: the last one carries mu (t = S mu)
+        const int t0 = A.btile[b], t1 = A.btile[b + 1];
+        unsigned char *stg = S.stage[pair];
+        bool pending = false;                                      // producer: the copy of its next tile is already in flight
+        // tile metadata of this warp's next 32 tiles, one per lane (a dependent L2 round trip per tile otherwise)
+        int Kl, offl = 0;
+        { const int tt = t0 + pair + QW_PAIRS * lane; Kl = tt < t1 ? tile_K[tt] : 0; if (PRODUCER && tt < t1) offl = tile_off[tt]; }
+        __syncthreads();                                           // the consumers are done with the previous bucket's M[U,U]
+        if (PRODUCER) {                                            // first tile of the bucket: start its copy before M[U,U] is staged
+            const int tl = t0 + pair;
+            const int K = tl < t1 ? __shfl_sync(0xffffffffu, Kl, 0) : -1;
+            if (K > 0) {
+                if (lane == 0) {
+                    const size_t off = (size_t)offl;
+                    mbar_arrive_expect_tx(&S.full_ell[pair], (unsigned)K * 288u);
+                    bulk_g2s(stg, A.ell_val + off, (unsigned)K * 256u, &S.full_ell[pair]);
+                    bulk_g2s(stg + KMAX * 256, A.ell_lid + off, (unsigned)K * 32u, &S.full_ell[pair]);
+                }
+                pending = true;
+            }
+        }
+        if (threadIdx.x < nU) S.ucol[threadIdx.x] = A.ucol_all[(size_t)b * UMAX + threadIdx.x];
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < Up * Up; idx += QW_T) {  // the block-upper part of M[U,U]; zero padding; mu in the last column
+            const int n = idx % Up, k = idx / Up;
+            double v = 0.0;
+            if (k < nU && n < nU && (k >> 3) <= (n >> 3)) {
+                v = __ldg(M + S.ucol[n] + (size_t)r * S.ucol[k]);
+                if ((k >> 3) < (n >> 3)) v *= 2.0;
+            } else if (n == Up - 1 && k < nU && mu) v = __ldg(mu + S.ucol[k]);
+            S.MU[k][n] = v;
+        }
+        __syncthreads();
+        if (PRODUCER) {
+            for (int j = 0, tl = t0 + pair; tl < t1; j++, tl += QW_PAIRS) {
+                if ((j & 31) == 0 && j > 0) {
+                    const int tt = tl + QW_PAIRS * lane;
+                    Kl = tt < t1 ? tile_K[tt] : 0; offl = tt < t1 ? tile_off[tt] : 0;
+                }
+                const int K = __shfl_sync(0xffffffffu, Kl, j & 31);
+                const int offc = __shfl_sync(0xffffffffu, offl, j & 31);
+                if (K <= 0) {                                      // a row longer than KMAX: direct, one row at a time (K == 0: empty rows)
+                    const int p0 = r0 + (tl - t0) * 32, nrows = min(32, r1 - p0);
+                    const int row = lane < nrows ? perm[p0 + lane] : -1;
+                    if (K < 0) for (int rl = 0; rl < nrows; rl++) quad_row_direct(__shfl_sync(0xffffffffu, row, rl), r, A.rowptr, A.col, A.val, M, mu, q, t, lane);
+                    else if (row >= 0) { if (q) q[row] = 0.0; if (t && mu) t[row] = 0.0; }
+                    continue;
+                }
+                if (!pending && lane == 0) {
+                    const size_t off = (size_t)offc;
+                    mbar_arrive_expect_tx(&S.full_ell[pair], (unsigned)K * 288u);
+                    bulk_g2s(stg, A.ell_val + off, (unsigned)K * 256u, &S.full_ell[pair]);
+                    bulk_g2s(stg + KMAX * 256, A.ell_lid + off, (unsigned)K * 32u, &S.full_ell[pair]);
+                }
+                mbar_wait(&S.full_ell[pair], ell_it & 1); ell_it++;
+                double2 v[KMAX / 2];
+                uchar4 l[KMAX / 4];
+                {
+                    const double2 *pv = reinterpret_cast<const double2 *>(stg) + lane;
+                    const uchar4 *pl = reinterpret_cast<const uchar4 *>(stg + KMAX * 256) + lane;
+#pragma unroll
+                    for (int jj = 0; jj < KMAX / 4; jj++)
+                        if (4 * jj < K) { v[2 * jj] = pv[(2 * jj) * 32]; v[2 * jj + 1] = pv[(2 * jj + 1) * 32]; l[jj] = pl[jj * 32]; }
+                }
+                __syncwarp();
+                {   // the staging area is free again: start the copy of this producer's next tile (no global load of this warp is
+                    // outstanding here -- the fence below would wait for it)
+                    const int nt = tl + QW_PAIRS;
+                    int nK, noffi;
+                    if (((j + 1) & 31) != 0) {
+                        nK = __shfl_sync(0xffffffffu, Kl, (j + 1) & 31); noffi = __shfl_sync(0xffffffffu, offl, (j + 1) & 31);
+                        if (nt >= t1) nK = -1;
+                    } else {                                       // the next batch of metadata is not loaded yet (once in 32 tiles)
+                        nK = nt < t1 ? tile_K[nt] : -1; noffi = nK > 0 ? tile_off[nt] : 0;
+                    }
+                    pending = nK > 0;
+                    if (pending && lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic-proxy reads before the async-proxy writes
+                        const size_t noff = (size_t)noffi;
+                        mbar_arrive_expect_tx(&S.full_ell[pair], (unsigned)nK * 288u);
+                        bulk_g2s(stg, A.ell_val + noff, (unsigned)nK * 256u, &S.full_ell[pair]);
+                        bulk_g2s(stg + KMAX * 256, A.ell_lid + noff, (unsigned)nK * 32u, &S.full_ell[pair]);
+                    }
+                }
+                const unsigned buf = it & 1;
+                mbar_wait(&S.empty_xt[pair][buf], ((it >> 1) & 1) ^ 1);
+                double (*Xt)[QD_LDX] = S.Xt[pair][buf];
+                for (int idx = lane; idx < Up * 16; idx += 32) {
+                    const int cc = idx >> 4, rr = (idx & 15) * 2;
+                    *reinterpret_cast<double2 *>(&Xt[cc][rr]) = make_double2(0.0, 0.0);
+                }
+                __syncwarp();
+                double *xs = &Xt[0][0];
+#pragma unroll
+                for (int jj = KMAX / 4 - 1; jj >= 0; jj--)         // last entry first: padding (val 0 at the last real column) gets overwritten
+                    if (4 * jj < K) {                              // Xt[c][row ^ (c & 4)]: see the layout note above tile_dmma_half
+                        xs[l[jj].w * QD_LDX + (lane ^ (l[jj].w & 4))] = v[2 * jj + 1].y;
+                        xs[l[jj].z * QD_LDX + (lane ^ (l[jj].z & 4))] = v[2 * jj + 1].x;
+                        xs[l[jj].y * QD_LDX + (lane ^ (l[jj].y & 4))] = v[2 * jj].y;
+                        xs[l[jj].x * QD_LDX + (lane ^ (l[jj].x & 4))] = v[2 * jj].x;
+                    }
+                mbar_arrive(&S.full_xt[pair][buf]);                // release: this lane's writes are visible to whoever sees the phase flip
+                it++;
+            }
+        } else {
+            for (int j = 0, tl = t0 + pair; tl < t1; j++, tl += QW_PAIRS) {
+                if ((j & 31) == 0 && j > 0) { const int tt = tl + QW_PAIRS * lane; Kl = tt < t1 ? tile_K[tt] : 0; }
+                const int K = __shfl_sync(0xffffffffu, Kl, j & 31);
+                if (K <= 0) continue;
+                const int p0 = r0 + (tl - t0) * 32, nrows = min(32, r1 - p0);
+                const int row = lane < nrows ? perm[p0 + lane] : -1;
+                const unsigned buf = it & 1;
+                mbar_wait(&S.full_xt[pair][buf], (it >> 1) & 1);
+                const double (*Xt)[QD_LDX] = S.Xt[pair][buf];
+                double qs[2], ts[2];
+                switch (nblk) {
+                    case 1: tile_dmma_half<1>(Xt, S.MU, g, tg, half, qs, ts); break;
+                    case 2: tile_dmma_half<2>(Xt, S.MU, g, tg, half, qs, ts); break;
+                    case 3: tile_dmma_half<3>(Xt, S.MU, g, tg, half, qs, ts); break;
+                    case 4: tile_dmma_half<4>(Xt, S.MU, g, tg, half, qs, ts); break;
+                    case 5: tile_dmma_half<5>(Xt, S.MU, g, tg, half, qs, ts); break;
+                    case 6: tile_dmma_half<6>(Xt, S.MU, g, tg, half, qs, ts); break;
+                    case 7: tile_dmma_half<7>(Xt, S.MU, g, tg, half, qs, ts); break;
+                    default: tile_dmma_half<8>(Xt, S.MU, g, tg, half, qs, ts); break;
+                }
+                mbar_arrive(&S.empty_xt[pair][buf]);               // qs depends on every shared-memory read of this lane
+                it++;
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    const int rr = __shfl_sync(0xffffffffu, row, 16 * half + 8 * mt + g);
+                    if (rr >= 0) {
+                        if (q && tg == mt) q[rr] = qs[mt];
+                        if (t && mu && tg == 3) t[rr] = ts[mt];
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(QW_T, 1) quadform_ws_kernel(const __grid_constant__ QuadWsArgs A) {
+    extern __shared__ __align__(16) unsigned char qsm_raw[];
+    QuadWsSmem &S = *reinterpret_cast<QuadWsSmem *>(qsm_raw);
+    if (threadIdx.x < QW_PAIRS) {
+        mbar_init(&S.full_xt[threadIdx.x][0], 32); mbar_init(&S.full_xt[threadIdx.x][1], 32);
+        mbar_init(&S.empty_xt[threadIdx.x][0], 64); mbar_init(&S.empty_xt[threadIdx.x][1], 64);
+        mbar_init(&S.full_ell[threadIdx.x], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x >= 2 * QW_PAIRS * 32) {                        // warpgroup 2: producers
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(QW_REGS_PRODUCER));
+        quadform_ws_role<true>(A, S);
+    } else {                                                       // warpgroups 0, 1: consumers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(QW_REGS_CONSUMER));
+        quadform_ws_role<false>(A, S);
+    }
+}
+
 int frk_rowbuckets_is_dense(const frk_rowbuckets *bk) { return bk && bk->dense; }
 
 // dense / implicit matrices only: the quadratic forms against M = L^-T L^-1 through the triangular factor (model.cu)
@@ -1356,6 +1667,22 @@ extern "C" int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const 
     FRK_REQUIRE(bk->n == n && bk->ncols == r, "frk_quadform_spmv_bucketed: the row buckets belong to a %lld x %d matrix", (long long)bk->n, bk->ncols);
     if (n == 0) return 0;
     if (bk->dense) return quadform_dense(ctx, bk, n, r, d_val, d_M, d_mu, d_q, d_t);
+    // warp-specialised kernel (one CTA per SM) when there is a matrix M and the buckets are long enough to keep its pipeline
+    // busy; FRK_QUAD_MODE = ws | v2 forces one of the two (A/B timing, tests)
+    const char *mode = getenv("FRK_QUAD_MODE");
+    const bool force_ws = mode && !strcmp(mode, "ws"), force_v2 = mode && !strcmp(mode, "v2");
+    if (d_M && bk->T > 0 && bk->max_nU < UMAX && !force_v2 && (force_ws || (int64_t)bk->T >= 8 * (int64_t)r)) {
+        static bool attr_ws = false;
+        if (!attr_ws) {
+            FRK_CHECK_CUDA(cudaFuncSetAttribute(quadform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QuadWsSmem)));
+            attr_ws = true;
+        }
+        const unsigned grid = (unsigned)std::min<int64_t>(r, (int64_t)ctx->sm_count);
+        QuadWsArgs A{r, r, bk->bptr, bk->perm, bk->ucol, bk->nU, bk->btile, bk->tile_K, bk->tile_off, bk->ell_val, bk->ell_lid,
+                     d_rowptr, d_col, d_val, d_M, d_mu, d_q, d_t};
+        FRK_LAUNCH(ctx, quadform_ws_kernel, grid, QW_T, sizeof(QuadWsSmem), A);
+        return 0;
+    }
     static bool attr = false;
     if (!attr) {
         FRK_CHECK_CUDA(cudaFuncSetAttribute(quadform_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QuadDmmaSmem)));
