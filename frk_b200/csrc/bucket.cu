@@ -1467,6 +1467,43 @@ struct QuadWsArgs {
 // 8 warps x 32 x 136 + 4 warps x 32 x 232 = 64512 <= 65536.
 constexpr int QW_REGS_CONSUMER = 136, QW_REGS_PRODUCER = 232;
 
+// Consumer side of one bucket: this warp's half (16 rows) of every tile of its producer.  Kl = tile_K of the warp's next 32 tiles
+// (one per lane), it = running count of tiles taken over (buffer index and mbarrier phase).
+template <int NBLK>
+__device__ __forceinline__ void quadform_ws_consume(const QuadWsArgs &A, QuadWsSmem &S, int t0, int t1, int r0, int r1, int Kl, unsigned &it) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int pair = wid & (QW_PAIRS - 1), half = (wid >> 2) & 1;
+    const int g = lane >> 2, tg = lane & 3;
+    const int *__restrict__ perm = A.perm;
+    double *__restrict__ q = A.q;
+    double *__restrict__ t = (A.t && A.mu) ? A.t : nullptr;
+    unsigned live = __ballot_sync(0xffffffffu, Kl > 0);            // tiles that come through the pipeline (K <= 0: the producer's business)
+    // the two rows this lane reports per tile: 16 half + 8 mt + g (q by the lane with tg == mt, t by tg == 3); their ids are
+    // fetched one tile ahead so that the L2 round trip never sits in front of a tile's products
+    int nrow0 = -1, nrow1 = -1;
+    { const int p0 = r0 + pair * 32 + 16 * half + g; if (t0 + pair < t1) { nrow0 = p0 < r1 ? perm[p0] : -1; nrow1 = p0 + 8 < r1 ? perm[p0 + 8] : -1; } }
+    for (int j = 0, tl = t0 + pair; tl < t1; j++, tl += QW_PAIRS) {
+        if ((j & 31) == 0 && j > 0) {
+            const int tt = tl + QW_PAIRS * lane;
+            live = __ballot_sync(0xffffffffu, tt < t1 && A.tile_K[tt] > 0);
+        }
+        const int row0 = nrow0, row1 = nrow1;
+        if (tl + QW_PAIRS < t1) {
+            const int p1 = r0 + (tl + QW_PAIRS - t0) * 32 + 16 * half + g;
+            nrow0 = p1 < r1 ? perm[p1] : -1; nrow1 = p1 + 8 < r1 ? perm[p1 + 8] : -1;
+        }
+        if (!((live >> (j & 31)) & 1u)) continue;
+        const unsigned buf = it & 1;
+        mbar_wait(&S.full_xt[pair][buf], (it >> 1) & 1);
+        double qs[2], ts[2];
+        tile_dmma_half<NBLK>(S.Xt[pair][buf], S.MU, g, tg, half, qs, ts);
+        mbar_arrive(&S.empty_xt[pair][buf]);                       // qs depends on every shared-memory read of this lane
+        it++;
+        if (row0 >= 0) { if (q && tg == 0) q[row0] = qs[0]; if (t && tg == 3) t[row0] = ts[0]; }
+        if (row1 >= 0) { if (q && tg == 1) q[row1] = qs[1]; if (t && tg == 3) t[row1] = ts[1]; }
+    }
+}
+
 // Both roles walk the same buckets and meet at the same three CTA-wide barriers per bucket (M[U,U] is restaged by all 384 threads);
 // between them a producer and its two consumers only talk through the mbarriers.
 template <bool PRODUCER>
@@ -1597,36 +1634,15 @@ __device__ __forceinline__ void quadform_ws_role(const QuadWsArgs &A, QuadWsSmem
                 it++;
             }
         } else {
-            for (int j = 0, tl = t0 + pair; tl < t1; j++, tl += QW_PAIRS) {
-                if ((j & 31) == 0 && j > 0) { const int tt = tl + QW_PAIRS * lane; Kl = tt < t1 ? tile_K[tt] : 0; }
-                const int K = __shfl_sync(0xffffffffu, Kl, j & 31);
-                if (K <= 0) continue;
-                const int p0 = r0 + (tl - t0) * 32, nrows = min(32, r1 - p0);
-                const int row = lane < nrows ? perm[p0 + lane] : -1;
-                const unsigned buf = it & 1;
-                mbar_wait(&S.full_xt[pair][buf], (it >> 1) & 1);
-                const double (*Xt)[QD_LDX] = S.Xt[pair][buf];
-                double qs[2], ts[2];
-                switch (nblk) {
-                    case 1: tile_dmma_half<1>(Xt, S.MU, g, tg, half, qs, ts); break;
-                    case 2: tile_dmma_half<2>(Xt, S.MU, g, tg, half, qs, ts); break;
-                    case 3: tile_dmma_half<3>(Xt, S.MU, g, tg, half, qs, ts); break;
-                    case 4: tile_dmma_half<4>(Xt, S.MU, g, tg, half, qs, ts); break;
-                    case 5: tile_dmma_half<5>(Xt, S.MU, g, tg, half, qs, ts); break;
-                    case 6: tile_dmma_half<6>(Xt, S.MU, g, tg, half, qs, ts); break;
-                    case 7: tile_dmma_half<7>(Xt, S.MU, g, tg, half, qs, ts); break;
-                    default: tile_dmma_half<8>(Xt, S.MU, g, tg, half, qs, ts); break;
-                }
-                mbar_arrive(&S.empty_xt[pair][buf]);               // qs depends on every shared-memory read of this lane
-                it++;
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++) {
-                    const int rr = __shfl_sync(0xffffffffu, row, 16 * half + 8 * mt + g);
-                    if (rr >= 0) {
-                        if (q && tg == mt) q[rr] = qs[mt];
-                        if (t && mu && tg == 3) t[rr] = ts[mt];
-                    }
-                }
+            switch (nblk) {                                        // the block count is a property of the bucket: one specialised tile loop each
+                case 1: quadform_ws_consume<1>(A, S, t0, t1, r0, r1, Kl, it); break;
+                case 2: quadform_ws_consume<2>(A, S, t0, t1, r0, r1, Kl, it); break;
+                case 3: quadform_ws_consume<3>(A, S, t0, t1, r0, r1, Kl, it); break;
+                case 4: quadform_ws_consume<4>(A, S, t0, t1, r0, r1, Kl, it); break;
+                case 5: quadform_ws_consume<5>(A, S, t0, t1, r0, r1, Kl, it); break;
+                case 6: quadform_ws_consume<6>(A, S, t0, t1, r0, r1, Kl, it); break;
+                case 7: quadform_ws_consume<7>(A, S, t0, t1, r0, r1, Kl, it); break;
+                default: quadform_ws_consume<8>(A, S, t0, t1, r0, r1, Kl, it); break;
             }
         }
     }
