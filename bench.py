@@ -341,7 +341,7 @@ def run_b200(args):
             if k["flops"] > 0:
                 ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
                 ent.update(bound="fp64", achieved=ach, peak=fp64_peak, unit="TFLOP/s", frac=ach / fp64_peak)
-            elif "gram_bucket_kernel" in k["kernel"] or "gram_ell" in k["kernel"] or "quadform_ell_kernel" in k["kernel"]:
+            elif "gram_bucket_kernel" in k["kernel"] or "gram_ell" in k["kernel"] or "quadform_ell_kernel" in k["kernel"] or "quadform_ws_kernel" in k["kernel"]:
                 # both ceilings: HBM (val 8 B + local id 1 B per non-zero, ...) and fp64 (the operation's own flops: 2 * sum_i nnz_i^2
                 # for the quadratic form, sum_i nnz_i (nnz_i + 1) for the Gram; lower bound nnz^2 / rows); the binding one is reported
                 if "gram" in k["kernel"]:
