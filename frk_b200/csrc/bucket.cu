@@ -1687,7 +1687,8 @@ extern "C" int frk_quadform_spmv_bucketed(frk_ctx *ctx, int64_t n, int r, const 
     // busy; FRK_QUAD_MODE = ws | v2 forces one of the two (A/B timing, tests)
     const char *mode = getenv("FRK_QUAD_MODE");
     const bool force_ws = mode && !strcmp(mode, "ws"), force_v2 = mode && !strcmp(mode, "v2");
-    static const int ws_min = getenv("FRK_QUAD_WS_MIN") ? atoi(getenv("FRK_QUAD_WS_MIN")) : 24;   // tiles per column (A/B timing)
+    static const int ws_env = getenv("FRK_QUAD_WS_MIN") ? atoi(getenv("FRK_QUAD_WS_MIN")) : 0;    // tiles per column (A/B timing)
+    const int ws_min = ws_env > 0 ? ws_env : ctx->quad_ws_min;
     if (d_M && bk->T > 0 && bk->max_nU < UMAX && !force_v2 && (force_ws || (int64_t)bk->T >= (int64_t)ws_min * r)) {
         static bool attr_ws = false;
         if (!attr_ws) {

@@ -22,6 +22,8 @@ struct frk_ctx {
     cudaStream_t stream3 = nullptr;      // second side stream: the rest of the trailing SYRK overlaps the whole next panel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_panel = nullptr, ev_next = nullptr, ev_rest[2] = {nullptr, nullptr};
     int sm_count = 148;
+    int quad_ws_min = 8;                 // tiles per column from which the quadratic form takes the warp-specialised kernel (bucket.cu); a context
+                                         // whose work runs BESIDE latency-bound chains sets 24: that kernel takes every SM's shared memory
     int64_t launches = 0;
     // growable scratch (device) + small pinned host staging
     void *scratch = nullptr;

@@ -1161,7 +1161,10 @@ int mstep(frk_model *M, int K_type, int nlambda, const double *lambda, const int
         if (M->linv_valid && frk_rowbuckets_is_dense(M->bk))        // dense rows: q_j = |L^-1 s_j|^2, half the flops of S_eta s_j
             RC(frk_quadform_dense_factor(M->aux, M->m, r, M->val, M->bk, M->Linv, M->mu_eta, M->q, M->t));
         else
+        {   // (runs beside the Nelder-Mead lanes: measured 1 % per EM iteration in favour of the kernel with the smaller footprint at C3)
+            M->aux->quad_ws_min = 24;
             RC(frk_quadform_spmv_bucketed(M->aux, M->m, r, M->rowptr, M->col, M->val, M->bk, M->S_eta, M->mu_eta, M->q, M->t));
+        }
         FRK_CHECK_CUDA(cudaEventRecord(M->ev_aux1, M->aux->stream));
         ctx->launches += M->aux->launches;
         M->aux->launches = 0;

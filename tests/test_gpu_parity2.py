@@ -494,3 +494,44 @@ def test_quadform_warp_specialised_kernel_matches_v2_and_scipy(dev, n, nres, mon
         np.testing.assert_allclose(out["ws", with_mu][1], out["v2", with_mu][1], rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(out["ws", True][0], q_ref, rtol=1e-11)
     np.testing.assert_allclose(out["ws", True][1], t_ref, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_quadform_warp_specialised_kernel_long_rows_and_empty_rows(dev, monkeypatch):
+    """The side paths of the warp-specialised quadratic form: tiles holding a row of more than 40 non-zeros (evaluated directly by the
+    producer warp while the consumers skip the tile), rows without any non-zero, ragged last tiles, buckets of every width up to 60
+    columns (block counts 1..8 with the spare column) -- on a synthetic matrix, against SciPy and the second-generation kernel."""
+    import scipy.sparse as sp
+    import frk_b200 as F
+    from frk_b200._lib import call
+    from frk_b200.basis import DeviceCSR
+    from test_gpu_parity import _dense_case
+    rng = np.random.default_rng(77)
+    n, r = 30011, 60
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        u = rng.random()
+        hi = int(rng.integers(1, r + 1))                       # the row lives on columns < hi: the bucket's union is at most hi wide
+        k = 0 if u < 0.01 else (min(hi, int(rng.integers(41, 56))) if u < 0.06 else min(hi, int(rng.integers(1, 31))))
+        c = np.sort(rng.choice(hi, size=k, replace=False))
+        rows += [i] * k; cols += c.tolist(); vals += rng.standard_normal(k).tolist()
+    So = sp.csr_matrix((vals, (rows, cols)), shape=(n, r))
+    So.sort_indices()
+    Sg = DeviceCSR(n, r, dev.upload(So.indptr.astype(np.int32)), dev.upload(So.indices.astype(np.int32)), dev.upload(So.data), So.nnz)
+    Mm = _dense_case(r, 5)
+    mu = rng.standard_normal(r)
+    q_ref = np.asarray(So.multiply(So @ Mm).sum(axis=1)).ravel()
+    t_ref = So @ mu
+    dM, dmu = dev.upload(Mm), dev.upload(mu)
+    bk = Sg.buckets(dev)
+    out = {}
+    for mode in ("v2", "ws"):
+        monkeypatch.setenv("FRK_QUAD_MODE", mode)
+        q, t = dev.zeros(n) + 7.0, dev.zeros(n) + 7.0          # (every entry must be written, empty rows included)
+        call("frk_quadform_spmv_bucketed", dev.ctx, n, r, dev.ptr(Sg.rowptr), dev.ptr(Sg.col), dev.ptr(Sg.val), bk, dev.ptr(dM),
+             dev.ptr(dmu), dev.ptr(q), dev.ptr(t))
+        out[mode] = (dev.download(q), dev.download(t))
+    scale = abs(q_ref).max()
+    np.testing.assert_allclose(out["ws"][0], q_ref, rtol=1e-11, atol=1e-13 * scale)
+    np.testing.assert_allclose(out["ws"][1], t_ref, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["ws"][0], out["v2"][0], rtol=1e-13, atol=1e-14 * scale)
