@@ -101,6 +101,7 @@ int frk_ctx_create_lane(const frk_ctx *parent, bool high_priority, frk_ctx **out
 // enqueue-only halves of frk_potrf / frk_dot (dense.cu): results are staged in the context's pinned buffer and read after a stream
 // synchronisation, so that one host thread can keep several contexts busy at once
 int frk_potrf_async(frk_ctx *ctx, int r, double *d_A);
+int frk_block_scatter_scaled(frk_ctx *ctx, int r, double *d_A, int ni, const int *d_idx, const double *d_in, double alpha);   // dense.cu
 int frk_potrf_finish(frk_ctx *ctx, double *h_logdet);
 int frk_potrf_status(frk_ctx *ctx, double *h_logdet);   // non-failing: order of the first bad leading minor, 0 if positive definite
 int frk_dot_async(frk_ctx *ctx, int64_t n, const double *d_A, const double *d_B);

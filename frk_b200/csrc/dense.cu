@@ -1461,10 +1461,10 @@ __global__ void block_gather_kernel(int r, const double *__restrict__ A, const d
     }
 }
 
-__global__ void block_scatter_kernel(int r, double *__restrict__ A, int ni, const int *__restrict__ idx, const double *__restrict__ in) {
+__global__ void block_scatter_kernel(int r, double *__restrict__ A, int ni, const int *__restrict__ idx, const double *__restrict__ in, double alpha) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)ni * ni; t += (int64_t)gridDim.x * blockDim.x) {
         int i = (int)(t % ni), j = (int)(t / ni);
-        A[idx[i] + (size_t)idx[j] * r] = in[t];
+        A[idx[i] + (size_t)idx[j] * r] = alpha * in[t];          // (alpha = 1: exact copy)
     }
 }
 
@@ -1486,7 +1486,16 @@ extern "C" int frk_block_gather_outer(frk_ctx *ctx, int r, const double *d_A, co
 extern "C" int frk_block_scatter(frk_ctx *ctx, int r, double *d_A, int ni, const int *d_idx, const double *d_in) {
     FRK_REQUIRE(ctx && d_A && d_idx && d_in, "frk_block_scatter: NULL argument");
     if (ni == 0) return 0;
-    FRK_LAUNCH(ctx, block_scatter_kernel, ctx->sm_count * 8, 256, 0, r, d_A, ni, d_idx, d_in);
+    FRK_LAUNCH(ctx, block_scatter_kernel, ctx->sm_count * 8, 256, 0, r, d_A, ni, d_idx, d_in, 1.0);
+    return 0;
+}
+
+// A[idx, idx] = alpha * in: the scaled block is written straight into place and `in` stays as it is (model.cu keeps the unscaled
+// exp(-D/tau)^-1 of the last K update for the next M-step)
+int frk_block_scatter_scaled(frk_ctx *ctx, int r, double *d_A, int ni, const int *d_idx, const double *d_in, double alpha) {
+    FRK_REQUIRE(ctx && d_A && d_idx && d_in, "frk_block_scatter_scaled: NULL argument");
+    if (ni == 0) return 0;
+    FRK_LAUNCH(ctx, block_scatter_kernel, ctx->sm_count * 8, 256, 0, r, d_A, ni, d_idx, d_in, alpha);
     return 0;
 }
 

@@ -32,6 +32,8 @@ struct Block {                    // one resolution of the block-exponential K
     int *d_ix = nullptr;
     double *D = nullptr, *eta2 = nullptr, *Ki = nullptr, *Kinv = nullptr, *work = nullptr, *KinvBest = nullptr;
     double D01 = 0.0;
+    // what KinvBest holds: exp(-D/kinv_tau0)^-1 (UNSCALED) and log|exp(-D/kinv_tau0)|; kinv_tau0 <= 0: nothing usable
+    double kinv_tau0 = -1.0, kinv_ld = 0.0;
     // tensor-product basis: n_i = ns * nt, K_i = kronecker(exp(-Dt/tau_t), exp(-D/tau_s)) (D = spatial distances, ns x ns)
     int ns = 0, nt = 0;
     double *Ks = nullptr, *Qs = nullptr, *ws = nullptr, *QsBest = nullptr;     // ns x ns
@@ -74,7 +76,7 @@ struct frk_model {
     // Prefetch: K_i(tau)^-1 and log|K_i(tau)| depend on tau only.  The first two points the NEXT M-step's Nelder-Mead will ask for
     // (its start value and start + step) are known as soon as this M-step has assembled K, so their factorisations are enqueued on the
     // lanes right away and run beside the next E-step's factorisation of Q instead of after it.  pre[j][c]: (active, tau) of lane c of block j.
-    struct PreSlot { bool on = false; double tau = 0.0; };
+    struct PreSlot { bool on = false; double tau = 0.0; bool reused = false; double tau0 = 0.0, ld = 0.0; };
     std::vector<std::array<PreSlot, 8>> pre;
     bool prefetch = true;
     // multi-rank reduction hook
@@ -622,6 +624,8 @@ struct NMSlot {                    // one concurrent evaluation: context + buffe
     frk_ctx *ctx = nullptr;
     double *Ki = nullptr, *Kinv = nullptr, *work = nullptr;
     double pt = 0.0, ld = 0.0;
+    double tau0 = 0.0;             // the tau its Kinv was actually factorised for (== pt unless the inverse was reused, see f_tau_reusable)
+    bool reused = false;           // Kinv is a copy of the block's saved inverse: no factorisation status to read, ld is known
     bool valid = false, used = false;
     int k = -1;
 };
@@ -653,7 +657,26 @@ int f_tau_factor_enqueue(const Block &B, NMSlot &s, double tau) {
 // ... and tr(K_i^-1 eta2_i), which needs the current E-step
 int f_tau_enqueue(const Block &B, NMSlot &s, double tau) {
     RC(f_tau_factor_enqueue(B, s, tau));
+    s.tau0 = tau; s.reused = false;
     return frk_dot_async(s.ctx, (int64_t)B.ni * B.ni, s.Kinv, B.eta2);
+}
+
+// Reuse of the last K update's inverse.  optim() starts every M-step from tau' = -D01 / log(K_i[1,2] / K_i[1,1]) read back from the K
+// the previous M-step assembled with its winner tau (R/SREfit.R:596-614): tau' is tau up to the rounding of exp, the division and log,
+// a few tens of ulps.  exp(-D/tau')^-1 and its log-determinant then agree with the saved exp(-D/tau)^-1 to ~1e-14 relative -- two
+// orders below the rounding error of a factorisation of these matrices (condition 1e3 - 1e6) -- so the saved inverse is copied
+// instead of factorising again: one of the two r_i^3 evaluations per resolution and M-step at convergence (25 of ~85 GFLOP per EM
+// iteration at C3).  The tolerance is relative to the tau that WAS factorised (kinv_tau0), so drift cannot accumulate over the
+// iterations.  FRK_NO_KINV_REUSE=1 switches it off (A/B timing; the parity tests run both ways).
+static bool f_tau_reusable(const Block &B, double tau) {
+    static const bool off = getenv("FRK_NO_KINV_REUSE") != nullptr;
+    return !off && B.ns == 0 && B.kinv_tau0 > 0.0 && std::fabs(tau - B.kinv_tau0) <= 1e-13 * B.kinv_tau0;
+}
+// the slot's Kinv := the saved inverse (the caller has ordered this stream after the last write of KinvBest)
+static int f_tau_reuse_enqueue(const Block &B, NMSlot &s) {
+    FRK_CHECK_CUDA(cudaMemcpyAsync(s.Kinv, B.KinvBest, (size_t)B.ni * B.ni * sizeof(double), cudaMemcpyDeviceToDevice, s.ctx->stream));
+    s.tau0 = B.kinv_tau0; s.ld = B.kinv_ld; s.reused = true;
+    return 0;
 }
 
 constexpr int LCAP = 8;            // slot (block j, lane c) -> lane context j*LCAP + c - 1: stable, so graph caches hit
@@ -726,9 +749,19 @@ int prefetch_f_tau(frk_model *M) {
             if (!(tau > 1e-10)) continue;
             NMSlot s;
             RC(nm_slot_setup(M, j, c, B, false, s));
-            RC(f_tau_factor_enqueue(B, s, tau));
-            M->pre[j][c].on = true;
-            M->pre[j][c].tau = tau;
+            Model_PreSlot &pf = M->pre[j][c];
+            if (f_tau_reusable(B, tau)) {                           // the start value: the saved inverse serves (see f_tau_reusable)
+                if (!M->ev_lane) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_lane, cudaEventDisableTiming));
+                FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));       // KinvBest is final once this stream has assembled K
+                FRK_CHECK_CUDA(cudaStreamWaitEvent(s.ctx->stream, M->ev_lane, 0));
+                RC(f_tau_reuse_enqueue(B, s));
+                pf.reused = true; pf.tau0 = s.tau0; pf.ld = s.ld;
+            } else {
+                RC(f_tau_factor_enqueue(B, s, tau));
+                pf.reused = false; pf.tau0 = tau;
+            }
+            pf.on = true;
+            pf.tau = tau;
         }
     }
     return 0;
@@ -767,6 +800,7 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
                 FRK_CHECK_CUDA(cudaMemcpyAsync(Sp->B->KinvBest, s.Kinv, nn2 * sizeof(double), cudaMemcpyDeviceToDevice,
                                                Sp->slot[0].ctx->stream));
                 Sp->bestTau = x[0]; Sp->bestLogdet = s.ld;
+                Sp->B->kinv_tau0 = s.tau0; Sp->B->kinv_ld = s.ld;     // (host-side tags of KinvBest, updated in enqueue order like the buffer)
                 break;
             }
             return 0;
@@ -812,8 +846,13 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
             Model_PreSlot &pf = M->pre[j][c];
             if (pf.on && pf.tau == tau && !one_stream && !M->spec_emulate) {
                 // this slot's buffers already hold K_i(tau)^-1 (or it is on its way): enqueued before the E-step.  Only the trace is left.
+                s.reused = pf.reused; s.tau0 = pf.tau0;
+                if (pf.reused) s.ld = pf.ld;
                 RC(frk_dot_async(s.ctx, (int64_t)S.B->ni * S.B->ni, s.Kinv, S.B->eta2));
                 M->nm_prefetch_hits += 1;
+            } else if (f_tau_reusable(*S.B, tau)) {                  // (this stream is ordered after every write of KinvBest: ev_copy / ev_lane)
+                RC(f_tau_reuse_enqueue(*S.B, s));
+                RC(frk_dot_async(s.ctx, (int64_t)S.B->ni * S.B->ni, s.Kinv, S.B->eta2));
             } else {
                 RC(f_tau_enqueue(*S.B, s, tau));
             }
@@ -843,7 +882,8 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
             s.used = false;
             double logdetKi;
             // a candidate that cannot be factorised is only a failed guess unless Nelder-Mead asks for it (SpecNM::check_requested)
-            const int bad = frk_potrf_status(s.ctx, &logdetKi);
+            const int bad = s.reused ? 0 : frk_potrf_status(s.ctx, &logdetKi);
+            if (s.reused) logdetKi = s.ld;
             const double t = s.ctx->h_pinned[FRK_PINNED_DOT];
             const double f = bad ? std::numeric_limits<double>::quiet_NaN() : -(0.5 * (-logdetKi) - S.omega / 2.0 * t);
             S.fl[s.k] = f; s.ld = logdetKi; s.valid = std::isfinite(f);
@@ -978,12 +1018,14 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
         }
         if (shared) {                                                // from the owner to everybody
             RC(bcast_dev(M, B.KinvBest, (int64_t)nn, own, own == nm_rank(M)));
-            RC(reduce_host(M, &S.bestLogdet, 1, 0));
+            const bool mine = own == nm_rank(M);
+            double tags[3] = {S.bestLogdet, mine ? B.kinv_tau0 : 0.0, mine ? B.kinv_ld : 0.0};
+            RC(reduce_host(M, tags, 3, 0));
+            S.bestLogdet = tags[0]; B.kinv_tau0 = tags[1]; B.kinv_ld = tags[2];
         }
         RC(frk_exp_kernel(ctx, (int64_t)nn, B.D, tau, 1.0 / omega, B.Ki));
         RC(frk_block_scatter(ctx, r, Knew, ni, B.d_ix, B.Ki));
-        RC(frk_scale(ctx, (int64_t)nn, omega, B.KinvBest));                       // K_i^-1 = omega_i exp(-D_i/tau_i)^-1
-        RC(frk_block_scatter(ctx, r, Kinvnew, ni, B.d_ix, B.KinvBest));
+        RC(frk_block_scatter_scaled(ctx, r, Kinvnew, ni, B.d_ix, B.KinvBest, omega));   // K_i^-1 = omega_i exp(-D_i/tau_i)^-1 (KinvBest stays unscaled)
         logdetK += S.bestLogdet - ni * std::log(omega);
     }
     return 0;
