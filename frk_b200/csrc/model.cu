@@ -34,6 +34,12 @@ struct Block {                    // one resolution of the block-exponential K
     double D01 = 0.0;
     // what KinvBest holds: exp(-D/kinv_tau0)^-1 (UNSCALED) and log|exp(-D/kinv_tau0)|; kinv_tau0 <= 0: nothing usable
     double kinv_tau0 = -1.0, kinv_ld = 0.0;
+    // memo of recent evaluations: exp(-D/tau0)^-1 and log|exp(-D/tau0)| are functions of tau alone, and the Nelder-Mead runs of
+    // consecutive M-steps ask for the same points again once a resolution's tau has settled (f_tau_lookup); LRU, buffers allocated
+    // with the block
+    struct Memo { double tau0 = -1.0, ld = 0.0; double *buf = nullptr; unsigned long long stamp = 0; };
+    std::vector<Memo> memo;
+    unsigned long long memo_clock = 0;
     // tensor-product basis: n_i = ns * nt, K_i = kronecker(exp(-Dt/tau_t), exp(-D/tau_s)) (D = spatial distances, ns x ns)
     int ns = 0, nt = 0;
     double *Ks = nullptr, *Qs = nullptr, *ws = nullptr, *QsBest = nullptr;     // ns x ns
@@ -624,7 +630,7 @@ struct NMSlot {                    // one concurrent evaluation: context + buffe
     frk_ctx *ctx = nullptr;
     double *Ki = nullptr, *Kinv = nullptr, *work = nullptr;
     double pt = 0.0, ld = 0.0;
-    double tau0 = 0.0;             // the tau its Kinv was actually factorised for (== pt unless the inverse was reused, see f_tau_reusable)
+    double tau0 = 0.0;             // the tau its Kinv was actually factorised for (== pt unless the inverse was reused, see f_tau_lookup)
     bool reused = false;           // Kinv is a copy of the block's saved inverse: no factorisation status to read, ld is known
     bool valid = false, used = false;
     int k = -1;
@@ -661,21 +667,46 @@ int f_tau_enqueue(const Block &B, NMSlot &s, double tau) {
     return frk_dot_async(s.ctx, (int64_t)B.ni * B.ni, s.Kinv, B.eta2);
 }
 
-// Reuse of the last K update's inverse.  optim() starts every M-step from tau' = -D01 / log(K_i[1,2] / K_i[1,1]) read back from the K
-// the previous M-step assembled with its winner tau (R/SREfit.R:596-614): tau' is tau up to the rounding of exp, the division and log,
-// a few tens of ulps.  exp(-D/tau')^-1 and its log-determinant then agree with the saved exp(-D/tau)^-1 to ~1e-14 relative -- two
-// orders below the rounding error of a factorisation of these matrices (condition 1e3 - 1e6) -- so the saved inverse is copied
-// instead of factorising again: one of the two r_i^3 evaluations per resolution and M-step at convergence (25 of ~85 GFLOP per EM
-// iteration at C3).  The tolerance is relative to the tau that WAS factorised (kinv_tau0), so drift cannot accumulate over the
-// iterations.  FRK_NO_KINV_REUSE=1 switches it off (A/B timing; the parity tests run both ways).
-static bool f_tau_reusable(const Block &B, double tau) {
+// Reuse of inverses.  K_i(tau)^-1 = exp(-D_i/tau)^-1 and log|K_i(tau)| depend on tau alone, so an evaluation whose tau was
+// factorised before only needs the trace against the new E-step.  Two sources:
+//  (1) KinvBest, the inverse the last K update kept (for the winner tau).  optim() starts every M-step from
+//      tau' = -D01 / log(K_i[1,2] / K_i[1,1]) read back from that K (R/SREfit.R:596-614): tau' is tau up to the rounding of exp, the
+//      division and log -- a few tens of ulps, often exactly tau.
+//  (2) a small LRU memo of recent evaluations (Block::memo): once a resolution's tau has settled, the Nelder-Mead runs of
+//      consecutive M-steps ask for the same points bit for bit (start, start + 10 %, ...).
+// A hit needs |tau - tau0| <= 1e-13 tau0 with tau0 the tau that WAS factorised (so drift cannot accumulate): the reused inverse then
+// agrees with exp(-D/tau)^-1 to ~1e-13 relative or exactly, below the rounding error of a factorisation of these matrices (condition
+// 1e3 - 1e6).  At C3 this removes both r_i^3 evaluations of the 2916-block per M-step (50 of ~85 GFLOP per EM iteration).
+// FRK_NO_KINV_REUSE=1 switches it off (A/B timing).
+static bool kinv_reuse_on() {
     static const bool off = getenv("FRK_NO_KINV_REUSE") != nullptr;
-    return !off && B.ns == 0 && B.kinv_tau0 > 0.0 && std::fabs(tau - B.kinv_tau0) <= 1e-13 * B.kinv_tau0;
+    return !off;
 }
-// the slot's Kinv := the saved inverse (the caller has ordered this stream after the last write of KinvBest)
-static int f_tau_reuse_enqueue(const Block &B, NMSlot &s) {
-    FRK_CHECK_CUDA(cudaMemcpyAsync(s.Kinv, B.KinvBest, (size_t)B.ni * B.ni * sizeof(double), cudaMemcpyDeviceToDevice, s.ctx->stream));
-    s.tau0 = B.kinv_tau0; s.ld = B.kinv_ld; s.reused = true;
+static const double *f_tau_lookup(Block &B, double tau, double &tau0, double &ld) {
+    if (!kinv_reuse_on() || B.ns != 0) return nullptr;
+    auto near = [tau](double t0) { return t0 > 0.0 && std::fabs(tau - t0) <= 1e-13 * t0; };
+    if (near(B.kinv_tau0)) { tau0 = B.kinv_tau0; ld = B.kinv_ld; return B.KinvBest; }
+    for (auto &e : B.memo)
+        if (near(e.tau0)) { e.stamp = ++B.memo_clock; tau0 = e.tau0; ld = e.ld; return e.buf; }
+    return nullptr;
+}
+// the slot's Kinv := a saved inverse (the caller has ordered this stream after the last write of the source)
+static int f_tau_reuse_enqueue(const Block &B, NMSlot &s, const double *src, double tau0, double ld) {
+    FRK_CHECK_CUDA(cudaMemcpyAsync(s.Kinv, src, (size_t)B.ni * B.ni * sizeof(double), cudaMemcpyDeviceToDevice, s.ctx->stream));
+    s.tau0 = tau0; s.ld = ld; s.reused = true;
+    return 0;
+}
+// a freshly factorised, valid evaluation into the memo (least recently used entry); `stream` is the block's copy stream (slot 0):
+// every lane of the block has been drained, and the lanes wait for that stream before they overwrite their buffers
+static int memo_insert(Block &B, const NMSlot &s, cudaStream_t stream) {
+    if (!kinv_reuse_on() || B.ns != 0 || B.memo.empty() || s.reused || !s.valid) return 0;
+    Block::Memo *lru = &B.memo[0];
+    for (auto &e : B.memo) {
+        if (e.tau0 == s.tau0) return 0;
+        if (e.stamp < lru->stamp) lru = &e;
+    }
+    FRK_CHECK_CUDA(cudaMemcpyAsync(lru->buf, s.Kinv, (size_t)B.ni * B.ni * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    lru->tau0 = s.tau0; lru->ld = s.ld; lru->stamp = ++B.memo_clock;
     return 0;
 }
 
@@ -750,12 +781,13 @@ int prefetch_f_tau(frk_model *M) {
             NMSlot s;
             RC(nm_slot_setup(M, j, c, B, false, s));
             Model_PreSlot &pf = M->pre[j][c];
-            if (f_tau_reusable(B, tau)) {                           // the start value: the saved inverse serves (see f_tau_reusable)
+            double tau0 = 0.0, ld = 0.0;
+            if (const double *src = f_tau_lookup(B, tau, tau0, ld)) {  // factorised before: a copy serves (see f_tau_lookup)
                 if (!M->ev_lane) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&M->ev_lane, cudaEventDisableTiming));
-                FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));       // KinvBest is final once this stream has assembled K
+                FRK_CHECK_CUDA(cudaEventRecord(M->ev_lane, ctx->stream));       // the saved inverses are final once this stream has assembled K
                 FRK_CHECK_CUDA(cudaStreamWaitEvent(s.ctx->stream, M->ev_lane, 0));
-                RC(f_tau_reuse_enqueue(B, s));
-                pf.reused = true; pf.tau0 = s.tau0; pf.ld = s.ld;
+                RC(f_tau_reuse_enqueue(B, s, src, tau0, ld));
+                pf.reused = true; pf.tau0 = tau0; pf.ld = ld;
             } else {
                 RC(f_tau_factor_enqueue(B, s, tau));
                 pf.reused = false; pf.tau0 = tau;
@@ -844,14 +876,15 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
             if (c > 0) FRK_CHECK_CUDA(cudaStreamWaitEvent(s.ctx->stream, S.ev_copy, 0));
             s.used = true; s.pt = tau;
             Model_PreSlot &pf = M->pre[j][c];
+            double rt0 = 0.0, rld = 0.0;
             if (pf.on && pf.tau == tau && !one_stream && !M->spec_emulate) {
                 // this slot's buffers already hold K_i(tau)^-1 (or it is on its way): enqueued before the E-step.  Only the trace is left.
                 s.reused = pf.reused; s.tau0 = pf.tau0;
                 if (pf.reused) s.ld = pf.ld;
                 RC(frk_dot_async(s.ctx, (int64_t)S.B->ni * S.B->ni, s.Kinv, S.B->eta2));
                 M->nm_prefetch_hits += 1;
-            } else if (f_tau_reusable(*S.B, tau)) {                  // (this stream is ordered after every write of KinvBest: ev_copy / ev_lane)
-                RC(f_tau_reuse_enqueue(*S.B, s));
+            } else if (const double *src = f_tau_lookup(*S.B, tau, rt0, rld)) {   // (this stream is ordered after every write of the saved inverses: ev_copy / ev_lane)
+                RC(f_tau_reuse_enqueue(*S.B, s, src, rt0, rld));
                 RC(frk_dot_async(s.ctx, (int64_t)S.B->ni * S.B->ni, s.Kinv, S.B->eta2));
             } else {
                 RC(f_tau_enqueue(*S.B, s, tau));
@@ -887,6 +920,7 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
             const double t = s.ctx->h_pinned[FRK_PINNED_DOT];
             const double f = bad ? std::numeric_limits<double>::quiet_NaN() : -(0.5 * (-logdetKi) - S.omega / 2.0 * t);
             S.fl[s.k] = f; s.ld = logdetKi; s.valid = std::isfinite(f);
+            RC(memo_insert(*S.B, s, S.slot[0].ctx->stream));
         }
         return 0;
     };
@@ -1473,6 +1507,8 @@ static int set_blocks_impl(frk_model *M, int nres, const int *h_res, const doubl
         const size_t nn = (size_t)B.ni * B.ni;
         RC(dalloc(M, &B.d_ix, ix.size())); RC(dalloc(M, &B.D, nn)); RC(dalloc(M, &B.eta2, nn)); RC(dalloc(M, &B.Ki, nn));
         RC(dalloc(M, &B.Kinv, nn)); RC(dalloc(M, &B.work, nn)); RC(dalloc(M, &B.KinvBest, nn));
+        B.memo.resize(B.ni >= 1024 ? 3 : 12);                        // (3 x 68 MB at n_i = 2916; 12 x 0.8 MB at 324)
+        for (auto &e : B.memo) RC(dalloc(M, &e.buf, nn));
         FRK_CHECK_CUDA(cudaMemcpyAsync(B.d_ix, ix.data(), ix.size() * sizeof(int), cudaMemcpyHostToDevice, M->ctx->stream));
         FRK_CHECK_CUDA(cudaStreamSynchronize(M->ctx->stream));       // ix is a temporary
         if (h_D) {
