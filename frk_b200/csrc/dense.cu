@@ -209,9 +209,12 @@ __global__ void __launch_bounds__(GEMM_T, 2) dgemm_kernel(GemmArgs p) {
 
 template <bool A_KC, bool B_KC>
 static int launch_gemm_t(frk_ctx *ctx, const GemmArgs &a, bool al) {
-    // 64-row tiles when 128-row tiles would leave SMs idle (fewer CTAs than SMs): skinny panel updates, small matrices
+    // 64-row tiles when 128-row tiles would leave SMs idle or make a launch as long as its longest tile (fewer than 4 tiles per SM):
+    // skinny panel updates, small matrices, the doubling levels of frk_potri (stand-alone 1.40 -> 1.22 ms at n = 3276).  With one tile
+    // per SM as the limit (FRK_GEMM_SMALL_PER_SM=1) the EM iteration at C3 is 2.6 % slower now that the E-step's chain runs alone.
     const int64_t ctas128 = cdiv(a.M, 128) * cdiv(a.N, BN) * (int64_t)a.nbatch;
-    const bool small = ctas128 < ctx->sm_count;
+    static const int small_per_sm = getenv("FRK_GEMM_SMALL_PER_SM") ? std::max(atoi(getenv("FRK_GEMM_SMALL_PER_SM")), 1) : 4;
+    const bool small = ctas128 < (int64_t)small_per_sm * ctx->sm_count;
     const int bm = small ? 64 : 128;
     dim3 grid((unsigned)cdiv(a.M, bm), (unsigned)cdiv(a.N, BN), (unsigned)a.nbatch);
     const double fl = ctx->next_flops;

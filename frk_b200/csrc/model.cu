@@ -730,15 +730,16 @@ int nm_slot_setup(frk_model *M, int j, int c, Block &B, bool one_stream, NMSlot 
     return 0;
 }
 
-// Lanes of block j: the configured number.  Deeper speculation for the small resolutions (their factorisations are short
-// latency-bound chains) was measured: FRK_SMALL_LANES = 4 / 8 for blocks of <= 1024 functions make the converged iterations 4 % faster
-// (the whole Nelder-Mead run fits the first, prefetched, round) but the first ~10 iterations from .EM_initialise 3 - 6 % slower
-// (more evaluations compete with the E-step), so the default leaves them at the configured count.
+// Lanes of block j: the configured number for the large resolutions; four for blocks of <= 1024 functions, whose factorisations are
+// short latency-bound chains (0.3 ms a round at n_i = 324, and 5-7 rounds per M-step while their tau is still moving): deeper
+// speculation turns 5 rounds into 4.  Measured at C3 (5 + 20 iterations): 5.63 -> 5.41 ms per EM iteration; 8 lanes evaluate twice as
+// many points for one round less and are slower.  (While the large block's own factorisations still ran beside the E-step -- before
+// the memo of f_tau_lookup -- the extra evaluations cost more than they saved; FRK_SMALL_LANES overrides.)
 inline int block_lanes(const frk_model *M, const Block &B, bool one_stream) {
     if (one_stream) return 1;
     const int L = std::max(M->lanes, 1);
     if (M->spec_emulate || L == 1) return L;                        // (L = 1: the strictly sequential reference run of the tests)
-    static const int small_lanes = getenv("FRK_SMALL_LANES") ? std::min(std::max(atoi(getenv("FRK_SMALL_LANES")), 1), LCAP) : 0;
+    static const int small_lanes = getenv("FRK_SMALL_LANES") ? std::min(std::max(atoi(getenv("FRK_SMALL_LANES")), 1), LCAP) : 4;
     return B.ni <= 1024 ? std::max(small_lanes, L) : L;
 }
 
