@@ -79,6 +79,7 @@ struct frk_model {
     std::vector<double> taus, omegas;
     double nm_requests = 0, nm_rounds = 0, nm_evals = 0, nm_reevals = 0;   // Nelder-Mead statistics of the last M-step (distinct points asked, batches, points evaluated)
     double nm_prefetch_hits = 0;     // ... of which had their factorisation enqueued before the E-step (prefetch_f_tau)
+    double nm_reuse_hits = 0;        // ... of which were served by a saved inverse instead of a factorisation (f_tau_lookup)
     // Prefetch: K_i(tau)^-1 and log|K_i(tau)| depend on tau only.  The first two points the NEXT M-step's Nelder-Mead will ask for
     // (its start value and start + step) are known as soon as this M-step has assembled K, so their factorisations are enqueued on the
     // lanes right away and run beside the next E-step's factorisation of Q instead of after it.  pre[j][c]: (active, tau) of lane c of block j.
@@ -678,10 +679,7 @@ int f_tau_enqueue(const Block &B, NMSlot &s, double tau) {
 // agrees with exp(-D/tau)^-1 to ~1e-13 relative or exactly, below the rounding error of a factorisation of these matrices (condition
 // 1e3 - 1e6).  At C3 this removes both r_i^3 evaluations of the 2916-block per M-step (50 of ~85 GFLOP per EM iteration).
 // FRK_NO_KINV_REUSE=1 switches it off (A/B timing).
-static bool kinv_reuse_on() {
-    static const bool off = getenv("FRK_NO_KINV_REUSE") != nullptr;
-    return !off;
-}
+static bool kinv_reuse_on() { return getenv("FRK_NO_KINV_REUSE") == nullptr; }   // (read at every call: the tests switch it within a process)
 static const double *f_tau_lookup(Block &B, double tau, double &tau0, double &ld) {
     if (!kinv_reuse_on() || B.ns != 0) return nullptr;
     auto near = [tau](double t0) { return t0 > 0.0 && std::fabs(tau - t0) <= 1e-13 * t0; };
@@ -881,12 +879,13 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
             if (pf.on && pf.tau == tau && !one_stream && !M->spec_emulate) {
                 // this slot's buffers already hold K_i(tau)^-1 (or it is on its way): enqueued before the E-step.  Only the trace is left.
                 s.reused = pf.reused; s.tau0 = pf.tau0;
-                if (pf.reused) s.ld = pf.ld;
+                if (pf.reused) { s.ld = pf.ld; M->nm_reuse_hits += 1; }
                 RC(frk_dot_async(s.ctx, (int64_t)S.B->ni * S.B->ni, s.Kinv, S.B->eta2));
                 M->nm_prefetch_hits += 1;
             } else if (const double *src = f_tau_lookup(*S.B, tau, rt0, rld)) {   // (this stream is ordered after every write of the saved inverses: ev_copy / ev_lane)
                 RC(f_tau_reuse_enqueue(*S.B, s, src, rt0, rld));
                 RC(frk_dot_async(s.ctx, (int64_t)S.B->ni * S.B->ni, s.Kinv, S.B->eta2));
+                M->nm_reuse_hits += 1;
             } else {
                 RC(f_tau_enqueue(*S.B, s, tau));
             }
@@ -1103,7 +1102,7 @@ int update_K(frk_model *M, int K_type, int nlambda, const double *lambda, const 
     FRK_REQUIRE(!M->blocks.empty(), "K_type = \"block-exponential\" needs the per-resolution distance matrices (frk_model_set_blocks)");
     // K_new is assembled in w1 and K_new^-1 in w2 (both free here); the old Khat / Khat_inv are read for omega and the start values
     M->taus.clear(); M->omegas.clear();
-    M->nm_requests = M->nm_rounds = M->nm_evals = M->nm_reevals = M->nm_prefetch_hits = 0;
+    M->nm_requests = M->nm_rounds = M->nm_evals = M->nm_reevals = M->nm_prefetch_hits = M->nm_reuse_hits = 0;
     double *Knew = M->w1, *Kinvnew = M->w2;
     FRK_CHECK_CUDA(cudaMemsetAsync(Knew, 0, rr * sizeof(double), ctx->stream));
     FRK_CHECK_CUDA(cudaMemsetAsync(Kinvnew, 0, rr * sizeof(double), ctx->stream));
@@ -1659,6 +1658,7 @@ extern "C" int frk_model_get(frk_model *M, const char *slot, double *h_out) {
     if (!strcmp(slot, "tau")) { for (size_t i = 0; i < M->taus.size(); i++) h_out[i] = M->taus[i]; return 0; }
     if (!strcmp(slot, "nm_stats")) { h_out[0] = M->nm_requests; h_out[1] = M->nm_rounds; h_out[2] = M->nm_evals; h_out[3] = M->nm_reevals; return 0; }
     if (!strcmp(slot, "nm_prefetch_hits")) { h_out[0] = M->nm_prefetch_hits; return 0; }
+    if (!strcmp(slot, "nm_reuse_hits")) { h_out[0] = M->nm_reuse_hits; return 0; }
     if (!strcmp(slot, "omega")) { for (size_t i = 0; i < M->omegas.size(); i++) h_out[i] = M->omegas[i]; return 0; }
     size_t n = 0;
     double *p = slot_ptr(M, slot, &n);

@@ -83,7 +83,7 @@ class SREModel:
     def get(self, name: str) -> np.ndarray:
         """Host copy of a slot (what the R shim writes back into the S4 object); r x r slots as (r, r) arrays."""
         n = {"mu_eta": self.r, "alphahat": self.p, "sigma2fshat": 1, "m_total": 1, "homoscedastic": 1,
-             "tau": 16, "omega": 16, "nm_stats": 4, "nm_prefetch_hits": 1}.get(name, self.r * self.r)
+             "tau": 16, "omega": 16, "nm_stats": 4, "nm_prefetch_hits": 1, "nm_reuse_hits": 1}.get(name, self.r * self.r)
         big = name in ("S_eta", "Q_eta", "Khat", "Khat_inv")
         out = self.dev.host_buffer(n) if big else np.zeros(n)       # pinned staging for the r x r slots
         call("frk_model_get", self.handle, name.encode(), vp(out.ctypes.data))
@@ -421,6 +421,7 @@ def SRE_fit(mdl: SREModel, n_EM: int = 100, tol: float = 0.01, method: str = "EM
         mdl.info_fit["omega"] = mdl.get("omega")[:nres].tolist()
         mdl.info_fit["nm_stats"] = dict(zip(("requests", "rounds", "evaluated", "re_evaluated"), mdl.get("nm_stats").tolist()))   # last M-step
         mdl.info_fit["nm_stats"]["prefetched"] = float(mdl.get("nm_prefetch_hits")[0])    # evaluations whose factorisation ran beside the E-step
+        mdl.info_fit["nm_stats"]["reused"] = float(mdl.get("nm_reuse_hits")[0])           # evaluations served by a saved inverse (no factorisation)
     return mdl
 
 

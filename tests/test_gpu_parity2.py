@@ -535,3 +535,44 @@ def test_quadform_warp_specialised_kernel_long_rows_and_empty_rows(dev, monkeypa
     np.testing.assert_allclose(out["ws"][0], q_ref, rtol=1e-11, atol=1e-13 * scale)
     np.testing.assert_allclose(out["ws"][1], t_ref, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(out["ws"][0], out["v2"][0], rtol=1e-13, atol=1e-14 * scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_block_exponential_inverse_memo_changes_nothing(dev, lanes, monkeypatch):
+    """The memo of Nelder-Mead inverses (model.cu f_tau_lookup: exp(-D/tau)^-1 and its log-determinant are functions of tau alone; the
+    next M-step's start value is the previous winner read back from K, R/SREfit.R:596-614) against the literal evaluation of every
+    point (FRK_NO_KINV_REUSE=1, what the reference does): same number of Nelder-Mead requests, same tau / omega bit for bit or to
+    the last digits, same log-likelihood trace and predictions; and the oracle agrees with both.  The memo must actually be used."""
+    import frk_b200 as F
+    from test_gpu_parity import _setup_plane
+    dev.set_deterministic(True)                                 # (atomics' last-bit noise would hide what is compared here)
+    try:
+        fits = {}
+        for off in (True, False):
+            if off:
+                monkeypatch.setenv("FRK_NO_KINV_REUSE", "1")
+            else:
+                monkeypatch.delenv("FRK_NO_KINV_REUSE", raising=False)
+            Mo, Mg = _setup_plane(F, m=3000, seed=11, nres=3, K_type="block-exponential")
+            reused = 0.0
+            llk, taus, reqs = [], [], []
+            for _ in range(12):                                 # one iteration per call: the statistics are those of the last M-step
+                F.SRE_fit(Mg, n_EM=1, tol=0.0, lanes=lanes)
+                st = Mg.info_fit["nm_stats"]
+                reused += st["reused"]; reqs.append(st["requests"])
+                llk.append(float(Mg.info_fit["llk"][-1])); taus.append(list(Mg.info_fit["tau"]))
+            pr = F.predict(Mg, obs_fs=False)
+            fits[off] = dict(llk=np.array(llk), tau=np.array(taus), reqs=reqs, reused=reused, mu=pr["mu"], var=pr["var"], Mo=Mo)
+    finally:
+        dev.set_deterministic(False)
+    a, b = fits[True], fits[False]
+    assert a["reused"] == 0 and b["reused"] >= 10, (a["reused"], b["reused"])
+    assert a["reqs"] == b["reqs"]
+    np.testing.assert_allclose(b["tau"], a["tau"], rtol=1e-12)
+    np.testing.assert_allclose(b["llk"], a["llk"], rtol=1e-12)
+    close(b["mu"], a["mu"], 1e-11)
+    close(b["var"], a["var"], 1e-11)
+    Mo = b["Mo"]
+    O.SRE_fit(Mo, n_EM=12, tol=0.0)
+    np.testing.assert_allclose(b["llk"][-1], Mo.info_fit["llk"][-1], rtol=RTOL)
