@@ -53,17 +53,19 @@ def parse():
     ap.add_argument("--predict-reps", type=int, default=5)
     ap.add_argument("--deterministic", action="store_true", help="fixed-order Gram flush instead of fp64 atomics (bit-reproducible runs)")
     ap.add_argument("--distribute-nm", dest="distribute_nm", action="store_true", default=None,
-                    help="spread the Nelder-Mead candidates over the ranks (default when N > 1 with the library's NCCL communicator: "
-                         "measured 163 / 167 against 157 / 158 EM it/s replicated at N = 8 / 4, profiles/r02h_scale_modes.txt)")
+                    help="spread the Nelder-Mead candidates over the ranks (one lane per rank, one small all-reduce per round).  Was the "
+                         "default for N > 1 while every candidate was a factorisation (163 / 167 against 157 / 158 EM it/s replicated at "
+                         "N = 8 / 4, profiles/r02h_scale_modes.txt); with the memo of inverses the large block needs none and the "
+                         "small blocks' rounds are faster on four local lanes: 169.5 against 188.3 replicated at N = 2 (tools/n2_modes.sh)")
     ap.add_argument("--replicate-nm", dest="distribute_nm", action="store_false",
-                    help="every rank evaluates the Nelder-Mead candidates on its own lanes (no exchange)")
+                    help="every rank evaluates the Nelder-Mead candidates on its own lanes (no exchange): the default")
     ap.add_argument("--lanes", type=int, default=None, help="concurrent Nelder-Mead evaluation lanes per GPU (frk_model_set_lanes)")
     ap.add_argument("--comm", default="nccl", choices=["nccl", "hook"],
                     help="multi-GPU reductions: the library's own NCCL communicator (frk_comm_init) or the torch.distributed hook")
     ap.add_argument("--parity-tol", type=float, default=1e-9, help="relative tolerance of the in-run parity check against the oracle")
     args = ap.parse_args()
-    if args.distribute_nm is None:          # default: distributed candidates on several GPUs over the library's communicator
-        args.distribute_nm = int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.comm == "nccl"
+    if args.distribute_nm is None:          # default: replicated candidates (see --distribute-nm)
+        args.distribute_nm = False
     return args
 
 
