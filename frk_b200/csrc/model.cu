@@ -821,6 +821,14 @@ int blockexp_nelder_mead(frk_model *M, std::vector<std::unique_ptr<BlkNM>> &nmb,
         // keep the inverse of the best requested point while it is still in a slot (slots are drained before any replay; the next
         // round starts after this copy)
         if (!S.ev_copy) FRK_CHECK_CUDA(cudaEventCreateWithFlags(&S.ev_copy, cudaEventDisableTiming));
+        // a prefetched COPY of a saved inverse on another lane reads a buffer that this run's first replay may overwrite (on slot 0's
+        // stream): order slot 0's stream after it (the copy finished long ago; this only makes the order explicit)
+        if (!one_stream)
+            for (int c = 1; c < L; c++)
+                if (M->pre[j][c].on && M->pre[j][c].reused && S.slot[c].ctx != S.slot[0].ctx) {
+                    FRK_CHECK_CUDA(cudaEventRecord(S.ev_copy, S.slot[c].ctx->stream));
+                    FRK_CHECK_CUDA(cudaStreamWaitEvent(S.slot[0].ctx->stream, S.ev_copy, 0));
+                }
         BlkNM *Sp = &S;
         S.spec->requested = [Sp](const double *x, double f) -> int {
             if (!(f < Sp->bestF)) return 0;
