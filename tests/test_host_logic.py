@@ -185,3 +185,28 @@ def test_space_time_auto_basis_is_the_tensor_product_of_the_reference():
     assert Bw.Basis2.loc[-1, 0] == np.ceil((secs.max() - secs.min()) / (7 * 86400.0)) + 1
     with pytest.raises(ValueError, match="tunit should be"):
         F.auto_basis(F.STplane(), xy, tunit="fortnights", end_time=secs)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs first): one JSON line on stdout with the base contract's keys,
+    `impl = "reference"`, a `cpu_baseline` describing this very run and an `e2e` block repeating the value with zero
+    transfer bytes -- on a workload small enough for the CPU suite.  Needs no GPU and must not load the CUDA library's device path."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--n-obs", "3000", "--grid", "80",
+                          "--nres", "2", "--regular", "1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "stdout must carry exactly one JSON line"
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["unit"] == "EM iters/s" and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
