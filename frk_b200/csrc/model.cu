@@ -439,11 +439,56 @@ struct SpecNM {
         return -1;
     }
 
-    // points nmmin may request after `x`, under hypothetical outcomes for the unknown ones (breadth first, at most `want`)
+    // Points nmmin may request after `x` (at most `want` in all, `x` included), for the lanes that would otherwise idle.
+    // (1) One dimension, at least two known values: f_tau is a smooth function of tau, so the outcome of the next comparisons is
+    //     PREDICTED from a local interpolant (the quadratic through the three known points nearest to the new one; a line through
+    //     two) and nmmin is replayed along that predicted path: its next unknown points, in the order it would ask for them.
+    //     With four or more evaluators and only a line to go by, one place is kept for an alternative (scheme 2).
+    // (2) Otherwise, and for that alternative: hypothetical outcomes for the unknown points -- M = between the best and the second
+    //     best known value (inside the simplex whatever its other vertices are), L = better than everything, H = worse than
+    //     everything -- breadth first, the commonest outcome first (M, then L, then H: tools/spec_predictor_eval.py).
+    // A wrong guess costs lane time only: values are used by nmmin only for points it asks for itself (replay).
     void candidates(const double *x, size_t want, std::vector<std::vector<double>> &batch) const {
-        // outcomes for an unknown point: H = worse than everything known, M = between the best and the worst, L = better than everything.
-        // Breadth first, "worse" first: near convergence (tau starts at the previous optimum) new points are usually worse than the best.
-        std::vector<std::string> queue = {"H", "M", "L"};
+        auto in_batch = [&](const std::vector<double> &c) {
+            for (auto &b : batch) { bool eq = true; for (int d = 0; d < dim; d++) eq = eq && b[d] == c[d]; if (eq) return true; }
+            return false;
+        };
+        static const bool no_model = getenv("FRK_SPEC_NO_MODEL") != nullptr;       // A/B: hypotheses only
+        // ---- (1) the predicted path ----
+        if (dim == 1 && !no_model && want > batch.size()) {
+            std::vector<std::pair<double, double>> known;
+            for (size_t i = 0; i < pts.size(); i++) if (std::isfinite(fv[i])) known.emplace_back(pts[i][0], fv[i]);
+            if (known.size() >= 2) {
+                auto predict = [&](double y) {
+                    std::vector<std::pair<double, double>> k = known;
+                    std::sort(k.begin(), k.end(), [y](const std::pair<double, double> &a, const std::pair<double, double> &b) {
+                        return std::fabs(a.first - y) < std::fabs(b.first - y); });
+                    const double x0 = k[0].first, f0 = k[0].second, x1 = k[1].first, f1 = k[1].second;
+                    if (k.size() == 2) return f0 + (f1 - f0) * (y - x0) / (x1 - x0);
+                    const double x2 = k[2].first, f2 = k[2].second;
+                    return f0 * (y - x1) * (y - x2) / ((x0 - x1) * (x0 - x2)) + f1 * (y - x0) * (y - x2) / ((x1 - x0) * (x1 - x2)) +
+                           f2 * (y - x0) * (y - x1) / ((x2 - x0) * (x2 - x1));
+                };
+                const size_t keep = (want >= 4 && known.size() < 3) ? 1 : 0;   // places left for scheme (2) while the model is a line
+                std::vector<std::vector<double>> hp;
+                std::vector<double> hf;
+                auto sim = [&](const double *y, double &f) -> int {
+                    const int i = find(y);
+                    if (i >= 0) { f = fv[i]; return std::isnan(f) ? 99 : 0; }
+                    for (size_t j = 0; j < hp.size(); j++) if (hp[j][0] == y[0]) { f = hf[j]; return 0; }
+                    if (batch.size() + keep >= want && !in_batch(std::vector<double>(y, y + 1))) return 99;
+                    f = predict(y[0]);
+                    if (!std::isfinite(f)) return 99;
+                    hp.emplace_back(y, y + 1); hf.push_back(f);
+                    if (!in_batch(hp.back())) batch.push_back(hp.back());
+                    return 0;
+                };
+                NMResult tmp;
+                (void)nmmin(sim, par0, tmp, maxit, reltol);
+            }
+        }
+        // ---- (2) hypothetical outcomes ----
+        std::vector<std::string> queue = {"M", "L", "H"};
         for (size_t qi = 0; qi < queue.size() && batch.size() < want && qi < 400; qi++) {
             const std::string hyp = queue[qi];
             std::vector<std::vector<double>> hp;
@@ -459,12 +504,21 @@ struct SpecNM {
                     if (eq) { f = hf[j]; return 0; }
                 }
                 if (used < hyp.size()) {
-                    double lo = 0.0, hi = 0.0;
-                    bool any = false;
-                    auto upd = [&](double v) { if (std::isfinite(v)) { lo = any ? std::min(lo, v) : v; hi = any ? std::max(hi, v) : v; any = true; } };
+                    double lo = 0.0, lo2 = 0.0, hi = 0.0;                // best, second best, worst of everything known or assumed
+                    int n = 0;
+                    auto upd = [&](double v) {
+                        if (!std::isfinite(v)) return;
+                        if (n == 0) { lo = lo2 = hi = v; }
+                        else {
+                            if (v < lo) { lo2 = lo; lo = v; } else if (n == 1 || v < lo2) lo2 = v;
+                            hi = std::max(hi, v);
+                        }
+                        n++;
+                    };
                     for (double v : fv) upd(v);
                     for (double v : hf) upd(v);
-                    f = hyp[used] == 'L' ? lo - 1.0 - 1e-3 * std::fabs(lo) : hyp[used] == 'H' ? hi + 1.0 + 1e-3 * std::fabs(hi) : 0.5 * (lo + hi);
+                    if (n == 1) lo2 = hi = lo;
+                    f = hyp[used] == 'L' ? lo - 1.0 - 1e-3 * std::fabs(lo) : hyp[used] == 'H' ? hi + 1.0 + 1e-3 * std::fabs(hi) : 0.5 * (lo + lo2);
                     used++;
                     hp.emplace_back(y, y + dim); hf.push_back(f);
                     return 0;
@@ -475,12 +529,10 @@ struct SpecNM {
             NMResult tmp;
             const int rc = nmmin(sim, par0, tmp, maxit, reltol);
             if (rc == 99) {
-                bool dup = find(cand.data()) >= 0;
-                for (auto &b : batch) { bool eq = true; for (int d = 0; d < dim; d++) eq = eq && b[d] == cand[d]; dup = dup || eq; }
-                if (!dup) batch.push_back(cand);
-                queue.push_back(hyp + "H");
+                if (find(cand.data()) < 0 && !in_batch(cand)) batch.push_back(cand);
                 queue.push_back(hyp + "M");
                 queue.push_back(hyp + "L");
+                queue.push_back(hyp + "H");
             }
         }
         (void)x;
