@@ -438,7 +438,9 @@ int frk_model_em_fit(frk_model *mdl, int n_EM, double tol, int K_type, int nlamb
 int frk_model_loglik(frk_model *mdl, double *h_out);
 /* slot access: "mu_eta" (r), "S_eta", "Q_eta", "Khat", "Khat_inv" (r x r column-major), "alphahat" (p),
  * "sigma2fshat" (1); read-only: "m_total", "homoscedastic", "tau", "omega" (per resolution, last M-step),
- * "nm_stats" (4: Nelder-Mead points requested / evaluation rounds / points evaluated / re-evaluations, last M-step)  */
+ * "nm_stats" (4: Nelder-Mead points requested / evaluation rounds / points evaluated / re-evaluations, last M-step),
+ * "nm_prefetch_hits" (1: evaluations whose factorisation ran beside the E-step), "nm_reuse_hits" (1: evaluations served by a saved
+ * inverse -- exp(-D/tau)^-1 depends on tau alone -- instead of a factorisation)  */
 int frk_model_get(frk_model *mdl, const char *slot, double *h_out);
 int frk_model_set(frk_model *mdl, const char *slot, const double *h_in);
 int frk_model_slot_device(frk_model *mdl, const char *slot, double **d_out);
